@@ -1,0 +1,382 @@
+"""Generate the golden fixtures in this directory from the LIVE reference.
+
+Run in the build container only (the reference checkout does not exist on the
+GPU box):
+
+    python tests/golden/make_goldens.py [/root/reference]
+
+Everything is computed by the unmodified reference (beer-asr/beer @ d53d2a1)
+in float64; inputs, parameters and outputs are dumped to ``*.npz`` so that the
+oracle (``oracle/beer_oracle.py``) and the CUDA path can be checked against
+them without the reference being present.
+"""
+
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+REF = sys.argv[1] if len(sys.argv) > 1 else '/root/reference'
+sys.path.insert(0, REF)
+warnings.filterwarnings('ignore')
+import beer  # noqa: E402  (the reference)
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+torch.set_default_dtype(torch.float32)
+
+
+def npy(t):
+    return t.detach().cpu().numpy().copy()
+
+
+def ng_params(dist, prefix):
+    p = dist.params
+    return {prefix + 'mean': npy(p.mean), prefix + 'scale': npy(p.scale),
+            prefix + 'shape': npy(p.shape), prefix + 'rates': npy(p.rates)}
+
+
+def save(name, **arrays):
+    path = os.path.join(OUT, name + '.npz')
+    np.savez_compressed(path, **arrays)
+    print(f'{name}: {os.path.getsize(path) / 1024:.1f} KiB, {len(arrays)} arrays')
+
+
+def unit_graph(n_states, first_pdf, self_loop=0.75):
+    g = beer.graph.Graph()
+    sts = [g.add_state(pdf_id=None)]
+    for i in range(n_states):
+        sts.append(g.add_state(pdf_id=first_pdf + i))
+    sts.append(g.add_state(pdf_id=None))
+    g.start_state, g.end_state = sts[0], sts[-1]
+    g.add_arc(sts[0], sts[1], 1.0)
+    for a in range(1, n_states + 1):
+        g.add_arc(sts[a], sts[a], self_loop)
+        g.add_arc(sts[a], sts[a + 1], 1 - self_loop)
+    return g
+
+
+def phone_loop(n_units, n_states):
+    """mkphoneloopgraph.py:28-77 + mkdecodegraph.py:50-58 without the CLI."""
+    g = beer.graph.Graph()
+    g.start_state = g.add_state()
+    g.end_state = g.add_state()
+    pivot = g.add_state()
+    us = [g.add_state() for _ in range(n_units)]
+    g.add_arc(g.start_state, pivot)
+    g.add_arc(pivot, g.end_state)
+    for s in us:
+        g.add_arc(pivot, s)
+        g.add_arc(s, pivot)
+    g.normalize()
+    units, start_pdf, end_pdf = {}, {}, {}
+    for i, s in enumerate(us):
+        u = unit_graph(n_states, i * n_states)
+        units[f'u{i}'] = u
+        start_pdf[f'u{i}'] = i * n_states
+        end_pdf[f'u{i}'] = (i + 1) * n_states - 1
+        g.replace_state(s, u)
+    g.normalize()
+    return g, units, start_pdf, end_pdf
+
+
+def ali_graph(seq, units):
+    """mkaligraph.py:18-39."""
+    g = beer.graph.Graph()
+    g.start_state = g.add_state()
+    last = g.start_state
+    phone_states = []
+    for _ in seq:
+        s = g.add_state()
+        phone_states.append(s)
+        g.add_arc(last, s)
+        last = s
+    s = g.add_state()
+    g.add_arc(last, s)
+    g.end_state = s
+    for i, ph in enumerate(seq):
+        g.replace_state(phone_states[i], units[ph])
+    g.normalize()
+    return g.compile()
+
+
+def graph_arrays(cg, prefix='g_'):
+    return {prefix + 'init': npy(cg.init_log_probs), prefix + 'final': npy(cg.final_log_probs),
+            prefix + 'trans': npy(cg.trans_log_probs),
+            prefix + 'map': np.asarray(cg.pdf_id_mapping, dtype=np.int64)}
+
+
+def sample_from_graph(rng, cg, means, T, noise=1.0):
+    init = np.exp(npy(cg.init_log_probs).astype(np.float64)); init /= init.sum()
+    A = np.exp(npy(cg.trans_log_probs).astype(np.float64)); A /= A.sum(1, keepdims=True)
+    K = len(init)
+    s = [rng.choice(K, p=init)]
+    for _ in range(1, T):
+        s.append(rng.choice(K, p=A[s[-1]]))
+    pdf = np.asarray(cg.pdf_id_mapping)[np.asarray(s)]
+    return (means[pdf] + noise * rng.standard_normal((T, means.shape[1]))).astype(np.float32)
+
+
+# ---------------------------------------------------------------------------
+def gold_dists():
+    torch.manual_seed(0)
+    M, D = 6, 5
+    mean = torch.randn(M, D).double()
+    scale = (torch.rand(M, 1) * 3 + .5).double()
+    shape = (torch.rand(M, 1) * 4 + 1.).double()
+    rates = (torch.rand(M, D) * 2 + .3).double()
+    q = beer.dists.NormalGamma.from_std_parameters(mean, scale, shape, rates)
+    p = beer.dists.NormalGamma.from_std_parameters(
+        torch.zeros(M, D).double(), torch.ones(M, 1).double(),
+        torch.ones(M, 1).double() * 2, torch.ones(M, D).double())
+    eta = q.natural_parameters()
+    back = beer.dists.NormalGammaStdParams.from_natural_parameters(eta)
+    X = torch.randn(9, D).double()
+    lfn = q.conjugate()
+    stats = lfn.sufficient_statistics(X)
+    out = dict(ng_mean=npy(mean), ng_scale=npy(scale), ng_shape=npy(shape), ng_rates=npy(rates),
+               ng_nat=npy(eta), ng_ets=npy(q.expected_sufficient_statistics()),
+               ng_lognorm=npy(q.log_norm()), ng_kl=npy(beer.dists.kl_div(q, p)),
+               ng_back_mean=npy(back.mean), ng_back_scale=npy(back.scale),
+               ng_back_shape=npy(back.shape), ng_back_rates=npy(back.rates),
+               ngp_mean=npy(p.params.mean), ngp_scale=npy(p.params.scale),
+               ngp_shape=npy(p.params.shape), ngp_rates=npy(p.params.rates),
+               X=npy(X), stats=npy(stats),
+               llh=npy(lfn(q.expected_sufficient_statistics(), stats)))
+    K, C = 4, 3
+    conc = (torch.rand(K, C) * 5 + .2).double()
+    dq = beer.dists.Dirichlet.from_std_parameters(conc)
+    dp = beer.dists.Dirichlet.from_std_parameters(torch.ones(K, C).double() * 1.5)
+    deta = dq.natural_parameters()
+    dback = beer.dists.DirichletStdParams.from_natural_parameters(deta.clone())
+    cl = dq.conjugate()
+    data = torch.rand(7, C).double()
+    cs = beer.CategoricalSet(beer.ConjugateBayesianParameter(dp, dq))
+    eye_stats = cs.sufficient_statistics(torch.eye(C).double())
+    out.update(dir_conc=npy(conc), dir_nat=npy(deta), dir_ets=npy(dq.expected_sufficient_statistics()),
+               dir_lognorm=npy(dq.log_norm()), dir_kl=npy(beer.dists.kl_div(dq, dp)),
+               dir_back=npy(dback.concentrations), dirp_conc=npy(dp.params.concentrations),
+               cat_data=npy(data), cat_stats=npy(cl.sufficient_statistics(data)),
+               dir_logw=npy(cs.expected_log_likelihood(eye_stats).t()))
+    save('dists', **out)
+
+
+# ---------------------------------------------------------------------------
+def vb_loop(model, X, n_iter, **kw):
+    optim = beer.VBConjugateOptimizer(model.mean_field_factorization(), lrate=1.)
+    elbos = []
+    for _ in range(n_iter):
+        optim.init_step()
+        elbo = beer.evidence_lower_bound(model, X, datasize=len(X), **kw)
+        elbo.backward()
+        elbos.append(float(elbo))
+        optim.step()
+    return np.asarray(elbos)
+
+
+def gold_gmm_cfg1():
+    """8-component diagonal Mixture on 2-D points (BASELINE.json configs[0])."""
+    rng = np.random.default_rng(1)
+    ang = 2 * np.pi * np.arange(8) / 8
+    centers = 6 * np.stack([np.cos(ang), np.sin(ang)], 1)
+    X = np.concatenate([c + rng.standard_normal((40, 2)) for c in centers]).astype(np.float32)
+    rng.shuffle(X)
+    torch.manual_seed(1)
+    mean = torch.from_numpy(X.mean(0)).float()
+    cov = torch.from_numpy(np.cov(X.T)).float()
+    ns = beer.NormalSet.create(mean, cov, size=8, prior_strength=1., noise_std=1.,
+                               cov_type='diagonal')
+    gmm = beer.Mixture.create(ns).double()
+    Xt = torch.from_numpy(X).double()
+    par = gmm.modelset.means_precisions
+    w = gmm.categorical.weights
+    out = dict(X=X, **ng_params(par.prior, 'prior_'), **ng_params(par.posterior, 'post0_'),
+               dprior=npy(w.prior.params.concentrations), dpost0=npy(w.posterior.params.concentrations))
+    # first E-step, observable pieces
+    stats = gmm.sufficient_statistics(Xt)
+    exp_llh = gmm.expected_log_likelihood(stats)
+    out.update(exp_llh=npy(exp_llh), resps=npy(gmm.cache['resps']),
+               kl=float(gmm.kl_div_posterior_prior().sum()))
+    acc = gmm.accumulate(stats)
+    out.update(acc_normal=npy(acc[par]), acc_dirichlet=npy(acc[w]))
+    gmm.clear_cache()
+    # labelled path (mixture.py:84-87)
+    labels = torch.from_numpy(rng.integers(0, 8, len(X)))
+    out.update(labels=npy(labels), exp_llh_labels=npy(gmm.expected_log_likelihood(stats, labels=labels)))
+    gmm.clear_cache()
+    out['elbos'] = vb_loop(gmm, Xt, 6)
+    out.update(**ng_params(par.posterior, 'post6_'), dpost6=npy(w.posterior.params.concentrations))
+    save('gmm_cfg1', **out)
+
+
+# ---------------------------------------------------------------------------
+def hmm_case(name, n_units, n_states, D, T, seed, scale=1.0, n_iter=3, noise_std=1.0):
+    rng = np.random.default_rng(seed)
+    torch.manual_seed(seed)
+    g, units, start_pdf, end_pdf = phone_loop(n_units, n_states)
+    cg = g.compile()
+    K = cg.n_states
+    means = 2.0 * rng.standard_normal((K, D))
+    X = sample_from_graph(rng, cg, means, T)
+    ns = beer.NormalSet.create(torch.zeros(D), torch.ones(D), size=K, prior_strength=1.,
+                               noise_std=noise_std, cov_type='diagonal')
+    hmm = beer.HMM.create(cg, ns).double()
+    Xt = torch.from_numpy(X).double()
+    par = ns.means_precisions
+    out = dict(X=X, scale=np.float64(scale), **graph_arrays(hmm.graph),
+               **ng_params(par.prior, 'prior_'), **ng_params(par.posterior, 'post0_'))
+    stats = hmm.sufficient_statistics(Xt)
+    exp_llh = hmm.expected_log_likelihood(stats, inference_graph=hmm.graph, scale=scale)
+    out.update(pdf_llh=npy(hmm.modelset.original_modelset.expected_log_likelihood(stats)),
+               gamma=npy(hmm.cache['resps']), exp_llh=npy(exp_llh),
+               kl=float(hmm.kl_div_posterior_prior().sum()))
+    acc = hmm.accumulate(stats)
+    out.update(acc_normal=npy(acc[par]))
+    hmm.clear_cache()
+    elbo = beer.evidence_lower_bound(hmm, Xt, datasize=3 * T, inference_graph=hmm.graph, scale=scale)
+    out.update(elbo_datasize3T=float(elbo))
+    # Viterbi alignment + Viterbi E-step
+    pc = scale * hmm._pc_llhs(stats, hmm.graph)
+    out['viterbi_path'] = npy(hmm.graph.best_path(pc))
+    out['decode'] = npy(hmm.decode(Xt, scale=scale))
+    out['posteriors'] = npy(hmm.posteriors(Xt))
+    exp_llh_v = hmm.expected_log_likelihood(stats, inference_graph=hmm.graph, viterbi=True, scale=scale)
+    out['exp_llh_viterbi'] = npy(exp_llh_v)
+    out['acc_normal_viterbi'] = npy(hmm.accumulate(stats)[par])
+    hmm.clear_cache()
+    out['elbos'] = vb_loop(hmm, Xt, n_iter, inference_graph=hmm.graph, scale=scale)
+    out.update(**ng_params(par.posterior, f'post{n_iter}_'))
+    save(name, **out)
+
+
+# ---------------------------------------------------------------------------
+def gold_phoneloop_mixtureset():
+    """The CLI stack: PhoneLoop(JointModelSet([MixtureSet(NormalSet), ...])) with two
+    groups of different C, with (xi path) and without an alignment graph."""
+    seed, D, T = 7, 4, 50
+    rng = np.random.default_rng(seed)
+    torch.manual_seed(seed)
+    n_units, n_states = 4, 3
+    g, units, start_pdf, end_pdf = phone_loop(n_units, n_states)
+    cg = g.compile()
+    K = cg.n_states
+    C1, C2, K1 = 3, 2, 6            # group 1: pdfs 0..5 with 3 comps, group 2: pdfs 6..11 with 2 comps
+    ns1 = beer.NormalSet.create(torch.zeros(D), torch.ones(D), size=K1 * C1, prior_strength=1.,
+                                noise_std=1., cov_type='diagonal')
+    ns2 = beer.NormalSet.create(torch.zeros(D), torch.ones(D), size=(K - K1) * C2, prior_strength=1.,
+                                noise_std=1., cov_type='diagonal')
+    ms1 = beer.MixtureSet.create(K1, ns1, prior_strength=1.)
+    ms2 = beer.MixtureSet.create(K - K1, ns2, prior_strength=1.)
+    emissions = beer.JointModelSet([ms1, ms2])
+    pl = beer.PhoneLoop.create(cg, start_pdf, end_pdf, emissions, prior_strength=1.).double()
+    means = 2.0 * rng.standard_normal((K, D))
+    X1 = sample_from_graph(rng, cg, means, T)
+    X2 = sample_from_graph(rng, cg, means, T + 13)
+    seq = ['u2', 'u0', 'u2', 'u3']
+    ag = ali_graph(seq, units).double()
+    X3 = sample_from_graph(rng, ag, means, 40)
+    p1, p2 = ns1.means_precisions, ns2.means_precisions
+    w1, w2 = ms1.categoricalset.weights, ms2.categoricalset.weights
+    wu = pl.categorical.weights
+    out = dict(X1=X1, X2=X2, X3=X3, C1=np.int64(C1), C2=np.int64(C2), K1=np.int64(K1),
+               start_idxs=np.asarray(list(start_pdf.values())), end_idxs=np.asarray(list(end_pdf.values())),
+               **graph_arrays(pl.graph), **graph_arrays(ag, 'ali_'),
+               **ng_params(p1.prior, 'g1_prior_'), **ng_params(p1.posterior, 'g1_post0_'),
+               **ng_params(p2.prior, 'g2_prior_'), **ng_params(p2.posterior, 'g2_post0_'),
+               g1_dprior=npy(w1.prior.params.concentrations), g1_dpost0=npy(w1.posterior.params.concentrations),
+               g2_dprior=npy(w2.prior.params.concentrations), g2_dpost0=npy(w2.posterior.params.concentrations),
+               u_dprior=npy(wu.prior.params.concentrations), u_dpost0=npy(wu.posterior.params.concentrations))
+    # (1) decoding graph, xi path (inference_graph=None)
+    Xt = torch.from_numpy(X1).double()
+    stats = pl.sufficient_statistics(Xt)
+    exp_llh = pl.expected_log_likelihood(stats)
+    out.update(u1_exp_llh=npy(exp_llh), u1_gamma=npy(pl.cache['resps']),
+               u1_xi_sum=npy(pl.cache['trans_resps'].sum(dim=0)),
+               u1_pdf_llh=npy(pl.modelset.original_modelset.expected_log_likelihood(stats)),
+               kl=float(pl.kl_div_posterior_prior().sum()))
+    acc = pl.accumulate(stats)
+    out.update(u1_acc_g1=npy(acc[p1]), u1_acc_g2=npy(acc[p2]), u1_acc_d1=npy(acc[w1]),
+               u1_acc_d2=npy(acc[w2]), u1_acc_units=npy(acc[wu]))
+    pl.clear_cache()
+    # (2) alignment graph with repeated pdf ids
+    Xt3 = torch.from_numpy(X3).double()
+    stats3 = pl.sufficient_statistics(Xt3)
+    exp_llh3 = pl.expected_log_likelihood(stats3, inference_graph=ag, scale=0.7)
+    out.update(u3_exp_llh=npy(exp_llh3), u3_gamma=npy(pl.cache['resps']))
+    acc3 = pl.accumulate(stats3)
+    out.update(u3_acc_g1=npy(acc3[p1]), u3_acc_g2=npy(acc3[p2]), u3_acc_d1=npy(acc3[w1]),
+               u3_acc_d2=npy(acc3[w2]), u3_acc_units=npy(acc3[wu]))
+    pl.clear_cache()
+    # (3) the accumulate/update loop over two utterances (accumulate.py:37-59, update.py:37-62)
+    optim = beer.VBConjugateOptimizer(pl.conjugate_bayesian_parameters(keepgroups=True), lrate=1.)
+    N = len(X1) + len(X2)
+    elbos = []
+    for it in range(3):
+        optim.init_step()
+        elbo = beer.evidence_lower_bound(datasize=N)
+        for X in (X1, X2):
+            elbo += beer.evidence_lower_bound(pl, torch.from_numpy(X).double(), datasize=N)
+        elbo.backward()
+        elbos.append(float(elbo))
+        optim.step()
+        out[f'it{it + 1}_trans'] = npy(pl.graph.trans_log_probs)
+    out['elbos'] = np.asarray(elbos)
+    out.update(**ng_params(p1.posterior, 'g1_post3_'), **ng_params(p2.posterior, 'g2_post3_'),
+               g1_dpost3=npy(w1.posterior.params.concentrations), g2_dpost3=npy(w2.posterior.params.concentrations),
+               u_dpost3=npy(wu.posterior.params.concentrations))
+    save('phoneloop_mixtureset', **out)
+
+
+# ---------------------------------------------------------------------------
+def gold_dense_ergodic():
+    """Dense ergodic transitions as in tests/test_hmm.py:149-151, with exact
+    Viterbi ties and an unreachable state."""
+    rng = np.random.default_rng(11)
+    K, T = 7, 40
+    A = rng.random((K, K)); A /= A.sum(1, keepdims=True)
+    init = rng.random(K); init /= init.sum()
+    final = rng.random(K); final /= final.sum()
+    llhs = rng.standard_normal((T, K)) * 3
+    cg = beer.graph.CompiledGraph(torch.from_numpy(np.log(init)), torch.from_numpy(np.log(final)),
+                                  torch.from_numpy(np.log(A)), list(range(K)))
+    (g, xi), ll = cg.posteriors(torch.from_numpy(llhs), trans_posteriors=True)
+    out = dict(llhs=llhs, **graph_arrays(cg), gamma=npy(g), xi_sum=npy(xi.sum(dim=0)), lognorm_mean=float(ll),
+               path=npy(cg.best_path(torch.from_numpy(llhs))))
+    # ties + -inf: states 0,1 identical rows/cols and identical llhs; state 6 unreachable
+    A2 = A.copy(); A2[1] = A2[0]; A2[:, 1] = A2[:, 0]; A2[:, 6] = 0; A2 /= A2.sum(1, keepdims=True)
+    init2 = init.copy(); init2[1] = init2[0]; init2[6] = 0; init2 /= init2.sum()
+    llhs2 = llhs.copy(); llhs2[:, 1] = llhs2[:, 0]
+    with np.errstate(divide='ignore'):
+        cg2 = beer.graph.CompiledGraph(torch.from_numpy(np.log(init2)), torch.from_numpy(np.log(final)),
+                                       torch.from_numpy(np.log(A2)), list(range(K)))
+    g2, _ = cg2.posteriors(torch.from_numpy(llhs2))
+    out.update(llhs2=llhs2, **graph_arrays(cg2, 'g2_'), gamma2=npy(g2),
+               path2=npy(cg2.best_path(torch.from_numpy(llhs2))))
+    save('dense_ergodic', **out)
+
+
+def gold_graph_compile():
+    g, units, start_pdf, end_pdf = phone_loop(5, 3)
+    cg = g.compile()
+    ag = ali_graph(['u1', 'u4', 'u1'], units)
+    # the HMM.ipynb cell 5 graph
+    e = beer.graph.Graph()
+    s0 = e.add_state(); s4 = e.add_state(); e.start_state = s0; e.end_state = s4
+    s1 = e.add_state(pdf_id=0); s2 = e.add_state(pdf_id=1); s3 = e.add_state(pdf_id=2)
+    for a, b in [(s0, s1), (s1, s1), (s1, s2), (s2, s2), (s2, s3), (s3, s3), (s3, s1), (s1, s4), (s2, s4), (s3, s4)]:
+        e.add_arc(a, b)
+    e.normalize()
+    ec = e.compile()
+    save('graph_compile', **graph_arrays(cg, 'pl_'), **graph_arrays(ag, 'ali_'), **graph_arrays(ec, 'ex_'))
+
+
+if __name__ == '__main__':
+    gold_dists()
+    gold_gmm_cfg1()
+    hmm_case('hmm_small', n_units=3, n_states=4, D=5, T=60, seed=3, scale=1.0)
+    hmm_case('hmm_scaled', n_units=4, n_states=3, D=6, T=45, seed=4, scale=0.5)
+    hmm_case('hmm_cfg2_T200', n_units=25, n_states=4, D=40, T=200, seed=5, n_iter=2)
+    gold_phoneloop_mixtureset()
+    gold_dense_ergodic()
+    gold_graph_compile()
