@@ -1,0 +1,77 @@
+"""ctypes binding of libbeer_b200.so (the C ABI declared in include/beer_b200.h).
+
+There is no CPU fallback: if the library is missing or a call fails, an exception
+is raised.  Loading the library itself needs no GPU (the symbol table can be
+inspected on a CPU-only machine); calling any kernel entry point does.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIBPATH = os.path.join(_HERE, 'lib', 'libbeer_b200.so')
+
+c_f32p = C.c_void_p   # device pointers travel as integers
+c_ptr = C.c_void_p
+
+# name -> (restype, argtypes); mirrors include/beer_b200.h one to one
+SIGNATURES = {
+    'beer_b200_version': (C.c_int, []),
+    'beer_normalgamma_expected_stats': (C.c_int, [c_ptr] * 4 + [C.c_int, C.c_int, c_ptr, c_ptr]),
+    'beer_dirichlet_expected_logw': (C.c_int, [c_ptr, C.c_int, C.c_int, c_ptr, c_ptr]),
+    'beer_emission_prepare': (C.c_int, [c_ptr] * 5 + [C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
+    'beer_emission_llh': (C.c_int, [c_ptr, C.c_int64, C.c_int, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr,
+                                    C.c_int, c_ptr, C.c_int64, c_ptr, c_ptr, c_ptr]),
+    'beer_graph_plan_create': (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int,
+                                         C.POINTER(C.c_void_p)]),
+    'beer_graph_plan_destroy': (None, [c_ptr]),
+    'beer_graph_plan_info': (C.c_int, [c_ptr, c_ptr]),
+    'beer_hmm_workspace_bytes': (C.c_int64, [c_ptr, C.c_int64]),
+    'beer_hmm_forward_backward': (C.c_int, [c_ptr, c_ptr, C.c_int64, c_ptr, c_ptr, C.c_int, C.c_float,
+                                            c_ptr, c_ptr, C.c_int64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    'beer_hmm_viterbi': (C.c_int, [c_ptr, c_ptr, C.c_int64, c_ptr, C.c_int, C.c_float, c_ptr, c_ptr,
+                                   c_ptr]),
+    'beer_accumulate_stats': (C.c_int, [c_ptr, C.c_int64, C.c_int, c_ptr, C.c_int64, c_ptr, C.c_int64,
+                                        c_ptr, c_ptr, C.c_int, C.c_int, c_ptr, c_ptr]),
+    'beer_mixture_weight_stats': (C.c_int, [c_ptr, C.c_int, C.c_int, c_ptr, C.c_int, c_ptr, c_ptr]),
+    'beer_normalgamma_update': (C.c_int, [c_ptr] * 9 + [C.c_double, C.c_double, C.c_int, C.c_int, c_ptr]),
+    'beer_normalgamma_kl': (C.c_int, [c_ptr] * 8 + [C.c_int, C.c_int, c_ptr, c_ptr]),
+    'beer_dirichlet_update': (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_double, C.c_double, C.c_int, C.c_int,
+                                        c_ptr]),
+    'beer_dirichlet_kl': (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, c_ptr, c_ptr]),
+}
+
+_lib = None
+
+
+class BeerB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once) and attach the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIBPATH):
+        raise BeerB200Error(
+            f'{LIBPATH} is missing: build it with `python -m beer_b200.build` '
+            '(there is no CPU or PyTorch fallback for the VB E-step)')
+    lib = C.CDLL(LIBPATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError if the ABI and the binding diverge
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+_ENGINE_ERRORS = {-1: 'invalid argument', -2: 'shape not supported by the sm_100a kernels',
+                  -3: 'allocation failed'}
+
+
+def check(code, what):
+    if code == 0:
+        return
+    if code < 0:
+        raise BeerB200Error(f'{what}: {_ENGINE_ERRORS.get(code, code)}')
+    raise BeerB200Error(f'{what}: CUDA error {code}')

@@ -1,0 +1,315 @@
+// Conjugate exponential-family parameter math on the device: expected natural
+// statistics, emission weights, natural-gradient M-step and KL divergences.
+// All of it is O(M*D) per VB iteration (< 0.1 % of the E-step), so it is computed
+// in fp64 from the fp32 standard parameters and rounded once.
+//
+// Reference semantics: beer/dists/normalgamma.py, beer/dists/dirichlet.py,
+// beer/dists/basedist.py:243-263, beer/models/parameters.py:134-141.
+#include "common.cuh"
+#include "../../include/beer_b200.h"
+
+namespace beer {
+
+constexpr double kLog2Pi = 1.8378770664093453;
+
+// ---- Normal-Gamma ----------------------------------------------------------
+
+// One warp per Gaussian.  ets row = [lam*m (D), lam (D), D/k + sum lam m^2, sum psi(a) - ln b]
+__global__ void ng_expected_stats_kernel(const float* __restrict__ mean, const float* __restrict__ scale,
+                                         const float* __restrict__ shape, const float* __restrict__ rates,
+                                         int M, int D, float* __restrict__ ets) {
+    int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (j >= M) return;
+    double a = shape[j], k = scale[j];
+    double psi_a = digamma_d(a);
+    double pqm = 0.0, logdet = 0.0;
+    int Q = 2 * D + 2;
+    for (int d = lane; d < D; d += 32) {
+        double m = mean[(size_t)j * D + d], b = rates[(size_t)j * D + d];
+        double lam = a / b;
+        ets[(size_t)j * Q + d] = (float)(lam * m);
+        ets[(size_t)j * Q + D + d] = (float)lam;
+        pqm += lam * m * m;
+        logdet += psi_a - log(b);
+    }
+    pqm = warp_sum(pqm);
+    logdet = warp_sum(logdet);
+    if (lane == 0) {
+        ets[(size_t)j * Q + 2 * D] = (float)(pqm + D / k);
+        ets[(size_t)j * Q + 2 * D + 1] = (float)logdet;
+    }
+}
+
+// Per-Gaussian bias before centring (fp64), one warp per Gaussian.
+__device__ __forceinline__ double ng_bias_row(const float* mean, const float* scale, const float* shape,
+                                              const float* rates, const float* logw, int j, int D, int lane) {
+    double a = shape[j], k = scale[j];
+    double psi_a = digamma_d(a);
+    double acc = 0.0;
+    for (int d = lane; d < D; d += 32) {
+        double m = mean[(size_t)j * D + d], b = rates[(size_t)j * D + d];
+        acc += -0.5 * (a / b) * m * m + 0.5 * (psi_a - log(b));
+    }
+    acc = warp_sum(acc);
+    acc += -0.5 * D / k - 0.5 * D * kLog2Pi;
+    if (logw != nullptr) acc += (double)logw[j];
+    return acc;
+}
+
+// Single block: ref[d] = mean_j lam_jd, ref[D] = mean_j bias_j.
+__global__ void emission_ref_kernel(const float* __restrict__ mean, const float* __restrict__ scale,
+                                    const float* __restrict__ shape, const float* __restrict__ rates,
+                                    const float* __restrict__ logw, int M, int D, float* __restrict__ ref) {
+    __shared__ double s_bias[32];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        double acc = 0.0;
+        for (int j = 0; j < M; ++j) acc += (double)shape[j] / (double)rates[(size_t)j * D + d];
+        ref[d] = (float)(acc / M);
+    }
+    double b = 0.0;
+    for (int j = warp; j < M; j += nwarp) b += ng_bias_row(mean, scale, shape, rates, logw, j, D, lane);
+    if (lane == 0) s_bias[warp] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < nwarp; ++w) t += s_bias[w];
+        ref[D] = (float)(t / M);
+    }
+}
+
+__global__ void emission_weights_kernel(const float* __restrict__ mean, const float* __restrict__ scale,
+                                        const float* __restrict__ shape, const float* __restrict__ rates,
+                                        const float* __restrict__ logw, int M, int D,
+                                        const float* __restrict__ ref, float* __restrict__ W,
+                                        float* __restrict__ bias) {
+    int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (j >= M) return;
+    double a = shape[j];
+    for (int d = lane; d < D; d += 32) {
+        double m = mean[(size_t)j * D + d], b = rates[(size_t)j * D + d];
+        double lam = a / b;
+        W[(size_t)j * 2 * D + d] = (float)(lam * m);
+        W[(size_t)j * 2 * D + D + d] = (float)(lam - (double)ref[d]);
+    }
+    double br = ng_bias_row(mean, scale, shape, rates, logw, j, D, lane);
+    if (lane == 0) bias[j] = (float)(br - (double)ref[D]);
+}
+
+// eta <- eta + lr (eta0 + s*acc - eta) per Gaussian, then back to standard form.
+__global__ void ng_update_kernel(const float* __restrict__ pm, const float* __restrict__ pk,
+                                 const float* __restrict__ pa, const float* __restrict__ pb, float* mean,
+                                 float* scale, float* shape, float* rates, const double* __restrict__ acc,
+                                 double s, double lr, int M, int D) {
+    int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (j >= M) return;
+    int Q = 2 * D + 2;
+    const double* st = acc + (size_t)j * Q;
+    double k0 = pk[j], a0 = pa[j], k = scale[j], a = shape[j];
+    double e3 = -0.5 * k, e4 = a - 0.5;
+    e3 += lr * (-0.5 * k0 + s * st[2 * D] - e3);
+    e4 += lr * (a0 - 0.5 + s * st[2 * D + 1] - e4);
+    double kn = -2.0 * e3, an = e4 + 0.5;
+    for (int d = lane; d < D; d += 32) {
+        size_t i = (size_t)j * D + d;
+        double m0 = pm[i], b0 = pb[i], m = mean[i], b = rates[i];
+        double e1 = k * m, e2 = -0.5 * k * m * m - b;
+        e1 += lr * (k0 * m0 + s * st[d] - e1);
+        e2 += lr * (-0.5 * k0 * m0 * m0 - b0 + s * st[D + d] - e2);
+        double mn = e1 / kn;
+        mean[i] = (float)mn;
+        rates[i] = (float)(-e2 - 0.5 * kn * mn * mn);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        scale[j] = (float)kn;
+        shape[j] = (float)an;
+    }
+}
+
+// KL(q || p) = A(p) - A(q) - <E_q[T], eta_p - eta_q>, summed over Gaussians.
+__global__ void ng_kl_kernel(const float* __restrict__ pm, const float* __restrict__ pk,
+                             const float* __restrict__ pa, const float* __restrict__ pb,
+                             const float* __restrict__ mean, const float* __restrict__ scale,
+                             const float* __restrict__ shape, const float* __restrict__ rates, int M, int D,
+                             double* kl) {
+    int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    double val = 0.0;
+    if (j < M) {
+        double k0 = pk[j], a0 = pa[j], k = scale[j], a = shape[j];
+        double psi_a = digamma_d(a);
+        double sum_lnb = 0.0, sum_lnb0 = 0.0, pqm = 0.0, logdet = 0.0, dot = 0.0;
+        for (int d = lane; d < D; d += 32) {
+            size_t i = (size_t)j * D + d;
+            double m0 = pm[i], b0 = pb[i], m = mean[i], b = rates[i];
+            double lam = a / b;
+            sum_lnb += log(b);
+            sum_lnb0 += log(b0);
+            pqm += lam * m * m;
+            logdet += psi_a - log(b);
+            // E[T]_1 * (eta_p1 - eta_q1) + E[T]_2 * (eta_p2 - eta_q2)
+            dot += lam * m * (k0 * m0 - k * m) + lam * ((-0.5 * k0 * m0 * m0 - b0) - (-0.5 * k * m * m - b));
+        }
+        sum_lnb = warp_sum(sum_lnb);
+        sum_lnb0 = warp_sum(sum_lnb0);
+        pqm = warp_sum(pqm);
+        logdet = warp_sum(logdet);
+        dot = warp_sum(dot);
+        double Aq = D * lgamma(a) - a * sum_lnb - 0.5 * D * log(k);
+        double Ap = D * lgamma(a0) - a0 * sum_lnb0 - 0.5 * D * log(k0);
+        dot += (pqm + D / k) * (-0.5 * k0 + 0.5 * k) + logdet * (a0 - a);
+        val = Ap - Aq - dot;
+    }
+    // block reduction -> one atomic per block
+    __shared__ double s_val[32];
+    int warp = threadIdx.x >> 5;
+    if (lane == 0) s_val[warp] = val;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_val[w];
+        atomicAdd(kl, t);
+    }
+}
+
+// ---- Dirichlet -------------------------------------------------------------
+
+// One thread per row (K rows, C small).
+__global__ void dir_logw_kernel(const float* __restrict__ conc, int K, int C, float* __restrict__ logw) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    double tot = 0.0;
+    for (int c = 0; c < C; ++c) tot += conc[(size_t)k * C + c];
+    double psi_tot = digamma_d(tot);
+    for (int c = 0; c < C; ++c) logw[(size_t)k * C + c] = (float)(digamma_d((double)conc[(size_t)k * C + c]) - psi_tot);
+}
+
+__global__ void dir_update_kernel(const float* __restrict__ prior, float* conc, const double* __restrict__ acc,
+                                  double s, double lr, int K, int C) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const float* p = prior + (size_t)k * C;
+    float* q = conc + (size_t)k * C;
+    const double* st = acc + (size_t)k * C;
+    double sum_p = 0.0, sum_q = 0.0, sum_new = 0.0;
+    for (int c = 0; c < C; ++c) {
+        sum_p += (double)p[c] - 1.0;
+        sum_q += (double)q[c] - 1.0;
+    }
+    double e_last = sum_q + lr * (sum_p + s * st[C - 1] - sum_q);
+    for (int c = 0; c < C - 1; ++c) {
+        double e = (double)q[c] - 1.0;
+        e += lr * ((double)p[c] - 1.0 + s * st[c] - e);
+        sum_new += e;
+        q[c] = (float)(e + 1.0);
+    }
+    q[C - 1] = (float)(e_last - sum_new + 1.0);
+}
+
+__global__ void dir_kl_kernel(const float* __restrict__ prior, const float* __restrict__ conc, int K, int C,
+                              double* kl) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    double val = 0.0;
+    if (k < K) {
+        const float* p = prior + (size_t)k * C;
+        const float* q = conc + (size_t)k * C;
+        double sp = 0.0, sq = 0.0, Ap = 0.0, Aq = 0.0;
+        for (int c = 0; c < C; ++c) {
+            sp += p[c];
+            sq += q[c];
+            Ap += lgamma((double)p[c]);
+            Aq += lgamma((double)q[c]);
+        }
+        Ap -= lgamma(sp);
+        Aq -= lgamma(sq);
+        double psi_last = digamma_d((double)q[C - 1]), psi_tot = digamma_d(sq);
+        double dot = 0.0;
+        for (int c = 0; c < C - 1; ++c)
+            dot += (digamma_d((double)q[c]) - psi_last) * ((double)p[c] - (double)q[c]);
+        dot += (psi_last - psi_tot) * ((sp - C) - (sq - C));
+        val = Ap - Aq - dot;
+    }
+    val = warp_sum(val);
+    if ((threadIdx.x & 31) == 0 && val != 0.0) atomicAdd(kl, val);
+}
+
+}  // namespace beer
+
+using namespace beer;
+
+extern "C" {
+
+int beer_b200_version(void) { return 100; }
+
+int beer_normalgamma_expected_stats(const float* mean, const float* scale, const float* shape,
+                                    const float* rates, int M, int D, float* ets, void* stream) {
+    if (M <= 0 || D <= 0) return BEER_ERR_ARG;
+    int threads = 128, blocks = (M * 32 + threads - 1) / threads;
+    ng_expected_stats_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(mean, scale, shape, rates, M, D, ets);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
+int beer_dirichlet_expected_logw(const float* conc, int K, int C, float* logw, void* stream) {
+    if (K <= 0 || C <= 0) return BEER_ERR_ARG;
+    dir_logw_kernel<<<(K + 127) / 128, 128, 0, (cudaStream_t)stream>>>(conc, K, C, logw);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
+int beer_emission_prepare(const float* mean, const float* scale, const float* shape, const float* rates,
+                          const float* logw, int M, int D, float* W, float* bias, float* ref, void* stream) {
+    if (M <= 0 || D <= 0) return BEER_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    emission_ref_kernel<<<1, 1024, 0, st>>>(mean, scale, shape, rates, logw, M, D, ref);
+    BEER_LAUNCH_CHECK();
+    int threads = 128, blocks = (M * 32 + threads - 1) / threads;
+    emission_weights_kernel<<<blocks, threads, 0, st>>>(mean, scale, shape, rates, logw, M, D, ref, W, bias);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
+int beer_normalgamma_update(const float* prior_mean, const float* prior_scale, const float* prior_shape,
+                            const float* prior_rates, float* mean, float* scale, float* shape, float* rates,
+                            const double* acc, double stats_scale, double lrate, int M, int D, void* stream) {
+    if (M <= 0 || D <= 0) return BEER_ERR_ARG;
+    int threads = 128, blocks = (M * 32 + threads - 1) / threads;
+    ng_update_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(prior_mean, prior_scale, prior_shape,
+                                                                   prior_rates, mean, scale, shape, rates, acc,
+                                                                   stats_scale, lrate, M, D);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
+int beer_normalgamma_kl(const float* prior_mean, const float* prior_scale, const float* prior_shape,
+                        const float* prior_rates, const float* mean, const float* scale, const float* shape,
+                        const float* rates, int M, int D, double* kl, void* stream) {
+    if (M <= 0 || D <= 0) return BEER_ERR_ARG;
+    int threads = 128, blocks = (M * 32 + threads - 1) / threads;
+    ng_kl_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(prior_mean, prior_scale, prior_shape, prior_rates,
+                                                               mean, scale, shape, rates, M, D, kl);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
+int beer_dirichlet_update(const float* prior_conc, float* conc, const double* acc, double stats_scale,
+                          double lrate, int K, int C, void* stream) {
+    if (K <= 0 || C <= 0) return BEER_ERR_ARG;
+    dir_update_kernel<<<(K + 127) / 128, 128, 0, (cudaStream_t)stream>>>(prior_conc, conc, acc, stats_scale, lrate,
+                                                                         K, C);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
+int beer_dirichlet_kl(const float* prior_conc, const float* conc, int K, int C, double* kl, void* stream) {
+    if (K <= 0 || C <= 0) return BEER_ERR_ARG;
+    dir_kl_kernel<<<(K + 127) / 128, 128, 0, (cudaStream_t)stream>>>(prior_conc, conc, K, C, kl);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
+}  // extern "C"

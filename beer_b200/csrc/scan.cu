@@ -1,0 +1,899 @@
+// KB / KV -- HMM forward-backward and Viterbi over a compiled graph.
+//
+// One warp owns one utterance; lane l owns the S consecutive states
+// [l*S, (l+1)*S).  The recursion runs in the log2 domain, renormalised every
+// frame (max = 0) so that fp32 stays accurate over thousands of frames -- the
+// reference (beer/graph.py:270-287) never renormalises and loses ~1e-2 on the
+// posteriors in fp32.  Transitions are a sparse "lane-major ELL" list; rank-1
+// blocks (unit-end -> unit-start of a phone loop) go through junction nodes.
+//
+// Reference semantics: beer/graph.py:270-344, beer/models/hmm.py:79-100,
+// beer/models/modelset.py:140-154.
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <vector>
+
+#include "common.cuh"
+#include "../../include/beer_b200.h"
+
+namespace beer {
+
+struct ScanLists {
+    const int* st_cnt;   // [S]  arcs per state slot (max over lanes)
+    const int* st_off;   // [S]  first ELL row of the slot
+    const int* jn_cnt;   // [J]  ELL rows per junction
+    const int* jn_off;   // [J]
+    const int* src;      // ELL sources: row r, lane l at r*32 + l
+    const float* lw;     // ELL weights (log2 domain for fwd/bwd, natural log for Viterbi)
+    const float* start;  // [K] initial (fwd, Viterbi) or final (bwd) log-probabilities
+};
+
+}  // namespace beer
+
+struct beer_graph_plan {
+    int K = 0, Kp = 0, J = 0, S = 0;
+    int n_direct = 0, n_jin = 0, n_jout = 0, dense_nnz = 0;
+    int map_identity = 0;
+    beer::ScanLists fwd{}, bwd{}, vit{};
+    const int* map = nullptr;        // device [K]
+    const float* vit_final = nullptr;  // device [K] natural log
+    void* dev_blob = nullptr;
+};
+
+namespace beer {
+
+// ---------------------------------------------------------------------------
+// host side: plan construction
+// ---------------------------------------------------------------------------
+struct Arc { int src; double lw; };
+
+struct EllBuilder {
+    std::vector<int> src;
+    std::vector<float> lw;
+    int rows = 0;
+    // append `n` rows, return first row
+    int add_rows(int n) {
+        int r = rows;
+        rows += n;
+        src.resize((size_t)rows * 32, 0);
+        lw.resize((size_t)rows * 32, -INFINITY);
+        return r;
+    }
+    void set(int row, int lane, int s, float w) {
+        src[(size_t)row * 32 + lane] = s;
+        lw[(size_t)row * 32 + lane] = w;
+    }
+};
+
+struct HostLists {
+    std::vector<int> st_cnt, st_off, jn_cnt, jn_off;
+    EllBuilder ell;
+    std::vector<float> start;
+};
+
+// state_lists[k] = arcs feeding state k; junction_lists[n] = arcs feeding junction n.
+static void build_lists(int K, int S, const std::vector<std::vector<Arc>>& state_lists,
+                        const std::vector<std::vector<Arc>>& junction_lists, double unit, HostLists& out) {
+    out.st_cnt.assign(S, 0);
+    out.st_off.assign(S, 0);
+    for (int s = 0; s < S; ++s) {
+        int cnt = 0;
+        for (int lane = 0; lane < 32; ++lane) {
+            int k = lane * S + s;
+            if (k < K) cnt = std::max(cnt, (int)state_lists[k].size());
+        }
+        int row0 = out.ell.add_rows(cnt);
+        out.st_cnt[s] = cnt;
+        out.st_off[s] = row0;
+        for (int lane = 0; lane < 32; ++lane) {
+            int k = lane * S + s;
+            if (k >= K) continue;
+            for (size_t a = 0; a < state_lists[k].size(); ++a)
+                out.ell.set(row0 + (int)a, lane, state_lists[k][a].src, (float)(state_lists[k][a].lw * unit));
+        }
+    }
+    int J = (int)junction_lists.size();
+    out.jn_cnt.assign(std::max(J, 1), 0);
+    out.jn_off.assign(std::max(J, 1), 0);
+    for (int n = 0; n < J; ++n) {
+        int cnt = ((int)junction_lists[n].size() + 31) / 32;
+        int row0 = out.ell.add_rows(cnt);
+        out.jn_cnt[n] = cnt;
+        out.jn_off[n] = row0;
+        for (size_t m = 0; m < junction_lists[n].size(); ++m)
+            out.ell.set(row0 + (int)(m / 32), (int)(m % 32), junction_lists[n][m].src,
+                        (float)(junction_lists[n][m].lw * unit));
+    }
+}
+
+struct BlobWriter {
+    std::vector<char> bytes;
+    size_t add(const void* p, size_t n) {
+        size_t off = (bytes.size() + 15) & ~(size_t)15;
+        bytes.resize(off + std::max<size_t>(n, 4), 0);
+        if (n) memcpy(bytes.data() + off, p, n);
+        return off;
+    }
+};
+
+struct ListOffsets { size_t st_cnt, st_off, jn_cnt, jn_off, src, lw, start; };
+
+static ListOffsets write_lists(BlobWriter& w, const HostLists& h) {
+    ListOffsets o;
+    o.st_cnt = w.add(h.st_cnt.data(), h.st_cnt.size() * 4);
+    o.st_off = w.add(h.st_off.data(), h.st_off.size() * 4);
+    o.jn_cnt = w.add(h.jn_cnt.data(), h.jn_cnt.size() * 4);
+    o.jn_off = w.add(h.jn_off.data(), h.jn_off.size() * 4);
+    o.src = w.add(h.ell.src.data(), h.ell.src.size() * 4);
+    o.lw = w.add(h.ell.lw.data(), h.ell.lw.size() * 4);
+    o.start = w.add(h.start.data(), h.start.size() * 4);
+    return o;
+}
+
+static ScanLists bind_lists(const char* base, const ListOffsets& o) {
+    ScanLists l;
+    l.st_cnt = (const int*)(base + o.st_cnt);
+    l.st_off = (const int*)(base + o.st_off);
+    l.jn_cnt = (const int*)(base + o.jn_cnt);
+    l.jn_off = (const int*)(base + o.jn_off);
+    l.src = (const int*)(base + o.src);
+    l.lw = (const float*)(base + o.lw);
+    l.start = (const float*)(base + o.start);
+    return l;
+}
+
+// ---------------------------------------------------------------------------
+// device side
+// ---------------------------------------------------------------------------
+
+// log2-domain logsumexp of one ELL list as seen by this lane.
+__device__ __forceinline__ float lane_list_lse(const int* __restrict__ src, const float* __restrict__ lw,
+                                               int row0, int cnt, int lane, const float* buf) {
+    if (cnt == 1) {
+        int i = row0 * 32 + lane;
+        return buf[__ldg(src + i)] + __ldg(lw + i);
+    }
+    if (cnt == 2) {
+        int i = row0 * 32 + lane;
+        float a = buf[__ldg(src + i)] + __ldg(lw + i);
+        float b = buf[__ldg(src + i + 32)] + __ldg(lw + i + 32);
+        float mx = fmaxf(a, b), mn = fminf(a, b);
+        float d = (mn == kNegInf) ? kNegInf : mn - mx;
+        return mx + lg2(1.f + ex2(d));
+    }
+    float m = kNegInf;
+    for (int a = 0; a < cnt; ++a) {
+        int i = (row0 + a) * 32 + lane;
+        m = fmaxf(m, buf[__ldg(src + i)] + __ldg(lw + i));
+    }
+    float ms = (m == kNegInf) ? 0.f : m;
+    float s = 0.f;
+    for (int a = 0; a < cnt; ++a) {
+        int i = (row0 + a) * 32 + lane;
+        s += ex2(buf[__ldg(src + i)] + __ldg(lw + i) - ms);
+    }
+    return ms + lg2(s);
+}
+
+// Junction value: logsumexp over a list spread over the whole warp.
+__device__ __forceinline__ float warp_list_lse(const int* __restrict__ src, const float* __restrict__ lw,
+                                               int row0, int cnt, int lane, const float* buf) {
+    float m = kNegInf;
+    for (int a = 0; a < cnt; ++a) {
+        int i = (row0 + a) * 32 + lane;
+        m = fmaxf(m, buf[__ldg(src + i)] + __ldg(lw + i));
+    }
+    m = warp_max(m);
+    float ms = (m == kNegInf) ? 0.f : m;
+    float s = 0.f;
+    for (int a = 0; a < cnt; ++a) {
+        int i = (row0 + a) * 32 + lane;
+        s += ex2(buf[__ldg(src + i)] + __ldg(lw + i) - ms);
+    }
+    s = warp_sum(s);
+    return ms + lg2(s);
+}
+
+struct FbArgs {
+    ScanLists fwd, bwd;
+    int K, J, Kp;
+    const int* map;
+    int map_identity;
+    const float* pl;
+    int64_t ld;
+    const float* frame_ref;
+    const int64_t* utt_off;
+    int n_utts;
+    float scale;
+    float* la_ws;  // [N, Kw] normalised log2 alphas
+    int Kw;
+    float* state_post;
+    float* pdf_post;
+    int64_t ld_post;
+    float* frame_exp_llh;
+    double* utt_exp_llh;
+    double* utt_logz;
+    int vec;  // 16-byte row copies are legal
+};
+
+constexpr int FB_WARPS = 4;
+
+template <int S>
+struct FbCfg {
+    static constexpr int PF = (S <= 4) ? 6 : (S <= 8 ? 4 : 2);  // prefetch depth (rows)
+};
+
+// Issue the async copy of this lane's S values of one row into a ring slot.
+template <int S>
+__device__ __forceinline__ void prefetch_row(float* ring_slot, const float* row, int lane, int K, bool vec,
+                                             const int* __restrict__ map, bool identity) {
+    float* dst = ring_slot + lane * S;
+    if (vec) {
+        if constexpr (S % 4 == 0) {
+#pragma unroll
+            for (int v = 0; v < S / 4; ++v)
+                if (lane * S + 4 * v < K) cp_async16(dst + 4 * v, row + lane * S + 4 * v);
+        }
+    } else {
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            int k = lane * S + s;
+            if (k < K) cp_async4(dst + s, row + (identity ? k : __ldg(map + k)));
+        }
+    }
+}
+
+template <int S>
+__global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_kernel(FbArgs a) {
+    constexpr int PF = FbCfg<S>::PF;
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nbuf = (a.K + a.J + 3) & ~3;
+    const int per_warp = nbuf + 2 * PF * 32 * S;
+    float* buf = smem + (size_t)warp * per_warp;
+    float* ring_p = buf + nbuf;            // [PF][32*S]
+    float* ring_a = ring_p + PF * 32 * S;  // [PF][32*S]
+    const int K = a.K, J = a.J;
+    const bool vec = a.vec != 0, ident = a.map_identity != 0;
+    const float p_scale = a.scale * kLog2e;
+    const int gwarp = blockIdx.x * FB_WARPS + warp, nwarps = gridDim.x * FB_WARPS;
+
+    for (int u = gwarp; u < a.n_utts; u += nwarps) {
+        const int64_t t0 = a.utt_off[u];
+        const int T = (int)(a.utt_off[u + 1] - t0);
+        if (T <= 0) {
+            if (lane == 0) {
+                a.utt_exp_llh[u] = 0.0;
+                if (a.utt_logz) a.utt_logz[u] = 0.0;
+            }
+            continue;
+        }
+        const float* pl_u = a.pl + (size_t)t0 * a.ld;
+        float* la_u = a.la_ws + (size_t)t0 * a.Kw;
+        // identity-mapped vector copies of la rows use the same helper (map unused)
+        double logz2 = 0.0;
+
+        // ------------------------------ forward ------------------------------
+        for (int r = 0; r < PF; ++r) {
+            if (r < T) prefetch_row<S>(ring_p + r * 32 * S, pl_u + (size_t)r * a.ld, lane, K, vec, a.map, ident);
+            cp_async_commit();
+        }
+        float cur[S];
+        for (int t = 0; t < T; ++t) {
+            cp_async_wait<PF - 1>();
+            float p[S];
+            const float* slot = ring_p + (t % PF) * 32 * S + lane * S;
+#pragma unroll
+            for (int s = 0; s < S; ++s) p[s] = (lane * S + s < K) ? slot[s] * p_scale : kNegInf;
+            if (t + PF < T)
+                prefetch_row<S>(ring_p + (t % PF) * 32 * S, pl_u + (size_t)(t + PF) * a.ld, lane, K, vec, a.map,
+                                ident);
+            cp_async_commit();
+
+            if (t == 0) {
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    int k = lane * S + s;
+                    cur[s] = (k < K) ? p[s] + __ldg(a.fwd.start + k) : kNegInf;
+                }
+            } else {
+                for (int n = 0; n < J; ++n) {
+                    float v = warp_list_lse(a.fwd.src, a.fwd.lw, __ldg(a.fwd.jn_off + n), __ldg(a.fwd.jn_cnt + n),
+                                            lane, buf);
+                    if (lane == 0) buf[K + n] = v;
+                }
+                if (J > 0) __syncwarp();
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    int k = lane * S + s;
+                    float v = lane_list_lse(a.fwd.src, a.fwd.lw, __ldg(a.fwd.st_off + s), __ldg(a.fwd.st_cnt + s),
+                                            lane, buf);
+                    cur[s] = (k < K) ? p[s] + v : kNegInf;
+                }
+            }
+            float mx = cur[0];
+#pragma unroll
+            for (int s = 1; s < S; ++s) mx = fmaxf(mx, cur[s]);
+            mx = warp_max(mx);
+            const float mxs = (mx == kNegInf) ? 0.f : mx;
+            logz2 += (double)mxs;
+            __syncwarp();  // every lane has finished reading buf
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                cur[s] -= mxs;
+                if (lane * S + s < K) buf[lane * S + s] = cur[s];
+            }
+            __syncwarp();
+            // store normalised log-alphas
+            float* la_row = la_u + (size_t)t * a.Kw;
+            if constexpr (S % 4 == 0) {
+                if ((a.Kw & 3) == 0) {
+#pragma unroll
+                    for (int v = 0; v < S / 4; ++v)
+                        if (lane * S + 4 * v < K)
+                            *reinterpret_cast<float4*>(la_row + lane * S + 4 * v) =
+                                make_float4(cur[4 * v], cur[4 * v + 1], cur[4 * v + 2], cur[4 * v + 3]);
+                } else {
+#pragma unroll
+                    for (int s = 0; s < S; ++s)
+                        if (lane * S + s < K) la_row[lane * S + s] = cur[s];
+                }
+            } else {
+#pragma unroll
+                for (int s = 0; s < S; ++s)
+                    if (lane * S + s < K) la_row[lane * S + s] = cur[s];
+            }
+        }
+        cp_async_wait<0>();
+
+        // log evidence: sum_t normalisers + LSE_k(la_{T-1,k} + final_k)
+        if (a.utt_logz != nullptr) {
+            float m = kNegInf;
+            float v[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                int k = lane * S + s;
+                v[s] = (k < K) ? cur[s] + __ldg(a.bwd.start + k) : kNegInf;
+                m = fmaxf(m, v[s]);
+            }
+            m = warp_max(m);
+            float ms = (m == kNegInf) ? 0.f : m;
+            float sum = 0.f;
+#pragma unroll
+            for (int s = 0; s < S; ++s) sum += ex2(v[s] - ms);
+            sum = warp_sum(sum);
+            double z = (logz2 + (double)ms + (double)lg2(sum)) * (double)kLn2;
+            double rs = 0.0;
+            if (a.frame_ref != nullptr)
+                for (int t = lane; t < T; t += 32) rs += (double)a.frame_ref[t0 + t];
+            rs = warp_sum(rs);
+            if (lane == 0) a.utt_logz[u] = z + (double)a.scale * rs;
+        }
+
+        // ------------------------------ backward -----------------------------
+        // make this warp's la stores visible to its own async copies
+        __threadfence_block();
+        __syncwarp();
+        const bool la_vec = (S % 4 == 0) && ((a.Kw & 3) == 0);
+        for (int r = 0; r < PF; ++r) {
+            int t = T - 1 - r;
+            if (t >= 0) {
+                prefetch_row<S>(ring_p + r * 32 * S, pl_u + (size_t)t * a.ld, lane, K, vec, a.map, ident);
+                prefetch_row<S>(ring_a + r * 32 * S, la_u + (size_t)t * a.Kw, lane, K, la_vec, nullptr, true);
+            }
+            cp_async_commit();
+        }
+        float lb[S];
+        {
+            float m = kNegInf;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                int k = lane * S + s;
+                lb[s] = (k < K) ? __ldg(a.bwd.start + k) : kNegInf;
+                m = fmaxf(m, lb[s]);
+            }
+            m = warp_max(m);
+            float ms = (m == kNegInf) ? 0.f : m;
+#pragma unroll
+            for (int s = 0; s < S; ++s) lb[s] -= ms;
+        }
+        double ell = 0.0;  // this lane's share of sum_t sum_k p2_tk gamma_tk
+        for (int i = 0; i < T; ++i) {
+            const int t = T - 1 - i;
+            cp_async_wait<PF - 1>();
+            float p[S], la[S];
+            const float* sp = ring_p + (i % PF) * 32 * S + lane * S;
+            const float* sa = ring_a + (i % PF) * 32 * S + lane * S;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                bool ok = lane * S + s < K;
+                p[s] = ok ? sp[s] * p_scale : kNegInf;
+                la[s] = ok ? sa[s] : kNegInf;
+            }
+            if (t - PF >= 0) {
+                prefetch_row<S>(ring_p + (i % PF) * 32 * S, pl_u + (size_t)(t - PF) * a.ld, lane, K, vec, a.map,
+                                ident);
+                prefetch_row<S>(ring_a + (i % PF) * 32 * S, la_u + (size_t)(t - PF) * a.Kw, lane, K, la_vec,
+                                nullptr, true);
+            }
+            cp_async_commit();
+
+            // gamma_t
+            float v[S], m = kNegInf;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                v[s] = la[s] + lb[s];
+                m = fmaxf(m, v[s]);
+            }
+            m = warp_max(m);
+            const float ms = (m == kNegInf) ? 0.f : m;
+            float sum = 0.f;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                v[s] = ex2(v[s] - ms);
+                sum += v[s];
+            }
+            sum = warp_sum(sum);
+            const float inv = (sum > 0.f) ? 1.f / sum : 0.f;
+            float fe = 0.f;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                v[s] *= inv;
+                if (v[s] > 0.f) fe = fmaf(p[s], v[s], fe);
+            }
+            ell += (double)fe;
+            if (a.frame_exp_llh != nullptr) {
+                float f = warp_sum(fe);
+                if (lane == 0) {
+                    float r = (a.frame_ref != nullptr) ? a.scale * a.frame_ref[t0 + t] : 0.f;
+                    a.frame_exp_llh[t0 + t] = f * kLn2 + r;
+                }
+            }
+            if (a.state_post != nullptr) {
+                float* row = a.state_post + (size_t)(t0 + t) * K;
+#pragma unroll
+                for (int s = 0; s < S; ++s)
+                    if (lane * S + s < K) row[lane * S + s] = v[s];
+            }
+            if (a.pdf_post != nullptr) {
+                float* row = a.pdf_post + (size_t)(t0 + t) * a.ld_post;
+                if (ident) {
+                    if constexpr (S % 4 == 0) {
+                        if ((a.ld_post & 3) == 0 && (K & 3) == 0) {
+#pragma unroll
+                            for (int q = 0; q < S / 4; ++q)
+                                if (lane * S + 4 * q < K)
+                                    *reinterpret_cast<float4*>(row + lane * S + 4 * q) =
+                                        make_float4(a.scale * v[4 * q], a.scale * v[4 * q + 1],
+                                                    a.scale * v[4 * q + 2], a.scale * v[4 * q + 3]);
+                        } else {
+#pragma unroll
+                            for (int s = 0; s < S; ++s)
+                                if (lane * S + s < K) row[lane * S + s] = a.scale * v[s];
+                        }
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < S; ++s)
+                            if (lane * S + s < K) row[lane * S + s] = a.scale * v[s];
+                    }
+                } else {
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        int k = lane * S + s;
+                        if (k < K && v[s] != 0.f) atomicAdd(row + __ldg(a.map + k), a.scale * v[s]);
+                    }
+                }
+            }
+
+            if (t == 0) break;
+            // beta_{t-1}: delta_j = p_tj + lb_tj, then the transposed recursion
+            __syncwarp();
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+                if (lane * S + s < K) buf[lane * S + s] = p[s] + lb[s];
+            __syncwarp();
+            for (int n = 0; n < J; ++n) {
+                float vj = warp_list_lse(a.bwd.src, a.bwd.lw, __ldg(a.bwd.jn_off + n), __ldg(a.bwd.jn_cnt + n), lane,
+                                         buf);
+                if (lane == 0) buf[K + n] = vj;
+            }
+            if (J > 0) __syncwarp();
+            float mb = kNegInf;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                int k = lane * S + s;
+                float vb = lane_list_lse(a.bwd.src, a.bwd.lw, __ldg(a.bwd.st_off + s), __ldg(a.bwd.st_cnt + s), lane,
+                                         buf);
+                lb[s] = (k < K) ? vb : kNegInf;
+                mb = fmaxf(mb, lb[s]);
+            }
+            mb = warp_max(mb);
+            const float mbs = (mb == kNegInf) ? 0.f : mb;
+#pragma unroll
+            for (int s = 0; s < S; ++s) lb[s] -= mbs;
+        }
+        cp_async_wait<0>();
+        ell = warp_sum(ell);
+        double rs = 0.0;
+        if (a.frame_ref != nullptr)
+            for (int t = lane; t < T; t += 32) rs += (double)a.frame_ref[t0 + t];
+        rs = warp_sum(rs);
+        if (lane == 0) a.utt_exp_llh[u] = ell * (double)kLn2 + (double)a.scale * rs;
+        __syncwarp();
+    }
+}
+
+// ------------------------------- Viterbi -----------------------------------
+struct VitArgs {
+    ScanLists vit;
+    const float* vit_final;
+    int K;
+    const int* map;
+    int map_identity;
+    const float* pl;
+    int64_t ld;
+    const int64_t* utt_off;
+    int n_utts;
+    float scale;
+    uint16_t* bt;  // [N, K]
+    int32_t* path;
+};
+
+template <int S>
+__global__ void __launch_bounds__(FB_WARPS * 32) hmm_viterbi_kernel(VitArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int K = a.K;
+    const int nbuf = (K + 3) & ~3;
+    float* buf = smem + (size_t)warp * nbuf;
+    const int gwarp = blockIdx.x * FB_WARPS + warp, nwarps = gridDim.x * FB_WARPS;
+    const bool ident = a.map_identity != 0;
+
+    for (int u = gwarp; u < a.n_utts; u += nwarps) {
+        const int64_t t0 = a.utt_off[u];
+        const int T = (int)(a.utt_off[u + 1] - t0);
+        if (T <= 0) continue;
+        float om[S];
+        for (int t = 0; t < T; ++t) {
+            const float* row = a.pl + (size_t)(t0 + t) * a.ld;
+            float p[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                int k = lane * S + s;
+                p[s] = (k < K) ? a.scale * __ldg(row + (ident ? k : __ldg(a.map + k))) : kNegInf;
+            }
+            if (t == 0) {
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    int k = lane * S + s;
+                    om[s] = (k < K) ? p[s] + __ldg(a.vit.start + k) : kNegInf;
+                }
+            } else {
+                uint16_t* bt_row = a.bt + (size_t)(t0 + t) * K;
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    int k = lane * S + s;
+                    const int row0 = __ldg(a.vit.st_off + s), cnt = __ldg(a.vit.st_cnt + s);
+                    float best = kNegInf;
+                    int arg = 0;
+                    for (int q = 0; q < cnt; ++q) {
+                        int i = (row0 + q) * 32 + lane;
+                        int sidx = __ldg(a.vit.src + i);
+                        float v = buf[sidx] + __ldg(a.vit.lw + i);
+                        if (v > best) { best = v; arg = sidx; }
+                    }
+                    if (k < K) {
+                        om[s] = p[s] + best;
+                        bt_row[k] = (uint16_t)arg;
+                    } else {
+                        om[s] = kNegInf;
+                    }
+                }
+            }
+            float mx = om[0];
+#pragma unroll
+            for (int s = 1; s < S; ++s) mx = fmaxf(mx, om[s]);
+            mx = warp_max(mx);
+            const float mxs = (mx == kNegInf) ? 0.f : mx;
+            __syncwarp();
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                om[s] -= mxs;
+                if (lane * S + s < K) buf[lane * S + s] = om[s];
+            }
+            __syncwarp();
+        }
+        // last state: first maximal index of omega + final
+        float best = kNegInf;
+        int arg = 0x7fffffff;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            int k = lane * S + s;
+            if (k < K) {
+                float v = om[s] + __ldg(a.vit_final + k);
+                if (arg == 0x7fffffff || v > best) { best = v; arg = k; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+        }
+        // torch.argmax of an all -inf row is 0; states of higher lanes never win ties
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) {
+            int k = arg;
+            a.path[t0 + T - 1] = k;
+            for (int t = T - 1; t >= 1; --t) {
+                k = a.bt[(size_t)(t0 + t) * K + k];
+                a.path[t0 + t - 1] = k;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <int S>
+static int launch_fb(const FbArgs& a, int n_utts, cudaStream_t st) {
+    constexpr int PF = FbCfg<S>::PF;
+    int nbuf = (a.K + a.J + 3) & ~3;
+    size_t smem = sizeof(float) * (size_t)FB_WARPS * (nbuf + 2 * PF * 32 * S);
+    if (smem > 200 * 1024) return BEER_ERR_UNSUPPORTED;
+    static bool attr_set = false;
+    if (!attr_set) {
+        BEER_CUDA_TRY(cudaFuncSetAttribute(hmm_fb_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    int blocks = (n_utts + FB_WARPS - 1) / FB_WARPS;
+    int max_blocks = kNumSMs * 16;
+    if (blocks > max_blocks) blocks = max_blocks;
+    hmm_fb_kernel<S><<<blocks, FB_WARPS * 32, smem, st>>>(a);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
+template <int S>
+static int launch_vit(const VitArgs& a, int n_utts, cudaStream_t st) {
+    int nbuf = (a.K + 3) & ~3;
+    size_t smem = sizeof(float) * (size_t)FB_WARPS * nbuf;
+    int blocks = (n_utts + FB_WARPS - 1) / FB_WARPS;
+    int max_blocks = kNumSMs * 16;
+    if (blocks > max_blocks) blocks = max_blocks;
+    hmm_viterbi_kernel<S><<<blocks, FB_WARPS * 32, smem, st>>>(a);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
+static int pick_S(int K) {
+    int S = 1;
+    while (S * 32 < K) S *= 2;
+    return S;
+}
+
+}  // namespace beer
+
+using namespace beer;
+
+extern "C" {
+
+int beer_graph_plan_create(const float* init_log, const float* final_log, const float* trans_log,
+                           const int32_t* pdf_map, int K, int Kp, int factorize, beer_graph_plan** plan_out) {
+    if (!init_log || !final_log || !trans_log || !pdf_map || !plan_out || K <= 0 || Kp <= 0) return BEER_ERR_ARG;
+    if (K > 1024) return BEER_ERR_UNSUPPORTED;
+    for (int k = 0; k < K; ++k)
+        if (pdf_map[k] < 0 || pdf_map[k] >= Kp) return BEER_ERR_ARG;
+    const int S = pick_S(K);
+
+    // dense -> sparse rows
+    std::vector<std::vector<Arc>> out_arcs(K);  // out_arcs[i] = (j, lw)
+    int nnz = 0;
+    for (int i = 0; i < K; ++i)
+        for (int j = 0; j < K; ++j) {
+            float w = trans_log[(size_t)i * K + j];
+            if (w > -INFINITY && w == w) {
+                out_arcs[i].push_back({j, (double)w});
+                ++nnz;
+            }
+        }
+
+    // rank-1 block detection
+    struct Junction { std::vector<int> rows; std::vector<double> lv; std::vector<int> cols; std::vector<double> lw; };
+    std::vector<Junction> junctions;
+    std::vector<char> row_factored(K, 0);
+    if (factorize) {
+        std::map<std::vector<int>, std::vector<int>> groups;
+        for (int i = 0; i < K; ++i) {
+            std::vector<int> key;
+            for (const Arc& a : out_arcs[i])
+                if (a.src != i) key.push_back(a.src);
+            if (key.size() >= 2) groups[key].push_back(i);
+        }
+        for (auto& kv : groups) {
+            const std::vector<int>& cols = kv.first;
+            const std::vector<int>& rows = kv.second;
+            if (rows.size() < 2) continue;
+            auto row_vals = [&](int i) {
+                std::vector<double> v;
+                for (const Arc& a : out_arcs[i])
+                    if (a.src != i) v.push_back(a.lw);
+                return v;
+            };
+            std::vector<double> base = row_vals(rows[0]);
+            double mx = base[0];
+            for (double b : base) mx = std::max(mx, b);
+            double se = 0.0;
+            for (double b : base) se += exp(b - mx);
+            double lse = mx + log(se);
+            Junction jn;
+            jn.cols = cols;
+            for (double b : base) jn.lw.push_back(b - lse);
+            for (int i : rows) {
+                std::vector<double> v = row_vals(i);
+                double mean = 0.0;
+                for (size_t c = 0; c < v.size(); ++c) mean += v[c] - jn.lw[c];
+                mean /= (double)v.size();
+                double dev = 0.0;
+                for (size_t c = 0; c < v.size(); ++c) dev = std::max(dev, fabs(v[c] - jn.lw[c] - mean));
+                if (dev <= 4e-6) {
+                    jn.rows.push_back(i);
+                    jn.lv.push_back(mean);
+                }
+            }
+            if (jn.rows.size() >= 2 && jn.rows.size() * cols.size() > jn.rows.size() + cols.size()) {
+                for (int i : jn.rows) row_factored[i] = 1;
+                junctions.push_back(std::move(jn));
+            }
+        }
+    }
+    const int J = (int)junctions.size();
+    if (K + J > 8192) return BEER_ERR_UNSUPPORTED;
+
+    // forward / backward / Viterbi lists
+    std::vector<std::vector<Arc>> f_state(K), b_state(K), v_state(K), f_jn(J), b_jn(J);
+    int n_direct = 0, n_jin = 0, n_jout = 0;
+    for (int i = 0; i < K; ++i)
+        for (const Arc& a : out_arcs[i]) {
+            v_state[a.src].push_back({i, a.lw});
+            if (row_factored[i] && a.src != i) continue;
+            f_state[a.src].push_back({i, a.lw});
+            b_state[i].push_back({a.src, a.lw});
+            ++n_direct;
+        }
+    for (int n = 0; n < J; ++n) {
+        const Junction& jn = junctions[n];
+        for (size_t r = 0; r < jn.rows.size(); ++r) {
+            f_jn[n].push_back({jn.rows[r], jn.lv[r]});
+            b_state[jn.rows[r]].push_back({K + n, jn.lv[r]});
+            ++n_jin;
+        }
+        for (size_t c = 0; c < jn.cols.size(); ++c) {
+            f_state[jn.cols[c]].push_back({K + n, jn.lw[c]});
+            b_jn[n].push_back({jn.cols[c], jn.lw[c]});
+            ++n_jout;
+        }
+    }
+    auto by_src = [](const Arc& x, const Arc& y) { return x.src < y.src; };
+    for (int k = 0; k < K; ++k) {
+        std::sort(f_state[k].begin(), f_state[k].end(), by_src);
+        std::sort(b_state[k].begin(), b_state[k].end(), by_src);
+        std::sort(v_state[k].begin(), v_state[k].end(), by_src);
+    }
+
+    const double L2E = 1.4426950408889634;
+    HostLists hf, hb, hv;
+    build_lists(K, S, f_state, f_jn, L2E, hf);
+    build_lists(K, S, b_state, b_jn, L2E, hb);
+    build_lists(K, S, v_state, {}, 1.0, hv);
+    hf.start.resize(K);
+    hb.start.resize(K);
+    hv.start.resize(K);
+    std::vector<float> vfinal(K);
+    for (int k = 0; k < K; ++k) {
+        hf.start[k] = (float)((double)init_log[k] * L2E);
+        hb.start[k] = (float)((double)final_log[k] * L2E);
+        hv.start[k] = init_log[k];
+        vfinal[k] = final_log[k];
+    }
+
+    BlobWriter w;
+    ListOffsets of = write_lists(w, hf), ob = write_lists(w, hb), ov = write_lists(w, hv);
+    size_t o_map = w.add(pdf_map, (size_t)K * 4);
+    size_t o_vfinal = w.add(vfinal.data(), (size_t)K * 4);
+
+    beer_graph_plan* p = new (std::nothrow) beer_graph_plan();
+    if (!p) return BEER_ERR_ALLOC;
+    cudaError_t e = cudaMalloc(&p->dev_blob, w.bytes.size());
+    if (e != cudaSuccess) { delete p; return (int)e; }
+    e = cudaMemcpy(p->dev_blob, w.bytes.data(), w.bytes.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(p->dev_blob); delete p; return (int)e; }
+    const char* base = (const char*)p->dev_blob;
+    p->K = K; p->Kp = Kp; p->J = J; p->S = S;
+    p->n_direct = n_direct; p->n_jin = n_jin; p->n_jout = n_jout; p->dense_nnz = nnz;
+    p->fwd = bind_lists(base, of);
+    p->bwd = bind_lists(base, ob);
+    p->vit = bind_lists(base, ov);
+    p->map = (const int*)(base + o_map);
+    p->vit_final = (const float*)(base + o_vfinal);
+    p->map_identity = 1;
+    for (int k = 0; k < K; ++k)
+        if (pdf_map[k] != k) p->map_identity = 0;
+    *plan_out = p;
+    return BEER_OK;
+}
+
+void beer_graph_plan_destroy(beer_graph_plan* plan) {
+    if (!plan) return;
+    if (plan->dev_blob) cudaFree(plan->dev_blob);
+    delete plan;
+}
+
+int beer_graph_plan_info(const beer_graph_plan* p, int32_t* info) {
+    if (!p || !info) return BEER_ERR_ARG;
+    info[0] = p->K; info[1] = p->J; info[2] = p->n_direct; info[3] = p->n_jin;
+    info[4] = p->n_jout; info[5] = p->S; info[6] = p->map_identity; info[7] = p->dense_nnz;
+    return BEER_OK;
+}
+
+static int fb_row_stride(const beer_graph_plan* p) { return (p->K + 3) & ~3; }
+
+int64_t beer_hmm_workspace_bytes(const beer_graph_plan* plan, int64_t N) {
+    if (!plan || N < 0) return BEER_ERR_ARG;
+    return (N * fb_row_stride(plan) + 64) * (int64_t)sizeof(float);
+}
+
+int beer_hmm_forward_backward(const beer_graph_plan* plan, const float* pdf_llh, int64_t ld_pdf,
+                              const float* frame_ref, const int64_t* utt_off, int n_utts, float scale,
+                              float* state_post, float* pdf_post, int64_t ld_post, float* frame_exp_llh,
+                              double* utt_exp_llh, double* utt_logz, void* workspace, void* stream) {
+    if (!plan || !pdf_llh || !utt_off || !utt_exp_llh || !workspace || n_utts < 0) return BEER_ERR_ARG;
+    if (ld_pdf < plan->Kp || (pdf_post && ld_post < plan->Kp)) return BEER_ERR_ARG;
+    if (n_utts == 0) return BEER_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    FbArgs a;
+    a.fwd = plan->fwd; a.bwd = plan->bwd;
+    a.K = plan->K; a.J = plan->J; a.Kp = plan->Kp;
+    a.map = plan->map; a.map_identity = plan->map_identity;
+    a.pl = pdf_llh; a.ld = ld_pdf; a.frame_ref = frame_ref; a.utt_off = utt_off; a.n_utts = n_utts;
+    a.scale = scale;
+    a.la_ws = (float*)workspace; a.Kw = fb_row_stride(plan);
+    a.state_post = state_post; a.pdf_post = pdf_post; a.ld_post = ld_post;
+    a.frame_exp_llh = frame_exp_llh; a.utt_exp_llh = utt_exp_llh; a.utt_logz = utt_logz;
+    a.vec = (plan->map_identity && plan->S % 4 == 0 && plan->K % 4 == 0 && ld_pdf % 4 == 0 &&
+             ((uintptr_t)pdf_llh & 15) == 0) ? 1 : 0;
+    switch (plan->S) {
+        case 1: return launch_fb<1>(a, n_utts, st);
+        case 2: return launch_fb<2>(a, n_utts, st);
+        case 4: return launch_fb<4>(a, n_utts, st);
+        case 8: return launch_fb<8>(a, n_utts, st);
+        case 16: return launch_fb<16>(a, n_utts, st);
+        case 32: return launch_fb<32>(a, n_utts, st);
+    }
+    return BEER_ERR_UNSUPPORTED;
+}
+
+int beer_hmm_viterbi(const beer_graph_plan* plan, const float* pdf_llh, int64_t ld_pdf, const int64_t* utt_off,
+                     int n_utts, float scale, int32_t* path, void* workspace, void* stream) {
+    if (!plan || !pdf_llh || !utt_off || !path || !workspace || n_utts < 0) return BEER_ERR_ARG;
+    if (ld_pdf < plan->Kp) return BEER_ERR_ARG;
+    if (n_utts == 0) return BEER_OK;
+    VitArgs a;
+    a.vit = plan->vit; a.vit_final = plan->vit_final; a.K = plan->K;
+    a.map = plan->map; a.map_identity = plan->map_identity;
+    a.pl = pdf_llh; a.ld = ld_pdf; a.utt_off = utt_off; a.n_utts = n_utts; a.scale = scale;
+    a.bt = (uint16_t*)workspace; a.path = path;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (plan->S) {
+        case 1: return launch_vit<1>(a, n_utts, st);
+        case 2: return launch_vit<2>(a, n_utts, st);
+        case 4: return launch_vit<4>(a, n_utts, st);
+        case 8: return launch_vit<8>(a, n_utts, st);
+        case 16: return launch_vit<16>(a, n_utts, st);
+        case 32: return launch_vit<32>(a, n_utts, st);
+    }
+    return BEER_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

@@ -1,0 +1,240 @@
+"""Functional wrappers: torch CUDA tensors -> C-ABI calls of libbeer_b200.so.
+
+PyTorch is used for device memory and streams only; every computation of the VB
+E-step / M-step below runs in the hand-written sm_100a kernels.  Each wrapper
+launches on the current torch CUDA stream and never synchronises.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+f32, f64, i32, i64 = torch.float32, torch.float64, torch.int32, torch.int64
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t, dtype=None, allow_none=False):
+    """Device pointer of a contiguous CUDA tensor."""
+    if t is None:
+        if allow_none:
+            return None
+        raise ValueError('missing tensor argument')
+    if not t.is_cuda:
+        raise _lib.BeerB200Error('beer_b200 kernels need CUDA tensors (there is no CPU fallback)')
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f'expected {dtype}, got {t.dtype}')
+    if not t.is_contiguous():
+        raise ValueError('tensor must be contiguous')
+    return C.c_void_p(t.data_ptr())
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.BeerB200Error('beer_b200 needs a CUDA device (B200, sm_100a); '
+                                 'there is no CPU fallback')
+    return _lib.load()
+
+
+# ---------------------------------------------------------------------------
+# parameter math
+# ---------------------------------------------------------------------------
+
+def normalgamma_expected_stats(mean, scale, shape, rates):
+    lib = require_cuda()
+    M, D = mean.shape
+    ets = torch.empty(M, 2 * D + 2, device=mean.device, dtype=f32)
+    _lib.check(lib.beer_normalgamma_expected_stats(_p(mean, f32), _p(scale, f32), _p(shape, f32),
+                                                   _p(rates, f32), M, D, _p(ets), _stream()),
+               'beer_normalgamma_expected_stats')
+    return ets
+
+
+def dirichlet_expected_logw(conc):
+    lib = require_cuda()
+    c2 = conc.reshape(-1, conc.shape[-1])
+    K, Cc = c2.shape
+    out = torch.empty_like(c2)
+    _lib.check(lib.beer_dirichlet_expected_logw(_p(c2, f32), K, Cc, _p(out), _stream()),
+               'beer_dirichlet_expected_logw')
+    return out.reshape(conc.shape)
+
+
+def emission_prepare(mean, scale, shape, rates, logw=None):
+    """-> (W [M,2D], bias [M], ref [D+1])."""
+    lib = require_cuda()
+    M, D = mean.shape
+    W = torch.empty(M, 2 * D, device=mean.device, dtype=f32)
+    bias = torch.empty(M, device=mean.device, dtype=f32)
+    ref = torch.empty(D + 1, device=mean.device, dtype=f32)
+    _lib.check(lib.beer_emission_prepare(_p(mean, f32), _p(scale, f32), _p(shape, f32), _p(rates, f32),
+                                         _p(logw, f32, True), M, D, _p(W), _p(bias), _p(ref), _stream()),
+               'beer_emission_prepare')
+    return W, bias, ref
+
+
+def emission_llh(X, W, bias, ref, comp_off=None, Kp=None, want_comp=False, out=None):
+    """-> (pdf_llh [N,Kp], comp_llh [N,M] or None, frame_ref [N]); offset form."""
+    lib = require_cuda()
+    N, D = X.shape
+    M = W.shape[0]
+    if Kp is None:
+        Kp = M if comp_off is None else comp_off.numel() - 1
+    pdf_llh = out if out is not None else torch.empty(N, Kp, device=X.device, dtype=f32)
+    comp = torch.empty(N, M, device=X.device, dtype=f32) if want_comp else None
+    fref = torch.empty(N, device=X.device, dtype=f32)
+    _lib.check(lib.beer_emission_llh(_p(X, f32), N, D, _p(W, f32), _p(bias, f32), _p(ref, f32), M,
+                                     _p(comp_off, i32, True), Kp, _p(pdf_llh, f32), pdf_llh.stride(0),
+                                     _p(comp, f32, True), _p(fref), _stream()),
+               'beer_emission_llh')
+    return pdf_llh, comp, fref
+
+
+# ---------------------------------------------------------------------------
+# graph plan
+# ---------------------------------------------------------------------------
+
+class GraphPlan:
+    """Device-resident sparse form of a compiled graph (beer_graph_plan)."""
+
+    def __init__(self, init_log, final_log, trans_log, pdf_map, n_pdfs=None, factorize=True):
+        lib = require_cuda()
+        init = np.ascontiguousarray(np.asarray(init_log, dtype=np.float32))
+        final = np.ascontiguousarray(np.asarray(final_log, dtype=np.float32))
+        trans = np.ascontiguousarray(np.asarray(trans_log, dtype=np.float32))
+        pmap = np.ascontiguousarray(np.asarray(pdf_map, dtype=np.int32))
+        K = init.shape[0]
+        if trans.shape != (K, K) or final.shape != (K,) or pmap.shape != (K,):
+            raise ValueError('inconsistent graph shapes')
+        self.n_states = K
+        self.n_pdfs = int(n_pdfs) if n_pdfs is not None else int(pmap.max()) + 1
+        handle = C.c_void_p()
+        _lib.check(lib.beer_graph_plan_create(init.ctypes.data, final.ctypes.data, trans.ctypes.data,
+                                              pmap.ctypes.data, K, self.n_pdfs, int(bool(factorize)),
+                                              C.byref(handle)), 'beer_graph_plan_create')
+        self._h = handle
+        self._lib = lib
+        info = np.zeros(8, dtype=np.int32)
+        _lib.check(lib.beer_graph_plan_info(self._h, info.ctypes.data), 'beer_graph_plan_info')
+        self.info = dict(K=int(info[0]), junctions=int(info[1]), direct_arcs=int(info[2]),
+                         junction_in=int(info[3]), junction_out=int(info[4]), states_per_lane=int(info[5]),
+                         map_identity=bool(info[6]), dense_nnz=int(info[7]))
+
+    def workspace_bytes(self, n_frames):
+        return int(self._lib.beer_hmm_workspace_bytes(self._h, int(n_frames)))
+
+    def __del__(self):
+        h, self._h = getattr(self, '_h', None), None
+        if h:
+            self._lib.beer_graph_plan_destroy(h)
+
+
+def hmm_forward_backward(plan, pdf_llh, frame_ref, utt_off, scale=1.0, want_state_post=False,
+                         want_pdf_post=True, want_frame_llh=False, want_logz=False, workspace=None):
+    """Forward-backward for a ragged batch.  -> dict(state_post, pdf_post, frame_exp_llh,
+    utt_exp_llh (fp64), utt_logz (fp64))."""
+    lib = require_cuda()
+    N = pdf_llh.shape[0]
+    n_utts = utt_off.numel() - 1
+    dev = pdf_llh.device
+    K, Kp = plan.n_states, plan.n_pdfs
+    if pdf_llh.shape[1] < Kp:
+        raise ValueError('pdf_llh has fewer columns than the graph has pdfs')
+    nbytes = plan.workspace_bytes(N)
+    if workspace is None or workspace.numel() * workspace.element_size() < nbytes:
+        workspace = torch.empty((nbytes + 3) // 4, device=dev, dtype=f32)
+    state_post = torch.empty(N, K, device=dev, dtype=f32) if want_state_post else None
+    pdf_post = None
+    if want_pdf_post:
+        pdf_post = (torch.empty if plan.info['map_identity'] and Kp == K else torch.zeros)(
+            N, Kp, device=dev, dtype=f32)
+    frame = torch.empty(N, device=dev, dtype=f32) if want_frame_llh else None
+    utt_ell = torch.empty(n_utts, device=dev, dtype=f64)
+    utt_logz = torch.empty(n_utts, device=dev, dtype=f64) if want_logz else None
+    _lib.check(lib.beer_hmm_forward_backward(
+        plan._h, _p(pdf_llh, f32), pdf_llh.stride(0), _p(frame_ref, f32, True), _p(utt_off, i64), n_utts,
+        float(scale), _p(state_post, f32, True), _p(pdf_post, f32, True), Kp, _p(frame, f32, True),
+        _p(utt_ell), _p(utt_logz, f64, True), _p(workspace), _stream()), 'beer_hmm_forward_backward')
+    return dict(state_post=state_post, pdf_post=pdf_post, frame_exp_llh=frame, utt_exp_llh=utt_ell,
+                utt_logz=utt_logz, workspace=workspace)
+
+
+def hmm_viterbi(plan, pdf_llh, utt_off, scale=1.0, workspace=None):
+    """Best state path (int32 [N]) of every utterance of a ragged batch."""
+    lib = require_cuda()
+    N = pdf_llh.shape[0]
+    n_utts = utt_off.numel() - 1
+    nbytes = N * plan.n_states * 2
+    if workspace is None or workspace.numel() * workspace.element_size() < nbytes:
+        workspace = torch.empty((nbytes + 3) // 4 + 1, device=pdf_llh.device, dtype=f32)
+    path = torch.empty(N, device=pdf_llh.device, dtype=i32)
+    _lib.check(lib.beer_hmm_viterbi(plan._h, _p(pdf_llh, f32), pdf_llh.stride(0), _p(utt_off, i64), n_utts,
+                                    float(scale), _p(path), _p(workspace), _stream()), 'beer_hmm_viterbi')
+    return path
+
+
+def accumulate_stats(X, acc_normal, pdf_post=None, pdf_llh=None, comp_llh=None, comp_off=None, Kp=None):
+    """acc_normal [M, 2D+2] (fp64) += posterior-weighted statistics."""
+    lib = require_cuda()
+    N, D = X.shape
+    M = acc_normal.shape[0]
+    if Kp is None:
+        Kp = M if comp_llh is None else (comp_off.numel() - 1 if comp_off is not None else pdf_llh.shape[1])
+    _lib.check(lib.beer_accumulate_stats(
+        _p(X, f32), N, D, _p(pdf_post, f32, True), pdf_post.stride(0) if pdf_post is not None else 0,
+        _p(pdf_llh, f32, True), pdf_llh.stride(0) if pdf_llh is not None else 0, _p(comp_llh, f32, True),
+        _p(comp_off, i32, True), Kp, M, _p(acc_normal, f64), _stream()), 'beer_accumulate_stats')
+    return acc_normal
+
+
+def mixture_weight_stats(acc_normal, D, comp_off=None, Kp=None):
+    lib = require_cuda()
+    M = acc_normal.shape[0]
+    if Kp is None:
+        Kp = comp_off.numel() - 1
+    out = torch.empty(M, device=acc_normal.device, dtype=f64)
+    _lib.check(lib.beer_mixture_weight_stats(_p(acc_normal, f64), M, D, _p(comp_off, i32, True), Kp, _p(out),
+                                             _stream()), 'beer_mixture_weight_stats')
+    return out
+
+
+def normalgamma_update(prior, post, acc, stats_scale=1.0, lrate=1.0):
+    """In-place natural-gradient step; prior/post = (mean, scale, shape, rates)."""
+    lib = require_cuda()
+    M, D = post[0].shape
+    _lib.check(lib.beer_normalgamma_update(*[_p(t, f32) for t in prior], *[_p(t, f32) for t in post],
+                                           _p(acc, f64), float(stats_scale), float(lrate), M, D, _stream()),
+               'beer_normalgamma_update')
+
+
+def normalgamma_kl(prior, post, out=None):
+    lib = require_cuda()
+    M, D = post[0].shape
+    if out is None:
+        out = torch.zeros(1, device=post[0].device, dtype=f64)
+    _lib.check(lib.beer_normalgamma_kl(*[_p(t, f32) for t in prior], *[_p(t, f32) for t in post], M, D,
+                                       _p(out, f64), _stream()), 'beer_normalgamma_kl')
+    return out
+
+
+def dirichlet_update(prior, post, acc, stats_scale=1.0, lrate=1.0):
+    lib = require_cuda()
+    p2, q2 = prior.reshape(-1, prior.shape[-1]), post.reshape(-1, post.shape[-1])
+    K, Cc = q2.shape
+    _lib.check(lib.beer_dirichlet_update(_p(p2, f32), _p(q2, f32), _p(acc, f64), float(stats_scale),
+                                         float(lrate), K, Cc, _stream()), 'beer_dirichlet_update')
+
+
+def dirichlet_kl(prior, post, out=None):
+    lib = require_cuda()
+    p2, q2 = prior.reshape(-1, prior.shape[-1]), post.reshape(-1, post.shape[-1])
+    K, Cc = q2.shape
+    if out is None:
+        out = torch.zeros(1, device=post.device, dtype=f64)
+    _lib.check(lib.beer_dirichlet_kl(_p(p2, f32), _p(q2, f32), K, Cc, _p(out, f64), _stream()),
+               'beer_dirichlet_kl')
+    return out

@@ -1,0 +1,187 @@
+/* beer_b200 -- C ABI of the B200-native VB-EM hot path (libbeer_b200.so).
+ *
+ * Drop-in boundary for ONE path of beer-asr/beer (reference @ d53d2a1): what
+ * `beer.evidence_lower_bound(model, X, ...)` runs on HMM / GMM models
+ * (beer/inference/objectives.py:119-190).  The reference has no FFI; each entry
+ * point below names the reference Python op site it replaces (file:line,
+ * relative to the reference checkout).  INTEGRATION.md shows the ctypes stub a
+ * maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *   - the caller owns every buffer, kernels never allocate (the only objects the
+ *     library owns are graph plans, created/destroyed explicitly);
+ *   - every call is stream-ordered on `stream` (a cudaStream_t passed as void*,
+ *     NULL = legacy default stream), performs no device synchronisation and is
+ *     re-entrant across streams;
+ *   - return value: 0 = ok, > 0 = cudaError_t, < 0 = BEER_ERR_* below;
+ *   - frames of all utterances are concatenated ("ragged batch"): X is [N, D]
+ *     row-major fp32, utt_off[n_utts + 1] (int64) holds the first frame of each
+ *     utterance and N at the end;
+ *   - float data is fp32, accumulated statistics and ELBO terms are fp64.
+ */
+#ifndef BEER_B200_H_
+#define BEER_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define BEER_API __attribute__((visibility("default")))
+#else
+#define BEER_API
+#endif
+
+#define BEER_ERR_ARG (-1)
+#define BEER_ERR_UNSUPPORTED (-2)
+#define BEER_ERR_ALLOC (-3)
+
+/* Library / ABI version (major * 100 + minor). */
+BEER_API int beer_b200_version(void);
+
+/* ------------------------------------------------------------------------
+ * Conjugate exponential-family parameter math (beer/dists)
+ * ---------------------------------------------------------------------- */
+
+/* E_q[T(theta)] of M Normal-Gamma posteriors, [M, 2D+2] =
+ * [a/b*m, a/b, D/k + sum a/b*m^2, sum psi(a) - ln b].
+ * Replaces NormalGamma.expected_sufficient_statistics (beer/dists/normalgamma.py:118-146).
+ * mean [M,D], scale [M], shape [M], rates [M,D]. */
+BEER_API int beer_normalgamma_expected_stats(const float* mean, const float* scale, const float* shape,
+                                    const float* rates, int M, int D, float* ets, void* stream);
+
+/* E[ln pi] of K Dirichlet posteriors with C categories, [K, C] =
+ * psi(a_kc) - psi(sum_c a_kc).  Replaces the eye(C) evaluation of
+ * MixtureSet._log_weights / Mixture._log_weights (beer/models/mixtureset.py:64-67,
+ * mixture.py:45-48) through Dirichlet.expected_sufficient_statistics
+ * (beer/dists/dirichlet.py:106-128). */
+BEER_API int beer_dirichlet_expected_logw(const float* conc, int K, int C, float* logw, void* stream);
+
+/* Emission weights for the per-frame expected log-likelihood kernel.
+ * From the Normal-Gamma posteriors of M diagonal Gaussians (and optional
+ * per-Gaussian mixture log-weights logw[M], NULL for none) builds
+ *   W[M, 2D]  = [a/b*m | a/b - lam_ref]            (fp32)
+ *   bias[M]   = -1/2 (D/k + sum a/b m^2) + 1/2 sum(psi(a) - ln b)
+ *               - D/2 ln 2pi + logw - bias_ref      (fp32, computed in fp64)
+ *   ref[D+1]  = [lam_ref (D) | bias_ref]            (mean over the M Gaussians)
+ * so that  llh_tj = [x_t, -x_t^2/2] . W_j + bias_j + r_t  with the per-frame
+ * constant  r_t = -1/2 sum_d lam_ref_d x_td^2 + bias_ref.  Splitting r_t off keeps
+ * the per-state values small so that fp32 resolves posteriors to ~1e-6.
+ * Same contraction as NormalDiagonalLikelihood.__call__
+ * (beer/dists/normalgamma.py:55-59) on the statistics of normalgamma.py:19-27. */
+BEER_API int beer_emission_prepare(const float* mean, const float* scale, const float* shape,
+                          const float* rates, const float* logw, int M, int D, float* W,
+                          float* bias, float* ref, void* stream);
+
+/* ------------------------------------------------------------------------
+ * E-step kernels
+ * ---------------------------------------------------------------------- */
+
+/* KA: per-frame per-pdf expected log-likelihood of a NormalSet / MixtureSet.
+ * Replaces NormalSet.expected_log_likelihood (beer/models/normalset.py:117-119)
+ * and MixtureSet.expected_log_likelihood (beer/models/mixtureset.py:85-98).
+ *   X [N,D]; W, bias, ref from beer_emission_prepare;
+ *   comp_off[Kp+1] (int32): pdf k owns Gaussians comp_off[k]..comp_off[k+1]-1
+ *     (NULL: one Gaussian per pdf, Kp == M);
+ *   pdf_llh [N, ld_pdf] <- logsumexp_c(llh_t,kc) - r_t     (offset form)
+ *   comp_llh [N, M] or NULL <- llh_tj - r_t                (kept for responsibilities)
+ *   frame_ref [N] <- r_t. */
+BEER_API int beer_emission_llh(const float* X, int64_t N, int D, const float* W, const float* bias,
+                      const float* ref, int M, const int32_t* comp_off, int Kp, float* pdf_llh,
+                      int64_t ld_pdf, float* comp_llh, float* frame_ref, void* stream);
+
+/* Graph plan: device-resident sparse form of a CompiledGraph
+ * (beer/graph.py:243-268: init_log_probs[K], final_log_probs[K], dense
+ * trans_log_probs[K,K], pdf_id_mapping[K]).  Host pointers in, opaque handle out.
+ * Arcs with log-probability -inf are dropped; with `factorize` != 0, groups of
+ * rows that share one off-diagonal support set with proportional weights (the
+ * unit-end -> unit-start block of a phone loop, beer/models/phoneloop.py:53-65)
+ * are routed through one non-emitting junction node, as they were in the
+ * uncompiled Graph (beer/graph.py:185-240). */
+typedef struct beer_graph_plan beer_graph_plan;
+BEER_API int beer_graph_plan_create(const float* init_log_host, const float* final_log_host,
+                           const float* trans_log_host, const int32_t* pdf_map_host, int K, int Kp,
+                           int factorize, beer_graph_plan** plan_out);
+BEER_API void beer_graph_plan_destroy(beer_graph_plan* plan);
+/* info[0]=K, [1]=#junctions, [2]=#direct arcs, [3]=#junction in-arcs, [4]=#junction
+ * out-arcs, [5]=states per lane, [6]=1 if pdf map is the identity, [7]=dense nnz. */
+BEER_API int beer_graph_plan_info(const beer_graph_plan* plan, int32_t* info8_host);
+
+/* Bytes of workspace beer_hmm_forward_backward needs for N frames. */
+BEER_API int64_t beer_hmm_workspace_bytes(const beer_graph_plan* plan, int64_t N);
+
+/* KB: forward-backward over one graph for a ragged batch of utterances.
+ * Replaces CompiledGraph._baum_welch_forward/_backward/posteriors
+ * (beer/graph.py:270-326) and the expected value of HMM.expected_log_likelihood
+ * (beer/models/hmm.py:79-92), p_tk = scale * pdf_llh[t, map[k]].
+ *   state_post [N,K] or NULL  <- gamma_tk (per-frame normalised, graph.py:306-307)
+ *   pdf_post  [N,ld_post] or NULL <- scale * sum_{k: map[k]=pdf} gamma_tk
+ *                                   (hmm.py:94-95 + modelset.py:148-154)
+ *   frame_exp_llh [N] or NULL <- sum_k p_tk gamma_tk + scale*frame_ref[t]  (hmm.py:87)
+ *   utt_exp_llh [n_utts] (fp64) <- sum_t of the above
+ *   utt_logz [n_utts] (fp64) or NULL <- log evidence of the scaled llhs (natural log,
+ *                                   includes scale*frame_ref)
+ *   workspace: beer_hmm_workspace_bytes(plan, N) bytes. */
+BEER_API int beer_hmm_forward_backward(const beer_graph_plan* plan, const float* pdf_llh, int64_t ld_pdf,
+                              const float* frame_ref, const int64_t* utt_off, int n_utts,
+                              float scale, float* state_post, float* pdf_post, int64_t ld_post,
+                              float* frame_exp_llh, double* utt_exp_llh, double* utt_logz,
+                              void* workspace, void* stream);
+
+/* KV: Viterbi best path (first-max tie-breaking) for a ragged batch.
+ * Replaces CompiledGraph.best_path (beer/graph.py:329-344).
+ *   path [N] (int32) <- state ids; workspace: N*K*sizeof(uint16_t) bytes. */
+BEER_API int beer_hmm_viterbi(const beer_graph_plan* plan, const float* pdf_llh, int64_t ld_pdf,
+                     const int64_t* utt_off, int n_utts, float scale, int32_t* path,
+                     void* workspace, void* stream);
+
+/* KC: posterior-weighted sufficient statistics, accumulated (+=) into a caller-zeroed
+ * fp64 buffer.  Replaces the joint responsibilities of MixtureSet.accumulate
+ * (beer/models/mixtureset.py:100-112) and NormalSet.accumulate
+ * (beer/models/normalset.py:121-123):  w_tj = pdf_post[t, pdf(j)] * r_tj,
+ * r_tj = exp(comp_llh_tj - pdf_llh_t,pdf(j)).
+ *   pdf_post [N, ld_post] or NULL (all ones: plain Mixture, mixture.py:95-102)
+ *   pdf_llh / comp_llh / comp_off as produced by beer_emission_llh
+ *     (comp_llh NULL: one Gaussian per pdf, w = pdf_post)
+ *   acc_normal [M, 2D+2] += [sum w x, -1/2 sum w x^2, -1/2 sum w, 1/2 sum w]. */
+BEER_API int beer_accumulate_stats(const float* X, int64_t N, int D, const float* pdf_post, int64_t ld_post,
+                          const float* pdf_llh, int64_t ld_pdf, const float* comp_llh,
+                          const int32_t* comp_off, int Kp, int M, double* acc_normal, void* stream);
+
+/* Categorical statistics of the mixture weights from the accumulated Normal statistics
+ * (sum_t w_tj = 2 * acc_normal[j, 2D+1]):  per pdf [n_c (c < C-1), sum_c n_c], the layout
+ * of CategoricalLikelihood.sufficient_statistics (beer/dists/dirichlet.py:18-21) summed
+ * over frames as CategoricalSet.accumulate_from_jointresps does
+ * (beer/models/categoricalset.py:54-55).  acc_weights [M] is overwritten. */
+BEER_API int beer_mixture_weight_stats(const double* acc_normal, int M, int D, const int32_t* comp_off, int Kp,
+                              double* acc_weights, void* stream);
+
+/* ------------------------------------------------------------------------
+ * M-step and KL (beer/models/parameters.py:134-141, beer/dists/basedist.py:243-263)
+ * ---------------------------------------------------------------------- */
+
+/* Natural-gradient step of M Normal-Gamma posteriors, in place:
+ *   eta <- eta + lrate * (eta_prior + stats_scale * acc - eta), then back to
+ *   (mean, scale, shape, rates) (beer/dists/normalgamma.py:76-94, 163-180). */
+BEER_API int beer_normalgamma_update(const float* prior_mean, const float* prior_scale,
+                            const float* prior_shape, const float* prior_rates, float* mean,
+                            float* scale, float* shape, float* rates, const double* acc,
+                            double stats_scale, double lrate, int M, int D, void* stream);
+/* kl[0] += sum_j KL(q_j || p_j) (fp64; normalgamma.py:151-157 log-normaliser). */
+BEER_API int beer_normalgamma_kl(const float* prior_mean, const float* prior_scale, const float* prior_shape,
+                        const float* prior_rates, const float* mean, const float* scale,
+                        const float* shape, const float* rates, int M, int D, double* kl,
+                        void* stream);
+/* Dirichlet counterparts (beer/dists/dirichlet.py:70-81, 135-159); conc [K,C]. */
+BEER_API int beer_dirichlet_update(const float* prior_conc, float* conc, const double* acc,
+                          double stats_scale, double lrate, int K, int C, void* stream);
+BEER_API int beer_dirichlet_kl(const float* prior_conc, const float* conc, int K, int C, double* kl,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BEER_B200_H_ */

@@ -1,0 +1,263 @@
+"""GPU parity tests, kernel level: every C-ABI entry point against the numpy oracle and
+the fp64 goldens generated from the live reference (tests/golden/make_goldens.py).
+
+Tolerances (north_star: "ELBO and state posteriors within 1e-5 relative in fp32"):
+  * state posteriors: |gamma - gamma_ref| <= 1e-5 (posteriors live in [0, 1]);
+  * expected log-likelihood sums / ELBO: 1e-5 relative (measured ~1e-7);
+  * accumulated statistics: 2e-5 relative to the largest statistic of the row block;
+  * Viterbi paths: identical.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import beer_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DEV = 'cuda'
+
+
+def dev(a, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(DEV).contiguous()
+
+
+def ng(g, p):
+    return g[p + 'mean'], g[p + 'scale'], g[p + 'shape'], g[p + 'rates']
+
+
+def ng_dev(t):
+    m, k, a, b = t
+    return dev(m), dev(k.reshape(-1)), dev(a.reshape(-1)), dev(b)
+
+
+def graph(g, p='g_'):
+    return g[p + 'init'], g[p + 'final'], g[p + 'trans'], g[p + 'map']
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from beer_b200 import ops
+    ops.require_cuda()
+    return ops
+
+
+def test_normalgamma_dirichlet_math(ops):
+    g = load_golden('dists')
+    q, p = ng(g, 'ng_'), ng(g, 'ngp_')
+    ets = ops.normalgamma_expected_stats(*ng_dev(q)).cpu().numpy()
+    np.testing.assert_allclose(ets, g['ng_ets'], rtol=2e-6, atol=1e-6)
+    kl = ops.normalgamma_kl(ng_dev(p), ng_dev(q)).item()
+    np.testing.assert_allclose(kl, g['ng_kl'].sum(), rtol=1e-6)
+    logw = ops.dirichlet_expected_logw(dev(g['dir_conc'])).cpu().numpy()
+    np.testing.assert_allclose(logw, g['dir_logw'], rtol=2e-6, atol=1e-6)
+    dkl = ops.dirichlet_kl(dev(g['dirp_conc']), dev(g['dir_conc'])).item()
+    np.testing.assert_allclose(dkl, g['dir_kl'].sum(), rtol=1e-6)
+    # natural-gradient step against the oracle (parameters.py:134-141)
+    rng = np.random.default_rng(0)
+    M, D = q[0].shape
+    n = rng.random(M) * 20
+    sx = rng.standard_normal((M, D)) * n[:, None]
+    sxx = (rng.random((M, D)) + 1) * n[:, None] * 2
+    acc = np.concatenate([sx, -.5 * sxx, -.5 * n[:, None], .5 * n[:, None]], axis=1)
+    for lr, s in ((1.0, 1.0), (0.3, 2.5)):
+        want = O.natural_grad_update_normalgamma(p, q, s * acc, lr)
+        post = ng_dev(q)
+        ops.normalgamma_update(ng_dev(p), post, dev(acc, torch.float64), s, lr)
+        for got, w in zip(post, want):
+            np.testing.assert_allclose(got.cpu().numpy().reshape(w.shape), w, rtol=1e-5, atol=1e-6)
+        cacc = rng.random(g['dir_conc'].shape) * 10
+        cacc[:, -1] = cacc.sum(axis=1)
+        want = O.natural_grad_update_dirichlet(g['dirp_conc'], g['dir_conc'], s * cacc, lr)
+        conc = dev(g['dir_conc'])
+        ops.dirichlet_update(dev(g['dirp_conc']), conc, dev(cacc, torch.float64), s, lr)
+        np.testing.assert_allclose(conc.cpu().numpy(), want, rtol=1e-5, atol=1e-6)
+
+
+def _emission(ops, X, post, dir_post=None, comp_off=None, want_comp=False):
+    logw = None
+    if dir_post is not None:
+        logw = torch.cat([ops.dirichlet_expected_logw(dev(d)).reshape(-1) for d in dir_post])
+    W, bias, ref = ops.emission_prepare(*ng_dev(post), logw=logw)
+    co = None if comp_off is None else dev(comp_off, torch.int32)
+    return ops.emission_llh(dev(X), W, bias, ref, comp_off=co, want_comp=want_comp)
+
+
+@pytest.mark.parametrize('name', ['hmm_small', 'hmm_scaled', 'hmm_cfg2_T200'])
+def test_emission_llh_normalset(ops, name):
+    g = load_golden(name)
+    pdf_llh, _, fref = _emission(ops, g['X'], ng(g, 'post0_'))
+    got = pdf_llh.double().cpu().numpy() + fref.double().cpu().numpy()[:, None]
+    np.testing.assert_allclose(got, g['pdf_llh'], rtol=0, atol=2e-4)   # absolute llh ~ -1e2: fp32 ulp
+    # what the scan consumes is the offset form: differences between states must be accurate
+    d_got = pdf_llh.double().cpu().numpy()
+    d_ref = g['pdf_llh'] - g['pdf_llh'].max(axis=1, keepdims=True)
+    d_got = d_got - d_got[np.arange(len(d_got)), g['pdf_llh'].argmax(axis=1)][:, None]
+    near = d_ref > -30
+    assert np.abs(d_got - d_ref)[near].max() < 3e-5
+
+
+def _fb_case(ops, llh, gr, scale=1.0, factorize=True, **kw):
+    plan = ops.GraphPlan(*gr, factorize=factorize)
+    T = llh.shape[0]
+    utt = torch.tensor([0, T], dtype=torch.int64, device=DEV)
+    return plan, ops.hmm_forward_backward(plan, dev(llh), None, utt, scale=scale, want_state_post=True,
+                                          want_frame_llh=True, want_logz=True, **kw)
+
+
+@pytest.mark.parametrize('factorize', [True, False])
+@pytest.mark.parametrize('name', ['hmm_small', 'hmm_scaled', 'hmm_cfg2_T200'])
+def test_forward_backward_golden(ops, name, factorize):
+    g = load_golden(name)
+    scale = float(g['scale'])
+    gr = graph(g)
+    # feed the reference's own (fp64 -> fp32, max-subtracted) llhs: isolates the scan
+    llh = g['pdf_llh'] - g['pdf_llh'].max(axis=1, keepdims=True)
+    plan, r = _fb_case(ops, llh, gr, scale=scale, factorize=factorize)
+    gamma = r['state_post'].double().cpu().numpy()
+    assert np.abs(gamma - g['gamma']).max() <= 1e-5
+    np.testing.assert_allclose(gamma.sum(axis=1), 1.0, atol=2e-6)
+    exp_llh = r['frame_exp_llh'].double().cpu().numpy() + scale * g['pdf_llh'].max(axis=1)
+    np.testing.assert_allclose(exp_llh.sum(), g['exp_llh'].sum(), rtol=1e-6)
+    np.testing.assert_allclose(r['utt_exp_llh'].item() + scale * g['pdf_llh'].max(axis=1).sum(),
+                               g['exp_llh'].sum(), rtol=1e-6)
+    # log evidence against the oracle's unnormalised forward pass
+    la = O.forward(scale * g['pdf_llh'], gr[0], gr[2])
+    logz = O.logsumexp(la[-1] + gr[1], axis=0)
+    np.testing.assert_allclose(r['utt_logz'].item() + scale * g['pdf_llh'].max(axis=1).sum(), logz, rtol=1e-6)
+    if factorize and name == 'hmm_cfg2_T200':
+        assert plan.info['junctions'] == 1 and plan.info['junction_in'] == 25 and plan.info['junction_out'] == 25
+
+
+def test_forward_backward_dense_and_unreachable(ops):
+    g = load_golden('dense_ergodic')
+    _, r = _fb_case(ops, g['llhs'], graph(g))
+    assert np.abs(r['state_post'].double().cpu().numpy() - g['gamma']).max() <= 1e-5
+    _, r2 = _fb_case(ops, g['llhs2'], graph(g, 'g2_'))
+    gam2 = r2['state_post'].double().cpu().numpy()
+    assert np.isfinite(gam2).all()
+    assert np.abs(gam2 - g['gamma2']).max() <= 1e-5
+    assert (gam2[:, 6] == 0).all()                       # unreachable state: exactly zero, no NaN
+
+
+@pytest.mark.parametrize('name', ['hmm_small', 'hmm_scaled', 'hmm_cfg2_T200'])
+def test_viterbi_golden(ops, name):
+    g = load_golden(name)
+    scale = float(g['scale'])
+    plan = ops.GraphPlan(*graph(g))
+    T = len(g['X'])
+    utt = torch.tensor([0, T], dtype=torch.int64, device=DEV)
+    pdf_llh, _, _ = _emission(ops, g['X'], ng(g, 'post0_'))
+    path = ops.hmm_viterbi(plan, pdf_llh, utt, scale=scale).cpu().numpy()
+    np.testing.assert_array_equal(path, g['viterbi_path'])
+
+
+def test_viterbi_ties_first_max(ops):
+    g = load_golden('dense_ergodic')
+    for sfx, gp in (('', 'g_'), ('2', 'g2_')):
+        llh = g['llhs' + sfx]
+        plan = ops.GraphPlan(*graph(g, gp))
+        utt = torch.tensor([0, len(llh)], dtype=torch.int64, device=DEV)
+        path = ops.hmm_viterbi(plan, dev(llh), utt).cpu().numpy()
+        np.testing.assert_array_equal(path, g['path' + sfx])
+
+
+@pytest.mark.parametrize('name', ['hmm_small', 'hmm_scaled', 'hmm_cfg2_T200'])
+def test_estep_chain_normalset(ops, name):
+    """KA -> KB -> KC chained on the device against the golden E-step of the reference."""
+    g = load_golden(name)
+    scale = float(g['scale'])
+    X = dev(g['X'])
+    T, D = g['X'].shape
+    pdf_llh, _, fref = _emission(ops, g['X'], ng(g, 'post0_'))
+    plan = ops.GraphPlan(*graph(g))
+    utt = torch.tensor([0, T], dtype=torch.int64, device=DEV)
+    r = ops.hmm_forward_backward(plan, pdf_llh, fref, utt, scale=scale, want_state_post=True)
+    assert np.abs(r['state_post'].double().cpu().numpy() - g['gamma']).max() <= 1e-5
+    np.testing.assert_allclose(r['utt_exp_llh'].item(), g['exp_llh'].sum(), rtol=1e-6)
+    K = g['gamma'].shape[1]
+    acc = torch.zeros(K, 2 * D + 2, device=DEV, dtype=torch.float64)
+    ops.accumulate_stats(X, acc, pdf_post=r['pdf_post'])
+    got = acc.cpu().numpy()
+    assert np.abs(got - g['acc_normal']).max() <= 2e-5 * np.abs(g['acc_normal']).max()
+    # ELBO with datasize = 3T (objectives.py:176-184)
+    prior, post = ng_dev(ng(g, 'prior_')), ng_dev(ng(g, 'post0_'))
+    kl = ops.normalgamma_kl(prior, post).item()
+    np.testing.assert_allclose(kl, g['kl'], rtol=1e-6)
+    np.testing.assert_allclose(3.0 * r['utt_exp_llh'].item() - kl, g['elbo_datasize3T'], rtol=1e-6)
+
+
+def test_mixtureset_two_groups(ops):
+    """Two MixtureSet groups with different numbers of components (CSR component offsets),
+    xi-free path over the decoding graph and over an alignment graph with repeated pdfs."""
+    g = load_golden('phoneloop_mixtureset')
+    C1, C2, K1 = int(g['C1']), int(g['C2']), int(g['K1'])
+    K = len(g['g_map'])
+    post = tuple(np.concatenate([g['g1_post0_' + k], g['g2_post0_' + k]]) for k in ('mean', 'scale', 'shape', 'rates'))
+    comp_off = np.concatenate([np.arange(K1) * C1, K1 * C1 + np.arange(K - K1 + 1) * C2])
+    M = comp_off[-1]
+    D = g['X1'].shape[1]
+    for X, gp, scale, tag in ((g['X1'], 'g_', 1.0, 'u1'), (g['X3'], 'ali_', 0.7, 'u3')):
+        pdf_llh, comp, fref = _emission(ops, X, post, dir_post=(g['g1_dpost0'], g['g2_dpost0']),
+                                        comp_off=comp_off, want_comp=True)
+        if tag == 'u1':
+            got = pdf_llh.double().cpu().numpy() + fref.double().cpu().numpy()[:, None]
+            np.testing.assert_allclose(got, g['u1_pdf_llh'], atol=1e-4)
+        plan = ops.GraphPlan(*graph(g, gp), n_pdfs=K)
+        utt = torch.tensor([0, len(X)], dtype=torch.int64, device=DEV)
+        r = ops.hmm_forward_backward(plan, pdf_llh, fref, utt, scale=scale, want_state_post=True,
+                                     want_frame_llh=True)
+        assert np.abs(r['state_post'].double().cpu().numpy() - g[tag + '_gamma']).max() <= 1e-5
+        np.testing.assert_allclose(r['frame_exp_llh'].double().cpu().numpy(), g[tag + '_exp_llh'],
+                                   rtol=1e-5, atol=1e-4)
+        acc = torch.zeros(M, 2 * D + 2, device=DEV, dtype=torch.float64)
+        ops.accumulate_stats(dev(X), acc, pdf_post=r['pdf_post'], pdf_llh=pdf_llh, comp_llh=comp,
+                             comp_off=dev(comp_off, torch.int32))
+        want = np.concatenate([g[tag + '_acc_g1'], g[tag + '_acc_g2']])
+        assert np.abs(acc.cpu().numpy() - want).max() <= 2e-5 * np.abs(want).max()
+        wst = ops.mixture_weight_stats(acc, D, comp_off=dev(comp_off, torch.int32)).cpu().numpy()
+        want_w = np.concatenate([g[tag + '_acc_d1'].reshape(-1), g[tag + '_acc_d2'].reshape(-1)])
+        np.testing.assert_allclose(wst, want_w, rtol=2e-5, atol=2e-5)
+
+
+def test_gmm_cfg1(ops):
+    """BASELINE configs[0]: 8-component diagonal Mixture on 2-D points."""
+    g = load_golden('gmm_cfg1')
+    X = g['X']
+    post, dpost = ng(g, 'post0_'), g['dpost0']
+    pdf_llh, comp, fref = _emission(ops, X, post, dir_post=(dpost[None],), comp_off=np.array([0, 8]),
+                                    want_comp=True)
+    exp_llh = pdf_llh.double().cpu().numpy()[:, 0] + fref.double().cpu().numpy()
+    np.testing.assert_allclose(exp_llh, g['exp_llh'], rtol=1e-5, atol=1e-5)
+    resps = torch.exp(comp - pdf_llh).double().cpu().numpy()
+    assert np.abs(resps - g['resps']).max() <= 1e-5
+    acc = torch.zeros(8, 2 * 2 + 2, device=DEV, dtype=torch.float64)
+    ops.accumulate_stats(dev(X), acc, pdf_llh=pdf_llh, comp_llh=comp, comp_off=dev(np.array([0, 8]), torch.int32))
+    assert np.abs(acc.cpu().numpy() - g['acc_normal']).max() <= 2e-5 * np.abs(g['acc_normal']).max()
+    wst = ops.mixture_weight_stats(acc, 2, comp_off=dev(np.array([0, 8]), torch.int32)).cpu().numpy()
+    np.testing.assert_allclose(wst, g['acc_dirichlet'], rtol=2e-5)
+
+
+def test_ragged_batch_equals_single(ops):
+    """A ragged batch (including an empty and a 1-frame utterance) gives, per utterance, what
+    separate calls give (EvidenceLowerBoundInstance.__add__ semantics, objectives.py:78-90)."""
+    g = load_golden('hmm_cfg2_T200')
+    X = g['X']
+    lens = [200, 0, 1, 37, 64, 200, 5]
+    rng = np.random.default_rng(3)
+    utts = [X[rng.integers(0, 200 - n + 1):][:n] if n else X[:0] for n in lens]
+    Xc = np.concatenate(utts)
+    off = np.concatenate([[0], np.cumsum(lens)])
+    post = ng(g, 'post0_')
+    pdf_llh, _, fref = _emission(ops, Xc, post)
+    plan = ops.GraphPlan(*graph(g))
+    r = ops.hmm_forward_backward(plan, pdf_llh, fref, dev(off, torch.int64), want_state_post=True)
+    gam = r['state_post'].double().cpu().numpy()
+    for i, n in enumerate(lens):
+        if n == 0:
+            assert r['utt_exp_llh'][i].item() == 0.0
+            continue
+        want = O.hmm_estep(utts[i].astype(np.float64), post, None, graph(g))
+        assert np.abs(gam[off[i]:off[i + 1]] - want['gamma']).max() <= 1e-5
+        np.testing.assert_allclose(r['utt_exp_llh'][i].item(), want['exp_llh'].sum(), rtol=1e-6)
