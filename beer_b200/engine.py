@@ -1,0 +1,259 @@
+"""Batched VB-EM engine: one VB iteration of an HMM-GMM over a ragged batch of utterances
+resident in HBM, the way `beer hmm accumulate` + `beer hmm update` compose it
+(beer/cli/subcommands/hmm/accumulate.py:37-63, update.py:37-62):
+
+    for every utterance u:  elbo += evidence_lower_bound(model, X_u, datasize=N, ...)
+    elbo.backward(); optim.step()
+
+but as a handful of kernel launches over all utterances at once:
+
+    KM  emission weights + KL        (beer_emission_prepare, beer_*_kl)
+    KA  per-frame per-pdf llh        (beer_emission_llh)
+    KB  forward-backward             (beer_hmm_forward_backward)
+    KC  sufficient statistics        (beer_accumulate_stats)
+    --  one all-reduce of the flat fp64 statistics buffer (torch.distributed, NCCL)
+    KM  natural-gradient M-step      (beer_normalgamma_update, beer_dirichlet_update)
+
+Utterances shard over ranks (one process per GPU); the only exchange is the all-reduce.
+"""
+import numpy as np
+import torch
+
+from . import ops
+
+f32, f64, i32, i64 = torch.float32, torch.float64, torch.int32, torch.int64
+
+
+class Utterances:
+    """Ragged batch: frames of all utterances concatenated in one [N, D] fp32 tensor."""
+
+    def __init__(self, X, lengths, device=None):
+        lengths = np.asarray(lengths, dtype=np.int64)
+        off = np.concatenate([[0], np.cumsum(lengths)])
+        if isinstance(X, (list, tuple)):
+            X = torch.cat([torch.as_tensor(x, dtype=f32) for x in X]) if len(X) else torch.zeros(0, 1)
+        X = torch.as_tensor(X, dtype=f32)
+        if X.shape[0] != off[-1]:
+            raise ValueError('sum(lengths) must equal the number of frames')
+        self.X = X.to(device).contiguous() if device is not None else X.contiguous()
+        self.lengths = lengths
+        self.offsets_host = off
+        self.offsets = torch.as_tensor(off, dtype=i64, device=self.X.device)
+
+    @classmethod
+    def from_list(cls, utts, device=None):
+        return cls(list(utts), [len(u) for u in utts], device=device)
+
+    def __len__(self):           # number of frames, like len(minibatch_data) in the reference
+        return int(self.offsets_host[-1])
+
+    @property
+    def n_utts(self):
+        return len(self.lengths)
+
+
+class WeightGroup:
+    """Dirichlet prior/posterior over the mixture weights of a run of pdfs with the same
+    number of components (one MixtureSet of a JointModelSet)."""
+
+    def __init__(self, pdf_start, n_pdfs, n_comp, prior_conc, post_conc):
+        self.pdf_start, self.n_pdfs, self.n_comp = pdf_start, n_pdfs, n_comp
+        self.prior, self.post = prior_conc, post_conc      # [n_pdfs, n_comp] fp32 on device
+
+
+class EmissionParams:
+    """Flat device view of the emission model: M diagonal Gaussians (Normal-Gamma prior and
+    posterior), grouped into Kp pdfs by `comp_off`, with optional mixture-weight groups."""
+
+    def __init__(self, prior, post, comp_off=None, weight_groups=()):
+        self.prior = tuple(prior)      # (mean [M,D], scale [M], shape [M], rates [M,D])
+        self.post = tuple(post)
+        self.M, self.D = self.post[0].shape
+        self.device = self.post[0].device
+        self.weight_groups = list(weight_groups)
+        if comp_off is None:
+            self.comp_off_host = np.arange(self.M + 1, dtype=np.int32)
+            self.comp_off = None
+            self.Kp = self.M
+        else:
+            self.comp_off_host = np.asarray(comp_off, dtype=np.int32)
+            self.Kp = len(self.comp_off_host) - 1
+            self.comp_off = torch.as_tensor(self.comp_off_host, dtype=i32, device=self.device)
+        self.has_mixtures = self.Kp != self.M
+        self.logw = torch.zeros(self.M, device=self.device, dtype=f32) if self.weight_groups else None
+
+    def refresh(self):
+        """(W, bias, ref) of the current posteriors."""
+        for g in self.weight_groups:
+            j0 = int(self.comp_off_host[g.pdf_start])
+            self.logw[j0:j0 + g.n_pdfs * g.n_comp] = ops.dirichlet_expected_logw(g.post).reshape(-1)
+        return ops.emission_prepare(*self.post, logw=self.logw)
+
+    def kl(self, out=None):
+        out = ops.normalgamma_kl(self.prior, self.post, out=out)
+        for g in self.weight_groups:
+            ops.dirichlet_kl(g.prior, g.post, out=out)
+        return out
+
+    def update(self, acc, stats_scale, lrate):
+        """Natural-gradient step of every parameter from the accumulated statistics."""
+        if self.weight_groups:
+            wst = ops.mixture_weight_stats(acc, self.D, comp_off=self.comp_off, Kp=self.Kp)
+            for g in self.weight_groups:
+                j0 = int(self.comp_off_host[g.pdf_start])
+                gacc = wst[j0:j0 + g.n_pdfs * g.n_comp]
+                ops.dirichlet_update(g.prior, g.post, gacc, stats_scale, lrate)
+        ops.normalgamma_update(self.prior, self.post, acc, stats_scale, lrate)
+
+
+class _StageTimer:
+    """CUDA events around one kernel stage on the current stream (only when profiling)."""
+
+    def __init__(self, profile, name):
+        self.profile, self.name = profile, name
+
+    def __enter__(self):
+        if self.profile is not None:
+            self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.ev[0].record()
+
+    def __exit__(self, *exc):
+        if self.profile is not None:
+            self.ev[1].record()
+            self.profile.setdefault(self.name, []).append(self.ev)
+        return False
+
+
+class VBEngine:
+    """One process per GPU; `utts` is this rank's shard and stays resident in HBM."""
+
+    def __init__(self, emission, plan, utts, datasize=None, scale=1.0, lrate=1.0, chunk_frames=None,
+                 process_group=None, distributed=None):
+        self.em, self.plan, self.utts = emission, plan, utts
+        self.scale, self.lrate = float(scale), float(lrate)
+        self.dev = emission.device
+        self.pg = process_group
+        if distributed is None:
+            distributed = torch.distributed.is_available() and torch.distributed.is_initialized()
+        self.distributed = distributed
+        M, D = emission.M, emission.D
+        self.Q = 2 * D + 2
+        # flat reduction buffer: [acc (M*Q) | sum_u (N/T_u) ell_u | sum_u T_u | n_utts | sum_u ell_u]
+        self.flat = torch.zeros(M * self.Q + 4, device=self.dev, dtype=f64)
+        self.acc = self.flat[:M * self.Q].view(M, self.Q)
+        self.extras = self.flat[M * self.Q:]
+        self.kl = torch.zeros(1, device=self.dev, dtype=f64)
+        self.local_frames = len(utts)
+        self.datasize = float(datasize) if datasize is not None else None
+        lens = torch.as_tensor(utts.lengths, dtype=f64, device=self.dev)
+        self.utt_len = lens
+        self.inv_len = torch.where(lens > 0, 1.0 / lens.clamp(min=1.0), torch.zeros_like(lens))
+        self.profile = None      # optional {stage: [(start_event, end_event), ...]} (bench.py)
+        self._chunks = self._make_chunks(chunk_frames)
+        nmax = max((c[3] for c in self._chunks), default=0)
+        Kp = emission.Kp
+        self.pdf_llh = torch.empty(nmax, Kp, device=self.dev, dtype=f32)
+        self.pdf_post = (torch.empty if plan.info['map_identity'] and plan.n_states == Kp else torch.zeros)(
+            nmax, Kp, device=self.dev, dtype=f32)
+        self.comp_llh = torch.empty(nmax, M, device=self.dev, dtype=f32) if emission.has_mixtures else None
+        self.ws = torch.empty((plan.workspace_bytes(nmax) + 3) // 4, device=self.dev, dtype=f32)
+        self.frame_ref = torch.empty(nmax, device=self.dev, dtype=f32)
+        self.utt_ell = torch.zeros(utts.n_utts, device=self.dev, dtype=f64)
+        self.gpu_launches = 0
+
+    def _make_chunks(self, chunk_frames):
+        """Split the shard into runs of whole utterances of at most `chunk_frames` frames:
+        (utt_begin, utt_end, frame_begin, n_frames, offsets tensor rebased to the chunk)."""
+        off = self.utts.offsets_host
+        n = self.utts.n_utts
+        if chunk_frames is None:
+            chunk_frames = 1 << 62
+        chunks, u0 = [], 0
+        while u0 < n:
+            u1 = u0 + 1
+            while u1 < n and off[u1 + 1] - off[u0] <= chunk_frames:
+                u1 += 1
+            rel = torch.as_tensor(off[u0:u1 + 1] - off[u0], dtype=i64, device=self.dev)
+            chunks.append((u0, u1, int(off[u0]), int(off[u1] - off[u0]), rel))
+            u0 = u1
+        return chunks
+
+    def _stage(self, name):
+        return _StageTimer(self.profile, name)
+
+    # -- one VB iteration -----------------------------------------------------
+    def e_step(self):
+        """Accumulate statistics and ELBO terms of the local shard into `self.flat`."""
+        em, plan = self.em, self.plan
+        self.flat.zero_()
+        self.kl.zero_()
+        W, bias, ref = em.refresh()
+        em.kl(out=self.kl)
+        self.gpu_launches += 2 + 1 + 2 * len(em.weight_groups)
+        nonident = not (plan.info['map_identity'] and plan.n_states == em.Kp)
+        for (u0, u1, f0, nf, rel) in self._chunks:
+            if nf == 0:
+                continue
+            X = self.utts.X[f0:f0 + nf]
+            pdf_llh = self.pdf_llh[:nf]
+            pdf_post = self.pdf_post[:nf]
+            comp = self.comp_llh[:nf] if self.comp_llh is not None else None
+            with self._stage('KA_emission_llh'):
+                _, _, fref = ops.emission_llh(X, W, bias, ref, comp_off=em.comp_off, Kp=em.Kp, out=pdf_llh,
+                                              out_comp=comp, out_ref=self.frame_ref[:nf])
+            if nonident:
+                pdf_post.zero_()
+            with self._stage('KB_forward_backward'):
+                ops.hmm_forward_backward(plan, pdf_llh, fref, rel, scale=self.scale, workspace=self.ws,
+                                         out_pdf_post=pdf_post, out_utt_exp_llh=self.utt_ell[u0:u1])
+            with self._stage('KC_accumulate'):
+                ops.accumulate_stats(X, self.acc, pdf_post=pdf_post,
+                                     pdf_llh=pdf_llh if comp is not None else None, comp_llh=comp,
+                                     comp_off=em.comp_off if comp is not None else None, Kp=em.Kp)
+            self.gpu_launches += 3
+        # ELBO bookkeeping of the shard (objectives.py:176-190 summed as in accumulate.py:39-59)
+        n_local = float(self.local_frames)
+        self.extras[1] = n_local
+        self.extras[2] = float(self.utts.n_utts)
+        self.extras[3] = self.utt_ell.sum()
+        # sum_u ell_u / T_u; multiplied by the global datasize after the reduction
+        self.extras[0] = (self.utt_ell * self.inv_len).sum()
+
+    def reduce(self):
+        """The one exchange step: sum the flat statistics buffer over ranks (NCCL)."""
+        if self.distributed:
+            torch.distributed.all_reduce(self.flat, group=self.pg)
+
+    def m_step(self):
+        """Replicated on every rank from the reduced statistics (no broadcast needed).
+        Returns the summed ELBO as a device scalar (no host sync)."""
+        total_frames = self.extras[1]
+        n_utts = self.extras[2]
+        # python float for the kernel arguments would force a sync; stats_scale is known on the
+        # host because datasize and the frame counts are host-side constants of the run.
+        datasize = self.datasize if self.datasize is not None else self._global_frames()
+        stats_scale = datasize / self._global_frames()
+        elbo = datasize * self.extras[0] - n_utts * self.kl[0]
+        self.em.update(self.acc, stats_scale, self.lrate)
+        self.gpu_launches += 1 + (1 + len(self.em.weight_groups) if self.em.weight_groups else 0)
+        return elbo
+
+    def _global_frames(self):
+        if not hasattr(self, '_gframes'):
+            n = torch.tensor([float(self.local_frames)], device=self.dev, dtype=f64)
+            if self.distributed:
+                torch.distributed.all_reduce(n, group=self.pg)
+            self._gframes = float(n.item())
+        return self._gframes
+
+    def step(self):
+        """E-step + all-reduce + M-step; returns the summed ELBO (device fp64 scalar)."""
+        self._global_frames()
+        self.e_step()
+        self.reduce()
+        return self.m_step()
+
+    def elbo_per_frame(self, elbo):
+        """The figure `beer hmm update` logs (update.py:72): ELBO / (n_utts * datasize)."""
+        datasize = self.datasize if self.datasize is not None else self._global_frames()
+        return elbo / (self.extras[2] * datasize)

@@ -77,7 +77,8 @@ def emission_prepare(mean, scale, shape, rates, logw=None):
     return W, bias, ref
 
 
-def emission_llh(X, W, bias, ref, comp_off=None, Kp=None, want_comp=False, out=None):
+def emission_llh(X, W, bias, ref, comp_off=None, Kp=None, want_comp=False, out=None, out_comp=None,
+                 out_ref=None):
     """-> (pdf_llh [N,Kp], comp_llh [N,M] or None, frame_ref [N]); offset form."""
     lib = require_cuda()
     N, D = X.shape
@@ -85,8 +86,10 @@ def emission_llh(X, W, bias, ref, comp_off=None, Kp=None, want_comp=False, out=N
     if Kp is None:
         Kp = M if comp_off is None else comp_off.numel() - 1
     pdf_llh = out if out is not None else torch.empty(N, Kp, device=X.device, dtype=f32)
-    comp = torch.empty(N, M, device=X.device, dtype=f32) if want_comp else None
-    fref = torch.empty(N, device=X.device, dtype=f32)
+    comp = out_comp
+    if comp is None and want_comp:
+        comp = torch.empty(N, M, device=X.device, dtype=f32)
+    fref = out_ref if out_ref is not None else torch.empty(N, device=X.device, dtype=f32)
     _lib.check(lib.beer_emission_llh(_p(X, f32), N, D, _p(W, f32), _p(bias, f32), _p(ref, f32), M,
                                      _p(comp_off, i32, True), Kp, _p(pdf_llh, f32), pdf_llh.stride(0),
                                      _p(comp, f32, True), _p(fref), _stream()),
@@ -134,9 +137,11 @@ class GraphPlan:
 
 
 def hmm_forward_backward(plan, pdf_llh, frame_ref, utt_off, scale=1.0, want_state_post=False,
-                         want_pdf_post=True, want_frame_llh=False, want_logz=False, workspace=None):
+                         want_pdf_post=True, want_frame_llh=False, want_logz=False, workspace=None,
+                         out_pdf_post=None, out_utt_exp_llh=None):
     """Forward-backward for a ragged batch.  -> dict(state_post, pdf_post, frame_exp_llh,
-    utt_exp_llh (fp64), utt_logz (fp64))."""
+    utt_exp_llh (fp64), utt_logz (fp64)).  `out_pdf_post` must be zero-filled by the caller
+    when the graph's pdf map is not the identity (the kernel then scatter-adds)."""
     lib = require_cuda()
     N = pdf_llh.shape[0]
     n_utts = utt_off.numel() - 1
@@ -148,17 +153,18 @@ def hmm_forward_backward(plan, pdf_llh, frame_ref, utt_off, scale=1.0, want_stat
     if workspace is None or workspace.numel() * workspace.element_size() < nbytes:
         workspace = torch.empty((nbytes + 3) // 4, device=dev, dtype=f32)
     state_post = torch.empty(N, K, device=dev, dtype=f32) if want_state_post else None
-    pdf_post = None
-    if want_pdf_post:
+    pdf_post = out_pdf_post
+    if pdf_post is None and want_pdf_post:
         pdf_post = (torch.empty if plan.info['map_identity'] and Kp == K else torch.zeros)(
             N, Kp, device=dev, dtype=f32)
     frame = torch.empty(N, device=dev, dtype=f32) if want_frame_llh else None
-    utt_ell = torch.empty(n_utts, device=dev, dtype=f64)
+    utt_ell = out_utt_exp_llh if out_utt_exp_llh is not None else torch.empty(n_utts, device=dev, dtype=f64)
     utt_logz = torch.empty(n_utts, device=dev, dtype=f64) if want_logz else None
     _lib.check(lib.beer_hmm_forward_backward(
         plan._h, _p(pdf_llh, f32), pdf_llh.stride(0), _p(frame_ref, f32, True), _p(utt_off, i64), n_utts,
-        float(scale), _p(state_post, f32, True), _p(pdf_post, f32, True), Kp, _p(frame, f32, True),
-        _p(utt_ell), _p(utt_logz, f64, True), _p(workspace), _stream()), 'beer_hmm_forward_backward')
+        float(scale), _p(state_post, f32, True), _p(pdf_post, f32, True),
+        pdf_post.stride(0) if pdf_post is not None else 0, _p(frame, f32, True),
+        _p(utt_ell, f64), _p(utt_logz, f64, True), _p(workspace), _stream()), 'beer_hmm_forward_backward')
     return dict(state_post=state_post, pdf_post=pdf_post, frame_exp_llh=frame, utt_exp_llh=utt_ell,
                 utt_logz=utt_logz, workspace=workspace)
 

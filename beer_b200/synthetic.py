@@ -1,0 +1,92 @@
+"""Synthetic HMM-GMM workloads named by BASELINE.json: a phone-loop
+decoding graph of P left-to-right units and 40-d "fbank" frames sampled from it.
+
+Used by bench.py, __graft_entry__.smoke() and the tests; everything is seeded."""
+import numpy as np
+import torch
+
+from .graph import Graph
+
+__all__ = ['unit_graph', 'phone_loop_graph', 'sample_utterances', 'initial_normal_gamma', 'CONFIGS']
+
+# name -> (units, states per unit, Gaussians per state, dim, frames per utterance, utterances per GPU)
+CONFIGS = {
+    'cfg2': dict(n_units=25, n_states=4, n_comp=1, dim=40, n_frames=1000, n_utts=4096),
+    'cfg3': dict(n_units=250, n_states=4, n_comp=8, dim=40, n_frames=1000, n_utts=1250),
+}
+
+
+def unit_graph(n_states, first_pdf, self_loop=0.75):
+    """Left-to-right unit (recipes/aud/conf/hmm.yml:37-44 topology)."""
+    g = Graph()
+    states = [g.add_state(pdf_id=None)]
+    states += [g.add_state(pdf_id=first_pdf + i) for i in range(n_states)]
+    states.append(g.add_state(pdf_id=None))
+    g.start_state, g.end_state = states[0], states[-1]
+    g.add_arc(states[0], states[1], 1.0)
+    for i in range(1, n_states + 1):
+        g.add_arc(states[i], states[i], self_loop)
+        g.add_arc(states[i], states[i + 1], 1 - self_loop)
+    return g
+
+
+def phone_loop_graph(n_units, n_states=4, self_loop=0.75):
+    """Decoding graph start -> pivot -> {units} -> pivot -> end, every unit spliced in with
+    replace_state, the construction of beer/cli/subcommands/hmm/mkphoneloopgraph.py:28-77 +
+    mkdecodegraph.py:50-58.  Returns (CompiledGraph, start pdf ids, end pdf ids)."""
+    g = Graph()
+    g.start_state = g.add_state()
+    g.end_state = g.add_state()
+    pivot = g.add_state()
+    placeholders = [g.add_state() for _ in range(n_units)]
+    g.add_arc(g.start_state, pivot)
+    g.add_arc(pivot, g.end_state)
+    for s in placeholders:
+        g.add_arc(pivot, s)
+        g.add_arc(s, pivot)
+    g.normalize()
+    starts, ends = [], []
+    for u, s in enumerate(placeholders):
+        g.replace_state(s, unit_graph(n_states, u * n_states, self_loop))
+        starts.append(u * n_states)
+        ends.append((u + 1) * n_states - 1)
+    g.normalize()
+    return g.compile(), starts, ends
+
+
+def sample_utterances(graph, means, n_utts, n_frames, seed, device='cpu', noise=1.0):
+    """Sample a state path per utterance from `graph` and emit x_t = mu[pdf(s_t)] + noise * eps.
+    Returns an [n_utts * n_frames, D] fp32 tensor on `device` (utterances back to back)."""
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    init = graph.init_log_probs.double().exp().to(device)
+    trans = graph.trans_log_probs.double().exp().to(device)
+    init = (init / init.sum()).float()
+    trans = (trans / trans.sum(dim=1, keepdim=True)).float()
+    pdf = torch.as_tensor(graph.pdf_id_mapping, device=device)
+    means = torch.as_tensor(means, dtype=torch.float32, device=device)
+    D = means.shape[1]
+    state = torch.multinomial(init.expand(n_utts, -1), 1, generator=gen).squeeze(1)
+    X = torch.empty(n_utts, n_frames, D, device=device, dtype=torch.float32)
+    for t in range(n_frames):
+        if t > 0:
+            state = torch.multinomial(trans[state], 1, generator=gen).squeeze(1)
+        X[:, t] = means[pdf[state]]
+    X += noise * torch.randn(X.shape, generator=gen, device=device, dtype=torch.float32)
+    return X.reshape(n_utts * n_frames, D)
+
+
+def initial_normal_gamma(n_gauss, dim, seed, device='cpu', prior_strength=1.0, noise_std=1.0):
+    """Prior / initial posterior of NormalSet.create(mean=0, cov=1, ...) for diagonal
+    covariances (beer/models/normalset.py:42-54): returns two tuples
+    (mean [M,D], scale [M], shape [M], rates [M,D])."""
+    gen = torch.Generator(device='cpu')
+    gen.manual_seed(seed)
+    mean0 = torch.zeros(n_gauss, dim)
+    noise = torch.randn(n_gauss, dim, generator=gen) * noise_std
+    scale = torch.full((n_gauss,), float(prior_strength))
+    shape = torch.full((n_gauss,), float(prior_strength))
+    rates = torch.full((n_gauss, dim), float(prior_strength))
+    prior = tuple(t.to(device).contiguous() for t in (mean0, scale, shape, rates))
+    post = tuple(t.to(device).contiguous() for t in (mean0 + noise, scale.clone(), shape.clone(), rates.clone()))
+    return prior, post

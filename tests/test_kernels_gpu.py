@@ -258,6 +258,12 @@ def test_ragged_batch_equals_single(ops):
         if n == 0:
             assert r['utt_exp_llh'][i].item() == 0.0
             continue
-        want = O.hmm_estep(utts[i].astype(np.float64), post, None, graph(g))
+        with np.errstate(all='ignore'):
+            want = O.hmm_estep(utts[i].astype(np.float64), post, None, graph(g))
+        if np.isnan(want['gamma']).any():
+            # too short to reach a final state: the reference divides -inf by -inf (NaN,
+            # graph.py:306-307); the kernel reports zero posteriors instead
+            assert n < 4 and (gam[off[i]:off[i + 1]] == 0).all()
+            continue
         assert np.abs(gam[off[i]:off[i + 1]] - want['gamma']).max() <= 1e-5
         np.testing.assert_allclose(r['utt_exp_llh'][i].item(), want['exp_llh'].sum(), rtol=1e-6)
