@@ -21,6 +21,11 @@ SIGNATURES = {
     'beer_emission_prepare': (C.c_int, [c_ptr] * 5 + [C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
     'beer_emission_llh': (C.c_int, [c_ptr, C.c_int64, C.c_int, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr,
                                     C.c_int, c_ptr, C.c_int64, c_ptr, c_ptr, c_ptr]),
+    'beer_emission_tc_supported': (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    'beer_emission_tc_image_floats': (C.c_int64, [C.c_int, C.c_int, C.c_int]),
+    'beer_emission_tc_pack': (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
+    'beer_emission_llh_tc': (C.c_int, [c_ptr, C.c_int64, C.c_int, c_ptr, c_ptr, C.c_int, C.c_int, c_ptr,
+                                       C.c_int64, c_ptr, c_ptr, c_ptr]),
     'beer_graph_plan_create': (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int,
                                          C.POINTER(C.c_void_p)]),
     'beer_graph_plan_destroy': (None, [c_ptr]),

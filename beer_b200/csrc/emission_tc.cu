@@ -1,0 +1,468 @@
+// KA on the 5th-generation tensor cores (tcgen05 + TMEM), 3xTF32 split for fp32 accuracy.
+//
+//   D[frame, gaussian] = [x, -x^2/2]_hi . W_hi + [x, -x^2/2]_lo . W_hi + [x, -x^2/2]_hi . W_lo
+//
+// One CTA = 128 frames (UMMA M) x chunks of <= 128 Gaussians (UMMA N), K = 2D features.
+// Operands live in shared memory in the canonical no-swizzle K-major core-matrix layout
+// ([row/8][k/4][row%8][k%4], 128-byte core matrices).  The weight image is packed once per VB
+// iteration by beer_emission_tc_pack and streamed in with cp.async.bulk (TMA, 1-D); the
+// statistics tile is built by the worker warps from X (hi = top 19 bits, lo = x - hi).
+// Accumulators are fp32 in TMEM (double buffered); the epilogue reads them back with
+// tcgen05.ld, adds the bias, takes the log-sum-exp over the C components of each pdf and
+// stores the offset-form llh.
+//
+// Warp roles: warps 0-3 = workers (tile builder + epilogue, one frame row per thread),
+// warp 4 = MMA issuer (one elected lane) + TMEM allocator, warp 5 = weight-image producer.
+//
+// Reference semantics: beer/dists/normalgamma.py:55-59, beer/models/mixtureset.py:85-98.
+#include "common.cuh"
+#include "../../include/beer_b200.h"
+
+namespace beer {
+namespace tc {
+
+constexpr int FR = 128;        // frames per tile (UMMA M)
+constexpr int NB_MAX = 128;    // Gaussians per chunk (UMMA N)
+constexpr int WORKERS = 128;
+constexpr int THREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t addr = smem_u32(bar), ok;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, tf32 inputs, fp32 accumulate.
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(
+            d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor: no swizzle, K-major, version 1 (sm_100).
+//   core matrix = 8 rows x 16 bytes, contiguous (128 B)
+//   LBO = byte stride between core matrices adjacent in K, SBO = between 8-row groups
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+// offset (in floats) of element (row, k) inside a [rows x Kd] core-matrix image
+__host__ __device__ __forceinline__ int img_off(int row, int k, int Kd) {
+    return (row >> 3) * (Kd * 8) + (k >> 2) * 32 + (row & 7) * 4 + (k & 3);
+}
+
+struct Args {
+    const float* X;
+    int64_t N;
+    const float* img;    // [n_chunks][2][NB * Kd] packed weights (hi image, lo image)
+    const float* bias;   // [n_chunks * NB], zero padded
+    const float* ref;    // [D + 1]
+    int M, C, Kp, NB, n_chunks, stages;
+    float* pdf_llh;
+    int64_t ld;
+    float* comp_llh;
+    float* frame_ref;
+};
+
+struct Barriers {
+    uint64_t a_ready, a_free;
+    uint64_t b_full[2], b_empty[2];
+    uint64_t t_full[2], t_empty[2];
+    uint32_t tmem_base;
+};
+
+template <int D4>
+__global__ void __launch_bounds__(THREADS, 1) emission_tc_kernel(Args a) {
+    constexpr int D = 4 * D4, Kd = 2 * D, KSTEPS = Kd / 8;
+    constexpr uint32_t LBO = 128, SBO = (Kd / 4) * 128;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    float* A_hi = reinterpret_cast<float*>(smem_raw);
+    float* A_lo = A_hi + FR * Kd;
+    float* Bst = A_lo + FR * Kd;                           // stages x [hi image | lo image]
+    const int b_stage_floats = 2 * a.NB * Kd;
+    float* s_bias = Bst + (size_t)a.stages * b_stage_floats;  // [n_chunks * NB] (or NB when streaming)
+    const int bias_floats = (a.stages == 1) ? a.NB : a.n_chunks * a.NB;
+    float* s_ref = s_bias + bias_floats;                   // [D + 1]
+    Barriers* bars = reinterpret_cast<Barriers*>(s_ref + ((D + 1 + 3) & ~3));
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t n_tiles = (a.N + FR - 1) / FR;
+    const uint32_t tmem_cols = (2 * a.NB <= 32) ? 32 : (2 * a.NB <= 64 ? 64 : (2 * a.NB <= 128 ? 128 : 256));
+
+    if (tid == 0) {
+        mbar_init(&bars->a_ready, WORKERS);
+        mbar_init(&bars->a_free, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars->b_full[i], 1);
+            mbar_init(&bars->b_empty[i], 1);
+            mbar_init(&bars->t_full[i], 1);
+            mbar_init(&bars->t_empty[i], WORKERS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) tmem_alloc(&bars->tmem_base, tmem_cols);
+    for (int i = tid; i < bias_floats; i += THREADS) s_bias[i] = a.bias[i];
+    for (int i = tid; i <= D; i += THREADS) s_ref[i] = a.ref[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 5) {
+        // ------------------------- weight-image producer -------------------------
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)b_stage_floats * 4u;
+            if (a.stages == 1) {
+                // a single chunk stays resident for the whole kernel
+                mbar_arrive_expect_tx(&bars->b_full[0], bytes);
+                bulk_g2s(Bst, a.img, bytes, &bars->b_full[0]);
+            } else {
+                uint32_t it = 0;
+                for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+                    for (int c = 0; c < a.n_chunks; ++c, ++it) {
+                        const int st = it & 1;
+                        mbar_wait(&bars->b_empty[st], ((it >> 1) & 1) ^ 1);
+                        mbar_arrive_expect_tx(&bars->b_full[st], bytes);
+                        bulk_g2s(Bst + (size_t)st * b_stage_floats, a.img + (size_t)c * b_stage_floats, bytes,
+                                 &bars->b_full[st]);
+                    }
+            }
+        }
+    } else if (warp == 4) {
+        // ------------------------------ MMA issuer -------------------------------
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=tf32, both K-major, N = NB, M = 128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.NB >> 3) << 17) |
+                                   ((uint32_t)(FR >> 4) << 24);
+            const uint32_t a_hi = smem_u32(A_hi), a_lo = smem_u32(A_lo);
+            uint32_t it = 0, tile_it = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+                mbar_wait(&bars->a_ready, tile_it & 1);
+                for (int c = 0; c < a.n_chunks; ++c, ++it) {
+                    const int st = (a.stages == 1) ? 0 : (it & 1);
+                    const int buf = it & 1;
+                    if (a.stages == 1) {
+                        if (it == 0) mbar_wait(&bars->b_full[0], 0);
+                    } else {
+                        mbar_wait(&bars->b_full[st], (it >> 1) & 1);
+                    }
+                    mbar_wait(&bars->t_empty[buf], ((it >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t b_hi = smem_u32(Bst + (size_t)st * b_stage_floats);
+                    const uint32_t b_lo = b_hi + (uint32_t)a.NB * Kd * 4u;
+                    const uint32_t d_tmem = tmem_base + (uint32_t)buf * (uint32_t)a.NB;
+#pragma unroll 1
+                    for (int s = 0; s < KSTEPS; ++s) {
+                        const uint32_t ko = (uint32_t)s * 256u;
+                        const uint64_t dah = make_desc(a_hi + ko, LBO, SBO), dal = make_desc(a_lo + ko, LBO, SBO);
+                        const uint64_t dbh = make_desc(b_hi + ko, LBO, SBO), dbl = make_desc(b_lo + ko, LBO, SBO);
+                        umma_tf32(d_tmem, dah, dbh, idesc, s > 0);
+                        umma_tf32(d_tmem, dal, dbh, idesc, 1);
+                        umma_tf32(d_tmem, dah, dbl, idesc, 1);
+                    }
+                    umma_commit(&bars->t_full[buf]);
+                    if (a.stages > 1) umma_commit(&bars->b_empty[st]);
+                }
+                umma_commit(&bars->a_free);
+            }
+        }
+    } else {
+        // ------------------------ workers: build tile, epilogue ------------------
+        const int r = tid;  // frame row inside the tile, also the TMEM lane
+        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+        uint32_t it = 0, tile_it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+            const int64_t t = tile * FR + r;
+            const bool valid = t < a.N;
+            float4 xv[D4];
+            const float4* xrow = reinterpret_cast<const float4*>(a.X + (size_t)(valid ? t : 0) * D);
+#pragma unroll
+            for (int c = 0; c < D4; ++c) xv[c] = valid ? __ldg(xrow + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            // the previous tile's MMAs must have finished reading A
+            mbar_wait(&bars->a_free, (tile_it & 1) ^ 1);
+            float rt = 0.f;
+            const int rbase = (r >> 3) * (Kd * 8) + (r & 7) * 4;
+#pragma unroll
+            for (int c = 0; c < D4; ++c) {
+                const float x[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w};
+                float h[4], l[4], qh[4], ql[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    h[e] = __uint_as_float(__float_as_uint(x[e]) & 0xffffe000u);
+                    l[e] = x[e] - h[e];
+                    const float q = -0.5f * x[e] * x[e];
+                    qh[e] = __uint_as_float(__float_as_uint(q) & 0xffffe000u);
+                    ql[e] = q - qh[e];
+                    rt = fmaf(q, s_ref[4 * c + e], rt);
+                }
+                *reinterpret_cast<float4*>(A_hi + rbase + c * 32) = make_float4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<float4*>(A_lo + rbase + c * 32) = make_float4(l[0], l[1], l[2], l[3]);
+                *reinterpret_cast<float4*>(A_hi + rbase + (D4 + c) * 32) = make_float4(qh[0], qh[1], qh[2], qh[3]);
+                *reinterpret_cast<float4*>(A_lo + rbase + (D4 + c) * 32) = make_float4(ql[0], ql[1], ql[2], ql[3]);
+            }
+            if (valid && a.frame_ref != nullptr) a.frame_ref[t] = rt + s_ref[D];
+            fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor core
+            mbar_arrive(&bars->a_ready);
+
+            for (int c = 0; c < a.n_chunks; ++c, ++it) {
+                const int buf = it & 1;
+                mbar_wait(&bars->t_full[buf], (it >> 1) & 1);
+                tc_fence_after();
+                const int g0 = c * a.NB;
+                const float* bias_c = s_bias + ((a.stages == 1) ? 0 : g0);
+                const uint32_t taddr = tmem_base + lane_addr + (uint32_t)buf * (uint32_t)a.NB;
+                for (int p = 0; p < a.NB; p += 16) {
+                    float v[16];
+                    tmem_ld16(taddr + (uint32_t)p, v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] += bias_c[p + i];
+                    if (valid) {
+                        const int g = g0 + p;
+                        if (a.comp_llh != nullptr) {
+                            float* dst = a.comp_llh + (size_t)t * a.M + g;
+                            if (g + 16 <= a.M && (a.M & 3) == 0) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q)
+                                    reinterpret_cast<float4*>(dst)[q] =
+                                        make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i)
+                                    if (g + i < a.M) dst[i] = v[i];
+                            }
+                        }
+                        // log-sum-exp over the C components of each pdf (C divides 16)
+                        const int C = a.C;
+                        float o[16];
+                        int no;
+                        if (C == 1) {
+                            no = 16;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) o[i] = v[i];
+                        } else {
+                            no = 16 / C;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) o[i] = 0.f;
+#pragma unroll
+                            for (int lg = 1; lg <= 4; ++lg) {
+                                if (C == (1 << lg)) {
+                                    const int CC = 1 << lg;
+#pragma unroll
+                                    for (int k = 0; k < 16 / CC; ++k) {
+                                        float m = v[k * CC];
+#pragma unroll
+                                        for (int j = 1; j < CC; ++j) m = fmaxf(m, v[k * CC + j]);
+                                        float s = 0.f;
+#pragma unroll
+                                        for (int j = 0; j < CC; ++j) s += __expf(v[k * CC + j] - m);
+                                        o[k] = m + __logf(s);
+                                    }
+                                }
+                            }
+                        }
+                        const int k0 = g / C;
+                        float* dst = a.pdf_llh + (size_t)t * a.ld + k0;
+                        if (no == 16 && k0 + 16 <= a.Kp && (a.ld & 3) == 0) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                reinterpret_cast<float4*>(dst)[q] =
+                                    make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (i < no && k0 + i < a.Kp) dst[i] = o[i];
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&bars->t_empty[buf]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// Pack W [M, 2D] + bias [M] into per-chunk core-matrix images (hi / lo split).
+__global__ void emission_tc_pack_kernel(const float* __restrict__ W, const float* __restrict__ bias, int M, int D,
+                                        int NB, int n_chunks, float* __restrict__ img, float* __restrict__ bias_pad) {
+    const int Kd = 2 * D;
+    const int per_chunk = 2 * NB * Kd;
+    const int64_t total = (int64_t)n_chunks * NB * Kd;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(e / (NB * Kd));
+        int rem = (int)(e - (int64_t)c * NB * Kd);
+        int n = rem / Kd, k = rem - n * Kd;
+        int g = c * NB + n;
+        float w = (g < M) ? W[(size_t)g * Kd + k] : 0.f;
+        float hi = __uint_as_float(__float_as_uint(w) & 0xffffe000u);
+        float lo = w - hi;
+        float* base = img + (size_t)c * per_chunk;
+        base[img_off(n, k, Kd)] = hi;
+        base[NB * Kd + img_off(n, k, Kd)] = lo;
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_chunks * NB; i += gridDim.x * blockDim.x)
+        bias_pad[i] = (i < M) ? bias[i] : 0.f;
+}
+
+struct Geometry { int NB, n_chunks, stages; };
+
+static bool geometry(int M, int D, int C, Geometry* g) {
+    if (D % 4 != 0) return false;
+    int d4 = D / 4;
+    if (!(d4 == 5 || d4 == 10 || d4 == 16 || d4 == 20)) return false;
+    if (!(C == 1 || C == 2 || C == 4 || C == 8 || C == 16)) return false;
+    if (M <= NB_MAX) {
+        g->NB = (M + 15) / 16 * 16;
+        g->n_chunks = 1;
+        g->stages = 1;
+    } else {
+        g->NB = 64;
+        g->n_chunks = (M + 63) / 64;
+        g->stages = 2;
+    }
+    return true;
+}
+
+static size_t smem_bytes(int D, const Geometry& g) {
+    int Kd = 2 * D;
+    size_t f = (size_t)2 * FR * Kd + (size_t)g.stages * 2 * g.NB * Kd +
+               (size_t)(g.stages == 1 ? g.NB : g.n_chunks * g.NB) + ((D + 1 + 3) & ~3);
+    return f * 4 + sizeof(Barriers) + 1024;
+}
+
+template <int D4>
+static int launch(const Args& a, const Geometry& g, cudaStream_t st) {
+    size_t smem = smem_bytes(4 * D4, g);
+    if (smem > 227 * 1024) return BEER_ERR_UNSUPPORTED;
+    static bool attr_set = false;
+    if (!attr_set) {
+        BEER_CUDA_TRY(cudaFuncSetAttribute(emission_tc_kernel<D4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           227 * 1024));
+        attr_set = true;
+    }
+    int64_t n_tiles = (a.N + FR - 1) / FR;
+    int grid = (int)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
+    emission_tc_kernel<D4><<<grid, THREADS, smem, st>>>(a);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
+}  // namespace tc
+}  // namespace beer
+
+using namespace beer;
+
+extern "C" {
+
+int beer_emission_tc_supported(int M, int D, int C) {
+    tc::Geometry g;
+    if (M <= 0 || D <= 0 || C <= 0 || M % C != 0) return 0;
+    if (!tc::geometry(M, D, C, &g)) return 0;
+    return tc::smem_bytes(D, g) <= 227 * 1024 ? 1 : 0;
+}
+
+int64_t beer_emission_tc_image_floats(int M, int D, int C) {
+    tc::Geometry g;
+    if (M <= 0 || D <= 0 || C <= 0 || !tc::geometry(M, D, C, &g)) return BEER_ERR_UNSUPPORTED;
+    return (int64_t)g.n_chunks * (2 * g.NB * 2 * D + g.NB);
+}
+
+int beer_emission_tc_pack(const float* W, const float* bias, int M, int D, int C, float* image, void* stream) {
+    tc::Geometry g;
+    if (!W || !bias || !image || M <= 0 || D <= 0 || !tc::geometry(M, D, C, &g)) return BEER_ERR_UNSUPPORTED;
+    float* bias_pad = image + (size_t)g.n_chunks * 2 * g.NB * 2 * D;
+    int64_t total = (int64_t)g.n_chunks * g.NB * 2 * D;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 1184) blocks = 1184;
+    tc::emission_tc_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(W, bias, M, D, g.NB, g.n_chunks, image,
+                                                                          bias_pad);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
+int beer_emission_llh_tc(const float* X, int64_t N, int D, const float* image, const float* ref, int M, int C,
+                         float* pdf_llh, int64_t ld_pdf, float* comp_llh, float* frame_ref, void* stream) {
+    tc::Geometry g;
+    if (!X || !image || !ref || !pdf_llh || N < 0 || M <= 0 || C <= 0 || M % C != 0) return BEER_ERR_ARG;
+    if (!tc::geometry(M, D, C, &g)) return BEER_ERR_UNSUPPORTED;
+    if (ld_pdf < M / C) return BEER_ERR_ARG;
+    if (((uintptr_t)X & 15) != 0 || ((uintptr_t)image & 15) != 0) return BEER_ERR_ARG;
+    if (N == 0) return BEER_OK;
+    tc::Args a;
+    a.X = X; a.N = N; a.img = image;
+    a.bias = image + (size_t)g.n_chunks * 2 * g.NB * 2 * D;
+    a.ref = ref; a.M = M; a.C = C; a.Kp = M / C; a.NB = g.NB; a.n_chunks = g.n_chunks; a.stages = g.stages;
+    a.pdf_llh = pdf_llh; a.ld = ld_pdf; a.comp_llh = comp_llh; a.frame_ref = frame_ref;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (D / 4) {
+        case 5: return tc::launch<5>(a, g, st);
+        case 10: return tc::launch<10>(a, g, st);
+        case 16: return tc::launch<16>(a, g, st);
+        case 20: return tc::launch<20>(a, g, st);
+    }
+    return BEER_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

@@ -97,6 +97,39 @@ def emission_llh(X, W, bias, ref, comp_off=None, Kp=None, want_comp=False, out=N
     return pdf_llh, comp, fref
 
 
+def emission_tc_supported(M, D, C):
+    return bool(_lib.load().beer_emission_tc_supported(int(M), int(D), int(C)))
+
+
+def emission_tc_pack(W, bias, C, out=None):
+    """Pack (W, bias) into the tensor-core weight image (hi/lo core-matrix layout)."""
+    lib = require_cuda()
+    M, D = W.shape[0], W.shape[1] // 2
+    n = int(lib.beer_emission_tc_image_floats(M, D, int(C)))
+    if n < 0:
+        raise _lib.BeerB200Error('no tensor-core emission path for this shape')
+    img = out if out is not None else torch.empty(n, device=W.device, dtype=f32)
+    _lib.check(lib.beer_emission_tc_pack(_p(W, f32), _p(bias, f32), M, D, int(C), _p(img, f32), _stream()),
+               'beer_emission_tc_pack')
+    return img
+
+
+def emission_llh_tc(X, image, ref, M, C, want_comp=False, out=None, out_comp=None, out_ref=None):
+    """tcgen05 version of emission_llh (uniform C components per pdf)."""
+    lib = require_cuda()
+    N, D = X.shape
+    Kp = M // C
+    pdf_llh = out if out is not None else torch.empty(N, Kp, device=X.device, dtype=f32)
+    comp = out_comp
+    if comp is None and want_comp:
+        comp = torch.empty(N, M, device=X.device, dtype=f32)
+    fref = out_ref if out_ref is not None else torch.empty(N, device=X.device, dtype=f32)
+    _lib.check(lib.beer_emission_llh_tc(_p(X, f32), N, D, _p(image, f32), _p(ref, f32), M, int(C),
+                                        _p(pdf_llh, f32), pdf_llh.stride(0), _p(comp, f32, True), _p(fref),
+                                        _stream()), 'beer_emission_llh_tc')
+    return pdf_llh, comp, fref
+
+
 # ---------------------------------------------------------------------------
 # graph plan
 # ---------------------------------------------------------------------------

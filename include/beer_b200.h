@@ -93,6 +93,21 @@ BEER_API int beer_emission_llh(const float* X, int64_t N, int D, const float* W,
                       const float* ref, int M, const int32_t* comp_off, int Kp, float* pdf_llh,
                       int64_t ld_pdf, float* comp_llh, float* frame_ref, void* stream);
 
+/* KA on the tensor cores (tcgen05 + TMEM, 3xTF32 split, fp32 accumulate): same result
+ * contract as beer_emission_llh for models with a uniform number C of Gaussians per pdf
+ * (C in {1,2,4,8,16}) and D in {20, 40}.  The weights are packed once per VB iteration:
+ *   beer_emission_tc_supported(M, D, C)      -> 1 if this shape has a tensor-core path
+ *   beer_emission_tc_image_floats(M, D, C)   -> floats of the packed image buffer
+ *   beer_emission_tc_pack(W, bias, ...)      -> image  (W, bias from beer_emission_prepare)
+ *   beer_emission_llh_tc(X, ..., image, ref) -> pdf_llh / comp_llh / frame_ref as above. */
+BEER_API int beer_emission_tc_supported(int M, int D, int C);
+BEER_API int64_t beer_emission_tc_image_floats(int M, int D, int C);
+BEER_API int beer_emission_tc_pack(const float* W, const float* bias, int M, int D, int C, float* image,
+                                   void* stream);
+BEER_API int beer_emission_llh_tc(const float* X, int64_t N, int D, const float* image, const float* ref, int M,
+                                  int C, float* pdf_llh, int64_t ld_pdf, float* comp_llh, float* frame_ref,
+                                  void* stream);
+
 /* Graph plan: device-resident sparse form of a CompiledGraph
  * (beer/graph.py:243-268: init_log_probs[K], final_log_probs[K], dense
  * trans_log_probs[K,K], pdf_id_mapping[K]).  Host pointers in, opaque handle out.
