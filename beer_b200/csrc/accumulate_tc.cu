@@ -1,0 +1,404 @@
+// KC on the 5th-generation tensor cores (tcgen05 + TMEM), 3xTF32 split for fp32 accuracy.
+//
+//   acc[j, :] += sum_t w_tj [x_t, x_t^2, 1]        w_tj = g_t,pdf(j) * r_tj
+//
+// A tall-skinny (M x T).(T x (2D+1)) contraction whose reduction dimension is time: both
+// operands are stored frame-major in HBM and are transposed while they are staged.  One CTA owns a tile of
+// 128 Gaussians (UMMA M) and a contiguous range of frames.  The fp32 accumulation in TMEM
+// truncates (measured: sums come out ~1e-7 low per 24 accumulations), so a TMEM accumulator
+// only ever holds ONE stage (64 frames); the stage results are drained into round-to-nearest
+// register sums (double-buffered TMEM, so the drain overlaps the next stage's MMAs) and the
+// CTA flushes once with fp64 atomics.
+//
+//   D[gauss, feat] += W_hi^T S_hi + W_lo^T S_hi + W_hi^T S_lo     (K = 8 frames per MMA)
+//
+// Warp roles: warps 0-7 = producers (global -> registers -> hi/lo split -> shared memory in
+// the canonical no-swizzle K-major core-matrix layout, i.e. transposed on the way: tf32
+// operands with the MN-major descriptor bit came back as zeros on B200; 2-stage ring, loads of
+// the next stage are in flight while the current one is split) and epilogue; warp 8 = MMA
+// issuer + TMEM allocator.  The count column (sum_t w) rides along as a constant-one feature.
+//
+// Reference semantics: beer/models/mixtureset.py:100-112, beer/models/normalset.py:121-123.
+#include <type_traits>
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "../../include/beer_b200.h"
+
+namespace beer {
+namespace kctc {
+
+using namespace tcu;
+
+constexpr int GM = 128;         // Gaussians per tile (UMMA M)
+constexpr int PRODUCERS = 256;
+constexpr int THREADS = PRODUCERS + 32;
+constexpr int MAX_STAGES = 4;
+
+struct Args {
+    const float* X;
+    int64_t N;
+    const float* pdf_post;
+    int64_t ld_post;
+    const float* pdf_llh;
+    int64_t ld_pdf;
+    const float* comp_llh;
+    const int32_t* comp_off;
+    int Kp, M, C;
+    double* acc;
+    int n_gtiles;
+    int64_t frames_per_cta;
+};
+
+struct Barriers {
+    uint64_t full[MAX_STAGES], empty[MAX_STAGES];   // shared-memory stages: producers <-> MMA
+    uint64_t tfull[2], tempty[2];           // TMEM accumulator buffers: MMA <-> drain
+    uint32_t tmem_base;
+};
+
+// D4 = D / 4; KF = frames per stage (multiple of 8); ST = shared-memory stages
+template <int D4, int KF, int ST>
+struct Cfg {
+    static constexpr int STAGES = ST;
+    static constexpr int D = 4 * D4;
+    static constexpr int NB = (2 * D + 1 + 15) / 16 * 16;  // [x | x^2 | 1 0 0 ...], UMMA N % 16 == 0 at M = 128
+    static constexpr int KG = KF / 8;            // K-groups (MMAs per pass) per stage
+    static constexpr int A_FLOATS = KF * GM;     // one A image (hi or lo)
+    static constexpr int B_FLOATS = KF * NB;
+    static constexpr int STAGE_FLOATS = 2 * A_FLOATS + 2 * B_FLOATS;
+    static constexpr int BU = ((KF / 4) * D + PRODUCERS - 1) / PRODUCERS;  // B units (4 frames x 1 feature) per thread
+    static constexpr int NCH = NB / 16;          // 16-column chunks of the accumulator
+    static constexpr int MYCH = (NCH + 1) / 2;   // chunks drained by one thread (two warps share a row)
+    static constexpr uint32_t TMEM_COLS = 2 * NB <= 64 ? 64 : (2 * NB <= 128 ? 128 : (2 * NB <= 256 ? 256 : 512));
+    // running sums across tiles: fp64 registers when they fit, fp32 (round-to-nearest) otherwise
+    using acc_t = typename std::conditional<(MYCH <= 3), double, float>::type;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_FLOATS * 4 + GM * 4 + sizeof(Barriers) + 1024;
+};
+
+template <int D4, int KF, int ST, bool MIX>
+__global__ void __launch_bounds__(THREADS, 1) accumulate_tc_kernel(Args a) {
+    using C = Cfg<D4, KF, ST>;
+    constexpr int D = C::D, NB = C::NB, KG = C::KG, STAGES = ST;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    float* stage_base = reinterpret_cast<float*>(smem_raw);
+    int* s_pdf = reinterpret_cast<int*>(stage_base + (size_t)STAGES * C::STAGE_FLOATS);
+    Barriers* bars = reinterpret_cast<Barriers*>(s_pdf + GM);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int gtile = blockIdx.x % a.n_gtiles;
+    const int64_t chunk = blockIdx.x / a.n_gtiles;
+    const int g0 = gtile * GM;
+    const int ng = min(GM, a.M - g0);
+    const int64_t f_begin = chunk * a.frames_per_cta;
+    const int64_t f_end = min(a.N, f_begin + a.frames_per_cta);
+    const int n_tiles = (f_end > f_begin) ? (int)((f_end - f_begin + KF - 1) / KF) : 0;
+
+    if (tid == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&bars->full[i], PRODUCERS);
+            mbar_init(&bars->empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars->tfull[i], 1);
+            mbar_init(&bars->tempty[i], PRODUCERS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == PRODUCERS / 32) tmem_alloc(&bars->tmem_base, C::TMEM_COLS);
+    // zero every image once: padded Gaussians / features stay zero for the whole kernel
+    for (int i = tid; i < STAGES * C::STAGE_FLOATS / 4; i += THREADS)
+        reinterpret_cast<float4*>(stage_base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // pdf of every Gaussian of the tile
+    for (int g = tid; g < GM; g += THREADS) {
+        int k = 0;
+        if (g < ng) {
+            int j = g0 + g;
+            if (a.comp_off == nullptr) {
+                k = j / a.C;
+            } else {
+                int lo = 0, hi = a.Kp;  // last k with comp_off[k] <= j
+                while (hi - lo > 1) {
+                    int mid = (lo + hi) >> 1;
+                    if (a.comp_off[mid] <= j) lo = mid; else hi = mid;
+                }
+                k = lo;
+            }
+        }
+        s_pdf[g] = k;
+    }
+    __syncthreads();
+    // the constant-one feature (count column) of the hi images
+    for (int i = tid; i < STAGES * KF; i += THREADS) {
+        int st = i / KF, f = i - st * KF;
+        float* b_hi = stage_base + (size_t)st * C::STAGE_FLOATS + 2 * C::A_FLOATS;
+        b_hi[((2 * D) >> 3) * (KF * 8) + (f >> 2) * 32 + ((2 * D) & 7) * 4 + (f & 3)] = 1.f;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == PRODUCERS / 32) {
+        // ------------------------------ MMA issuer -------------------------------
+        if (lane == 0 && n_tiles > 0) {
+            // D = f32, A = B = tf32, both K-major (K = frames), N = NB, M = 128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NB >> 3) << 17) |
+                                   ((uint32_t)(GM >> 4) << 24);
+            constexpr uint32_t LBO = 128, SBO = (KF / 4) * 128;
+            for (int it = 0; it < n_tiles; ++it) {
+                const int st = it % STAGES;
+                const int buf = it & 1;
+                mbar_wait(&bars->full[st], (it / STAGES) & 1);
+                mbar_wait(&bars->tempty[buf], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * NB);
+                const uint32_t a_hi = smem_u32(stage_base + (size_t)st * C::STAGE_FLOATS);
+                const uint32_t a_lo = a_hi + C::A_FLOATS * 4u;
+                const uint32_t b_hi = a_lo + C::A_FLOATS * 4u;
+                const uint32_t b_lo = b_hi + C::B_FLOATS * 4u;
+#pragma unroll 1
+                for (int ks = 0; ks < KG; ++ks) {
+                    const uint32_t ko = (uint32_t)ks * 256u;   // 8 frames = two 16-byte core-matrix columns
+                    const uint64_t dah = make_desc(a_hi + ko, LBO, SBO), dal = make_desc(a_lo + ko, LBO, SBO);
+                    const uint64_t dbh = make_desc(b_hi + ko, LBO, SBO), dbl = make_desc(b_lo + ko, LBO, SBO);
+                    // the TMEM accumulation truncates: keep it short (KF frames), sum tiles in registers
+                    umma_tf32(d_tmem, dah, dbh, idesc, ks != 0);
+                    umma_tf32(d_tmem, dal, dbh, idesc, 1);
+                    umma_tf32(d_tmem, dah, dbl, idesc, 1);
+                }
+                umma_commit(&bars->empty[st]);
+                umma_commit(&bars->tfull[buf]);
+            }
+        }
+    } else {
+        // ------------------------------ producers --------------------------------
+        // The operands are frame-major in HBM but K-major (frames contiguous) for the MMA: a
+        // thread gathers 4 consecutive frames of ONE Gaussian / feature (each load instruction is
+        // coalesced across the warp) and writes them as one 16-byte core-matrix row.
+        const int gl = tid & (GM - 1);       // Gaussian (local) of this thread's A cells
+        const int fq0 = tid >> 7;            // first frame quad; quads fq0, fq0 + 2, ...
+        const bool a_active = gl < ng;
+        const int kpdf = s_pdf[gl];
+        constexpr int AU = KF / 8;           // A units (frame quads) per thread
+        const int a_row = (gl >> 3) * (KF * 8) + (gl & 7) * 4;
+
+        float wa[AU][4];
+        float xb[C::BU][4];
+
+        // drain: TMEM lane quarter q (row = Gaussian), 16-column chunks half, half + 2, ...
+        using acc_t = typename C::acc_t;
+        const int q = warp & 3, half = warp >> 2;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        acc_t sums[C::MYCH][16];
+#pragma unroll
+        for (int m = 0; m < C::MYCH; ++m)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sums[m][i] = (acc_t)0;
+        auto drain = [&](int it) {
+            const int buf = it & 1;
+            mbar_wait(&bars->tfull[buf], (it >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int m = 0; m < C::MYCH; ++m) {
+                const int ch = half + 2 * m;
+                if (ch < C::NCH) {
+                    float v[16];
+                    tmem_ld16(taddr + (uint32_t)(buf * NB + ch * 16), v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) sums[m][i] += (acc_t)v[i];
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&bars->tempty[buf]);
+        };
+
+        auto load_tile = [&](int it) {
+            const int64_t t0 = f_begin + (int64_t)it * KF;
+#pragma unroll
+            for (int j = 0; j < AU; ++j) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int64_t t = t0 + (fq0 + 2 * j) * 4 + i;
+                    // branch-free on loaded values, so that the 4 * AU loads of a tile stay in flight together
+                    const bool ok = a_active && t < f_end;
+                    const size_t tt = ok ? (size_t)t : (size_t)f_begin;
+                    float w = (a.pdf_post != nullptr) ? __ldg(a.pdf_post + tt * a.ld_post + kpdf) : 1.f;
+                    if constexpr (MIX) {
+                        const float c = __ldg(a.comp_llh + tt * a.M + g0 + (a_active ? gl : 0));
+                        const float l = __ldg(a.pdf_llh + tt * a.ld_pdf + kpdf);
+                        const float r = __expf(c - l);
+                        w = (w != 0.f) ? w * r : 0.f;
+                    }
+                    w = ok ? w : 0.f;
+                    wa[j][i] = w;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < C::BU; ++j) {
+                const int u = tid + j * PRODUCERS;
+                const int d = u % D, fq = u / D;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int64_t t = t0 + fq * 4 + i;
+                    xb[j][i] = (u < (KF / 4) * D && t < f_end) ? __ldg(a.X + (size_t)t * D + d) : 0.f;
+                }
+            }
+        };
+
+        if (n_tiles > 0) load_tile(0);
+        for (int it = 0; it < n_tiles; ++it) {
+            const int st = it % STAGES;
+            float* A_hi = stage_base + (size_t)st * C::STAGE_FLOATS;
+            float* A_lo = A_hi + C::A_FLOATS;
+            float* B_hi = A_lo + C::A_FLOATS;
+            float* B_lo = B_hi + C::B_FLOATS;
+            mbar_wait(&bars->empty[st], ((it / STAGES) & 1) ^ 1);
+            if (a_active) {
+#pragma unroll
+                for (int j = 0; j < AU; ++j) {
+                    float h[4], l[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        h[i] = tf32_rn(wa[j][i]);
+                        l[i] = tf32_rn(wa[j][i] - h[i]);
+                    }
+                    const int off = a_row + (fq0 + 2 * j) * 32;
+                    *reinterpret_cast<float4*>(A_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<float4*>(A_lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < C::BU; ++j) {
+                const int u = tid + j * PRODUCERS;
+                if (u < (KF / 4) * D) {
+                    const int d = u % D, fq = u / D;
+                    float xh[4], xl[4], qh[4], ql[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float x = xb[j][i], q = x * x;
+                        xh[i] = tf32_rn(x);
+                        xl[i] = tf32_rn(x - xh[i]);
+                        qh[i] = tf32_rn(q);
+                        ql[i] = tf32_rn(q - qh[i]);
+                    }
+                    const int offx = (d >> 3) * (KF * 8) + fq * 32 + (d & 7) * 4;
+                    const int offq = ((D + d) >> 3) * (KF * 8) + fq * 32 + ((D + d) & 7) * 4;
+                    *reinterpret_cast<float4*>(B_hi + offx) = make_float4(xh[0], xh[1], xh[2], xh[3]);
+                    *reinterpret_cast<float4*>(B_lo + offx) = make_float4(xl[0], xl[1], xl[2], xl[3]);
+                    *reinterpret_cast<float4*>(B_hi + offq) = make_float4(qh[0], qh[1], qh[2], qh[3]);
+                    *reinterpret_cast<float4*>(B_lo + offq) = make_float4(ql[0], ql[1], ql[2], ql[3]);
+                }
+            }
+            fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core
+            mbar_arrive(&bars->full[st]);
+            if (it + 1 < n_tiles) load_tile(it + 1);
+            if (it > 0) drain(it - 1);
+        }
+
+        // ------------------------------ epilogue ---------------------------------
+        if (n_tiles > 0) {
+            drain(n_tiles - 1);
+            const int g = q * 32 + lane;
+            if (g < ng) {
+                const int Q = 2 * D + 2;
+                double* row = a.acc + (size_t)(g0 + g) * Q;
+#pragma unroll
+                for (int m = 0; m < C::MYCH; ++m) {
+                    const int ch = half + 2 * m;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int c = ch * 16 + i;
+                        const double v = (double)sums[m][i];
+                        if (c < 2 * D) {
+                            if (v != 0.0) atomicAdd(row + c, c < D ? v : -0.5 * v);
+                        } else if (c == 2 * D) {
+                            if (v != 0.0) {
+                                atomicAdd(row + 2 * D, -0.5 * v);
+                                atomicAdd(row + 2 * D + 1, 0.5 * v);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == PRODUCERS / 32) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+template <int D4, int KF, int ST>
+static int launch(const Args& a0, cudaStream_t st) {
+    using C = Cfg<D4, KF, ST>;
+    static_assert(C::SMEM <= 227 * 1024, "stage too large");
+    static_assert(C::NB <= 256 && C::NB % 8 == 0, "UMMA N");
+    static bool attr_set = false;
+    if (!attr_set) {
+        BEER_CUDA_TRY(cudaFuncSetAttribute(accumulate_tc_kernel<D4, KF, ST, false>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        BEER_CUDA_TRY(cudaFuncSetAttribute(accumulate_tc_kernel<D4, KF, ST, true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        attr_set = true;
+    }
+    Args a = a0;
+    a.n_gtiles = (a.M + GM - 1) / GM;
+    // one CTA per SM (shared memory bound): ~3 waves when there are many Gaussian tiles
+    int64_t chunks = (a.n_gtiles >= kNumSMs) ? 1 : ((a.n_gtiles > kNumSMs / 3 ? 3 * kNumSMs : kNumSMs) / a.n_gtiles);
+    int64_t max_chunks = (a.N + KF - 1) / KF;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    int64_t fpc = (a.N + chunks - 1) / chunks;
+    fpc = (fpc + KF - 1) / KF * KF;
+    chunks = (a.N + fpc - 1) / fpc;
+    a.frames_per_cta = fpc;
+    int grid = (int)(chunks * a.n_gtiles);
+    if (a.comp_llh != nullptr)
+        accumulate_tc_kernel<D4, KF, ST, true><<<grid, THREADS, C::SMEM, st>>>(a);
+    else
+        accumulate_tc_kernel<D4, KF, ST, false><<<grid, THREADS, C::SMEM, st>>>(a);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
+}  // namespace kctc
+}  // namespace beer
+
+using namespace beer;
+
+extern "C" {
+
+int beer_accumulate_tc_supported(int M, int D) {
+    if (M <= 0 || D <= 0 || D % 4 != 0) return 0;
+    int d4 = D / 4;
+    return (d4 == 5 || d4 == 10 || d4 == 16 || d4 == 20) ? 1 : 0;
+}
+
+int beer_accumulate_stats_tc(const float* X, int64_t N, int D, const float* pdf_post, int64_t ld_post,
+                             const float* pdf_llh, int64_t ld_pdf, const float* comp_llh, const int32_t* comp_off,
+                             int Kp, int M, double* acc_normal, void* stream) {
+    if (!X || !acc_normal || N < 0 || D <= 0 || M <= 0 || Kp <= 0) return BEER_ERR_ARG;
+    if (comp_llh != nullptr && pdf_llh == nullptr) return BEER_ERR_ARG;
+    if (comp_off == nullptr && M % Kp != 0) return BEER_ERR_ARG;
+    if (comp_llh == nullptr && M != Kp) return BEER_ERR_ARG;
+    if (pdf_post != nullptr && ld_post < Kp) return BEER_ERR_ARG;
+    if (!beer_accumulate_tc_supported(M, D)) return BEER_ERR_UNSUPPORTED;
+    if (((uintptr_t)X & 15) != 0) return BEER_ERR_ARG;
+    if (N == 0) return BEER_OK;
+    kctc::Args a;
+    a.X = X; a.N = N; a.pdf_post = pdf_post; a.ld_post = ld_post; a.pdf_llh = pdf_llh; a.ld_pdf = ld_pdf;
+    a.comp_llh = comp_llh; a.comp_off = comp_off; a.Kp = Kp; a.M = M; a.C = M / Kp; a.acc = acc_normal;
+    a.n_gtiles = 0; a.frames_per_cta = 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (D / 4) {
+        case 5: return kctc::launch<5, 64, 2>(a, st);
+        case 10: return kctc::launch<10, 32, 4>(a, st);
+        case 16: return kctc::launch<16, 32, 2>(a, st);
+        case 20: return kctc::launch<20, 32, 2>(a, st);
+    }
+    return BEER_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

@@ -6,7 +6,7 @@
 // Operands live in shared memory in the canonical no-swizzle K-major core-matrix layout
 // ([row/8][k/4][row%8][k%4], 128-byte core matrices).  The weight image is packed once per VB
 // iteration by beer_emission_tc_pack and streamed in with cp.async.bulk (TMA, 1-D); the
-// statistics tile is built by the worker warps from X (hi = top 19 bits, lo = x - hi).
+// statistics tile is built by the worker warps from X (hi = rn_tf32(x), lo = rn_tf32(x - hi)).
 // Accumulators are fp32 in TMEM (double buffered); the epilogue reads them back with
 // tcgen05.ld, adds the bias, takes the log-sum-exp over the C components of each pdf and
 // stores the offset-form llh.
@@ -16,6 +16,7 @@
 //
 // Reference semantics: beer/dists/normalgamma.py:55-59, beer/models/mixtureset.py:85-98.
 #include "common.cuh"
+#include "tc_common.cuh"
 #include "../../include/beer_b200.h"
 
 namespace beer {
@@ -26,82 +27,7 @@ constexpr int NB_MAX = 128;    // Gaussians per chunk (UMMA N)
 constexpr int WORKERS = 128;
 constexpr int THREADS = 192;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t addr = smem_u32(bar), ok;
-    do {
-        asm volatile(
-            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-// D[tmem] (+)= A[smem] . B[smem]^T, tf32 inputs, fp32 accumulate.
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(
-            d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// Shared-memory matrix descriptor: no swizzle, K-major, version 1 (sm_100).
-//   core matrix = 8 rows x 16 bytes, contiguous (128 B)
-//   LBO = byte stride between core matrices adjacent in K, SBO = between 8-row groups
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
-    d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
-    d |= (uint64_t)1 << 46;
-    return d;
-}
+using namespace tcu;
 
 // offset (in floats) of element (row, k) inside a [rows x Kd] core-matrix image
 __host__ __device__ __forceinline__ int img_off(int row, int k, int Kd) {
@@ -245,11 +171,11 @@ __global__ void __launch_bounds__(THREADS, 1) emission_tc_kernel(Args a) {
                 float h[4], l[4], qh[4], ql[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    h[e] = __uint_as_float(__float_as_uint(x[e]) & 0xffffe000u);
-                    l[e] = x[e] - h[e];
+                    h[e] = tf32_rn(x[e]);
+                    l[e] = tf32_rn(x[e] - h[e]);
                     const float q = -0.5f * x[e] * x[e];
-                    qh[e] = __uint_as_float(__float_as_uint(q) & 0xffffe000u);
-                    ql[e] = q - qh[e];
+                    qh[e] = tf32_rn(q);
+                    ql[e] = tf32_rn(q - qh[e]);
                     rt = fmaf(q, s_ref[4 * c + e], rt);
                 }
                 *reinterpret_cast<float4*>(A_hi + rbase + c * 32) = make_float4(h[0], h[1], h[2], h[3]);
@@ -356,8 +282,8 @@ __global__ void emission_tc_pack_kernel(const float* __restrict__ W, const float
         int n = rem / Kd, k = rem - n * Kd;
         int g = c * NB + n;
         float w = (g < M) ? W[(size_t)g * Kd + k] : 0.f;
-        float hi = __uint_as_float(__float_as_uint(w) & 0xffffe000u);
-        float lo = w - hi;
+        float hi = tf32_rn(w);
+        float lo = tf32_rn(w - hi);
         float* base = img + (size_t)c * per_chunk;
         base[img_off(n, k, Kd)] = hi;
         base[NB * Kd + img_off(n, k, Kd)] = lo;

@@ -81,13 +81,29 @@ class EmissionParams:
             self.comp_off = torch.as_tensor(self.comp_off_host, dtype=i32, device=self.device)
         self.has_mixtures = self.Kp != self.M
         self.logw = torch.zeros(self.M, device=self.device, dtype=f32) if self.weight_groups else None
+        # uniform number of Gaussians per pdf -> tensor-core (tcgen05) emission kernel
+        counts = np.diff(self.comp_off_host)
+        self.uniform_C = int(counts[0]) if len(counts) and np.all(counts == counts[0]) else 0
+        self.use_tc = bool(self.uniform_C) and ops.emission_tc_supported(self.M, self.D, self.uniform_C)
+        self._image = None
 
     def refresh(self):
         """(W, bias, ref) of the current posteriors."""
         for g in self.weight_groups:
             j0 = int(self.comp_off_host[g.pdf_start])
             self.logw[j0:j0 + g.n_pdfs * g.n_comp] = ops.dirichlet_expected_logw(g.post).reshape(-1)
-        return ops.emission_prepare(*self.post, logw=self.logw)
+        W, bias, ref = ops.emission_prepare(*self.post, logw=self.logw)
+        if self.use_tc:
+            self._image = ops.emission_tc_pack(W, bias, self.uniform_C, out=self._image)
+        return W, bias, ref
+
+    def llh(self, X, W, bias, ref, out, out_comp, out_ref):
+        """KA over a run of frames: tcgen05 path when the shape has one, SIMT kernel otherwise."""
+        if self.use_tc:
+            return ops.emission_llh_tc(X, self._image, ref, self.M, self.uniform_C, out=out, out_comp=out_comp,
+                                       out_ref=out_ref)
+        return ops.emission_llh(X, W, bias, ref, comp_off=self.comp_off, Kp=self.Kp, out=out, out_comp=out_comp,
+                                out_ref=out_ref)
 
     def kl(self, out=None):
         out = ops.normalgamma_kl(self.prior, self.post, out=out)
@@ -189,7 +205,7 @@ class VBEngine:
         self.kl.zero_()
         W, bias, ref = em.refresh()
         em.kl(out=self.kl)
-        self.gpu_launches += 2 + 1 + 2 * len(em.weight_groups)
+        self.gpu_launches += 2 + 1 + 2 * len(em.weight_groups) + int(em.use_tc)
         nonident = not (plan.info['map_identity'] and plan.n_states == em.Kp)
         for (u0, u1, f0, nf, rel) in self._chunks:
             if nf == 0:
@@ -199,8 +215,7 @@ class VBEngine:
             pdf_post = self.pdf_post[:nf]
             comp = self.comp_llh[:nf] if self.comp_llh is not None else None
             with self._stage('KA_emission_llh'):
-                _, _, fref = ops.emission_llh(X, W, bias, ref, comp_off=em.comp_off, Kp=em.Kp, out=pdf_llh,
-                                              out_comp=comp, out_ref=self.frame_ref[:nf])
+                _, _, fref = em.llh(X, W, bias, ref, pdf_llh, comp, self.frame_ref[:nf])
             if nonident:
                 pdf_post.zero_()
             with self._stage('KB_forward_backward'):

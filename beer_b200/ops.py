@@ -216,14 +216,23 @@ def hmm_viterbi(plan, pdf_llh, utt_off, scale=1.0, workspace=None):
     return path
 
 
-def accumulate_stats(X, acc_normal, pdf_post=None, pdf_llh=None, comp_llh=None, comp_off=None, Kp=None):
-    """acc_normal [M, 2D+2] (fp64) += posterior-weighted statistics."""
+def accumulate_tc_supported(M, D):
+    return bool(_lib.load().beer_accumulate_tc_supported(int(M), int(D)))
+
+
+def accumulate_stats(X, acc_normal, pdf_post=None, pdf_llh=None, comp_llh=None, comp_off=None, Kp=None,
+                     tensor_cores=None):
+    """acc_normal [M, 2D+2] (fp64) += posterior-weighted statistics.  `tensor_cores`: None = use
+    the tcgen05 kernel when the shape has one, False = SIMT kernel, True = require tcgen05."""
     lib = require_cuda()
     N, D = X.shape
     M = acc_normal.shape[0]
     if Kp is None:
         Kp = M if comp_llh is None else (comp_off.numel() - 1 if comp_off is not None else pdf_llh.shape[1])
-    _lib.check(lib.beer_accumulate_stats(
+    if tensor_cores is None:
+        tensor_cores = accumulate_tc_supported(M, D) and X.data_ptr() % 16 == 0
+    fn = lib.beer_accumulate_stats_tc if tensor_cores else lib.beer_accumulate_stats
+    _lib.check(fn(
         _p(X, f32), N, D, _p(pdf_post, f32, True), pdf_post.stride(0) if pdf_post is not None else 0,
         _p(pdf_llh, f32, True), pdf_llh.stride(0) if pdf_llh is not None else 0, _p(comp_llh, f32, True),
         _p(comp_off, i32, True), Kp, M, _p(acc_normal, f64), _stream()), 'beer_accumulate_stats')

@@ -166,6 +166,14 @@ BEER_API int beer_accumulate_stats(const float* X, int64_t N, int D, const float
                           const float* pdf_llh, int64_t ld_pdf, const float* comp_llh,
                           const int32_t* comp_off, int Kp, int M, double* acc_normal, void* stream);
 
+/* KC on the tensor cores (tcgen05 + TMEM, 3xTF32 split, fp32 accumulation in TMEM, one fp64
+ * atomic flush per CTA): same contract as beer_accumulate_stats for D in {20, 40, 64, 80}.
+ *   beer_accumulate_tc_supported(M, D) -> 1 if this shape has a tensor-core path. */
+BEER_API int beer_accumulate_tc_supported(int M, int D);
+BEER_API int beer_accumulate_stats_tc(const float* X, int64_t N, int D, const float* pdf_post, int64_t ld_post,
+                             const float* pdf_llh, int64_t ld_pdf, const float* comp_llh,
+                             const int32_t* comp_off, int Kp, int M, double* acc_normal, void* stream);
+
 /* Categorical statistics of the mixture weights from the accumulated Normal statistics
  * (sum_t w_tj = 2 * acc_normal[j, 2D+1]):  per pdf [n_c (c < C-1), sum_c n_c], the layout
  * of CategoricalLikelihood.sufficient_statistics (beer/dists/dirichlet.py:18-21) summed

@@ -75,12 +75,19 @@ def test_normalgamma_dirichlet_math(ops):
         np.testing.assert_allclose(conc.cpu().numpy(), want, rtol=1e-5, atol=1e-6)
 
 
-def _emission(ops, X, post, dir_post=None, comp_off=None, want_comp=False):
+def _emission(ops, X, post, dir_post=None, comp_off=None, want_comp=False, tc=False):
     logw = None
     if dir_post is not None:
         logw = torch.cat([ops.dirichlet_expected_logw(dev(d)).reshape(-1) for d in dir_post])
     W, bias, ref = ops.emission_prepare(*ng_dev(post), logw=logw)
     co = None if comp_off is None else dev(comp_off, torch.int32)
+    if tc:      # tcgen05 kernel (uniform number of Gaussians per pdf)
+        M, D = post[0].shape
+        C = 1 if comp_off is None else int(comp_off[1] - comp_off[0])
+        if not ops.emission_tc_supported(M, D, C):
+            pytest.skip('no tensor-core emission path for this shape')
+        img = ops.emission_tc_pack(W, bias, C)
+        return ops.emission_llh_tc(dev(X), img, ref, M, C, want_comp=want_comp)
     return ops.emission_llh(dev(X), W, bias, ref, comp_off=co, want_comp=want_comp)
 
 
@@ -163,14 +170,16 @@ def test_viterbi_ties_first_max(ops):
         np.testing.assert_array_equal(path, g['path' + sfx])
 
 
+@pytest.mark.parametrize('tc', [False, True])
 @pytest.mark.parametrize('name', ['hmm_small', 'hmm_scaled', 'hmm_cfg2_T200'])
-def test_estep_chain_normalset(ops, name):
-    """KA -> KB -> KC chained on the device against the golden E-step of the reference."""
+def test_estep_chain_normalset(ops, name, tc):
+    """KA -> KB -> KC chained on the device against the golden E-step of the reference
+    (tc: tcgen05 emission and statistics kernels; otherwise the SIMT ones)."""
     g = load_golden(name)
     scale = float(g['scale'])
     X = dev(g['X'])
     T, D = g['X'].shape
-    pdf_llh, _, fref = _emission(ops, g['X'], ng(g, 'post0_'))
+    pdf_llh, _, fref = _emission(ops, g['X'], ng(g, 'post0_'), tc=tc)
     plan = ops.GraphPlan(*graph(g))
     utt = torch.tensor([0, T], dtype=torch.int64, device=DEV)
     r = ops.hmm_forward_backward(plan, pdf_llh, fref, utt, scale=scale, want_state_post=True)
@@ -178,7 +187,7 @@ def test_estep_chain_normalset(ops, name):
     np.testing.assert_allclose(r['utt_exp_llh'].item(), g['exp_llh'].sum(), rtol=1e-6)
     K = g['gamma'].shape[1]
     acc = torch.zeros(K, 2 * D + 2, device=DEV, dtype=torch.float64)
-    ops.accumulate_stats(X, acc, pdf_post=r['pdf_post'])
+    ops.accumulate_stats(X, acc, pdf_post=r['pdf_post'], tensor_cores=tc)
     got = acc.cpu().numpy()
     assert np.abs(got - g['acc_normal']).max() <= 2e-5 * np.abs(g['acc_normal']).max()
     # ELBO with datasize = 3T (objectives.py:176-184)
