@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(THREADS, 1) accumulate_tc_kernel(Args a) {
         const int a_row = (gl >> 3) * (KF * 8) + (gl & 7) * 4;
 
         float wa[AU][4];
+        float ca[MIX ? AU : 1][4], la[MIX ? AU : 1][4];   // component / pdf llh (mixtures only)
         float xb[C::BU][4];
 
         // drain: TMEM lane quarter q (row = Gaussian), 16-column chunks half, half + 2, ...
@@ -219,18 +220,20 @@ __global__ void __launch_bounds__(THREADS, 1) accumulate_tc_kernel(Args a) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int64_t t = t0 + (fq0 + 2 * j) * 4 + i;
-                    // branch-free on loaded values, so that the 4 * AU loads of a tile stay in flight together
+                    // predicated loads straight into their registers, nothing consumed here: all the
+                    // loads of a tile stay in flight together (a select right behind each load made
+                    // ptxas funnel them through one temporary, i.e. one DRAM round trip per load)
                     const bool ok = a_active && t < f_end;
-                    const size_t tt = ok ? (size_t)t : (size_t)f_begin;
-                    float w = (a.pdf_post != nullptr) ? __ldg(a.pdf_post + tt * a.ld_post + kpdf) : 1.f;
+                    wa[j][i] = (a.pdf_post != nullptr) ? 0.f : (ok ? 1.f : 0.f);
+                    if (ok && a.pdf_post != nullptr) wa[j][i] = __ldg(a.pdf_post + (size_t)t * a.ld_post + kpdf);
                     if constexpr (MIX) {
-                        const float c = __ldg(a.comp_llh + tt * a.M + g0 + (a_active ? gl : 0));
-                        const float l = __ldg(a.pdf_llh + tt * a.ld_pdf + kpdf);
-                        const float r = __expf(c - l);
-                        w = (w != 0.f) ? w * r : 0.f;
+                        ca[j][i] = 0.f;
+                        la[j][i] = 0.f;
+                        if (ok) {
+                            ca[j][i] = __ldg(a.comp_llh + (size_t)t * a.M + g0 + gl);
+                            la[j][i] = __ldg(a.pdf_llh + (size_t)t * a.ld_pdf + kpdf);
+                        }
                     }
-                    w = ok ? w : 0.f;
-                    wa[j][i] = w;
                 }
             }
 #pragma unroll
@@ -259,8 +262,10 @@ __global__ void __launch_bounds__(THREADS, 1) accumulate_tc_kernel(Args a) {
                     float h[4], l[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        h[i] = tf32_rn(wa[j][i]);
-                        l[i] = tf32_rn(wa[j][i] - h[i]);
+                        float w = wa[j][i];
+                        if constexpr (MIX) w = (w != 0.f) ? w * __expf(ca[j][i] - la[j][i]) : 0.f;
+                        h[i] = tf32_rn(w);
+                        l[i] = tf32_rn(w - h[i]);
                     }
                     const int off = a_row + (fq0 + 2 * j) * 32;
                     *reinterpret_cast<float4*>(A_hi + off) = make_float4(h[0], h[1], h[2], h[3]);

@@ -10,6 +10,7 @@
 // Reference semantics: beer/graph.py:270-344, beer/models/hmm.py:79-100,
 // beer/models/modelset.py:140-154.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <vector>
@@ -35,6 +36,8 @@ struct beer_graph_plan {
     int K = 0, Kp = 0, J = 0, S = 0;
     int n_direct = 0, n_jin = 0, n_jout = 0, dense_nnz = 0;
     int map_identity = 0;
+    int fast_ok = 0;   // every state has <= 2 in/out arcs after factoring and there is <= 1 junction
+    int jrows = 0;     // ELL rows of that junction (max over directions)
     beer::ScanLists fwd{}, bwd{}, vit{};
     const int* map = nullptr;        // device [K]
     const float* vit_final = nullptr;  // device [K] natural log
@@ -524,6 +527,362 @@ __global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_kernel(FbArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// Fast path: graphs whose states have at most two incoming and two outgoing arcs once the
+// rank-1 blocks are routed through (at most one) junction -- phone loops of left-to-right
+// units (beer/cli/subcommands/hmm/mkphoneloopgraph.py) and alignment graphs (mkaligraph.py).
+// The arc lists of a lane live in registers for the whole kernel, the junction value is
+// reduced into a register of every lane (no shared-memory round trip) and selected into the
+// arcs that leave it.  Same arithmetic as the generic kernel.
+// ---------------------------------------------------------------------------
+template <int S, int JR>
+struct LaneLists {
+    int src[S][2];
+    float w[S][2];
+    unsigned jmask;   // bit 2s+c: arc c of slot s leaves the junction
+    int jsrc[JR];
+    float jw[JR];
+};
+
+template <int S, int JR>
+__device__ __forceinline__ void load_lane_lists(LaneLists<S, JR>& L, const ScanLists& l, int K, int J, int lane) {
+    L.jmask = 0u;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const int row0 = __ldg(l.st_off + s), cnt = __ldg(l.st_cnt + s);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            int src = 0;
+            float w = kNegInf;
+            if (c < cnt) {
+                const int i = (row0 + c) * 32 + lane;
+                src = __ldg(l.src + i);
+                w = __ldg(l.lw + i);
+            }
+            if (src >= K) {
+                L.jmask |= 1u << (2 * s + c);
+                src = 0;
+            }
+            L.src[s][c] = src;
+            L.w[s][c] = w;
+        }
+    }
+    const int jrow0 = (J > 0) ? __ldg(l.jn_off) : 0, jcnt = (J > 0) ? __ldg(l.jn_cnt) : 0;
+#pragma unroll
+    for (int r = 0; r < JR; ++r) {
+        L.jsrc[r] = 0;
+        L.jw[r] = kNegInf;
+        if (r < jcnt) {
+            const int i = (jrow0 + r) * 32 + lane;
+            L.jsrc[r] = __ldg(l.src + i);
+            L.jw[r] = __ldg(l.lw + i);
+        }
+    }
+}
+
+// log2-domain log(2^a + 2^b); -inf safe (NaN of -inf - -inf is absorbed by fmaxf)
+__device__ __forceinline__ float lse2(float a, float b) {
+    const float mx = fmaxf(a, b), mn = fminf(a, b);
+    const float d = fmaxf(mn - mx, -1000.f);
+    return mx + lg2(1.f + ex2(d));
+}
+
+// value of the junction from the published per-state values in buf
+template <int S, int JR>
+__device__ __forceinline__ float junction_value(const LaneLists<S, JR>& L, const float* buf) {
+    float v[JR], m = kNegInf;
+#pragma unroll
+    for (int r = 0; r < JR; ++r) {
+        v[r] = buf[L.jsrc[r]] + L.jw[r];
+        m = fmaxf(m, v[r]);
+    }
+    m = warp_max(m);
+    const float ms = (m == kNegInf) ? 0.f : m;
+    float sum = 0.f;
+#pragma unroll
+    for (int r = 0; r < JR; ++r) sum += ex2(v[r] - ms);
+    sum = warp_sum(sum);
+    return ms + lg2(sum);
+}
+
+template <int S, int JR>
+__device__ __forceinline__ void lane_states(const LaneLists<S, JR>& L, const float* buf, float jv, float* out) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        float x0 = buf[L.src[s][0]], x1 = buf[L.src[s][1]];
+        if (L.jmask & (1u << (2 * s))) x0 = jv;
+        if (L.jmask & (1u << (2 * s + 1))) x1 = jv;
+        out[s] = lse2(x0 + L.w[s][0], x1 + L.w[s][1]);
+    }
+}
+
+template <int S, int JR>
+__global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_fast_kernel(FbArgs a) {
+    static_assert(S % 4 == 0, "vector rows");
+    constexpr int PF = FbCfg<S>::PF;
+    constexpr int ROW = 32 * S;
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int per_warp = ROW + 2 * PF * ROW;
+    float* buf = smem + (size_t)warp * per_warp;   // [32 * S] published per-state values
+    float* ring_p = buf + ROW;                     // [PF][32 * S]
+    float* ring_a = ring_p + PF * ROW;             // [PF][32 * S]
+    const int K = a.K, J = a.J;
+    const float p_scale = a.scale * kLog2e;
+    const int gwarp = blockIdx.x * FB_WARPS + warp, nwarps = gridDim.x * FB_WARPS;
+    const bool own = lane * S < K;                 // this lane holds real states (K % 4 == 0)
+    // lanes past K never receive async copies: keep their ring slots finite
+    for (int i = lane; i < 2 * PF * ROW; i += 32) ring_p[i] = 0.f;
+    __syncwarp();
+
+    LaneLists<S, JR> F, B;
+    load_lane_lists(F, a.fwd, K, J, lane);
+    load_lane_lists(B, a.bwd, K, J, lane);
+    float f_start[S], b_start[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const int k = lane * S + s;
+        f_start[s] = (k < K) ? __ldg(a.fwd.start + k) : kNegInf;
+        b_start[s] = (k < K) ? __ldg(a.bwd.start + k) : kNegInf;
+    }
+
+    auto prefetch = [&](float* slot, const float* row) {
+        if (own) {
+#pragma unroll
+            for (int v = 0; v < S / 4; ++v)
+                if (lane * S + 4 * v < K) cp_async16(slot + lane * S + 4 * v, row + lane * S + 4 * v);
+        }
+    };
+
+    for (int u = gwarp; u < a.n_utts; u += nwarps) {
+        const int64_t t0 = a.utt_off[u];
+        const int T = (int)(a.utt_off[u + 1] - t0);
+        if (T <= 0) {
+            if (lane == 0) {
+                a.utt_exp_llh[u] = 0.0;
+                if (a.utt_logz) a.utt_logz[u] = 0.0;
+            }
+            continue;
+        }
+        const float* pl_u = a.pl + (size_t)t0 * a.ld;
+        float* la_u = a.la_ws + (size_t)t0 * a.Kw;
+        double logz2 = 0.0;
+
+        // ------------------------------ forward ------------------------------
+        for (int r = 0; r < PF; ++r) {
+            if (r < T) prefetch(ring_p + r * ROW, pl_u + (size_t)r * a.ld);
+            cp_async_commit();
+        }
+        float cur[S];
+        for (int t = 0; t < T; ++t) {
+            cp_async_wait<PF - 1>();
+            const float4* slot = reinterpret_cast<const float4*>(ring_p + (t % PF) * ROW + lane * S);
+            float p[S];
+#pragma unroll
+            for (int v = 0; v < S / 4; ++v) {
+                const float4 q = slot[v];
+                p[4 * v] = q.x * p_scale; p[4 * v + 1] = q.y * p_scale;
+                p[4 * v + 2] = q.z * p_scale; p[4 * v + 3] = q.w * p_scale;
+            }
+            if (t + PF < T) prefetch(ring_p + (t % PF) * ROW, pl_u + (size_t)(t + PF) * a.ld);
+            cp_async_commit();
+
+            if (t == 0) {
+#pragma unroll
+                for (int s = 0; s < S; ++s) cur[s] = p[s] + f_start[s];
+            } else {
+                const float jv = (J > 0) ? junction_value(F, buf) : kNegInf;
+                float v[S];
+                lane_states(F, buf, jv, v);
+#pragma unroll
+                for (int s = 0; s < S; ++s) cur[s] = p[s] + v[s];
+            }
+            float mx = cur[0];
+#pragma unroll
+            for (int s = 1; s < S; ++s) mx = fmaxf(mx, cur[s]);
+            mx = warp_max(mx);
+            const float mxs = (mx == kNegInf) ? 0.f : mx;
+            logz2 += (double)mxs;
+#pragma unroll
+            for (int s = 0; s < S; ++s) cur[s] -= mxs;
+            __syncwarp();  // every lane has finished reading buf
+#pragma unroll
+            for (int v = 0; v < S / 4; ++v)
+                reinterpret_cast<float4*>(buf + lane * S)[v] = make_float4(cur[4 * v], cur[4 * v + 1], cur[4 * v + 2], cur[4 * v + 3]);
+            __syncwarp();
+            if (own) {
+                float* la_row = la_u + (size_t)t * a.Kw + lane * S;
+#pragma unroll
+                for (int v = 0; v < S / 4; ++v)
+                    if (lane * S + 4 * v < K)
+                        reinterpret_cast<float4*>(la_row)[v] = make_float4(cur[4 * v], cur[4 * v + 1], cur[4 * v + 2], cur[4 * v + 3]);
+            }
+        }
+        cp_async_wait<0>();
+
+        if (a.utt_logz != nullptr) {
+            float m = kNegInf, v[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                v[s] = cur[s] + b_start[s];
+                m = fmaxf(m, v[s]);
+            }
+            m = warp_max(m);
+            const float ms = (m == kNegInf) ? 0.f : m;
+            float sum = 0.f;
+#pragma unroll
+            for (int s = 0; s < S; ++s) sum += ex2(v[s] - ms);
+            sum = warp_sum(sum);
+            const double z = (logz2 + (double)ms + (double)lg2(sum)) * (double)kLn2;
+            double rs = 0.0;
+            if (a.frame_ref != nullptr)
+                for (int t = lane; t < T; t += 32) rs += (double)a.frame_ref[t0 + t];
+            rs = warp_sum(rs);
+            if (lane == 0) a.utt_logz[u] = z + (double)a.scale * rs;
+        }
+
+        // ------------------------------ backward -----------------------------
+        __threadfence_block();   // this warp's la stores -> visible to its own async copies
+        __syncwarp();
+        for (int r = 0; r < PF; ++r) {
+            const int t = T - 1 - r;
+            if (t >= 0) {
+                prefetch(ring_p + r * ROW, pl_u + (size_t)t * a.ld);
+                prefetch(ring_a + r * ROW, la_u + (size_t)t * a.Kw);
+            }
+            cp_async_commit();
+        }
+        float lb[S];
+        {
+            float m = kNegInf;
+#pragma unroll
+            for (int s = 0; s < S; ++s) m = fmaxf(m, b_start[s]);
+            m = warp_max(m);
+            const float ms = (m == kNegInf) ? 0.f : m;
+#pragma unroll
+            for (int s = 0; s < S; ++s) lb[s] = b_start[s] - ms;
+        }
+        float ell = 0.f;        // this lane's share of sum_t sum_k p2_tk gamma_tk (flushed every 32 frames)
+        double ell_d = 0.0;
+        for (int i = 0; i < T; ++i) {
+            const int t = T - 1 - i;
+            cp_async_wait<PF - 1>();
+            const float4* sp = reinterpret_cast<const float4*>(ring_p + (i % PF) * ROW + lane * S);
+            const float4* sa = reinterpret_cast<const float4*>(ring_a + (i % PF) * ROW + lane * S);
+            float p[S], la[S];
+#pragma unroll
+            for (int v = 0; v < S / 4; ++v) {
+                const float4 q = sp[v], r = sa[v];
+                p[4 * v] = q.x * p_scale; p[4 * v + 1] = q.y * p_scale;
+                p[4 * v + 2] = q.z * p_scale; p[4 * v + 3] = q.w * p_scale;
+                la[4 * v] = r.x; la[4 * v + 1] = r.y; la[4 * v + 2] = r.z; la[4 * v + 3] = r.w;
+            }
+            if (t - PF >= 0) {
+                prefetch(ring_p + (i % PF) * ROW, pl_u + (size_t)(t - PF) * a.ld);
+                prefetch(ring_a + (i % PF) * ROW, la_u + (size_t)(t - PF) * a.Kw);
+            }
+            cp_async_commit();
+
+            // gamma_t (lanes past K: la = 0, lb = -inf -> 0)
+            float v[S], m = kNegInf;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                v[s] = la[s] + lb[s];
+                m = fmaxf(m, v[s]);
+            }
+            m = warp_max(m);
+            const float ms = (m == kNegInf) ? 0.f : m;
+            float sum = 0.f;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                v[s] = ex2(v[s] - ms);
+                sum += v[s];
+            }
+            sum = warp_sum(sum);
+            const float inv = (sum > 0.f) ? __fdividef(1.f, sum) : 0.f;
+            float fe = 0.f;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                v[s] *= inv;
+                if (v[s] > 0.f) fe = fmaf(p[s], v[s], fe);
+            }
+            ell += fe;
+            if ((i & 31) == 31) {
+                ell_d += (double)ell;
+                ell = 0.f;
+            }
+            if (a.frame_exp_llh != nullptr) {
+                const float f = warp_sum(fe);
+                if (lane == 0) {
+                    const float r = (a.frame_ref != nullptr) ? a.scale * a.frame_ref[t0 + t] : 0.f;
+                    a.frame_exp_llh[t0 + t] = f * kLn2 + r;
+                }
+            }
+            if (own) {
+                if (a.state_post != nullptr) {
+                    float* row = a.state_post + (size_t)(t0 + t) * K + lane * S;
+#pragma unroll
+                    for (int q = 0; q < S / 4; ++q)
+                        if (lane * S + 4 * q < K)
+                            reinterpret_cast<float4*>(row)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                }
+                if (a.pdf_post != nullptr) {
+                    float* row = a.pdf_post + (size_t)(t0 + t) * a.ld_post + lane * S;
+#pragma unroll
+                    for (int q = 0; q < S / 4; ++q)
+                        if (lane * S + 4 * q < K)
+                            reinterpret_cast<float4*>(row)[q] = make_float4(a.scale * v[4 * q], a.scale * v[4 * q + 1],
+                                                                           a.scale * v[4 * q + 2], a.scale * v[4 * q + 3]);
+                }
+            }
+            if (t == 0) break;
+            // beta_{t-1}: delta_j = p_tj + lb_tj published, then the transposed recursion
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < S / 4; ++q)
+                reinterpret_cast<float4*>(buf + lane * S)[q] = make_float4(p[4 * q] + lb[4 * q], p[4 * q + 1] + lb[4 * q + 1],
+                                                                           p[4 * q + 2] + lb[4 * q + 2], p[4 * q + 3] + lb[4 * q + 3]);
+            __syncwarp();
+            const float jv = (J > 0) ? junction_value(B, buf) : kNegInf;
+            lane_states(B, buf, jv, lb);
+            float mb = lb[0];
+#pragma unroll
+            for (int s = 1; s < S; ++s) mb = fmaxf(mb, lb[s]);
+            mb = warp_max(mb);
+            const float mbs = (mb == kNegInf) ? 0.f : mb;
+#pragma unroll
+            for (int s = 0; s < S; ++s) lb[s] -= mbs;
+        }
+        cp_async_wait<0>();
+        ell_d += (double)ell;
+        ell_d = warp_sum(ell_d);
+        double rs = 0.0;
+        if (a.frame_ref != nullptr)
+            for (int t = lane; t < T; t += 32) rs += (double)a.frame_ref[t0 + t];
+        rs = warp_sum(rs);
+        if (lane == 0) a.utt_exp_llh[u] = ell_d * (double)kLn2 + (double)a.scale * rs;
+        __syncwarp();
+    }
+}
+
+template <int S, int JR>
+static int launch_fb_fast(const FbArgs& a, int n_utts, cudaStream_t st) {
+    constexpr int PF = FbCfg<S>::PF;
+    size_t smem = sizeof(float) * (size_t)FB_WARPS * (32 * S + 2 * PF * 32 * S);
+    static bool attr_set = false;
+    if (!attr_set) {
+        BEER_CUDA_TRY(cudaFuncSetAttribute(hmm_fb_fast_kernel<S, JR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem));
+        attr_set = true;
+    }
+    int blocks = (n_utts + FB_WARPS - 1) / FB_WARPS;
+    int max_blocks = kNumSMs * 16;
+    if (blocks > max_blocks) blocks = max_blocks;
+    hmm_fb_fast_kernel<S, JR><<<blocks, FB_WARPS * 32, smem, st>>>(a);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
 // ------------------------------- Viterbi -----------------------------------
 struct VitArgs {
     ScanLists vit;
@@ -820,6 +1179,14 @@ int beer_graph_plan_create(const float* init_log, const float* final_log, const 
     p->map_identity = 1;
     for (int k = 0; k < K; ++k)
         if (pdf_map[k] != k) p->map_identity = 0;
+    {
+        int max_cnt = 0, jr = 0;
+        for (int v : hf.st_cnt) max_cnt = std::max(max_cnt, v);
+        for (int v : hb.st_cnt) max_cnt = std::max(max_cnt, v);
+        if (J > 0) jr = std::max(hf.jn_cnt[0], hb.jn_cnt[0]);
+        p->jrows = jr;
+        p->fast_ok = (max_cnt <= 2 && J <= 1 && jr <= 2 && (S == 4 || S == 8) && K % 4 == 0) ? 1 : 0;
+    }
     *plan_out = p;
     return BEER_OK;
 }
@@ -863,6 +1230,13 @@ int beer_hmm_forward_backward(const beer_graph_plan* plan, const float* pdf_llh,
     a.frame_exp_llh = frame_exp_llh; a.utt_exp_llh = utt_exp_llh; a.utt_logz = utt_logz;
     a.vec = (plan->map_identity && plan->S % 4 == 0 && plan->K % 4 == 0 && ld_pdf % 4 == 0 &&
              ((uintptr_t)pdf_llh & 15) == 0) ? 1 : 0;
+    if (plan->fast_ok && a.vec && (state_post == nullptr || plan->K % 4 == 0) &&
+        (pdf_post == nullptr || (ld_post % 4 == 0 && ((uintptr_t)pdf_post & 15) == 0)) &&
+        (state_post == nullptr || ((uintptr_t)state_post & 15) == 0) && getenv("BEER_B200_GENERIC_SCAN") == nullptr) {
+        const int jr = plan->jrows <= 1 ? 1 : 2;
+        if (plan->S == 4) return jr == 1 ? launch_fb_fast<4, 1>(a, n_utts, st) : launch_fb_fast<4, 2>(a, n_utts, st);
+        if (plan->S == 8) return jr == 1 ? launch_fb_fast<8, 1>(a, n_utts, st) : launch_fb_fast<8, 2>(a, n_utts, st);
+    }
     switch (plan->S) {
         case 1: return launch_fb<1>(a, n_utts, st);
         case 2: return launch_fb<2>(a, n_utts, st);
