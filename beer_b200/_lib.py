@@ -46,6 +46,17 @@ SIGNATURES = {
     'beer_dirichlet_update': (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_double, C.c_double, C.c_int, C.c_int,
                                         c_ptr]),
     'beer_dirichlet_kl': (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, c_ptr, c_ptr]),
+    'beer_normal_sufficient_statistics': (C.c_int, [c_ptr, C.c_int64, C.c_int, c_ptr, c_ptr]),
+    'beer_normalgamma_natural_params': (C.c_int, [c_ptr] * 4 + [C.c_int, C.c_int, c_ptr, c_ptr]),
+    'beer_normalgamma_from_natural': (C.c_int, [c_ptr, C.c_int, C.c_int] + [c_ptr] * 5),
+    'beer_normalgamma_log_norm': (C.c_int, [c_ptr] * 3 + [C.c_int, C.c_int, c_ptr, c_ptr]),
+    'beer_dirichlet_natural_params': (C.c_int, [c_ptr, C.c_int, C.c_int, c_ptr, c_ptr]),
+    'beer_dirichlet_expected_stats': (C.c_int, [c_ptr, C.c_int, C.c_int, c_ptr, c_ptr]),
+    'beer_dirichlet_log_norm': (C.c_int, [c_ptr, C.c_int, C.c_int, c_ptr, c_ptr]),
+    'beer_dirichlet_from_natural': (C.c_int, [c_ptr, C.c_int, C.c_int, c_ptr, c_ptr]),
+    'beer_segment_logsumexp': (C.c_int, [c_ptr, C.c_int64, C.c_int, c_ptr, C.c_int, c_ptr, C.c_int64, c_ptr]),
+    'beer_path_posteriors': (C.c_int, [c_ptr, C.c_int64, c_ptr, C.c_float, c_ptr, C.c_int64, c_ptr, c_ptr,
+                                       C.c_int64, C.c_int, c_ptr, c_ptr]),
 }
 
 _lib = None

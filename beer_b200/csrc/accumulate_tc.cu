@@ -69,8 +69,11 @@ struct Cfg {
     static constexpr int NCH = NB / 16;          // 16-column chunks of the accumulator
     static constexpr int MYCH = (NCH + 1) / 2;   // chunks drained by one thread (two warps share a row)
     static constexpr uint32_t TMEM_COLS = 2 * NB <= 64 ? 64 : (2 * NB <= 128 ? 128 : (2 * NB <= 256 ? 256 : 512));
-    // running sums across tiles: fp64 registers when they fit, fp32 (round-to-nearest) otherwise
+    // running sums across drains: fp64 registers when they fit, fp32 (round-to-nearest) otherwise
     using acc_t = typename std::conditional<(MYCH <= 3), double, float>::type;
+    // stages accumulated in TMEM between drains: 64 frames = 24 truncating accumulations (the
+    // float -> double conversions of the drain issue on the quarter-rate XU pipe)
+    static constexpr int DR = 64 / KF;
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_FLOATS * 4 + GM * 4 + sizeof(Barriers) + 1024;
 };
 
@@ -147,9 +150,10 @@ __global__ void __launch_bounds__(THREADS, 1) accumulate_tc_kernel(Args a) {
             constexpr uint32_t LBO = 128, SBO = (KF / 4) * 128;
             for (int it = 0; it < n_tiles; ++it) {
                 const int st = it % STAGES;
-                const int buf = it & 1;
+                const int grp = it / C::DR, buf = grp & 1;
+                const bool first = it % C::DR == 0, last = (it % C::DR == C::DR - 1) || it == n_tiles - 1;
                 mbar_wait(&bars->full[st], (it / STAGES) & 1);
-                mbar_wait(&bars->tempty[buf], ((it >> 1) & 1) ^ 1);
+                if (first) mbar_wait(&bars->tempty[buf], ((grp >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * NB);
                 const uint32_t a_hi = smem_u32(stage_base + (size_t)st * C::STAGE_FLOATS);
@@ -162,12 +166,12 @@ __global__ void __launch_bounds__(THREADS, 1) accumulate_tc_kernel(Args a) {
                     const uint64_t dah = make_desc(a_hi + ko, LBO, SBO), dal = make_desc(a_lo + ko, LBO, SBO);
                     const uint64_t dbh = make_desc(b_hi + ko, LBO, SBO), dbl = make_desc(b_lo + ko, LBO, SBO);
                     // the TMEM accumulation truncates: keep it short (KF frames), sum tiles in registers
-                    umma_tf32(d_tmem, dah, dbh, idesc, ks != 0);
+                    umma_tf32(d_tmem, dah, dbh, idesc, !(first && ks == 0));
                     umma_tf32(d_tmem, dal, dbh, idesc, 1);
                     umma_tf32(d_tmem, dah, dbl, idesc, 1);
                 }
                 umma_commit(&bars->empty[st]);
-                umma_commit(&bars->tfull[buf]);
+                if (last) umma_commit(&bars->tfull[buf]);
             }
         }
     } else {
@@ -187,17 +191,17 @@ __global__ void __launch_bounds__(THREADS, 1) accumulate_tc_kernel(Args a) {
         float xb[C::BU][4];
 
         // drain: TMEM lane quarter q (row = Gaussian), 16-column chunks half, half + 2, ...
-        using acc_t = typename C::acc_t;
         const int q = warp & 3, half = warp >> 2;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        using acc_t = typename C::acc_t;
         acc_t sums[C::MYCH][16];
 #pragma unroll
         for (int m = 0; m < C::MYCH; ++m)
 #pragma unroll
             for (int i = 0; i < 16; ++i) sums[m][i] = (acc_t)0;
-        auto drain = [&](int it) {
-            const int buf = it & 1;
-            mbar_wait(&bars->tfull[buf], (it >> 1) & 1);
+        auto drain = [&](int g) {      // g = drain group (DR stages)
+            const int buf = g & 1;
+            mbar_wait(&bars->tfull[buf], (g >> 1) & 1);
             tc_fence_after();
 #pragma unroll
             for (int m = 0; m < C::MYCH; ++m) {
@@ -213,16 +217,53 @@ __global__ void __launch_bounds__(THREADS, 1) accumulate_tc_kernel(Args a) {
             mbar_arrive(&bars->tempty[buf]);
         };
 
+        // per-thread constants of the gathers (inactive threads read a valid cell and never store it)
+        const int gl_c = a_active ? gl : 0;
+        const int kpdf_c = a_active ? kpdf : 0;
+        int xd[C::BU], xfq[C::BU];
+        bool x_active[C::BU];
+#pragma unroll
+        for (int j = 0; j < C::BU; ++j) {
+            const int u = tid + j * PRODUCERS;
+            x_active[j] = u < (KF / 4) * D;
+            xd[j] = x_active[j] ? u % D : 0;
+            xfq[j] = x_active[j] ? u / D : 0;
+        }
+
+        // Loads of one stage straight into their registers, nothing consumed here, so that they all
+        // stay in flight together (a select right behind each load made ptxas funnel them through
+        // one temporary: one DRAM round trip per load).  Full stages carry no predicates at all.
         auto load_tile = [&](int it) {
             const int64_t t0 = f_begin + (int64_t)it * KF;
+            if (t0 + KF <= f_end) {
+                const float* pp = (a.pdf_post != nullptr) ? a.pdf_post + (size_t)(t0 + fq0 * 4) * a.ld_post + kpdf_c : nullptr;
+                const float* pc = MIX ? a.comp_llh + (size_t)(t0 + fq0 * 4) * a.M + g0 + gl_c : nullptr;
+                const float* pl = MIX ? a.pdf_llh + (size_t)(t0 + fq0 * 4) * a.ld_pdf + kpdf_c : nullptr;
+#pragma unroll
+                for (int j = 0; j < AU; ++j) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = 8 * j + i;   // frame offset of quad fq0 + 2j
+                        wa[j][i] = (pp != nullptr) ? __ldg(pp + (size_t)r * a.ld_post) : 1.f;
+                        if constexpr (MIX) {
+                            ca[j][i] = __ldg(pc + (size_t)r * a.M);
+                            la[j][i] = __ldg(pl + (size_t)r * a.ld_pdf);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < C::BU; ++j) {
+                    const float* px = a.X + (size_t)(t0 + xfq[j] * 4) * D + xd[j];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) xb[j][i] = __ldg(px + i * D);
+                }
+                return;
+            }
 #pragma unroll
             for (int j = 0; j < AU; ++j) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int64_t t = t0 + (fq0 + 2 * j) * 4 + i;
-                    // predicated loads straight into their registers, nothing consumed here: all the
-                    // loads of a tile stay in flight together (a select right behind each load made
-                    // ptxas funnel them through one temporary, i.e. one DRAM round trip per load)
                     const bool ok = a_active && t < f_end;
                     wa[j][i] = (a.pdf_post != nullptr) ? 0.f : (ok ? 1.f : 0.f);
                     if (ok && a.pdf_post != nullptr) wa[j][i] = __ldg(a.pdf_post + (size_t)t * a.ld_post + kpdf);
@@ -238,12 +279,11 @@ __global__ void __launch_bounds__(THREADS, 1) accumulate_tc_kernel(Args a) {
             }
 #pragma unroll
             for (int j = 0; j < C::BU; ++j) {
-                const int u = tid + j * PRODUCERS;
-                const int d = u % D, fq = u / D;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int64_t t = t0 + fq * 4 + i;
-                    xb[j][i] = (u < (KF / 4) * D && t < f_end) ? __ldg(a.X + (size_t)t * D + d) : 0.f;
+                    const int64_t t = t0 + xfq[j] * 4 + i;
+                    xb[j][i] = 0.f;
+                    if (x_active[j] && t < f_end) xb[j][i] = __ldg(a.X + (size_t)t * D + xd[j]);
                 }
             }
         };
@@ -265,7 +305,7 @@ __global__ void __launch_bounds__(THREADS, 1) accumulate_tc_kernel(Args a) {
                         float w = wa[j][i];
                         if constexpr (MIX) w = (w != 0.f) ? w * __expf(ca[j][i] - la[j][i]) : 0.f;
                         h[i] = tf32_rn(w);
-                        l[i] = tf32_rn(w - h[i]);
+                        l[i] = w - h[i];
                     }
                     const int off = a_row + (fq0 + 2 * j) * 32;
                     *reinterpret_cast<float4*>(A_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
@@ -274,17 +314,16 @@ __global__ void __launch_bounds__(THREADS, 1) accumulate_tc_kernel(Args a) {
             }
 #pragma unroll
             for (int j = 0; j < C::BU; ++j) {
-                const int u = tid + j * PRODUCERS;
-                if (u < (KF / 4) * D) {
-                    const int d = u % D, fq = u / D;
+                if (x_active[j]) {
+                    const int d = xd[j], fq = xfq[j];
                     float xh[4], xl[4], qh[4], ql[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const float x = xb[j][i], q = x * x;
                         xh[i] = tf32_rn(x);
-                        xl[i] = tf32_rn(x - xh[i]);
+                        xl[i] = x - xh[i];
                         qh[i] = tf32_rn(q);
-                        ql[i] = tf32_rn(q - qh[i]);
+                        ql[i] = q - qh[i];
                     }
                     const int offx = (d >> 3) * (KF * 8) + fq * 32 + (d & 7) * 4;
                     const int offq = ((D + d) >> 3) * (KF * 8) + fq * 32 + ((D + d) & 7) * 4;
@@ -297,12 +336,13 @@ __global__ void __launch_bounds__(THREADS, 1) accumulate_tc_kernel(Args a) {
             fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core
             mbar_arrive(&bars->full[st]);
             if (it + 1 < n_tiles) load_tile(it + 1);
-            if (it > 0) drain(it - 1);
+            // the previous group's MMAs have had a whole stage to finish
+            if (it % C::DR == 0 && it > 0) drain(it / C::DR - 1);
         }
 
         // ------------------------------ epilogue ---------------------------------
         if (n_tiles > 0) {
-            drain(n_tiles - 1);
+            drain((n_tiles - 1) / C::DR);
             const int g = q * 32 + lane;
             if (g < ng) {
                 const int Q = 2 * D + 2;

@@ -5,6 +5,7 @@
 //
 // Reference semantics: beer/dists/normalgamma.py, beer/dists/dirichlet.py,
 // beer/dists/basedist.py:243-263, beer/models/parameters.py:134-141.
+#include <algorithm>
 #include "common.cuh"
 #include "../../include/beer_b200.h"
 
@@ -237,6 +238,144 @@ __global__ void dir_kl_kernel(const float* __restrict__ prior, const float* __re
     if ((threadIdx.x & 31) == 0 && val != 0.0) atomicAdd(kl, val);
 }
 
+
+// ---- API-completeness kernels (beer.dists accessors; not on the VB iteration's hot path) -------
+
+// [x, -x^2/2, -1/2, 1/2] per frame (beer/dists/normalgamma.py:19-27).
+__global__ void normal_suff_stats_kernel(const float* __restrict__ X, int64_t N, int D, float* __restrict__ out) {
+    const int Q = 2 * D + 2;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < N * Q; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t t = e / Q;
+        const int c = (int)(e - t * Q);
+        float v;
+        if (c < D) v = X[t * D + c];
+        else if (c < 2 * D) { const float x = X[t * D + c - D]; v = -0.5f * x * x; }
+        else v = (c == 2 * D) ? -0.5f : 0.5f;
+        out[e] = v;
+    }
+}
+
+// eta = [k m, -k m^2 / 2 - b, -k / 2, a - 1/2] (normalgamma.py:163-180), one warp per Gaussian.
+__global__ void ng_natural_kernel(const float* __restrict__ mean, const float* __restrict__ scale,
+                                  const float* __restrict__ shape, const float* __restrict__ rates, int M, int D,
+                                  float* __restrict__ out) {
+    int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (j >= M) return;
+    const int Q = 2 * D + 2;
+    const double k = scale[j], a = shape[j];
+    for (int d = lane; d < D; d += 32) {
+        const double m = mean[(size_t)j * D + d], b = rates[(size_t)j * D + d];
+        out[(size_t)j * Q + d] = (float)(k * m);
+        out[(size_t)j * Q + D + d] = (float)(-0.5 * k * m * m - b);
+    }
+    if (lane == 0) {
+        out[(size_t)j * Q + 2 * D] = (float)(-0.5 * k);
+        out[(size_t)j * Q + 2 * D + 1] = (float)(a - 0.5);
+    }
+}
+
+// inverse map (normalgamma.py:76-94)
+__global__ void ng_from_natural_kernel(const float* __restrict__ nat, int M, int D, float* __restrict__ mean,
+                                       float* __restrict__ scale, float* __restrict__ shape,
+                                       float* __restrict__ rates) {
+    int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (j >= M) return;
+    const int Q = 2 * D + 2;
+    const double k = -2.0 * (double)nat[(size_t)j * Q + 2 * D];
+    for (int d = lane; d < D; d += 32) {
+        const double m = (double)nat[(size_t)j * Q + d] / k;
+        mean[(size_t)j * D + d] = (float)m;
+        rates[(size_t)j * D + d] = (float)(-(double)nat[(size_t)j * Q + D + d] - 0.5 * k * m * m);
+    }
+    if (lane == 0) {
+        scale[j] = (float)k;
+        shape[j] = (float)((double)nat[(size_t)j * Q + 2 * D + 1] + 0.5);
+    }
+}
+
+// A(eta) = D lgamma(a) - a sum ln b - D/2 ln k (normalgamma.py:151-157)
+__global__ void ng_log_norm_kernel(const float* __restrict__ scale, const float* __restrict__ shape,
+                                   const float* __restrict__ rates, int M, int D, double* __restrict__ out) {
+    int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (j >= M) return;
+    double s = 0.0;
+    for (int d = lane; d < D; d += 32) s += log((double)rates[(size_t)j * D + d]);
+    s = warp_sum(s);
+    const double a = shape[j], k = scale[j];
+    if (lane == 0) out[j] = D * lgamma(a) - a * s - 0.5 * D * log(k);
+}
+
+// per-Gaussian KL (the vector kl_div returns, basedist.py:243-263): same arithmetic as ng_kl_kernel
+__global__ void dir_rows_kernel(const float* __restrict__ conc, int K, int C, int what, float* __restrict__ outf,
+                                double* __restrict__ outd) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const float* q = conc + (size_t)k * C;
+    double tot = 0.0;
+    for (int c = 0; c < C; ++c) tot += q[c];
+    if (what == 0) {            // natural parameters [a_i - 1 (i < C-1), sum_i (a_i - 1)] (dirichlet.py:144-159)
+        for (int c = 0; c < C - 1; ++c) outf[(size_t)k * C + c] = (float)((double)q[c] - 1.0);
+        outf[(size_t)k * C + C - 1] = (float)(tot - C);
+    } else if (what == 1) {     // expected statistics, log-odds form (dirichlet.py:106-128)
+        const double psi_last = digamma_d((double)q[C - 1]);
+        for (int c = 0; c < C - 1; ++c) outf[(size_t)k * C + c] = (float)(digamma_d((double)q[c]) - psi_last);
+        outf[(size_t)k * C + C - 1] = (float)(psi_last - digamma_d(tot));
+    } else if (what == 2) {     // log-normaliser (dirichlet.py:135-138)
+        double A = 0.0;
+        for (int c = 0; c < C; ++c) A += lgamma((double)q[c]);
+        outd[k] = A - lgamma(tot);
+    } else {                    // from natural parameters, in: conc holds eta (dirichlet.py:70-81)
+        double s = 0.0;
+        for (int c = 0; c < C - 1; ++c) {
+            s += q[c];
+            outf[(size_t)k * C + c] = (float)((double)q[c] + 1.0);
+        }
+        outf[(size_t)k * C + C - 1] = (float)((double)q[C - 1] - s + 1.0);
+    }
+}
+
+// pdf_llh[t, k] = logsumexp_{j in pdf k} comp_llh[t, j]: mixtures wider than one emission tile
+__global__ void segment_lse_kernel(const float* __restrict__ comp, int64_t N, int M,
+                                   const int32_t* __restrict__ comp_off, int Kp, float* __restrict__ out,
+                                   int64_t ld) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t e = gw; e < N * Kp; e += nw) {
+        const int64_t t = e / Kp;
+        const int k = (int)(e - t * Kp);
+        int c0, c1;
+        if (comp_off == nullptr) { const int C = M / Kp; c0 = k * C; c1 = c0 + C; }
+        else { c0 = comp_off[k]; c1 = comp_off[k + 1]; }
+        const float* row = comp + (size_t)t * M;
+        float m = kNegInf;
+        for (int c = c0 + lane; c < c1; c += 32) m = fmaxf(m, row[c]);
+        m = warp_max(m);
+        const float ms = (m == kNegInf) ? 0.f : m;
+        float s = 0.f;
+        for (int c = c0 + lane; c < c1; c += 32) s += __expf(row[c] - ms);
+        s = warp_sum(s);
+        if (lane == 0) out[(size_t)t * ld + k] = ms + __logf(s);
+    }
+}
+
+// Posteriors of a given state path (Viterbi training / forced path, beer/models/hmm.py:42-58, 87):
+// pdf_post[t, map[path_t]] = scale, frame_exp_llh[t] = scale * (pdf_llh[t, map[path_t]] + frame_ref[t]).
+__global__ void path_posteriors_kernel(const int32_t* __restrict__ path, int64_t N, const int32_t* __restrict__ map,
+                                       float scale, const float* __restrict__ pdf_llh, int64_t ld_pdf,
+                                       const float* __restrict__ frame_ref, float* __restrict__ pdf_post,
+                                       int64_t ld_post, int Kp, float* __restrict__ frame_exp_llh) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < N; t += (int64_t)gridDim.x * blockDim.x) {
+        const int s = path[t];
+        const int k = (map != nullptr) ? map[s] : s;
+        if (pdf_post != nullptr) {
+            float* row = pdf_post + (size_t)t * ld_post;
+            for (int c = 0; c < Kp; ++c) row[c] = (c == k) ? scale : 0.f;
+        }
+        if (frame_exp_llh != nullptr)
+            frame_exp_llh[t] = scale * (pdf_llh[(size_t)t * ld_pdf + k] + (frame_ref != nullptr ? frame_ref[t] : 0.f));
+    }
+}
+
 }  // namespace beer
 
 using namespace beer;
@@ -308,6 +447,85 @@ int beer_dirichlet_update(const float* prior_conc, float* conc, const double* ac
 int beer_dirichlet_kl(const float* prior_conc, const float* conc, int K, int C, double* kl, void* stream) {
     if (K <= 0 || C <= 0) return BEER_ERR_ARG;
     dir_kl_kernel<<<(K + 127) / 128, 128, 0, (cudaStream_t)stream>>>(prior_conc, conc, K, C, kl);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
+int beer_normal_sufficient_statistics(const float* X, int64_t N, int D, float* out, void* stream) {
+    if (!X || !out || N < 0 || D <= 0) return BEER_ERR_ARG;
+    if (N == 0) return BEER_OK;
+    int64_t total = N * (2 * D + 2);
+    int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
+    normal_suff_stats_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(X, N, D, out);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
+int beer_normalgamma_natural_params(const float* mean, const float* scale, const float* shape, const float* rates,
+                                    int M, int D, float* nat, void* stream) {
+    if (M <= 0 || D <= 0) return BEER_ERR_ARG;
+    ng_natural_kernel<<<(M * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mean, scale, shape, rates, M, D, nat);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
+int beer_normalgamma_from_natural(const float* nat, int M, int D, float* mean, float* scale, float* shape,
+                                  float* rates, void* stream) {
+    if (M <= 0 || D <= 0) return BEER_ERR_ARG;
+    ng_from_natural_kernel<<<(M * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(nat, M, D, mean, scale, shape,
+                                                                                   rates);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
+int beer_normalgamma_log_norm(const float* scale, const float* shape, const float* rates, int M, int D,
+                              double* out, void* stream) {
+    if (M <= 0 || D <= 0) return BEER_ERR_ARG;
+    ng_log_norm_kernel<<<(M * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(scale, shape, rates, M, D, out);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
+static int dir_rows(const float* in, int K, int C, int what, float* outf, double* outd, void* stream) {
+    if (!in || K <= 0 || C <= 0) return BEER_ERR_ARG;
+    dir_rows_kernel<<<(K + 127) / 128, 128, 0, (cudaStream_t)stream>>>(in, K, C, what, outf, outd);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+int beer_dirichlet_natural_params(const float* conc, int K, int C, float* nat, void* stream) {
+    return dir_rows(conc, K, C, 0, nat, nullptr, stream);
+}
+int beer_dirichlet_expected_stats(const float* conc, int K, int C, float* ets, void* stream) {
+    return dir_rows(conc, K, C, 1, ets, nullptr, stream);
+}
+int beer_dirichlet_log_norm(const float* conc, int K, int C, double* out, void* stream) {
+    return dir_rows(conc, K, C, 2, nullptr, out, stream);
+}
+int beer_dirichlet_from_natural(const float* nat, int K, int C, float* conc, void* stream) {
+    return dir_rows(nat, K, C, 3, conc, nullptr, stream);
+}
+
+int beer_segment_logsumexp(const float* comp_llh, int64_t N, int M, const int32_t* comp_off, int Kp,
+                           float* pdf_llh, int64_t ld_pdf, void* stream) {
+    if (!comp_llh || !pdf_llh || N < 0 || M <= 0 || Kp <= 0 || ld_pdf < Kp) return BEER_ERR_ARG;
+    if (comp_off == nullptr && M % Kp != 0) return BEER_ERR_ARG;
+    if (N == 0) return BEER_OK;
+    int64_t warps = N * Kp;
+    int blocks = (int)std::min<int64_t>((warps + 7) / 8, 148 * 16);
+    segment_lse_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(comp_llh, N, M, comp_off, Kp, pdf_llh, ld_pdf);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
+int beer_path_posteriors(const int32_t* path, int64_t N, const int32_t* pdf_map, float scale, const float* pdf_llh,
+                         int64_t ld_pdf, const float* frame_ref, float* pdf_post, int64_t ld_post, int Kp,
+                         float* frame_exp_llh, void* stream) {
+    if (!path || N < 0 || Kp <= 0) return BEER_ERR_ARG;
+    if (frame_exp_llh != nullptr && pdf_llh == nullptr) return BEER_ERR_ARG;
+    if (N == 0) return BEER_OK;
+    int blocks = (int)std::min<int64_t>((N + 127) / 128, 148 * 16);
+    path_posteriors_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(path, N, pdf_map, scale, pdf_llh, ld_pdf,
+                                                                     frame_ref, pdf_post, ld_post, Kp, frame_exp_llh);
     BEER_LAUNCH_CHECK();
     return BEER_OK;
 }

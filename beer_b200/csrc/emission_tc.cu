@@ -6,7 +6,7 @@
 // Operands live in shared memory in the canonical no-swizzle K-major core-matrix layout
 // ([row/8][k/4][row%8][k%4], 128-byte core matrices).  The weight image is packed once per VB
 // iteration by beer_emission_tc_pack and streamed in with cp.async.bulk (TMA, 1-D); the
-// statistics tile is built by the worker warps from X (hi = rn_tf32(x), lo = rn_tf32(x - hi)).
+// statistics tile is built by the worker warps from X (hi = rn_tf32(x), lo = x - hi).
 // Accumulators are fp32 in TMEM (double buffered); the epilogue reads them back with
 // tcgen05.ld, adds the bias, takes the log-sum-exp over the C components of each pdf and
 // stores the offset-form llh.
@@ -172,10 +172,10 @@ __global__ void __launch_bounds__(THREADS, 1) emission_tc_kernel(Args a) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     h[e] = tf32_rn(x[e]);
-                    l[e] = tf32_rn(x[e] - h[e]);
+                    l[e] = x[e] - h[e];
                     const float q = -0.5f * x[e] * x[e];
                     qh[e] = tf32_rn(q);
-                    ql[e] = tf32_rn(q - qh[e]);
+                    ql[e] = q - qh[e];
                     rt = fmaf(q, s_ref[4 * c + e], rt);
                 }
                 *reinterpret_cast<float4*>(A_hi + rbase + c * 32) = make_float4(h[0], h[1], h[2], h[3]);

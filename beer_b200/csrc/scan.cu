@@ -563,7 +563,7 @@ __device__ __forceinline__ void load_lane_lists(LaneLists<S, JR>& L, const ScanL
                 L.jmask |= 1u << (2 * s + c);
                 src = 0;
             }
-            L.src[s][c] = src;
+            L.src[s][c] = (src % S) * 32 + src / S;   // slot-major position in buf (conflict-free reads)
             L.w[s][c] = w;
         }
     }
@@ -574,7 +574,8 @@ __device__ __forceinline__ void load_lane_lists(LaneLists<S, JR>& L, const ScanL
         L.jw[r] = kNegInf;
         if (r < jcnt) {
             const int i = (jrow0 + r) * 32 + lane;
-            L.jsrc[r] = __ldg(l.src + i);
+            const int src = __ldg(l.src + i);
+            L.jsrc[r] = (src % S) * 32 + src / S;
             L.jw[r] = __ldg(l.lw + i);
         }
     }
@@ -624,7 +625,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_fast_kernel(FbArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int per_warp = ROW + 2 * PF * ROW;
-    float* buf = smem + (size_t)warp * per_warp;   // [32 * S] published per-state values
+    float* buf = smem + (size_t)warp * per_warp;   // [S][32] published per-state values, slot-major
     float* ring_p = buf + ROW;                     // [PF][32 * S]
     float* ring_a = ring_p + PF * ROW;             // [PF][32 * S]
     const int K = a.K, J = a.J;
@@ -707,8 +708,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_fast_kernel(FbArgs a) {
             for (int s = 0; s < S; ++s) cur[s] -= mxs;
             __syncwarp();  // every lane has finished reading buf
 #pragma unroll
-            for (int v = 0; v < S / 4; ++v)
-                reinterpret_cast<float4*>(buf + lane * S)[v] = make_float4(cur[4 * v], cur[4 * v + 1], cur[4 * v + 2], cur[4 * v + 3]);
+            for (int s = 0; s < S; ++s) buf[s * 32 + lane] = cur[s];
             __syncwarp();
             if (own) {
                 float* la_row = la_u + (size_t)t * a.Kw + lane * S;
@@ -839,9 +839,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_fast_kernel(FbArgs a) {
             // beta_{t-1}: delta_j = p_tj + lb_tj published, then the transposed recursion
             __syncwarp();
 #pragma unroll
-            for (int q = 0; q < S / 4; ++q)
-                reinterpret_cast<float4*>(buf + lane * S)[q] = make_float4(p[4 * q] + lb[4 * q], p[4 * q + 1] + lb[4 * q + 1],
-                                                                           p[4 * q + 2] + lb[4 * q + 2], p[4 * q + 3] + lb[4 * q + 3]);
+            for (int s = 0; s < S; ++s) buf[s * 32 + lane] = p[s] + lb[s];
             __syncwarp();
             const float jv = (J > 0) ? junction_value(B, buf) : kNegInf;
             lane_states(B, buf, jv, lb);

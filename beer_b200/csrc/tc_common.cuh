@@ -34,11 +34,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-// fp32 -> tf32, round to nearest (low 13 mantissa bits cleared): the hi part of the split.
+// fp32 -> tf32, round to nearest / ties away (low 13 mantissa bits cleared): the hi part of the
+// 3xTF32 split.  Two integer-pipe instructions instead of cvt.rna.tf32.f32, which issues on the
+// quarter-rate XU pipe (it was 23 % of the statistics kernel's pipe time).  The lo part x - hi is
+// handed to the tensor core unrounded: the MMA ignores the 13 low mantissa bits (|err| <= 2^-21 |x|).
 __device__ __forceinline__ float tf32_rn(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

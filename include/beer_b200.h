@@ -204,6 +204,41 @@ BEER_API int beer_dirichlet_update(const float* prior_conc, float* conc, const d
 BEER_API int beer_dirichlet_kl(const float* prior_conc, const float* conc, int K, int C, double* kl,
                       void* stream);
 
+
+/* ------------------------------------------------------------------------
+ * beer.dists accessors (API completeness; none of them is on the per-iteration hot path)
+ * ---------------------------------------------------------------------- */
+
+/* T(x) = [x, -x^2/2, -1/2, 1/2], out [N, 2D+2].  Replaces
+ * NormalDiagonalLikelihood.sufficient_statistics (beer/dists/normalgamma.py:19-27). */
+BEER_API int beer_normal_sufficient_statistics(const float* X, int64_t N, int D, float* out, void* stream);
+/* NormalGamma.natural_parameters (normalgamma.py:163-180), nat [M, 2D+2]. */
+BEER_API int beer_normalgamma_natural_params(const float* mean, const float* scale, const float* shape,
+                                    const float* rates, int M, int D, float* nat, void* stream);
+/* NormalGammaStdParams.from_natural_parameters (normalgamma.py:76-94). */
+BEER_API int beer_normalgamma_from_natural(const float* nat, int M, int D, float* mean, float* scale, float* shape,
+                                  float* rates, void* stream);
+/* NormalGamma.log_norm (normalgamma.py:151-157), out [M] fp64. */
+BEER_API int beer_normalgamma_log_norm(const float* scale, const float* shape, const float* rates, int M, int D,
+                              double* out, void* stream);
+/* Dirichlet.natural_parameters / expected_sufficient_statistics (log-odds form) / log_norm /
+ * DirichletStdParams.from_natural_parameters (beer/dists/dirichlet.py:144-159, 106-128, 135-138, 70-81). */
+BEER_API int beer_dirichlet_natural_params(const float* conc, int K, int C, float* nat, void* stream);
+BEER_API int beer_dirichlet_expected_stats(const float* conc, int K, int C, float* ets, void* stream);
+BEER_API int beer_dirichlet_log_norm(const float* conc, int K, int C, double* out, void* stream);
+BEER_API int beer_dirichlet_from_natural(const float* nat, int K, int C, float* conc, void* stream);
+
+/* pdf_llh[t, k] = logsumexp over the Gaussians of pdf k of comp_llh[t, :] (mixtures with more
+ * Gaussians than one emission tile holds: Mixture.expected_log_likelihood, beer/models/mixture.py:79-83). */
+BEER_API int beer_segment_logsumexp(const float* comp_llh, int64_t N, int M, const int32_t* comp_off, int Kp,
+                           float* pdf_llh, int64_t ld_pdf, void* stream);
+
+/* Posteriors of a GIVEN state path (viterbi=True / state_path=..., beer/models/hmm.py:42-58, 87):
+ * pdf_post[t, :] = scale * onehot(map[path_t]) (overwritten), frame_exp_llh[t] = scale * llh of that pdf. */
+BEER_API int beer_path_posteriors(const int32_t* path, int64_t N, const int32_t* pdf_map, float scale,
+                         const float* pdf_llh, int64_t ld_pdf, const float* frame_ref, float* pdf_post,
+                         int64_t ld_post, int Kp, float* frame_exp_llh, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
