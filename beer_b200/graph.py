@@ -222,6 +222,14 @@ class CompiledGraph(torch.nn.Module):
         self._plans[tag] = (key, plan)
         return plan
 
+    def pdf_map_device(self, device):
+        """pdf_id_mapping as an int32 tensor on `device` (cached)."""
+        cached = self._plans.get(('map', str(device)))
+        if cached is None:
+            cached = torch.as_tensor(np.asarray(self.pdf_id_mapping), dtype=torch.int32, device=device)
+            self._plans[('map', str(device))] = cached
+        return cached
+
     @staticmethod
     def _as_device_llhs(llhs):
         if not llhs.is_cuda:

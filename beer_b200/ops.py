@@ -286,3 +286,103 @@ def dirichlet_kl(prior, post, out=None):
     _lib.check(lib.beer_dirichlet_kl(_p(p2, f32), _p(q2, f32), K, Cc, _p(out, f64), _stream()),
                'beer_dirichlet_kl')
     return out
+
+
+# ---------------------------------------------------------------------------
+# beer.dists accessors
+# ---------------------------------------------------------------------------
+
+def normal_sufficient_statistics(X):
+    """T(x) = [x, -x^2/2, -1/2, 1/2] -> [N, 2D+2]."""
+    lib = require_cuda()
+    N, D = X.shape
+    out = torch.empty(N, 2 * D + 2, device=X.device, dtype=f32)
+    _lib.check(lib.beer_normal_sufficient_statistics(_p(X, f32), N, D, _p(out), _stream()),
+               'beer_normal_sufficient_statistics')
+    return out
+
+
+def normalgamma_natural_params(mean, scale, shape, rates):
+    lib = require_cuda()
+    M, D = mean.shape
+    out = torch.empty(M, 2 * D + 2, device=mean.device, dtype=f32)
+    _lib.check(lib.beer_normalgamma_natural_params(_p(mean, f32), _p(scale, f32), _p(shape, f32), _p(rates, f32),
+                                                   M, D, _p(out), _stream()), 'beer_normalgamma_natural_params')
+    return out
+
+
+def normalgamma_from_natural(nat):
+    """-> (mean [M,D], scale [M,1], shape [M,1], rates [M,D])."""
+    lib = require_cuda()
+    nat2 = nat.reshape(-1, nat.shape[-1]).contiguous()
+    M, Q = nat2.shape
+    D = (Q - 2) // 2
+    dev = nat.device
+    mean, rates = torch.empty(M, D, device=dev, dtype=f32), torch.empty(M, D, device=dev, dtype=f32)
+    scale, shape = torch.empty(M, 1, device=dev, dtype=f32), torch.empty(M, 1, device=dev, dtype=f32)
+    _lib.check(lib.beer_normalgamma_from_natural(_p(nat2, f32), M, D, _p(mean), _p(scale), _p(shape), _p(rates),
+                                                 _stream()), 'beer_normalgamma_from_natural')
+    return mean, scale, shape, rates
+
+
+def normalgamma_log_norm(mean, scale, shape, rates):
+    lib = require_cuda()
+    M, D = rates.shape
+    out = torch.empty(M, device=rates.device, dtype=f64)
+    _lib.check(lib.beer_normalgamma_log_norm(_p(scale, f32), _p(shape, f32), _p(rates, f32), M, D, _p(out),
+                                             _stream()), 'beer_normalgamma_log_norm')
+    return out
+
+
+def _dirichlet_rows(fn_name, conc, out_dtype=f32, per_row=False):
+    lib = require_cuda()
+    c2 = conc.reshape(-1, conc.shape[-1]).contiguous()
+    K, Cc = c2.shape
+    out = torch.empty(K if per_row else (K, Cc), device=conc.device, dtype=out_dtype)
+    _lib.check(getattr(lib, fn_name)(_p(c2, f32), K, Cc, _p(out), _stream()), fn_name)
+    if per_row:
+        return out if conc.dim() > 1 else out[0]
+    return out.reshape(conc.shape)
+
+
+def dirichlet_natural_params(conc):
+    return _dirichlet_rows('beer_dirichlet_natural_params', conc)
+
+
+def dirichlet_expected_stats(conc):
+    return _dirichlet_rows('beer_dirichlet_expected_stats', conc)
+
+
+def dirichlet_from_natural(nat):
+    return _dirichlet_rows('beer_dirichlet_from_natural', nat)
+
+
+def dirichlet_log_norm(conc):
+    return _dirichlet_rows('beer_dirichlet_log_norm', conc, out_dtype=f64, per_row=True)
+
+
+def segment_logsumexp(comp_llh, comp_off=None, Kp=1, out=None):
+    """pdf_llh[t, k] = logsumexp of comp_llh[t, comp_off[k]:comp_off[k+1]]."""
+    lib = require_cuda()
+    N, M = comp_llh.shape
+    if comp_off is not None:
+        Kp = comp_off.numel() - 1
+    pdf_llh = out if out is not None else torch.empty(N, Kp, device=comp_llh.device, dtype=f32)
+    _lib.check(lib.beer_segment_logsumexp(_p(comp_llh, f32), N, M, _p(comp_off, i32, True), Kp, _p(pdf_llh, f32),
+                                          pdf_llh.stride(0), _stream()), 'beer_segment_logsumexp')
+    return pdf_llh
+
+
+def path_posteriors(path, n_pdfs, pdf_map=None, scale=1.0, pdf_llh=None, frame_ref=None, want_post=True,
+                    want_frame_llh=True):
+    """Posteriors / per-frame expected llh of a given state path (int32 [N])."""
+    lib = require_cuda()
+    N = path.numel()
+    dev = path.device
+    post = torch.empty(N, n_pdfs, device=dev, dtype=f32) if want_post else None
+    frame = torch.empty(N, device=dev, dtype=f32) if want_frame_llh else None
+    _lib.check(lib.beer_path_posteriors(_p(path, i32), N, _p(pdf_map, i32, True), float(scale),
+                                        _p(pdf_llh, f32, True), pdf_llh.stride(0) if pdf_llh is not None else 0,
+                                        _p(frame_ref, f32, True), _p(post, f32, True), n_pdfs, n_pdfs,
+                                        _p(frame, f32, True), _stream()), 'beer_path_posteriors')
+    return post, frame

@@ -1,0 +1,258 @@
+"""GPU parity tests through the public, reference-shaped API (`import beer_b200 as beer`) against the
+fp64 goldens dumped from the live reference by tests/golden/make_goldens.py.  Each test mirrors the
+reference call sequence that produced its golden (same class names, same keyword arguments).
+
+Tolerances: ELBO / expected log-likelihood sums 1e-5 relative (north_star), posteriors 1e-5
+absolute, accumulated statistics 3e-5 of the largest entry, updated standard parameters 2e-4
+(they are fp32 tensors compared with an fp64 run), alignments identical.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+@pytest.fixture(scope='module')
+def beer():
+    import beer_b200
+    beer_b200.ops.require_cuda() if hasattr(beer_b200, 'ops') else None
+    return beer_b200
+
+
+def t32(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32, device=DEV)
+
+
+def set_ng(dist, g, prefix):
+    p = dist.params
+    for name in ('mean', 'scale', 'shape', 'rates'):
+        getattr(p, name).copy_(t32(g[prefix + name]).reshape(getattr(p, name).shape))
+
+
+def get_ng(dist):
+    p = dist.params
+    return [getattr(p, n).double().cpu().numpy() for n in ('mean', 'scale', 'shape', 'rates')]
+
+
+def compiled(beer, g, prefix='g_'):
+    return beer.CompiledGraph(torch.from_numpy(g[prefix + 'init']).float(), torch.from_numpy(g[prefix + 'final']).float(),
+                              torch.from_numpy(g[prefix + 'trans']).float(), [int(i) for i in g[prefix + 'map']])
+
+
+def normalset(beer, g, size, D, prior='prior_', post='post0_'):
+    ns = beer.NormalSet.create(torch.zeros(D, device=DEV), torch.ones(D, device=DEV), size=size, prior_strength=1.,
+                               noise_std=1., cov_type='diagonal')
+    set_ng(ns.means_precisions.prior, g, prior)
+    set_ng(ns.means_precisions.posterior, g, post)
+    return ns
+
+
+def vb_loop(beer, model, X, n_iter, **kw):
+    optim = beer.VBConjugateOptimizer(model.mean_field_factorization(), lrate=1.)
+    elbos = []
+    for _ in range(n_iter):
+        optim.init_step()
+        elbo = beer.evidence_lower_bound(model, X, datasize=len(X), **kw)
+        elbo.backward()
+        elbos.append(float(elbo))
+        optim.step()
+    return np.asarray(elbos)
+
+
+# ---------------------------------------------------------------------------------------------
+def test_dists_against_reference(beer):
+    g = load_golden('dists')
+    q = beer.dists.NormalGamma.from_std_parameters(t32(g['ng_mean']), t32(g['ng_scale']), t32(g['ng_shape']),
+                                                   t32(g['ng_rates']))
+    p = beer.dists.NormalGamma.from_std_parameters(t32(g['ngp_mean']), t32(g['ngp_scale']), t32(g['ngp_shape']),
+                                                   t32(g['ngp_rates']))
+    np.testing.assert_allclose(q.natural_parameters().cpu().numpy(), g['ng_nat'], rtol=2e-6, atol=1e-6)
+    np.testing.assert_allclose(q.expected_sufficient_statistics().cpu().numpy(), g['ng_ets'], rtol=2e-6, atol=1e-6)
+    np.testing.assert_allclose(q.log_norm().cpu().numpy(), g['ng_lognorm'], rtol=1e-6)
+    np.testing.assert_allclose(beer.dists.kl_div(q, p).item(), g['ng_kl'].sum(), rtol=1e-6)
+    back = beer.dists.NormalGammaStdParams.from_natural_parameters(t32(g['ng_nat']))
+    for name in ('mean', 'scale', 'shape', 'rates'):
+        np.testing.assert_allclose(getattr(back, name).cpu().numpy(), g['ng_back_' + name], rtol=2e-5, atol=2e-6)
+    lfn = q.conjugate()
+    stats = lfn.sufficient_statistics(t32(g['X']))
+    np.testing.assert_allclose(stats.cpu().numpy(), g['stats'], rtol=1e-6)
+    llh = lfn(q.expected_sufficient_statistics(), stats)
+    np.testing.assert_allclose(llh.cpu().numpy(), g['llh'], rtol=1e-5, atol=1e-4)
+    assert len(q) == 6 and q.dim == (6, 5, 5)
+
+    dq = beer.dists.Dirichlet.from_std_parameters(t32(g['dir_conc']))
+    dp = beer.dists.Dirichlet.from_std_parameters(t32(g['dirp_conc']))
+    np.testing.assert_allclose(dq.natural_parameters().cpu().numpy(), g['dir_nat'], rtol=2e-6, atol=1e-6)
+    np.testing.assert_allclose(dq.expected_sufficient_statistics().cpu().numpy(), g['dir_ets'], rtol=2e-6, atol=1e-6)
+    np.testing.assert_allclose(dq.log_norm().cpu().numpy(), g['dir_lognorm'], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(beer.dists.kl_div(dq, dp).item(), g['dir_kl'].sum(), rtol=1e-6)
+    dback = beer.dists.DirichletStdParams.from_natural_parameters(t32(g['dir_nat']))
+    np.testing.assert_allclose(dback.concentrations.cpu().numpy(), g['dir_back'], rtol=2e-6, atol=2e-6)
+    cl = dq.conjugate()
+    np.testing.assert_allclose(cl.sufficient_statistics(t32(g['cat_data'])).cpu().numpy(), g['cat_stats'], rtol=1e-6)
+    np.testing.assert_allclose(dq.expected_log_weights().cpu().numpy(), g['dir_logw'], rtol=2e-6, atol=1e-6)
+    with pytest.raises(beer.dists.DistributionTypeMismatch):
+        beer.dists.kl_div(q, dq)
+
+
+def test_mixture_cfg1(beer):
+    """BASELINE configs[0]: 8-component diagonal Mixture on 2-D points, the loop of examples/HMM.ipynb
+    cell 9 with a Mixture."""
+    g = load_golden('gmm_cfg1')
+    X = t32(g['X'])
+    ns = normalset(beer, g, 8, 2)
+    gmm = beer.Mixture.create(ns)
+    w = gmm.categorical.weights
+    w.prior.params.concentrations.copy_(t32(g['dprior']))
+    w.posterior.params.concentrations.copy_(t32(g['dpost0']))
+    par = gmm.modelset.means_precisions
+
+    stats = gmm.sufficient_statistics(X)
+    exp_llh = gmm.expected_log_likelihood(stats)
+    np.testing.assert_allclose(exp_llh.double().cpu().numpy(), g['exp_llh'], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(gmm.kl_div_posterior_prior().item(), g['kl'], rtol=1e-6)
+    acc = gmm.accumulate(stats)
+    assert np.abs(acc[par].cpu().numpy() - g['acc_normal']).max() <= 3e-5 * np.abs(g['acc_normal']).max()
+    np.testing.assert_allclose(acc[w].cpu().numpy(), g['acc_dirichlet'], rtol=2e-5)
+    gmm.clear_cache()
+    assert np.abs(gmm.posteriors(X).double().cpu().numpy() - g['resps']).max() <= 1e-5
+    # labelled path (mixture.py:84-87)
+    got = gmm.expected_log_likelihood(stats, labels=torch.from_numpy(g['labels']))
+    np.testing.assert_allclose(got.double().cpu().numpy(), g['exp_llh_labels'], rtol=1e-5, atol=1e-4)
+    gmm.clear_cache()
+    elbos = vb_loop(beer, gmm, X, 6)
+    np.testing.assert_allclose(elbos, g['elbos'], rtol=1e-5)
+    for got, name in zip(get_ng(par.posterior), ('mean', 'scale', 'shape', 'rates')):
+        np.testing.assert_allclose(got.reshape(g['post6_' + name].shape), g['post6_' + name], rtol=2e-4, atol=2e-4)
+    np.testing.assert_allclose(w.posterior.params.concentrations.cpu().numpy(), g['dpost6'], rtol=2e-4)
+
+
+@pytest.mark.parametrize('name,n_iter', [('hmm_small', 3), ('hmm_scaled', 3), ('hmm_cfg2_T200', 2)])
+def test_hmm_against_reference(beer, name, n_iter):
+    g = load_golden(name)
+    scale = float(g['scale'])
+    X = t32(g['X'])
+    T, D = g['X'].shape
+    graph = compiled(beer, g)
+    K = graph.n_states
+    ns = normalset(beer, g, K, D)
+    hmm = beer.HMM.create(graph, ns)
+    par = ns.means_precisions
+
+    stats = hmm.sufficient_statistics(X)
+    exp_llh = hmm.expected_log_likelihood(stats, inference_graph=hmm.graph, scale=scale)
+    np.testing.assert_allclose(exp_llh.double().sum().item(), g['exp_llh'].sum(), rtol=1e-5)
+    np.testing.assert_allclose(exp_llh.double().cpu().numpy(), g['exp_llh'], rtol=1e-4, atol=2e-3)
+    np.testing.assert_allclose(hmm.kl_div_posterior_prior().item(), g['kl'], rtol=1e-6)
+    acc = hmm.accumulate(stats)
+    assert np.abs(acc[par].cpu().numpy() - g['acc_normal']).max() <= 3e-5 * np.abs(g['acc_normal']).max()
+    hmm.clear_cache()
+    elbo = beer.evidence_lower_bound(hmm, X, datasize=3 * T, inference_graph=hmm.graph, scale=scale)
+    np.testing.assert_allclose(float(elbo), g['elbo_datasize3T'], rtol=1e-5)
+
+    # Viterbi: alignment, decode, one-hot E-step
+    pc = scale * ns.expected_log_likelihood(stats)[:, torch.as_tensor(graph.pdf_id_mapping, device=DEV)]
+    np.testing.assert_array_equal(hmm.graph.best_path(pc).numpy(), g['viterbi_path'])
+    np.testing.assert_array_equal(hmm.decode(X, scale=scale).numpy(), g['decode'])
+    assert np.abs(hmm.posteriors(X).double().cpu().numpy() - g['posteriors']).max() <= 1e-5
+    exp_llh_v = hmm.expected_log_likelihood(stats, inference_graph=hmm.graph, viterbi=True, scale=scale)
+    np.testing.assert_allclose(exp_llh_v.double().cpu().numpy(), g['exp_llh_viterbi'], rtol=1e-5, atol=2e-4)
+    acc_v = hmm.accumulate(stats)[par].cpu().numpy()
+    assert np.abs(acc_v - g['acc_normal_viterbi']).max() <= 3e-5 * np.abs(g['acc_normal_viterbi']).max()
+    hmm.clear_cache()
+    # a given state path is the same code path as Viterbi (hmm.py:45-48)
+    exp_llh_p = hmm.expected_log_likelihood(stats, inference_graph=hmm.graph, state_path=g['viterbi_path'],
+                                            scale=scale)
+    np.testing.assert_allclose(exp_llh_p.cpu().numpy(), exp_llh_v.cpu().numpy(), rtol=0, atol=0)
+    hmm.clear_cache()
+
+    elbos = vb_loop(beer, hmm, X, n_iter, inference_graph=hmm.graph, scale=scale)
+    np.testing.assert_allclose(elbos, g['elbos'], rtol=1e-5)
+    for got, pname in zip(get_ng(par.posterior), ('mean', 'scale', 'shape', 'rates')):
+        want = g[f'post{n_iter}_' + pname]
+        np.testing.assert_allclose(got.reshape(want.shape), want, rtol=2e-4, atol=2e-4)
+
+
+def _joint_model(beer, g):
+    C1, C2, K1 = int(g['C1']), int(g['C2']), int(g['K1'])
+    K = len(g['g_map'])
+    D = g['X1'].shape[1]
+    ns1 = normalset(beer, g, K1 * C1, D, 'g1_prior_', 'g1_post0_')
+    ns2 = normalset(beer, g, (K - K1) * C2, D, 'g2_prior_', 'g2_post0_')
+    ms1 = beer.MixtureSet.create(K1, ns1, prior_strength=1.)
+    ms2 = beer.MixtureSet.create(K - K1, ns2, prior_strength=1.)
+    for ms, tag in ((ms1, 'g1'), (ms2, 'g2')):
+        ms.categoricalset.weights.prior.params.concentrations.copy_(t32(g[tag + '_dprior']))
+        ms.categoricalset.weights.posterior.params.concentrations.copy_(t32(g[tag + '_dpost0']))
+    return beer.JointModelSet([ms1, ms2]), (ns1, ns2, ms1, ms2)
+
+
+def test_joint_mixtureset_hmm_with_alignment_graph(beer):
+    """The CLI emission stack JointModelSet([MixtureSet(NormalSet), MixtureSet(NormalSet)]) with two
+    different numbers of components, driven through an alignment graph with repeated pdf ids and an
+    acoustic scale (accumulate.py:47-57)."""
+    g = load_golden('phoneloop_mixtureset')
+    emissions, (ns1, ns2, ms1, ms2) = _joint_model(beer, g)
+    hmm = beer.HMM.create(compiled(beer, g), emissions)
+    ag = compiled(beer, g, 'ali_')
+    X3 = t32(g['X3'])
+    stats = hmm.sufficient_statistics(X3)
+    exp_llh = hmm.expected_log_likelihood(stats, inference_graph=ag, scale=0.7)
+    np.testing.assert_allclose(exp_llh.double().cpu().numpy(), g['u3_exp_llh'], rtol=1e-5, atol=1e-4)
+    acc = hmm.accumulate(stats)
+    for param, key in ((ns1.means_precisions, 'u3_acc_g1'), (ns2.means_precisions, 'u3_acc_g2'),
+                       (ms1.categoricalset.weights, 'u3_acc_d1'), (ms2.categoricalset.weights, 'u3_acc_d2')):
+        got = acc[param].cpu().numpy()
+        assert np.abs(got - g[key]).max() <= 3e-5 * max(np.abs(g[key]).max(), 1.0), key
+    hmm.clear_cache()
+    # decoding graph (state posteriors of utterance 1)
+    X1 = t32(g['X1'])
+    assert np.abs(hmm.posteriors(X1).double().cpu().numpy() - g['u1_gamma']).max() <= 1e-5
+    # standalone JointModelSet / MixtureSet calls (mixtureset.py:85-112)
+    llh = emissions.expected_log_likelihood(emissions.sufficient_statistics(X1))
+    np.testing.assert_allclose(llh.double().cpu().numpy(), g['u1_pdf_llh'], atol=1e-4)
+    emissions.clear_cache()
+
+
+def test_utterance_batch_equals_sum_of_utterances(beer):
+    """`elbo += evidence_lower_bound(model, X_u, datasize=N)` over utterances (accumulate.py:39-59) ==
+    one call on the ragged batch."""
+    g = load_golden('hmm_cfg2_T200')
+    D = g['X'].shape[1]
+    graph = compiled(beer, g)
+    hmm = beer.HMM.create(graph, normalset(beer, g, graph.n_states, D))
+    lens = [200, 64, 37, 120]
+    rng = np.random.default_rng(0)
+    utts = [t32(g['X'][s:s + n]) for s, n in ((int(rng.integers(0, 200 - n + 1)), n) for n in lens)]
+    N = sum(lens)
+    total = beer.evidence_lower_bound(datasize=N)
+    for X in utts:
+        total += beer.evidence_lower_bound(hmm, X, datasize=N, inference_graph=graph)
+    batch = beer.evidence_lower_bound(hmm, beer.Utterances.from_list(utts, device=DEV), datasize=N,
+                                      inference_graph=graph)
+    np.testing.assert_allclose(float(batch), float(total), rtol=1e-6)
+    par = hmm.modelset.original_modelset.means_precisions
+    np.testing.assert_allclose(batch._acc_stats[par].cpu().numpy(), total._acc_stats[par].cpu().numpy(),
+                               rtol=1e-5, atol=1e-5)
+    assert batch._minibatchsize == total._minibatchsize == N
+
+
+def test_error_behaviour(beer):
+    """Argument checks raise what the reference raises (objectives.py:79-83, 173-175)."""
+    with pytest.raises(ValueError):
+        beer.evidence_lower_bound()
+    with pytest.raises(ValueError):
+        beer.evidence_lower_bound(datasize=10) + beer.evidence_lower_bound(datasize=11)
+    with pytest.raises(ValueError):
+        beer.evidence_lower_bound(datasize=10) + 3
+    with pytest.raises(NotImplementedError):
+        beer.NormalSet.create(torch.zeros(2, device=DEV), torch.ones(2, device=DEV), 3, cov_type='full')
+    with pytest.raises(beer._lib.BeerB200Error):      # CPU tensors: no fallback, fail loudly
+        beer.NormalSet.create(torch.zeros(2), torch.ones(2), 3, cov_type='diagonal')
+    ns = beer.NormalSet.create(torch.zeros(2, device=DEV), torch.ones(2, device=DEV), 3, cov_type='diagonal')
+    with pytest.raises(beer._lib.BeerB200Error):
+        ns.expected_log_likelihood(ns.sufficient_statistics(torch.zeros(4, 2)))
