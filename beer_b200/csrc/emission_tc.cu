@@ -41,6 +41,7 @@ struct Args {
     const float* bias;   // [n_chunks * NB], zero padded
     const float* ref;    // [D + 1]
     int M, C, Kp, NB, n_chunks, stages;
+    int staged;          // llh tile staged in shared memory and written with one bulk store
     float* pdf_llh;
     int64_t ld;
     float* comp_llh;
@@ -52,6 +53,7 @@ struct Barriers {
     uint64_t b_full[2], b_empty[2];
     uint64_t t_full[2], t_empty[2];
     uint32_t tmem_base;
+    uint32_t pad[3];     // keeps what follows (the staged llh tile) 16-byte aligned
 };
 
 template <int D4>
@@ -153,21 +155,24 @@ __global__ void __launch_bounds__(THREADS, 1) emission_tc_kernel(Args a) {
         // ------------------------ workers: build tile, epilogue ------------------
         const int r = tid;  // frame row inside the tile, also the TMEM lane
         const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-        uint32_t it = 0, tile_it = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+        const int rbase = (r >> 3) * (Kd * 8) + (r & 7) * 4;
+        float* s_out = a.staged ? reinterpret_cast<float*>(bars + 1) : nullptr;   // [FR][Kp] llh tile
+
+        auto load_x = [&](int64_t tile, float4 (&xv)[D4]) {
+            const int64_t t = tile * FR + r;
+            const float4* xrow = reinterpret_cast<const float4*>(a.X + (size_t)(t < a.N ? t : 0) * D);
+#pragma unroll
+            for (int c = 0; c < D4; ++c) xv[c] = __ldg(xrow + c);
+        };
+        // statistics tile [x | -x^2/2] of this thread's frame, hi / lo split, + the per-frame constant
+        auto build = [&](int64_t tile, const float4 (&xv)[D4]) {
             const int64_t t = tile * FR + r;
             const bool valid = t < a.N;
-            float4 xv[D4];
-            const float4* xrow = reinterpret_cast<const float4*>(a.X + (size_t)(valid ? t : 0) * D);
-#pragma unroll
-            for (int c = 0; c < D4; ++c) xv[c] = valid ? __ldg(xrow + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-            // the previous tile's MMAs must have finished reading A
-            mbar_wait(&bars->a_free, (tile_it & 1) ^ 1);
             float rt = 0.f;
-            const int rbase = (r >> 3) * (Kd * 8) + (r & 7) * 4;
 #pragma unroll
             for (int c = 0; c < D4; ++c) {
-                const float x[4] = {xv[c].x, xv[c].y, xv[c].z, xv[c].w};
+                const float x[4] = {valid ? xv[c].x : 0.f, valid ? xv[c].y : 0.f, valid ? xv[c].z : 0.f,
+                                    valid ? xv[c].w : 0.f};
                 float h[4], l[4], qh[4], ql[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -184,81 +189,128 @@ __global__ void __launch_bounds__(THREADS, 1) emission_tc_kernel(Args a) {
                 *reinterpret_cast<float4*>(A_lo + rbase + (D4 + c) * 32) = make_float4(ql[0], ql[1], ql[2], ql[3]);
             }
             if (valid && a.frame_ref != nullptr) a.frame_ref[t] = rt + s_ref[D];
-            fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor core
-            mbar_arrive(&bars->a_ready);
-
-            for (int c = 0; c < a.n_chunks; ++c, ++it) {
-                const int buf = it & 1;
-                mbar_wait(&bars->t_full[buf], (it >> 1) & 1);
-                tc_fence_after();
-                const int g0 = c * a.NB;
-                const float* bias_c = s_bias + ((a.stages == 1) ? 0 : g0);
-                const uint32_t taddr = tmem_base + lane_addr + (uint32_t)buf * (uint32_t)a.NB;
-                for (int p = 0; p < a.NB; p += 16) {
-                    float v[16];
-                    tmem_ld16(taddr + (uint32_t)p, v);
+        };
+        // TMEM -> registers -> bias, log-sum-exp over the C components -> llh (chunk c of a tile)
+        auto epilogue = [&](int64_t tile, uint32_t it, int c) {
+            const int64_t t = tile * FR + r;
+            const bool valid = t < a.N;
+            const int buf = it & 1;
+            if (a.staged) {
+                // the previous tile's bulk store must have read the staging tile before it is rewritten
+                if (tid == 0) bulk_wait_read0();
+                asm volatile("bar.sync 1, %0;" ::"n"(WORKERS) : "memory");
+            }
+            mbar_wait(&bars->t_full[buf], (it >> 1) & 1);
+            tc_fence_after();
+            const int g0 = c * a.NB;
+            const float* bias_c = s_bias + ((a.stages == 1) ? 0 : g0);
+            const uint32_t taddr = tmem_base + lane_addr + (uint32_t)buf * (uint32_t)a.NB;
+            for (int p = 0; p < a.NB; p += 16) {
+                float v[16];
+                tmem_ld16(taddr + (uint32_t)p, v);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] += bias_c[p + i];
-                    if (valid) {
-                        const int g = g0 + p;
-                        if (a.comp_llh != nullptr) {
-                            float* dst = a.comp_llh + (size_t)t * a.M + g;
-                            if (g + 16 <= a.M && (a.M & 3) == 0) {
-#pragma unroll
-                                for (int q = 0; q < 4; ++q)
-                                    reinterpret_cast<float4*>(dst)[q] =
-                                        make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < 16; ++i)
-                                    if (g + i < a.M) dst[i] = v[i];
-                            }
-                        }
-                        // log-sum-exp over the C components of each pdf (C divides 16)
-                        const int C = a.C;
-                        float o[16];
-                        int no;
-                        if (C == 1) {
-                            no = 16;
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) o[i] = v[i];
-                        } else {
-                            no = 16 / C;
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) o[i] = 0.f;
-#pragma unroll
-                            for (int lg = 1; lg <= 4; ++lg) {
-                                if (C == (1 << lg)) {
-                                    const int CC = 1 << lg;
-#pragma unroll
-                                    for (int k = 0; k < 16 / CC; ++k) {
-                                        float m = v[k * CC];
-#pragma unroll
-                                        for (int j = 1; j < CC; ++j) m = fmaxf(m, v[k * CC + j]);
-                                        float s = 0.f;
-#pragma unroll
-                                        for (int j = 0; j < CC; ++j) s += __expf(v[k * CC + j] - m);
-                                        o[k] = m + __logf(s);
-                                    }
-                                }
-                            }
-                        }
-                        const int k0 = g / C;
-                        float* dst = a.pdf_llh + (size_t)t * a.ld + k0;
-                        if (no == 16 && k0 + 16 <= a.Kp && (a.ld & 3) == 0) {
+                for (int i = 0; i < 16; ++i) v[i] += bias_c[p + i];
+                if (valid || a.staged) {
+                    const int g = g0 + p;
+                    if (valid && a.comp_llh != nullptr) {
+                        float* dst = a.comp_llh + (size_t)t * a.M + g;
+                        if (g + 16 <= a.M && (a.M & 3) == 0) {
 #pragma unroll
                             for (int q = 0; q < 4; ++q)
                                 reinterpret_cast<float4*>(dst)[q] =
-                                    make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+                                    make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                         } else {
 #pragma unroll
                             for (int i = 0; i < 16; ++i)
-                                if (i < no && k0 + i < a.Kp) dst[i] = o[i];
+                                if (g + i < a.M) dst[i] = v[i];
                         }
                     }
+                    // log-sum-exp over the C components of each pdf (C divides 16)
+                    const int C = a.C;
+                    float o[16];
+                    int no;
+                    if (C == 1) {
+                        no = 16;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[i] = v[i];
+                    } else {
+                        no = 16 / C;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[i] = 0.f;
+#pragma unroll
+                        for (int lg = 1; lg <= 4; ++lg) {
+                            if (C == (1 << lg)) {
+                                const int CC = 1 << lg;
+#pragma unroll
+                                for (int k = 0; k < 16 / CC; ++k) {
+                                    float m = v[k * CC];
+#pragma unroll
+                                    for (int j = 1; j < CC; ++j) m = fmaxf(m, v[k * CC + j]);
+                                    float sm = 0.f;
+#pragma unroll
+                                    for (int j = 0; j < CC; ++j) sm += __expf(v[k * CC + j] - m);
+                                    o[k] = m + __logf(sm);
+                                }
+                            }
+                        }
+                    }
+                    const int k0 = g / C;
+                    // staged: the tile [FR][Kp] is contiguous in HBM, rows go to shared memory first
+                    float* dst = a.staged ? s_out + (size_t)r * a.Kp + k0 : a.pdf_llh + (size_t)t * a.ld + k0;
+                    if (no == 16 && k0 + 16 <= a.Kp && ((a.staged ? a.Kp : a.ld) & 3) == 0) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            reinterpret_cast<float4*>(dst)[q] =
+                                make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (i < no && k0 + i < a.Kp) dst[i] = o[i];
+                    }
                 }
-                tc_fence_before();
-                mbar_arrive(&bars->t_empty[buf]);
+            }
+            tc_fence_before();
+            mbar_arrive(&bars->t_empty[buf]);
+            if (a.staged) {
+                // one bulk (TMA) store of the whole tile instead of 128 strided row stores
+                fence_proxy_async();
+                asm volatile("bar.sync 1, %0;" ::"n"(WORKERS) : "memory");
+                if (tid == 0) {
+                    const int64_t rows = min((int64_t)FR, a.N - tile * FR);
+                    bulk_s2g(a.pdf_llh + (size_t)tile * FR * a.Kp, s_out, (uint32_t)(rows * a.Kp * 4));
+                    bulk_commit();
+                }
+            }
+        };
+
+        if (a.n_chunks == 1) {
+            // Software pipeline: the epilogue of tile i-1 runs under the MMAs of tile i and the
+            // frames of tile i+1 are already in flight.
+            float4 xv[D4];
+            int64_t tile = blockIdx.x, prev = -1;
+            uint32_t it = 0;
+            if (tile < n_tiles) load_x(tile, xv);
+            for (; tile < n_tiles; tile += gridDim.x, ++it) {
+                mbar_wait(&bars->a_free, (it & 1) ^ 1);   // the previous tile's MMAs have read A
+                build(tile, xv);
+                fence_proxy_async();                      // generic-proxy smem writes -> tensor core
+                mbar_arrive(&bars->a_ready);
+                if (tile + gridDim.x < n_tiles) load_x(tile + gridDim.x, xv);
+                if (prev >= 0) epilogue(prev, it - 1, 0);
+                prev = tile;
+            }
+            if (prev >= 0) epilogue(prev, it - 1, 0);
+            if (a.staged && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        } else {
+            uint32_t it = 0, tile_it = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+                float4 xv[D4];
+                load_x(tile, xv);
+                mbar_wait(&bars->a_free, (tile_it & 1) ^ 1);
+                build(tile, xv);
+                fence_proxy_async();
+                mbar_arrive(&bars->a_ready);
+                for (int c = 0; c < a.n_chunks; ++c, ++it) epilogue(tile, it, c);
             }
         }
     }
@@ -311,16 +363,16 @@ static bool geometry(int M, int D, int C, Geometry* g) {
     return true;
 }
 
-static size_t smem_bytes(int D, const Geometry& g) {
+static size_t smem_bytes(int D, const Geometry& g, int staged_kp = 0) {
     int Kd = 2 * D;
     size_t f = (size_t)2 * FR * Kd + (size_t)g.stages * 2 * g.NB * Kd +
-               (size_t)(g.stages == 1 ? g.NB : g.n_chunks * g.NB) + ((D + 1 + 3) & ~3);
+               (size_t)(g.stages == 1 ? g.NB : g.n_chunks * g.NB) + ((D + 1 + 3) & ~3) + (size_t)FR * staged_kp;
     return f * 4 + sizeof(Barriers) + 1024;
 }
 
 template <int D4>
 static int launch(const Args& a, const Geometry& g, cudaStream_t st) {
-    size_t smem = smem_bytes(4 * D4, g);
+    size_t smem = smem_bytes(4 * D4, g, a.staged ? a.Kp : 0);
     if (smem > 227 * 1024) return BEER_ERR_UNSUPPORTED;
     static bool attr_set = false;
     if (!attr_set) {
@@ -381,6 +433,9 @@ int beer_emission_llh_tc(const float* X, int64_t N, int D, const float* image, c
     a.bias = image + (size_t)g.n_chunks * 2 * g.NB * 2 * D;
     a.ref = ref; a.M = M; a.C = C; a.Kp = M / C; a.NB = g.NB; a.n_chunks = g.n_chunks; a.stages = g.stages;
     a.pdf_llh = pdf_llh; a.ld = ld_pdf; a.comp_llh = comp_llh; a.frame_ref = frame_ref;
+    // stage + bulk-store the llh tile when its rows are contiguous in HBM and it fits next to the operands
+    a.staged = (g.n_chunks == 1 && ld_pdf == a.Kp && (a.Kp & 3) == 0 && ((uintptr_t)pdf_llh & 15) == 0 &&
+                tc::smem_bytes(D, g, a.Kp) <= 227 * 1024) ? 1 : 0;
     cudaStream_t st = (cudaStream_t)stream;
     switch (D / 4) {
         case 5: return tc::launch<5>(a, g, st);

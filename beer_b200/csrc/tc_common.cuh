@@ -41,6 +41,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ float tf32_rn(float x) {
     return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
+// shared -> global bulk copy (TMA, 1-D), tracked by the bulk async-group of the issuing thread
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
