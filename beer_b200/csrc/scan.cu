@@ -38,6 +38,8 @@ struct beer_graph_plan {
     int map_identity = 0;
     int fast_ok = 0;   // every state has <= 2 in/out arcs after factoring and there is <= 1 junction
     int jrows = 0;     // ELL rows of that junction (max over directions)
+    int lr_su = 0, lr_u = 0;          // aligned left-to-right loop: states per unit, units per lane (0 = not)
+    const float* lr_w = nullptr;      // device [3][32 * lr_su * lr_u]: self, incoming, end->junction (log2)
     beer::ScanLists fwd{}, bwd{}, vit{};
     const int* map = nullptr;        // device [K]
     const float* vit_final = nullptr;  // device [K] natural log
@@ -218,6 +220,7 @@ struct FbArgs {
     double* utt_exp_llh;
     double* utt_logz;
     int vec;  // 16-byte row copies are legal
+    const float* lr_w;  // aligned left-to-right loop weights (hmm_fb_lr_kernel)
 };
 
 constexpr int FB_WARPS = 4;
@@ -881,6 +884,294 @@ static int launch_fb_fast(const FbArgs& a, int n_utts, cudaStream_t st) {
     return BEER_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Aligned left-to-right loop: P units of SU states each (self-loop + next), unit ends feeding
+// one junction that feeds the unit starts -- the phone loop of mkphoneloopgraph.py with one
+// topology for all units.  A lane owns U whole units, so every arc of the recursion connects
+// two registers of the same lane or goes through the junction, which is a warp reduction:
+// no shared-memory traffic, no warp barriers.  Weights per slot j (log2): w_self[j],
+// w_in[j] (from slot j-1, or from the junction for a unit start), w_jout[j] (unit end ->
+// junction, -inf elsewhere); the backward recursion uses the same three transposed.
+// ---------------------------------------------------------------------------
+template <int SU, int U>
+__global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_lr_kernel(FbArgs a) {
+    constexpr int S = SU * U;
+    constexpr bool VEC = (S % 4 == 0);
+    constexpr int PF = (S <= 4) ? 6 : (S <= 8 ? 4 : 3);
+    constexpr int ROW = 32 * S;
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* ring_p = smem + (size_t)warp * (2 * PF * ROW);   // [PF][32 * S]
+    float* ring_a = ring_p + PF * ROW;                      // [PF][32 * S]
+    const int K = a.K;
+    const float p_scale = a.scale * kLog2e;
+    const int gwarp = blockIdx.x * FB_WARPS + warp, nwarps = gridDim.x * FB_WARPS;
+    const bool own = lane * S < K;
+    for (int i = lane; i < 2 * PF * ROW; i += 32) ring_p[i] = 0.f;   // lanes past K stay finite
+    __syncwarp();
+
+    float w_self[S], w_in[S], w_jout[S], f_start[S], b_start[S];
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+        const int k = lane * S + j;
+        w_self[j] = __ldg(a.lr_w + k);
+        w_in[j] = __ldg(a.lr_w + ROW + k);
+        w_jout[j] = __ldg(a.lr_w + 2 * ROW + k);
+        f_start[j] = (k < K) ? __ldg(a.fwd.start + k) : kNegInf;
+        b_start[j] = (k < K) ? __ldg(a.bwd.start + k) : kNegInf;
+    }
+
+    auto prefetch = [&](float* slot, const float* row) {
+        if (!own) return;
+        if constexpr (VEC) {
+#pragma unroll
+            for (int v = 0; v < S / 4; ++v)
+                if (lane * S + 4 * v < K) cp_async16(slot + lane * S + 4 * v, row + lane * S + 4 * v);
+        } else {
+#pragma unroll
+            for (int j = 0; j < S; ++j)
+                if (lane * S + j < K) cp_async4(slot + lane * S + j, row + lane * S + j);
+        }
+    };
+    auto read_row = [&](const float* slot, float* out) {
+        if constexpr (VEC) {
+#pragma unroll
+            for (int v = 0; v < S / 4; ++v) {
+                const float4 q = reinterpret_cast<const float4*>(slot + lane * S)[v];
+                out[4 * v] = q.x; out[4 * v + 1] = q.y; out[4 * v + 2] = q.z; out[4 * v + 3] = q.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < S; ++j) out[j] = slot[lane * S + j];
+        }
+    };
+    auto write_row = [&](float* row, const float* v, float mul) {
+        if (!own) return;
+        if constexpr (VEC) {
+#pragma unroll
+            for (int q = 0; q < S / 4; ++q)
+                if (lane * S + 4 * q < K)
+                    reinterpret_cast<float4*>(row + lane * S)[q] =
+                        make_float4(mul * v[4 * q], mul * v[4 * q + 1], mul * v[4 * q + 2], mul * v[4 * q + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < S; ++j)
+                if (lane * S + j < K) row[lane * S + j] = mul * v[j];
+        }
+    };
+    // log2-sum-exp2 over the warp of U values per lane
+    auto warp_lse = [&](const float* v) {
+        float m = v[0];
+#pragma unroll
+        for (int u = 1; u < U; ++u) m = fmaxf(m, v[u]);
+        m = warp_max(m);
+        const float ms = (m == kNegInf) ? 0.f : m;
+        float sum = 0.f;
+#pragma unroll
+        for (int u = 0; u < U; ++u) sum += ex2(v[u] - ms);
+        sum = warp_sum(sum);
+        return ms + lg2(sum);
+    };
+
+    for (int u = gwarp; u < a.n_utts; u += nwarps) {
+        const int64_t t0 = a.utt_off[u];
+        const int T = (int)(a.utt_off[u + 1] - t0);
+        if (T <= 0) {
+            if (lane == 0) {
+                a.utt_exp_llh[u] = 0.0;
+                if (a.utt_logz) a.utt_logz[u] = 0.0;
+            }
+            continue;
+        }
+        const float* pl_u = a.pl + (size_t)t0 * a.ld;
+        float* la_u = a.la_ws + (size_t)t0 * a.Kw;
+        double logz2 = 0.0;
+
+        // ------------------------------ forward ------------------------------
+        for (int r = 0; r < PF; ++r) {
+            if (r < T) prefetch(ring_p + r * ROW, pl_u + (size_t)r * a.ld);
+            cp_async_commit();
+        }
+        float cur[S];
+        for (int t = 0; t < T; ++t) {
+            cp_async_wait<PF - 1>();
+            float p[S];
+            read_row(ring_p + (t % PF) * ROW, p);
+            if (t + PF < T) prefetch(ring_p + (t % PF) * ROW, pl_u + (size_t)(t + PF) * a.ld);
+            cp_async_commit();
+            if (t == 0) {
+#pragma unroll
+                for (int j = 0; j < S; ++j) cur[j] = fmaf(p[j], p_scale, f_start[j]);
+            } else {
+                float ends[U];
+#pragma unroll
+                for (int q = 0; q < U; ++q) ends[q] = cur[q * SU + SU - 1] + w_jout[q * SU + SU - 1];
+                const float jv = warp_lse(ends);
+                float v[S];
+#pragma unroll
+                for (int j = 0; j < S; ++j)
+                    v[j] = lse2(cur[j] + w_self[j], ((j % SU == 0) ? jv : cur[j - (j % SU == 0 ? 0 : 1)]) + w_in[j]);
+#pragma unroll
+                for (int j = 0; j < S; ++j) cur[j] = fmaf(p[j], p_scale, v[j]);
+            }
+            float mx = cur[0];
+#pragma unroll
+            for (int j = 1; j < S; ++j) mx = fmaxf(mx, cur[j]);
+            mx = warp_max(mx);
+            const float mxs = (mx == kNegInf) ? 0.f : mx;
+            logz2 += (double)mxs;
+#pragma unroll
+            for (int j = 0; j < S; ++j) cur[j] -= mxs;
+            write_row(la_u + (size_t)t * a.Kw, cur, 1.f);
+        }
+        cp_async_wait<0>();
+
+        if (a.utt_logz != nullptr) {
+            float m = kNegInf, v[S];
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                v[j] = cur[j] + b_start[j];
+                m = fmaxf(m, v[j]);
+            }
+            m = warp_max(m);
+            const float ms = (m == kNegInf) ? 0.f : m;
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < S; ++j) sum += ex2(v[j] - ms);
+            sum = warp_sum(sum);
+            const double z = (logz2 + (double)ms + (double)lg2(sum)) * (double)kLn2;
+            double rs = 0.0;
+            if (a.frame_ref != nullptr)
+                for (int t = lane; t < T; t += 32) rs += (double)a.frame_ref[t0 + t];
+            rs = warp_sum(rs);
+            if (lane == 0) a.utt_logz[u] = z + (double)a.scale * rs;
+        }
+
+        // ------------------------------ backward -----------------------------
+        __threadfence_block();   // this warp's la stores -> visible to its own async copies
+        __syncwarp();
+        for (int r = 0; r < PF; ++r) {
+            const int t = T - 1 - r;
+            if (t >= 0) {
+                prefetch(ring_p + r * ROW, pl_u + (size_t)t * a.ld);
+                prefetch(ring_a + r * ROW, la_u + (size_t)t * a.Kw);
+            }
+            cp_async_commit();
+        }
+        float lb[S];
+        {
+            float m = kNegInf;
+#pragma unroll
+            for (int j = 0; j < S; ++j) m = fmaxf(m, b_start[j]);
+            m = warp_max(m);
+            const float ms = (m == kNegInf) ? 0.f : m;
+#pragma unroll
+            for (int j = 0; j < S; ++j) lb[j] = b_start[j] - ms;
+        }
+        float ell = 0.f;
+        double ell_d = 0.0;
+        for (int i = 0; i < T; ++i) {
+            const int t = T - 1 - i;
+            cp_async_wait<PF - 1>();
+            float p[S], la[S];
+            read_row(ring_p + (i % PF) * ROW, p);
+            read_row(ring_a + (i % PF) * ROW, la);
+#pragma unroll
+            for (int j = 0; j < S; ++j) p[j] *= p_scale;
+            if (t - PF >= 0) {
+                prefetch(ring_p + (i % PF) * ROW, pl_u + (size_t)(t - PF) * a.ld);
+                prefetch(ring_a + (i % PF) * ROW, la_u + (size_t)(t - PF) * a.Kw);
+            }
+            cp_async_commit();
+
+            float v[S], m = kNegInf;
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                v[j] = la[j] + lb[j];
+                m = fmaxf(m, v[j]);
+            }
+            m = warp_max(m);
+            const float ms = (m == kNegInf) ? 0.f : m;
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                v[j] = ex2(v[j] - ms);
+                sum += v[j];
+            }
+            sum = warp_sum(sum);
+            const float inv = (sum > 0.f) ? __fdividef(1.f, sum) : 0.f;
+            float fe = 0.f;
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                v[j] *= inv;
+                if (v[j] > 0.f) fe = fmaf(p[j], v[j], fe);
+            }
+            ell += fe;
+            if ((i & 31) == 31) {
+                ell_d += (double)ell;
+                ell = 0.f;
+            }
+            if (a.frame_exp_llh != nullptr) {
+                const float f = warp_sum(fe);
+                if (lane == 0) {
+                    const float r = (a.frame_ref != nullptr) ? a.scale * a.frame_ref[t0 + t] : 0.f;
+                    a.frame_exp_llh[t0 + t] = f * kLn2 + r;
+                }
+            }
+            if (a.state_post != nullptr) write_row(a.state_post + (size_t)(t0 + t) * K, v, 1.f);
+            if (a.pdf_post != nullptr) write_row(a.pdf_post + (size_t)(t0 + t) * a.ld_post, v, a.scale);
+            if (t == 0) break;
+            // beta_{t-1}: delta_j = p_tj + lb_tj, transposed recursion on registers
+            float delta[S], starts[U];
+#pragma unroll
+            for (int j = 0; j < S; ++j) delta[j] = p[j] + lb[j];
+#pragma unroll
+            for (int q = 0; q < U; ++q) starts[q] = delta[q * SU] + w_in[q * SU];
+            const float jb = warp_lse(starts);
+            float mb = kNegInf;
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                const bool end = (j % SU == SU - 1);
+                const float nxt = end ? jb + w_jout[j] : delta[end ? j : j + 1] + w_in[end ? j : j + 1];
+                lb[j] = lse2(delta[j] + w_self[j], nxt);
+                mb = fmaxf(mb, lb[j]);
+            }
+            mb = warp_max(mb);
+            const float mbs = (mb == kNegInf) ? 0.f : mb;
+#pragma unroll
+            for (int j = 0; j < S; ++j) lb[j] -= mbs;
+        }
+        cp_async_wait<0>();
+        ell_d += (double)ell;
+        ell_d = warp_sum(ell_d);
+        double rs = 0.0;
+        if (a.frame_ref != nullptr)
+            for (int t = lane; t < T; t += 32) rs += (double)a.frame_ref[t0 + t];
+        rs = warp_sum(rs);
+        if (lane == 0) a.utt_exp_llh[u] = ell_d * (double)kLn2 + (double)a.scale * rs;
+        __syncwarp();
+    }
+}
+
+template <int SU, int U>
+static int launch_fb_lr(const FbArgs& a, int n_utts, cudaStream_t st) {
+    constexpr int S = SU * U;
+    constexpr int PF = (S <= 4) ? 6 : (S <= 8 ? 4 : 3);
+    size_t smem = sizeof(float) * (size_t)FB_WARPS * (2 * PF * 32 * S);
+    static bool attr_set = false;
+    if (!attr_set) {
+        BEER_CUDA_TRY(cudaFuncSetAttribute(hmm_fb_lr_kernel<SU, U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem));
+        attr_set = true;
+    }
+    int blocks = (n_utts + FB_WARPS - 1) / FB_WARPS;
+    int max_blocks = kNumSMs * 16;
+    if (blocks > max_blocks) blocks = max_blocks;
+    hmm_fb_lr_kernel<SU, U><<<blocks, FB_WARPS * 32, smem, st>>>(a);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
 // ------------------------------- Viterbi -----------------------------------
 struct VitArgs {
     ScanLists vit;
@@ -1155,8 +1446,43 @@ int beer_graph_plan_create(const float* init_log, const float* final_log, const 
         vfinal[k] = final_log[k];
     }
 
+    // aligned left-to-right loop?  (unit starts = junction destinations 0, SU, 2 SU, ...)
+    int lr_su = 0, lr_u = 0;
+    std::vector<float> lr_w;
+    if (J == 1 && junctions[0].cols.size() >= 2) {
+        const Junction& jn = junctions[0];
+        std::vector<int> cols = jn.cols;   // sorted (built from sorted keys)
+        const int su = cols[1] - cols[0];
+        bool ok = su >= 1 && su <= 8 && K % su == 0 && (int)cols.size() == K / su;
+        for (size_t c = 0; ok && c < cols.size(); ++c) ok = cols[c] == (int)c * su;
+        for (int i = 0; ok && i < K; ++i) {
+            if (row_factored[i] && i % su != su - 1) ok = false;
+            for (const Arc& a : out_arcs[i]) {
+                if (a.src == i) continue;                                  // self loop
+                if (row_factored[i]) continue;                             // through the junction
+                if (!(a.src == i + 1 && (i + 1) % su != 0)) ok = false;    // only "next state of my unit"
+            }
+        }
+        const int P = ok ? K / su : 0;
+        int u = (P + 31) / 32;
+        u = (u <= 1) ? 1 : (u <= 2 ? 2 : (u <= 4 ? 4 : 0));
+        if (ok && u > 0 && (su == 3 || su == 4)) {
+            lr_su = su; lr_u = u;
+            const int row = 32 * su * u;
+            lr_w.assign((size_t)3 * row, -INFINITY);
+            for (int i = 0; i < K; ++i)
+                for (const Arc& a : out_arcs[i]) {
+                    if (a.src == i) lr_w[i] = (float)(a.lw * L2E);
+                    else if (!row_factored[i]) lr_w[row + a.src] = (float)(a.lw * L2E);
+                }
+            for (size_t c = 0; c < jn.cols.size(); ++c) lr_w[row + jn.cols[c]] = (float)(jn.lw[c] * L2E);
+            for (size_t r = 0; r < jn.rows.size(); ++r) lr_w[2 * row + jn.rows[r]] = (float)(jn.lv[r] * L2E);
+        }
+    }
+
     BlobWriter w;
     ListOffsets of = write_lists(w, hf), ob = write_lists(w, hb), ov = write_lists(w, hv);
+    size_t o_lrw = w.add(lr_w.data(), lr_w.size() * 4);
     size_t o_map = w.add(pdf_map, (size_t)K * 4);
     size_t o_vfinal = w.add(vfinal.data(), (size_t)K * 4);
 
@@ -1173,6 +1499,8 @@ int beer_graph_plan_create(const float* init_log, const float* final_log, const 
     p->bwd = bind_lists(base, ob);
     p->vit = bind_lists(base, ov);
     p->map = (const int*)(base + o_map);
+    p->lr_su = lr_su; p->lr_u = lr_u;
+    p->lr_w = lr_su ? (const float*)(base + o_lrw) : nullptr;
     p->vit_final = (const float*)(base + o_vfinal);
     p->map_identity = 1;
     for (int k = 0; k < K; ++k)
@@ -1228,13 +1556,33 @@ int beer_hmm_forward_backward(const beer_graph_plan* plan, const float* pdf_llh,
     a.frame_exp_llh = frame_exp_llh; a.utt_exp_llh = utt_exp_llh; a.utt_logz = utt_logz;
     a.vec = (plan->map_identity && plan->S % 4 == 0 && plan->K % 4 == 0 && ld_pdf % 4 == 0 &&
              ((uintptr_t)pdf_llh & 15) == 0) ? 1 : 0;
+    a.lr_w = plan->lr_w;
+    const bool post_ok = (pdf_post == nullptr || (ld_post % 4 == 0 && ((uintptr_t)pdf_post & 15) == 0)) &&
+                         (state_post == nullptr || (plan->K % 4 == 0 && ((uintptr_t)state_post & 15) == 0));
+    const char* force = getenv("BEER_B200_SCAN");   // debug: "generic" | "fast" | unset (best available)
+    const bool lr_vec = (plan->lr_su * plan->lr_u) % 4 == 0;   // the kernel moves whole float4 rows
+    if (plan->lr_su && plan->map_identity && (force == nullptr || force[0] == 'l') &&
+        (!lr_vec || (a.vec && post_ok))) {
+        const int u = plan->lr_u;
+        if (plan->lr_su == 4) {
+            if (u == 1) return launch_fb_lr<4, 1>(a, n_utts, st);
+            if (u == 2) return launch_fb_lr<4, 2>(a, n_utts, st);
+            if (u == 4) return launch_fb_lr<4, 4>(a, n_utts, st);
+        } else if (plan->lr_su == 3) {
+            if (u == 1) return launch_fb_lr<3, 1>(a, n_utts, st);
+            if (u == 2) return launch_fb_lr<3, 2>(a, n_utts, st);
+            if (u == 4) return launch_fb_lr<3, 4>(a, n_utts, st);
+        }
+    }
+    if (force != nullptr && force[0] == 'g') goto generic;
     if (plan->fast_ok && a.vec && (state_post == nullptr || plan->K % 4 == 0) &&
         (pdf_post == nullptr || (ld_post % 4 == 0 && ((uintptr_t)pdf_post & 15) == 0)) &&
-        (state_post == nullptr || ((uintptr_t)state_post & 15) == 0) && getenv("BEER_B200_GENERIC_SCAN") == nullptr) {
+        (state_post == nullptr || ((uintptr_t)state_post & 15) == 0)) {
         const int jr = plan->jrows <= 1 ? 1 : 2;
         if (plan->S == 4) return jr == 1 ? launch_fb_fast<4, 1>(a, n_utts, st) : launch_fb_fast<4, 2>(a, n_utts, st);
         if (plan->S == 8) return jr == 1 ? launch_fb_fast<8, 1>(a, n_utts, st) : launch_fb_fast<8, 2>(a, n_utts, st);
     }
+generic:
     switch (plan->S) {
         case 1: return launch_fb<1>(a, n_utts, st);
         case 2: return launch_fb<2>(a, n_utts, st);

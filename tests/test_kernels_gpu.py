@@ -137,6 +137,26 @@ def test_forward_backward_golden(ops, name, factorize):
         assert plan.info['junctions'] == 1 and plan.info['junction_in'] == 25 and plan.info['junction_out'] == 25
 
 
+@pytest.mark.parametrize('path', ['lr', 'fast', 'generic'])
+@pytest.mark.parametrize('name', ['hmm_scaled', 'hmm_cfg2_T200'])
+def test_forward_backward_every_scan_kernel(ops, name, path, monkeypatch):
+    """The three forward-backward kernels (aligned left-to-right loop in registers, register arc lists
+    + shared memory, interpretive ELL) give the same posteriors / evidence on the same graph."""
+    monkeypatch.setenv('BEER_B200_SCAN', path)
+    g = load_golden(name)
+    scale = float(g['scale'])
+    llh = g['pdf_llh'] - g['pdf_llh'].max(axis=1, keepdims=True)
+    plan, r = _fb_case(ops, llh, graph(g), scale=scale)
+    if path == 'lr':
+        assert plan.info['junctions'] == 1
+    gamma = r['state_post'].double().cpu().numpy()
+    assert np.abs(gamma - g['gamma']).max() <= 1e-5
+    np.testing.assert_allclose(r['utt_exp_llh'].item() + scale * g['pdf_llh'].max(axis=1).sum(),
+                               g['exp_llh'].sum(), rtol=1e-6)
+    pdf_post = r['pdf_post'].double().cpu().numpy()
+    np.testing.assert_allclose(pdf_post, scale * g['gamma'], atol=1e-5)
+
+
 def test_forward_backward_dense_and_unreachable(ops):
     g = load_golden('dense_ergodic')
     _, r = _fb_case(ops, g['llhs'], graph(g))
