@@ -140,8 +140,37 @@ class _StageTimer:
         return False
 
 
+def shard_utterances(lengths, world_size):
+    """Static utterance -> rank assignment balancing the frames per rank (longest-processing-time
+    greedy): the `split` step of the reference's job arrays (recipes/zrc2019/utils/parallel/split.sh)
+    with balanced shards.  Returns a list of index arrays, one per rank."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    order = np.argsort(-lengths, kind='stable')
+    load = np.zeros(world_size, dtype=np.int64)
+    shards = [[] for _ in range(world_size)]
+    for i in order:
+        r = int(np.argmin(load))
+        shards[r].append(int(i))
+        load[r] += lengths[i]
+    return [np.asarray(sorted(s), dtype=np.int64) for s in shards]
+
+
+def elbo_from_flat(extras, kl, datasize):
+    """Summed ELBO of `beer hmm accumulate` + `update` from the reduced bookkeeping terms
+    extras = [sum_u ell_u / T_u, sum_u T_u, n_utts, sum_u ell_u]: every utterance contributes
+    (datasize / T_u) * ell_u - KL (objectives.py:180-184 added up as in accumulate.py:39-59)."""
+    return datasize * extras[0] - extras[2] * kl
+
+
+def stats_scale_from_flat(total_frames, datasize):
+    """`backward()` hands datasize / (frames seen) * statistics to the parameters (objectives.py:98-106)."""
+    return datasize / total_frames
+
+
 class VBEngine:
-    """One process per GPU; `utts` is this rank's shard and stays resident in HBM."""
+    """One process per GPU; `utts` is this rank's shard.  Its frames stay resident in HBM, or --
+    when `utts.X` is a pinned HOST tensor -- are streamed through two device staging buffers, the
+    copy of chunk i+1 overlapping the kernels of chunk i."""
 
     def __init__(self, emission, plan, utts, datasize=None, scale=1.0, lrate=1.0, chunk_frames=None,
                  process_group=None, distributed=None):
@@ -165,8 +194,19 @@ class VBEngine:
         self.utt_len = lens
         self.inv_len = torch.where(lens > 0, 1.0 / lens.clamp(min=1.0), torch.zeros_like(lens))
         self.profile = None      # optional {stage: [(start_event, end_event), ...]} (bench.py)
+        self.host_mode = not utts.X.is_cuda
+        if self.host_mode and chunk_frames is None:
+            chunk_frames = max(1, len(utts) // 8)
         self._chunks = self._make_chunks(chunk_frames)
         nmax = max((c[3] for c in self._chunks), default=0)
+        if self.host_mode:
+            if not utts.X.is_pinned():
+                raise ValueError('host-resident features must be in pinned memory')
+            self._stage_buf = [torch.empty(nmax, D, device=self.dev, dtype=f32) for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
+            self._ready = [torch.cuda.Event() for _ in range(2)]
+            self._free = [torch.cuda.Event() for _ in range(2)]
+            self._free_valid = [False, False]
         Kp = emission.Kp
         self.pdf_llh = torch.empty(nmax, Kp, device=self.dev, dtype=f32)
         self.pdf_post = (torch.empty if plan.info['map_identity'] and plan.n_states == Kp else torch.zeros)(
@@ -207,10 +247,18 @@ class VBEngine:
         em.kl(out=self.kl)
         self.gpu_launches += 2 + 1 + 2 * len(em.weight_groups) + int(em.use_tc)
         nonident = not (plan.info['map_identity'] and plan.n_states == em.Kp)
-        for (u0, u1, f0, nf, rel) in self._chunks:
-            if nf == 0:
-                continue
-            X = self.utts.X[f0:f0 + nf]
+        chunks = [c for c in self._chunks if c[3] > 0]
+        if self.host_mode and chunks:
+            self._issue_copy(chunks[0], 0)
+        for ci, (u0, u1, f0, nf, rel) in enumerate(chunks):
+            if self.host_mode:
+                b = ci & 1
+                if ci + 1 < len(chunks):
+                    self._issue_copy(chunks[ci + 1], (ci + 1) & 1)
+                torch.cuda.current_stream().wait_event(self._ready[b])
+                X = self._stage_buf[b][:nf]
+            else:
+                X = self.utts.X[f0:f0 + nf]
             pdf_llh = self.pdf_llh[:nf]
             pdf_post = self.pdf_post[:nf]
             comp = self.comp_llh[:nf] if self.comp_llh is not None else None
@@ -226,6 +274,9 @@ class VBEngine:
                                      pdf_llh=pdf_llh if comp is not None else None, comp_llh=comp,
                                      comp_off=em.comp_off if comp is not None else None, Kp=em.Kp)
             self.gpu_launches += 3
+            if self.host_mode:
+                self._free[ci & 1].record()
+                self._free_valid[ci & 1] = True
         # ELBO bookkeeping of the shard (objectives.py:176-190 summed as in accumulate.py:39-59)
         n_local = float(self.local_frames)
         self.extras[1] = n_local
@@ -233,6 +284,15 @@ class VBEngine:
         self.extras[3] = self.utt_ell.sum()
         # sum_u ell_u / T_u; multiplied by the global datasize after the reduction
         self.extras[0] = (self.utt_ell * self.inv_len).sum()
+
+    def _issue_copy(self, chunk, b):
+        """H2D copy of one chunk into staging buffer b on the copy stream."""
+        _, _, f0, nf, _ = chunk
+        with torch.cuda.stream(self._copy_stream):
+            if self._free_valid[b]:
+                self._copy_stream.wait_event(self._free[b])   # the kernels that last read b are done
+            self._stage_buf[b][:nf].copy_(self.utts.X[f0:f0 + nf], non_blocking=True)
+            self._ready[b].record()
 
     def reduce(self):
         """The one exchange step: sum the flat statistics buffer over ranks (NCCL)."""
@@ -247,8 +307,8 @@ class VBEngine:
         # python float for the kernel arguments would force a sync; stats_scale is known on the
         # host because datasize and the frame counts are host-side constants of the run.
         datasize = self.datasize if self.datasize is not None else self._global_frames()
-        stats_scale = datasize / self._global_frames()
-        elbo = datasize * self.extras[0] - n_utts * self.kl[0]
+        stats_scale = stats_scale_from_flat(self._global_frames(), datasize)
+        elbo = elbo_from_flat(self.extras, self.kl[0], datasize)
         self.em.update(self.acc, stats_scale, self.lrate)
         self.gpu_launches += 1 + (1 + len(self.em.weight_groups) if self.em.weight_groups else 0)
         return elbo

@@ -196,7 +196,7 @@ def run_gpu(args, c):
     X = synthetic.sample_utterances(graph, means, U, T, seed=100 + rank, device=dev)
     utts = Utterances(X, [T] * U)
 
-    def make_engine():
+    def make_engine(utts=utts, chunk_frames=args.chunk_frames):
         prior, post = synthetic.initial_normal_gamma(M, D, seed=2, device=dev)
         groups, comp_off = (), None
         if C > 1:
@@ -204,7 +204,7 @@ def run_gpu(args, c):
             groups = (WeightGroup(0, K, C, conc.clone(), conc.clone()),)
             comp_off = np.arange(K + 1) * C
         em = EmissionParams(prior, post, comp_off=comp_off, weight_groups=groups)
-        return VBEngine(em, plan, utts, datasize=float(world * U * T), chunk_frames=args.chunk_frames,
+        return VBEngine(em, plan, utts, datasize=float(world * U * T), chunk_frames=chunk_frames,
                         distributed=world > 1)
 
     def barrier():
@@ -224,10 +224,12 @@ def run_gpu(args, c):
         sampler.start()
     t_wall = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.nvtx.range_push('bench_timed')     # ncu --nvtx --nvtx-include "bench_timed/" selects these launches
     ev0.record()
     for _ in range(args.steps):
         elbos.append(eng.step())
     ev1.record()
+    torch.cuda.nvtx.range_pop()
     barrier()
     wall = time.perf_counter() - t_wall
     clocks = sampler.stop() if rank == 0 else None
@@ -242,15 +244,18 @@ def run_gpu(args, c):
     frames_per_step = world * U * T
     value = frames_per_step * args.steps / (ms * 1e-3)
     elbo_pf = [float(eng.elbo_per_frame(e).item()) for e in elbos]
+    launches_step = launches // max(args.steps, 1)
 
     # ---- end to end: features in pinned host memory, H2D every step, ELBO read back --------
     host_X = torch.empty(X.shape, dtype=torch.float32, pin_memory=True)
     host_X.copy_(X)
-    eng2 = make_engine()
+    del eng
+    # features stay in pinned host memory: the engine streams them in chunks of whole utterances (the H2D
+    # copy of chunk i+1 under the kernels of chunk i) and the ELBO is read back to the host every step
+    eng2 = make_engine(Utterances(host_X, [T] * U), chunk_frames=args.e2e_chunk_frames or max(T, U * T // 8))
     n_e2e = max(1, min(args.steps, 5))
 
     def e2e_step():
-        eng2.utts.X.copy_(host_X, non_blocking=True)
         return float(eng2.step().item())
 
     e2e_step()
@@ -268,13 +273,23 @@ def run_gpu(args, c):
     if rank == 0:
         peak, peak_src = measured_peaks()
         # dominant kernel and its algorithmic bytes per frame (DESIGN.md "Kernels and rooflines")
-        alg = {'KA_emission_llh': 4 * D + 4 * K, 'KB_forward_backward': 12 * K, 'KC_accumulate': 4 * D + 4 * K}
+        # B_alg = 8D + 16K per frame = KA (read X, write llh) + KB (read llh once more, write and
+        # read alpha) + KC (read X); posteriors and responsibilities count as on-chip in the algorithmic figure
+        alg = {'KA_emission_llh': 4 * D + 4 * K, 'KB_forward_backward': 12 * K, 'KC_accumulate': 4 * D}
+        traffic_pf = {}
+        tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+        if os.path.exists(tpath):        # dram bytes per frame per launch from the committed ncu capture
+            with open(tpath) as f:
+                traffic_pf = json.load(f).get(args.config, {})
         dom = max((k for k in stage_ms if k in alg), key=lambda k: stage_ms[k], default=None)
         roofline = None
         if dom is not None:
             achieved = alg[dom] * U * T / (stage_ms[dom] * 1e-3) / 1e9
             roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                        'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                        'frac': achieved / peak,
+                        'traffic': (traffic_pf[dom] * U * T if dom in traffic_pf else None),
+                        'traffic_unit': 'bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)',
+                        'peak_source': peak_src,
                         'alg_bytes_per_frame': alg[dom], 'launch_ms': stage_ms[dom],
                         'step_alg_bytes_per_frame': 8 * D + 16 * K,
                         'step_frac': (8 * D + 16 * K) * U * T / (ms / args.steps * 1e-3) / 1e9 / peak,
@@ -311,6 +326,7 @@ def main():
     ap.add_argument('--config', default='cfg2')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--chunk-frames', type=int, default=None)
+    ap.add_argument('--e2e-chunk-frames', type=int, default=None)
     ap.add_argument('--n-utts', type=int, default=None, help='override utterances per GPU (debug)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

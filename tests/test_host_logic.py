@@ -1,0 +1,168 @@
+"""CPU tests of the host-side logic: the C-ABI library loads and exports every symbol the header
+declares (no compute calls), utterance sharding, the world_size-2 reduction of the flat statistics
+buffer over `gloo` against the single-process oracle iteration, the ELBO value object, the graph
+builder against the reference's compiled graphs."""
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from conftest import load_golden  # noqa: E402
+from oracle import beer_oracle as O  # noqa: E402
+
+
+def test_library_exports_every_declared_symbol():
+    from beer_b200 import _lib, build
+    build.build()
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, 'include', 'beer_b200.h')).read()
+    declared = set(re.findall(r'BEER_API\s+[\w\s\*]+?\b(beer_\w+)\s*\(', header))
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), f'{name} declared in include/beer_b200.h but not exported'
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.beer_b200_version() >= 100
+    assert lib.beer_emission_tc_supported(100, 40, 1) == 1 and lib.beer_emission_tc_supported(100, 13, 1) == 0
+    assert lib.beer_accumulate_tc_supported(100, 40) == 1
+
+
+def test_package_imports_without_gpu_and_fails_loudly():
+    import beer_b200 as beer
+    assert beer.evidence_lower_bound and beer.HMM and beer.vbi.BayesianModelOptimizer is beer.VBOptimizer
+    if not torch.cuda.is_available():
+        with pytest.raises(beer._lib.BeerB200Error):
+            beer.NormalSet.create(torch.zeros(3), torch.ones(3), size=4, cov_type='diagonal')
+
+
+def test_shard_utterances_balances_frames():
+    from beer_b200.engine import shard_utterances
+    rng = np.random.default_rng(0)
+    lens = rng.integers(50, 3000, size=1000)
+    for world in (1, 2, 4, 8):
+        shards = shard_utterances(lens, world)
+        allidx = np.sort(np.concatenate(shards))
+        np.testing.assert_array_equal(allidx, np.arange(len(lens)))      # a partition
+        loads = np.array([lens[s].sum() for s in shards])
+        assert loads.max() - loads.min() <= lens.max()                    # LPT bound
+    assert [len(s) for s in shard_utterances([5, 5], 4)] == [1, 1, 0, 0]
+
+
+def test_graph_builder_matches_reference_compile():
+    """beer_b200.graph.Graph.compile against the reference's compiled graphs (graph.py:185-240)."""
+    from beer_b200.graph import Graph
+    from beer_b200.synthetic import unit_graph
+    g = load_golden('graph_compile')
+    pl = Graph()
+    pl.start_state, pl.end_state = pl.add_state(), pl.add_state()
+    pivot = pl.add_state()
+    us = [pl.add_state() for _ in range(5)]
+    pl.add_arc(pl.start_state, pivot)
+    pl.add_arc(pivot, pl.end_state)
+    for s in us:
+        pl.add_arc(pivot, s)
+        pl.add_arc(s, pivot)
+    pl.normalize()
+    for i, s in enumerate(us):
+        pl.replace_state(s, unit_graph(3, i * 3))
+    pl.normalize()
+    cg = pl.compile()
+    with np.errstate(invalid='ignore'):
+        for name, t in (('init', cg.init_log_probs), ('final', cg.final_log_probs), ('trans', cg.trans_log_probs)):
+            want = g['pl_' + name]
+            got = t.numpy()
+            assert np.array_equal(np.isinf(got), np.isinf(want))
+            np.testing.assert_allclose(got[~np.isinf(got)], want[~np.isinf(want)], rtol=1e-6, atol=1e-6)
+    np.testing.assert_array_equal(np.asarray(cg.pdf_id_mapping), g['pl_map'])
+
+
+def test_elbo_instance_semantics():
+    """EvidenceLowerBoundInstance.__add__ / backward / sync (objectives.py:78-116) on plain tensors."""
+    from beer_b200.inference import EvidenceLowerBoundInstance, evidence_lower_bound
+
+    class P:
+        def __init__(self):
+            self.stored = None
+
+        def store_stats(self, s):
+            self.stored = s
+
+    p1, p2 = P(), P()
+    a = EvidenceLowerBoundInstance(torch.tensor(-3.), {p1: torch.ones(2)}, [p1], 10, 100)
+    b = EvidenceLowerBoundInstance(torch.tensor(-4.), {p1: torch.ones(2), p2: 2 * torch.ones(3)}, [p1, p2], 30, 100)
+    c = evidence_lower_bound(datasize=100) + a + b
+    assert float(c) == -7. and c._minibatchsize == 40
+    c.backward()
+    np.testing.assert_allclose(p1.stored.numpy(), 100 / 40 * 2 * np.ones(2))
+    np.testing.assert_allclose(p2.stored.numpy(), 100 / 40 * 2 * np.ones(3))
+    with pytest.raises(ValueError):
+        a + EvidenceLowerBoundInstance(0., {}, [], 1, 99)
+    with pytest.raises(ValueError):
+        evidence_lower_bound(model=object())
+
+
+# ---------------------------------------------------------------------------------------------
+# world_size 2 over gloo: shards + one all-reduce of the flat buffer == single process
+# ---------------------------------------------------------------------------------------------
+
+def _make_case():
+    rng = np.random.default_rng(5)
+    P, S, D = 4, 3, 6
+    graph, _, _ = O.phone_loop_graph(P, S)
+    K = P * S
+    means = 2.0 * rng.standard_normal((K, D))
+    lens = [40, 25, 61, 33, 18, 50]
+    utts = [O.sample_utterances(rng, graph, means, 1, n)[0] for n in lens]
+    prior = (np.zeros((K, D)), np.ones((K, 1)), np.ones((K, 1)), np.ones((K, D)))
+    post = (rng.standard_normal((K, D)), np.ones((K, 1)), np.ones((K, 1)), np.ones((K, D)))
+    return graph, utts, prior, post
+
+
+def _rank_main(rank, world, port, out):
+    import torch.distributed as dist
+    from beer_b200.engine import elbo_from_flat, shard_utterances, stats_scale_from_flat
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    graph, utts, prior, post = _make_case()
+    mine = shard_utterances([len(u) for u in utts], world)[rank]
+    K, D = post[0].shape
+    Q = 2 * D + 2
+    # the engine's flat buffer layout: [acc (M*Q) | sum_u ell_u/T_u | sum_u T_u | n_utts | sum_u ell_u]
+    flat = torch.zeros(K * Q + 4, dtype=torch.float64)
+    for i in mine:
+        r = O.hmm_estep(utts[i], post, None, graph)      # the E-step itself is the GPU kernels' job
+        flat[:K * Q] += torch.from_numpy(r['acc_normal'].reshape(-1))
+        ell = float(r['exp_llh'].sum())
+        flat[K * Q + 0] += ell / len(utts[i])
+        flat[K * Q + 1] += len(utts[i])
+        flat[K * Q + 2] += 1
+        flat[K * Q + 3] += ell
+    dist.all_reduce(flat)                                 # the one exchange step of a VB iteration
+    datasize = float(sum(len(u) for u in utts))
+    kl = float(O.normalgamma_kl(post, prior).sum())
+    elbo = float(elbo_from_flat(flat[K * Q:], kl, datasize))
+    scale = stats_scale_from_flat(float(flat[K * Q + 1]), datasize)
+    if rank == 0:
+        np.savez(out, flat=flat.numpy(), elbo=elbo, scale=scale)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_reduction_equals_single_process(tmp_path):
+    import torch.multiprocessing as mp
+    out = str(tmp_path / 'rank0.npz')
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_rank_main, args=(2, port, out), nprocs=2, join=True)
+    got = np.load(out)
+    graph, utts, prior, post = _make_case()
+    want_elbo, _, _, info = O.vb_iteration_hmm(utts, prior, post, None, None, graph)
+    K, D = post[0].shape
+    np.testing.assert_allclose(got['flat'][:K * (2 * D + 2)].reshape(K, -1), info['acc_normal'], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(float(got['elbo']), want_elbo, rtol=1e-12)
+    np.testing.assert_allclose(float(got['scale']), 1.0)
+    assert got['flat'][-3] == sum(len(u) for u in utts) and got['flat'][-2] == len(utts)
