@@ -57,7 +57,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-lms', '200', '-i', str(self.idx)], stdout=subprocess.PIPE,
+                                          '-lms', '50', '-i', str(self.idx)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -143,7 +143,7 @@ def run_reference(args, c):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    upw = 2 if c['n_comp'] == 1 else 1
+    upw = 48 if c['n_comp'] == 1 else 1          # ~5-10 s of CPU work per step on 16 cores
     vals = []
     for _ in range(args.warmup):
         cpu_reference_throughput(c, 1)
@@ -182,7 +182,17 @@ def run_gpu(args, c):
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+        # NCCL announces its version on stdout at the first collective: keep stdout to the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
     ops.require_cuda()
 
     K = c['n_units'] * c['n_states']
@@ -241,6 +251,20 @@ def run_gpu(args, c):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+    if ms < 400.0:
+        # the timed region is shorter than a few nvidia-smi sampling periods: sample the same step loop,
+        # untimed, for ~0.6 s right behind it (same number of extra steps on every rank)
+        n_probe = int(600.0 / max(ms / args.steps, 1e-3)) + 1
+        probe = ClockSampler(local_rank)
+        if rank == 0:
+            probe.start()
+        for _ in range(n_probe):
+            eng.step()
+        barrier()
+        if rank == 0:
+            clocks = probe.stop()
+            clocks['window'] = (f'{n_probe} more steps of the same loop right after the timed region '
+                                '(timed region too short to sample)')
     frames_per_step = world * U * T
     value = frames_per_step * args.steps / (ms * 1e-3)
     elbo_pf = [float(eng.elbo_per_frame(e).item()) for e in elbos]
@@ -296,7 +320,7 @@ def run_gpu(args, c):
                         'stage_ms': stage_ms}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            upw = 2 if C == 1 else 1
+            upw = 96 if C == 1 else 1        # ~10 s of CPU work
             v, cores, frames, took = cpu_reference_throughput(c, upw)
             cpu = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                    'sample': f'{cores} worker processes x {upw} utterance(s) x {T} frames, numpy port of the '
@@ -309,8 +333,8 @@ def run_gpu(args, c):
                            'chunk_frames': args.chunk_frames, 'parallelism': f'dp{world} (utterances sharded, '
                            'one all-reduce of the statistics per step)'},
                 'clocks': clocks, 'wall_s_timed_region': wall,
-                'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(X.numel() * 4),
-                        'd2h_bytes_per_step': 8, 'steps': n_e2e},
+                'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(world * X.numel() * 4),
+                        'd2h_bytes_per_step': 8 * world, 'steps': n_e2e},
                 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu,
                 'elbo_per_frame': {'first': elbo_pf[0], 'last': elbo_pf[-1]}}
         print(json.dumps(line), flush=True)
