@@ -19,6 +19,7 @@
 // issuer + TMEM allocator.  The count column (sum_t w) rides along as a constant-one feature.
 //
 // Reference semantics: beer/models/mixtureset.py:100-112, beer/models/normalset.py:121-123.
+#include <cstdlib>
 #include <type_traits>
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -408,6 +409,294 @@ static int launch(const Args& a0, cudaStream_t st) {
     return BEER_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Bulk-staged variant: one Gaussian tile (M <= 128), no mixtures, posteriors stored densely
+// ([N, M], the layout KB writes).  The frames x M posterior block and the frames x D feature
+// block of a stage are each ONE contiguous range in HBM, so a loader thread moves them with two
+// cp.async.bulk (TMA) copies into a deep shared-memory ring: ~100 KB in flight per SM instead
+// of one stage of per-thread loads.  Producers transpose / split from that ring.
+// ---------------------------------------------------------------------------
+constexpr int RAW_KF = 32;          // frames per stage
+constexpr int RAW_OPS = 2;          // operand (MMA) stages
+constexpr int RAW_MAX = 8;          // raw ring depth (upper bound)
+constexpr int RAW_THREADS = PRODUCERS + 64;   // + MMA warp + loader warp
+
+struct RawBarriers {
+    uint64_t raw_full[RAW_MAX], raw_empty[RAW_MAX];
+    uint64_t full[RAW_OPS], empty[RAW_OPS];
+    uint64_t tfull[2], tempty[2];
+    uint32_t tmem_base;
+    uint32_t pad[3];
+};
+
+template <int D4>
+struct RawCfg {
+    static constexpr int D = 4 * D4, KF = RAW_KF;
+    static constexpr int NB = (2 * D + 1 + 15) / 16 * 16;
+    static constexpr int KG = KF / 8;
+    static constexpr int A_FLOATS = KF * GM, B_FLOATS = KF * NB;
+    static constexpr int STAGE_FLOATS = 2 * A_FLOATS + 2 * B_FLOATS;
+    static constexpr int BU = ((KF / 4) * D + PRODUCERS - 1) / PRODUCERS;
+    static constexpr int NCH = NB / 16, MYCH = (NCH + 1) / 2;
+    static constexpr uint32_t TMEM_COLS = 2 * NB <= 64 ? 64 : (2 * NB <= 128 ? 128 : (2 * NB <= 256 ? 256 : 512));
+    static constexpr int DR = 64 / KF;
+    using acc_t = typename std::conditional<(MYCH <= 3), double, float>::type;
+    static constexpr size_t FIXED = (size_t)RAW_OPS * STAGE_FLOATS * 4 + sizeof(RawBarriers) + 1024;
+    static size_t raw_stage_bytes(int M) { return (size_t)KF * (M + D) * 4; }
+    static int raw_stages(int M) {
+        size_t left = 227 * 1024 - FIXED;
+        int n = (int)(left / raw_stage_bytes(M));
+        return n > RAW_MAX ? RAW_MAX : n;
+    }
+};
+
+template <int D4>
+__global__ void __launch_bounds__(RAW_THREADS, 1) accumulate_tc_raw_kernel(Args a, int RS) {
+    using C = RawCfg<D4>;
+    constexpr int D = C::D, NB = C::NB, KG = C::KG, KF = C::KF, STAGES = RAW_OPS;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    float* stage_base = reinterpret_cast<float*>(smem_raw);
+    RawBarriers* bars = reinterpret_cast<RawBarriers*>(stage_base + (size_t)STAGES * C::STAGE_FLOATS);
+    float* ring = reinterpret_cast<float*>(bars + 1);          // RS x [KF x M posteriors | KF x D features]
+    const int M = a.M;
+    const int raw_floats = KF * (M + D);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t f_begin = (int64_t)blockIdx.x * a.frames_per_cta;
+    const int64_t f_end = min(a.N, f_begin + a.frames_per_cta);
+    const int n_tiles = (f_end > f_begin) ? (int)((f_end - f_begin + KF - 1) / KF) : 0;
+
+    if (tid == 0) {
+        for (int i = 0; i < RAW_MAX; ++i) {
+            mbar_init(&bars->raw_full[i], 1);
+            mbar_init(&bars->raw_empty[i], PRODUCERS);
+        }
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&bars->full[i], PRODUCERS);
+            mbar_init(&bars->empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars->tfull[i], 1);
+            mbar_init(&bars->tempty[i], PRODUCERS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == PRODUCERS / 32) tmem_alloc(&bars->tmem_base, C::TMEM_COLS);
+    for (int i = tid; i < STAGES * C::STAGE_FLOATS / 4; i += RAW_THREADS)
+        reinterpret_cast<float4*>(stage_base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    for (int i = tid; i < STAGES * KF; i += RAW_THREADS) {
+        int st = i / KF, f = i - st * KF;
+        float* b_hi = stage_base + (size_t)st * C::STAGE_FLOATS + 2 * C::A_FLOATS;
+        b_hi[((2 * D) >> 3) * (KF * 8) + (f >> 2) * 32 + ((2 * D) & 7) * 4 + (f & 3)] = 1.f;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == PRODUCERS / 32 + 1) {
+        // ------------------------------- loader -----------------------------------
+        if (lane == 0) {
+            for (int it = 0; it < n_tiles; ++it) {
+                const int rs = it % RS;
+                const int64_t t0 = f_begin + (int64_t)it * KF;
+                const uint32_t rows = (uint32_t)min((int64_t)KF, f_end - t0);
+                mbar_wait(&bars->raw_empty[rs], ((it / RS) & 1) ^ 1);
+                float* dst = ring + (size_t)rs * raw_floats;
+                mbar_arrive_expect_tx(&bars->raw_full[rs], rows * (uint32_t)(M + D) * 4u);
+                bulk_g2s(dst, a.pdf_post + (size_t)t0 * M, rows * (uint32_t)M * 4u, &bars->raw_full[rs]);
+                bulk_g2s(dst + KF * M, a.X + (size_t)t0 * D, rows * (uint32_t)D * 4u, &bars->raw_full[rs]);
+            }
+        }
+    } else if (warp == PRODUCERS / 32) {
+        // ------------------------------ MMA issuer -------------------------------
+        if (lane == 0 && n_tiles > 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NB >> 3) << 17) |
+                                   ((uint32_t)(GM >> 4) << 24);
+            constexpr uint32_t LBO = 128, SBO = (KF / 4) * 128;
+            for (int it = 0; it < n_tiles; ++it) {
+                const int st = it % STAGES;
+                const int grp = it / C::DR, buf = grp & 1;
+                const bool first = it % C::DR == 0, last = (it % C::DR == C::DR - 1) || it == n_tiles - 1;
+                mbar_wait(&bars->full[st], (it / STAGES) & 1);
+                if (first) mbar_wait(&bars->tempty[buf], ((grp >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * NB);
+                const uint32_t a_hi = smem_u32(stage_base + (size_t)st * C::STAGE_FLOATS);
+                const uint32_t a_lo = a_hi + C::A_FLOATS * 4u;
+                const uint32_t b_hi = a_lo + C::A_FLOATS * 4u;
+                const uint32_t b_lo = b_hi + C::B_FLOATS * 4u;
+#pragma unroll 1
+                for (int ks = 0; ks < KG; ++ks) {
+                    const uint32_t ko = (uint32_t)ks * 256u;
+                    const uint64_t dah = make_desc(a_hi + ko, LBO, SBO), dal = make_desc(a_lo + ko, LBO, SBO);
+                    const uint64_t dbh = make_desc(b_hi + ko, LBO, SBO), dbl = make_desc(b_lo + ko, LBO, SBO);
+                    umma_tf32(d_tmem, dah, dbh, idesc, !(first && ks == 0));
+                    umma_tf32(d_tmem, dal, dbh, idesc, 1);
+                    umma_tf32(d_tmem, dah, dbl, idesc, 1);
+                }
+                umma_commit(&bars->empty[st]);
+                if (last) umma_commit(&bars->tfull[buf]);
+            }
+        }
+    } else {
+        // ------------------------------ producers --------------------------------
+        const int gl = tid & (GM - 1);
+        const int fq0 = tid >> 7;
+        const bool a_active = gl < M;
+        constexpr int AU = KF / 8;
+        const int a_row = (gl >> 3) * (KF * 8) + (gl & 7) * 4;
+        int xd[C::BU], xfq[C::BU];
+        bool x_active[C::BU];
+#pragma unroll
+        for (int j = 0; j < C::BU; ++j) {
+            const int u = tid + j * PRODUCERS;
+            x_active[j] = u < (KF / 4) * D;
+            xd[j] = x_active[j] ? u % D : 0;
+            xfq[j] = x_active[j] ? u / D : 0;
+        }
+        using acc_t = typename C::acc_t;
+        const int q = warp & 3, half = warp >> 2;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        acc_t sums[C::MYCH][16];
+#pragma unroll
+        for (int m = 0; m < C::MYCH; ++m)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sums[m][i] = (acc_t)0;
+        auto drain = [&](int g) {
+            const int buf = g & 1;
+            mbar_wait(&bars->tfull[buf], (g >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int m = 0; m < C::MYCH; ++m) {
+                const int ch = half + 2 * m;
+                if (ch < C::NCH) {
+                    float v[16];
+                    tmem_ld16(taddr + (uint32_t)(buf * NB + ch * 16), v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) sums[m][i] += (acc_t)v[i];
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&bars->tempty[buf]);
+        };
+
+        for (int it = 0; it < n_tiles; ++it) {
+            const int st = it % STAGES, rs = it % RS;
+            const int rows = (int)min((int64_t)KF, f_end - (f_begin + (int64_t)it * KF));
+            const float* rp = ring + (size_t)rs * raw_floats;     // posteriors [KF][M]
+            const float* rx = rp + KF * M;                         // features   [KF][D]
+            float* A_hi = stage_base + (size_t)st * C::STAGE_FLOATS;
+            float* A_lo = A_hi + C::A_FLOATS;
+            float* B_hi = A_lo + C::A_FLOATS;
+            float* B_lo = B_hi + C::B_FLOATS;
+            mbar_wait(&bars->raw_full[rs], (it / RS) & 1);
+            mbar_wait(&bars->empty[st], ((it / STAGES) & 1) ^ 1);
+            if (a_active) {
+#pragma unroll
+                for (int j = 0; j < AU; ++j) {
+                    const int f0 = (fq0 + 2 * j) * 4;
+                    float h[4], l[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float w = (f0 + i < rows) ? rp[(f0 + i) * M + gl] : 0.f;
+                        h[i] = tf32_rn(w);
+                        l[i] = w - h[i];
+                    }
+                    const int off = a_row + (fq0 + 2 * j) * 32;
+                    *reinterpret_cast<float4*>(A_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<float4*>(A_lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < C::BU; ++j) {
+                if (x_active[j]) {
+                    const int d = xd[j], fq = xfq[j];
+                    float xh[4], xl[4], qh[4], ql[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float x = (fq * 4 + i < rows) ? rx[(fq * 4 + i) * D + d] : 0.f;
+                        const float qq = x * x;
+                        xh[i] = tf32_rn(x);
+                        xl[i] = x - xh[i];
+                        qh[i] = tf32_rn(qq);
+                        ql[i] = qq - qh[i];
+                    }
+                    const int offx = (d >> 3) * (KF * 8) + fq * 32 + (d & 7) * 4;
+                    const int offq = ((D + d) >> 3) * (KF * 8) + fq * 32 + ((D + d) & 7) * 4;
+                    *reinterpret_cast<float4*>(B_hi + offx) = make_float4(xh[0], xh[1], xh[2], xh[3]);
+                    *reinterpret_cast<float4*>(B_lo + offx) = make_float4(xl[0], xl[1], xl[2], xl[3]);
+                    *reinterpret_cast<float4*>(B_hi + offq) = make_float4(qh[0], qh[1], qh[2], qh[3]);
+                    *reinterpret_cast<float4*>(B_lo + offq) = make_float4(ql[0], ql[1], ql[2], ql[3]);
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(&bars->full[st]);
+            mbar_arrive(&bars->raw_empty[rs]);
+            if (it % C::DR == 0 && it > 0) drain(it / C::DR - 1);
+        }
+        if (n_tiles > 0) {
+            drain((n_tiles - 1) / C::DR);
+            const int g = q * 32 + lane;
+            if (g < M) {
+                const int Q = 2 * D + 2;
+                double* row = a.acc + (size_t)g * Q;
+#pragma unroll
+                for (int m = 0; m < C::MYCH; ++m) {
+                    const int ch = half + 2 * m;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int c = ch * 16 + i;
+                        const double v = (double)sums[m][i];
+                        if (c < 2 * D) {
+                            if (v != 0.0) atomicAdd(row + c, c < D ? v : -0.5 * v);
+                        } else if (c == 2 * D) {
+                            if (v != 0.0) {
+                                atomicAdd(row + 2 * D, -0.5 * v);
+                                atomicAdd(row + 2 * D + 1, 0.5 * v);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == PRODUCERS / 32) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+template <int D4>
+static int launch_raw(const Args& a0, cudaStream_t st) {
+    using C = RawCfg<D4>;
+    Args a = a0;
+    const int RS = C::raw_stages(a.M);
+    if (RS < 3) return BEER_ERR_UNSUPPORTED;
+    const size_t smem = C::FIXED + (size_t)RS * C::raw_stage_bytes(a.M);
+    static bool attr_set = false;
+    if (!attr_set) {
+        BEER_CUDA_TRY(cudaFuncSetAttribute(accumulate_tc_raw_kernel<D4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           227 * 1024));
+        attr_set = true;
+    }
+    a.n_gtiles = 1;
+    int64_t chunks = kNumSMs;
+    int64_t max_chunks = (a.N + RAW_KF - 1) / RAW_KF;
+    if (chunks > max_chunks) chunks = max_chunks;
+    int64_t fpc = (a.N + chunks - 1) / chunks;
+    fpc = (fpc + RAW_KF - 1) / RAW_KF * RAW_KF;
+    chunks = (a.N + fpc - 1) / fpc;
+    a.frames_per_cta = fpc;
+    accumulate_tc_raw_kernel<D4><<<(int)chunks, RAW_THREADS, smem, st>>>(a, RS);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
 }  // namespace kctc
 }  // namespace beer
 
@@ -437,6 +726,18 @@ int beer_accumulate_stats_tc(const float* X, int64_t N, int D, const float* pdf_
     a.comp_llh = comp_llh; a.comp_off = comp_off; a.Kp = Kp; a.M = M; a.C = M / Kp; a.acc = acc_normal;
     a.n_gtiles = 0; a.frames_per_cta = 0;
     cudaStream_t st = (cudaStream_t)stream;
+    // dense posteriors of a single Gaussian tile: bulk-staged kernel (every stage is two contiguous copies)
+    if (comp_llh == nullptr && pdf_post != nullptr && M <= kctc::GM && ld_post == M && M % 4 == 0 &&
+        ((uintptr_t)pdf_post & 15) == 0 && getenv("BEER_B200_KC_NO_BULK") == nullptr) {
+        int rc = BEER_ERR_UNSUPPORTED;
+        switch (D / 4) {
+            case 5: rc = kctc::launch_raw<5>(a, st); break;
+            case 10: rc = kctc::launch_raw<10>(a, st); break;
+            case 16: rc = kctc::launch_raw<16>(a, st); break;
+            case 20: rc = kctc::launch_raw<20>(a, st); break;
+        }
+        if (rc != BEER_ERR_UNSUPPORTED) return rc;
+    }
     switch (D / 4) {
         case 5: return kctc::launch<5, 64, 2>(a, st);
         case 10: return kctc::launch<10, 32, 4>(a, st);

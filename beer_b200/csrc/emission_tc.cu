@@ -11,8 +11,9 @@
 // tcgen05.ld, adds the bias, takes the log-sum-exp over the C components of each pdf and
 // stores the offset-form llh.
 //
-// Warp roles: warps 0-3 = workers (tile builder + epilogue, one frame row per thread),
-// warp 4 = MMA issuer (one elected lane) + TMEM allocator, warp 5 = weight-image producer.
+// Warp roles: warps 0-7 = workers (tile builder: two threads per frame row; epilogue: one frame
+// row per thread, the two warps of a TMEM lane quarter split the columns), warp 8 = MMA issuer
+// (one elected lane) + TMEM allocator, warp 9 = weight-image producer.
 //
 // Reference semantics: beer/dists/normalgamma.py:55-59, beer/models/mixtureset.py:85-98.
 #include "common.cuh"
@@ -24,8 +25,9 @@ namespace tc {
 
 constexpr int FR = 128;        // frames per tile (UMMA M)
 constexpr int NB_MAX = 128;    // Gaussians per chunk (UMMA N)
-constexpr int WORKERS = 128;
-constexpr int THREADS = 192;
+constexpr int WORKERS = 256;          // 8 worker warps: two per scheduler (one per scheduler left them latency-bound)
+constexpr int MMA_WARP = WORKERS / 32, LOAD_WARP = MMA_WARP + 1;
+constexpr int THREADS = WORKERS + 64;
 
 using namespace tcu;
 
@@ -85,7 +87,7 @@ __global__ void __launch_bounds__(THREADS, 1) emission_tc_kernel(Args a) {
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) tmem_alloc(&bars->tmem_base, tmem_cols);
+    if (warp == MMA_WARP) tmem_alloc(&bars->tmem_base, tmem_cols);
     for (int i = tid; i < bias_floats; i += THREADS) s_bias[i] = a.bias[i];
     for (int i = tid; i <= D; i += THREADS) s_ref[i] = a.ref[i];
     tc_fence_before();
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(THREADS, 1) emission_tc_kernel(Args a) {
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
-    if (warp == 5) {
+    if (warp == LOAD_WARP) {
         // ------------------------- weight-image producer -------------------------
         if (lane == 0) {
             const uint32_t bytes = (uint32_t)b_stage_floats * 4u;
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(THREADS, 1) emission_tc_kernel(Args a) {
                     }
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == MMA_WARP) {
         // ------------------------------ MMA issuer -------------------------------
         if (lane == 0) {
             // instruction descriptor: D=f32, A=B=tf32, both K-major, N = NB, M = 128
@@ -153,26 +155,35 @@ __global__ void __launch_bounds__(THREADS, 1) emission_tc_kernel(Args a) {
         }
     } else {
         // ------------------------ workers: build tile, epilogue ------------------
-        const int r = tid;  // frame row inside the tile, also the TMEM lane
-        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-        const int rbase = (r >> 3) * (Kd * 8) + (r & 7) * 4;
+        // build: lanes l and l ^ 8 share a frame row (interleaved 16-byte chunks of x);
+        // epilogue: TMEM lane = frame row 32 (warp % 4) + lane, warps w and w + 4 split the columns
+        const int rb = (tid & 7) + 8 * (tid >> 4), hb = (tid >> 3) & 1;   // 8 lanes = 8 rows: conflict-free stores
+        const int r = (warp & 3) * 32 + lane, he = warp >> 2;
+        const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+        const int rbase = (rb >> 3) * (Kd * 8) + (rb & 7) * 4;
+        constexpr int XC = (D4 + 1) / 2;     // x chunks per builder thread
         float* s_out = a.staged ? reinterpret_cast<float*>(bars + 1) : nullptr;   // [FR][Kp] llh tile
 
-        auto load_x = [&](int64_t tile, float4 (&xv)[D4]) {
-            const int64_t t = tile * FR + r;
+        auto load_x = [&](int64_t tile, float4 (&xv)[XC]) {
+            const int64_t t = tile * FR + rb;
             const float4* xrow = reinterpret_cast<const float4*>(a.X + (size_t)(t < a.N ? t : 0) * D);
 #pragma unroll
-            for (int c = 0; c < D4; ++c) xv[c] = __ldg(xrow + c);
+            for (int i = 0; i < XC; ++i) {
+                const int c = 2 * i + hb;
+                xv[i] = (c < D4) ? __ldg(xrow + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         };
         // statistics tile [x | -x^2/2] of this thread's frame, hi / lo split, + the per-frame constant
-        auto build = [&](int64_t tile, const float4 (&xv)[D4]) {
-            const int64_t t = tile * FR + r;
+        auto build = [&](int64_t tile, const float4 (&xv)[XC]) {
+            const int64_t t = tile * FR + rb;
             const bool valid = t < a.N;
             float rt = 0.f;
 #pragma unroll
-            for (int c = 0; c < D4; ++c) {
-                const float x[4] = {valid ? xv[c].x : 0.f, valid ? xv[c].y : 0.f, valid ? xv[c].z : 0.f,
-                                    valid ? xv[c].w : 0.f};
+            for (int i = 0; i < XC; ++i) {
+                const int c = 2 * i + hb;
+                if (c >= D4) continue;
+                const float x[4] = {valid ? xv[i].x : 0.f, valid ? xv[i].y : 0.f, valid ? xv[i].z : 0.f,
+                                    valid ? xv[i].w : 0.f};
                 float h[4], l[4], qh[4], ql[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -188,7 +199,8 @@ __global__ void __launch_bounds__(THREADS, 1) emission_tc_kernel(Args a) {
                 *reinterpret_cast<float4*>(A_hi + rbase + (D4 + c) * 32) = make_float4(qh[0], qh[1], qh[2], qh[3]);
                 *reinterpret_cast<float4*>(A_lo + rbase + (D4 + c) * 32) = make_float4(ql[0], ql[1], ql[2], ql[3]);
             }
-            if (valid && a.frame_ref != nullptr) a.frame_ref[t] = rt + s_ref[D];
+            rt += __shfl_xor_sync(0xffffffffu, rt, 8);      // the two halves of the row
+            if (valid && hb == 0 && a.frame_ref != nullptr) a.frame_ref[t] = rt + s_ref[D];
         };
         // TMEM -> registers -> bias, log-sum-exp over the C components -> llh (chunk c of a tile)
         auto epilogue = [&](int64_t tile, uint32_t it, int c) {
@@ -205,7 +217,8 @@ __global__ void __launch_bounds__(THREADS, 1) emission_tc_kernel(Args a) {
             const int g0 = c * a.NB;
             const float* bias_c = s_bias + ((a.stages == 1) ? 0 : g0);
             const uint32_t taddr = tmem_base + lane_addr + (uint32_t)buf * (uint32_t)a.NB;
-            for (int p = 0; p < a.NB; p += 16) {
+            const int nch = a.NB >> 4, ch0 = he ? (nch + 1) / 2 : 0, ch1 = he ? nch : (nch + 1) / 2;
+            for (int p = ch0 * 16; p < ch1 * 16; p += 16) {
                 float v[16];
                 tmem_ld16(taddr + (uint32_t)p, v);
 #pragma unroll
@@ -286,7 +299,7 @@ __global__ void __launch_bounds__(THREADS, 1) emission_tc_kernel(Args a) {
         if (a.n_chunks == 1) {
             // Software pipeline: the epilogue of tile i-1 runs under the MMAs of tile i and the
             // frames of tile i+1 are already in flight.
-            float4 xv[D4];
+            float4 xv[XC];
             int64_t tile = blockIdx.x, prev = -1;
             uint32_t it = 0;
             if (tile < n_tiles) load_x(tile, xv);
@@ -304,7 +317,7 @@ __global__ void __launch_bounds__(THREADS, 1) emission_tc_kernel(Args a) {
         } else {
             uint32_t it = 0, tile_it = 0;
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
-                float4 xv[D4];
+                float4 xv[XC];
                 load_x(tile, xv);
                 mbar_wait(&bars->a_free, (tile_it & 1) ^ 1);
                 build(tile, xv);
@@ -316,7 +329,7 @@ __global__ void __launch_bounds__(THREADS, 1) emission_tc_kernel(Args a) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == MMA_WARP) {
         tc_fence_after();
         tmem_dealloc(tmem_base, tmem_cols);
     }
