@@ -419,7 +419,8 @@ static int launch(const Args& a0, cudaStream_t st) {
 constexpr int RAW_KF = 32;          // frames per stage
 constexpr int RAW_OPS = 2;          // operand (MMA) stages
 constexpr int RAW_MAX = 8;          // raw ring depth (upper bound)
-constexpr int RAW_THREADS = PRODUCERS + 64;   // + MMA warp + loader warp
+constexpr int RAW_PRODUCERS = 512;  // 16 producer warps = 4 per scheduler (2 per scheduler were latency-bound)
+constexpr int RAW_THREADS = RAW_PRODUCERS + 64;   // + MMA warp + loader warp
 
 struct RawBarriers {
     uint64_t raw_full[RAW_MAX], raw_empty[RAW_MAX];
@@ -436,11 +437,10 @@ struct RawCfg {
     static constexpr int KG = KF / 8;
     static constexpr int A_FLOATS = KF * GM, B_FLOATS = KF * NB;
     static constexpr int STAGE_FLOATS = 2 * A_FLOATS + 2 * B_FLOATS;
-    static constexpr int BU = ((KF / 4) * D + PRODUCERS - 1) / PRODUCERS;
-    static constexpr int NCH = NB / 16, MYCH = (NCH + 1) / 2;
+    static constexpr int BU = ((KF / 4) * D + RAW_PRODUCERS - 1) / RAW_PRODUCERS;
+    static constexpr int NCH = NB / 16, MYCH = (NCH + 3) / 4;   // four warps share a TMEM lane quarter
     static constexpr uint32_t TMEM_COLS = 2 * NB <= 64 ? 64 : (2 * NB <= 128 ? 128 : (2 * NB <= 256 ? 256 : 512));
     static constexpr int DR = 64 / KF;
-    using acc_t = typename std::conditional<(MYCH <= 3), double, float>::type;
     static constexpr size_t FIXED = (size_t)RAW_OPS * STAGE_FLOATS * 4 + sizeof(RawBarriers) + 1024;
     static size_t raw_stage_bytes(int M) { return (size_t)KF * (M + D) * 4; }
     static int raw_stages(int M) {
@@ -469,19 +469,19 @@ __global__ void __launch_bounds__(RAW_THREADS, 1) accumulate_tc_raw_kernel(Args 
     if (tid == 0) {
         for (int i = 0; i < RAW_MAX; ++i) {
             mbar_init(&bars->raw_full[i], 1);
-            mbar_init(&bars->raw_empty[i], PRODUCERS);
+            mbar_init(&bars->raw_empty[i], RAW_PRODUCERS);
         }
         for (int i = 0; i < STAGES; ++i) {
-            mbar_init(&bars->full[i], PRODUCERS);
+            mbar_init(&bars->full[i], RAW_PRODUCERS);
             mbar_init(&bars->empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars->tfull[i], 1);
-            mbar_init(&bars->tempty[i], PRODUCERS);
+            mbar_init(&bars->tempty[i], RAW_PRODUCERS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == PRODUCERS / 32) tmem_alloc(&bars->tmem_base, C::TMEM_COLS);
+    if (warp == RAW_PRODUCERS / 32) tmem_alloc(&bars->tmem_base, C::TMEM_COLS);
     for (int i = tid; i < STAGES * C::STAGE_FLOATS / 4; i += RAW_THREADS)
         reinterpret_cast<float4*>(stage_base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(RAW_THREADS, 1) accumulate_tc_raw_kernel(Args 
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
-    if (warp == PRODUCERS / 32 + 1) {
+    if (warp == RAW_PRODUCERS / 32 + 1) {
         // ------------------------------- loader -----------------------------------
         if (lane == 0) {
             for (int it = 0; it < n_tiles; ++it) {
@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(RAW_THREADS, 1) accumulate_tc_raw_kernel(Args 
                 bulk_g2s(dst + KF * M, a.X + (size_t)t0 * D, rows * (uint32_t)D * 4u, &bars->raw_full[rs]);
             }
         }
-    } else if (warp == PRODUCERS / 32) {
+    } else if (warp == RAW_PRODUCERS / 32) {
         // ------------------------------ MMA issuer -------------------------------
         if (lane == 0 && n_tiles > 0) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NB >> 3) << 17) |
@@ -544,39 +544,45 @@ __global__ void __launch_bounds__(RAW_THREADS, 1) accumulate_tc_raw_kernel(Args 
     } else {
         // ------------------------------ producers --------------------------------
         const int gl = tid & (GM - 1);
-        const int fq0 = tid >> 7;
+        const int fq0 = tid >> 7;            // quads fq0, fq0 + 4, ...
         const bool a_active = gl < M;
-        constexpr int AU = KF / 8;
+        constexpr int AU = KF / 16;
         const int a_row = (gl >> 3) * (KF * 8) + (gl & 7) * 4;
         int xd[C::BU], xfq[C::BU];
         bool x_active[C::BU];
 #pragma unroll
         for (int j = 0; j < C::BU; ++j) {
-            const int u = tid + j * PRODUCERS;
+            const int u = tid + j * RAW_PRODUCERS;
             x_active[j] = u < (KF / 4) * D;
             xd[j] = x_active[j] ? u % D : 0;
             xfq[j] = x_active[j] ? u / D : 0;
         }
-        using acc_t = typename C::acc_t;
-        const int q = warp & 3, half = warp >> 2;
+        // drain: lane quarter q, 16-column chunks part, part + 4, ...; Kahan-compensated fp32 sums
+        // (fp64 adds + float->double conversions throttled the fp64 / XU pipes)
+        const int q = warp & 3, part = warp >> 2;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-        acc_t sums[C::MYCH][16];
+        float sums[C::MYCH][16], comp[C::MYCH][16];
 #pragma unroll
         for (int m = 0; m < C::MYCH; ++m)
 #pragma unroll
-            for (int i = 0; i < 16; ++i) sums[m][i] = (acc_t)0;
+            for (int i = 0; i < 16; ++i) sums[m][i] = comp[m][i] = 0.f;
         auto drain = [&](int g) {
             const int buf = g & 1;
             mbar_wait(&bars->tfull[buf], (g >> 1) & 1);
             tc_fence_after();
 #pragma unroll
             for (int m = 0; m < C::MYCH; ++m) {
-                const int ch = half + 2 * m;
+                const int ch = part + 4 * m;
                 if (ch < C::NCH) {
                     float v[16];
                     tmem_ld16(taddr + (uint32_t)(buf * NB + ch * 16), v);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) sums[m][i] += (acc_t)v[i];
+                    for (int i = 0; i < 16; ++i) {
+                        const float y = v[i] - comp[m][i];
+                        const float t = sums[m][i] + y;
+                        comp[m][i] = (t - sums[m][i]) - y;
+                        sums[m][i] = t;
+                    }
                 }
             }
             tc_fence_before();
@@ -597,7 +603,7 @@ __global__ void __launch_bounds__(RAW_THREADS, 1) accumulate_tc_raw_kernel(Args 
             if (a_active) {
 #pragma unroll
                 for (int j = 0; j < AU; ++j) {
-                    const int f0 = (fq0 + 2 * j) * 4;
+                    const int f0 = (fq0 + 4 * j) * 4;
                     float h[4], l[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -605,7 +611,7 @@ __global__ void __launch_bounds__(RAW_THREADS, 1) accumulate_tc_raw_kernel(Args 
                         h[i] = tf32_rn(w);
                         l[i] = w - h[i];
                     }
-                    const int off = a_row + (fq0 + 2 * j) * 32;
+                    const int off = a_row + (fq0 + 4 * j) * 32;
                     *reinterpret_cast<float4*>(A_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
                     *reinterpret_cast<float4*>(A_lo + off) = make_float4(l[0], l[1], l[2], l[3]);
                 }
@@ -645,11 +651,11 @@ __global__ void __launch_bounds__(RAW_THREADS, 1) accumulate_tc_raw_kernel(Args 
                 double* row = a.acc + (size_t)g * Q;
 #pragma unroll
                 for (int m = 0; m < C::MYCH; ++m) {
-                    const int ch = half + 2 * m;
+                    const int ch = part + 4 * m;
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const int c = ch * 16 + i;
-                        const double v = (double)sums[m][i];
+                        const double v = (double)sums[m][i] - (double)comp[m][i];
                         if (c < 2 * D) {
                             if (v != 0.0) atomicAdd(row + c, c < D ? v : -0.5 * v);
                         } else if (c == 2 * D) {
@@ -665,7 +671,7 @@ __global__ void __launch_bounds__(RAW_THREADS, 1) accumulate_tc_raw_kernel(Args 
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == PRODUCERS / 32) {
+    if (warp == RAW_PRODUCERS / 32) {
         tc_fence_after();
         tmem_dealloc(tmem_base, C::TMEM_COLS);
     }
@@ -731,10 +737,8 @@ int beer_accumulate_stats_tc(const float* X, int64_t N, int D, const float* pdf_
         ((uintptr_t)pdf_post & 15) == 0 && getenv("BEER_B200_KC_NO_BULK") == nullptr) {
         int rc = BEER_ERR_UNSUPPORTED;
         switch (D / 4) {
-            case 5: rc = kctc::launch_raw<5>(a, st); break;
-            case 10: rc = kctc::launch_raw<10>(a, st); break;
-            case 16: rc = kctc::launch_raw<16>(a, st); break;
-            case 20: rc = kctc::launch_raw<20>(a, st); break;
+            case 5: rc = kctc::launch_raw<5>(a, st); break;      // wider D: the drain's register sums
+            case 10: rc = kctc::launch_raw<10>(a, st); break;    // do not fit 18 warps per SM
         }
         if (rc != BEER_ERR_UNSUPPORTED) return rc;
     }
