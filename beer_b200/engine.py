@@ -173,7 +173,7 @@ class VBEngine:
     copy of chunk i+1 overlapping the kernels of chunk i."""
 
     def __init__(self, emission, plan, utts, datasize=None, scale=1.0, lrate=1.0, chunk_frames=None,
-                 process_group=None, distributed=None):
+                 process_group=None, distributed=None, use_graph=False):
         self.em, self.plan, self.utts = emission, plan, utts
         self.scale, self.lrate = float(scale), float(lrate)
         self.dev = emission.device
@@ -216,6 +216,10 @@ class VBEngine:
         self.frame_ref = torch.empty(nmax, device=self.dev, dtype=f32)
         self.utt_ell = torch.zeros(utts.n_utts, device=self.dev, dtype=f64)
         self.gpu_launches = 0
+        # the SIMT emission kernel reads the component offsets back to size its grid: not capturable
+        self.use_graph = bool(use_graph) and (emission.use_tc or not emission.has_mixtures)
+        self._shard_counts = torch.tensor([float(self.local_frames), float(utts.n_utts)], device=self.dev, dtype=f64)
+        self._graph, self._graph_elbo, self._graph_launches, self._eager_steps = None, None, 0, 0
 
     def _make_chunks(self, chunk_frames):
         """Split the shard into runs of whole utterances of at most `chunk_frames` frames:
@@ -278,9 +282,7 @@ class VBEngine:
                 self._free[ci & 1].record()
                 self._free_valid[ci & 1] = True
         # ELBO bookkeeping of the shard (objectives.py:176-190 summed as in accumulate.py:39-59)
-        n_local = float(self.local_frames)
-        self.extras[1] = n_local
-        self.extras[2] = float(self.utts.n_utts)
+        self.extras[1:3].copy_(self._shard_counts)       # device -> device: capturable in a CUDA graph
         self.extras[3] = self.utt_ell.sum()
         # sum_u ell_u / T_u; multiplied by the global datasize after the reduction
         self.extras[0] = (self.utt_ell * self.inv_len).sum()
@@ -322,11 +324,43 @@ class VBEngine:
         return self._gframes
 
     def step(self):
-        """E-step + all-reduce + M-step; returns the summed ELBO (device fp64 scalar)."""
+        """E-step + all-reduce + M-step; returns the summed ELBO (device fp64 scalar).
+
+        With `use_graph` (resident features, no stage profiling) the ~16 launches of an iteration
+        are captured once into a CUDA graph and replayed: the kernels are unchanged, only the
+        launch gaps between the small parameter kernels go away.  The returned tensor is then a
+        static buffer that the next step overwrites."""
         self._global_frames()
+        if self.use_graph and not self.host_mode and self.profile is None:
+            if self._graph is None and self._eager_steps >= 1:
+                self._capture()
+            if self._graph is not None:
+                self._graph.replay()
+                self.gpu_launches += self._graph_launches
+                return self._graph_elbo
+        self._eager_steps += 1
+        return self._step_eager()
+
+    def _step_eager(self):
         self.e_step()
         self.reduce()
         return self.m_step()
+
+    def _capture(self):
+        """Capture one iteration (side stream, as CUDA requires) after an eager one has run."""
+        before = self.gpu_launches
+        try:
+            torch.cuda.synchronize(self.dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                elbo = self._step_eager()
+            self._graph, self._graph_elbo = graph, elbo
+            self._graph_launches = self.gpu_launches - before
+        except Exception as exc:       # capture is an optimisation: fall back to plain launches
+            import warnings
+            warnings.warn(f'CUDA graph capture of the VB iteration failed ({exc}); launching eagerly')
+            self.use_graph = False
+        self.gpu_launches = before
 
     def elbo_per_frame(self, elbo):
         """The figure `beer hmm update` logs (update.py:72): ELBO / (n_utts * datasize)."""

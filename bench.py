@@ -206,7 +206,7 @@ def run_gpu(args, c):
     X = synthetic.sample_utterances(graph, means, U, T, seed=100 + rank, device=dev)
     utts = Utterances(X, [T] * U)
 
-    def make_engine(utts=utts, chunk_frames=args.chunk_frames):
+    def make_engine(utts=utts, chunk_frames=args.chunk_frames, use_graph=False):
         prior, post = synthetic.initial_normal_gamma(M, D, seed=2, device=dev)
         groups, comp_off = (), None
         if C > 1:
@@ -215,20 +215,19 @@ def run_gpu(args, c):
             comp_off = np.arange(K + 1) * C
         em = EmissionParams(prior, post, comp_off=comp_off, weight_groups=groups)
         return VBEngine(em, plan, utts, datasize=float(world * U * T), chunk_frames=chunk_frames,
-                        distributed=world > 1)
+                        distributed=world > 1, use_graph=use_graph)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    eng = make_engine()
+    eng = make_engine(use_graph=not args.no_graph)
     elbos = []
     for _ in range(args.warmup):
-        elbos.append(eng.step())
+        elbos.append(eng.step().clone())
     barrier()
     eng.gpu_launches = 0
-    eng.profile = {}
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -237,7 +236,7 @@ def run_gpu(args, c):
     torch.cuda.nvtx.range_push('bench_timed')     # ncu --nvtx --nvtx-include "bench_timed/" selects these launches
     ev0.record()
     for _ in range(args.steps):
-        elbos.append(eng.step())
+        elbos.append(eng.step().clone())     # the graph's ELBO buffer is overwritten by the next step
     ev1.record()
     torch.cuda.nvtx.range_pop()
     barrier()
@@ -245,6 +244,11 @@ def run_gpu(args, c):
     clocks = sampler.stop() if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
     launches = eng.gpu_launches
+    # per-stage kernel durations: the same iteration launched eagerly with CUDA events around the stages
+    eng.profile = {}
+    for _ in range(3):
+        eng.step()
+    torch.cuda.synchronize()
     stage_ms = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in eng.profile.items()}
     eng.profile = None
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -353,6 +357,7 @@ def main():
     ap.add_argument('--e2e-chunk-frames', type=int, default=None)
     ap.add_argument('--n-utts', type=int, default=None, help='override utterances per GPU (debug)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch every kernel eagerly (no CUDA graph)')
     args = ap.parse_args()
     from beer_b200.synthetic import CONFIGS
     c = dict(CONFIGS[args.config])

@@ -14,8 +14,9 @@ def _host(t):
     return m, k[:, None], a[:, None], b
 
 
-@pytest.mark.parametrize('C,chunk', [(1, None), (1, 130), (3, None), (3, 200)])
-def test_vb_iterations_match_oracle(C, chunk):
+@pytest.mark.parametrize('C,chunk,graph', [(1, None, False), (1, 130, False), (3, None, False), (3, 200, False),
+                                           (1, None, True), (3, 130, True)])
+def test_vb_iterations_match_oracle(C, chunk, graph):
     from beer_b200 import ops, synthetic
     from beer_b200.engine import EmissionParams, Utterances, VBEngine, WeightGroup
     dev = torch.device('cuda', 0)
@@ -39,7 +40,8 @@ def test_vb_iterations_match_oracle(C, chunk):
         dprior, dpost = conc.double().cpu().numpy(), conc.double().cpu().numpy()
     em = EmissionParams(prior, post, comp_off=comp_off, weight_groups=groups)
     N = sum(lens)
-    eng = VBEngine(em, plan, Utterances(X, lens), datasize=float(N), chunk_frames=chunk, distributed=False)
+    eng = VBEngine(em, plan, Utterances(X, lens), datasize=float(N), chunk_frames=chunk, distributed=False,
+                   use_graph=graph)
     ng_prior, ng_post = _host(prior), _host(post)
     og = (graph.init_log_probs.double().numpy(), graph.final_log_probs.double().numpy(),
           graph.trans_log_probs.double().numpy(), graph.pdf_id_mapping)
