@@ -33,6 +33,9 @@ SIGNATURES = {
     'beer_hmm_workspace_bytes': (C.c_int64, [c_ptr, C.c_int64]),
     'beer_hmm_forward_backward': (C.c_int, [c_ptr, c_ptr, C.c_int64, c_ptr, c_ptr, C.c_int, C.c_float,
                                             c_ptr, c_ptr, C.c_int64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    'beer_hmm_unit_count_size': (C.c_int, [c_ptr]),
+    'beer_hmm_forward_backward_units': (C.c_int, [c_ptr, c_ptr, C.c_int64, c_ptr, c_ptr, C.c_int, C.c_float,
+                                                  c_ptr, c_ptr, C.c_int64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     'beer_hmm_viterbi': (C.c_int, [c_ptr, c_ptr, C.c_int64, c_ptr, C.c_int, C.c_float, c_ptr, c_ptr,
                                    c_ptr]),
     'beer_accumulate_stats': (C.c_int, [c_ptr, C.c_int64, C.c_int, c_ptr, C.c_int64, c_ptr, C.c_int64,

@@ -221,6 +221,7 @@ struct FbArgs {
     double* utt_logz;
     int vec;  // 16-byte row copies are legal
     const float* lr_w;  // aligned left-to-right loop weights (hmm_fb_lr_kernel)
+    double* unit_counts;  // [K / SU] or NULL: sum_t xi_t(unit ends -> unit start) + gamma_0(start)
 };
 
 constexpr int FB_WARPS = 4;
@@ -1070,6 +1071,10 @@ __global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_lr_kernel(FbArgs a) {
         }
         float ell = 0.f;
         double ell_d = 0.0;
+        const bool units = a.unit_counts != nullptr;
+        float cnt[U], dstart[U], mbs_prev = 0.f;   // unit counts, delta_{t+1} of the unit starts
+#pragma unroll
+        for (int q = 0; q < U; ++q) cnt[q] = dstart[q] = 0.f;
         for (int i = 0; i < T; ++i) {
             const int t = T - 1 - i;
             cp_async_wait<PF - 1>();
@@ -1118,6 +1123,22 @@ __global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_lr_kernel(FbArgs a) {
                     a.frame_exp_llh[t0 + t] = f * kLn2 + r;
                 }
             }
+            if (units && sum > 0.f) {
+                // transition posteriors through the junction, reduced over the unit ends (graph.py:308-323,
+                // phoneloop.py:88-97): xi_t(ends -> start_q) = 2^(jv_t + w_in + delta_{t+1}(start_q) - mbs_t - Zg_t)
+                if (i > 0) {
+                    float ends[U];
+#pragma unroll
+                    for (int q = 0; q < U; ++q) ends[q] = la[q * SU + SU - 1] + w_jout[q * SU + SU - 1];
+                    const float base = warp_lse(ends) - mbs_prev - (ms + lg2(sum));
+#pragma unroll
+                    for (int q = 0; q < U; ++q) cnt[q] += ex2(base + w_in[q * SU] + dstart[q]);
+                }
+                if (t == 0) {
+#pragma unroll
+                    for (int q = 0; q < U; ++q) cnt[q] += v[q * SU];
+                }
+            }
             if (a.state_post != nullptr) write_row(a.state_post + (size_t)(t0 + t) * K, v, 1.f);
             if (a.pdf_post != nullptr) write_row(a.pdf_post + (size_t)(t0 + t) * a.ld_post, v, a.scale);
             if (t == 0) break;
@@ -1140,8 +1161,18 @@ __global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_lr_kernel(FbArgs a) {
             const float mbs = (mb == kNegInf) ? 0.f : mb;
 #pragma unroll
             for (int j = 0; j < S; ++j) lb[j] -= mbs;
+            mbs_prev = mbs;
+#pragma unroll
+            for (int q = 0; q < U; ++q) dstart[q] = delta[q * SU];
         }
         cp_async_wait<0>();
+        if (units) {
+#pragma unroll
+            for (int q = 0; q < U; ++q) {
+                const int unit = lane * U + q;
+                if (unit * SU < K && cnt[q] != 0.f) atomicAdd(a.unit_counts + unit, (double)cnt[q]);
+            }
+        }
         ell_d += (double)ell;
         ell_d = warp_sum(ell_d);
         double rs = 0.0;
@@ -1537,10 +1568,25 @@ int64_t beer_hmm_workspace_bytes(const beer_graph_plan* plan, int64_t N) {
     return (N * fb_row_stride(plan) + 64) * (int64_t)sizeof(float);
 }
 
+int beer_hmm_unit_count_size(const beer_graph_plan* plan) {
+    if (!plan) return BEER_ERR_ARG;
+    return plan->lr_su ? plan->K / plan->lr_su : 0;
+}
+
 int beer_hmm_forward_backward(const beer_graph_plan* plan, const float* pdf_llh, int64_t ld_pdf,
                               const float* frame_ref, const int64_t* utt_off, int n_utts, float scale,
                               float* state_post, float* pdf_post, int64_t ld_post, float* frame_exp_llh,
                               double* utt_exp_llh, double* utt_logz, void* workspace, void* stream) {
+    return beer_hmm_forward_backward_units(plan, pdf_llh, ld_pdf, frame_ref, utt_off, n_utts, scale, state_post,
+                                           pdf_post, ld_post, frame_exp_llh, utt_exp_llh, utt_logz, nullptr,
+                                           workspace, stream);
+}
+
+int beer_hmm_forward_backward_units(const beer_graph_plan* plan, const float* pdf_llh, int64_t ld_pdf,
+                                    const float* frame_ref, const int64_t* utt_off, int n_utts, float scale,
+                                    float* state_post, float* pdf_post, int64_t ld_post, float* frame_exp_llh,
+                                    double* utt_exp_llh, double* utt_logz, double* unit_counts, void* workspace,
+                                    void* stream) {
     if (!plan || !pdf_llh || !utt_off || !utt_exp_llh || !workspace || n_utts < 0) return BEER_ERR_ARG;
     if (ld_pdf < plan->Kp || (pdf_post && ld_post < plan->Kp)) return BEER_ERR_ARG;
     if (n_utts == 0) return BEER_OK;
@@ -1557,9 +1603,12 @@ int beer_hmm_forward_backward(const beer_graph_plan* plan, const float* pdf_llh,
     a.vec = (plan->map_identity && plan->S % 4 == 0 && plan->K % 4 == 0 && ld_pdf % 4 == 0 &&
              ((uintptr_t)pdf_llh & 15) == 0) ? 1 : 0;
     a.lr_w = plan->lr_w;
+    a.unit_counts = unit_counts;
+    if (unit_counts != nullptr && !(plan->lr_su && plan->map_identity)) return BEER_ERR_UNSUPPORTED;
     const bool post_ok = (pdf_post == nullptr || (ld_post % 4 == 0 && ((uintptr_t)pdf_post & 15) == 0)) &&
                          (state_post == nullptr || (plan->K % 4 == 0 && ((uintptr_t)state_post & 15) == 0));
     const char* force = getenv("BEER_B200_SCAN");   // debug: "generic" | "fast" | unset (best available)
+    if (unit_counts != nullptr) force = nullptr;    // unit counts live in the left-to-right loop kernel
     const bool lr_vec = (plan->lr_su * plan->lr_u) % 4 == 0;   // the kernel moves whole float4 rows
     if (plan->lr_su && plan->map_identity && (force == nullptr || force[0] == 'l') &&
         (!lr_vec || (a.vec && post_ok))) {

@@ -26,7 +26,7 @@ from .engine import Utterances
 from .parameters import ConjugateBayesianParameter
 
 __all__ = ['Model', 'DiscreteLatentModel', 'ModelSet', 'NormalSet', 'Categorical', 'CategoricalSet', 'Mixture',
-           'MixtureSet', 'JointModelSet', 'DynamicallyOrderedModelSet', 'HMM', 'UnknownCovarianceType']
+           'MixtureSet', 'JointModelSet', 'DynamicallyOrderedModelSet', 'HMM', 'PhoneLoop', 'UnknownCovarianceType']
 
 f32, f64, i32, i64 = torch.float32, torch.float64, torch.int32, torch.int64
 
@@ -615,10 +615,12 @@ class HMM(DiscreteLatentModel):
     def _emission(self):
         return _Emission(_leaves(self.modelset))
 
-    def expected_log_likelihood(self, stats, inference_graph=None, viterbi=False, state_path=None, scale=1.):
+    def expected_log_likelihood(self, stats, inference_graph=None, viterbi=False, state_path=None, scale=1.,
+                                _unit_counts=None):
         """Per-frame sum_k p_tk gamma_tk with p = scale * llh[:, pdf_id_mapping] (hmm.py:73-92).
         Forward-backward by default; `viterbi=True` or a `state_path` give one-hot posteriors.
-        `stats` may come from an `Utterances` batch: every utterance is then its own sequence."""
+        `stats` may come from an `Utterances` batch: every utterance is then its own sequence.
+        (`_unit_counts`: PhoneLoop's reduction of the transition posteriors, see below.)"""
         graph = self.graph if inference_graph is None else inference_graph
         em = self._emission()
         X = frames_of(stats, em.D)
@@ -633,8 +635,10 @@ class HMM(DiscreteLatentModel):
             post, frame = ops.path_posteriors(path, em.Kp, pdf_map=graph.pdf_map_device(X.device), scale=scale,
                                               pdf_llh=pdf, frame_ref=fref)
             utt_ell = None
+            self.cache['path'] = path
         else:
-            r = ops.hmm_forward_backward(plan, pdf, fref, off, scale=scale, want_frame_llh=True)
+            r = ops.hmm_forward_backward(plan, pdf, fref, off, scale=scale, want_frame_llh=True,
+                                         unit_counts=_unit_counts)
             post, frame, utt_ell = r['pdf_post'], r['frame_exp_llh'], r['utt_exp_llh']
         self.cache.update(X=X, pdf_post=post, pdf_llh=pdf, comp_llh=comp, emission=em, scale=scale,
                           utts=utts, utt_exp_llh=utt_ell)
@@ -670,3 +674,89 @@ class HMM(DiscreteLatentModel):
         r = ops.hmm_forward_backward(graph.plan(n_pdfs=em.Kp), pdf, fref, off, scale=scale, want_state_post=True,
                                      want_pdf_post=False)
         return r['state_post']
+
+
+# ---------------------------------------------------------------------------------------------
+# PhoneLoop (beer/models/phoneloop.py:12-101)
+# ---------------------------------------------------------------------------------------------
+
+class PhoneLoop(HMM):
+    """Phone-loop HMM whose unit weights are learned: the end -> start transitions of the decoding
+    graph are rewritten from E[ln w] after every update (phoneloop.py:53-65) and the unit counts
+    come from the transition posteriors (phoneloop.py:83-101).  The (T-1, K, K) tensor of the
+    reference is never formed: the forward-backward kernel reduces it to one count per unit."""
+
+    @classmethod
+    def create(cls, graph, start_pdf, end_pdf, modelset, categorical=None, prior_strength=1.0):
+        if categorical is None:
+            ref = modelset.mean_field_factorization()[0][0].posterior.params.mean
+            weights = torch.ones(len(start_pdf), dtype=f32, device=ref.device) / len(start_pdf)
+            categorical = Categorical.create(weights, prior_strength)
+        return cls(graph, modelset, start_pdf, end_pdf, categorical)
+
+    def __init__(self, graph, modelset, start_pdf, end_pdf, categorical):
+        super().__init__(graph, modelset)
+        self.start_pdf = start_pdf
+        self.end_pdf = end_pdf
+        self.categorical = categorical
+        param = self.categorical.mean_field_factorization()[0][0]
+        param.register_callback(self._on_weights_update)
+        self._on_weights_update()
+
+    def _on_weights_update(self):
+        """ln A[end, starts] = ln(1 - A[end, end]) + E[ln w], in place (host side: P x P numbers per
+        update; the device plan of the graph is rebuilt from the new values on its next use)."""
+        log_weights = self.categorical.weights.posterior.expected_log_weights()
+        trans = self.graph.trans_log_probs
+        log_weights = log_weights.to(device=trans.device, dtype=trans.dtype)
+        start_idxs = [value for value in self.start_pdf.values()]
+        for end_idx in self.end_pdf.values():
+            loop_prob = trans[end_idx, end_idx].exp()
+            trans[end_idx, start_idxs] = (1 - loop_prob).log() + log_weights
+
+    def mean_field_factorization(self):
+        return _merge_groups(self.modelset.mean_field_factorization(), self.categorical.mean_field_factorization())
+
+    def expected_log_likelihood(self, stats, inference_graph=None, viterbi=False, state_path=None, scale=1.):
+        counts = None
+        if inference_graph is None and not viterbi and state_path is None:
+            # the reference switches the transition posteriors on when no inference graph is given
+            # (hmm.py:76); here: one count per unit, reduced inside the backward sweep
+            dev = self.categorical.weights.posterior.params.concentrations.device
+            plan = self.graph.plan(n_pdfs=self._emission().Kp)
+            if plan.n_units == 0:
+                raise NotImplementedError('unit counts need an aligned left-to-right phone loop (same number of '
+                                          'states in every unit); pass inference_graph= for aligned training')
+            counts = torch.zeros(plan.n_units, dtype=f64, device=dev)
+        retval = super().expected_log_likelihood(stats, inference_graph=inference_graph, viterbi=viterbi,
+                                                 state_path=state_path, scale=scale, _unit_counts=counts)
+        if counts is not None:
+            self.cache['unit_counts'] = counts
+        elif inference_graph is None:
+            self.cache['unit_path'] = self.cache['path']
+        return retval
+
+    def accumulate(self, stats, parent_msg=None):
+        retval = super().accumulate(stats, parent_msg)
+        weights = self.categorical.weights
+        start_idxs = [value for value in self.start_pdf.values()]
+        n_units = len(start_idxs)
+        if 'unit_counts' in self.cache:
+            counts = self.cache['unit_counts']
+            su = self.graph.n_states // counts.numel()
+            order = torch.as_tensor([s // su for s in start_idxs], device=counts.device)
+            phone_resps = counts[order]
+        elif 'unit_path' in self.cache:
+            # one-hot transition posteriors of a Viterbi / given path (hmm.py:49-54)
+            path = self.cache['unit_path'].long()
+            ends = torch.zeros(self.graph.n_states, dtype=torch.bool, device=path.device)
+            ends[torch.as_tensor(list(self.end_pdf.values()), device=path.device)] = True
+            starts = torch.as_tensor(start_idxs, device=path.device)
+            hit = ends[path[:-1]][:, None] & (path[1:, None] == starts[None, :])
+            phone_resps = hit.sum(dim=0).to(f64) + (path[0] == starts).to(f64)
+        else:
+            phone_resps = torch.zeros(n_units, dtype=f64, device=weights.posterior.params.concentrations.device)
+        stats_w = phone_resps.clone()
+        stats_w[-1] = phone_resps.sum()
+        retval[weights] = stats_w
+        return retval

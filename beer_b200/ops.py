@@ -160,6 +160,11 @@ class GraphPlan:
                          junction_in=int(info[3]), junction_out=int(info[4]), states_per_lane=int(info[5]),
                          map_identity=bool(info[6]), dense_nnz=int(info[7]))
 
+    @property
+    def n_units(self):
+        """Units of an aligned left-to-right loop (0 if the graph is not one)."""
+        return int(self._lib.beer_hmm_unit_count_size(self._h))
+
     def workspace_bytes(self, n_frames):
         return int(self._lib.beer_hmm_workspace_bytes(self._h, int(n_frames)))
 
@@ -171,7 +176,7 @@ class GraphPlan:
 
 def hmm_forward_backward(plan, pdf_llh, frame_ref, utt_off, scale=1.0, want_state_post=False,
                          want_pdf_post=True, want_frame_llh=False, want_logz=False, workspace=None,
-                         out_pdf_post=None, out_utt_exp_llh=None):
+                         out_pdf_post=None, out_utt_exp_llh=None, unit_counts=None):
     """Forward-backward for a ragged batch.  -> dict(state_post, pdf_post, frame_exp_llh,
     utt_exp_llh (fp64), utt_logz (fp64)).  `out_pdf_post` must be zero-filled by the caller
     when the graph's pdf map is not the identity (the kernel then scatter-adds)."""
@@ -193,11 +198,12 @@ def hmm_forward_backward(plan, pdf_llh, frame_ref, utt_off, scale=1.0, want_stat
     frame = torch.empty(N, device=dev, dtype=f32) if want_frame_llh else None
     utt_ell = out_utt_exp_llh if out_utt_exp_llh is not None else torch.empty(n_utts, device=dev, dtype=f64)
     utt_logz = torch.empty(n_utts, device=dev, dtype=f64) if want_logz else None
-    _lib.check(lib.beer_hmm_forward_backward(
+    _lib.check(lib.beer_hmm_forward_backward_units(
         plan._h, _p(pdf_llh, f32), pdf_llh.stride(0), _p(frame_ref, f32, True), _p(utt_off, i64), n_utts,
         float(scale), _p(state_post, f32, True), _p(pdf_post, f32, True),
         pdf_post.stride(0) if pdf_post is not None else 0, _p(frame, f32, True),
-        _p(utt_ell, f64), _p(utt_logz, f64, True), _p(workspace), _stream()), 'beer_hmm_forward_backward')
+        _p(utt_ell, f64), _p(utt_logz, f64, True), _p(unit_counts, f64, True), _p(workspace), _stream()),
+        'beer_hmm_forward_backward')
     return dict(state_post=state_post, pdf_post=pdf_post, frame_exp_llh=frame, utt_exp_llh=utt_ell,
                 utt_logz=utt_logz, workspace=workspace)
 

@@ -146,6 +146,19 @@ BEER_API int beer_hmm_forward_backward(const beer_graph_plan* plan, const float*
                               float* frame_exp_llh, double* utt_exp_llh, double* utt_logz,
                               void* workspace, void* stream);
 
+/* KB + the transition-posterior reductions a phone loop needs (beer/graph.py:308-323 reduced as in
+ * PhoneLoop.accumulate, beer/models/phoneloop.py:88-97): same as beer_hmm_forward_backward, and
+ *   unit_counts [P] (fp64, += ) <- sum_t sum_{e in unit ends} xi_t[e, start_u] + gamma_0[start_u]
+ * for every unit u of an aligned left-to-right loop (P = beer_hmm_unit_count_size(plan) units of
+ * K / P states each; 0 = the graph is not such a loop, the call then returns BEER_ERR_UNSUPPORTED).
+ * The (T-1) x K x K tensor of the reference is never formed. */
+BEER_API int beer_hmm_unit_count_size(const beer_graph_plan* plan);
+BEER_API int beer_hmm_forward_backward_units(const beer_graph_plan* plan, const float* pdf_llh, int64_t ld_pdf,
+                                    const float* frame_ref, const int64_t* utt_off, int n_utts, float scale,
+                                    float* state_post, float* pdf_post, int64_t ld_post, float* frame_exp_llh,
+                                    double* utt_exp_llh, double* utt_logz, double* unit_counts, void* workspace,
+                                    void* stream);
+
 /* KV: Viterbi best path (first-max tie-breaking) for a ragged batch.
  * Replaces CompiledGraph.best_path (beer/graph.py:329-344).
  *   path [N] (int32) <- state ids; workspace: N*K*sizeof(uint16_t) bytes. */

@@ -256,3 +256,59 @@ def test_error_behaviour(beer):
     ns = beer.NormalSet.create(torch.zeros(2, device=DEV), torch.ones(2, device=DEV), 3, cov_type='diagonal')
     with pytest.raises(beer._lib.BeerB200Error):
         ns.expected_log_likelihood(ns.sufficient_statistics(torch.zeros(4, 2)))
+
+
+def test_phoneloop_unit_counts_and_training_loop(beer):
+    """PhoneLoop over the CLI emission stack (golden 'phoneloop_mixtureset'): the transition-posterior
+    path (inference_graph=None, hmm.py:76) with the unit counts reduced in the scan kernel, the in-place
+    rewrite of the graph after every update (phoneloop.py:53-65) and the accumulate/update loop of
+    `beer hmm accumulate` + `beer hmm update` over two utterances (accumulate.py:37-59, update.py:37-62)."""
+    g = load_golden('phoneloop_mixtureset')
+    emissions, (ns1, ns2, ms1, ms2) = _joint_model(beer, g)
+    start_pdf = {f'u{i}': int(s) for i, s in enumerate(g['start_idxs'])}
+    end_pdf = {f'u{i}': int(s) for i, s in enumerate(g['end_idxs'])}
+    pl = beer.PhoneLoop.create(compiled(beer, g), start_pdf, end_pdf, emissions, prior_strength=1.)
+    wu = pl.categorical.weights
+    np.testing.assert_allclose(wu.posterior.params.concentrations.cpu().numpy(), g['u_dpost0'], rtol=1e-6)
+    np.testing.assert_allclose(pl.graph.trans_log_probs.numpy(), g['g_trans'], rtol=1e-5, atol=1e-6)
+
+    X1, X2 = t32(g['X1']), t32(g['X2'])
+    stats = pl.sufficient_statistics(X1)
+    exp_llh = pl.expected_log_likelihood(stats)
+    np.testing.assert_allclose(exp_llh.double().cpu().numpy(), g['u1_exp_llh'], rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(pl.kl_div_posterior_prior().item(), g['kl'], rtol=1e-6)
+    acc = pl.accumulate(stats)
+    np.testing.assert_allclose(acc[wu].cpu().numpy(), g['u1_acc_units'], rtol=2e-5, atol=2e-5)
+    for param, key in ((ns1.means_precisions, 'u1_acc_g1'), (ns2.means_precisions, 'u1_acc_g2'),
+                       (ms1.categoricalset.weights, 'u1_acc_d1'), (ms2.categoricalset.weights, 'u1_acc_d2')):
+        assert np.abs(acc[param].cpu().numpy() - g[key]).max() <= 3e-5 * max(np.abs(g[key]).max(), 1.0), key
+    pl.clear_cache()
+    # aligned training: no transition posteriors, zero unit statistics (phoneloop.py:98-100)
+    ag = compiled(beer, g, 'ali_')
+    s3 = pl.sufficient_statistics(t32(g['X3']))
+    pl.expected_log_likelihood(s3, inference_graph=ag, scale=0.7)
+    np.testing.assert_allclose(pl.accumulate(s3)[wu].cpu().numpy(), g['u3_acc_units'], atol=1e-12)
+    pl.clear_cache()
+
+    optim = beer.VBConjugateOptimizer(pl.conjugate_bayesian_parameters(keepgroups=True), lrate=1.)
+    N = len(X1) + len(X2)
+    elbos = []
+    for it in range(3):
+        optim.init_step()
+        elbo = beer.evidence_lower_bound(datasize=N)
+        for X in (X1, X2):
+            elbo += beer.evidence_lower_bound(pl, X, datasize=N)
+        elbo.backward()
+        elbos.append(float(elbo))
+        optim.step()
+        want = g[f'it{it + 1}_trans']
+        got = pl.graph.trans_log_probs.numpy()
+        fin = np.isfinite(want)
+        assert np.array_equal(np.isfinite(got), fin)
+        np.testing.assert_allclose(got[fin], want[fin], rtol=2e-4, atol=2e-4)
+    np.testing.assert_allclose(elbos, g['elbos'], rtol=1e-5)
+    np.testing.assert_allclose(wu.posterior.params.concentrations.cpu().numpy(), g['u_dpost3'], rtol=2e-4)
+    for ns, tag in ((ns1, 'g1'), (ns2, 'g2')):
+        for got, pname in zip(get_ng(ns.means_precisions.posterior), ('mean', 'scale', 'shape', 'rates')):
+            want = g[f'{tag}_post3_' + pname]
+            np.testing.assert_allclose(got.reshape(want.shape), want, rtol=3e-4, atol=3e-4)
