@@ -221,6 +221,7 @@ struct FbArgs {
     double* utt_logz;
     int vec;  // 16-byte row copies are legal
     const float* lr_w;  // aligned left-to-right loop weights (hmm_fb_lr_kernel)
+    int lr_row;         // stride between the three weight arrays
     double* unit_counts;  // [K / SU] or NULL: sum_t xi_t(unit ends -> unit start) + gamma_0(start)
 };
 
@@ -1203,6 +1204,310 @@ static int launch_fb_lr(const FbArgs& a, int n_utts, cudaStream_t st) {
     return BEER_OK;
 }
 
+// ---------------------------------------------------------------------------
+// The same aligned left-to-right loop for MANY units (P > 128, e.g. 250 units x 4 states = the
+// 1000-state HMM of BASELINE configs[2]): W warps share one utterance, every lane owns ONE unit,
+// and the two warp reductions of a step (normaliser, junction) become one exchange through shared
+// memory + one block barrier (partials are published relative to the warp's own maximum and
+// recombined, so a single round suffices; slots are double-buffered, so one barrier per exchange).
+// Forward: 1 exchange per frame; backward: 2 (posterior normaliser, junction of the beta recursion).
+// ---------------------------------------------------------------------------
+template <int SU, int W>
+__global__ void __launch_bounds__(W * 32) hmm_fb_lrb_kernel(FbArgs a) {
+    constexpr int S = SU;
+    constexpr bool VEC = (S % 4 == 0);
+    constexpr int PF = 4;
+    constexpr int ROW = 32 * S;                 // one warp's slice of a row
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* ring_p = smem + (size_t)warp * (2 * PF * ROW);
+    float* ring_a = ring_p + PF * ROW;
+    float* xch = smem + (size_t)W * (2 * PF * ROW);     // [2][W][4] exchange slots
+    const int K = a.K;
+    const float p_scale = a.scale * kLog2e;
+    const int gl = warp * 32 + lane;            // unit owned by this lane
+    const int k0 = gl * S;                      // its first state
+    const bool own = k0 < K;
+    for (int i = lane; i < 2 * PF * ROW; i += 32) ring_p[i] = 0.f;
+    __syncwarp();
+
+    float w_self[S], w_in[S], w_jout, f_start[S], b_start[S];
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+        const int k = k0 + j;
+        w_self[j] = own ? __ldg(a.lr_w + k) : kNegInf;
+        w_in[j] = own ? __ldg(a.lr_w + a.lr_row + k) : kNegInf;
+        f_start[j] = (k < K) ? __ldg(a.fwd.start + k) : kNegInf;
+        b_start[j] = (k < K) ? __ldg(a.bwd.start + k) : kNegInf;
+    }
+    w_jout = own ? __ldg(a.lr_w + 2 * a.lr_row + k0 + S - 1) : kNegInf;
+
+    auto prefetch = [&](float* slot, const float* row) {
+        if (!own) return;
+        if constexpr (VEC) {
+#pragma unroll
+            for (int v = 0; v < S / 4; ++v) cp_async16(slot + lane * S + 4 * v, row + k0 + 4 * v);
+        } else {
+#pragma unroll
+            for (int j = 0; j < S; ++j)
+                if (k0 + j < K) cp_async4(slot + lane * S + j, row + k0 + j);
+        }
+    };
+    auto read_row = [&](const float* slot, float* out) {
+#pragma unroll
+        for (int j = 0; j < S; ++j) out[j] = slot[lane * S + j];
+    };
+    auto write_row = [&](float* row, const float* v, float mul) {
+        if (!own) return;
+        if constexpr (VEC) {
+#pragma unroll
+            for (int q = 0; q < S / 4; ++q)
+                reinterpret_cast<float4*>(row + k0)[q] =
+                    make_float4(mul * v[4 * q], mul * v[4 * q + 1], mul * v[4 * q + 2], mul * v[4 * q + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < S; ++j)
+                if (k0 + j < K) row[k0 + j] = mul * v[j];
+        }
+    };
+    // One exchange: every warp publishes (its max m, sum s of 2^(x - m), optional extra e scaled the
+    // same way); afterwards every thread holds the block maximum M, S = sum_w s_w 2^(m_w - M) and E.
+    int xn = 0;
+    auto exchange = [&](float m, float s, float e, float& M, float& Ssum, float& E) {
+        float* slot = xch + (xn & 1) * (W * 4);
+        ++xn;
+        if (lane == 0) {
+            slot[warp * 4] = m;
+            slot[warp * 4 + 1] = s;
+            slot[warp * 4 + 2] = e;
+        }
+        __syncthreads();
+        float mm[W];
+        M = kNegInf;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            mm[w] = slot[w * 4];
+            M = fmaxf(M, mm[w]);
+        }
+        const float Ms = (M == kNegInf) ? 0.f : M;
+        Ssum = 0.f;
+        E = 0.f;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            const float f = ex2(mm[w] - Ms);       // 2^(-inf) = 0 for warps without reachable states
+            Ssum = fmaf(slot[w * 4 + 1], f, Ssum);
+            E = fmaf(slot[w * 4 + 2], f, E);
+        }
+        M = Ms;
+    };
+
+    for (int u = blockIdx.x; u < a.n_utts; u += gridDim.x) {
+        const int64_t t0 = a.utt_off[u];
+        const int T = (int)(a.utt_off[u + 1] - t0);
+        if (T <= 0) {
+            if (threadIdx.x == 0) {
+                a.utt_exp_llh[u] = 0.0;
+                if (a.utt_logz) a.utt_logz[u] = 0.0;
+            }
+            continue;
+        }
+        const float* pl_u = a.pl + (size_t)t0 * a.ld;
+        float* la_u = a.la_ws + (size_t)t0 * a.Kw;
+        double logz2 = 0.0;
+
+        // ------------------------------ forward ------------------------------
+        for (int r = 0; r < PF; ++r) {
+            if (r < T) prefetch(ring_p + r * ROW, pl_u + (size_t)r * a.ld);
+            cp_async_commit();
+        }
+        float cur[S], jv = kNegInf;
+        for (int t = 0; t < T; ++t) {
+            cp_async_wait<PF - 1>();
+            float p[S];
+            read_row(ring_p + (t % PF) * ROW, p);
+            if (t + PF < T) prefetch(ring_p + (t % PF) * ROW, pl_u + (size_t)(t + PF) * a.ld);
+            cp_async_commit();
+            if (t == 0) {
+#pragma unroll
+                for (int j = 0; j < S; ++j) cur[j] = fmaf(p[j], p_scale, f_start[j]);
+            } else {
+                float v[S];
+#pragma unroll
+                for (int j = 0; j < S; ++j)
+                    v[j] = lse2(cur[j] + w_self[j], ((j == 0) ? jv : cur[j == 0 ? 0 : j - 1]) + w_in[j]);
+#pragma unroll
+                for (int j = 0; j < S; ++j) cur[j] = fmaf(p[j], p_scale, v[j]);
+            }
+            float ml = cur[0];
+#pragma unroll
+            for (int j = 1; j < S; ++j) ml = fmaxf(ml, cur[j]);
+            ml = warp_max(ml);
+            const float mls = (ml == kNegInf) ? 0.f : ml;
+            const float sl = warp_sum(ex2(cur[S - 1] + w_jout - mls));
+            float mx, js, unused;
+            exchange(ml, sl, 0.f, mx, js, unused);
+            jv = lg2(js);                         // junction of the NORMALISED values
+            logz2 += (double)mx;
+#pragma unroll
+            for (int j = 0; j < S; ++j) cur[j] -= mx;
+            write_row(la_u + (size_t)t * a.Kw, cur, 1.f);
+        }
+        cp_async_wait<0>();
+
+        if (a.utt_logz != nullptr) {
+            float m = kNegInf, v[S];
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                v[j] = cur[j] + b_start[j];
+                m = fmaxf(m, v[j]);
+            }
+            m = warp_max(m);
+            const float ms = (m == kNegInf) ? 0.f : m;
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < S; ++j) sum += ex2(v[j] - ms);
+            sum = warp_sum(sum);
+            float M, Ssum, unused;
+            exchange(m, sum, 0.f, M, Ssum, unused);
+            double rs = 0.0;
+            if (a.frame_ref != nullptr && warp == 0)
+                for (int t = lane; t < T; t += 32) rs += (double)a.frame_ref[t0 + t];
+            rs = warp_sum(rs);
+            if (threadIdx.x == 0)
+                a.utt_logz[u] = (logz2 + (double)M + (double)lg2(Ssum)) * (double)kLn2 + (double)a.scale * rs;
+        }
+
+        // ------------------------------ backward -----------------------------
+        __threadfence_block();
+        __syncthreads();         // every warp's la stores are visible to every warp's async copies
+        for (int r = 0; r < PF; ++r) {
+            const int t = T - 1 - r;
+            if (t >= 0) {
+                prefetch(ring_p + r * ROW, pl_u + (size_t)t * a.ld);
+                prefetch(ring_a + r * ROW, la_u + (size_t)t * a.Kw);
+            }
+            cp_async_commit();
+        }
+        float lb[S];
+        {
+            float m = kNegInf;
+#pragma unroll
+            for (int j = 0; j < S; ++j) m = fmaxf(m, b_start[j]);
+            m = warp_max(m);
+            float M, s0, s1;
+            exchange(m, 0.f, 0.f, M, s0, s1);
+#pragma unroll
+            for (int j = 0; j < S; ++j) lb[j] = b_start[j] - M;
+        }
+        float ell = 0.f;
+        double ell_d = 0.0;
+        for (int i = 0; i < T; ++i) {
+            const int t = T - 1 - i;
+            cp_async_wait<PF - 1>();
+            float p[S], la[S];
+            read_row(ring_p + (i % PF) * ROW, p);
+            read_row(ring_a + (i % PF) * ROW, la);
+#pragma unroll
+            for (int j = 0; j < S; ++j) p[j] *= p_scale;
+            if (t - PF >= 0) {
+                prefetch(ring_p + (i % PF) * ROW, pl_u + (size_t)(t - PF) * a.ld);
+                prefetch(ring_a + (i % PF) * ROW, la_u + (size_t)(t - PF) * a.Kw);
+            }
+            cp_async_commit();
+
+            // gamma_t: exchange (max, sum, sum of p * 2^(v - max))
+            float v[S], m = kNegInf;
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                v[j] = own ? la[j] + lb[j] : kNegInf;
+                m = fmaxf(m, v[j]);
+            }
+            m = warp_max(m);
+            const float mls = (m == kNegInf) ? 0.f : m;
+            float sl = 0.f, pe = 0.f;
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                v[j] = ex2(v[j] - mls);
+                sl += v[j];
+                pe = fmaf(p[j], v[j], pe);
+            }
+            sl = warp_sum(sl);
+            pe = warp_sum(pe);
+            float ms, sum, pes;
+            exchange(m, sl, pe, ms, sum, pes);
+            const float inv = (sum > 0.f) ? __fdividef(1.f, sum) : 0.f;
+            const float resc = ex2(mls - ms) * inv;            // this warp's values -> block normalisation
+#pragma unroll
+            for (int j = 0; j < S; ++j) v[j] *= resc;
+            if (threadIdx.x == 0) {
+                ell += pes * inv;
+                if ((i & 31) == 31) {
+                    ell_d += (double)ell;
+                    ell = 0.f;
+                }
+                if (a.frame_exp_llh != nullptr) {
+                    const float r = (a.frame_ref != nullptr) ? a.scale * a.frame_ref[t0 + t] : 0.f;
+                    a.frame_exp_llh[t0 + t] = pes * inv * kLn2 + r;
+                }
+            }
+            if (a.state_post != nullptr) write_row(a.state_post + (size_t)(t0 + t) * K, v, 1.f);
+            if (a.pdf_post != nullptr) write_row(a.pdf_post + (size_t)(t0 + t) * a.ld_post, v, a.scale);
+            if (t == 0) break;
+            // beta_{t-1}: exchange (max of delta, junction partial over the unit starts)
+            float delta[S];
+            float md = kNegInf;
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                delta[j] = p[j] + lb[j];
+                md = fmaxf(md, delta[j]);
+            }
+            md = warp_max(md);
+            const float mds = (md == kNegInf) ? 0.f : md;
+            const float sj = warp_sum(ex2(delta[0] + w_in[0] - mds));
+            float Md, Sj, unused;
+            exchange(md, sj, 0.f, Md, Sj, unused);
+            const float jb = Md + lg2(Sj);
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                const bool end = (j == S - 1);
+                const float nxt = end ? jb + w_jout : delta[end ? j : j + 1] + w_in[end ? j : j + 1];
+                lb[j] = lse2(delta[j] + w_self[j], nxt) - Md;      // normalised by max(delta): <= 1
+            }
+        }
+        cp_async_wait<0>();
+        if (threadIdx.x == 0) {
+            ell_d += (double)ell;
+            double rs = 0.0;
+            a.utt_exp_llh[u] = ell_d * (double)kLn2;
+            (void)rs;
+        }
+        if (warp == 0) {
+            double rs = 0.0;
+            if (a.frame_ref != nullptr)
+                for (int t = lane; t < T; t += 32) rs += (double)a.frame_ref[t0 + t];
+            rs = warp_sum(rs);
+            if (lane == 0) a.utt_exp_llh[u] += (double)a.scale * rs;
+        }
+        __syncthreads();
+    }
+}
+
+template <int SU, int W>
+static int launch_fb_lrb(const FbArgs& a, int n_utts, cudaStream_t st) {
+    constexpr int PF = 4;
+    size_t smem = sizeof(float) * ((size_t)W * (2 * PF * 32 * SU) + 2 * W * 4);
+    static bool attr_set = false;
+    if (!attr_set) {
+        BEER_CUDA_TRY(cudaFuncSetAttribute(hmm_fb_lrb_kernel<SU, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem));
+        attr_set = true;
+    }
+    int blocks = n_utts < kNumSMs * 8 ? n_utts : kNumSMs * 8;
+    hmm_fb_lrb_kernel<SU, W><<<blocks, W * 32, smem, st>>>(a);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
 // ------------------------------- Viterbi -----------------------------------
 struct VitArgs {
     ScanLists vit;
@@ -1496,7 +1801,7 @@ int beer_graph_plan_create(const float* init_log, const float* final_log, const 
         }
         const int P = ok ? K / su : 0;
         int u = (P + 31) / 32;
-        u = (u <= 1) ? 1 : (u <= 2 ? 2 : (u <= 4 ? 4 : 0));
+        u = (u <= 1) ? 1 : (u <= 2 ? 2 : (u <= 4 ? 4 : (u <= 8 ? 8 : 0)));   // 8: block kernel, 8 warps x 1 unit per lane
         if (ok && u > 0 && (su == 3 || su == 4)) {
             lr_su = su; lr_u = u;
             const int row = 32 * su * u;
@@ -1603,6 +1908,7 @@ int beer_hmm_forward_backward_units(const beer_graph_plan* plan, const float* pd
     a.vec = (plan->map_identity && plan->S % 4 == 0 && plan->K % 4 == 0 && ld_pdf % 4 == 0 &&
              ((uintptr_t)pdf_llh & 15) == 0) ? 1 : 0;
     a.lr_w = plan->lr_w;
+    a.lr_row = 32 * plan->lr_su * plan->lr_u;
     a.unit_counts = unit_counts;
     if (unit_counts != nullptr && !(plan->lr_su && plan->map_identity)) return BEER_ERR_UNSUPPORTED;
     const bool post_ok = (pdf_post == nullptr || (ld_post % 4 == 0 && ((uintptr_t)pdf_post & 15) == 0)) &&
@@ -1613,6 +1919,10 @@ int beer_hmm_forward_backward_units(const beer_graph_plan* plan, const float* pd
     if (plan->lr_su && plan->map_identity && (force == nullptr || force[0] == 'l') &&
         (!lr_vec || (a.vec && post_ok))) {
         const int u = plan->lr_u;
+        if (u == 8 && unit_counts == nullptr) {
+            if (plan->lr_su == 4) return launch_fb_lrb<4, 8>(a, n_utts, st);
+            if (plan->lr_su == 3) return launch_fb_lrb<3, 8>(a, n_utts, st);
+        }
         if (plan->lr_su == 4) {
             if (u == 1) return launch_fb_lr<4, 1>(a, n_utts, st);
             if (u == 2) return launch_fb_lr<4, 2>(a, n_utts, st);

@@ -296,3 +296,38 @@ def test_ragged_batch_equals_single(ops):
             continue
         assert np.abs(gam[off[i]:off[i + 1]] - want['gamma']).max() <= 1e-5
         np.testing.assert_allclose(r['utt_exp_llh'][i].item(), want['exp_llh'].sum(), rtol=1e-6)
+
+
+@pytest.mark.parametrize('P,S', [(130, 4), (250, 4), (140, 3)])
+def test_forward_backward_many_units_block_kernel(ops, P, S, monkeypatch):
+    """Loops with more than 128 units (BASELINE configs[2]: 250 units x 4 states) run W warps per utterance
+    with one shared-memory exchange per reduction; same posteriors / evidence as the generic kernel and as
+    the fp64 oracle on a ragged batch."""
+    from beer_b200 import synthetic
+    cg, _, _ = synthetic.phone_loop_graph(P, S)
+    K = P * S
+    rng = np.random.default_rng(P)
+    lens = [37, 120, 1, 64]
+    off = np.concatenate([[0], np.cumsum(lens)])
+    llh = (rng.standard_normal((off[-1], K)) * 4).astype(np.float32)
+    llh -= llh.max(axis=1, keepdims=True)
+    gr = (cg.init_log_probs.numpy(), cg.final_log_probs.numpy(), cg.trans_log_probs.numpy(), np.arange(K))
+    plan = ops.GraphPlan(*gr)
+    assert plan.info['junctions'] == 1
+    outs = {}
+    for path in ('best', 'generic'):
+        if path == 'generic':
+            monkeypatch.setenv('BEER_B200_SCAN', 'generic')
+        r = ops.hmm_forward_backward(plan, dev(llh), None, dev(off, torch.int64), scale=0.8, want_state_post=True,
+                                     want_frame_llh=True, want_logz=True)
+        outs[path] = {k: v.double().cpu().numpy() for k, v in r.items() if k != 'workspace' and v is not None}
+    for k in ('state_post', 'pdf_post'):
+        assert np.abs(outs['best'][k] - outs['generic'][k]).max() <= 1e-5, k
+    for k in ('utt_exp_llh', 'utt_logz', 'frame_exp_llh'):
+        np.testing.assert_allclose(outs['best'][k], outs['generic'][k], rtol=2e-6, atol=2e-4, err_msg=k)
+    # fp64 oracle on the longest utterance
+    g64 = tuple(np.asarray(x, dtype=np.float64) for x in gr[:3])
+    u = 1
+    with np.errstate(all='ignore'):
+        gamma, _ = O.posteriors(0.8 * llh[off[u]:off[u + 1]].astype(np.float64), *g64)
+    assert np.abs(outs['best']['state_post'][off[u]:off[u + 1]] - gamma).max() <= 1e-5
