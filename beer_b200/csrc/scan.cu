@@ -995,12 +995,20 @@ __global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_lr_kernel(FbArgs a) {
             cp_async_commit();
         }
         float cur[S];
+        const bool want_logz = a.utt_logz != nullptr;
+        float lz = 0.f;                                   // normalisers, folded into fp64 every 16 frames
+        int slot = 0;                                     // ring slot of frame t
+        const float* pf_row = pl_u + (size_t)PF * a.ld;   // row to prefetch next
+        float* la_row = la_u;
         for (int t = 0; t < T; ++t) {
             cp_async_wait<PF - 1>();
             float p[S];
-            read_row(ring_p + (t % PF) * ROW, p);
-            if (t + PF < T) prefetch(ring_p + (t % PF) * ROW, pl_u + (size_t)(t + PF) * a.ld);
+            float* ring_slot = ring_p + slot * ROW;
+            read_row(ring_slot, p);
+            if (t + PF < T) prefetch(ring_slot, pf_row);
             cp_async_commit();
+            pf_row += a.ld;
+            slot = (slot + 1 == PF) ? 0 : slot + 1;
             if (t == 0) {
 #pragma unroll
                 for (int j = 0; j < S; ++j) cur[j] = fmaf(p[j], p_scale, f_start[j]);
@@ -1021,12 +1029,20 @@ __global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_lr_kernel(FbArgs a) {
             for (int j = 1; j < S; ++j) mx = fmaxf(mx, cur[j]);
             mx = warp_max(mx);
             const float mxs = (mx == kNegInf) ? 0.f : mx;
-            logz2 += (double)mxs;
+            if (want_logz) {
+                lz += mxs;
+                if ((t & 15) == 15) {
+                    logz2 += (double)lz;
+                    lz = 0.f;
+                }
+            }
 #pragma unroll
             for (int j = 0; j < S; ++j) cur[j] -= mxs;
-            write_row(la_u + (size_t)t * a.Kw, cur, 1.f);
+            write_row(la_row, cur, 1.f);
+            la_row += a.Kw;
         }
         cp_async_wait<0>();
+        logz2 += (double)lz;
 
         if (a.utt_logz != nullptr) {
             float m = kNegInf, v[S];
@@ -1076,19 +1092,23 @@ __global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_lr_kernel(FbArgs a) {
         float cnt[U], dstart[U], mbs_prev = 0.f;   // unit counts, delta_{t+1} of the unit starts
 #pragma unroll
         for (int q = 0; q < U; ++q) cnt[q] = dstart[q] = 0.f;
+        slot = 0;
+        const float* pfb_p = pl_u + (ptrdiff_t)(T - 1 - PF) * (ptrdiff_t)a.ld;      // rows to prefetch next (t - PF)
+        const float* pfb_a = la_u + (ptrdiff_t)(T - 1 - PF) * (ptrdiff_t)a.Kw;
         for (int i = 0; i < T; ++i) {
             const int t = T - 1 - i;
             cp_async_wait<PF - 1>();
-            float p[S], la[S];
-            read_row(ring_p + (i % PF) * ROW, p);
-            read_row(ring_a + (i % PF) * ROW, la);
-#pragma unroll
-            for (int j = 0; j < S; ++j) p[j] *= p_scale;
+            float p[S], la[S];     // p: RAW llh (the scale is folded into the FMAs below)
+            read_row(ring_p + slot * ROW, p);
+            read_row(ring_a + slot * ROW, la);
             if (t - PF >= 0) {
-                prefetch(ring_p + (i % PF) * ROW, pl_u + (size_t)(t - PF) * a.ld);
-                prefetch(ring_a + (i % PF) * ROW, la_u + (size_t)(t - PF) * a.Kw);
+                prefetch(ring_p + slot * ROW, pfb_p);
+                prefetch(ring_a + slot * ROW, pfb_a);
             }
             cp_async_commit();
+            pfb_p -= a.ld;
+            pfb_a -= a.Kw;
+            slot = (slot + 1 == PF) ? 0 : slot + 1;
 
             float v[S], m = kNegInf;
 #pragma unroll
@@ -1106,11 +1126,11 @@ __global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_lr_kernel(FbArgs a) {
             }
             sum = warp_sum(sum);
             const float inv = (sum > 0.f) ? __fdividef(1.f, sum) : 0.f;
-            float fe = 0.f;
+            float fe = 0.f;      // sum_k llh_k gamma_k in raw-llh units (x p_scale at the end); llh is finite
 #pragma unroll
             for (int j = 0; j < S; ++j) {
                 v[j] *= inv;
-                if (v[j] > 0.f) fe = fmaf(p[j], v[j], fe);
+                fe = fmaf(p[j], v[j], fe);
             }
             ell += fe;
             if ((i & 31) == 31) {
@@ -1121,7 +1141,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_lr_kernel(FbArgs a) {
                 const float f = warp_sum(fe);
                 if (lane == 0) {
                     const float r = (a.frame_ref != nullptr) ? a.scale * a.frame_ref[t0 + t] : 0.f;
-                    a.frame_exp_llh[t0 + t] = f * kLn2 + r;
+                    a.frame_exp_llh[t0 + t] = f * p_scale * kLn2 + r;
                 }
             }
             if (units && sum > 0.f) {
@@ -1146,7 +1166,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_lr_kernel(FbArgs a) {
             // beta_{t-1}: delta_j = p_tj + lb_tj, transposed recursion on registers
             float delta[S], starts[U];
 #pragma unroll
-            for (int j = 0; j < S; ++j) delta[j] = p[j] + lb[j];
+            for (int j = 0; j < S; ++j) delta[j] = fmaf(p[j], p_scale, lb[j]);
 #pragma unroll
             for (int q = 0; q < U; ++q) starts[q] = delta[q * SU] + w_in[q * SU];
             const float jb = warp_lse(starts);
@@ -1180,7 +1200,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_lr_kernel(FbArgs a) {
         if (a.frame_ref != nullptr)
             for (int t = lane; t < T; t += 32) rs += (double)a.frame_ref[t0 + t];
         rs = warp_sum(rs);
-        if (lane == 0) a.utt_exp_llh[u] = ell_d * (double)kLn2 + (double)a.scale * rs;
+        if (lane == 0) a.utt_exp_llh[u] = ell_d * (double)p_scale * (double)kLn2 + (double)a.scale * rs;
         __syncwarp();
     }
 }

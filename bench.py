@@ -37,11 +37,31 @@ def workload_name(cfg, c):
 
 
 def measured_peaks():
+    """HBM peak in GB/s: the driver-written MEASURED_PEAKS.json when present (key `hbm_gbs`; any numeric key
+    naming hbm is accepted), else the fallback of B200_PROFILING.md."""
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
-        with open(path) as f:
-            p = json.load(f)
-        return float(p['hbm_gbs']), 'measured'
+        try:
+            with open(path) as f:
+                p = json.load(f)
+
+            def find(d):
+                if isinstance(d, dict):
+                    if isinstance(d.get('hbm_gbs'), (int, float)):
+                        return float(d['hbm_gbs'])
+                    for k, v in d.items():
+                        if 'hbm' in str(k).lower() and isinstance(v, (int, float)):
+                            return float(v) * (1000.0 if float(v) < 50 else 1.0)     # TB/s -> GB/s
+                    for v in d.values():
+                        r = find(v)
+                        if r:
+                            return r
+                return None
+            v = find(p)
+            if v:
+                return v, 'measured'
+        except (OSError, ValueError):
+            pass
     return 6650.0, 'fallback'
 
 
