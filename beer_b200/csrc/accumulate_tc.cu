@@ -440,7 +440,7 @@ struct RawCfg {
     static constexpr int BU = ((KF / 4) * D + RAW_PRODUCERS - 1) / RAW_PRODUCERS;
     static constexpr int NCH = NB / 16, MYCH = (NCH + 3) / 4;   // four warps share a TMEM lane quarter
     static constexpr uint32_t TMEM_COLS = 2 * NB <= 64 ? 64 : (2 * NB <= 128 ? 128 : (2 * NB <= 256 ? 256 : 512));
-    static constexpr int DR = 64 / KF;
+    static constexpr int DR = 128 / KF;    // stages per drain: 48 truncating TMEM accumulations (~3e-7 low)
     static constexpr size_t FIXED = (size_t)RAW_OPS * STAGE_FLOATS * 4 + sizeof(RawBarriers) + 1024;
     static size_t raw_stage_bytes(int M) { return (size_t)KF * (M + D) * 4; }
     static int raw_stages(int M) {
@@ -499,15 +499,20 @@ __global__ void __launch_bounds__(RAW_THREADS, 1) accumulate_tc_raw_kernel(Args 
     if (warp == RAW_PRODUCERS / 32 + 1) {
         // ------------------------------- loader -----------------------------------
         if (lane == 0) {
+            int rs = 0;
+            uint32_t rph = 0;                      // ring position / pass parity (no runtime division)
             for (int it = 0; it < n_tiles; ++it) {
-                const int rs = it % RS;
                 const int64_t t0 = f_begin + (int64_t)it * KF;
                 const uint32_t rows = (uint32_t)min((int64_t)KF, f_end - t0);
-                mbar_wait(&bars->raw_empty[rs], ((it / RS) & 1) ^ 1);
+                mbar_wait(&bars->raw_empty[rs], rph ^ 1);
                 float* dst = ring + (size_t)rs * raw_floats;
                 mbar_arrive_expect_tx(&bars->raw_full[rs], rows * (uint32_t)(M + D) * 4u);
                 bulk_g2s(dst, a.pdf_post + (size_t)t0 * M, rows * (uint32_t)M * 4u, &bars->raw_full[rs]);
                 bulk_g2s(dst + KF * M, a.X + (size_t)t0 * D, rows * (uint32_t)D * 4u, &bars->raw_full[rs]);
+                if (++rs == RS) {
+                    rs = 0;
+                    rph ^= 1;
+                }
             }
         }
     } else if (warp == RAW_PRODUCERS / 32) {
@@ -589,8 +594,10 @@ __global__ void __launch_bounds__(RAW_THREADS, 1) accumulate_tc_raw_kernel(Args 
             mbar_arrive(&bars->tempty[buf]);
         };
 
+        int rs = 0;
+        uint32_t rph = 0;
         for (int it = 0; it < n_tiles; ++it) {
-            const int st = it % STAGES, rs = it % RS;
+            const int st = it % STAGES;
             const int rows = (int)min((int64_t)KF, f_end - (f_begin + (int64_t)it * KF));
             const float* rp = ring + (size_t)rs * raw_floats;     // posteriors [KF][M]
             const float* rx = rp + KF * M;                         // features   [KF][D]
@@ -598,7 +605,7 @@ __global__ void __launch_bounds__(RAW_THREADS, 1) accumulate_tc_raw_kernel(Args 
             float* A_lo = A_hi + C::A_FLOATS;
             float* B_hi = A_lo + C::A_FLOATS;
             float* B_lo = B_hi + C::B_FLOATS;
-            mbar_wait(&bars->raw_full[rs], (it / RS) & 1);
+            mbar_wait(&bars->raw_full[rs], rph);
             mbar_wait(&bars->empty[st], ((it / STAGES) & 1) ^ 1);
             if (a_active) {
 #pragma unroll
@@ -641,10 +648,19 @@ __global__ void __launch_bounds__(RAW_THREADS, 1) accumulate_tc_raw_kernel(Args 
             fence_proxy_async();
             mbar_arrive(&bars->full[st]);
             mbar_arrive(&bars->raw_empty[rs]);
-            if (it % C::DR == 0 && it > 0) drain(it / C::DR - 1);
+            if (++rs == RS) {
+                rs = 0;
+                rph ^= 1;
+            }
+            // drain the previous group one stage late: its last MMAs have certainly retired by then
+            if (it % C::DR == 1 && it > C::DR) drain(it / C::DR - 1);
         }
         if (n_tiles > 0) {
-            drain((n_tiles - 1) / C::DR);
+            const int last_g = (n_tiles - 1) / C::DR;
+            // groups not drained inside the loop: the last one, and the one before it when the loop ended
+            // before that group's (late) drain slot
+            if (last_g >= 1 && (n_tiles - 1) < last_g * C::DR + 1) drain(last_g - 1);
+            drain(last_g);
             const int g = q * 32 + lane;
             if (g < M) {
                 const int Q = 2 * D + 2;

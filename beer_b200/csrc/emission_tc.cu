@@ -43,6 +43,7 @@ struct Args {
     const float* bias;   // [n_chunks * NB], zero padded
     const float* ref;    // [D + 1]
     int M, C, Kp, NB, n_chunks, stages;
+    int logC;            // log2(C)
     int staged;          // llh tile staged in shared memory and written with one bulk store
     float* pdf_llh;
     int64_t ld;
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(THREADS, 1) emission_tc_kernel(Args a) {
                             }
                         }
                     }
-                    const int k0 = g / C;
+                    const int k0 = g >> a.logC;          // C is a power of two
                     // staged: the tile [FR][Kp] is contiguous in HBM, rows go to shared memory first
                     float* dst = a.staged ? s_out + (size_t)r * a.Kp + k0 : a.pdf_llh + (size_t)t * a.ld + k0;
                     if (no == 16 && k0 + 16 <= a.Kp && ((a.staged ? a.Kp : a.ld) & 3) == 0) {
@@ -446,6 +447,8 @@ int beer_emission_llh_tc(const float* X, int64_t N, int D, const float* image, c
     a.bias = image + (size_t)g.n_chunks * 2 * g.NB * 2 * D;
     a.ref = ref; a.M = M; a.C = C; a.Kp = M / C; a.NB = g.NB; a.n_chunks = g.n_chunks; a.stages = g.stages;
     a.pdf_llh = pdf_llh; a.ld = ld_pdf; a.comp_llh = comp_llh; a.frame_ref = frame_ref;
+    a.logC = 0;
+    while ((1 << a.logC) < C) ++a.logC;
     // stage + bulk-store the llh tile when its rows are contiguous in HBM and it fits next to the operands
     a.staged = (g.n_chunks == 1 && ld_pdf == a.Kp && (a.Kp & 3) == 0 && ((uintptr_t)pdf_llh & 15) == 0 &&
                 tc::smem_bytes(D, g, a.Kp) <= 227 * 1024) ? 1 : 0;
