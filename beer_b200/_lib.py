@@ -58,6 +58,8 @@ SIGNATURES = {
     'beer_dirichlet_log_norm': (C.c_int, [c_ptr, C.c_int, C.c_int, c_ptr, c_ptr]),
     'beer_dirichlet_from_natural': (C.c_int, [c_ptr, C.c_int, C.c_int, c_ptr, c_ptr]),
     'beer_segment_logsumexp': (C.c_int, [c_ptr, C.c_int64, C.c_int, c_ptr, C.c_int, c_ptr, C.c_int64, c_ptr]),
+    'beer_fbank': (C.c_int, [c_ptr, C.c_int64, C.c_int, C.c_int, C.c_float, c_ptr, c_ptr, C.c_int, C.c_int, c_ptr, c_ptr]),
+    'beer_add_deltas': (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
     'beer_path_posteriors': (C.c_int, [c_ptr, C.c_int64, c_ptr, C.c_float, c_ptr, C.c_int64, c_ptr, c_ptr,
                                        C.c_int64, C.c_int, c_ptr, c_ptr]),
 }

@@ -392,3 +392,29 @@ def path_posteriors(path, n_pdfs, pdf_map=None, scale=1.0, pdf_llh=None, frame_r
                                         _p(frame_ref, f32, True), _p(post, f32, True), n_pdfs, n_pdfs,
                                         _p(frame, f32, True), _stream()), 'beer_path_posteriors')
     return post, frame
+
+
+# ---------------------------------------------------------------------------
+# fbank front-end
+# ---------------------------------------------------------------------------
+
+def fbank(signal, window, filters_t, frame_shift, preemph, fft_len):
+    """signal [L] fp32 -> log(1 + mel energies) [n_frames, n_filters]."""
+    lib = require_cuda()
+    L, flen = signal.numel(), window.numel()
+    n_filters = filters_t.shape[1]
+    nframes = max(0, (L - flen) // frame_shift + 1) if L >= flen else 0
+    out = torch.empty(nframes, n_filters, device=signal.device, dtype=f32)
+    if nframes == 0:
+        return out
+    _lib.check(lib.beer_fbank(_p(signal, f32), L, flen, int(frame_shift), float(preemph), _p(window, f32),
+                              _p(filters_t, f32), int(fft_len), n_filters, _p(out), _stream()), 'beer_fbank')
+    return out
+
+
+def add_deltas(fea, wlen):
+    lib = require_cuda()
+    T, F = fea.shape
+    out = torch.empty_like(fea)
+    _lib.check(lib.beer_add_deltas(_p(fea, f32), T, F, int(wlen), _p(out), _stream()), 'beer_add_deltas')
+    return out

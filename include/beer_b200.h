@@ -252,6 +252,21 @@ BEER_API int beer_path_posteriors(const int32_t* path, int64_t N, const int32_t*
                          const float* pdf_llh, int64_t ld_pdf, const float* frame_ref, float* pdf_post,
                          int64_t ld_post, int Kp, float* frame_exp_llh, void* stream);
 
+/* ------------------------------------------------------------------------
+ * fbank front-end (beer/features.py; not on the timed VB path)
+ * ---------------------------------------------------------------------- */
+
+/* log(1 + mel filterbank energies of |rFFT| of the pre-emphasised, windowed frames).  Replaces
+ * beer.features.fbank (beer/features.py:145-204).
+ *   signal [n_samples] fp32; window [frame_len]; filters_t [fft_len/2, n_filters] (the transposed matrix of
+ *   create_fbank, features.py:47-79); fft_len in {256, 512, 1024};
+ *   out [(n_samples - frame_len) / frame_shift + 1, n_filters]. */
+BEER_API int beer_fbank(const float* signal, int64_t n_samples, int frame_len, int frame_shift, float preemph,
+               const float* window, const float* filters_t, int fft_len, int n_filters, float* out, void* stream);
+/* One order of the delta regression filter with replicated edges (beer/features.py:82-100):
+ * out[t] = sum_{k=1..wlen} k (fea[t+k] - fea[t-k]) / (2 sum k^2). */
+BEER_API int beer_add_deltas(const float* fea, int n_frames, int dim, int wlen, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

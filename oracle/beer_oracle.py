@@ -586,3 +586,71 @@ def sample_utterances(rng, graph, means, n_utts, n_frames, noise=1.0):
         utts.append((means[pdf] + noise * rng.standard_normal((T, means.shape[1])))
                     .astype(np.float32))
     return utts
+
+
+# --------------------------------------------------------------------------
+# fbank front-end (beer/features.py) -- "next" row of SURVEY section 8(f)
+# --------------------------------------------------------------------------
+
+def hz2mel(freq_hz):
+    """features.py:9-11."""
+    return 1127 * np.log(1 + freq_hz / 700.0)
+
+
+def mel2hz(mel):
+    """features.py:14-16."""
+    return 700.0 * (np.exp(mel / 1127.0) - 1)
+
+
+def _triangle(center, start, end, freqs):
+    """Triangular filter sampled on the FFT bins (features.py:30-43): both slopes are linspaces
+    between the first and the last bin inside [start, center] resp. [center, end]."""
+    out = np.zeros(len(freqs))
+    up = (freqs >= start) & (freqs <= center)
+    if up.any():
+        f = freqs[up]
+        out[up] = np.linspace((f[0] - start) / (center - start), (f[-1] - start) / (center - start), len(f))
+    down = (freqs >= center) & (freqs <= end)
+    if down.any():
+        f = freqs[down]
+        out[down] = np.linspace((end - f[0]) / (end - center), (end - f[-1]) / (end - center), len(f))
+    return out
+
+
+def create_fbank(nfilters, fft_len=512, srate=16000, lowfreq=0, highfreq=None):
+    """Mel filterbank with the filter centres aligned to FFT bins (features.py:47-79)."""
+    highfreq = highfreq or srate / 2
+    centers = np.linspace(hz2mel(lowfreq), hz2mel(highfreq), nfilters + 2)
+    centers = np.floor(fft_len * mel2hz(centers) / srate)
+    bins = np.arange(0, fft_len // 2)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        return np.stack([_triangle(centers[i], centers[i - 1], centers[i + 1], bins)
+                         for i in range(1, nfilters + 1)])
+
+
+def fbank(signal, flen=0.025, frate=0.01, hifreq=8000, lowfreq=20, nfilters=26, preemph=0.97, srate=16000):
+    """log(1 + mel filterbank energies of |rFFT| of the pre-emphasised, Hamming-windowed frames)
+    (features.py:145-204; pre-emphasis on the whole signal in fp32, first sample against itself)."""
+    frate_samp, flen_samp = int(srate * frate), int(srate * flen)
+    nframes = (len(signal) - flen_samp) // frate_samp + 1
+    s_t = np.array(signal, dtype=np.float32)
+    s_t -= np.float32(preemph) * np.r_[s_t[0], s_t[:-1]]
+    idx = np.arange(nframes)[:, None] * frate_samp + np.arange(flen_samp)[None, :]
+    frames = s_t[idx] * np.hamming(flen_samp)[None, :]
+    fft_len = int(2 ** np.floor(np.log2(flen_samp) + 1))
+    magspec = np.abs(np.fft.rfft(frames, n=fft_len, axis=-1)[:, :-1])
+    filters = create_fbank(nfilters, fft_len, srate=srate, lowfreq=lowfreq, highfreq=hifreq)
+    return np.log(magspec @ filters.T + 1)
+
+
+def add_deltas(fea, winlens=(2, 2)):
+    """Append delta / delta-delta features: regression filter over +-wlen frames with the edges
+    replicated (features.py:82-100)."""
+    out = [fea]
+    for wlen in winlens:
+        k = np.arange(-wlen, wlen + 1)
+        coef = k / (2.0 * (k @ k))
+        pad = np.r_[fea[[0]].repeat(wlen, 0), fea, fea[[-1]].repeat(wlen, 0)]
+        fea = sum(coef[i] * pad[i:i + len(fea)] for i in range(2 * wlen + 1))
+        out.append(fea)
+    return np.hstack(out)

@@ -371,7 +371,27 @@ def gold_graph_compile():
     save('graph_compile', **graph_arrays(cg, 'pl_'), **graph_arrays(ag, 'ali_'), **graph_arrays(ec, 'ex_'))
 
 
+def gold_fbank():
+    """beer/features.py: fbank (145-204), create_fbank (47-79), add_deltas (82-100) on a seeded synthetic signal (the reference module needs `np.float`, removed in NumPy 2)."""
+    if not hasattr(np, 'float'):
+        np.float = float
+    from beer import features as F
+    rng = np.random.default_rng(21)
+    n = 16000 + 123
+    t = np.arange(n) / 16000.
+    sig = (3000 * np.sin(2 * np.pi * 440 * t) + 1500 * np.sin(2 * np.pi * 2500 * t + 1.)
+           + 800 * rng.standard_normal(n)) * (0.3 + 0.7 * np.abs(np.sin(2 * np.pi * 1.5 * t)))
+    sig = np.round(sig).astype(np.int16)
+    fb40 = F.fbank(sig, nfilters=40)
+    fb26 = F.fbank(sig)
+    save('fbank', signal=sig, fbank40=fb40, fbank26=fb26, filters40=F.create_fbank(40, 512, lowfreq=20, highfreq=8000),
+         filters26=F.create_fbank(26, 512, lowfreq=20, highfreq=8000), deltas40=F.add_deltas(fb40))
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 2 and sys.argv[2] == 'fbank':
+        gold_fbank()
+        sys.exit(0)
     gold_dists()
     gold_gmm_cfg1()
     hmm_case('hmm_small', n_units=3, n_states=4, D=5, T=60, seed=3, scale=1.0)
@@ -380,3 +400,4 @@ if __name__ == '__main__':
     gold_phoneloop_mixtureset()
     gold_dense_ergodic()
     gold_graph_compile()
+    gold_fbank()

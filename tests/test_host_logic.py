@@ -166,3 +166,10 @@ def test_two_rank_reduction_equals_single_process(tmp_path):
     np.testing.assert_allclose(float(got['elbo']), want_elbo, rtol=1e-12)
     np.testing.assert_allclose(float(got['scale']), 1.0)
     assert got['flat'][-3] == sum(len(u) for u in utts) and got['flat'][-2] == len(utts)
+
+
+def test_filterbank_matrix_matches_reference():
+    from beer_b200 import features as F
+    g = load_golden('fbank')
+    for nf in (40, 26):
+        np.testing.assert_allclose(F.create_fbank(nf, 512, lowfreq=20, highfreq=8000), g[f'filters{nf}'], atol=1e-15)

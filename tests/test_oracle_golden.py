@@ -213,3 +213,12 @@ def test_phoneloop_mixtureset():
     np.testing.assert_allclose(upost, g['u_dpost3'], rtol=1e-8)
     np.testing.assert_allclose(posts[0][0], g['g1_post3_mean'], rtol=1e-7, atol=1e-9)
     np.testing.assert_allclose(dposts[1], g['g2_dpost3'], rtol=1e-8)
+
+
+def test_fbank_front_end():
+    """beer/features.py restated (fbank, create_fbank, add_deltas) against the live-reference golden."""
+    g = load_golden('fbank')
+    for nf in (40, 26):
+        np.testing.assert_allclose(O.create_fbank(nf, 512, lowfreq=20, highfreq=8000), g[f'filters{nf}'], atol=1e-15)
+        np.testing.assert_allclose(O.fbank(g['signal'], nfilters=nf), g[f'fbank{nf}'], rtol=1e-12)
+    np.testing.assert_allclose(O.add_deltas(g['fbank40']), g['deltas40'], atol=1e-12)
