@@ -80,6 +80,41 @@ __global__ void emission_ref_kernel(const float* __restrict__ mean, const float*
     }
 }
 
+// Same reference for many Gaussians (the single block above takes 2.4 ms at M = 8000): per-block partial
+// sums in a fixed order into a scratch area, then one block adds the partials in a fixed order, so the
+// result does not depend on scheduling.  part [n_blocks][D + 1] (fp64).
+__global__ void emission_ref_partial_kernel(const float* __restrict__ mean, const float* __restrict__ scale,
+                                            const float* __restrict__ shape, const float* __restrict__ rates,
+                                            const float* __restrict__ logw, int M, int D, double* __restrict__ part) {
+    __shared__ double s_bias[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    const int per = (M + gridDim.x - 1) / gridDim.x, j0 = blockIdx.x * per, j1 = min(M, j0 + per);
+    double* out = part + (size_t)blockIdx.x * (D + 1);
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        double acc = 0.0;
+        for (int j = j0; j < j1; ++j) acc += (double)shape[j] / (double)rates[(size_t)j * D + d];
+        out[d] = acc;
+    }
+    double b = 0.0;
+    for (int j = j0 + warp; j < j1; j += nwarp) b += ng_bias_row(mean, scale, shape, rates, logw, j, D, lane);
+    if (lane == 0) s_bias[warp] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < nwarp; ++w) t += s_bias[w];
+        out[D] = t;
+    }
+}
+
+__global__ void emission_ref_finish_kernel(const double* __restrict__ part, int n_blocks, int M, int D,
+                                           float* __restrict__ ref) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d > D) return;
+    double t = 0.0;
+    for (int b = 0; b < n_blocks; ++b) t += part[(size_t)b * (D + 1) + d];
+    ref[d] = (float)(t / M);
+}
+
 __global__ void emission_weights_kernel(const float* __restrict__ mean, const float* __restrict__ scale,
                                         const float* __restrict__ shape, const float* __restrict__ rates,
                                         const float* __restrict__ logw, int M, int D,
@@ -404,8 +439,19 @@ int beer_emission_prepare(const float* mean, const float* scale, const float* sh
                           const float* logw, int M, int D, float* W, float* bias, float* ref, void* stream) {
     if (M <= 0 || D <= 0) return BEER_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    emission_ref_kernel<<<1, 1024, 0, st>>>(mean, scale, shape, rates, logw, M, D, ref);
-    BEER_LAUNCH_CHECK();
+    // many Gaussians: two-stage reduction with W (written only after ref is final) as fp64 scratch
+    const int n_blocks = 64;
+    if (M >= 1024 && (size_t)M * 2 * D * sizeof(float) >= (size_t)n_blocks * (D + 1) * sizeof(double) &&
+        ((uintptr_t)W & 7) == 0) {
+        double* part = reinterpret_cast<double*>(W);
+        emission_ref_partial_kernel<<<n_blocks, 256, 0, st>>>(mean, scale, shape, rates, logw, M, D, part);
+        BEER_LAUNCH_CHECK();
+        emission_ref_finish_kernel<<<(D + 1 + 127) / 128, 128, 0, st>>>(part, n_blocks, M, D, ref);
+        BEER_LAUNCH_CHECK();
+    } else {
+        emission_ref_kernel<<<1, 1024, 0, st>>>(mean, scale, shape, rates, logw, M, D, ref);
+        BEER_LAUNCH_CHECK();
+    }
     int threads = 128, blocks = (M * 32 + threads - 1) / threads;
     emission_weights_kernel<<<blocks, threads, 0, st>>>(mean, scale, shape, rates, logw, M, D, ref, W, bias);
     BEER_LAUNCH_CHECK();

@@ -1,0 +1,56 @@
+"""Small end-to-end pass over every kernel family, meant to run under compute-sanitizer:
+
+    compute-sanitizer --tool memcheck python tools/sanitize.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from beer_b200 import features, ops, synthetic  # noqa: E402
+from beer_b200.engine import EmissionParams, Utterances, VBEngine, WeightGroup  # noqa: E402
+
+dev = torch.device('cuda', 0)
+
+
+def run(P, S, C, D, lens, tag):
+    K, M = P * S, P * S * C
+    graph, _, _ = synthetic.phone_loop_graph(P, S)
+    plan = ops.GraphPlan(graph.init_log_probs.numpy(), graph.final_log_probs.numpy(), graph.trans_log_probs.numpy(),
+                         graph.pdf_id_mapping, n_pdfs=K)
+    means = 2.0 * torch.randn(K, D, generator=torch.Generator().manual_seed(0))
+    full = synthetic.sample_utterances(graph, means, len(lens), max(lens), seed=1, device=dev).reshape(len(lens), max(lens), D)
+    X = torch.cat([full[i, :n] for i, n in enumerate(lens)])
+    prior, post = synthetic.initial_normal_gamma(M, D, seed=2, device=dev)
+    groups, comp_off = (), None
+    if C > 1:
+        conc = torch.full((K, C), 1.0 / C, device=dev)
+        groups = (WeightGroup(0, K, C, conc.clone(), conc.clone()),)
+        comp_off = np.arange(K + 1) * C
+    em = EmissionParams(prior, post, comp_off=comp_off, weight_groups=groups)
+    eng = VBEngine(em, plan, Utterances(X, lens), datasize=float(sum(lens)), distributed=False)
+    vals = [float(eng.step().item()) for _ in range(2)]
+    off = torch.as_tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int64, device=dev)
+    pdf, _, fref = em.llh(X, *em.refresh(), torch.empty(len(X), em.Kp, device=dev), None if C == 1 else
+                          torch.empty(len(X), M, device=dev), torch.empty(len(X), device=dev))
+    path = ops.hmm_viterbi(plan, pdf, off)
+    counts = torch.zeros(max(plan.n_units, 1), dtype=torch.float64, device=dev)
+    if plan.n_units and plan.info['states_per_lane'] <= 16:
+        ops.hmm_forward_backward(plan, pdf, fref, off, want_state_post=True, want_frame_llh=True, want_logz=True,
+                                 unit_counts=counts)
+    torch.cuda.synchronize()
+    print(f'{tag}: elbo {vals}, tc={em.use_tc}, path[:5]={path[:5].tolist()}, units={plan.n_units}')
+
+
+run(25, 4, 1, 40, [200, 37, 1, 129, 64], 'cfg2-like (tcgen05 KA/KC, LR scan)')
+run(6, 3, 1, 40, [50, 33], 'S=3 units (LR scalar rows)')
+run(16, 4, 8, 40, [130, 77, 40], 'mixtures C=8 (tcgen05, streamed weight image)')
+run(130, 4, 1, 40, [60, 35], 'many units (block scan), 5 Gaussian tiles')
+run(5, 4, 2, 12, [40, 41], 'SIMT kernels (D=12)')
+sig = (np.random.default_rng(0).standard_normal(16000) * 1000).astype(np.int16)
+fb = features.fbank(sig, nfilters=40)
+print('fbank', tuple(fb.shape), tuple(features.add_deltas(fb).shape))
+torch.cuda.synchronize()
+print('sanitize pass done')
