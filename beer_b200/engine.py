@@ -122,6 +122,28 @@ class EmissionParams:
         ops.normalgamma_update(self.prior, self.post, acc, stats_scale, lrate)
 
 
+class UnitWeights:
+    """Learned unit weights of a phone loop (PhoneLoop.categorical, beer/models/phoneloop.py:12-101):
+    Dirichlet prior / posterior concentrations [P] on the device, the compiled decoding graph whose
+    end -> start transitions are rewritten from E[ln w] after every update, and the start / end state of
+    every unit (in the order of the weights)."""
+
+    def __init__(self, prior_conc, post_conc, graph, start_idxs, end_idxs):
+        self.prior, self.post = prior_conc, post_conc
+        self.graph = graph
+        self.start_idxs = [int(i) for i in start_idxs]
+        self.end_idxs = [int(i) for i in end_idxs]
+
+    def rewrite_graph(self):
+        """ln A[end, starts] = ln(1 - A[end, end]) + E[ln w] (phoneloop.py:53-65), on the host copy of the
+        graph; its device plan is rebuilt on the next use."""
+        logw = ops.dirichlet_expected_logw(self.post)
+        trans = self.graph.trans_log_probs
+        logw = logw.to(device=trans.device, dtype=trans.dtype)
+        for e in self.end_idxs:
+            trans[e, self.start_idxs] = (1 - trans[e, e].exp()).log() + logw
+
+
 class _StageTimer:
     """CUDA events around one kernel stage on the current stream (only when profiling)."""
 
@@ -173,7 +195,7 @@ class VBEngine:
     copy of chunk i+1 overlapping the kernels of chunk i."""
 
     def __init__(self, emission, plan, utts, datasize=None, scale=1.0, lrate=1.0, chunk_frames=None,
-                 process_group=None, distributed=None, use_graph=False):
+                 process_group=None, distributed=None, use_graph=False, unit_weights=None):
         self.em, self.plan, self.utts = emission, plan, utts
         self.scale, self.lrate = float(scale), float(lrate)
         self.dev = emission.device
@@ -183,10 +205,15 @@ class VBEngine:
         self.distributed = distributed
         M, D = emission.M, emission.D
         self.Q = 2 * D + 2
-        # flat reduction buffer: [acc (M*Q) | sum_u (N/T_u) ell_u | sum_u T_u | n_utts | sum_u ell_u]
-        self.flat = torch.zeros(M * self.Q + 4, device=self.dev, dtype=f64)
+        # flat reduction buffer: [acc (M*Q) | unit counts (P) | sum_u (N/T_u) ell_u | sum_u T_u | n_utts | sum_u ell_u]
+        self.units = unit_weights
+        P = plan.n_units if unit_weights is not None else 0
+        if unit_weights is not None and P == 0:
+            raise ValueError('unit weights need an aligned left-to-right phone loop (see beer_hmm_forward_backward_units)')
+        self.flat = torch.zeros(M * self.Q + P + 4, device=self.dev, dtype=f64)
         self.acc = self.flat[:M * self.Q].view(M, self.Q)
-        self.extras = self.flat[M * self.Q:]
+        self.unit_counts = self.flat[M * self.Q:M * self.Q + P] if P else None
+        self.extras = self.flat[M * self.Q + P:]
         self.kl = torch.zeros(1, device=self.dev, dtype=f64)
         self.local_frames = len(utts)
         self.datasize = float(datasize) if datasize is not None else None
@@ -217,7 +244,8 @@ class VBEngine:
         self.utt_ell = torch.zeros(utts.n_utts, device=self.dev, dtype=f64)
         self.gpu_launches = 0
         # the SIMT emission kernel reads the component offsets back to size its grid: not capturable
-        self.use_graph = bool(use_graph) and (emission.use_tc or not emission.has_mixtures)
+        self.use_graph = (bool(use_graph) and (emission.use_tc or not emission.has_mixtures)
+                          and unit_weights is None)      # the graph rewrite syncs with the host
         self._shard_counts = torch.tensor([float(self.local_frames), float(utts.n_utts)], device=self.dev, dtype=f64)
         self._graph, self._graph_elbo, self._graph_launches, self._eager_steps = None, None, 0, 0
 
@@ -249,6 +277,8 @@ class VBEngine:
         self.kl.zero_()
         W, bias, ref = em.refresh()
         em.kl(out=self.kl)
+        if self.units is not None:
+            ops.dirichlet_kl(self.units.prior, self.units.post, out=self.kl)
         self.gpu_launches += 2 + 1 + 2 * len(em.weight_groups) + int(em.use_tc)
         nonident = not (plan.info['map_identity'] and plan.n_states == em.Kp)
         chunks = [c for c in self._chunks if c[3] > 0]
@@ -272,7 +302,8 @@ class VBEngine:
                 pdf_post.zero_()
             with self._stage('KB_forward_backward'):
                 ops.hmm_forward_backward(plan, pdf_llh, fref, rel, scale=self.scale, workspace=self.ws,
-                                         out_pdf_post=pdf_post, out_utt_exp_llh=self.utt_ell[u0:u1])
+                                         out_pdf_post=pdf_post, out_utt_exp_llh=self.utt_ell[u0:u1],
+                                         unit_counts=self.unit_counts)
             with self._stage('KC_accumulate'):
                 ops.accumulate_stats(X, self.acc, pdf_post=pdf_post,
                                      pdf_llh=pdf_llh if comp is not None else None, comp_llh=comp,
@@ -313,6 +344,18 @@ class VBEngine:
         elbo = elbo_from_flat(self.extras, self.kl[0], datasize)
         self.em.update(self.acc, stats_scale, self.lrate)
         self.gpu_launches += 1 + (1 + len(self.em.weight_groups) if self.em.weight_groups else 0)
+        if self.units is not None:
+            # unit counts in the order of the weights -> Dirichlet statistics (last entry = total,
+            # dirichlet.py:18-21) -> natural-gradient step -> rewrite the graph -> new device plan
+            u = self.units
+            su = self.plan.n_states // self.unit_counts.numel()
+            order = torch.as_tensor([s // su for s in u.start_idxs], device=self.dev)
+            stats = self.unit_counts[order].clone()
+            stats[-1] = stats.sum()
+            ops.dirichlet_update(u.prior, u.post, stats, stats_scale, self.lrate)
+            u.rewrite_graph()
+            self.plan = u.graph.plan(n_pdfs=self.em.Kp)
+            self.gpu_launches += 2
         return elbo
 
     def _global_frames(self):
