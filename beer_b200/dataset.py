@@ -1,0 +1,81 @@
+"""Data-set format of the reference CLI (beer/cli/dataset.py:38-80, subcommands/dataset/create.py:14-38):
+an `.npz` archive of per-utterance float arrays [T_u, D] plus the global mean / variance / frame count.
+Host-side I/O only; `Dataset.shard(rank, world)` returns this rank's utterances as the ragged batch the
+engine keeps resident in HBM (the `split` step of the reference's job arrays)."""
+import numpy as np
+import torch
+
+from .engine import Utterances, shard_utterances
+
+__all__ = ['Dataset', 'Utterance']
+
+
+class Utterance:
+    """An utterance id with its features (dataset.py:10-15)."""
+
+    def __init__(self, id, features):
+        self.id, self.features = id, features
+
+
+class Dataset:
+    """Utterances of a features archive with the statistics `beer dataset create` stores."""
+
+    def __init__(self, feapath, mean=None, var=None, size=None):
+        self.feapath = feapath
+        self._fea = None
+        if mean is None or var is None or size is None:
+            mean, var, size = self.accumulate(feapath)
+        self.mean, self.var, self.size = mean, var, size
+
+    @staticmethod
+    def accumulate(feapath):
+        """Global mean, variance and number of frames (create.py:14-38)."""
+        feats = np.load(feapath)
+        keys = list(feats.keys())
+        dim = feats[keys[0]].shape[1]
+        tot, tot2, n = np.zeros(dim), np.zeros(dim), 0
+        for k in keys:
+            x = feats[k]
+            tot += x.sum(axis=0)
+            tot2 += (x ** 2).sum(axis=0)
+            n += len(x)
+        mean = tot / n
+        return torch.from_numpy(mean).float(), torch.from_numpy(tot2 / n - mean ** 2).float(), int(n)
+
+    @property
+    def fea_dict(self):
+        if self._fea is None:
+            self._fea = np.load(self.feapath)
+        return self._fea
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state['_fea'] = None
+        return state
+
+    def __len__(self):
+        return len(self.fea_dict.files)
+
+    def __getitem__(self, key):
+        return Utterance(key, torch.from_numpy(self.fea_dict[key]).float())
+
+    def utterances(self, random_order=False):
+        ids = sorted(self.fea_dict.keys())
+        if random_order:
+            import random
+            random.shuffle(ids)
+        for uttid in ids:
+            yield self[uttid]
+
+    def shard(self, rank=0, world_size=1, device='cuda', pinned_host=False):
+        """(utterance ids, Utterances) of this rank: utterances dealt to ranks so that the frames per rank
+        are balanced.  `pinned_host`: keep the frames in pinned host memory (the engine then streams them)."""
+        ids = sorted(self.fea_dict.keys())
+        lens = [len(self.fea_dict[i]) for i in ids]
+        mine = shard_utterances(lens, world_size)[rank]
+        feats = [np.asarray(self.fea_dict[ids[i]], dtype=np.float32) for i in mine]
+        dim = self.fea_dict[ids[0]].shape[1]
+        X = torch.from_numpy(np.concatenate(feats) if feats else np.zeros((0, dim), np.float32))
+        if pinned_host:
+            return [ids[i] for i in mine], Utterances(X.pin_memory(), [lens[i] for i in mine])
+        return [ids[i] for i in mine], Utterances(X, [lens[i] for i in mine], device=device)

@@ -173,3 +173,30 @@ def test_filterbank_matrix_matches_reference():
     g = load_golden('fbank')
     for nf in (40, 26):
         np.testing.assert_allclose(F.create_fbank(nf, 512, lowfreq=20, highfreq=8000), g[f'filters{nf}'], atol=1e-15)
+
+
+def test_dataset_archive_roundtrip(tmp_path):
+    """The reference's features archive (npz of per-utterance arrays) -> statistics and balanced shards."""
+    from beer_b200.dataset import Dataset
+    rng = np.random.default_rng(3)
+    utts = {f'utt{i:02d}': rng.standard_normal((int(n), 5)).astype(np.float32) + 2
+            for i, n in enumerate(rng.integers(5, 60, size=11))}
+    path = str(tmp_path / 'feats.npz')
+    np.savez(path, **utts)
+    ds = Dataset(path)
+    allx = np.concatenate(list(utts.values()))
+    assert ds.size == len(allx) and len(ds) == 11
+    np.testing.assert_allclose(ds.mean.numpy(), allx.mean(0), rtol=1e-5)
+    np.testing.assert_allclose(ds.var.numpy(), allx.var(0), rtol=1e-4)
+    seen = []
+    for rank in range(3):
+        ids, batch = ds.shard(rank, 3, device='cpu')
+        seen += ids
+        assert batch.n_utts == len(ids) and len(batch) == sum(len(utts[i]) for i in ids)
+        off = batch.offsets_host
+        for j, i in enumerate(ids):
+            np.testing.assert_array_equal(batch.X[off[j]:off[j + 1]].numpy(), utts[i])
+    assert sorted(seen) == sorted(utts)
+    import pickle
+    ds2 = pickle.loads(pickle.dumps(ds))
+    assert ds2.size == ds.size and len(ds2['utt03'].features) == len(utts['utt03'])
