@@ -415,6 +415,11 @@ static int launch(const Args& a0, cudaStream_t st) {
 // block of a stage are each ONE contiguous range in HBM, so a loader thread moves them with two
 // cp.async.bulk (TMA) copies into a deep shared-memory ring: ~100 KB in flight per SM instead
 // of one stage of per-thread loads.  Producers transpose / split from that ring.
+//
+// MIX = true: mixtures with C | 128 components per pdf and any number of Gaussian tiles.  A stage of a
+// tile is 32 rows of 128 per-Gaussian llhs + 32 rows of 128 / C pdf posteriors and pdf llhs (one bulk row
+// copy per frame and array, issued by the 32 lanes of the loader warp) + the contiguous feature block; the
+// producers form w = post * exp(comp_llh - pdf_llh) from shared memory (mixtureset.py:100-112).
 // ---------------------------------------------------------------------------
 constexpr int RAW_KF = 32;          // frames per stage
 constexpr int RAW_OPS = 2;          // operand (MMA) stages
@@ -442,15 +447,16 @@ struct RawCfg {
     static constexpr uint32_t TMEM_COLS = 2 * NB <= 64 ? 64 : (2 * NB <= 128 ? 128 : (2 * NB <= 256 ? 256 : 512));
     static constexpr int DR = 128 / KF;    // stages per drain: 48 truncating TMEM accumulations (~3e-7 low)
     static constexpr size_t FIXED = (size_t)RAW_OPS * STAGE_FLOATS * 4 + sizeof(RawBarriers) + 1024;
-    static size_t raw_stage_bytes(int M) { return (size_t)KF * (M + D) * 4; }
-    static int raw_stages(int M) {
+    // floats of one raw stage; w = width of the posterior block (M, or for mixtures GM + 2 * GM / C)
+    static size_t raw_stage_bytes(int w) { return (size_t)KF * (w + D) * 4; }
+    static int raw_stages(int w) {
         size_t left = 227 * 1024 - FIXED;
-        int n = (int)(left / raw_stage_bytes(M));
+        int n = (int)(left / raw_stage_bytes(w));
         return n > RAW_MAX ? RAW_MAX : n;
     }
 };
 
-template <int D4>
+template <int D4, bool MIX>
 __global__ void __launch_bounds__(RAW_THREADS, 1) accumulate_tc_raw_kernel(Args a, int RS) {
     using C = RawCfg<D4>;
     constexpr int D = C::D, NB = C::NB, KG = C::KG, KF = C::KF, STAGES = RAW_OPS;
@@ -458,17 +464,22 @@ __global__ void __launch_bounds__(RAW_THREADS, 1) accumulate_tc_raw_kernel(Args 
     float* stage_base = reinterpret_cast<float*>(smem_raw);
     RawBarriers* bars = reinterpret_cast<RawBarriers*>(stage_base + (size_t)STAGES * C::STAGE_FLOATS);
     float* ring = reinterpret_cast<float*>(bars + 1);          // RS x [KF x M posteriors | KF x D features]
-    const int M = a.M;
-    const int raw_floats = KF * (M + D);
+    // mixtures: RS x [KF x GM comp llh | KF x nk posteriors | KF x nk pdf llh | KF x D features]
+    const int gtile = MIX ? (int)(blockIdx.x % a.n_gtiles) : 0;
+    const int g0 = gtile * GM;
+    const int M = MIX ? min(GM, a.M - g0) : a.M;                // Gaussians of this tile
+    const int nk = MIX ? GM / a.C : 0, k0 = MIX ? g0 / a.C : 0;
+    const int PW = MIX ? GM + 2 * nk : M;                      // floats per frame ahead of the features
+    const int raw_floats = KF * (PW + D);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t f_begin = (int64_t)blockIdx.x * a.frames_per_cta;
+    const int64_t f_begin = (int64_t)(MIX ? blockIdx.x / a.n_gtiles : blockIdx.x) * a.frames_per_cta;
     const int64_t f_end = min(a.N, f_begin + a.frames_per_cta);
     const int n_tiles = (f_end > f_begin) ? (int)((f_end - f_begin + KF - 1) / KF) : 0;
 
     if (tid == 0) {
         for (int i = 0; i < RAW_MAX; ++i) {
-            mbar_init(&bars->raw_full[i], 1);
+            mbar_init(&bars->raw_full[i], MIX ? 32 : 1);
             mbar_init(&bars->raw_empty[i], RAW_PRODUCERS);
         }
         for (int i = 0; i < STAGES; ++i) {
@@ -498,7 +509,42 @@ __global__ void __launch_bounds__(RAW_THREADS, 1) accumulate_tc_raw_kernel(Args 
 
     if (warp == RAW_PRODUCERS / 32 + 1) {
         // ------------------------------- loader -----------------------------------
-        if (lane == 0) {
+        if constexpr (MIX) {
+            // Row pieces of 64 - 512 bytes: 16-byte cp.async (LDGSTS) per lane, completion counted on the stage's
+            // mbarrier by one asynchronous arrive per lane (a bulk copy per row piece cost ~65 cycles of TMA issue
+            // each, 97 per stage: slower than the per-thread gathers it replaced).
+            const int cq = M >> 2, kq = (M / a.C) >> 2;           // 16-byte pieces per row: comp llh, posteriors
+            const int nkq = nk >> 2;
+            int rs = 0;
+            uint32_t rph = 0;
+            for (int it = 0; it < n_tiles; ++it) {
+                const int64_t t0 = f_begin + (int64_t)it * KF;
+                const int rows = (int)min((int64_t)KF, f_end - t0);
+                mbar_wait(&bars->raw_empty[rs], rph ^ 1);
+                float* dst = ring + (size_t)rs * raw_floats;
+                if (lane < cq) {
+                    const float* src = a.comp_llh + (size_t)t0 * a.M + g0 + 4 * lane;
+                    for (int r = 0; r < rows; ++r) cp_async16(dst + r * GM + 4 * lane, src + (size_t)r * a.M);
+                }
+                // posteriors and pdf llhs: [rows][nk] pieces, piece p of row r = lane-strided
+                for (int e = lane; e < rows * nkq; e += 32) {
+                    const int r = e / nkq, p = e - r * nkq;
+                    if (p < kq) {
+                        cp_async16(dst + KF * GM + r * nk + 4 * p, a.pdf_post + (size_t)(t0 + r) * a.ld_post + k0 + 4 * p);
+                        cp_async16(dst + KF * (GM + nk) + r * nk + 4 * p,
+                                   a.pdf_llh + (size_t)(t0 + r) * a.ld_pdf + k0 + 4 * p);
+                    }
+                }
+                for (int e = lane; e < rows * (D / 4); e += 32)
+                    cp_async16(dst + KF * PW + 4 * e, a.X + (size_t)t0 * D + 4 * e);
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars->raw_full[rs]))
+                             : "memory");
+                if (++rs == RS) {
+                    rs = 0;
+                    rph ^= 1;
+                }
+            }
+        } else if (lane == 0) {
             int rs = 0;
             uint32_t rph = 0;                      // ring position / pass parity (no runtime division)
             for (int it = 0; it < n_tiles; ++it) {
@@ -551,6 +597,7 @@ __global__ void __launch_bounds__(RAW_THREADS, 1) accumulate_tc_raw_kernel(Args 
         const int gl = tid & (GM - 1);
         const int fq0 = tid >> 7;            // quads fq0, fq0 + 4, ...
         const bool a_active = gl < M;
+        const int kl = MIX ? gl / a.C : 0;   // pdf (local) of this thread's Gaussian
         constexpr int AU = KF / 16;
         const int a_row = (gl >> 3) * (KF * 8) + (gl & 7) * 4;
         int xd[C::BU], xfq[C::BU];
@@ -599,8 +646,8 @@ __global__ void __launch_bounds__(RAW_THREADS, 1) accumulate_tc_raw_kernel(Args 
         for (int it = 0; it < n_tiles; ++it) {
             const int st = it % STAGES;
             const int rows = (int)min((int64_t)KF, f_end - (f_begin + (int64_t)it * KF));
-            const float* rp = ring + (size_t)rs * raw_floats;     // posteriors [KF][M]
-            const float* rx = rp + KF * M;                         // features   [KF][D]
+            const float* rp = ring + (size_t)rs * raw_floats;     // posteriors [KF][M] (mixtures: comp llh [KF][GM])
+            const float* rx = rp + KF * PW;                        // features   [KF][D]
             float* A_hi = stage_base + (size_t)st * C::STAGE_FLOATS;
             float* A_lo = A_hi + C::A_FLOATS;
             float* B_hi = A_lo + C::A_FLOATS;
@@ -614,7 +661,14 @@ __global__ void __launch_bounds__(RAW_THREADS, 1) accumulate_tc_raw_kernel(Args 
                     float h[4], l[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const float w = (f0 + i < rows) ? rp[(f0 + i) * M + gl] : 0.f;
+                        float w;
+                        if constexpr (MIX) {
+                            const float* rq = rp + KF * GM + (f0 + i) * nk + kl;
+                            const float post = rq[0];
+                            w = (f0 + i < rows && post != 0.f) ? post * __expf(rp[(f0 + i) * GM + gl] - rq[KF * nk]) : 0.f;
+                        } else {
+                            w = (f0 + i < rows) ? rp[(f0 + i) * M + gl] : 0.f;
+                        }
                         h[i] = tf32_rn(w);
                         l[i] = w - h[i];
                     }
@@ -664,7 +718,7 @@ __global__ void __launch_bounds__(RAW_THREADS, 1) accumulate_tc_raw_kernel(Args 
             const int g = q * 32 + lane;
             if (g < M) {
                 const int Q = 2 * D + 2;
-                double* row = a.acc + (size_t)g * Q;
+                double* row = a.acc + (size_t)(g0 + g) * Q;
 #pragma unroll
                 for (int m = 0; m < C::MYCH; ++m) {
                     const int ch = part + 4 * m;
@@ -693,28 +747,30 @@ __global__ void __launch_bounds__(RAW_THREADS, 1) accumulate_tc_raw_kernel(Args 
     }
 }
 
-template <int D4>
+template <int D4, bool MIX>
 static int launch_raw(const Args& a0, cudaStream_t st) {
     using C = RawCfg<D4>;
     Args a = a0;
-    const int RS = C::raw_stages(a.M);
+    const int pw = MIX ? GM + 2 * (GM / a.C) : a.M;
+    const int RS = C::raw_stages(pw);
     if (RS < 3) return BEER_ERR_UNSUPPORTED;
-    const size_t smem = C::FIXED + (size_t)RS * C::raw_stage_bytes(a.M);
+    const size_t smem = C::FIXED + (size_t)RS * C::raw_stage_bytes(pw);
     static bool attr_set = false;
     if (!attr_set) {
-        BEER_CUDA_TRY(cudaFuncSetAttribute(accumulate_tc_raw_kernel<D4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           227 * 1024));
+        BEER_CUDA_TRY(cudaFuncSetAttribute(accumulate_tc_raw_kernel<D4, MIX>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    a.n_gtiles = 1;
-    int64_t chunks = kNumSMs;
+    a.n_gtiles = MIX ? (a.M + GM - 1) / GM : 1;
+    // one CTA per SM; with several Gaussian tiles: the largest grid of whole tile sets within 3 waves
+    int64_t chunks = MIX ? (a.n_gtiles >= 3 * kNumSMs ? 1 : 3 * kNumSMs / a.n_gtiles) : kNumSMs;
     int64_t max_chunks = (a.N + RAW_KF - 1) / RAW_KF;
     if (chunks > max_chunks) chunks = max_chunks;
     int64_t fpc = (a.N + chunks - 1) / chunks;
     fpc = (fpc + RAW_KF - 1) / RAW_KF * RAW_KF;
     chunks = (a.N + fpc - 1) / fpc;
     a.frames_per_cta = fpc;
-    accumulate_tc_raw_kernel<D4><<<(int)chunks, RAW_THREADS, smem, st>>>(a, RS);
+    accumulate_tc_raw_kernel<D4, MIX><<<(int)(chunks * a.n_gtiles), RAW_THREADS, smem, st>>>(a, RS);
     BEER_LAUNCH_CHECK();
     return BEER_OK;
 }
@@ -753,8 +809,20 @@ int beer_accumulate_stats_tc(const float* X, int64_t N, int D, const float* pdf_
         ((uintptr_t)pdf_post & 15) == 0 && getenv("BEER_B200_KC_NO_BULK") == nullptr) {
         int rc = BEER_ERR_UNSUPPORTED;
         switch (D / 4) {
-            case 5: rc = kctc::launch_raw<5>(a, st); break;      // wider D: the drain's register sums
-            case 10: rc = kctc::launch_raw<10>(a, st); break;    // do not fit 18 warps per SM
+            case 5: rc = kctc::launch_raw<5, false>(a, st); break;      // wider D: the drain's register sums
+            case 10: rc = kctc::launch_raw<10, false>(a, st); break;    // do not fit 18 warps per SM
+        }
+        if (rc != BEER_ERR_UNSUPPORTED) return rc;
+    }
+    // mixtures, C | 128 components per pdf: bulk-staged rows (16-byte aligned row pieces)
+    if (comp_llh != nullptr && pdf_post != nullptr && comp_off == nullptr && a.C >= 1 && a.C <= 32 &&
+        (a.C & (a.C - 1)) == 0 && M % 4 == 0 && Kp % 4 == 0 && ld_post % 4 == 0 && ld_pdf % 4 == 0 &&
+        ((uintptr_t)pdf_post & 15) == 0 && ((uintptr_t)pdf_llh & 15) == 0 && ((uintptr_t)comp_llh & 15) == 0 &&
+        getenv("BEER_B200_KC_NO_BULK") == nullptr) {
+        int rc = BEER_ERR_UNSUPPORTED;
+        switch (D / 4) {
+            case 5: rc = kctc::launch_raw<5, true>(a, st); break;
+            case 10: rc = kctc::launch_raw<10, true>(a, st); break;
         }
         if (rc != BEER_ERR_UNSUPPORTED) return rc;
     }

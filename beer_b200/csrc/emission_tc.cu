@@ -16,6 +16,7 @@
 // (one elected lane) + TMEM allocator, warp 9 = weight-image producer.
 //
 // Reference semantics: beer/dists/normalgamma.py:55-59, beer/models/mixtureset.py:85-98.
+#include <cuda.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "../../include/beer_b200.h"
@@ -28,6 +29,10 @@ constexpr int NB_MAX = 128;    // Gaussians per chunk (UMMA N)
 constexpr int WORKERS = 256;          // 8 worker warps: two per scheduler (one per scheduler left them latency-bound)
 constexpr int MMA_WARP = WORKERS / 32, LOAD_WARP = MMA_WARP + 1;
 constexpr int THREADS = WORKERS + 64;
+// Streamed chunks: the bias of chunk i rides with its weight image into slot i % BIAS_RING.  Slot reuse
+// (chunk i + 4) waits for the MMAs of chunk i + 2, which wait for the epilogue of chunk i (TMEM buffer).
+constexpr int BIAS_RING = 4;
+constexpr int CBOX = 32;       // columns of one staged per-Gaussian llh box: 128-byte rows, 128B-swizzled (TMA store)
 
 using namespace tcu;
 
@@ -45,6 +50,7 @@ struct Args {
     int M, C, Kp, NB, n_chunks, stages;
     int logC;            // log2(C)
     int staged;          // llh tile staged in shared memory and written with one bulk store
+    int cstaged;         // streamed chunks: per-Gaussian llh tile staged in shared memory, rows bulk-stored
     float* pdf_llh;
     int64_t ld;
     float* comp_llh;
@@ -60,7 +66,7 @@ struct Barriers {
 };
 
 template <int D4>
-__global__ void __launch_bounds__(THREADS, 1) emission_tc_kernel(Args a) {
+__global__ void __launch_bounds__(THREADS, 1) emission_tc_kernel(Args a, const __grid_constant__ CUtensorMap cmap) {
     constexpr int D = 4 * D4, Kd = 2 * D, KSTEPS = Kd / 8;
     constexpr uint32_t LBO = 128, SBO = (Kd / 4) * 128;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -68,8 +74,8 @@ __global__ void __launch_bounds__(THREADS, 1) emission_tc_kernel(Args a) {
     float* A_lo = A_hi + FR * Kd;
     float* Bst = A_lo + FR * Kd;                           // stages x [hi image | lo image]
     const int b_stage_floats = 2 * a.NB * Kd;
-    float* s_bias = Bst + (size_t)a.stages * b_stage_floats;  // [n_chunks * NB] (or NB when streaming)
-    const int bias_floats = (a.stages == 1) ? a.NB : a.n_chunks * a.NB;
+    float* s_bias = Bst + (size_t)a.stages * b_stage_floats;  // [NB] resident, or a BIAS_RING-deep ring when streaming
+    const int bias_floats = (a.stages == 1) ? a.NB : BIAS_RING * a.NB;
     float* s_ref = s_bias + bias_floats;                   // [D + 1]
     Barriers* bars = reinterpret_cast<Barriers*>(s_ref + ((D + 1 + 3) & ~3));
 
@@ -89,7 +95,8 @@ __global__ void __launch_bounds__(THREADS, 1) emission_tc_kernel(Args a) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == MMA_WARP) tmem_alloc(&bars->tmem_base, tmem_cols);
-    for (int i = tid; i < bias_floats; i += THREADS) s_bias[i] = a.bias[i];
+    if (a.stages == 1)
+        for (int i = tid; i < bias_floats; i += THREADS) s_bias[i] = a.bias[i];
     for (int i = tid; i <= D; i += THREADS) s_ref[i] = a.ref[i];
     tc_fence_before();
     __syncthreads();
@@ -110,8 +117,10 @@ __global__ void __launch_bounds__(THREADS, 1) emission_tc_kernel(Args a) {
                     for (int c = 0; c < a.n_chunks; ++c, ++it) {
                         const int st = it & 1;
                         mbar_wait(&bars->b_empty[st], ((it >> 1) & 1) ^ 1);
-                        mbar_arrive_expect_tx(&bars->b_full[st], bytes);
+                        mbar_arrive_expect_tx(&bars->b_full[st], bytes + (uint32_t)a.NB * 4u);
                         bulk_g2s(Bst + (size_t)st * b_stage_floats, a.img + (size_t)c * b_stage_floats, bytes,
+                                 &bars->b_full[st]);
+                        bulk_g2s(s_bias + (it & (BIAS_RING - 1)) * a.NB, a.bias + (size_t)c * a.NB, (uint32_t)a.NB * 4u,
                                  &bars->b_full[st]);
                     }
             }
@@ -216,7 +225,7 @@ __global__ void __launch_bounds__(THREADS, 1) emission_tc_kernel(Args a) {
             mbar_wait(&bars->t_full[buf], (it >> 1) & 1);
             tc_fence_after();
             const int g0 = c * a.NB;
-            const float* bias_c = s_bias + ((a.stages == 1) ? 0 : g0);
+            const float* bias_c = s_bias + ((a.stages == 1) ? 0 : (int)(it & (BIAS_RING - 1)) * a.NB);
             const uint32_t taddr = tmem_base + lane_addr + (uint32_t)buf * (uint32_t)a.NB;
             const int nch = a.NB >> 4, ch0 = he ? (nch + 1) / 2 : 0, ch1 = he ? nch : (nch + 1) / 2;
             for (int p = ch0 * 16; p < ch1 * 16; p += 16) {
@@ -297,6 +306,83 @@ __global__ void __launch_bounds__(THREADS, 1) emission_tc_kernel(Args a) {
             }
         };
 
+        // Streamed chunks of a mixture: the per-Gaussian llh tile goes through shared memory and out as TMA tensor
+        // stores (a thread's own row stores are 16-byte pieces of 128 distinct lines per instruction, and one bulk
+        // row copy per frame cost ~35 cycles of TMA issue each: both bounded the kernel well below HBM).  The two
+        // warps of a TMEM lane quarter own one [FR x 32] box each (128-byte rows, 128B swizzle: conflict-free
+        // float4 stores); the log-sum-exp runs under the store.
+        auto epilogue_cs = [&](int64_t tile, uint32_t it, int c) {
+            const int64_t t = tile * FR + r;
+            const bool valid = t < a.N;
+            const int buf = it & 1;
+            // boxes: 1024-byte aligned (the swizzle is a function of the address)
+            uint8_t* s_box = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bars + 1) + 1023) & ~uintptr_t(1023)) +
+                             (size_t)he * (FR * CBOX * 4);
+            const bool issuer = (warp & 3) == 0 && lane == 0;
+            if (issuer) bulk_wait_read0();            // the previous chunk's store has read the box
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + he) : "memory");
+            mbar_wait(&bars->t_full[buf], (it >> 1) & 1);
+            tc_fence_after();
+            const int g0 = c * a.NB;
+            // the bias slot landed with the weight image the MMAs behind t_full have read (no wait on b_full here:
+            // it may already be two phases ahead, which a parity wait cannot tell from "not yet")
+            const float* bias_c = s_bias + (int)(it & (BIAS_RING - 1)) * a.NB;
+            const uint32_t taddr = tmem_base + lane_addr + (uint32_t)buf * (uint32_t)a.NB;
+            float v[2][16];
+            const int p0 = he * 32;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                tmem_ld16(taddr + (uint32_t)(p0 + 16 * h), v[h]);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[h][i] += bias_c[p0 + 16 * h + i];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    *reinterpret_cast<float4*>(s_box + (size_t)r * 128 + (((4 * h + q) ^ (r & 7)) << 4)) =
+                        make_float4(v[h][4 * q], v[h][4 * q + 1], v[h][4 * q + 2], v[h][4 * q + 3]);
+            }
+            tc_fence_before();
+            mbar_arrive(&bars->t_empty[buf]);
+            fence_proxy_async();
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + he) : "memory");
+            if (issuer) {
+                // rows past N and columns past M are clipped by the tensor map
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&cmap),
+                             "r"(smem_u32(s_box)), "r"(g0 + p0), "r"((int)(tile * FR))
+                             : "memory");
+                bulk_commit();
+            }
+            if (!valid) return;
+            // log-sum-exp over the C components of each pdf
+            const int C = a.C, no = 32 / C;
+            float o[8];
+#pragma unroll
+            for (int lg = 2; lg <= 4; ++lg) {
+                if (C == (1 << lg)) {
+                    const int CC = 1 << lg;
+#pragma unroll
+                    for (int k = 0; k < 32 / CC; ++k) {
+                        const float* vv = &v[0][0] + k * CC;
+                        float m = vv[0];
+#pragma unroll
+                        for (int j = 1; j < CC; ++j) m = fmaxf(m, vv[j]);
+                        float sm = 0.f;
+#pragma unroll
+                        for (int j = 0; j < CC; ++j) sm += __expf(vv[j] - m);
+                        o[k] = m + __logf(sm);
+                    }
+                }
+            }
+            const int k0 = (g0 + p0) >> a.logC;
+            float* dst = a.pdf_llh + (size_t)t * a.ld + k0;
+            if (no == 4 && k0 + 4 <= a.Kp && (a.ld & 3) == 0) {
+                *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (i < no && k0 + i < a.Kp) dst[i] = o[i];
+            }
+        };
+
         if (a.n_chunks == 1) {
             // Software pipeline: the epilogue of tile i-1 runs under the MMAs of tile i and the
             // frames of tile i+1 are already in flight.
@@ -324,8 +410,12 @@ __global__ void __launch_bounds__(THREADS, 1) emission_tc_kernel(Args a) {
                 build(tile, xv);
                 fence_proxy_async();
                 mbar_arrive(&bars->a_ready);
-                for (int c = 0; c < a.n_chunks; ++c, ++it) epilogue(tile, it, c);
+                if (a.cstaged)
+                    for (int c = 0; c < a.n_chunks; ++c, ++it) epilogue_cs(tile, it, c);
+                else
+                    for (int c = 0; c < a.n_chunks; ++c, ++it) epilogue(tile, it, c);
             }
+            if (a.cstaged && (warp & 3) == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
     }
     tc_fence_before();
@@ -360,6 +450,10 @@ __global__ void emission_tc_pack_kernel(const float* __restrict__ W, const float
 
 struct Geometry { int NB, n_chunks, stages; };
 
+typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
 static bool geometry(int M, int D, int C, Geometry* g) {
     if (D % 4 != 0) return false;
     int d4 = D / 4;
@@ -380,13 +474,13 @@ static bool geometry(int M, int D, int C, Geometry* g) {
 static size_t smem_bytes(int D, const Geometry& g, int staged_kp = 0) {
     int Kd = 2 * D;
     size_t f = (size_t)2 * FR * Kd + (size_t)g.stages * 2 * g.NB * Kd +
-               (size_t)(g.stages == 1 ? g.NB : g.n_chunks * g.NB) + ((D + 1 + 3) & ~3) + (size_t)FR * staged_kp;
+               (size_t)(g.stages == 1 ? g.NB : BIAS_RING * g.NB) + ((D + 1 + 3) & ~3) + (size_t)FR * staged_kp;
     return f * 4 + sizeof(Barriers) + 1024;
 }
 
 template <int D4>
 static int launch(const Args& a, const Geometry& g, cudaStream_t st) {
-    size_t smem = smem_bytes(4 * D4, g, a.staged ? a.Kp : 0);
+    size_t smem = smem_bytes(4 * D4, g, a.staged ? a.Kp : (a.cstaged ? 2 * CBOX + 8 : 0));   // + 1 KB alignment slack
     if (smem > 227 * 1024) return BEER_ERR_UNSUPPORTED;
     static bool attr_set = false;
     if (!attr_set) {
@@ -396,7 +490,28 @@ static int launch(const Args& a, const Geometry& g, cudaStream_t st) {
     }
     int64_t n_tiles = (a.N + FR - 1) / FR;
     int grid = (int)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
-    emission_tc_kernel<D4><<<grid, THREADS, smem, st>>>(a);
+    CUtensorMap cmap;
+    memset(&cmap, 0, sizeof(cmap));
+    if (a.cstaged) {
+        // comp_llh [N, M] fp32 row-major, boxes of [FR rows x CBOX columns], 128B swizzle in shared memory
+        static EncodeTiled encode = nullptr;
+        if (encode == nullptr) {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            BEER_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+            if (fn == nullptr || q != cudaDriverEntryPointSuccess) return BEER_ERR_UNSUPPORTED;
+            encode = reinterpret_cast<EncodeTiled>(fn);
+        }
+        const cuuint64_t gdim[2] = {(cuuint64_t)a.M, (cuuint64_t)a.N};
+        const cuuint64_t gstride[1] = {(cuuint64_t)a.M * 4};
+        const cuuint32_t box[2] = {CBOX, FR};
+        const cuuint32_t estr[2] = {1, 1};
+        if (encode(&cmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a.comp_llh, gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return BEER_ERR_UNSUPPORTED;
+    }
+    emission_tc_kernel<D4><<<grid, THREADS, smem, st>>>(a, cmap);
     BEER_LAUNCH_CHECK();
     return BEER_OK;
 }
@@ -452,6 +567,9 @@ int beer_emission_llh_tc(const float* X, int64_t N, int D, const float* image, c
     // stage + bulk-store the llh tile when its rows are contiguous in HBM and it fits next to the operands
     a.staged = (g.n_chunks == 1 && ld_pdf == a.Kp && (a.Kp & 3) == 0 && ((uintptr_t)pdf_llh & 15) == 0 &&
                 tc::smem_bytes(D, g, a.Kp) <= 227 * 1024) ? 1 : 0;
+    // streamed chunks of a mixture (C = 4, 8, 16): per-Gaussian llh rows leave through shared memory + bulk copies
+    a.cstaged = (g.n_chunks > 1 && g.NB == 64 && comp_llh != nullptr && (C == 4 || C == 8 || C == 16) && (M & 3) == 0 &&
+                 ((uintptr_t)comp_llh & 15) == 0 && tc::smem_bytes(D, g, 2 * tc::CBOX + 8) <= 227 * 1024) ? 1 : 0;
     cudaStream_t st = (cudaStream_t)stream;
     switch (D / 4) {
         case 5: return tc::launch<5>(a, g, st);

@@ -307,7 +307,8 @@ class VBEngine:
             with self._stage('KC_accumulate'):
                 ops.accumulate_stats(X, self.acc, pdf_post=pdf_post,
                                      pdf_llh=pdf_llh if comp is not None else None, comp_llh=comp,
-                                     comp_off=em.comp_off if comp is not None else None, Kp=em.Kp)
+                                     comp_off=em.comp_off if (comp is not None and not em.uniform_C) else None,
+                                     Kp=em.Kp)
             self.gpu_launches += 3
             if self.host_mode:
                 self._free[ci & 1].record()

@@ -19,7 +19,10 @@ def _exact(X, w):
 CASES = [(100, 1, 40, 4000, True), (100, 1, 40, 77, True), (7, 1, 40, 1000, True), (130, 1, 40, 900, True),
          (100, 1, 40, 64 * 148 * 2 + 13, True), (100, 1, 40, 148 * 32 * 40 + 5, True), (64, 8, 40, 1500, True), (200, 4, 40, 1031, True),
          (96, 3, 20, 555, True), (8, 8, 40, 3000, False), (512, 1, 40, 2000, False), (48, 1, 64, 700, True),
-         (40, 2, 80, 333, True)]
+         (40, 2, 80, 333, True),
+         # mixtures on the bulk-staged path: several Gaussian tiles, a partial last tile, ragged last stage
+         (1024, 8, 40, 3000, True), (2112, 8, 40, 2531, True), (160, 4, 40, 777, True), (512, 16, 40, 1000, True),
+         (256, 32, 20, 413, True), (128, 1, 40, 500, True)]
 
 
 @pytest.mark.parametrize('M,C,D,N,use_post', CASES)
@@ -39,7 +42,8 @@ def test_tc_statistics(M, C, D, N, use_post):
     if C > 1:
         comp = (torch.randn(N, M, generator=g) * 3 - 50).to(DEV).contiguous()
         pdf = torch.logsumexp(comp.reshape(N, Kp, C), dim=-1).contiguous()
-        comp_off = torch.arange(Kp + 1, dtype=torch.int32, device=DEV) * C
+        # uniform C: no CSR offsets (the bulk-staged mixture path); three cases keep the CSR form of the same layout
+        comp_off = torch.arange(Kp + 1, dtype=torch.int32, device=DEV) * C if N in (1031, 555, 333) else None
         resp = torch.exp(comp.double().reshape(N, Kp, C) - pdf.double()[:, :, None])
         w = resp * (post.double()[:, :, None] if use_post else 1.)
         w = w.reshape(N, M)

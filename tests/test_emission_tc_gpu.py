@@ -19,7 +19,9 @@ def _params(M, D, seed):
 
 
 @pytest.mark.parametrize('M,C,D,N', [(100, 1, 40, 1000), (100, 1, 40, 77), (16, 1, 40, 300), (128, 2, 40, 515),
-                                     (200, 2, 40, 400), (1024, 8, 40, 260), (96, 4, 20, 333), (48, 16, 40, 129)])
+                                     (200, 2, 40, 400), (1024, 8, 40, 260), (96, 4, 20, 333), (48, 16, 40, 129),
+                                     # streamed chunks with the staged per-Gaussian tile; partial last chunk
+                                     (1000, 8, 40, 300), (520, 4, 40, 200), (2048, 16, 40, 1000), (640, 8, 20, 131)])
 def test_tc_matches_simt(M, C, D, N):
     from beer_b200 import ops
     ops.require_cuda()
