@@ -426,6 +426,9 @@ constexpr int RAW_OPS = 2;          // operand (MMA) stages
 constexpr int RAW_MAX = 8;          // raw ring depth (upper bound)
 constexpr int RAW_PRODUCERS = 512;  // 16 producer warps = 4 per scheduler (2 per scheduler were latency-bound)
 constexpr int RAW_THREADS = RAW_PRODUCERS + 64;   // + MMA warp + loader warp
+constexpr int MIX_LOADERS = 96;                   // mixtures: three loader warps (one warp's issue latency bound the ring;
+                                                  // 20 warps keep the 96-register budget of the producers)
+constexpr int MIX_THREADS = RAW_PRODUCERS + 32 + MIX_LOADERS;
 
 struct RawBarriers {
     uint64_t raw_full[RAW_MAX], raw_empty[RAW_MAX];
@@ -457,7 +460,7 @@ struct RawCfg {
 };
 
 template <int D4, bool MIX>
-__global__ void __launch_bounds__(RAW_THREADS, 1) accumulate_tc_raw_kernel(Args a, int RS) {
+__global__ void __launch_bounds__(MIX ? MIX_THREADS : RAW_THREADS, 1) accumulate_tc_raw_kernel(Args a, int RS) {
     using C = RawCfg<D4>;
     constexpr int D = C::D, NB = C::NB, KG = C::KG, KF = C::KF, STAGES = RAW_OPS;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -479,7 +482,7 @@ __global__ void __launch_bounds__(RAW_THREADS, 1) accumulate_tc_raw_kernel(Args 
 
     if (tid == 0) {
         for (int i = 0; i < RAW_MAX; ++i) {
-            mbar_init(&bars->raw_full[i], MIX ? 32 : 1);
+            mbar_init(&bars->raw_full[i], MIX ? MIX_LOADERS : 1);
             mbar_init(&bars->raw_empty[i], RAW_PRODUCERS);
         }
         for (int i = 0; i < STAGES; ++i) {
@@ -493,10 +496,10 @@ __global__ void __launch_bounds__(RAW_THREADS, 1) accumulate_tc_raw_kernel(Args 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == RAW_PRODUCERS / 32) tmem_alloc(&bars->tmem_base, C::TMEM_COLS);
-    for (int i = tid; i < STAGES * C::STAGE_FLOATS / 4; i += RAW_THREADS)
+    for (int i = tid; i < STAGES * C::STAGE_FLOATS / 4; i += (int)blockDim.x)
         reinterpret_cast<float4*>(stage_base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
-    for (int i = tid; i < STAGES * KF; i += RAW_THREADS) {
+    for (int i = tid; i < STAGES * KF; i += (int)blockDim.x) {
         int st = i / KF, f = i - st * KF;
         float* b_hi = stage_base + (size_t)st * C::STAGE_FLOATS + 2 * C::A_FLOATS;
         b_hi[((2 * D) >> 3) * (KF * 8) + (f >> 2) * 32 + ((2 * D) & 7) * 4 + (f & 3)] = 1.f;
@@ -507,35 +510,42 @@ __global__ void __launch_bounds__(RAW_THREADS, 1) accumulate_tc_raw_kernel(Args 
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
-    if (warp == RAW_PRODUCERS / 32 + 1) {
+    if (warp > RAW_PRODUCERS / 32) {
         // ------------------------------- loader -----------------------------------
         if constexpr (MIX) {
             // Row pieces of 64 - 512 bytes: 16-byte cp.async (LDGSTS) per lane, completion counted on the stage's
             // mbarrier by one asynchronous arrive per lane (a bulk copy per row piece cost ~65 cycles of TMA issue
             // each, 97 per stage: slower than the per-thread gathers it replaced).
             const int cq = M >> 2, kq = (M / a.C) >> 2;           // 16-byte pieces per row: comp llh, posteriors
-            const int nkq = nk >> 2;
+            const int lw = warp - (RAW_PRODUCERS / 32 + 1);       // loader warp: rows lw, lw + NLW, ...
+            const int lt = lw * 32 + lane;
+            // posteriors / pdf llhs: nk / 4 (a power of two) pieces per row, thread lt -> (row, piece) of element lt, lt + 128, ...
+            const int nkq = nk >> 2, nkq_sh = 31 - __clz(nkq);
             int rs = 0;
             uint32_t rph = 0;
-            for (int it = 0; it < n_tiles; ++it) {
+            const float* c_src = a.comp_llh + (size_t)(f_begin + lw) * a.M + g0 + 4 * lane;
+            constexpr int NLW = MIX_LOADERS / 32;
+            const size_t c_step = (size_t)NLW * a.M, c_adv = (size_t)KF * a.M;
+            for (int it = 0; it < n_tiles; ++it, c_src += c_adv) {
                 const int64_t t0 = f_begin + (int64_t)it * KF;
                 const int rows = (int)min((int64_t)KF, f_end - t0);
                 mbar_wait(&bars->raw_empty[rs], rph ^ 1);
                 float* dst = ring + (size_t)rs * raw_floats;
                 if (lane < cq) {
-                    const float* src = a.comp_llh + (size_t)t0 * a.M + g0 + 4 * lane;
-                    for (int r = 0; r < rows; ++r) cp_async16(dst + r * GM + 4 * lane, src + (size_t)r * a.M);
+                    const float* src = c_src;
+                    float* d = dst + lw * GM + 4 * lane;
+#pragma unroll 4
+                    for (int r = lw; r < rows; r += NLW, src += c_step, d += NLW * GM) cp_async16(d, src);
                 }
-                // posteriors and pdf llhs: [rows][nk] pieces, piece p of row r = lane-strided
-                for (int e = lane; e < rows * nkq; e += 32) {
-                    const int r = e / nkq, p = e - r * nkq;
+                for (int e = lt; e < (rows << nkq_sh); e += MIX_LOADERS) {
+                    const int r = e >> nkq_sh, p = e & (nkq - 1);
                     if (p < kq) {
                         cp_async16(dst + KF * GM + r * nk + 4 * p, a.pdf_post + (size_t)(t0 + r) * a.ld_post + k0 + 4 * p);
                         cp_async16(dst + KF * (GM + nk) + r * nk + 4 * p,
                                    a.pdf_llh + (size_t)(t0 + r) * a.ld_pdf + k0 + 4 * p);
                     }
                 }
-                for (int e = lane; e < rows * (D / 4); e += 32)
+                for (int e = lt; e < rows * (D / 4); e += MIX_LOADERS)
                     cp_async16(dst + KF * PW + 4 * e, a.X + (size_t)t0 * D + 4 * e);
                 asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars->raw_full[rs]))
                              : "memory");
@@ -654,6 +664,13 @@ __global__ void __launch_bounds__(RAW_THREADS, 1) accumulate_tc_raw_kernel(Args 
             float* B_lo = B_hi + C::B_FLOATS;
             mbar_wait(&bars->raw_full[rs], rph);
             mbar_wait(&bars->empty[st], ((it / STAGES) & 1) ^ 1);
+            if constexpr (MIX) {
+                if (rows < KF) {      // ragged last stage: stale posterior rows -> 0 (w = 0 for those frames)
+                    float* rq0 = const_cast<float*>(rp) + KF * GM;
+                    for (int e = rows * nk + tid; e < KF * nk; e += RAW_PRODUCERS) rq0[e] = 0.f;
+                    asm volatile("bar.sync 1, %0;" ::"n"(RAW_PRODUCERS) : "memory");
+                }
+            }
             if (a_active) {
 #pragma unroll
                 for (int j = 0; j < AU; ++j) {
@@ -663,9 +680,12 @@ __global__ void __launch_bounds__(RAW_THREADS, 1) accumulate_tc_raw_kernel(Args 
                     for (int i = 0; i < 4; ++i) {
                         float w;
                         if constexpr (MIX) {
+                            // log2 domain: one FFMA feeds the ex2; rows past the end of a ragged stage hold zeros
+                            // (cleared below), posteriors that are exactly zero stay zero whatever the llhs are
                             const float* rq = rp + KF * GM + (f0 + i) * nk + kl;
                             const float post = rq[0];
-                            w = (f0 + i < rows && post != 0.f) ? post * __expf(rp[(f0 + i) * GM + gl] - rq[KF * nk]) : 0.f;
+                            const float e = ex2(1.4426950408889634f * (rp[(f0 + i) * GM + gl] - rq[KF * nk]));
+                            w = (post != 0.f) ? post * e : 0.f;
                         } else {
                             w = (f0 + i < rows) ? rp[(f0 + i) * M + gl] : 0.f;
                         }
@@ -770,7 +790,7 @@ static int launch_raw(const Args& a0, cudaStream_t st) {
     fpc = (fpc + RAW_KF - 1) / RAW_KF * RAW_KF;
     chunks = (a.N + fpc - 1) / fpc;
     a.frames_per_cta = fpc;
-    accumulate_tc_raw_kernel<D4, MIX><<<(int)(chunks * a.n_gtiles), RAW_THREADS, smem, st>>>(a, RS);
+    accumulate_tc_raw_kernel<D4, MIX><<<(int)(chunks * a.n_gtiles), MIX ? MIX_THREADS : RAW_THREADS, smem, st>>>(a, RS);
     BEER_LAUNCH_CHECK();
     return BEER_OK;
 }
