@@ -60,6 +60,8 @@ SIGNATURES = {
     'beer_segment_logsumexp': (C.c_int, [c_ptr, C.c_int64, C.c_int, c_ptr, C.c_int, c_ptr, C.c_int64, c_ptr]),
     'beer_fbank': (C.c_int, [c_ptr, C.c_int64, C.c_int, C.c_int, C.c_float, c_ptr, c_ptr, C.c_int, C.c_int, c_ptr, c_ptr]),
     'beer_add_deltas': (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
+    'beer_hmm_transition_posteriors': (C.c_int, [c_ptr, C.c_int64, c_ptr, C.c_float, c_ptr, c_ptr, C.c_int, c_ptr,
+                                                 c_ptr, C.c_int, c_ptr, C.c_int, c_ptr, C.c_int, c_ptr, c_ptr]),
     'beer_path_posteriors': (C.c_int, [c_ptr, C.c_int64, c_ptr, C.c_float, c_ptr, C.c_int64, c_ptr, c_ptr,
                                        C.c_int64, C.c_int, c_ptr, c_ptr]),
 }

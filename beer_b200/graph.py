@@ -254,10 +254,16 @@ class CompiledGraph(torch.nn.Module):
 
     def _transition_posteriors(self, llhs, gamma):
         """Dense (T-1, K, K) tensor of graph.py:308-323, for API parity only (O(T K^2) memory,
-        not on the training path, which only needs reductions of it).  Built from the kernel's
-        posteriors: xi_t[i,j] = gamma_t[i] A_ij b_{t+1,j} beta_{t+1,j} / beta_t[i]."""
-        raise NotImplementedError('dense transition posteriors are not materialised by the B200 '
-                                  'engine; PhoneLoop statistics use fused reductions instead')
+        not on the training path, which only needs reductions of it).  Built from the scan kernel's
+        posteriors and one more forward recursion:
+        xi_t[i,j] = gamma_{t+1}[j] alpha_t[i] A_ij / sum_i' alpha_t[i'] A_i'j  (csrc/transitions.cu)."""
+        T = llhs.shape[0]
+        off = torch.tensor([0, T], dtype=torch.int64, device=llhs.device)
+        dev = llhs.device
+        return ops.hmm_transition_posteriors(
+            llhs, gamma.to(torch.float32).contiguous(), off,
+            self.init_log_probs.detach().to(device=dev, dtype=torch.float32).contiguous(),
+            self.trans_log_probs.detach().to(device=dev, dtype=torch.float32).contiguous()).to(gamma.dtype)
 
     def best_path(self, llhs):
         """Viterbi path, first-max tie-breaking (graph.py:329-344); CPU LongTensor like the

@@ -26,7 +26,7 @@ from .engine import Utterances
 from .parameters import ConjugateBayesianParameter
 
 __all__ = ['Model', 'DiscreteLatentModel', 'ModelSet', 'NormalSet', 'Categorical', 'CategoricalSet', 'Mixture',
-           'MixtureSet', 'JointModelSet', 'DynamicallyOrderedModelSet', 'HMM', 'PhoneLoop', 'UnknownCovarianceType']
+           'MixtureSet', 'JointModelSet', 'DynamicallyOrderedModelSet', 'HMM', 'PhoneLoop', 'BigramPhoneLoop', 'UnknownCovarianceType']
 
 f32, f64, i32, i64 = torch.float32, torch.float64, torch.int32, torch.int64
 
@@ -616,11 +616,13 @@ class HMM(DiscreteLatentModel):
         return _Emission(_leaves(self.modelset))
 
     def expected_log_likelihood(self, stats, inference_graph=None, viterbi=False, state_path=None, scale=1.,
-                                _unit_counts=None):
+                                _unit_counts=None, _trans=None):
         """Per-frame sum_k p_tk gamma_tk with p = scale * llh[:, pdf_id_mapping] (hmm.py:73-92).
         Forward-backward by default; `viterbi=True` or a `state_path` give one-hot posteriors.
         `stats` may come from an `Utterances` batch: every utterance is then its own sequence.
-        (`_unit_counts`: PhoneLoop's reduction of the transition posteriors, see below.)"""
+        (`_unit_counts`: PhoneLoop's reduction of the transition posteriors, see below; `_trans` =
+        (rows, cols) state ids: cache the block xi[:, rows, cols] of the transition posteriors the
+        reference computes whenever no inference graph is given (hmm.py:76), as `trans_resps`.)"""
         graph = self.graph if inference_graph is None else inference_graph
         em = self._emission()
         X = frames_of(stats, em.D)
@@ -636,10 +638,20 @@ class HMM(DiscreteLatentModel):
                                               pdf_llh=pdf, frame_ref=fref)
             utt_ell = None
             self.cache['path'] = path
+            if _trans is not None:
+                self.cache['trans_resps'] = _onehot_transitions(path, off, *_trans)
         else:
             r = ops.hmm_forward_backward(plan, pdf, fref, off, scale=scale, want_frame_llh=True,
-                                         unit_counts=_unit_counts)
+                                         unit_counts=_unit_counts, want_state_post=_trans is not None)
             post, frame, utt_ell = r['pdf_post'], r['frame_exp_llh'], r['utt_exp_llh']
+            if _trans is not None:
+                dev = X.device
+                rows, cols = (torch.as_tensor(v, dtype=i32, device=dev) for v in _trans)
+                self.cache['trans_resps'] = ops.hmm_transition_posteriors(
+                    pdf, r['state_post'], off, graph.init_log_probs.detach().to(device=dev, dtype=f32).contiguous(),
+                    graph.trans_log_probs.detach().to(device=dev, dtype=f32).contiguous(),
+                    pdf_map=graph.pdf_map_device(dev), scale=scale, rows=rows, cols=cols)
+                self.cache['first_state_post'] = r['state_post'][off[:-1]]      # gamma_0 of every utterance
         self.cache.update(X=X, pdf_post=post, pdf_llh=pdf, comp_llh=comp, emission=em, scale=scale,
                           utts=utts, utt_exp_llh=utt_ell)
         return frame
@@ -674,6 +686,19 @@ class HMM(DiscreteLatentModel):
         r = ops.hmm_forward_backward(graph.plan(n_pdfs=em.Kp), pdf, fref, off, scale=scale, want_state_post=True,
                                      want_pdf_post=False)
         return r['state_post']
+
+
+def _onehot_transitions(path, off, rows, cols):
+    """One-hot transition posteriors of a state path (hmm.py:49-54), only the block [rows, cols]:
+    [N - n_utts, R, C] with no entry across an utterance boundary."""
+    dev = path.device
+    rows = torch.as_tensor(rows, device=dev, dtype=path.dtype)
+    cols = torch.as_tensor(cols, device=dev, dtype=path.dtype)
+    keep = torch.ones(path.numel(), dtype=torch.bool, device=dev)
+    keep[off[1:] - 1] = False                      # the last frame of an utterance starts no transition
+    src = path[keep]
+    dst = path[torch.roll(keep, 1)]                # frame t + 1 of every kept t
+    return ((src[:, None] == rows[None, :])[:, :, None] & (dst[:, None] == cols[None, :])[:, None, :]).to(f32)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -718,21 +743,24 @@ class PhoneLoop(HMM):
         return _merge_groups(self.modelset.mean_field_factorization(), self.categorical.mean_field_factorization())
 
     def expected_log_likelihood(self, stats, inference_graph=None, viterbi=False, state_path=None, scale=1.):
-        counts = None
+        counts = trans = None
         if inference_graph is None and not viterbi and state_path is None:
             # the reference switches the transition posteriors on when no inference graph is given
             # (hmm.py:76); here: one count per unit, reduced inside the backward sweep
             dev = self.categorical.weights.posterior.params.concentrations.device
             plan = self.graph.plan(n_pdfs=self._emission().Kp)
             if plan.n_units == 0:
-                raise NotImplementedError('unit counts need an aligned left-to-right phone loop (same number of '
-                                          'states in every unit); pass inference_graph= for aligned training')
-            counts = torch.zeros(plan.n_units, dtype=f64, device=dev)
+                # units of different lengths (or any other loop the fused reduction has no kernel for): the
+                # ends x starts block of the transition posteriors, as the reference reads it
+                trans = (list(self.end_pdf.values()), list(self.start_pdf.values()))
+            else:
+                counts = torch.zeros(plan.n_units, dtype=f64, device=dev)
         retval = super().expected_log_likelihood(stats, inference_graph=inference_graph, viterbi=viterbi,
-                                                 state_path=state_path, scale=scale, _unit_counts=counts)
+                                                 state_path=state_path, scale=scale, _unit_counts=counts,
+                                                 _trans=trans)
         if counts is not None:
             self.cache['unit_counts'] = counts
-        elif inference_graph is None:
+        elif inference_graph is None and 'path' in self.cache:
             self.cache['unit_path'] = self.cache['path']
         return retval
 
@@ -746,6 +774,10 @@ class PhoneLoop(HMM):
             su = self.graph.n_states // counts.numel()
             order = torch.as_tensor([s // su for s in start_idxs], device=counts.device)
             phone_resps = counts[order]
+        elif 'trans_resps' in self.cache:
+            block = self.cache['trans_resps'].to(f64)            # [N - n_utts, ends, starts]
+            first = self.cache['first_state_post'].to(f64)
+            phone_resps = block.sum(dim=(0, 1)) + first[:, torch.as_tensor(start_idxs, device=first.device)].sum(dim=0)
         elif 'unit_path' in self.cache:
             # one-hot transition posteriors of a Viterbi / given path (hmm.py:49-54)
             path = self.cache['unit_path'].long()
@@ -759,4 +791,67 @@ class PhoneLoop(HMM):
         stats_w = phone_resps.clone()
         stats_w[-1] = phone_resps.sum()
         retval[weights] = stats_w
+        return retval
+
+
+# ---------------------------------------------------------------------------------------------
+# BigramPhoneLoop (beer/models/phoneloop.py:105-191)
+# ---------------------------------------------------------------------------------------------
+
+class BigramPhoneLoop(HMM):
+    """Phone loop with a bigram model over the units: one Dirichlet per unit end over the unit starts.
+    Its statistics are the ends x starts block of the transition posteriors (phoneloop.py:175-186), which
+    `csrc/transitions.cu` produces directly ([T-1, P, P] instead of the reference's [T-1, K, K])."""
+
+    @classmethod
+    def create(cls, graph, start_pdf, end_pdf, modelset, categoricalset=None, prior_strength=1.0):
+        if categoricalset is None:
+            ref = modelset.mean_field_factorization()[0][0].posterior.params.mean
+            n = len(start_pdf)
+            weights = torch.ones(n, n, dtype=f32, device=ref.device) / n
+            categoricalset = CategoricalSet.create(weights, prior_strength)
+        return cls(graph, modelset, start_pdf, end_pdf, categoricalset)
+
+    def __init__(self, graph, modelset, start_pdf, end_pdf, categoricalset):
+        super().__init__(graph, modelset)
+        self.start_pdf = start_pdf
+        self.end_pdf = end_pdf
+        self.categoricalset = categoricalset
+        param = self.categoricalset.mean_field_factorization()[0][0]
+        param.register_callback(self._on_weights_update)
+        self._on_weights_update()
+
+    def _on_weights_update(self):
+        """phoneloop.py:145-157.  The reference evaluates the set on eye(P), which is indexed
+        [class, model], and writes row i onto the arcs out of unit i's end state: arc (end_i -> start_m)
+        gets E[ln pi_m(i)].  Kept as it is (results identical to the reference)."""
+        logw = self.categoricalset.weights.posterior.expected_log_weights()       # [model, class]
+        trans = self.graph.trans_log_probs
+        logw = logw.to(device=trans.device, dtype=trans.dtype)
+        start_idxs = [value for value in self.start_pdf.values()]
+        for i, end_idx in enumerate(self.end_pdf.values()):
+            loop_prob = trans[end_idx, end_idx].exp()
+            trans[end_idx, start_idxs] = (1 - loop_prob).log() + logw[:, i]
+
+    def mean_field_factorization(self):
+        return _merge_groups(self.modelset.mean_field_factorization(), self.categoricalset.mean_field_factorization())
+
+    def expected_log_likelihood(self, stats, inference_graph=None, viterbi=False, state_path=None, scale=1.):
+        trans = None
+        if inference_graph is None:
+            trans = (list(self.end_pdf.values()), list(self.start_pdf.values()))
+        return super().expected_log_likelihood(stats, inference_graph=inference_graph, viterbi=viterbi,
+                                               state_path=state_path, scale=scale, _trans=trans)
+
+    def accumulate(self, stats, parent_msg=None):
+        retval = super().accumulate(stats, parent_msg)
+        weights = self.categoricalset.weights
+        conc = weights.posterior.params.concentrations
+        if 'trans_resps' in self.cache:
+            w_stats = self.cache['trans_resps'].to(f64).sum(dim=0)     # [ends, starts]
+            w_stats[:, -1] = w_stats.sum(dim=-1)                       # dirichlet.py:18-21
+        else:
+            # forced alignments: the transitions are not trained (phoneloop.py:187-190)
+            w_stats = torch.zeros(conc.shape, dtype=f64, device=conc.device)
+        retval[weights] = w_stats
         return retval

@@ -208,6 +208,24 @@ def hmm_forward_backward(plan, pdf_llh, frame_ref, utt_off, scale=1.0, want_stat
                 utt_logz=utt_logz, workspace=workspace)
 
 
+def hmm_transition_posteriors(pdf_llh, state_post, utt_off, log_init, log_trans, pdf_map=None, scale=1.0, rows=None,
+                              cols=None):
+    """Per-step normalised transition posteriors [N - n_utts, R, C] of a ragged batch (graph.py:308-323);
+    `rows` / `cols` (int32 state ids) keep a sub-block, e.g. unit ends x unit starts."""
+    lib = require_cuda()
+    N, K = state_post.shape
+    n_utts = utt_off.numel() - 1
+    R = K if rows is None else rows.numel()
+    Cn = K if cols is None else cols.numel()
+    xi = torch.empty(max(N - n_utts, 0), R, Cn, device=pdf_llh.device, dtype=f32)
+    _lib.check(lib.beer_hmm_transition_posteriors(
+        _p(pdf_llh, f32), pdf_llh.stride(0), _p(pdf_map, i32, True), float(scale), _p(log_init, f32),
+        _p(log_trans, f32), K, _p(state_post, f32), _p(utt_off, i64), n_utts, _p(rows, i32, True),
+        0 if rows is None else R, _p(cols, i32, True), 0 if cols is None else Cn, _p(xi, f32), _stream()),
+        'beer_hmm_transition_posteriors')
+    return xi
+
+
 def hmm_viterbi(plan, pdf_llh, utt_off, scale=1.0, workspace=None):
     """Best state path (int32 [N]) of every utterance of a ragged batch."""
     lib = require_cuda()

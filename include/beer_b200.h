@@ -166,6 +166,19 @@ BEER_API int beer_hmm_viterbi(const beer_graph_plan* plan, const float* pdf_llh,
                      const int64_t* utt_off, int n_utts, float scale, int32_t* path,
                      void* workspace, void* stream);
 
+/* Transition posteriors, per-step normalised with NaN -> 0: CompiledGraph.posteriors(trans_posteriors=True)
+ * (beer/graph.py:308-323), or only the rows / columns a caller keeps: BigramPhoneLoop.accumulate reads
+ * xi[:, ends, starts] (beer/models/phoneloop.py:175-186).  Dense O(T R C) output by definition: the API-parity
+ * path for small graphs (K <= 1024); PhoneLoop training uses the fused unit counts of
+ * beer_hmm_forward_backward_units instead.
+ *   pdf_llh [N, ld_pdf], pdf_map [K] int32 or NULL (identity), log_init [K], log_trans [K, K] (natural log),
+ *   state_post [N, K] from beer_hmm_forward_backward*, rows [n_rows] / cols [n_cols] int32 state ids or NULL
+ *   (all K), xi [N - n_utts, R, C] <- utterance u starts at row utt_off[u] - u. */
+BEER_API int beer_hmm_transition_posteriors(const float* pdf_llh, int64_t ld_pdf, const int32_t* pdf_map, float scale,
+                                   const float* log_init, const float* log_trans, int K, const float* state_post,
+                                   const int64_t* utt_off, int n_utts, const int32_t* rows, int n_rows,
+                                   const int32_t* cols, int n_cols, float* xi, void* stream);
+
 /* KC: posterior-weighted sufficient statistics, accumulated (+=) into a caller-zeroed
  * fp64 buffer.  Replaces the joint responsibilities of MixtureSet.accumulate
  * (beer/models/mixtureset.py:100-112) and NormalSet.accumulate

@@ -451,6 +451,26 @@ def phoneloop_update_graph(trans_log, conc, start_idxs, end_idxs):
     return trans_log
 
 
+def bigram_counts(xi, start_idxs, end_idxs):
+    """BigramPhoneLoop.accumulate (phoneloop.py:175-186): the (T-1, ends, starts) block of the
+    transition posteriors -> CategoricalSet statistics, summed over time (categoricalset.py:54-55)."""
+    block = xi[:, :, start_idxs][:, end_idxs, :]
+    return categorical_sufficient_statistics(block).sum(axis=0)
+
+
+def bigram_update_graph(trans_log, conc, start_idxs, end_idxs):
+    """BigramPhoneLoop._on_weights_update (phoneloop.py:145-157), in place.  Reference quirk kept:
+    `expected_log_likelihood(eye(P))` is indexed [class, model], and the reference writes row i of it
+    onto the arcs out of unit i's end state, i.e. arc (end_i -> start_m) gets E[ln pi_m(i)] -- the
+    transpose of the matrix the statistics of `bigram_counts` (model = end unit, class = start unit)
+    are accumulated for."""
+    logw = np.stack([categorical_log_weights(c) for c in conc]).astype(trans_log.dtype)   # [model, class]
+    for i, e in enumerate(end_idxs):
+        loop = np.exp(trans_log[e, e])
+        trans_log[e, start_idxs] = np.log(1 - loop) + logw[:, i]
+    return trans_log
+
+
 def gmm_estep(X, ng_post, dir_post, labels=None):
     """Mixture E-step + accumulate (mixture.py:70-102)."""
     stats = normal_diag_sufficient_statistics(X)

@@ -328,6 +328,80 @@ def gold_phoneloop_mixtureset():
     save('phoneloop_mixtureset', **out)
 
 
+def phone_loop_uneven(n_states_list):
+    """phone_loop() with a different number of states per unit."""
+    g = beer.graph.Graph()
+    g.start_state = g.add_state()
+    g.end_state = g.add_state()
+    pivot = g.add_state()
+    us = [g.add_state() for _ in n_states_list]
+    g.add_arc(g.start_state, pivot)
+    g.add_arc(pivot, g.end_state)
+    for s in us:
+        g.add_arc(pivot, s)
+        g.add_arc(s, pivot)
+    g.normalize()
+    start_pdf, end_pdf, first = {}, {}, 0
+    for i, (s, n) in enumerate(zip(us, n_states_list)):
+        g.replace_state(s, unit_graph(n, first))
+        start_pdf[f'u{i}'] = first
+        end_pdf[f'u{i}'] = first + n - 1
+        first += n
+    g.normalize()
+    return g, start_pdf, end_pdf
+
+
+def gold_bigram_phoneloop():
+    """BigramPhoneLoop (phoneloop.py:105-191) and a PhoneLoop whose units have different lengths: both read
+    the dense transition posteriors (hmm.py:76, graph.py:308-323)."""
+    seed, D = 11, 3
+    rng = np.random.default_rng(seed)
+    torch.manual_seed(seed)
+    out = {}
+    for tag, sizes, cls in (('bg', [2, 2, 2], beer.BigramPhoneLoop), ('un', [2, 3, 1], beer.PhoneLoop)):
+        g, start_pdf, end_pdf = phone_loop_uneven(sizes)
+        cg = g.compile()
+        K = cg.n_states
+        ns = beer.NormalSet.create(torch.zeros(D), torch.ones(D), size=K, prior_strength=1., noise_std=1.,
+                                   cov_type='diagonal')
+        out.update(graph_arrays(cg, f'{tag}_g0_'))      # before the weight callback rewrites the end -> start arcs
+        pl = cls.create(cg, start_pdf, end_pdf, ns, prior_strength=1.).double()
+        means = 2.0 * rng.standard_normal((K, D))
+        X1 = sample_from_graph(rng, cg, means, 40)
+        X2 = sample_from_graph(rng, cg, means, 31)
+        p = ns.means_precisions
+        wu = (pl.categoricalset if cls is beer.BigramPhoneLoop else pl.categorical).weights
+        start_idxs, end_idxs = list(start_pdf.values()), list(end_pdf.values())
+        out.update({f'{tag}_X1': X1, f'{tag}_X2': X2, f'{tag}_start_idxs': np.asarray(start_idxs),
+                    f'{tag}_end_idxs': np.asarray(end_idxs), **graph_arrays(pl.graph, f'{tag}_g_'),
+                    **ng_params(p.prior, f'{tag}_prior_'), **ng_params(p.posterior, f'{tag}_post0_'),
+                    f'{tag}_u_dprior': npy(wu.prior.params.concentrations),
+                    f'{tag}_u_dpost0': npy(wu.posterior.params.concentrations)})
+        Xt = torch.from_numpy(X1).double()
+        stats = pl.sufficient_statistics(Xt)
+        exp_llh = pl.expected_log_likelihood(stats)
+        xi = pl.cache['trans_resps']
+        out.update({f'{tag}_exp_llh': npy(exp_llh), f'{tag}_gamma': npy(pl.cache['resps']), f'{tag}_xi': npy(xi),
+                    f'{tag}_xi_block': npy(xi[:, :, start_idxs][:, end_idxs, :])})
+        acc = pl.accumulate(stats)
+        out.update({f'{tag}_acc_normal': npy(acc[p]), f'{tag}_acc_units': npy(acc[wu])})
+        pl.clear_cache()
+        optim = beer.VBConjugateOptimizer(pl.conjugate_bayesian_parameters(keepgroups=True), lrate=1.)
+        N = len(X1) + len(X2)
+        elbos = []
+        for it in range(2):
+            optim.init_step()
+            elbo = beer.evidence_lower_bound(datasize=N)
+            for X in (X1, X2):
+                elbo += beer.evidence_lower_bound(pl, torch.from_numpy(X).double(), datasize=N)
+            elbo.backward()
+            elbos.append(float(elbo))
+            optim.step()
+        out.update({f'{tag}_elbos': np.asarray(elbos), f'{tag}_trans2': npy(pl.graph.trans_log_probs),
+                    f'{tag}_u_dpost2': npy(wu.posterior.params.concentrations), **ng_params(p.posterior, f'{tag}_post2_')})
+    save('bigram_phoneloop', **out)
+
+
 # ---------------------------------------------------------------------------
 def gold_dense_ergodic():
     """Dense ergodic transitions as in tests/test_hmm.py:149-151, with exact
@@ -398,6 +472,7 @@ if __name__ == '__main__':
     hmm_case('hmm_scaled', n_units=4, n_states=3, D=6, T=45, seed=4, scale=0.5)
     hmm_case('hmm_cfg2_T200', n_units=25, n_states=4, D=40, T=200, seed=5, n_iter=2)
     gold_phoneloop_mixtureset()
+    gold_bigram_phoneloop()
     gold_dense_ergodic()
     gold_graph_compile()
     gold_fbank()

@@ -312,3 +312,78 @@ def test_phoneloop_unit_counts_and_training_loop(beer):
         for got, pname in zip(get_ng(ns.means_precisions.posterior), ('mean', 'scale', 'shape', 'rates')):
             want = g[f'{tag}_post3_' + pname]
             np.testing.assert_allclose(got.reshape(want.shape), want, rtol=3e-4, atol=3e-4)
+
+
+def test_compiled_graph_transition_posteriors(beer):
+    """CompiledGraph.posteriors(llhs, trans_posteriors=True) (graph.py:289-326): dense ergodic graph with an
+    unreachable state (the reference's NaN -> 0), and the full (T-1, K, K) tensor of a phone loop."""
+    g = load_golden('dense_ergodic')
+    cg = compiled(beer, g)
+    (gamma, xi), lognorm = cg.posteriors(t32(g['llhs']), trans_posteriors=True)
+    assert xi.shape == (len(g['llhs']) - 1, cg.n_states, cg.n_states)
+    assert np.abs(gamma.double().cpu().numpy() - g['gamma']).max() <= 1e-5
+    assert np.abs(xi.double().sum(dim=0).cpu().numpy() - g['xi_sum']).max() <= 2e-5 * len(g['llhs'])
+    np.testing.assert_allclose(xi.double().sum(dim=(1, 2)).cpu().numpy(), 1.0, atol=1e-5)
+    cg2 = compiled(beer, g, 'g2_')
+    (_, xi2), _ = cg2.posteriors(t32(g['llhs2']), trans_posteriors=True)
+    assert torch.isfinite(xi2).all() and (xi2[:, :, 6] == 0).all()          # unreachable destination
+    b = load_golden('bigram_phoneloop')
+    for tag in ('bg', 'un'):
+        cgb = compiled(beer, b, tag + '_g_')
+        ns = normalset(beer, b, cgb.n_states, b[tag + '_X1'].shape[1], prior=tag + '_prior_', post=tag + '_post0_')
+        llhs = ns.expected_log_likelihood(ns.sufficient_statistics(t32(b[tag + '_X1'])))
+        (gam, x), _ = cgb.posteriors(llhs[:, [int(i) for i in b[tag + '_g_map']]], trans_posteriors=True)
+        assert np.abs(gam.double().cpu().numpy() - b[tag + '_gamma']).max() <= 1e-5
+        assert np.abs(x.double().cpu().numpy() - b[tag + '_xi']).max() <= 1e-5
+
+
+@pytest.mark.parametrize('tag', ['bg', 'un'])
+def test_bigram_and_uneven_phoneloop(beer, tag):
+    """BigramPhoneLoop (phoneloop.py:105-191) and a PhoneLoop whose units have different lengths: the models that
+    read the transition posteriors themselves (golden 'bigram_phoneloop', two VB iterations over two utterances)."""
+    g = load_golden('bigram_phoneloop')
+    cg = compiled(beer, g, tag + '_g0_')          # the graph before the model's weight callback ran
+    D = g[tag + '_X1'].shape[1]
+    ns = normalset(beer, g, cg.n_states, D, prior=tag + '_prior_', post=tag + '_post0_')
+    start_pdf = {f'u{i}': int(s) for i, s in enumerate(g[tag + '_start_idxs'])}
+    end_pdf = {f'u{i}': int(s) for i, s in enumerate(g[tag + '_end_idxs'])}
+    cls = beer.BigramPhoneLoop if tag == 'bg' else beer.PhoneLoop
+    pl = cls.create(cg, start_pdf, end_pdf, ns, prior_strength=1.)
+    wu = (pl.categoricalset if tag == 'bg' else pl.categorical).weights
+    np.testing.assert_allclose(wu.posterior.params.concentrations.cpu().numpy(), g[tag + '_u_dpost0'], rtol=1e-6)
+    np.testing.assert_allclose(pl.graph.trans_log_probs.numpy(), g[tag + '_g_trans'], rtol=1e-5, atol=1e-6)
+    X1, X2 = t32(g[tag + '_X1']), t32(g[tag + '_X2'])
+    stats = pl.sufficient_statistics(X1)
+    exp_llh = pl.expected_log_likelihood(stats)
+    np.testing.assert_allclose(exp_llh.double().cpu().numpy(), g[tag + '_exp_llh'], rtol=1e-5, atol=1e-4)
+    assert np.abs(pl.cache['trans_resps'].double().cpu().numpy() - g[tag + '_xi_block']).max() <= 1e-5
+    acc = pl.accumulate(stats)
+    np.testing.assert_allclose(acc[wu].cpu().numpy(), g[tag + '_acc_units'], rtol=2e-5, atol=2e-5)
+    want = g[tag + '_acc_normal']
+    assert np.abs(acc[ns.means_precisions].cpu().numpy() - want).max() <= 3e-5 * np.abs(want).max()
+    pl.clear_cache()
+    # Viterbi training: one-hot transition posteriors (hmm.py:49-54) sum to T - 1 transitions in the block at most
+    pl.expected_log_likelihood(stats, viterbi=True)
+    assert pl.accumulate(stats)[wu].sum().item() <= 2 * (len(X1) - 1) + 2
+    pl.clear_cache()
+
+    optim = beer.VBConjugateOptimizer(pl.conjugate_bayesian_parameters(keepgroups=True), lrate=1.)
+    N = len(X1) + len(X2)
+    elbos = []
+    for _ in range(2):
+        optim.init_step()
+        elbo = beer.evidence_lower_bound(datasize=N)
+        for X in (X1, X2):
+            elbo += beer.evidence_lower_bound(pl, X, datasize=N)
+        elbo.backward()
+        elbos.append(float(elbo))
+        optim.step()
+    np.testing.assert_allclose(elbos, g[tag + '_elbos'], rtol=1e-5)
+    np.testing.assert_allclose(wu.posterior.params.concentrations.cpu().numpy(), g[tag + '_u_dpost2'], rtol=2e-4)
+    got, want = pl.graph.trans_log_probs.numpy(), g[tag + '_trans2']
+    fin = np.isfinite(want)
+    assert np.array_equal(np.isfinite(got), fin)
+    np.testing.assert_allclose(got[fin], want[fin], rtol=2e-4, atol=2e-4)
+    for gotp, pname in zip(get_ng(ns.means_precisions.posterior), ('mean', 'scale', 'shape', 'rates')):
+        wantp = g[tag + '_post2_' + pname]
+        np.testing.assert_allclose(gotp.reshape(wantp.shape), wantp, rtol=3e-4, atol=3e-4)

@@ -215,6 +215,44 @@ def test_phoneloop_mixtureset():
     np.testing.assert_allclose(dposts[1], g['g2_dpost3'], rtol=1e-8)
 
 
+def test_bigram_and_uneven_phoneloop():
+    """Models that read the dense transition posteriors: BigramPhoneLoop (phoneloop.py:105-191) and a
+    PhoneLoop whose units differ in length, two VB iterations over two utterances each."""
+    g = load_golden('bigram_phoneloop')
+    for tag in ('bg', 'un'):
+        gr = graph(g, tag + '_g_')
+        starts, ends = list(g[tag + '_start_idxs']), list(g[tag + '_end_idxs'])
+        post, prior = ng(g, tag + '_post0_'), ng(g, tag + '_prior_')
+        upost, uprior = g[tag + '_u_dpost0'], g[tag + '_u_dprior']
+        counts = (lambda r: O.bigram_counts(r['xi'], starts, ends)) if tag == 'bg' else \
+            (lambda r: O.phoneloop_counts(r['gamma'], r['xi'], starts, ends))
+        regraph = O.bigram_update_graph if tag == 'bg' else O.phoneloop_update_graph
+        r = O.hmm_estep(g[tag + '_X1'].astype(np.float64), post, None, gr, trans_posteriors=True)
+        np.testing.assert_allclose(r['gamma'], g[tag + '_gamma'], rtol=1e-7, atol=1e-12)
+        np.testing.assert_allclose(r['xi'], g[tag + '_xi'], rtol=1e-7, atol=1e-12)
+        np.testing.assert_allclose(r['exp_llh'], g[tag + '_exp_llh'], rtol=1e-9)
+        np.testing.assert_allclose(r['acc_normal'], g[tag + '_acc_normal'], rtol=1e-7, atol=1e-9)
+        np.testing.assert_allclose(counts(r), g[tag + '_acc_units'], rtol=1e-7, atol=1e-12)
+        trans = gr[2].copy()
+        N = len(g[tag + '_X1']) + len(g[tag + '_X2'])
+        elbos = []
+        for _ in range(2):
+            kl = O.normalgamma_kl(post, prior).sum() + O.dirichlet_kl(upost, uprior).sum()
+            tot, acc, du, frames = 0., 0., 0., 0
+            for X in (g[tag + '_X1'], g[tag + '_X2']):
+                r = O.hmm_estep(X.astype(np.float64), post, None, (gr[0], gr[1], trans, gr[3]), trans_posteriors=True)
+                tot += O.elbo_value(r['exp_llh'], kl, N)
+                acc, du, frames = acc + r['acc_normal'], du + counts(r), frames + len(X)
+            elbos.append(tot)
+            post = O.natural_grad_update_normalgamma(prior, post, N / frames * acc, 1.)
+            upost = O.natural_grad_update_dirichlet(uprior, upost, N / frames * du, 1.)
+            trans = regraph(trans, upost, starts, ends)
+        np.testing.assert_allclose(elbos, g[tag + '_elbos'], rtol=1e-9)
+        np.testing.assert_allclose(upost, g[tag + '_u_dpost2'], rtol=1e-8)
+        np.testing.assert_allclose(trans, g[tag + '_trans2'], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(post[0], g[tag + '_post2_mean'], rtol=1e-7, atol=1e-9)
+
+
 def test_fbank_front_end():
     """beer/features.py restated (fbank, create_fbank, add_deltas) against the live-reference golden."""
     g = load_golden('fbank')
