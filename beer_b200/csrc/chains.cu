@@ -1,0 +1,358 @@
+// KB for per-utterance alignment graphs (aligned training: `beer hmm accumulate --alis`,
+// beer/cli/subcommands/hmm/accumulate.py:47-57 -> HMM.expected_log_likelihood(inference_graph=...)
+// beer/models/hmm.py:73-92).  An alignment graph (mkaligraph.py:18-39) compiles to a left-to-right
+// CHAIN: state j has a self loop and one arc to state j + 1, the sequence starts in state 0 and
+// ends in the last state.  Every utterance of a batch brings its own chain (own length, own pdf
+// ids, own weights), stored back to back:
+//
+//   chain_off [n_utts + 1], and per state: pdf id, ln a(j,j), ln a(j,j+1) (last state: the final weight)
+//
+// One warp per utterance, lane l owns states l*S .. l*S+S-1 in registers; the only exchange between
+// lanes is the neighbour's edge state (one shuffle per frame and direction) and the per-frame
+// normaliser (one redux).  log2 domain, renormalised every frame, like the other scan kernels.
+// The llhs are gathered through the chain's pdf ids by 4-byte cp.async into a per-warp ring; the
+// posteriors are scatter-added onto pdf ids (modelset.py:148-154: a pdf may occur several times in a chain).
+#include "common.cuh"
+#include "../../include/beer_b200.h"
+
+namespace beer {
+namespace {
+
+constexpr int CH_WARPS = 4;
+
+struct ChainArgs {
+    const float* pl;
+    int64_t ld;
+    const float* frame_ref;
+    const int64_t* utt_off;
+    int n_utts;
+    float scale;
+    const int64_t* chain_off;
+    const int32_t* pdf;
+    const float* lself;
+    const float* lnext;
+    const float* linit;      // [n_utts] ln weight of entering state 0
+    float* la_ws;            // [N, Kw]
+    int Kw;
+    float* state_post;       // [N, Kw] or null (row stride Kw: chains differ in length)
+    float* pdf_post;         // [N, ld_post], zeroed by the caller
+    int64_t ld_post;
+    float* frame_exp_llh;
+    double* utt_exp_llh;
+    double* utt_logz;
+};
+
+__device__ __forceinline__ float lse2c(float a, float b) {
+    const float mx = fmaxf(a, b), mn = fminf(a, b);
+    const float d = fmaxf(mn - mx, -1000.f);
+    return mx + lg2(1.f + ex2(d));
+}
+
+template <int S>
+__global__ void __launch_bounds__(CH_WARPS * 32) hmm_fb_chain_kernel(ChainArgs a) {
+    static_assert(S % 4 == 0, "vector rows");
+    constexpr int PF = (S <= 4) ? 6 : (S <= 8 ? 4 : 3);
+    constexpr int ROW = 32 * S;
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* ring_p = smem + (size_t)warp * (2 * PF * ROW);
+    float* ring_a = ring_p + PF * ROW;
+    const float p_scale = a.scale * kLog2e;
+    const int gwarp = blockIdx.x * CH_WARPS + warp, nwarps = gridDim.x * CH_WARPS;
+
+    for (int u = gwarp; u < a.n_utts; u += nwarps) {
+        const int64_t t0 = a.utt_off[u];
+        const int T = (int)(a.utt_off[u + 1] - t0);
+        const int64_t c0 = a.chain_off[u];
+        const int L = (int)(a.chain_off[u + 1] - c0);
+        if (T <= 0 || L <= 0) {
+            if (lane == 0) {
+                a.utt_exp_llh[u] = 0.0;
+                if (a.utt_logz) a.utt_logz[u] = 0.0;
+            }
+            continue;
+        }
+        // this lane's states
+        int pdf[S];
+        float w_self[S], w_in[S];
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+            const int k = lane * S + j;
+            pdf[j] = (k < L) ? __ldg(a.pdf + c0 + k) : 0;
+            w_self[j] = (k < L) ? __ldg(a.lself + c0 + k) * kLog2e : kNegInf;
+            w_in[j] = (k < L && k > 0) ? __ldg(a.lnext + c0 + k - 1) * kLog2e : kNegInf;
+        }
+        const bool own = lane * S < L;
+        for (int i = lane; i < 2 * PF * ROW; i += 32) ring_p[i] = 0.f;   // states past L stay finite
+        __syncwarp();
+        const float* pl_u = a.pl + (size_t)t0 * a.ld;
+        float* la_u = a.la_ws + (size_t)t0 * a.Kw;
+
+        auto gather = [&](float* slot, const float* row) {
+            if (!own) return;
+#pragma unroll
+            for (int j = 0; j < S; ++j)
+                if (lane * S + j < L) cp_async4(slot + lane * S + j, row + pdf[j]);
+        };
+        auto copy_row = [&](float* slot, const float* row) {
+            if (!own) return;
+#pragma unroll
+            for (int v = 0; v < S / 4; ++v)
+                if (lane * S + 4 * v < L) cp_async16(slot + lane * S + 4 * v, row + lane * S + 4 * v);
+        };
+        auto read_row = [&](const float* slot, float* out) {
+#pragma unroll
+            for (int v = 0; v < S / 4; ++v) {
+                const float4 q = reinterpret_cast<const float4*>(slot + lane * S)[v];
+                out[4 * v] = q.x; out[4 * v + 1] = q.y; out[4 * v + 2] = q.z; out[4 * v + 3] = q.w;
+            }
+        };
+        auto write_row = [&](float* row, const float* v) {
+            if (!own) return;
+#pragma unroll
+            for (int q = 0; q < S / 4; ++q)
+                if (lane * S + 4 * q < L)
+                    reinterpret_cast<float4*>(row + lane * S)[q] =
+                        make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        };
+
+        // ------------------------------ forward ------------------------------
+        for (int r = 0; r < PF; ++r) {
+            if (r < T) gather(ring_p + r * ROW, pl_u + (size_t)r * a.ld);
+            cp_async_commit();
+        }
+        float cur[S];
+        double logz2 = 0.0;
+        float lz = 0.f;
+        int slot = 0;
+        for (int t = 0; t < T; ++t) {
+            cp_async_wait<PF - 1>();
+            float p[S];
+            float* ring_slot = ring_p + slot * ROW;
+            read_row(ring_slot, p);
+            if (t + PF < T) gather(ring_slot, pl_u + (size_t)(t + PF) * a.ld);
+            cp_async_commit();
+            slot = (slot + 1 == PF) ? 0 : slot + 1;
+            if (t == 0) {
+#pragma unroll
+                for (int j = 0; j < S; ++j)
+                    cur[j] = (lane == 0 && j == 0) ? fmaf(p[0], p_scale, __ldg(a.linit + u) * kLog2e) : kNegInf;
+            } else {
+                float up = __shfl_up_sync(0xffffffffu, cur[S - 1], 1);
+                if (lane == 0) up = kNegInf;
+#pragma unroll
+                for (int j = S - 1; j >= 0; --j) {
+                    const float prev = (j == 0) ? up : cur[j == 0 ? 0 : j - 1];
+                    cur[j] = fmaf(p[j], p_scale, lse2c(cur[j] + w_self[j], prev + w_in[j]));
+                }
+            }
+            float mx = cur[0];
+#pragma unroll
+            for (int j = 1; j < S; ++j) mx = fmaxf(mx, cur[j]);
+            mx = warp_max(mx);
+            const float mxs = (mx == kNegInf) ? 0.f : mx;
+            lz += mxs;
+            if ((t & 15) == 15) {
+                logz2 += (double)lz;
+                lz = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < S; ++j) cur[j] -= mxs;
+            write_row(la_u + (size_t)t * a.Kw, cur);
+        }
+        cp_async_wait<0>();
+        logz2 += (double)lz;
+        // final weight: the "next" arc of the last state
+        float b_start[S];
+#pragma unroll
+        for (int j = 0; j < S; ++j)
+            b_start[j] = (lane * S + j == L - 1) ? __ldg(a.lnext + c0 + L - 1) * kLog2e : kNegInf;
+        if (a.utt_logz != nullptr) {
+            float m = kNegInf;
+#pragma unroll
+            for (int j = 0; j < S; ++j) m = fmaxf(m, cur[j] + b_start[j]);
+            m = warp_max(m);      // a single state carries it
+            double rs = 0.0;
+            if (a.frame_ref != nullptr)
+                for (int t = lane; t < T; t += 32) rs += (double)a.frame_ref[t0 + t];
+            rs = warp_sum(rs);
+            if (lane == 0) a.utt_logz[u] = (logz2 + (double)m) * (double)kLn2 + (double)a.scale * rs;
+        }
+
+        // ------------------------------ backward -----------------------------
+        __threadfence_block();   // this warp's la stores -> visible to its own async copies
+        __syncwarp();
+        for (int r = 0; r < PF; ++r) {
+            const int t = T - 1 - r;
+            if (t >= 0) {
+                gather(ring_p + r * ROW, pl_u + (size_t)t * a.ld);
+                copy_row(ring_a + r * ROW, la_u + (size_t)t * a.Kw);
+            }
+            cp_async_commit();
+        }
+        float lb[S];
+        {
+            float m = kNegInf;
+#pragma unroll
+            for (int j = 0; j < S; ++j) m = fmaxf(m, b_start[j]);
+            m = warp_max(m);
+            const float ms = (m == kNegInf) ? 0.f : m;
+#pragma unroll
+            for (int j = 0; j < S; ++j) lb[j] = b_start[j] - ms;
+        }
+        float ell = 0.f;
+        double ell_d = 0.0;
+        slot = 0;
+        for (int i = 0; i < T; ++i) {
+            const int t = T - 1 - i;
+            cp_async_wait<PF - 1>();
+            float p[S], la[S];
+            read_row(ring_p + slot * ROW, p);
+            read_row(ring_a + slot * ROW, la);
+            if (t - PF >= 0) {
+                gather(ring_p + slot * ROW, pl_u + (size_t)(t - PF) * a.ld);
+                copy_row(ring_a + slot * ROW, la_u + (size_t)(t - PF) * a.Kw);
+            }
+            cp_async_commit();
+            slot = (slot + 1 == PF) ? 0 : slot + 1;
+
+            float v[S], m = kNegInf;
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                v[j] = (lane * S + j < L) ? la[j] + lb[j] : kNegInf;
+                m = fmaxf(m, v[j]);
+            }
+            m = warp_max(m);
+            const float ms = (m == kNegInf) ? 0.f : m;
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                v[j] = ex2(v[j] - ms);
+                sum += v[j];
+            }
+            sum = warp_sum(sum);
+            const float inv = (sum > 0.f) ? __fdividef(1.f, sum) : 0.f;
+            float fe = 0.f;
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                v[j] *= inv;
+                fe = fmaf(p[j], v[j], fe);
+            }
+            ell += fe;
+            if ((i & 31) == 31) {
+                ell_d += (double)ell;
+                ell = 0.f;
+            }
+            if (a.frame_exp_llh != nullptr) {
+                const float f = warp_sum(fe);
+                if (lane == 0) {
+                    const float r = (a.frame_ref != nullptr) ? a.scale * a.frame_ref[t0 + t] : 0.f;
+                    a.frame_exp_llh[t0 + t] = f * p_scale * kLn2 + r;
+                }
+            }
+            if (a.state_post != nullptr) write_row(a.state_post + (size_t)(t0 + t) * a.Kw, v);
+            if (a.pdf_post != nullptr) {
+                float* prow = a.pdf_post + (size_t)(t0 + t) * a.ld_post;
+#pragma unroll
+                for (int j = 0; j < S; ++j)
+                    if (v[j] != 0.f) atomicAdd(prow + pdf[j], a.scale * v[j]);
+            }
+            if (t == 0) break;
+            float delta[S];
+#pragma unroll
+            for (int j = 0; j < S; ++j) delta[j] = fmaf(p[j], p_scale, lb[j]);
+            float dn = __shfl_down_sync(0xffffffffu, delta[0] + w_in[0], 1);   // into the next lane's first state
+            if (lane == 31) dn = kNegInf;
+            float mb = kNegInf;
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                const float nxt = (j == S - 1) ? dn : delta[j == S - 1 ? j : j + 1] + w_in[j == S - 1 ? j : j + 1];
+                lb[j] = lse2c(delta[j] + w_self[j], nxt);
+                mb = fmaxf(mb, lb[j]);
+            }
+            mb = warp_max(mb);
+            const float mbs = (mb == kNegInf) ? 0.f : mb;
+#pragma unroll
+            for (int j = 0; j < S; ++j) lb[j] -= mbs;
+        }
+        cp_async_wait<0>();
+        ell_d += (double)ell;
+        ell_d = warp_sum(ell_d);
+        double rs = 0.0;
+        if (a.frame_ref != nullptr)
+            for (int t = lane; t < T; t += 32) rs += (double)a.frame_ref[t0 + t];
+        rs = warp_sum(rs);
+        if (lane == 0) a.utt_exp_llh[u] = ell_d * (double)p_scale * (double)kLn2 + (double)a.scale * rs;
+        __syncwarp();
+    }
+}
+
+template <int S>
+int launch_chain(const ChainArgs& a, cudaStream_t st) {
+    constexpr int PF = (S <= 4) ? 6 : (S <= 8 ? 4 : 3);
+    const size_t smem = sizeof(float) * (size_t)CH_WARPS * (2 * PF * 32 * S);
+    static bool attr_set = false;
+    if (!attr_set) {
+        BEER_CUDA_TRY(cudaFuncSetAttribute(hmm_fb_chain_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem));
+        attr_set = true;
+    }
+    int blocks = (a.n_utts + CH_WARPS - 1) / CH_WARPS;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    hmm_fb_chain_kernel<S><<<blocks, CH_WARPS * 32, smem, st>>>(a);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
+int chain_S(int max_len) {
+    for (int s : {4, 8, 16, 32})
+        if (max_len <= 32 * s) return s;
+    return 0;
+}
+
+}  // namespace
+}  // namespace beer
+
+using namespace beer;
+
+extern "C" {
+
+int beer_hmm_chain_row_stride(int max_chain_len) {
+    const int s = chain_S(max_chain_len);
+    return s ? 32 * s : BEER_ERR_UNSUPPORTED;
+}
+
+int64_t beer_hmm_chain_workspace_bytes(int max_chain_len, int64_t N) {
+    const int s = chain_S(max_chain_len);
+    return s ? (int64_t)N * 32 * s * (int64_t)sizeof(float) : BEER_ERR_UNSUPPORTED;
+}
+
+int beer_hmm_forward_backward_chains(const float* pdf_llh, int64_t ld_pdf, const float* frame_ref, const int64_t* utt_off,
+                                     int n_utts, const int64_t* chain_off, const int32_t* chain_pdf,
+                                     const float* chain_log_self, const float* chain_log_next,
+                                     const float* chain_log_init, int max_chain_len, float scale, float* state_post,
+                                     float* pdf_post, int64_t ld_post, float* frame_exp_llh, double* utt_exp_llh,
+                                     double* utt_logz, void* workspace, void* stream) {
+    if (!pdf_llh || !utt_off || !chain_off || !chain_pdf || !chain_log_self || !chain_log_next || !chain_log_init ||
+        !utt_exp_llh || !workspace || n_utts < 0 || max_chain_len <= 0)
+        return BEER_ERR_ARG;
+    const int S = chain_S(max_chain_len);
+    if (S == 0) return BEER_ERR_UNSUPPORTED;
+    if (n_utts == 0) return BEER_OK;
+    ChainArgs a;
+    a.pl = pdf_llh; a.ld = ld_pdf; a.frame_ref = frame_ref; a.utt_off = utt_off; a.n_utts = n_utts; a.scale = scale;
+    a.chain_off = chain_off; a.pdf = chain_pdf; a.lself = chain_log_self; a.lnext = chain_log_next;
+    a.linit = chain_log_init; a.la_ws = (float*)workspace; a.Kw = 32 * S; a.state_post = state_post;
+    a.pdf_post = pdf_post; a.ld_post = ld_post; a.frame_exp_llh = frame_exp_llh; a.utt_exp_llh = utt_exp_llh;
+    a.utt_logz = utt_logz;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (S) {
+        case 4: return launch_chain<4>(a, st);
+        case 8: return launch_chain<8>(a, st);
+        case 16: return launch_chain<16>(a, st);
+        case 32: return launch_chain<32>(a, st);
+    }
+    return BEER_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

@@ -207,6 +207,11 @@ class VBEngine:
         self.Q = 2 * D + 2
         # flat reduction buffer: [acc (M*Q) | unit counts (P) | sum_u (N/T_u) ell_u | sum_u T_u | n_utts | sum_u ell_u]
         self.units = unit_weights
+        # per-utterance alignment chains (ops.ChainBatch: chain i belongs to utterance i of this shard) or one graph plan
+        self.chains = isinstance(plan, ops.ChainBatch)
+        if self.chains and (unit_weights is not None or plan.n_utts != utts.n_utts):
+            raise ValueError('a ChainBatch needs one chain per utterance of the shard (and trains no unit weights: '
+                             'phoneloop.py:98-100)')
         P = plan.n_units if unit_weights is not None else 0
         if unit_weights is not None and P == 0:
             raise ValueError('unit weights need an aligned left-to-right phone loop (see beer_hmm_forward_backward_units)')
@@ -236,8 +241,8 @@ class VBEngine:
             self._free_valid = [False, False]
         Kp = emission.Kp
         self.pdf_llh = torch.empty(nmax, Kp, device=self.dev, dtype=f32)
-        self.pdf_post = (torch.empty if plan.info['map_identity'] and plan.n_states == Kp else torch.zeros)(
-            nmax, Kp, device=self.dev, dtype=f32)
+        self._nonident = self.chains or not (plan.info['map_identity'] and plan.n_states == Kp)
+        self.pdf_post = (torch.zeros if self._nonident else torch.empty)(nmax, Kp, device=self.dev, dtype=f32)
         self.comp_llh = torch.empty(nmax, M, device=self.dev, dtype=f32) if emission.has_mixtures else None
         self.ws = torch.empty((plan.workspace_bytes(nmax) + 3) // 4, device=self.dev, dtype=f32)
         self.frame_ref = torch.empty(nmax, device=self.dev, dtype=f32)
@@ -280,7 +285,7 @@ class VBEngine:
         if self.units is not None:
             ops.dirichlet_kl(self.units.prior, self.units.post, out=self.kl)
         self.gpu_launches += 2 + 1 + 2 * len(em.weight_groups) + int(em.use_tc)
-        nonident = not (plan.info['map_identity'] and plan.n_states == em.Kp)
+        nonident = self._nonident
         chunks = [c for c in self._chunks if c[3] > 0]
         if self.host_mode and chunks:
             self._issue_copy(chunks[0], 0)
@@ -301,9 +306,14 @@ class VBEngine:
             if nonident:
                 pdf_post.zero_()
             with self._stage('KB_forward_backward'):
-                ops.hmm_forward_backward(plan, pdf_llh, fref, rel, scale=self.scale, workspace=self.ws,
-                                         out_pdf_post=pdf_post, out_utt_exp_llh=self.utt_ell[u0:u1],
-                                         unit_counts=self.unit_counts)
+                if self.chains:
+                    ops.hmm_forward_backward_chains(plan, pdf_llh, fref, rel, scale=self.scale, first_utt=u0,
+                                                    workspace=self.ws, out_pdf_post=pdf_post,
+                                                    out_utt_exp_llh=self.utt_ell[u0:u1])
+                else:
+                    ops.hmm_forward_backward(plan, pdf_llh, fref, rel, scale=self.scale, workspace=self.ws,
+                                             out_pdf_post=pdf_post, out_utt_exp_llh=self.utt_ell[u0:u1],
+                                             unit_counts=self.unit_counts)
             with self._stage('KC_accumulate'):
                 ops.accumulate_stats(X, self.acc, pdf_post=pdf_post,
                                      pdf_llh=pdf_llh if comp is not None else None, comp_llh=comp,

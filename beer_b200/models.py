@@ -628,6 +628,17 @@ class HMM(DiscreteLatentModel):
         X = frames_of(stats, em.D)
         off, utts = _offsets_of(stats, X.shape[0], X.device)
         pdf, comp, fref = em.llh(X)
+        if isinstance(graph, (list, tuple)):
+            # one alignment graph per utterance of the batch (the loop of accumulate.py:47-57 as one launch)
+            if viterbi or state_path is not None or _trans is not None:
+                raise NotImplementedError('a list of inference graphs runs forward-backward only')
+            if len(graph) != off.numel() - 1:
+                raise ValueError('need one inference graph per utterance of the batch')
+            r = ops.hmm_forward_backward_chains(ops.ChainBatch(graph, X.device), pdf, fref, off, scale=scale,
+                                                want_frame_llh=True)
+            self.cache.update(X=X, pdf_post=r['pdf_post'], pdf_llh=pdf, comp_llh=comp, emission=em, scale=scale,
+                              utts=utts, utt_exp_llh=r['utt_exp_llh'])
+            return r['frame_exp_llh']
         plan = graph.plan(n_pdfs=em.Kp)
         if viterbi or state_path is not None:
             if state_path is None:

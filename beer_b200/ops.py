@@ -208,6 +208,88 @@ def hmm_forward_backward(plan, pdf_llh, frame_ref, utt_off, scale=1.0, want_stat
                 utt_logz=utt_logz, workspace=workspace)
 
 
+class ChainBatch:
+    """Per-utterance alignment graphs (mkaligraph.py:18-39) of a ragged batch, as left-to-right chains on the
+    device: `chain_off` [n+1] and per state the pdf id, ln a(j,j) and ln a(j,j+1) (last state: final weight)."""
+
+    def __init__(self, graphs, device):
+        offs, pdf, lself, lnext, linit = [0], [], [], [], []
+        for g in graphs:
+            init, final, trans, pmap = _graph_arrays(g)
+            K = len(init)
+            fin = np.isfinite(trans)
+            band = np.eye(K, dtype=bool) | np.eye(K, k=1, dtype=bool)
+            if K == 0 or (fin & ~band).any() or np.isfinite(init[1:]).any() or np.isfinite(final[:-1]).any() \
+                    or not np.isfinite(init[0]) or not np.isfinite(final[-1]):
+                raise ValueError('not a left-to-right chain (self loop + one arc to the next state, start in the '
+                                 'first state, end in the last): use a GraphPlan for this graph')
+            offs.append(offs[-1] + K)
+            pdf.append(np.asarray(pmap, dtype=np.int32))
+            lself.append(np.diagonal(trans).astype(np.float32))
+            lnext.append(np.concatenate([np.diagonal(trans, 1), final[-1:]]).astype(np.float32))
+            linit.append(init[0])
+        self.n_utts = len(graphs)
+        self.lengths = np.diff(offs)
+        self.max_len = int(self.lengths.max()) if self.n_utts else 0
+        self.n_pdfs = int(max(p.max() for p in pdf)) + 1 if pdf else 0
+        self.chain_off = torch.as_tensor(np.asarray(offs, dtype=np.int64), device=device)
+        self.pdf = torch.as_tensor(np.concatenate(pdf) if pdf else np.zeros(0, np.int32), device=device)
+        self.log_self = torch.as_tensor(np.concatenate(lself) if pdf else np.zeros(0, np.float32), device=device)
+        self.log_next = torch.as_tensor(np.concatenate(lnext) if pdf else np.zeros(0, np.float32), device=device)
+        self.log_init = torch.as_tensor(np.asarray(linit, dtype=np.float32), device=device)
+        self.row_stride = int(_lib.load().beer_hmm_chain_row_stride(max(self.max_len, 1)))
+        if self.row_stride < 0:
+            raise _lib.BeerB200Error('alignment chains longer than 1024 states are not supported')
+
+    def workspace_bytes(self, N):
+        return int(_lib.load().beer_hmm_chain_workspace_bytes(max(self.max_len, 1), int(N)))
+
+
+def _graph_arrays(g):
+    """(init, final, trans, pdf map) of a CompiledGraph-like object or a 4-tuple, as numpy."""
+    if isinstance(g, (tuple, list)):
+        init, final, trans, pmap = g
+    else:
+        init, final, trans, pmap = g.init_log_probs, g.final_log_probs, g.trans_log_probs, g.pdf_id_mapping
+    def to_np(x):
+        return x.detach().cpu().numpy() if torch.is_tensor(x) else np.asarray(x)
+    return to_np(init).astype(np.float32), to_np(final).astype(np.float32), to_np(trans).astype(np.float32), \
+        np.asarray(pmap)
+
+
+def hmm_forward_backward_chains(chains, pdf_llh, frame_ref, utt_off, scale=1.0, first_utt=0, want_state_post=False,
+                                want_frame_llh=False, want_logz=False, workspace=None, out_pdf_post=None,
+                                out_utt_exp_llh=None):
+    """Forward-backward of a ragged batch in which utterance i runs over chain `first_utt + i` of `chains`
+    (hmm.py:73-92 with a per-utterance inference_graph).  `out_pdf_post` must be zero-filled by the caller.
+    -> dict like hmm_forward_backward (state_post has row stride chains.row_stride)."""
+    lib = require_cuda()
+    N = pdf_llh.shape[0]
+    n_utts = utt_off.numel() - 1
+    dev = pdf_llh.device
+    if first_utt + n_utts > chains.n_utts:
+        raise ValueError('more utterances than alignment chains')
+    if pdf_llh.shape[1] < chains.n_pdfs:
+        raise ValueError('pdf_llh has fewer columns than the chains have pdfs')
+    nbytes = chains.workspace_bytes(N)
+    if workspace is None or workspace.numel() * workspace.element_size() < nbytes:
+        workspace = torch.empty((nbytes + 3) // 4, device=dev, dtype=f32)
+    state_post = torch.zeros(N, chains.row_stride, device=dev, dtype=f32) if want_state_post else None
+    pdf_post = out_pdf_post if out_pdf_post is not None else torch.zeros(N, pdf_llh.shape[1], device=dev, dtype=f32)
+    frame = torch.empty(N, device=dev, dtype=f32) if want_frame_llh else None
+    utt_ell = out_utt_exp_llh if out_utt_exp_llh is not None else torch.empty(n_utts, device=dev, dtype=f64)
+    utt_logz = torch.empty(n_utts, device=dev, dtype=f64) if want_logz else None
+    chain_off = chains.chain_off[first_utt:first_utt + n_utts + 1]
+    _lib.check(lib.beer_hmm_forward_backward_chains(
+        _p(pdf_llh, f32), pdf_llh.stride(0), _p(frame_ref, f32, True), _p(utt_off, i64), n_utts, _p(chain_off, i64),
+        _p(chains.pdf, i32), _p(chains.log_self, f32), _p(chains.log_next, f32),
+        _p(chains.log_init[first_utt:first_utt + n_utts], f32), max(chains.max_len, 1), float(scale),
+        _p(state_post, f32, True), _p(pdf_post, f32), pdf_post.stride(0), _p(frame, f32, True), _p(utt_ell, f64),
+        _p(utt_logz, f64, True), _p(workspace), _stream()), 'beer_hmm_forward_backward_chains')
+    return dict(state_post=state_post, pdf_post=pdf_post, frame_exp_llh=frame, utt_exp_llh=utt_ell,
+                utt_logz=utt_logz, workspace=workspace)
+
+
 def hmm_transition_posteriors(pdf_llh, state_post, utt_off, log_init, log_trans, pdf_map=None, scale=1.0, rows=None,
                               cols=None):
     """Per-step normalised transition posteriors [N - n_utts, R, C] of a ragged batch (graph.py:308-323);

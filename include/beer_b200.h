@@ -166,6 +166,24 @@ BEER_API int beer_hmm_viterbi(const beer_graph_plan* plan, const float* pdf_llh,
                      const int64_t* utt_off, int n_utts, float scale, int32_t* path,
                      void* workspace, void* stream);
 
+/* KB for per-utterance alignment graphs (aligned training: accumulate.py:47-57 -> hmm.py:73-92 with
+ * inference_graph=).  An alignment graph (mkaligraph.py:18-39) compiles to a left-to-right chain: state j has a
+ * self loop and one arc to j + 1, the path starts in state 0 and ends in the last state.  Utterance u owns states
+ * chain_off[u] .. chain_off[u+1]-1 of the per-state arrays (device): chain_pdf (pdf id), chain_log_self = ln a(j,j),
+ * chain_log_next = ln a(j,j+1) (last state: the final weight); chain_log_init [n_utts] = ln weight of entering state 0.
+ * Outputs as beer_hmm_forward_backward, except: pdf_post must be ZEROED by the caller (scatter-add, a pdf may occur
+ * several times in a chain) and state_post, if given, has row stride beer_hmm_chain_row_stride(max_chain_len).
+ * max_chain_len <= 1024.  workspace: beer_hmm_chain_workspace_bytes(max_chain_len, N) bytes. */
+BEER_API int beer_hmm_chain_row_stride(int max_chain_len);
+BEER_API int64_t beer_hmm_chain_workspace_bytes(int max_chain_len, int64_t N);
+BEER_API int beer_hmm_forward_backward_chains(const float* pdf_llh, int64_t ld_pdf, const float* frame_ref,
+                                     const int64_t* utt_off, int n_utts, const int64_t* chain_off,
+                                     const int32_t* chain_pdf, const float* chain_log_self,
+                                     const float* chain_log_next, const float* chain_log_init, int max_chain_len,
+                                     float scale, float* state_post, float* pdf_post, int64_t ld_post,
+                                     float* frame_exp_llh, double* utt_exp_llh, double* utt_logz, void* workspace,
+                                     void* stream);
+
 /* Transition posteriors, per-step normalised with NaN -> 0: CompiledGraph.posteriors(trans_posteriors=True)
  * (beer/graph.py:308-323), or only the rows / columns a caller keeps: BigramPhoneLoop.accumulate reads
  * xi[:, ends, starts] (beer/models/phoneloop.py:175-186).  Dense O(T R C) output by definition: the API-parity
