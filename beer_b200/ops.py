@@ -228,15 +228,29 @@ class ChainBatch:
             lself.append(np.diagonal(trans).astype(np.float32))
             lnext.append(np.concatenate([np.diagonal(trans, 1), final[-1:]]).astype(np.float32))
             linit.append(init[0])
-        self.n_utts = len(graphs)
+        self._set(np.asarray(offs, dtype=np.int64), np.concatenate(pdf) if pdf else np.zeros(0, np.int32),
+                  np.concatenate(lself) if pdf else np.zeros(0, np.float32),
+                  np.concatenate(lnext) if pdf else np.zeros(0, np.float32), np.asarray(linit, dtype=np.float32), device)
+
+    @classmethod
+    def from_arrays(cls, chain_off, pdf, log_self, log_next, log_init, device):
+        """The flat form directly (host arrays): no dense K x K matrix per utterance."""
+        self = cls.__new__(cls)
+        self._set(np.asarray(chain_off, dtype=np.int64), np.asarray(pdf, dtype=np.int32),
+                  np.asarray(log_self, dtype=np.float32), np.asarray(log_next, dtype=np.float32),
+                  np.asarray(log_init, dtype=np.float32), device)
+        return self
+
+    def _set(self, offs, pdf, lself, lnext, linit, device):
+        self.n_utts = len(offs) - 1
         self.lengths = np.diff(offs)
         self.max_len = int(self.lengths.max()) if self.n_utts else 0
-        self.n_pdfs = int(max(p.max() for p in pdf)) + 1 if pdf else 0
-        self.chain_off = torch.as_tensor(np.asarray(offs, dtype=np.int64), device=device)
-        self.pdf = torch.as_tensor(np.concatenate(pdf) if pdf else np.zeros(0, np.int32), device=device)
-        self.log_self = torch.as_tensor(np.concatenate(lself) if pdf else np.zeros(0, np.float32), device=device)
-        self.log_next = torch.as_tensor(np.concatenate(lnext) if pdf else np.zeros(0, np.float32), device=device)
-        self.log_init = torch.as_tensor(np.asarray(linit, dtype=np.float32), device=device)
+        self.n_pdfs = int(pdf.max()) + 1 if len(pdf) else 0
+        self.chain_off = torch.as_tensor(offs, device=device)
+        self.pdf = torch.as_tensor(pdf, device=device)
+        self.log_self = torch.as_tensor(lself, device=device)
+        self.log_next = torch.as_tensor(lnext, device=device)
+        self.log_init = torch.as_tensor(linit, device=device)
         self.row_stride = int(_lib.load().beer_hmm_chain_row_stride(max(self.max_len, 1)))
         if self.row_stride < 0:
             raise _lib.BeerB200Error('alignment chains longer than 1024 states are not supported')

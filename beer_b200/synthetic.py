@@ -7,12 +7,15 @@ import torch
 
 from .graph import Graph
 
-__all__ = ['unit_graph', 'phone_loop_graph', 'sample_utterances', 'initial_normal_gamma', 'CONFIGS']
+__all__ = ['unit_graph', 'phone_loop_graph', 'sample_utterances', 'alignment_chains', 'initial_normal_gamma', 'CONFIGS']
 
 # name -> (units, states per unit, Gaussians per state, dim, frames per utterance, utterances per GPU)
 CONFIGS = {
     'cfg2': dict(n_units=25, n_states=4, n_comp=1, dim=40, n_frames=1000, n_utts=4096),
     'cfg3': dict(n_units=250, n_states=4, n_comp=8, dim=40, n_frames=1000, n_utts=1250),
+    # cfg2 trained with one alignment graph per utterance (`beer hmm accumulate --alis`): the unit sequence each
+    # utterance was sampled through, as a left-to-right chain
+    'cfg2ali': dict(n_units=25, n_states=4, n_comp=1, dim=40, n_frames=1000, n_utts=4096, aligned=True),
 }
 
 
@@ -54,9 +57,10 @@ def phone_loop_graph(n_units, n_states=4, self_loop=0.75):
     return g.compile(), starts, ends
 
 
-def sample_utterances(graph, means, n_utts, n_frames, seed, device='cpu', noise=1.0):
+def sample_utterances(graph, means, n_utts, n_frames, seed, device='cpu', noise=1.0, return_paths=False):
     """Sample a state path per utterance from `graph` and emit x_t = mu[pdf(s_t)] + noise * eps.
-    Returns an [n_utts * n_frames, D] fp32 tensor on `device` (utterances back to back)."""
+    Returns an [n_utts * n_frames, D] fp32 tensor on `device` (utterances back to back); with
+    `return_paths` also the sampled state paths [n_utts, n_frames] (int64, on `device`)."""
     gen = torch.Generator(device=device)
     gen.manual_seed(seed)
     init = graph.init_log_probs.double().exp().to(device)
@@ -68,12 +72,37 @@ def sample_utterances(graph, means, n_utts, n_frames, seed, device='cpu', noise=
     D = means.shape[1]
     state = torch.multinomial(init.expand(n_utts, -1), 1, generator=gen).squeeze(1)
     X = torch.empty(n_utts, n_frames, D, device=device, dtype=torch.float32)
+    paths = torch.empty(n_utts, n_frames, device=device, dtype=torch.int64) if return_paths else None
     for t in range(n_frames):
         if t > 0:
             state = torch.multinomial(trans[state], 1, generator=gen).squeeze(1)
         X[:, t] = means[pdf[state]]
+        if return_paths:
+            paths[:, t] = state
     X += noise * torch.randn(X.shape, generator=gen, device=device, dtype=torch.float32)
-    return X.reshape(n_utts * n_frames, D)
+    X = X.reshape(n_utts * n_frames, D)
+    return (X, paths) if return_paths else X
+
+
+def alignment_chains(paths, n_states, self_loop=0.75):
+    """Alignment chains (mkaligraph.py:18-39 after compile) of the unit sequences the state paths of a phone loop
+    of `n_states`-state units went through: flat arrays for ops.ChainBatch.from_arrays.  Unit u = states
+    u*n_states .. u*n_states+n_states-1 = its pdf ids; every chain state has a self loop `self_loop`."""
+    paths = np.asarray(paths.cpu() if torch.is_tensor(paths) else paths)
+    offs, pdf = [0], []
+    for p in paths:
+        units = p // n_states
+        # a new unit instance starts where the unit changes or the path re-enters a first state from a last one
+        new = np.ones(len(p), dtype=bool)
+        new[1:] = (units[1:] != units[:-1]) | ((p[1:] % n_states == 0) & (p[:-1] % n_states == n_states - 1))
+        seq = units[new]
+        ids = (seq[:, None] * n_states + np.arange(n_states)[None, :]).reshape(-1)
+        pdf.append(ids)
+        offs.append(offs[-1] + len(ids))
+    pdf = np.concatenate(pdf).astype(np.int32)
+    log_self = np.full(len(pdf), np.log(self_loop), dtype=np.float32)
+    log_next = np.full(len(pdf), np.log(1 - self_loop), dtype=np.float32)
+    return np.asarray(offs, dtype=np.int64), pdf, log_self, log_next, np.zeros(len(paths), dtype=np.float32)
 
 
 def initial_normal_gamma(n_gauss, dim, seed, device='cpu', prior_strength=1.0, noise_std=1.0):

@@ -33,7 +33,8 @@ def workload_name(cfg, c):
     K = c['n_units'] * c['n_states']
     return (f"{cfg}: HMM-GMM {K} states x {c['n_comp']} diag-Gauss, {c['dim']}-d synthetic fbank, "
             f"{c['n_utts']} utterances x {c['n_frames']} frames per GPU, phone-loop graph "
-            f"({c['n_units']} units x {c['n_states']} states)")
+            f"({c['n_units']} units x {c['n_states']} states)"
+            + (', every utterance aligned to its own left-to-right chain' if c.get('aligned') else ''))
 
 
 def measured_peaks():
@@ -223,7 +224,12 @@ def run_gpu(args, c):
                          graph.trans_log_probs.numpy(), graph.pdf_id_mapping, n_pdfs=K)
     gen = torch.Generator().manual_seed(7)
     means = 2.0 * torch.randn(K, D, generator=gen)
-    X = synthetic.sample_utterances(graph, means, U, T, seed=100 + rank, device=dev)
+    if c.get('aligned'):
+        X, paths = synthetic.sample_utterances(graph, means, U, T, seed=100 + rank, device=dev, return_paths=True)
+        plan = ops.ChainBatch.from_arrays(*synthetic.alignment_chains(paths, c['n_states']), device=dev)
+        del paths
+    else:
+        X = synthetic.sample_utterances(graph, means, U, T, seed=100 + rank, device=dev)
     utts = Utterances(X, [T] * U)
 
     def make_engine(utts=utts, chunk_frames=args.chunk_frames, use_graph=False):
