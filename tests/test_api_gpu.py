@@ -387,3 +387,40 @@ def test_bigram_and_uneven_phoneloop(beer, tag):
     for gotp, pname in zip(get_ng(ns.means_precisions.posterior), ('mean', 'scale', 'shape', 'rates')):
         wantp = g[tag + '_post2_' + pname]
         np.testing.assert_allclose(gotp.reshape(wantp.shape), wantp, rtol=3e-4, atol=3e-4)
+
+
+def test_mixture_cfg5_shape(beer):
+    """BASELINE configs[4] shape: the E-step + M-step of a 512-component diagonal GMM on 40-d frames (the inner
+    model of the GSM-GMM example), two VB iterations against the oracle (mixture.py:70-102)."""
+    from oracle import beer_oracle as O
+    Cn, D, N = 512, 40, 6000
+    gen = torch.Generator().manual_seed(11)
+    centres = 3.0 * torch.randn(32, D, generator=gen)
+    X = (centres[torch.randint(0, 32, (N,), generator=gen)] + torch.randn(N, D, generator=gen)).to(DEV)
+    ns = beer.NormalSet.create(torch.zeros(D, device=DEV), torch.ones(D, device=DEV), size=Cn, prior_strength=1.,
+                               noise_std=1., cov_type='diagonal')
+    gmm = beer.Mixture.create(ns)
+    par, w = ns.means_precisions, gmm.categorical.weights
+
+    def host(dist):
+        m, k, a, b = get_ng(dist)
+        return m, k.reshape(-1, 1), a.reshape(-1, 1), b
+    ng_prior, ng_post = host(par.prior), host(par.posterior)
+    dprior = w.prior.params.concentrations.double().cpu().numpy()
+    dpost = w.posterior.params.concentrations.double().cpu().numpy()
+    Xh = X.double().cpu().numpy()
+    optim = beer.VBConjugateOptimizer(gmm.mean_field_factorization(), lrate=1.)
+    for _ in range(2):
+        r = O.gmm_estep(Xh, ng_post, dpost)
+        kl = O.normalgamma_kl(ng_post, ng_prior).sum() + O.dirichlet_kl(dpost, dprior).sum()
+        want = O.elbo_value(r['exp_llh'], kl, N)
+        optim.init_step()
+        elbo = beer.evidence_lower_bound(gmm, X, datasize=N)
+        elbo.backward()
+        optim.step()
+        np.testing.assert_allclose(float(elbo), want, rtol=1e-5)
+        ng_post = O.natural_grad_update_normalgamma(ng_prior, ng_post, r['acc_normal'], 1.)
+        dpost = O.natural_grad_update_dirichlet(dprior, dpost, r['acc_dirichlet'], 1.)
+    for got, want in zip(host(par.posterior), ng_post):
+        np.testing.assert_allclose(got, want, rtol=3e-4, atol=3e-4)
+    np.testing.assert_allclose(w.posterior.params.concentrations.double().cpu().numpy(), dpost, rtol=3e-4, atol=1e-5)
