@@ -200,3 +200,50 @@ def test_dataset_archive_roundtrip(tmp_path):
     import pickle
     ds2 = pickle.loads(pickle.dumps(ds))
     assert ds2.size == ds.size and len(ds2['utt03'].features) == len(utts['utt03'])
+
+
+def test_chain_batch_host_logic():
+    """Alignment graphs -> flat chain arrays (mkaligraph.py:18-39 after Graph.compile): lengths, pdf ids and
+    weights of every chain, rejection of graphs that are not chains, and the chains of sampled state paths."""
+    from beer_b200 import ops, synthetic
+    gr, _, _ = O.phone_loop_graph(3, 2)
+    with pytest.raises(ValueError):
+        ops.ChainBatch([gr], 'cpu')
+    # two hand-made chains as (init, final, trans, map)
+    def chain(L, pdfs, loop):
+        trans = np.full((L, L), -np.inf, dtype=np.float32)
+        trans[np.arange(L), np.arange(L)] = np.log(loop)
+        trans[np.arange(L - 1), np.arange(1, L)] = np.log(1 - loop)
+        init = np.full(L, -np.inf, dtype=np.float32)
+        init[0] = 0.
+        final = np.full(L, -np.inf, dtype=np.float32)
+        final[-1] = np.log(1 - loop)
+        return init, final, trans, pdfs
+    cb = ops.ChainBatch([chain(3, [4, 5, 4], 0.75), chain(1, [2], 0.5)], 'cpu')
+    assert cb.n_utts == 2 and cb.max_len == 3 and cb.n_pdfs == 6 and cb.row_stride == 128
+    np.testing.assert_array_equal(cb.chain_off.numpy(), [0, 3, 4])
+    np.testing.assert_array_equal(cb.pdf.numpy(), [4, 5, 4, 2])
+    np.testing.assert_allclose(cb.log_self.numpy(), np.log([.75, .75, .75, .5]), rtol=1e-6)
+    np.testing.assert_allclose(cb.log_next.numpy(), np.log([.25, .25, .25, .5]), rtol=1e-6)
+    assert cb.workspace_bytes(10) == 10 * 128 * 4
+    # chains of sampled paths: unit instances in visiting order, re-entry of the same unit is a new instance
+    paths = np.array([[0, 0, 1, 1, 0, 1, 2, 3, 3, 2]])           # 2-state units: u0, u0 again, u1, u1 again
+    off, pdf, ls, ln, li = synthetic.alignment_chains(paths, 2)
+    np.testing.assert_array_equal(off, [0, 8])
+    np.testing.assert_array_equal(pdf, [0, 1, 0, 1, 2, 3, 2, 3])
+    cb2 = ops.ChainBatch.from_arrays(off, pdf, ls, ln, li, 'cpu')
+    assert cb2.max_len == 8 and cb2.n_pdfs == 4
+
+
+def test_onehot_transitions_of_a_path():
+    """hmm.py:49-54 restricted to rows x columns, with no transition across an utterance boundary."""
+    from beer_b200.models import _onehot_transitions
+    path = torch.tensor([0, 1, 1, 2, 0, 2, 2], dtype=torch.int32)
+    off = torch.tensor([0, 4, 7])
+    rows, cols = [1, 2], [0, 2]
+    got = _onehot_transitions(path, off, rows, cols).numpy()
+    want = []
+    for a, b in ((0, 4), (4, 7)):
+        for t in range(a, b - 1):
+            want.append([[float(path[t] == r and path[t + 1] == c) for c in cols] for r in rows])
+    np.testing.assert_array_equal(got, np.asarray(want, dtype=np.float32))
