@@ -162,6 +162,27 @@ class _StageTimer:
         return False
 
 
+def bind_to_gpu_cpus(device_index):
+    """Pin this process to the CPUs NVML reports as local to GPU `device_index` (same NUMA node / PCIe root), so
+    that the pinned host buffers it allocates afterwards sit next to the GPU they feed.  Matters for the
+    host-streaming mode at several ranks per box; returns the CPU set or None when NVML / affinity is unavailable."""
+    try:
+        import os
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        n = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1 and 64 * w + b < n}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:       # no NVML, restricted container, non-Linux: placement stays as the launcher left it
+        return None
+
+
 def shard_utterances(lengths, world_size):
     """Static utterance -> rank assignment balancing the frames per rank (longest-processing-time
     greedy): the `split` step of the reference's job arrays (recipes/zrc2019/utils/parallel/split.sh)

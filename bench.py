@@ -203,6 +203,9 @@ def run_gpu(args, c):
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
+        from beer_b200.engine import bind_to_gpu_cpus
+        bind_to_gpu_cpus(local_rank)      # pinned feature buffers next to this rank's GPU (e2e leg)
+    if world > 1:
         # NCCL announces its version on stdout at the first collective: keep stdout to the one JSON line
         sys.stdout.flush()
         saved = os.dup(1)
