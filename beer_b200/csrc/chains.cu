@@ -10,6 +10,11 @@
 // One warp per utterance, lane l owns states l*S .. l*S+S-1 in registers; the only exchange between
 // lanes is the neighbour's edge state (one shuffle per frame and direction) and the per-frame
 // normaliser (one redux).  log2 domain, renormalised every frame, like the other scan kernels.
+// S (4, 8, 16 or 32 states per lane) is picked PER UTTERANCE from its chain length: the batch is launched once per
+// class and a warp skips the utterances of the other classes (a batch-wide S = 16 for one long chain cost every
+// utterance 168 registers).  Rows in shared memory and in the alpha workspace are stored chunk-major (16-byte
+// chunk v of lane l at float offset (32 v + l) * 4): conflict-free 16-byte accesses for every S (lane-major rows
+// were 4-way conflicted at S = 16) and 512-byte coalesced global rows.
 // The llhs are gathered through the chain's pdf ids by 4-byte cp.async into a per-warp ring; the
 // posteriors are scatter-added onto pdf ids (modelset.py:148-154: a pdf may occur several times in a chain).
 #include "common.cuh"
@@ -42,6 +47,10 @@ struct ChainArgs {
     double* utt_logz;
 };
 
+__host__ __device__ __forceinline__ int chain_class(int len) {
+    return len <= 128 ? 4 : (len <= 256 ? 8 : (len <= 512 ? 16 : (len <= 1024 ? 32 : 0)));
+}
+
 __device__ __forceinline__ float lse2c(float a, float b) {
     const float mx = fmaxf(a, b), mn = fminf(a, b);
     const float d = fmaxf(mn - mx, -1000.f);
@@ -66,12 +75,13 @@ __global__ void __launch_bounds__(CH_WARPS * 32) hmm_fb_chain_kernel(ChainArgs a
         const int64_t c0 = a.chain_off[u];
         const int L = (int)(a.chain_off[u + 1] - c0);
         if (T <= 0 || L <= 0) {
-            if (lane == 0) {
+            if (lane == 0 && S == 4) {
                 a.utt_exp_llh[u] = 0.0;
                 if (a.utt_logz) a.utt_logz[u] = 0.0;
             }
             continue;
         }
+        if (chain_class(L) != S) continue;         // another launch of this batch owns this utterance
         // this lane's states
         int pdf[S];
         float w_self[S], w_in[S];
@@ -92,27 +102,28 @@ __global__ void __launch_bounds__(CH_WARPS * 32) hmm_fb_chain_kernel(ChainArgs a
             if (!own) return;
 #pragma unroll
             for (int j = 0; j < S; ++j)
-                if (lane * S + j < L) cp_async4(slot + lane * S + j, row + pdf[j]);
+                if (lane * S + j < L) cp_async4(slot + ((j >> 2) * 32 + lane) * 4 + (j & 3), row + pdf[j]);
         };
         auto copy_row = [&](float* slot, const float* row) {
             if (!own) return;
 #pragma unroll
             for (int v = 0; v < S / 4; ++v)
-                if (lane * S + 4 * v < L) cp_async16(slot + lane * S + 4 * v, row + lane * S + 4 * v);
+                if (lane * S + 4 * v < L) cp_async16(slot + (v * 32 + lane) * 4, row + (v * 32 + lane) * 4);
         };
         auto read_row = [&](const float* slot, float* out) {
 #pragma unroll
             for (int v = 0; v < S / 4; ++v) {
-                const float4 q = reinterpret_cast<const float4*>(slot + lane * S)[v];
+                const float4 q = reinterpret_cast<const float4*>(slot)[v * 32 + lane];
                 out[4 * v] = q.x; out[4 * v + 1] = q.y; out[4 * v + 2] = q.z; out[4 * v + 3] = q.w;
             }
         };
-        auto write_row = [&](float* row, const float* v) {
+        // chunk-major (alpha workspace) or natural state order (state posteriors handed to the caller)
+        auto write_row = [&](float* row, const float* v, bool natural) {
             if (!own) return;
 #pragma unroll
             for (int q = 0; q < S / 4; ++q)
                 if (lane * S + 4 * q < L)
-                    reinterpret_cast<float4*>(row + lane * S)[q] =
+                    reinterpret_cast<float4*>(row)[natural ? (lane * S) / 4 + q : q * 32 + lane] =
                         make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         };
 
@@ -158,7 +169,7 @@ __global__ void __launch_bounds__(CH_WARPS * 32) hmm_fb_chain_kernel(ChainArgs a
             }
 #pragma unroll
             for (int j = 0; j < S; ++j) cur[j] -= mxs;
-            write_row(la_u + (size_t)t * a.Kw, cur);
+            write_row(la_u + (size_t)t * a.Kw, cur, false);
         }
         cp_async_wait<0>();
         logz2 += (double)lz;
@@ -250,7 +261,7 @@ __global__ void __launch_bounds__(CH_WARPS * 32) hmm_fb_chain_kernel(ChainArgs a
                     a.frame_exp_llh[t0 + t] = f * p_scale * kLn2 + r;
                 }
             }
-            if (a.state_post != nullptr) write_row(a.state_post + (size_t)(t0 + t) * a.Kw, v);
+            if (a.state_post != nullptr) write_row(a.state_post + (size_t)(t0 + t) * a.Kw, v, true);
             if (a.pdf_post != nullptr) {
                 float* prow = a.pdf_post + (size_t)(t0 + t) * a.ld_post;
 #pragma unroll
@@ -304,11 +315,7 @@ int launch_chain(const ChainArgs& a, cudaStream_t st) {
     return BEER_OK;
 }
 
-int chain_S(int max_len) {
-    for (int s : {4, 8, 16, 32})
-        if (max_len <= 32 * s) return s;
-    return 0;
-}
+int chain_S(int max_len) { return chain_class(max_len); }
 
 }  // namespace
 }  // namespace beer
@@ -346,13 +353,12 @@ int beer_hmm_forward_backward_chains(const float* pdf_llh, int64_t ld_pdf, const
     a.pdf_post = pdf_post; a.ld_post = ld_post; a.frame_exp_llh = frame_exp_llh; a.utt_exp_llh = utt_exp_llh;
     a.utt_logz = utt_logz;
     cudaStream_t st = (cudaStream_t)stream;
-    switch (S) {
-        case 4: return launch_chain<4>(a, st);
-        case 8: return launch_chain<8>(a, st);
-        case 16: return launch_chain<16>(a, st);
-        case 32: return launch_chain<32>(a, st);
-    }
-    return BEER_ERR_UNSUPPORTED;
+    // one launch per length class up to the longest chain's; a warp skips the utterances of the other classes
+    int rc = launch_chain<4>(a, st);
+    if (rc == BEER_OK && S >= 8) rc = launch_chain<8>(a, st);
+    if (rc == BEER_OK && S >= 16) rc = launch_chain<16>(a, st);
+    if (rc == BEER_OK && S >= 32) rc = launch_chain<32>(a, st);
+    return rc;
 }
 
 }  // extern "C"
