@@ -10,7 +10,7 @@ __version__ = '0.2.0'
 
 from . import dists, features, graph, vbi                                                    # noqa: F401
 from .engine import EmissionParams, UnitWeights, Utterances, VBEngine, WeightGroup              # noqa: F401
-from .dataset import Dataset                                                      # noqa: F401
+from .dataset import Alignments, Dataset                                                      # noqa: F401
 from .graph import CompiledGraph, Graph                                            # noqa: F401
 from .inference import (EvidenceLowerBoundInstance, VBConjugateOptimizer, VBOptimizer,  # noqa: F401
                         evidence_lower_bound)

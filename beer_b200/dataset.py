@@ -2,12 +2,15 @@
 an `.npz` archive of per-utterance float arrays [T_u, D] plus the global mean / variance / frame count.
 Host-side I/O only; `Dataset.shard(rank, world)` returns this rank's utterances as the ragged batch the
 engine keeps resident in HBM (the `split` step of the reference's job arrays)."""
+import contextlib
+import sys
+
 import numpy as np
 import torch
 
 from .engine import Utterances, shard_utterances
 
-__all__ = ['Dataset', 'Utterance']
+__all__ = ['Dataset', 'Utterance', 'Alignments']
 
 
 class Utterance:
@@ -79,3 +82,49 @@ class Dataset:
         if pinned_host:
             return [ids[i] for i in mine], Utterances(X.pin_memory(), [lens[i] for i in mine])
         return [ids[i] for i in mine], Utterances(X, [lens[i] for i in mine], device=device)
+
+
+@contextlib.contextmanager
+def _reference_module_names():
+    """While an archive written by the reference is unpickled, `beer.graph.CompiledGraph` resolves to this
+    package's class (same buffers, same attribute names), so the reference need not be installed."""
+    from . import graph as _graph
+    import beer_b200 as _pkg
+    saved = {k: sys.modules.get(k) for k in ('beer', 'beer.graph')}
+    if saved['beer'] is None:
+        sys.modules['beer'], sys.modules['beer.graph'] = _pkg, _graph
+    try:
+        yield
+    finally:
+        if saved['beer'] is None:
+            for k in ('beer', 'beer.graph'):
+                sys.modules.pop(k, None)
+
+
+class Alignments:
+    """Alignment graphs of `beer hmm mkaligraph` as the recipes archive them for `beer hmm accumulate --alis`
+    (mkaligraph.py:40-63, accumulate.py:33-51): an npz with one `np.array([CompiledGraph])` per utterance id.
+    `alis[uttid]` is the utterance's CompiledGraph; `chain_batch(uttids, device)` flattens the graphs of a shard
+    into the per-utterance chains the batched engine runs in one launch (ops.ChainBatch)."""
+
+    def __init__(self, path):
+        self.path = path
+        with _reference_module_names():
+            archive = np.load(path, allow_pickle=True)
+            self._graphs = {k: archive[k][0] for k in archive.files}
+
+    def __contains__(self, uttid):
+        return uttid in self._graphs
+
+    def __len__(self):
+        return len(self._graphs)
+
+    def keys(self):
+        return self._graphs.keys()
+
+    def __getitem__(self, uttid):
+        return self._graphs[uttid]
+
+    def chain_batch(self, uttids, device):
+        from . import ops
+        return ops.ChainBatch([self._graphs[u] for u in uttids], device)

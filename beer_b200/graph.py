@@ -195,6 +195,11 @@ class CompiledGraph(torch.nn.Module):
         state['_plans'] = {}           # device handles are not picklable; rebuilt on demand
         return state
 
+    def __setstate__(self, state):
+        # also reached by graphs pickled by the reference (no `_plans` there)
+        self.__dict__.update(state)
+        self.__dict__.setdefault('_plans', {})
+
     @property
     def n_states(self):
         return len(self.trans_log_probs)

@@ -402,6 +402,24 @@ def gold_bigram_phoneloop():
     save('bigram_phoneloop', **out)
 
 
+def gold_alignment_archive():
+    """The alignment-graph archive the recipes hand to `beer hmm accumulate --alis` (mkaligraph.py:40-63: one
+    `np.array([CompiledGraph])` per utterance, zipped into an npz that accumulate.py:33-51 reads with
+    `np.load(..., allow_pickle=True)[uttid][0]`), pickled by the live reference, plus the same graphs as plain
+    arrays."""
+    g, units, start_pdf, end_pdf = phone_loop(4, 3)
+    seqs = {'utt_a': ['u2', 'u0'], 'utt_b': ['u1'], 'utt_c': ['u3', 'u3', 'u0', 'u2']}
+    objs, plain = {}, {}
+    for uttid, seq in seqs.items():
+        cg = ali_graph(seq, units)
+        objs[uttid] = np.array([cg])
+        plain.update(graph_arrays(cg, uttid + '_'))
+    path = os.path.join(OUT, 'alis.npz')
+    np.savez(path, **objs)
+    print(f'alis: {os.path.getsize(path) / 1024:.1f} KiB')
+    save('alis_expected', **plain)
+
+
 # ---------------------------------------------------------------------------
 def gold_dense_ergodic():
     """Dense ergodic transitions as in tests/test_hmm.py:149-151, with exact
@@ -473,6 +491,7 @@ if __name__ == '__main__':
     hmm_case('hmm_cfg2_T200', n_units=25, n_states=4, D=40, T=200, seed=5, n_iter=2)
     gold_phoneloop_mixtureset()
     gold_bigram_phoneloop()
+    gold_alignment_archive()
     gold_dense_ergodic()
     gold_graph_compile()
     gold_fbank()

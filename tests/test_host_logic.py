@@ -247,3 +247,26 @@ def test_onehot_transitions_of_a_path():
         for t in range(a, b - 1):
             want.append([[float(path[t] == r and path[t + 1] == c) for c in cols] for r in rows])
     np.testing.assert_array_equal(got, np.asarray(want, dtype=np.float32))
+
+
+def test_alignment_archive_written_by_the_reference():
+    """tests/golden/alis.npz was pickled by the live reference (mkaligraph.py:40-63 layout): it loads without the
+    reference installed, gives the same graphs as the plain-array dump, and flattens into per-utterance chains."""
+    from beer_b200 import Alignments, CompiledGraph
+    here = os.path.join(ROOT, 'tests', 'golden')
+    assert 'beer' not in sys.modules or sys.modules['beer'].__name__ != 'beer'
+    alis = Alignments(os.path.join(here, 'alis.npz'))
+    want = np.load(os.path.join(here, 'alis_expected.npz'))
+    assert sorted(alis.keys()) == ['utt_a', 'utt_b', 'utt_c'] and 'utt_b' in alis and len(alis) == 3
+    for u in alis.keys():
+        g = alis[u]
+        assert isinstance(g, CompiledGraph)
+        np.testing.assert_array_equal(g.trans_log_probs.numpy(), want[u + '_trans'])
+        np.testing.assert_array_equal(g.init_log_probs.numpy(), want[u + '_init'])
+        np.testing.assert_array_equal(g.final_log_probs.numpy(), want[u + '_final'])
+        assert list(g.pdf_id_mapping) == list(want[u + '_map'])
+    cb = alis.chain_batch(['utt_c', 'utt_b'], 'cpu')
+    assert list(cb.lengths) == [12, 3] and cb.max_len == 12
+    np.testing.assert_array_equal(cb.pdf.numpy()[:12], want['utt_c_map'])
+    np.testing.assert_allclose(cb.log_self.numpy()[12:], np.diagonal(want['utt_b_trans']), rtol=1e-6)
+    assert 'beer' not in sys.modules or sys.modules['beer'].__name__ != 'beer'
