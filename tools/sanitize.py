@@ -49,6 +49,48 @@ run(6, 3, 1, 40, [50, 33], 'S=3 units (LR scalar rows)')
 run(16, 4, 8, 40, [130, 77, 40], 'mixtures C=8 (tcgen05, streamed weight image)')
 run(130, 4, 1, 40, [60, 35], 'many units (block scan), 5 Gaussian tiles')
 run(5, 4, 2, 12, [40, 41], 'SIMT kernels (D=12)')
+run(40, 4, 8, 40, [300, 61, 129], 'mixtures C=8, M=1280 (TMA tensor-map stores in KA, cp.async raw ring in KC)')
+
+
+def run_chains():
+    """Per-utterance alignment chains of three length classes + the transition-posterior kernel."""
+    rng = np.random.default_rng(1)
+    Kp, D = 60, 40
+    shapes = [(7, 40), (130, 150), (260, 300), (1, 3)]
+    offs, pdf = [0], []
+    for L, _ in shapes:
+        pdf.append(rng.integers(0, Kp, L))
+        offs.append(offs[-1] + L)
+    n = offs[-1]
+    chains = ops.ChainBatch.from_arrays(offs, np.concatenate(pdf), np.full(n, np.log(.7)), np.full(n, np.log(.3)),
+                                        np.zeros(len(shapes)), dev)
+    lens = [T for _, T in shapes]
+    prior, post = synthetic.initial_normal_gamma(Kp, D, seed=3, device=dev)
+    X = torch.randn(sum(lens), D, generator=torch.Generator().manual_seed(4)).to(dev)
+    eng = VBEngine(EmissionParams(prior, post), chains, Utterances(X, lens), datasize=float(sum(lens)), distributed=False)
+    vals = [float(eng.step().item()) for _ in range(2)]
+    off = torch.as_tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int64, device=dev)
+    llh = torch.randn(sum(lens), Kp, generator=torch.Generator().manual_seed(5)).to(dev)
+    r = ops.hmm_forward_backward_chains(chains, llh, None, off, want_state_post=True, want_frame_llh=True, want_logz=True)
+    graph, starts, ends = synthetic.phone_loop_graph(5, 3)
+    K = graph.n_states
+    plan = ops.GraphPlan(graph.init_log_probs.numpy(), graph.final_log_probs.numpy(), graph.trans_log_probs.numpy(),
+                         graph.pdf_id_mapping, n_pdfs=K)
+    off2 = torch.tensor([0, 50, 81], dtype=torch.int64, device=dev)
+    llh2 = torch.randn(81, K, generator=torch.Generator().manual_seed(6)).to(dev)
+    fb = ops.hmm_forward_backward(plan, llh2, None, off2, want_state_post=True, want_pdf_post=False)
+    init = graph.init_log_probs.float().to(dev).contiguous()
+    trans = graph.trans_log_probs.float().to(dev).contiguous()
+    xi = ops.hmm_transition_posteriors(llh2, fb['state_post'], off2, init, trans)
+    blk = ops.hmm_transition_posteriors(llh2, fb['state_post'], off2, init, trans,
+                                        rows=torch.as_tensor(ends, dtype=torch.int32, device=dev),
+                                        cols=torch.as_tensor(starts, dtype=torch.int32, device=dev))
+    torch.cuda.synchronize()
+    print(f'chains: elbo {vals}, logz {r["utt_logz"].tolist()}, xi {tuple(xi.shape)} sums to '
+          f'{float(xi.sum()):.3f}, block {tuple(blk.shape)}')
+
+
+run_chains()
 sig = (np.random.default_rng(0).standard_normal(16000) * 1000).astype(np.int16)
 fb = features.fbank(sig, nfilters=40)
 print('fbank', tuple(fb.shape), tuple(features.add_deltas(fb).shape))
