@@ -25,7 +25,7 @@ from .dists import Dirichlet, NormalGamma, frames_of
 from .engine import Utterances
 from .parameters import ConjugateBayesianParameter
 
-__all__ = ['Model', 'DiscreteLatentModel', 'ModelSet', 'NormalSet', 'Categorical', 'CategoricalSet', 'Mixture',
+__all__ = ['Model', 'DiscreteLatentModel', 'ModelSet', 'NormalSet', 'Categorical', 'SBCategorical', 'CategoricalSet', 'Mixture',
            'MixtureSet', 'JointModelSet', 'DynamicallyOrderedModelSet', 'HMM', 'PhoneLoop', 'BigramPhoneLoop', 'UnknownCovarianceType']
 
 f32, f64, i32, i64 = torch.float32, torch.float64, torch.int32, torch.int64
@@ -356,6 +356,81 @@ class Categorical(Model):
 
     def accumulate(self, stats, parent_msg=None):
         return {self.weights: stats.sum(dim=0).to(f64)}
+
+    def expected_log_weights(self):
+        """E[ln pi]: what evaluating the model on eye(C) yields (phoneloop.py:53-59)."""
+        return self.weights.posterior.expected_log_weights()
+
+
+class SBCategorical(Model):
+    """Categorical with a truncated stick-breaking prior (categorical.py:82-165): one Beta (a two-category Dirichlet
+    row) per stick.  The counts a model accumulates for it are re-ordered by decreasing size and turned into the
+    Beta statistics [n_k, sum_{j>k} n_j] by a callback right before the update (categorical.py:107-116)."""
+
+    @classmethod
+    def create(cls, truncation, prior_strength=1., device=None):
+        params = torch.ones(truncation, 2, dtype=f32, device='cuda' if device is None else device)
+        params[:, 1] = prior_strength
+        return cls(ConjugateBayesianParameter(Dirichlet.from_std_parameters(params),
+                                              Dirichlet.from_std_parameters(params.clone())))
+
+    def __init__(self, stickbreaking):
+        super().__init__()
+        self.stickbreaking = stickbreaking
+        conc = self.stickbreaking.posterior.params.concentrations
+        self.ordering = torch.arange(conc.shape[0], device=conc.device)
+        self.stickbreaking.register_callback(self._transform_stats, notify_before_update=True)
+
+    def _transform_stats(self):
+        stats = self.stickbreaking.stats
+        self.ordering = stats.sort(descending=True)[1]
+        stats = stats[self.ordering]
+        s2 = torch.zeros_like(stats)
+        s2[:-1] = stats[1:]
+        s2 = torch.flip(torch.flip(s2, dims=(0,)).cumsum(dim=0), dims=(0,))
+        new_stats = torch.cat([stats[:, None], s2[:, None]], dim=-1)
+        new_stats[:, -1] += new_stats[:, :-1].sum(dim=-1)
+        self.stickbreaking.stats = new_stats[self.reverse_ordering, :]
+
+    def _log_v(self):
+        c = self.stickbreaking.posterior.params.concentrations[self.ordering].double()
+        s_dig = torch.digamma(c.sum(dim=-1))
+        return torch.digamma(c[:, 0]) - s_dig, torch.digamma(c[:, 1]) - s_dig
+
+    def _log_prob(self):
+        log_v, log_1_v = self._log_v()
+        log_prob = log_v
+        log_prob[1:] += log_1_v[:-1].cumsum(dim=0)
+        return log_prob, log_1_v
+
+    @property
+    def reverse_ordering(self):
+        return torch.argsort(self.ordering)
+
+    @property
+    def mean(self):
+        c = self.stickbreaking.posterior.params.concentrations[self.ordering].double()
+        norm = c.sum(dim=-1) + torch.finfo(torch.float64).eps
+        weights = c[:, 0] / norm
+        residual = (c[:, 1] / norm).cumprod(dim=0)
+        weights[1:] *= residual[:-1]
+        return weights[self.reverse_ordering].to(f32)
+
+    def sufficient_statistics(self, data):
+        return data          # one-hot encodings
+
+    def mean_field_factorization(self):
+        return [[self.stickbreaking]]
+
+    def expected_log_weights(self):
+        log_prob, _ = self._log_prob()
+        return log_prob[self.reverse_ordering].to(f32)
+
+    def expected_log_likelihood(self, stats):
+        return stats @ self.expected_log_weights().to(stats.dtype)
+
+    def accumulate(self, stats, parent_msg=None):
+        return {self.stickbreaking: stats.sum(dim=0).to(f64)}
 
 
 class CategoricalSet(ModelSet):
@@ -742,7 +817,7 @@ class PhoneLoop(HMM):
     def _on_weights_update(self):
         """ln A[end, starts] = ln(1 - A[end, end]) + E[ln w], in place (host side: P x P numbers per
         update; the device plan of the graph is rebuilt from the new values on its next use)."""
-        log_weights = self.categorical.weights.posterior.expected_log_weights()
+        log_weights = self.categorical.expected_log_weights()
         trans = self.graph.trans_log_probs
         log_weights = log_weights.to(device=trans.device, dtype=trans.dtype)
         start_idxs = [value for value in self.start_pdf.values()]
@@ -758,7 +833,7 @@ class PhoneLoop(HMM):
         if inference_graph is None and not viterbi and state_path is None:
             # the reference switches the transition posteriors on when no inference graph is given
             # (hmm.py:76); here: one count per unit, reduced inside the backward sweep
-            dev = self.categorical.weights.posterior.params.concentrations.device
+            dev = self.categorical.mean_field_factorization()[0][0].posterior.params.concentrations.device
             plan = self.graph.plan(n_pdfs=self._emission().Kp)
             if plan.n_units == 0:
                 # units of different lengths (or any other loop the fused reduction has no kernel for): the
@@ -777,7 +852,7 @@ class PhoneLoop(HMM):
 
     def accumulate(self, stats, parent_msg=None):
         retval = super().accumulate(stats, parent_msg)
-        weights = self.categorical.weights
+        weights = self.categorical.mean_field_factorization()[0][0]
         start_idxs = [value for value in self.start_pdf.values()]
         n_units = len(start_idxs)
         if 'unit_counts' in self.cache:
@@ -799,6 +874,9 @@ class PhoneLoop(HMM):
             phone_resps = hit.sum(dim=0).to(f64) + (path[0] == starts).to(f64)
         else:
             phone_resps = torch.zeros(n_units, dtype=f64, device=weights.posterior.params.concentrations.device)
+        if isinstance(self.categorical, SBCategorical):
+            retval[weights] = phone_resps.to(f64)        # plain counts: its callback makes the Beta statistics
+            return retval
         stats_w = phone_resps.clone()
         stats_w[-1] = phone_resps.sum()
         retval[weights] = stats_w

@@ -471,6 +471,43 @@ def bigram_update_graph(trans_log, conc, start_idxs, end_idxs):
     return trans_log
 
 
+def sb_log_weights(conc, ordering):
+    """SBCategorical.expected_log_likelihood on eye(K) (categorical.py:121-165): E[ln v_k] + sum_{j<k} E[ln(1 - v_j)]
+    along the current ordering of the sticks, returned in the original index order."""
+    c = conc[ordering]
+    s = digamma(c.sum(axis=-1))
+    log_v, log_1_v = digamma(c[:, 0]) - s, digamma(c[:, 1]) - s
+    lp = log_v.copy()
+    lp[1:] += np.cumsum(log_1_v[:-1])
+    out = np.empty_like(lp)
+    out[ordering] = lp
+    return out
+
+
+def sb_transform_stats(counts):
+    """SBCategorical._transform_stats (categorical.py:107-116): sticks re-ordered by decreasing count, Beta
+    statistics [n_k, sum_{j>k} n_j] with the Dirichlet convention (last column += the others).
+    Returns (stats [K, 2] in the original index order, new ordering)."""
+    ordering = np.argsort(-counts, kind='stable')
+    s = counts[ordering]
+    s2 = np.zeros_like(s)
+    s2[:-1] = s[1:]
+    s2 = np.cumsum(s2[::-1])[::-1]
+    new = np.stack([s, s2 + s], axis=-1)
+    out = np.empty_like(new)
+    out[ordering] = new
+    return out, ordering
+
+
+def sb_phoneloop_update_graph(trans_log, conc, ordering, start_idxs, end_idxs):
+    """PhoneLoop._on_weights_update with stick-breaking weights (phoneloop.py:53-65)."""
+    logw = sb_log_weights(conc, ordering).astype(trans_log.dtype)
+    for e in end_idxs:
+        loop = np.exp(trans_log[e, e])
+        trans_log[e, start_idxs] = np.log(1 - loop) + logw
+    return trans_log
+
+
 def gmm_estep(X, ng_post, dir_post, labels=None):
     """Mixture E-step + accumulate (mixture.py:70-102)."""
     stats = normal_diag_sufficient_statistics(X)

@@ -420,6 +420,48 @@ def gold_alignment_archive():
     save('alis_expected', **plain)
 
 
+def gold_sb_phoneloop():
+    """PhoneLoop whose unit weights have a truncated stick-breaking prior (categorical.py:82-165), the model the
+    CLI builds by default (mkphoneloop.py: `gamma_dirichlet_process` -> SBCategorical*): the statistics are
+    re-ordered and turned into Beta statistics by a callback right before the update."""
+    seed, D = 13, 3
+    rng = np.random.default_rng(seed)
+    torch.manual_seed(seed)
+    g, units, start_pdf, end_pdf = phone_loop(4, 2)
+    cg = g.compile()
+    K = cg.n_states
+    out = dict(graph_arrays(cg, 'g0_'))
+    ns = beer.NormalSet.create(torch.zeros(D), torch.ones(D), size=K, prior_strength=1., noise_std=1.,
+                               cov_type='diagonal')
+    sb = beer.SBCategorical.create(len(start_pdf), prior_strength=2.)
+    pl = beer.PhoneLoop.create(cg, start_pdf, end_pdf, ns, categorical=sb).double()
+    means = 2.0 * rng.standard_normal((K, D))
+    X1 = sample_from_graph(rng, cg, means, 45)
+    X2 = sample_from_graph(rng, cg, means, 38)
+    p = ns.means_precisions
+    w = sb.stickbreaking
+    out.update(X1=X1, X2=X2, start_idxs=np.asarray(list(start_pdf.values())), end_idxs=np.asarray(list(end_pdf.values())),
+               **graph_arrays(pl.graph), **ng_params(p.prior, 'prior_'), **ng_params(p.posterior, 'post0_'),
+               sb_prior=npy(w.prior.params.concentrations), sb_post0=npy(w.posterior.params.concentrations),
+               mean0=npy(sb.mean))
+    optim = beer.VBConjugateOptimizer(pl.conjugate_bayesian_parameters(keepgroups=True), lrate=1.)
+    N = len(X1) + len(X2)
+    elbos = []
+    for it in range(3):
+        optim.init_step()
+        elbo = beer.evidence_lower_bound(datasize=N)
+        for X in (X1, X2):
+            elbo += beer.evidence_lower_bound(pl, torch.from_numpy(X).double(), datasize=N)
+        elbo.backward()
+        elbos.append(float(elbo))
+        optim.step()
+        out[f'it{it + 1}_trans'] = npy(pl.graph.trans_log_probs)
+        out[f'it{it + 1}_sb_post'] = npy(w.posterior.params.concentrations)
+        out[f'it{it + 1}_ordering'] = npy(sb.ordering)
+    out.update(elbos=np.asarray(elbos), mean3=npy(sb.mean), **ng_params(p.posterior, 'post3_'))
+    save('sb_phoneloop', **out)
+
+
 # ---------------------------------------------------------------------------
 def gold_dense_ergodic():
     """Dense ergodic transitions as in tests/test_hmm.py:149-151, with exact
@@ -492,6 +534,7 @@ if __name__ == '__main__':
     gold_phoneloop_mixtureset()
     gold_bigram_phoneloop()
     gold_alignment_archive()
+    gold_sb_phoneloop()
     gold_dense_ergodic()
     gold_graph_compile()
     gold_fbank()

@@ -424,3 +424,40 @@ def test_mixture_cfg5_shape(beer):
     for got, want in zip(host(par.posterior), ng_post):
         np.testing.assert_allclose(got, want, rtol=3e-4, atol=3e-4)
     np.testing.assert_allclose(w.posterior.params.concentrations.double().cpu().numpy(), dpost, rtol=3e-4, atol=1e-5)
+
+
+def test_stick_breaking_phoneloop(beer):
+    """PhoneLoop.create(..., categorical=SBCategorical.create(P, prior_strength)) — the unit-weight prior the CLI uses
+    by default (mkphoneloop.py) — against the live-reference golden: three accumulate/update iterations."""
+    g = load_golden('sb_phoneloop')
+    cg = compiled(beer, g, 'g0_')
+    D = g['X1'].shape[1]
+    ns = normalset(beer, g, cg.n_states, D)
+    start_pdf = {f'u{i}': int(s) for i, s in enumerate(g['start_idxs'])}
+    end_pdf = {f'u{i}': int(s) for i, s in enumerate(g['end_idxs'])}
+    sb = beer.SBCategorical.create(len(start_pdf), prior_strength=2., device=DEV)
+    pl = beer.PhoneLoop.create(cg, start_pdf, end_pdf, ns, categorical=sb)
+    w = sb.stickbreaking
+    np.testing.assert_allclose(w.prior.params.concentrations.cpu().numpy(), g['sb_prior'], rtol=1e-6)
+    np.testing.assert_allclose(sb.mean.cpu().numpy(), g['mean0'], rtol=1e-6)
+    np.testing.assert_allclose(pl.graph.trans_log_probs.numpy(), g['g_trans'], rtol=1e-5, atol=1e-6)
+    X1, X2 = t32(g['X1']), t32(g['X2'])
+    optim = beer.VBConjugateOptimizer(pl.conjugate_bayesian_parameters(keepgroups=True), lrate=1.)
+    N = len(X1) + len(X2)
+    elbos = []
+    for it in range(3):
+        optim.init_step()
+        elbo = beer.evidence_lower_bound(datasize=N)
+        for X in (X1, X2):
+            elbo += beer.evidence_lower_bound(pl, X, datasize=N)
+        elbo.backward()
+        elbos.append(float(elbo))
+        optim.step()
+        np.testing.assert_array_equal(sb.ordering.cpu().numpy(), g[f'it{it + 1}_ordering'])
+        np.testing.assert_allclose(w.posterior.params.concentrations.cpu().numpy(), g[f'it{it + 1}_sb_post'], rtol=2e-4)
+        got, want = pl.graph.trans_log_probs.numpy(), g[f'it{it + 1}_trans']
+        fin = np.isfinite(want)
+        assert np.array_equal(np.isfinite(got), fin)
+        np.testing.assert_allclose(got[fin], want[fin], rtol=2e-4, atol=2e-4)
+    np.testing.assert_allclose(elbos, g['elbos'], rtol=1e-5)
+    np.testing.assert_allclose(sb.mean.cpu().numpy(), g['mean3'], rtol=2e-4)

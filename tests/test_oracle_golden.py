@@ -253,6 +253,38 @@ def test_bigram_and_uneven_phoneloop():
         np.testing.assert_allclose(post[0], g[tag + '_post2_mean'], rtol=1e-7, atol=1e-9)
 
 
+def test_stick_breaking_phoneloop():
+    """PhoneLoop with SBCategorical unit weights (categorical.py:82-165), three VB iterations over two utterances."""
+    g = load_golden('sb_phoneloop')
+    gr = graph(g)
+    starts, ends = list(g['start_idxs']), list(g['end_idxs'])
+    post, prior = ng(g, 'post0_'), ng(g, 'prior_')
+    sb_post, sb_prior = g['sb_post0'], g['sb_prior']
+    ordering = np.arange(len(starts))
+    trans = gr[2].copy()
+    N = len(g['X1']) + len(g['X2'])
+    elbos = []
+    for it in range(3):
+        kl = O.normalgamma_kl(post, prior).sum() + O.dirichlet_kl(sb_post, sb_prior).sum()
+        tot, acc, counts, frames = 0., 0., 0., 0
+        for X in (g['X1'], g['X2']):
+            r = O.hmm_estep(X.astype(np.float64), post, None, (gr[0], gr[1], trans, gr[3]), trans_posteriors=True)
+            tot += O.elbo_value(r['exp_llh'], kl, N)
+            tr = r['xi'].sum(axis=0)
+            counts = counts + tr[:, starts][ends, :].sum(axis=0) + r['gamma'][0][starts]
+            acc, frames = acc + r['acc_normal'], frames + len(X)
+        elbos.append(tot)
+        post = O.natural_grad_update_normalgamma(prior, post, N / frames * acc, 1.)
+        stats, ordering = O.sb_transform_stats(N / frames * counts)
+        sb_post = O.natural_grad_update_dirichlet(sb_prior, sb_post, stats, 1.)
+        trans = O.sb_phoneloop_update_graph(trans, sb_post, ordering, starts, ends)
+        np.testing.assert_array_equal(ordering, g[f'it{it + 1}_ordering'])
+        np.testing.assert_allclose(sb_post, g[f'it{it + 1}_sb_post'], rtol=1e-8)
+        np.testing.assert_allclose(trans, g[f'it{it + 1}_trans'], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(elbos, g['elbos'], rtol=1e-9)
+    np.testing.assert_allclose(post[0], g['post3_mean'], rtol=1e-7, atol=1e-9)
+
+
 def test_fbank_front_end():
     """beer/features.py restated (fbank, create_fbank, add_deltas) against the live-reference golden."""
     g = load_golden('fbank')
