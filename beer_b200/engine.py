@@ -216,8 +216,11 @@ class VBEngine:
     copy of chunk i+1 overlapping the kernels of chunk i."""
 
     def __init__(self, emission, plan, utts, datasize=None, scale=1.0, lrate=1.0, chunk_frames=None,
-                 process_group=None, distributed=None, use_graph=False, unit_weights=None):
+                 process_group=None, distributed=None, use_graph=False, unit_weights=None, viterbi=False):
         self.em, self.plan, self.utts = emission, plan, utts
+        # Viterbi training (hmm.py:42-58 with viterbi=True, what recipes/zrc2019 trains with): one-hot posteriors of
+        # the best path instead of forward-backward
+        self.viterbi = bool(viterbi)
         self.scale, self.lrate = float(scale), float(lrate)
         self.dev = emission.device
         self.pg = process_group
@@ -230,9 +233,11 @@ class VBEngine:
         self.units = unit_weights
         # per-utterance alignment chains (ops.ChainBatch: chain i belongs to utterance i of this shard) or one graph plan
         self.chains = isinstance(plan, ops.ChainBatch)
-        if self.chains and (unit_weights is not None or plan.n_utts != utts.n_utts):
-            raise ValueError('a ChainBatch needs one chain per utterance of the shard (and trains no unit weights: '
-                             'phoneloop.py:98-100)')
+        if self.chains and (unit_weights is not None or plan.n_utts != utts.n_utts or self.viterbi):
+            raise ValueError('a ChainBatch needs one chain per utterance of the shard, runs forward-backward and '
+                             'trains no unit weights (phoneloop.py:98-100)')
+        if self.viterbi and unit_weights is not None:
+            raise ValueError('Viterbi training of the unit weights is only available through the model API')
         P = plan.n_units if unit_weights is not None else 0
         if unit_weights is not None and P == 0:
             raise ValueError('unit weights need an aligned left-to-right phone loop (see beer_hmm_forward_backward_units)')
@@ -265,7 +270,12 @@ class VBEngine:
         self._nonident = self.chains or not (plan.info['map_identity'] and plan.n_states == Kp)
         self.pdf_post = (torch.zeros if self._nonident else torch.empty)(nmax, Kp, device=self.dev, dtype=f32)
         self.comp_llh = torch.empty(nmax, M, device=self.dev, dtype=f32) if emission.has_mixtures else None
-        self.ws = torch.empty((plan.workspace_bytes(nmax) + 3) // 4, device=self.dev, dtype=f32)
+        ws_bytes = plan.workspace_bytes(nmax)
+        if self.viterbi:
+            ws_bytes = max(ws_bytes, nmax * plan.n_states * 2 + 4)      # uint16 back-pointers
+            self._pdf_map = torch.as_tensor(np.asarray(plan.pdf_map), dtype=i32, device=self.dev)
+            self._frame_llh = torch.empty(nmax, device=self.dev, dtype=f32)
+        self.ws = torch.empty((ws_bytes + 3) // 4, device=self.dev, dtype=f32)
         self.frame_ref = torch.empty(nmax, device=self.dev, dtype=f32)
         self.utt_ell = torch.zeros(utts.n_utts, device=self.dev, dtype=f64)
         self.gpu_launches = 0
@@ -327,7 +337,15 @@ class VBEngine:
             if nonident:
                 pdf_post.zero_()
             with self._stage('KB_forward_backward'):
-                if self.chains:
+                if self.viterbi:
+                    path = ops.hmm_viterbi(plan, pdf_llh, rel, scale=self.scale, workspace=self.ws)
+                    _, frame = ops.path_posteriors(path, em.Kp, pdf_map=self._pdf_map, scale=self.scale,
+                                                   pdf_llh=pdf_llh, frame_ref=fref, out_post=pdf_post,
+                                                   out_frame=self._frame_llh[:nf])
+                    # per-utterance sums of the per-frame expected llh (fp64 prefix sums, differences at the offsets)
+                    cs = torch.cat([torch.zeros(1, dtype=f64, device=self.dev), frame.double().cumsum(0)])
+                    self.utt_ell[u0:u1] = cs[rel[1:]] - cs[rel[:-1]]
+                elif self.chains:
                     ops.hmm_forward_backward_chains(plan, pdf_llh, fref, rel, scale=self.scale, first_utt=u0,
                                                     workspace=self.ws, out_pdf_post=pdf_post,
                                                     out_utt_exp_llh=self.utt_ell[u0:u1])

@@ -148,6 +148,7 @@ class GraphPlan:
             raise ValueError('inconsistent graph shapes')
         self.n_states = K
         self.n_pdfs = int(n_pdfs) if n_pdfs is not None else int(pmap.max()) + 1
+        self.pdf_map = pmap
         handle = C.c_void_p()
         _lib.check(lib.beer_graph_plan_create(init.ctypes.data, final.ctypes.data, trans.ctypes.data,
                                               pmap.ctypes.data, K, self.n_pdfs, int(bool(factorize)),
@@ -494,13 +495,13 @@ def segment_logsumexp(comp_llh, comp_off=None, Kp=1, out=None):
 
 
 def path_posteriors(path, n_pdfs, pdf_map=None, scale=1.0, pdf_llh=None, frame_ref=None, want_post=True,
-                    want_frame_llh=True):
+                    want_frame_llh=True, out_post=None, out_frame=None):
     """Posteriors / per-frame expected llh of a given state path (int32 [N])."""
     lib = require_cuda()
     N = path.numel()
     dev = path.device
-    post = torch.empty(N, n_pdfs, device=dev, dtype=f32) if want_post else None
-    frame = torch.empty(N, device=dev, dtype=f32) if want_frame_llh else None
+    post = out_post if out_post is not None else (torch.empty(N, n_pdfs, device=dev, dtype=f32) if want_post else None)
+    frame = out_frame if out_frame is not None else (torch.empty(N, device=dev, dtype=f32) if want_frame_llh else None)
     _lib.check(lib.beer_path_posteriors(_p(path, i32), N, _p(pdf_map, i32, True), float(scale),
                                         _p(pdf_llh, f32, True), pdf_llh.stride(0) if pdf_llh is not None else 0,
                                         _p(frame_ref, f32, True), _p(post, f32, True), n_pdfs, n_pdfs,

@@ -547,7 +547,7 @@ def natural_grad_update_dirichlet(prior, post, stats, lrate):
 # --------------------------------------------------------------------------
 
 def vb_iteration_hmm(utts, ng_prior, ng_post, dir_prior, dir_post, graph,
-                     datasize=None, scale=1., lrate=1., graphs=None):
+                     datasize=None, scale=1., lrate=1., graphs=None, viterbi=False):
     """One data-parallel VB-EM iteration, the way ``beer hmm accumulate`` /
     ``beer hmm update`` compose it (accumulate.py:37-63, update.py:37-62,
     objectives.py:78-107): per-utterance ELBO objects are summed (so the
@@ -564,7 +564,7 @@ def vb_iteration_hmm(utts, ng_prior, ng_post, dir_prior, dir_post, graph,
     acc_n, acc_d = 0., 0.
     for i, X in enumerate(utts):
         g = graph if graphs is None else graphs[i]
-        r = hmm_estep(X, ng_post, dir_post, g, scale=scale)
+        r = hmm_estep(X, ng_post, dir_post, g, scale=scale, viterbi=viterbi)
         total += elbo_value(r['exp_llh'], kl, datasize)
         acc_n = acc_n + r['acc_normal']
         if dir_post is not None:

@@ -150,3 +150,47 @@ def test_engine_learns_unit_weights_like_phoneloop_model():
     ta, tb = ga.trans_log_probs.numpy(), gb.trans_log_probs.numpy()
     fin = np.isfinite(ta)
     np.testing.assert_allclose(tb[fin], ta[fin], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('C,chunk,scale', [(1, None, 1.0), (2, 150, 0.8)])
+def test_viterbi_training_matches_oracle(C, chunk, scale):
+    """Viterbi training in the batched engine (hmm.py:42-58 with viterbi=True): one-hot posteriors of the best path,
+    three VB iterations against the oracle."""
+    from beer_b200 import ops, synthetic
+    from beer_b200.engine import EmissionParams, Utterances, VBEngine, WeightGroup
+    dev = torch.device('cuda', 0)
+    P, S, D = 5, 3, 8
+    K, M = P * S, P * S * C
+    lens = [90, 33, 140, 61]
+    graph, _, _ = synthetic.phone_loop_graph(P, S)
+    plan = ops.GraphPlan(graph.init_log_probs.numpy(), graph.final_log_probs.numpy(),
+                         graph.trans_log_probs.numpy(), graph.pdf_id_mapping, n_pdfs=K)
+    means = 2.0 * torch.randn(K, D, generator=torch.Generator().manual_seed(0))
+    full = synthetic.sample_utterances(graph, means, len(lens), max(lens), seed=1, device=dev)
+    full = full.reshape(len(lens), max(lens), D)
+    utts_dev = [full[i, :n] for i, n in enumerate(lens)]
+    X = torch.cat(utts_dev)
+    prior, post = synthetic.initial_normal_gamma(M, D, seed=2, device=dev)
+    groups, comp_off, dprior, dpost = (), None, None, None
+    if C > 1:
+        conc = torch.full((K, C), 1.0 / C, device=dev)
+        groups = (WeightGroup(0, K, C, conc.clone(), conc.clone()),)
+        comp_off = np.arange(K + 1) * C
+        dprior, dpost = conc.double().cpu().numpy(), conc.double().cpu().numpy()
+    em = EmissionParams(prior, post, comp_off=comp_off, weight_groups=groups)
+    N = sum(lens)
+    eng = VBEngine(em, plan, Utterances(X, lens), datasize=float(N), chunk_frames=chunk, distributed=False,
+                   scale=scale, viterbi=True)
+    ng_prior, ng_post = _host(prior), _host(post)
+    og = (graph.init_log_probs.double().numpy(), graph.final_log_probs.double().numpy(),
+          graph.trans_log_probs.double().numpy(), graph.pdf_id_mapping)
+    utts = [u.double().cpu().numpy() for u in utts_dev]
+    for it in range(3):
+        want, ng_post, dpost, info = O.vb_iteration_hmm(utts, ng_prior, ng_post, dprior, dpost, og, scale=scale,
+                                                        viterbi=True)
+        got = float(eng.step().item())
+        assert abs(got - want) <= 1e-5 * abs(want), (it, got, want)
+        acc = eng.acc.cpu().numpy()
+        assert np.abs(acc - info['acc_normal']).max() <= 3e-5 * np.abs(info['acc_normal']).max()
+    for g, w in zip(_host(em.post), ng_post):
+        np.testing.assert_allclose(g, w, rtol=2e-4, atol=2e-4)
