@@ -399,15 +399,33 @@ __global__ void path_posteriors_kernel(const int32_t* __restrict__ path, int64_t
                                        float scale, const float* __restrict__ pdf_llh, int64_t ld_pdf,
                                        const float* __restrict__ frame_ref, float* __restrict__ pdf_post,
                                        int64_t ld_post, int Kp, float* __restrict__ frame_exp_llh) {
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < N; t += (int64_t)gridDim.x * blockDim.x) {
-        const int s = path[t];
-        const int k = (map != nullptr) ? map[s] : s;
-        if (pdf_post != nullptr) {
-            float* row = pdf_post + (size_t)t * ld_post;
-            for (int c = 0; c < Kp; ++c) row[c] = (c == k) ? scale : 0.f;
-        }
-        if (frame_exp_llh != nullptr)
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+    if (frame_exp_llh != nullptr) {
+        for (int64_t t = tid; t < N; t += nthr) {
+            const int s = path[t];
+            const int k = (map != nullptr) ? map[s] : s;
             frame_exp_llh[t] = scale * (pdf_llh[(size_t)t * ld_pdf + k] + (frame_ref != nullptr ? frame_ref[t] : 0.f));
+        }
+    }
+    if (pdf_post == nullptr) return;
+    // one-hot rows, written coalesced: consecutive threads take consecutive (groups of four) columns of a row
+    if (ld_post == Kp && (Kp & 3) == 0 && ((uintptr_t)pdf_post & 15) == 0) {
+        const int q = Kp >> 2;
+        for (int64_t i = tid; i < N * q; i += nthr) {
+            const int64_t t = i / q;
+            const int c0 = (int)(i - t * q) * 4;
+            const int s = path[t];
+            const int k = ((map != nullptr) ? map[s] : s) - c0;
+            reinterpret_cast<float4*>(pdf_post)[i] = make_float4(k == 0 ? scale : 0.f, k == 1 ? scale : 0.f,
+                                                                  k == 2 ? scale : 0.f, k == 3 ? scale : 0.f);
+        }
+    } else {
+        for (int64_t i = tid; i < N * Kp; i += nthr) {
+            const int64_t t = i / Kp;
+            const int c = (int)(i - t * Kp);
+            const int s = path[t];
+            pdf_post[(size_t)t * ld_post + c] = (c == ((map != nullptr) ? map[s] : s)) ? scale : 0.f;
+        }
     }
 }
 
@@ -569,8 +587,8 @@ int beer_path_posteriors(const int32_t* path, int64_t N, const int32_t* pdf_map,
     if (!path || N < 0 || Kp <= 0) return BEER_ERR_ARG;
     if (frame_exp_llh != nullptr && pdf_llh == nullptr) return BEER_ERR_ARG;
     if (N == 0) return BEER_OK;
-    int blocks = (int)std::min<int64_t>((N + 127) / 128, 148 * 16);
-    path_posteriors_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(path, N, pdf_map, scale, pdf_llh, ld_pdf,
+    int blocks = (int)std::min<int64_t>((N + 255) / 256, 148 * 8);
+    path_posteriors_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(path, N, pdf_map, scale, pdf_llh, ld_pdf,
                                                                      frame_ref, pdf_post, ld_post, Kp, frame_exp_llh);
     BEER_LAUNCH_CHECK();
     return BEER_OK;

@@ -1640,6 +1640,199 @@ __global__ void __launch_bounds__(FB_WARPS * 32) hmm_viterbi_kernel(VitArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// Viterbi over an aligned left-to-right loop with one unit per lane (P <= 32 units of SU states: the phone loop of
+// BASELINE configs[1]).  Same arithmetic and the same first-max tie-breaking as the generic kernel (the candidates of
+// a state are compared in ascending source order with a strict >, torch.argmax of graph.py:329-344), but the
+// recursion lives in registers: a non-start state has two candidates (previous state, itself), a unit start has the
+// 32 unit ends -- fetched by shuffles and weighted with the DENSE ln A[end, start] values, not the factored ones,
+// so that near-ties resolve exactly as in the reference -- and itself.  llh rows come through a cp.async ring,
+// back-pointers are one uint16 per lane and frame (2 bits per inner state, 6 bits for the unit start: 64 bytes per
+// frame instead of 2 K), and the backtrack walks them through shared memory 32 frames at a time.
+// ---------------------------------------------------------------------------
+template <int SU>
+__global__ void __launch_bounds__(FB_WARPS * 32) hmm_viterbi_lr_kernel(VitArgs a) {
+    constexpr int S = SU, PF = 6, ROW = 32 * S;
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* ring = smem + (size_t)warp * (PF * ROW + 512);           // [PF][32 * S] llh rows
+    uint16_t* bt_s = reinterpret_cast<uint16_t*>(ring + PF * ROW);   // [32 frames][32 lanes]
+    const int K = a.K, P = K / SU;
+    const bool own = lane < P;
+    const int gwarp = blockIdx.x * FB_WARPS + warp, nwarps = gridDim.x * FB_WARPS;
+    uint16_t* bt16 = a.bt;                                           // [N][32]
+
+    // weights of this lane's unit (natural log, dense lists of the plan)
+    float w_self[S], w_prev[S], wend[32], start[S], fin[S];
+#pragma unroll
+    for (int v = 0; v < 32; ++v) wend[v] = kNegInf;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const int k = lane * S + s;
+        w_self[s] = w_prev[s] = kNegInf;
+        start[s] = (k < K) ? __ldg(a.vit.start + k) : kNegInf;
+        fin[s] = (k < K) ? __ldg(a.vit_final + k) : kNegInf;
+        const int row0 = __ldg(a.vit.st_off + s), cnt = __ldg(a.vit.st_cnt + s);
+        for (int q = 0; q < cnt; ++q) {
+            const int i = (row0 + q) * 32 + lane;
+            const int src = __ldg(a.vit.src + i);
+            const float lw = __ldg(a.vit.lw + i);
+            if (k >= K || lw == kNegInf) continue;
+            if (src == k) {
+                w_self[s] = lw;
+            } else if (s > 0) {
+                if (src == k - 1) w_prev[s] = lw;
+            } else {
+#pragma unroll
+                for (int v = 0; v < 32; ++v)
+                    if (src == v * SU + SU - 1) wend[v] = lw;
+            }
+        }
+    }
+    for (int i = lane; i < PF * ROW; i += 32) ring[i] = 0.f;
+    __syncwarp();
+
+    auto prefetch = [&](float* slot, const float* row) {
+        if (!own) return;
+        if constexpr (SU == 4) {
+            cp_async16(slot + lane * 4, row + lane * 4);
+        } else {
+#pragma unroll
+            for (int j = 0; j < S; ++j) cp_async4(slot + lane * S + j, row + lane * S + j);
+        }
+    };
+
+    for (int u = gwarp; u < a.n_utts; u += nwarps) {
+        const int64_t t0 = a.utt_off[u];
+        const int T = (int)(a.utt_off[u + 1] - t0);
+        if (T <= 0) continue;
+        const float* pl_u = a.pl + (size_t)t0 * a.ld;
+        for (int r = 0; r < PF; ++r) {
+            if (r < T) prefetch(ring + r * ROW, pl_u + (size_t)r * a.ld);
+            cp_async_commit();
+        }
+        float om[S];
+        int slot = 0;
+        for (int t = 0; t < T; ++t) {
+            cp_async_wait<PF - 1>();
+            float p[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) p[s] = own ? a.scale * ring[slot * ROW + lane * S + s] : kNegInf;
+            if (t + PF < T) prefetch(ring + slot * ROW, pl_u + (size_t)(t + PF) * a.ld);
+            cp_async_commit();
+            slot = (slot + 1 == PF) ? 0 : slot + 1;
+            if (t == 0) {
+#pragma unroll
+                for (int s = 0; s < S; ++s) om[s] = p[s] + start[s];
+            } else {
+                // unit start: first maximum over the unit ends (ascending source), then this state itself
+                const float e = om[S - 1];
+                float best = kNegInf;
+                int code = 33;                                   // 33: every candidate is -inf (argmax -> state 0)
+#pragma unroll
+                for (int v = 0; v < 32; ++v) {
+                    const float c = __shfl_sync(0xffffffffu, e, v) + wend[v];
+                    if (c > best) {
+                        best = c;
+                        code = v;
+                    }
+                }
+                const float self0 = om[0] + w_self[0];
+                // source of the self arc is SU * lane: it precedes the end of unit v iff lane <= v
+                if (self0 > best || (self0 == best && self0 != kNegInf && lane <= code)) {
+                    best = self0;
+                    code = 32;
+                }
+                unsigned packed = (unsigned)code << 8;
+                float nw[S];
+                nw[0] = p[0] + best;
+#pragma unroll
+                for (int s = 1; s < S; ++s) {
+                    const float prev = om[s - 1] + w_prev[s], self = om[s] + w_self[s];
+                    float b = prev;
+                    unsigned c = (prev == kNegInf) ? 2u : 1u;    // 1: previous state, 0: itself, 2: all -inf
+                    if (self > b) {
+                        b = self;
+                        c = 0u;
+                    }
+                    packed |= c << (2 * (s - 1));
+                    nw[s] = p[s] + b;
+                }
+#pragma unroll
+                for (int s = 0; s < S; ++s) om[s] = own ? nw[s] : kNegInf;
+                bt16[(size_t)(t0 + t) * 32 + lane] = (uint16_t)packed;
+            }
+            float mx = om[0];
+#pragma unroll
+            for (int s = 1; s < S; ++s) mx = fmaxf(mx, om[s]);
+            mx = warp_max(mx);
+            const float mxs = (mx == kNegInf) ? 0.f : mx;
+#pragma unroll
+            for (int s = 0; s < S; ++s) om[s] -= mxs;
+        }
+        cp_async_wait<0>();
+        // last state: first maximal index of omega + final
+        float best = kNegInf;
+        int arg = 0x7fffffff;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const int k = lane * S + s;
+            if (k < K) {
+                const float v = om[s] + fin[s];
+                if (arg == 0x7fffffff || v > best) { best = v; arg = k; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+        }
+        __threadfence_block();
+        __syncwarp();
+        // backtrack, 32 frames of back-pointers at a time through shared memory
+        int k = arg;
+        if (lane == 0) a.path[t0 + T - 1] = k;
+        for (int tb = T - 1; tb >= 1; tb -= 32) {
+            const int t = tb - lane;
+            if (t >= 1) {
+                const uint4* src = reinterpret_cast<const uint4*>(bt16 + (size_t)(t0 + t) * 32);
+                uint4* dst = reinterpret_cast<uint4*>(bt_s + lane * 32);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) dst[q] = src[q];
+            }
+            __syncwarp();
+            if (lane == 0) {
+                for (int i = 0; i < 32 && tb - i >= 1; ++i) {
+                    const unsigned w = bt_s[i * 32 + k / SU];
+                    const int s = k % SU;
+                    int kp;
+                    if (s == 0) {
+                        const int c = (int)(w >> 8);
+                        kp = c < 32 ? c * SU + SU - 1 : (c == 32 ? k : 0);
+                    } else {
+                        const unsigned c = (w >> (2 * (s - 1))) & 3u;
+                        kp = c == 1u ? k - 1 : (c == 0u ? k : 0);
+                    }
+                    a.path[t0 + tb - i - 1] = kp;
+                    k = kp;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+template <int SU>
+static int launch_vit_lr(const VitArgs& a, int n_utts, cudaStream_t st) {
+    const size_t smem = sizeof(float) * (size_t)FB_WARPS * (6 * 32 * SU + 512);
+    int blocks = (n_utts + FB_WARPS - 1) / FB_WARPS;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    hmm_viterbi_lr_kernel<SU><<<blocks, FB_WARPS * 32, smem, st>>>(a);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
 template <int S>
 static int launch_fb(const FbArgs& a, int n_utts, cudaStream_t st) {
     constexpr int PF = FbCfg<S>::PF;
@@ -1984,6 +2177,18 @@ int beer_hmm_viterbi(const beer_graph_plan* plan, const float* pdf_llh, int64_t 
     a.pl = pdf_llh; a.ld = ld_pdf; a.utt_off = utt_off; a.n_utts = n_utts; a.scale = scale;
     a.bt = (uint16_t*)workspace; a.path = path;
     cudaStream_t st = (cudaStream_t)stream;
+    // aligned left-to-right loop, one unit per lane: register-resident kernel (its back-pointers need 64 bytes per
+    // frame of the N * K * 2 byte workspace, hence K >= 32)
+    {
+        const char* force = getenv("BEER_B200_SCAN");
+        if (plan->lr_su && plan->lr_u == 1 && plan->map_identity && plan->S == plan->lr_su && plan->K >= 32 &&
+            plan->K == plan->lr_su * (plan->K / plan->lr_su) && plan->K / plan->lr_su <= 32 &&
+            ((uintptr_t)workspace & 15) == 0 && (force == nullptr || force[0] == 'l')) {
+            if (plan->lr_su == 4 && ld_pdf % 4 == 0 && ((uintptr_t)pdf_llh & 15) == 0)
+                return launch_vit_lr<4>(a, n_utts, st);
+            if (plan->lr_su == 3) return launch_vit_lr<3>(a, n_utts, st);
+        }
+    }
     switch (plan->S) {
         case 1: return launch_vit<1>(a, n_utts, st);
         case 2: return launch_vit<2>(a, n_utts, st);

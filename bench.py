@@ -34,7 +34,8 @@ def workload_name(cfg, c):
     return (f"{cfg}: HMM-GMM {K} states x {c['n_comp']} diag-Gauss, {c['dim']}-d synthetic fbank, "
             f"{c['n_utts']} utterances x {c['n_frames']} frames per GPU, phone-loop graph "
             f"({c['n_units']} units x {c['n_states']} states)"
-            + (', every utterance aligned to its own left-to-right chain' if c.get('aligned') else ''))
+            + (', every utterance aligned to its own left-to-right chain' if c.get('aligned') else '')
+            + (', Viterbi training' if c.get('viterbi') else ''))
 
 
 def measured_peaks():
@@ -244,7 +245,7 @@ def run_gpu(args, c):
             comp_off = np.arange(K + 1) * C
         em = EmissionParams(prior, post, comp_off=comp_off, weight_groups=groups)
         return VBEngine(em, plan, utts, datasize=float(world * U * T), chunk_frames=chunk_frames,
-                        distributed=world > 1, use_graph=use_graph)
+                        distributed=world > 1, use_graph=use_graph, viterbi=args.viterbi)
 
     def barrier():
         if world > 1:
@@ -387,11 +388,15 @@ def main():
     ap.add_argument('--n-utts', type=int, default=None, help='override utterances per GPU (debug)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel eagerly (no CUDA graph)')
+    ap.add_argument('--viterbi', action='store_true', help='Viterbi training (one-hot posteriors of the best path) '
+                    'instead of forward-backward; a secondary workload, not the BASELINE metric')
     args = ap.parse_args()
     from beer_b200.synthetic import CONFIGS
     c = dict(CONFIGS[args.config])
     if args.n_utts:
         c['n_utts'] = args.n_utts
+    if args.viterbi:
+        c['viterbi'] = True
     if args.impl == 'reference':
         run_reference(args, c)
     else:

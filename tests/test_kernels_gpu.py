@@ -331,3 +331,30 @@ def test_forward_backward_many_units_block_kernel(ops, P, S, monkeypatch):
     with np.errstate(all='ignore'):
         gamma, _ = O.posteriors(0.8 * llh[off[u]:off[u + 1]].astype(np.float64), *g64)
     assert np.abs(outs['best']['state_post'][off[u]:off[u + 1]] - gamma).max() <= 1e-5
+
+
+@pytest.mark.parametrize('P,SU', [(8, 4), (25, 4), (11, 3), (32, 4)])
+def test_viterbi_loop_kernel_equals_generic_kernel_with_ties(ops, P, SU, monkeypatch):
+    """The register-resident Viterbi kernel of aligned left-to-right loops against the generic one on llhs quantised
+    to quarter units (thousands of exact ties): identical paths, i.e. the same first-max tie-breaking
+    (graph.py:329-344), and identical to the oracle where fp32 and fp64 agree on the ties (uniform weights)."""
+    gr, _, _ = O.phone_loop_graph(P, SU, self_loop=0.5)
+    K = P * SU
+    rng = np.random.default_rng(P * 10 + SU)
+    lens = [1, 2, 33, 64, 257, 1000]
+    off = np.concatenate([[0], np.cumsum(lens)])
+    llh = np.round(rng.standard_normal((off[-1], K)) * 8) / 4 - 10.0
+    plan = ops.GraphPlan(*gr)
+    utt = torch.as_tensor(off, dtype=torch.int64, device=DEV)
+    x = dev(llh)
+    monkeypatch.delenv('BEER_B200_SCAN', raising=False)
+    fast = ops.hmm_viterbi(plan, x, utt).cpu().numpy()
+    monkeypatch.setenv('BEER_B200_SCAN', 'generic')
+    slow = ops.hmm_viterbi(plan, x, utt).cpu().numpy()
+    monkeypatch.delenv('BEER_B200_SCAN', raising=False)
+    np.testing.assert_array_equal(fast, slow)
+    # short utterances: no rounding drift yet, fp64 argmax sees the same ties
+    for u in range(3):
+        a, b = off[u], off[u + 1]
+        want = O.best_path(llh[a:b].astype(np.float32).astype(np.float64), *[np.asarray(g, dtype=np.float64) for g in gr[:3]])
+        np.testing.assert_array_equal(fast[a:b], want)
