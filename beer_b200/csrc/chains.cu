@@ -353,11 +353,30 @@ int beer_hmm_forward_backward_chains(const float* pdf_llh, int64_t ld_pdf, const
     a.pdf_post = pdf_post; a.ld_post = ld_post; a.frame_exp_llh = frame_exp_llh; a.utt_exp_llh = utt_exp_llh;
     a.utt_logz = utt_logz;
     cudaStream_t st = (cudaStream_t)stream;
-    // one launch per length class up to the longest chain's; a warp skips the utterances of the other classes
-    int rc = launch_chain<4>(a, st);
-    if (rc == BEER_OK && S >= 8) rc = launch_chain<8>(a, st);
-    if (rc == BEER_OK && S >= 16) rc = launch_chain<16>(a, st);
-    if (rc == BEER_OK && S >= 32) rc = launch_chain<32>(a, st);
+    // One launch per length class up to the longest chain's; a warp skips the utterances of the other classes.  The
+    // classes are independent (disjoint utterances, scatter-adds into disjoint rows), so they run side by side on
+    // forked streams: the longer classes are register-limited to 12 - 17 warps per SM and leave room for the others
+    // (fork / join with events: stream-ordered for the caller and capturable in a CUDA graph).
+    if (S == 4) return launch_chain<4>(a, st);
+    static cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
+    static cudaEvent_t fork = nullptr, join[3] = {nullptr, nullptr, nullptr};
+    if (fork == nullptr) {
+        BEER_CUDA_TRY(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        for (int i = 0; i < 3; ++i) {
+            BEER_CUDA_TRY(cudaStreamCreateWithFlags(&aux[i], cudaStreamNonBlocking));
+            BEER_CUDA_TRY(cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming));
+        }
+    }
+    BEER_CUDA_TRY(cudaEventRecord(fork, st));
+    const int n_aux = S >= 32 ? 3 : (S >= 16 ? 2 : 1);
+    int rc = BEER_OK;
+    for (int i = 0; i < n_aux && rc == BEER_OK; ++i) {
+        BEER_CUDA_TRY(cudaStreamWaitEvent(aux[i], fork, 0));
+        rc = i == 0 ? launch_chain<8>(a, aux[0]) : (i == 1 ? launch_chain<16>(a, aux[1]) : launch_chain<32>(a, aux[2]));
+        BEER_CUDA_TRY(cudaEventRecord(join[i], aux[i]));
+    }
+    if (rc == BEER_OK) rc = launch_chain<4>(a, st);
+    for (int i = 0; i < n_aux; ++i) BEER_CUDA_TRY(cudaStreamWaitEvent(st, join[i], 0));
     return rc;
 }
 
