@@ -194,3 +194,45 @@ def test_viterbi_training_matches_oracle(C, chunk, scale):
         assert np.abs(acc - info['acc_normal']).max() <= 3e-5 * np.abs(info['acc_normal']).max()
     for g, w in zip(_host(em.post), ng_post):
         np.testing.assert_allclose(g, w, rtol=2e-4, atol=2e-4)
+
+
+@pytest.mark.parametrize('chunk', [None, 170])
+def test_vb_iterations_streamed_mixture_kernels(chunk):
+    """M = 160 Gaussians (20 pdfs x 8) at D = 20: the emission kernel streams its weight image in chunks and stores the
+    per-Gaussian llhs with TMA tensor stores, the statistics kernel runs its bulk-staged mixture variant; three VB
+    iterations (ragged utterances, chunk boundaries inside frame tiles) against the oracle."""
+    from beer_b200 import ops, synthetic
+    from beer_b200.engine import EmissionParams, Utterances, VBEngine, WeightGroup
+    dev = torch.device('cuda', 0)
+    P, S, D, C = 5, 4, 20, 8
+    K, M = P * S, P * S * C
+    lens = [150, 41, 97, 129, 64]
+    graph, _, _ = synthetic.phone_loop_graph(P, S)
+    plan = ops.GraphPlan(graph.init_log_probs.numpy(), graph.final_log_probs.numpy(),
+                         graph.trans_log_probs.numpy(), graph.pdf_id_mapping, n_pdfs=K)
+    means = 2.0 * torch.randn(K, D, generator=torch.Generator().manual_seed(0))
+    full = synthetic.sample_utterances(graph, means, len(lens), max(lens), seed=1, device=dev)
+    full = full.reshape(len(lens), max(lens), D)
+    utts_dev = [full[i, :n] for i, n in enumerate(lens)]
+    X = torch.cat(utts_dev)
+    prior, post = synthetic.initial_normal_gamma(M, D, seed=2, device=dev)
+    conc = torch.full((K, C), 1.0 / C, device=dev)
+    groups = (WeightGroup(0, K, C, conc.clone(), conc.clone()),)
+    em = EmissionParams(prior, post, comp_off=np.arange(K + 1) * C, weight_groups=groups)
+    assert em.use_tc and ops.accumulate_tc_supported(M, D)
+    dprior, dpost = conc.double().cpu().numpy(), conc.double().cpu().numpy()
+    N = sum(lens)
+    eng = VBEngine(em, plan, Utterances(X, lens), datasize=float(N), chunk_frames=chunk, distributed=False)
+    ng_prior, ng_post = _host(prior), _host(post)
+    og = (graph.init_log_probs.double().numpy(), graph.final_log_probs.double().numpy(),
+          graph.trans_log_probs.double().numpy(), graph.pdf_id_mapping)
+    utts = [u.double().cpu().numpy() for u in utts_dev]
+    for it in range(3):
+        want, ng_post, dpost, info = O.vb_iteration_hmm(utts, ng_prior, ng_post, dprior, dpost, og)
+        got = float(eng.step().item())
+        assert abs(got - want) <= 1e-5 * abs(want), (it, got, want)
+        acc = eng.acc.cpu().numpy()
+        assert np.abs(acc - info['acc_normal']).max() <= 3e-5 * np.abs(info['acc_normal']).max()
+    for g, w in zip(_host(em.post), ng_post):
+        np.testing.assert_allclose(g, w, rtol=2e-4, atol=2e-4)
+    np.testing.assert_allclose(groups[0].post.double().cpu().numpy(), dpost, rtol=2e-4, atol=1e-5)
