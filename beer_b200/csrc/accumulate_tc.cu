@@ -664,12 +664,17 @@ __global__ void __launch_bounds__(MIX ? MIX_THREADS : RAW_THREADS, 1) accumulate
             float* B_lo = B_hi + C::B_FLOATS;
             mbar_wait(&bars->raw_full[rs], rph);
             mbar_wait(&bars->empty[st], ((it / STAGES) & 1) ^ 1);
-            if constexpr (MIX) {
-                if (rows < KF) {      // ragged last stage: stale posterior rows -> 0 (w = 0 for those frames)
-                    float* rq0 = const_cast<float*>(rp) + KF * GM;
-                    for (int e = rows * nk + tid; e < KF * nk; e += RAW_PRODUCERS) rq0[e] = 0.f;
-                    asm volatile("bar.sync 1, %0;" ::"n"(RAW_PRODUCERS) : "memory");
+            if (rows < KF) {
+                // ragged last stage of the range: stale posterior and feature rows -> 0 (w = 0 and x = 0 for those
+                // frames), so that the loads below carry no per-element row predicate
+                float* r0 = const_cast<float*>(rp);
+                if constexpr (MIX) {
+                    for (int e = rows * nk + tid; e < KF * nk; e += RAW_PRODUCERS) r0[KF * GM + e] = 0.f;
+                } else {
+                    for (int e = rows * M + tid; e < KF * M; e += RAW_PRODUCERS) r0[e] = 0.f;
                 }
+                for (int e = rows * D + tid; e < KF * D; e += RAW_PRODUCERS) r0[KF * PW + e] = 0.f;
+                asm volatile("bar.sync 1, %0;" ::"n"(RAW_PRODUCERS) : "memory");
             }
             if (a_active) {
 #pragma unroll
@@ -687,7 +692,7 @@ __global__ void __launch_bounds__(MIX ? MIX_THREADS : RAW_THREADS, 1) accumulate
                             const float e = ex2(1.4426950408889634f * (rp[(f0 + i) * GM + gl] - rq[KF * nk]));
                             w = (post != 0.f) ? post * e : 0.f;
                         } else {
-                            w = (f0 + i < rows) ? rp[(f0 + i) * M + gl] : 0.f;
+                            w = rp[(f0 + i) * M + gl];
                         }
                         h[i] = tf32_rn(w);
                         l[i] = w - h[i];
@@ -704,7 +709,7 @@ __global__ void __launch_bounds__(MIX ? MIX_THREADS : RAW_THREADS, 1) accumulate
                     float xh[4], xl[4], qh[4], ql[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const float x = (fq * 4 + i < rows) ? rx[(fq * 4 + i) * D + d] : 0.f;
+                        const float x = rx[(fq * 4 + i) * D + d];
                         const float qq = x * x;
                         xh[i] = tf32_rn(x);
                         xl[i] = x - xh[i];
