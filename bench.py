@@ -67,6 +67,21 @@ def measured_peaks():
     return 6650.0, 'fallback'
 
 
+def measured_bf16_tflops():
+    """Dense bf16 TFLOP/s (sustained figure: the contraction runs inside a long step) from MEASURED_PEAKS.json, else
+    the 1590 fallback of B200_PROFILING.md."""
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(path) as f:
+            p = json.load(f)
+        for k in ('bf16_tflops_sustained', 'bf16_tflops'):
+            if isinstance(p.get(k), (int, float)):
+                return float(p[k]), 'measured'
+    except (OSError, ValueError):
+        pass
+    return 1590.0, 'fallback'
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
@@ -352,6 +367,20 @@ def run_gpu(args, c):
                         'step_alg_bytes_per_frame': 8 * D + 16 * K,
                         'step_frac': (8 * D + 16 * K) * U * T / (ms / args.steps * 1e-3) / 1e9 / peak,
                         'stage_ms': stage_ms}
+            # the whole step against its three rooflines, per GPU: HBM (B_alg = 8D + 16K bytes / frame),
+            # tensor pipe (F_alg = 4 Q M flop / frame at 3xTF32 = bf16 / 6) and the scan's special-function unit
+            # (S_alg = 2 nnz(A) log-add-exp terms / frame, phone loop nnz = 2K - P + P^2, against 148 SMs x 16 MUFU
+            # lanes x the measured SM clock)
+            fps = U * T / (ms / args.steps * 1e-3)
+            bf16, bf16_src = measured_bf16_tflops()
+            Pn = c['n_units']
+            nnz = 2 * K - Pn + Pn * Pn
+            mhz = (clocks or {}).get('sm_mhz') or 1965.0
+            roofline['step_fractions'] = {
+                'hbm': fps * (8 * D + 16 * K) / 1e9 / peak,
+                'tensor_3xtf32': fps * 4 * (2 * D + 2) * M / 1e12 / (bf16 / 6.0),
+                'scan_mufu': fps * 2 * nnz / (148 * 16 * mhz * 1e6),
+                'tensor_peak_tflops': bf16 / 6.0, 'tensor_peak_source': bf16_src + ' bf16 / 6'}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             upw = 96 if C == 1 else 1        # ~10 s of CPU work
