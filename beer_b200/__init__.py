@@ -16,6 +16,6 @@ from .inference import (EvidenceLowerBoundInstance, VBConjugateOptimizer, VBOpti
                         evidence_lower_bound)
 from .models import (HMM, Categorical, CategoricalSet, DiscreteLatentModel,        # noqa: F401
                      DynamicallyOrderedModelSet, JointModelSet, Mixture, MixtureSet, Model, ModelSet,
-                     NormalSet, PhoneLoop, BigramPhoneLoop, SBCategorical)
+                     NormalSet, PhoneLoop, BigramPhoneLoop, SBCategorical, SBCategoricalHyperPrior)
 from .parameters import BayesianParameter, ConjugateBayesianParameter             # noqa: F401
 from .utils import logsumexp, onehot                                               # noqa: F401

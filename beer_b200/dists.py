@@ -12,7 +12,7 @@ import torch
 
 from . import ops
 
-__all__ = ['ConjugateLikelihood', 'ExponentialFamily', 'NormalDiagonalLikelihood', 'NormalGamma',
+__all__ = ['Gamma', 'GammaStdParams', 'GammaLikelihood', 'ConjugateLikelihood', 'ExponentialFamily', 'NormalDiagonalLikelihood', 'NormalGamma',
            'NormalGammaStdParams', 'CategoricalLikelihood', 'Dirichlet', 'DirichletStdParams', 'kl_div',
            'DistributionTypeMismatch', 'SupportDimensionMismatch']
 
@@ -232,6 +232,92 @@ class Dirichlet(ExponentialFamily):
 
     def _natural_grad_update(self, prior, stats, lrate, stats_scale=1.0):
         ops.dirichlet_update(prior.params.concentrations, self.params.concentrations, stats, stats_scale, lrate)
+
+
+# ---------------------------------------------------------------------------------------------
+# Gamma (beer/dists/gamma.py): the hyper-prior over the concentration of a stick-breaking process.  One or a few
+# scalars per model, updated once per VB iteration from a callback: plain tensor arithmetic in fp64, no kernel.
+# ---------------------------------------------------------------------------------------------
+
+class GammaLikelihood(ConjugateLikelihood):
+    """beer/dists/gamma.py:14-56."""
+
+    def __init__(self, dim):
+        self.dim = dim
+
+    def sufficient_statistics_dim(self, zero_stats=True):
+        return 2 * self.dim + (1 if zero_stats else 0)
+
+    @staticmethod
+    def sufficient_statistics(data):
+        return torch.cat([-data, data.log(), torch.ones(len(data), 1, dtype=data.dtype, device=data.device)], dim=-1)
+
+    def __call__(self, pdfvecs, stats):
+        if pdfvecs.dim() == 1:
+            pdfvecs = pdfvecs.view(1, -1)
+        return stats @ pdfvecs.t()
+
+
+class GammaStdParams(torch.nn.Module):
+    """shape, rate (gamma.py:59-79)."""
+
+    def __init__(self, shape, rate):
+        super().__init__()
+        self.register_buffer('shape', _f32(shape).clone())
+        self.register_buffer('rate', _f32(rate).clone())
+
+    @classmethod
+    def from_natural_parameters(cls, natural_params):
+        nat = natural_params.reshape(-1, natural_params.shape[-1])
+        dim = nat.shape[-1] // 2
+        shape, rate = nat[:, dim:] + 1, -nat[:, :dim]
+        if natural_params.dim() == 1:
+            return cls(shape.reshape(-1), rate.reshape(-1))
+        return cls(shape, rate)
+
+
+class Gamma(ExponentialFamily):
+    """beer/dists/gamma.py:82-153."""
+    _std_params_cls = GammaStdParams
+
+    @property
+    def dim(self):
+        shape = self.params.shape
+        return len(shape) if shape.dim() <= 1 else tuple(shape.shape)
+
+    def conjugate(self):
+        return GammaLikelihood(self.params.shape.shape[-1])
+
+    def expected_sufficient_statistics(self):
+        shape, rate = self.params.shape.double(), self.params.rate.double()
+        return torch.cat([shape / rate, torch.digamma(shape) - torch.log(rate)], dim=-1)
+
+    def expected_value(self):
+        return self.params.shape / self.params.rate
+
+    def log_norm(self):
+        shape, rate = self.params.shape.double(), self.params.rate.double()
+        return (torch.lgamma(shape) - shape * torch.log(rate)).sum(dim=-1)
+
+    def natural_parameters(self):
+        return torch.cat([-self.params.rate.double(), self.params.shape.double() - 1], dim=-1)
+
+    def _kl(self, prior, out=None):
+        """basedist.py:243-263 with this distribution as pdf1."""
+        kl = prior.log_norm() - self.log_norm() - torch.sum(
+            self.expected_sufficient_statistics() * (prior.natural_parameters() - self.natural_parameters()), dim=-1)
+        kl = kl.reshape(-1).sum().reshape(1)
+        if out is None:
+            return kl
+        out += kl
+        return out
+
+    def _natural_grad_update(self, prior, stats, lrate, stats_scale=1.0):
+        eta_p, eta_q = prior.natural_parameters(), self.natural_parameters()
+        new = eta_q + lrate * (eta_p + stats_scale * stats.to(eta_q) - eta_q)
+        upd = GammaStdParams.from_natural_parameters(new)
+        self.params.shape.copy_(upd.shape.reshape(self.params.shape.shape))
+        self.params.rate.copy_(upd.rate.reshape(self.params.rate.shape))
 
 
 def kl_div(model1, model2):

@@ -21,11 +21,11 @@ import numpy as np
 import torch
 
 from . import ops
-from .dists import Dirichlet, NormalGamma, frames_of
+from .dists import Dirichlet, Gamma, NormalGamma, frames_of
 from .engine import Utterances
 from .parameters import ConjugateBayesianParameter
 
-__all__ = ['Model', 'DiscreteLatentModel', 'ModelSet', 'NormalSet', 'Categorical', 'SBCategorical', 'CategoricalSet', 'Mixture',
+__all__ = ['Model', 'DiscreteLatentModel', 'ModelSet', 'NormalSet', 'Categorical', 'SBCategorical', 'SBCategoricalHyperPrior', 'CategoricalSet', 'Mixture',
            'MixtureSet', 'JointModelSet', 'DynamicallyOrderedModelSet', 'HMM', 'PhoneLoop', 'BigramPhoneLoop', 'UnknownCovarianceType']
 
 f32, f64, i32, i64 = torch.float32, torch.float64, torch.int32, torch.int64
@@ -431,6 +431,44 @@ class SBCategorical(Model):
 
     def accumulate(self, stats, parent_msg=None):
         return {self.stickbreaking: stats.sum(dim=0).to(f64)}
+
+
+class SBCategoricalHyperPrior(SBCategorical):
+    """Stick-breaking weights with a Gamma hyper-prior over the concentration of the process
+    (categorical.py:168-209; `gamma_dirichlet_process`, the CLI's default unit-weight prior): after every update of
+    the sticks the concentration's posterior is re-estimated from E[ln(1 - v_k)], and its mean becomes the second
+    concentration of every stick's prior."""
+
+    @classmethod
+    def create(cls, truncation, prior_strength=1., hyper_prior_strength=1., device=None):
+        dev = 'cuda' if device is None else device
+        mean = torch.ones(1, dtype=f32, device=dev) * prior_strength
+        shape = torch.ones_like(mean) * hyper_prior_strength
+        rate = hyper_prior_strength / mean
+        concentration = ConjugateBayesianParameter(Gamma.from_std_parameters(shape, rate),
+                                                   Gamma.from_std_parameters(shape.clone(), rate.clone()))
+        params = torch.ones(truncation, 2, dtype=f32, device=dev)
+        params[:, 1] = prior_strength
+        sb = ConjugateBayesianParameter(Dirichlet.from_std_parameters(params),
+                                        Dirichlet.from_std_parameters(params.clone()))
+        return cls(sb, concentration)
+
+    def __init__(self, stickbreaking, concentration):
+        super().__init__(stickbreaking)
+        self.concentration = concentration
+        self.stickbreaking.register_callback(self._on_stickbreaking_update)
+        self.concentration.register_callback(self._on_concentration_update)
+        self._on_concentration_update()
+
+    def _on_concentration_update(self):
+        self.stickbreaking.prior.params.concentrations[:, 1] = self.concentration.value().to(f32)
+
+    def _on_stickbreaking_update(self):
+        _, log_1_v = self._log_prob()
+        pad = torch.ones_like(log_1_v)
+        sb_stats = torch.cat([log_1_v[:, None], pad[:, None]], dim=-1)
+        self.concentration.stats = sb_stats.sum(dim=0)
+        self.concentration.natural_grad_update(lrate=1.)
 
 
 class CategoricalSet(ModelSet):

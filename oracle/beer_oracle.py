@@ -499,6 +499,17 @@ def sb_transform_stats(counts):
     return out, ordering
 
 
+def sb_hyper_update(sb_post, ordering, conc_prior):
+    """SBCategoricalHyperPrior._on_stickbreaking_update (categorical.py:200-209): Gamma posterior of the
+    concentration from E[ln(1 - v_k)] of the updated sticks (natural-gradient step with lrate 1 = prior + statistics,
+    gamma.py:148-153).  conc_prior = (shape, rate); returns the posterior (shape, rate); its mean shape / rate is the
+    second concentration of every stick's prior from then on (categorical.py:196-198)."""
+    c = sb_post[ordering]
+    log_1_v = digamma(c[:, 1]) - digamma(c.sum(axis=-1))
+    shape0, rate0 = conc_prior
+    return shape0 + len(c), rate0 - log_1_v.sum()
+
+
 def sb_phoneloop_update_graph(trans_log, conc, ordering, start_idxs, end_idxs):
     """PhoneLoop._on_weights_update with stick-breaking weights (phoneloop.py:53-65)."""
     logw = sb_log_weights(conc, ordering).astype(trans_log.dtype)

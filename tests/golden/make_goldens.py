@@ -420,7 +420,7 @@ def gold_alignment_archive():
     save('alis_expected', **plain)
 
 
-def gold_sb_phoneloop():
+def gold_sb_phoneloop(hyper=False):
     """PhoneLoop whose unit weights have a truncated stick-breaking prior (categorical.py:82-165), the model the
     CLI builds by default (mkphoneloop.py: `gamma_dirichlet_process` -> SBCategorical*): the statistics are
     re-ordered and turned into Beta statistics by a callback right before the update."""
@@ -433,7 +433,10 @@ def gold_sb_phoneloop():
     out = dict(graph_arrays(cg, 'g0_'))
     ns = beer.NormalSet.create(torch.zeros(D), torch.ones(D), size=K, prior_strength=1., noise_std=1.,
                                cov_type='diagonal')
-    sb = beer.SBCategorical.create(len(start_pdf), prior_strength=2.)
+    if hyper:
+        sb = beer.SBCategoricalHyperPrior.create(len(start_pdf), prior_strength=2., hyper_prior_strength=1.)
+    else:
+        sb = beer.SBCategorical.create(len(start_pdf), prior_strength=2.)
     pl = beer.PhoneLoop.create(cg, start_pdf, end_pdf, ns, categorical=sb).double()
     means = 2.0 * rng.standard_normal((K, D))
     X1 = sample_from_graph(rng, cg, means, 45)
@@ -458,8 +461,15 @@ def gold_sb_phoneloop():
         out[f'it{it + 1}_trans'] = npy(pl.graph.trans_log_probs)
         out[f'it{it + 1}_sb_post'] = npy(w.posterior.params.concentrations)
         out[f'it{it + 1}_ordering'] = npy(sb.ordering)
+        if hyper:
+            out[f'it{it + 1}_conc'] = np.asarray([float(sb.concentration.posterior.params.shape),
+                                                  float(sb.concentration.posterior.params.rate)])
+            out[f'it{it + 1}_sb_prior'] = npy(w.prior.params.concentrations)
     out.update(elbos=np.asarray(elbos), mean3=npy(sb.mean), **ng_params(p.posterior, 'post3_'))
-    save('sb_phoneloop', **out)
+    if hyper:
+        out.update(conc_prior=np.asarray([float(sb.concentration.prior.params.shape),
+                                          float(sb.concentration.prior.params.rate)]))
+    save('sb_hyper_phoneloop' if hyper else 'sb_phoneloop', **out)
 
 
 # ---------------------------------------------------------------------------
@@ -535,6 +545,7 @@ if __name__ == '__main__':
     gold_bigram_phoneloop()
     gold_alignment_archive()
     gold_sb_phoneloop()
+    gold_sb_phoneloop(hyper=True)
     gold_dense_ergodic()
     gold_graph_compile()
     gold_fbank()

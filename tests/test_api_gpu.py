@@ -426,16 +426,21 @@ def test_mixture_cfg5_shape(beer):
     np.testing.assert_allclose(w.posterior.params.concentrations.double().cpu().numpy(), dpost, rtol=3e-4, atol=1e-5)
 
 
-def test_stick_breaking_phoneloop(beer):
-    """PhoneLoop.create(..., categorical=SBCategorical.create(P, prior_strength)) — the unit-weight prior the CLI uses
-    by default (mkphoneloop.py) — against the live-reference golden: three accumulate/update iterations."""
-    g = load_golden('sb_phoneloop')
+@pytest.mark.parametrize('hyper', [False, True])
+def test_stick_breaking_phoneloop(beer, hyper):
+    """PhoneLoop.create(..., categorical=SBCategorical[HyperPrior].create(P, ...)) — the unit-weight priors of the CLI
+    (mkphoneloop.py; `gamma_dirichlet_process`, its default, is the hyper-prior variant) — against the live-reference
+    goldens: three accumulate/update iterations."""
+    g = load_golden('sb_hyper_phoneloop' if hyper else 'sb_phoneloop')
     cg = compiled(beer, g, 'g0_')
     D = g['X1'].shape[1]
     ns = normalset(beer, g, cg.n_states, D)
     start_pdf = {f'u{i}': int(s) for i, s in enumerate(g['start_idxs'])}
     end_pdf = {f'u{i}': int(s) for i, s in enumerate(g['end_idxs'])}
-    sb = beer.SBCategorical.create(len(start_pdf), prior_strength=2., device=DEV)
+    if hyper:
+        sb = beer.SBCategoricalHyperPrior.create(len(start_pdf), prior_strength=2., hyper_prior_strength=1., device=DEV)
+    else:
+        sb = beer.SBCategorical.create(len(start_pdf), prior_strength=2., device=DEV)
     pl = beer.PhoneLoop.create(cg, start_pdf, end_pdf, ns, categorical=sb)
     w = sb.stickbreaking
     np.testing.assert_allclose(w.prior.params.concentrations.cpu().numpy(), g['sb_prior'], rtol=1e-6)
@@ -455,6 +460,10 @@ def test_stick_breaking_phoneloop(beer):
         optim.step()
         np.testing.assert_array_equal(sb.ordering.cpu().numpy(), g[f'it{it + 1}_ordering'])
         np.testing.assert_allclose(w.posterior.params.concentrations.cpu().numpy(), g[f'it{it + 1}_sb_post'], rtol=2e-4)
+        if hyper:
+            cp = sb.concentration.posterior.params
+            np.testing.assert_allclose([float(cp.shape), float(cp.rate)], g[f'it{it + 1}_conc'], rtol=2e-4)
+            np.testing.assert_allclose(w.prior.params.concentrations.cpu().numpy(), g[f'it{it + 1}_sb_prior'], rtol=2e-4)
         got, want = pl.graph.trans_log_probs.numpy(), g[f'it{it + 1}_trans']
         fin = np.isfinite(want)
         assert np.array_equal(np.isfinite(got), fin)

@@ -1,5 +1,6 @@
 """Pin the numpy oracle to the fp64 outputs of the live reference (tests/golden/*.npz)."""
 import numpy as np
+import pytest
 
 from oracle import beer_oracle as O
 from conftest import load_golden
@@ -253,13 +254,15 @@ def test_bigram_and_uneven_phoneloop():
         np.testing.assert_allclose(post[0], g[tag + '_post2_mean'], rtol=1e-7, atol=1e-9)
 
 
-def test_stick_breaking_phoneloop():
-    """PhoneLoop with SBCategorical unit weights (categorical.py:82-165), three VB iterations over two utterances."""
-    g = load_golden('sb_phoneloop')
+@pytest.mark.parametrize('hyper', [False, True])
+def test_stick_breaking_phoneloop(hyper):
+    """PhoneLoop with SBCategorical / SBCategoricalHyperPrior unit weights (categorical.py:82-209), three VB
+    iterations over two utterances."""
+    g = load_golden('sb_hyper_phoneloop' if hyper else 'sb_phoneloop')
     gr = graph(g)
     starts, ends = list(g['start_idxs']), list(g['end_idxs'])
     post, prior = ng(g, 'post0_'), ng(g, 'prior_')
-    sb_post, sb_prior = g['sb_post0'], g['sb_prior']
+    sb_post, sb_prior = g['sb_post0'], g['sb_prior'].copy()
     ordering = np.arange(len(starts))
     trans = gr[2].copy()
     N = len(g['X1']) + len(g['X2'])
@@ -278,6 +281,11 @@ def test_stick_breaking_phoneloop():
         stats, ordering = O.sb_transform_stats(N / frames * counts)
         sb_post = O.natural_grad_update_dirichlet(sb_prior, sb_post, stats, 1.)
         trans = O.sb_phoneloop_update_graph(trans, sb_post, ordering, starts, ends)
+        if hyper:
+            shape, rate = O.sb_hyper_update(sb_post, ordering, tuple(g['conc_prior']))
+            np.testing.assert_allclose([shape, rate], g[f'it{it + 1}_conc'], rtol=1e-9)
+            sb_prior[:, 1] = shape / rate
+            np.testing.assert_allclose(sb_prior, g[f'it{it + 1}_sb_prior'], rtol=1e-9)
         np.testing.assert_array_equal(ordering, g[f'it{it + 1}_ordering'])
         np.testing.assert_allclose(sb_post, g[f'it{it + 1}_sb_post'], rtol=1e-8)
         np.testing.assert_allclose(trans, g[f'it{it + 1}_trans'], rtol=1e-9, atol=1e-12)
