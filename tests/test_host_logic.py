@@ -270,3 +270,22 @@ def test_alignment_archive_written_by_the_reference():
     np.testing.assert_array_equal(cb.pdf.numpy()[:12], want['utt_c_map'])
     np.testing.assert_allclose(cb.log_self.numpy()[12:], np.diagonal(want['utt_b_trans']), rtol=1e-6)
     assert 'beer' not in sys.modules or sys.modules['beer'].__name__ != 'beer'
+
+
+def test_gamma_distribution_math():
+    """beer/dists/gamma.py restated: natural parameters, expected statistics, log-normaliser, KL
+    (basedist.py:243-263) and the natural-gradient step with lrate 1 (posterior = prior + statistics), against scipy."""
+    from scipy.special import digamma, gammaln
+    from beer_b200.dists import Gamma, kl_div
+    a1, b1, a0, b0 = 5.0, 3.5, 1.0, 0.5
+    q = Gamma.from_std_parameters(torch.tensor([a1]), torch.tensor([b1]))
+    p = Gamma.from_std_parameters(torch.tensor([a0]), torch.tensor([b0]))
+    np.testing.assert_allclose(q.natural_parameters().numpy(), [-b1, a1 - 1])
+    np.testing.assert_allclose(q.expected_sufficient_statistics().numpy(), [a1 / b1, digamma(a1) - np.log(b1)], rtol=1e-12)
+    np.testing.assert_allclose(float(q.log_norm()), gammaln(a1) - a1 * np.log(b1), rtol=1e-12)
+    np.testing.assert_allclose(float(q.expected_value()), a1 / b1, rtol=1e-6)
+    # closed form KL(Gamma(a1, b1) || Gamma(a0, b0))
+    want = (a1 - a0) * digamma(a1) - gammaln(a1) + gammaln(a0) + a0 * (np.log(b1) - np.log(b0)) + a1 * (b0 - b1) / b1
+    np.testing.assert_allclose(float(kl_div(q, p)), want, rtol=1e-10)
+    q._natural_grad_update(p, torch.tensor([-2.0, 4.0], dtype=torch.float64), 1.0)
+    np.testing.assert_allclose([float(q.params.shape), float(q.params.rate)], [a0 + 4.0, b0 + 2.0], rtol=1e-6)
