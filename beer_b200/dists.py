@@ -71,6 +71,15 @@ class NormalDiagonalLikelihood(ConjugateLikelihood):
     def sufficient_statistics(data):
         """T(x) = [x, -x^2/2, -1/2, 1/2] (normalgamma.py:19-27).  The source frames stay attached
         to the result so that the kernels downstream read them instead of slicing T(x)."""
+        if torch.is_tensor(data) and data.requires_grad:
+            # differentiable inputs (an encoder in front of the model, vae.py): the statistics are formed by tensor
+            # arithmetic so that the graph reaches `data`; the kernels downstream read the frames themselves and the
+            # model's expected log-likelihood re-attaches its gradient to them (models._FrameLlhGrad)
+            x = data.to(torch.float32)
+            ones = torch.ones(len(x), 1, dtype=x.dtype, device=x.device)
+            stats = torch.cat([x, -0.5 * x * x, -0.5 * ones, 0.5 * ones], dim=-1)
+            stats._beer_frames = x
+            return stats
         X = _f32(data)
         stats = ops.normal_sufficient_statistics(X)
         stats._beer_frames = X
@@ -91,6 +100,12 @@ def frames_of(stats, dim):
     if X is None:
         X = stats[:, :dim].detach().to(torch.float32).contiguous()
     return X
+
+
+def frames_with_grad(stats):
+    """The frames behind `stats` when they are part of an autograd graph, else None."""
+    X = getattr(stats, '_beer_frames', None)
+    return X if (X is not None and X.requires_grad) else None
 
 
 class NormalGammaStdParams(torch.nn.Module):

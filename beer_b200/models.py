@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .dists import Dirichlet, Gamma, NormalGamma, frames_of
+from .dists import Dirichlet, Gamma, NormalGamma, frames_of, frames_with_grad
 from .engine import Utterances
 from .parameters import ConjugateBayesianParameter
 
@@ -541,7 +541,7 @@ class Mixture(DiscreteLatentModel):
         """Per-frame E[ln p(x, z)] - KL(q(z) || p(z)) = logsumexp_c(llh_c + E ln pi_c); with
         `labels` the responsibilities are one-hot and there is no KL term (mixture.py:70-93)."""
         em = self._emission()
-        X = frames_of(stats, em.D)
+        X = frames_of(stats, em.D).detach()
         pdf, comp, fref = em.llh(X, want_comp=True)
         self.cache.update(X=X, pdf_llh=pdf, comp_llh=comp, emission=em, labels=None)
         if labels is None:
@@ -607,7 +607,7 @@ class MixtureSet(ModelSet):
         """Per-mixture log-normaliser [N, K]; the component llhs stay cached for accumulate
         (mixtureset.py:85-98)."""
         em = _Emission(_leaves(self))
-        X = frames_of(stats, em.D)
+        X = frames_of(stats, em.D).detach()
         pdf, comp, fref = em.llh(X)
         self.cache.update(X=X, pdf_llh=pdf, comp_llh=comp, emission=em)
         return pdf + fref[:, None]
@@ -645,7 +645,7 @@ class JointModelSet(ModelSet):
 
     def expected_log_likelihood(self, stats):
         em = _Emission(_leaves(self))
-        X = frames_of(stats, em.D)
+        X = frames_of(stats, em.D).detach()
         pdf, comp, fref = em.llh(X)
         self.cache.update(X=X, pdf_llh=pdf, comp_llh=comp, emission=em)
         return pdf + fref[:, None]
@@ -704,6 +704,27 @@ class DynamicallyOrderedModelSet(ModelSet):
         return len(self.original_modelset)
 
 
+class _FrameLlhGrad(torch.autograd.Function):
+    """Gradient of the per-frame expected log-likelihood w.r.t. the frames with the posteriors held fixed
+    (hmm.py:79-87: the inference runs on `pc_llhs.detach()`, the returned value is `(pc_llhs * resps).sum(-1)`):
+    d/dx_t sum_k w_tk llh_k(x_t) = sum_k w_tk (E[lambda_k mu_k] - x_t E[lambda_k]), w = scale * posteriors per pdf.
+    Forward hands back the values the kernels computed; backward is two [N, Kp] x [Kp, D] products (a library GEMM:
+    this is the encoder-facing side of the model, not the VB hot path).  Single-Gaussian pdfs only."""
+
+    @staticmethod
+    def forward(ctx, X, frame, pdf_post, ets, dim):
+        ctx.save_for_backward(X, pdf_post, ets)
+        ctx.dim = dim
+        return frame.clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        X, post, ets = ctx.saved_tensors
+        D = ctx.dim
+        g = post @ ets[:, :D] - X.detach() * (post @ ets[:, D:2 * D])
+        return grad_out[:, None] * g, None, None, None, None
+
+
 # ---------------------------------------------------------------------------------------------
 # HMM (beer/models/hmm.py)
 # ---------------------------------------------------------------------------------------------
@@ -738,7 +759,7 @@ class HMM(DiscreteLatentModel):
         reference computes whenever no inference graph is given (hmm.py:76), as `trans_resps`.)"""
         graph = self.graph if inference_graph is None else inference_graph
         em = self._emission()
-        X = frames_of(stats, em.D)
+        X = frames_of(stats, em.D).detach()
         off, utts = _offsets_of(stats, X.shape[0], X.device)
         pdf, comp, fref = em.llh(X)
         if isinstance(graph, (list, tuple)):
@@ -778,6 +799,12 @@ class HMM(DiscreteLatentModel):
                 self.cache['first_state_post'] = r['state_post'][off[:-1]]      # gamma_0 of every utterance
         self.cache.update(X=X, pdf_post=post, pdf_llh=pdf, comp_llh=comp, emission=em, scale=scale,
                           utts=utts, utt_exp_llh=utt_ell)
+        Xg = frames_with_grad(stats)
+        if Xg is not None:
+            if em.has_mixtures:
+                raise NotImplementedError('gradients w.r.t. the frames are available for single-Gaussian pdfs')
+            ets = ops.normalgamma_expected_stats(*em._cat('posterior'))
+            frame = _FrameLlhGrad.apply(Xg, frame, post, ets, em.D)
         return frame
 
     def accumulate(self, stats, parent_msg=None):
@@ -791,7 +818,7 @@ class HMM(DiscreteLatentModel):
         graph = self.graph if inference_graph is None else inference_graph
         em = self._emission()
         stats = self.sufficient_statistics(data)
-        X = frames_of(stats, em.D)
+        X = frames_of(stats, em.D).detach()
         off, _ = _offsets_of(stats, X.shape[0], X.device)
         pdf, _, _ = em.llh(X, want_comp=False)
         path = ops.hmm_viterbi(graph.plan(n_pdfs=em.Kp), pdf, off, scale=scale).cpu().long()
@@ -804,7 +831,7 @@ class HMM(DiscreteLatentModel):
         graph = self.graph if inference_graph is None else inference_graph
         em = self._emission()
         stats = self.sufficient_statistics(data)
-        X = frames_of(stats, em.D)
+        X = frames_of(stats, em.D).detach()
         off, _ = _offsets_of(stats, X.shape[0], X.device)
         pdf, _, fref = em.llh(X, want_comp=False)
         r = ops.hmm_forward_backward(graph.plan(n_pdfs=em.Kp), pdf, fref, off, scale=scale, want_state_post=True,

@@ -472,6 +472,33 @@ def gold_sb_phoneloop(hyper=False):
     save('sb_hyper_phoneloop' if hyper else 'sb_phoneloop', **out)
 
 
+def gold_input_gradient():
+    """d sum_t exp_llh_t / dX through HMM.expected_log_likelihood (the posteriors are detached, hmm.py:79-87): the
+    gradient an encoder in front of the HMM receives (HMM-VAE, vae.py).  Built on the models of 'hmm_small' /
+    'hmm_scaled' (their goldens must exist)."""
+    out = {}
+    for name in ('hmm_small', 'hmm_scaled'):
+        g = np.load(os.path.join(OUT, name + '.npz'))
+        cg = beer.graph.CompiledGraph(torch.from_numpy(g['g_init']), torch.from_numpy(g['g_final']),
+                                      torch.from_numpy(g['g_trans']), [int(i) for i in g['g_map']])
+        K, D = cg.n_states, g['X'].shape[1]
+        ns = beer.NormalSet.create(torch.zeros(D), torch.ones(D), size=K, prior_strength=1., noise_std=1.,
+                                   cov_type='diagonal')
+        for dist, pre in ((ns.means_precisions.prior, 'prior_'), (ns.means_precisions.posterior, 'post0_')):
+            for pn in ('mean', 'scale', 'shape', 'rates'):
+                getattr(dist.params, pn).copy_(torch.from_numpy(g[pre + pn]).reshape(getattr(dist.params, pn).shape))
+        hmm = beer.HMM.create(cg, ns).double()
+        X = torch.from_numpy(g['X']).double().requires_grad_(True)
+        exp_llh = hmm.expected_log_likelihood(hmm.sufficient_statistics(X), inference_graph=hmm.graph,
+                                              scale=float(g['scale']))
+        np.testing.assert_allclose(npy(exp_llh), g['exp_llh'], rtol=1e-9)
+        w = torch.linspace(0.5, 1.5, len(X), dtype=torch.float64)        # a non-trivial upstream gradient
+        (exp_llh * w).sum().backward()
+        out[name + '_grad'] = npy(X.grad)
+        out[name + '_upstream'] = npy(w)
+    save('hmm_input_grad', **out)
+
+
 # ---------------------------------------------------------------------------
 def gold_dense_ergodic():
     """Dense ergodic transitions as in tests/test_hmm.py:149-151, with exact
@@ -546,6 +573,7 @@ if __name__ == '__main__':
     gold_alignment_archive()
     gold_sb_phoneloop()
     gold_sb_phoneloop(hyper=True)
+    gold_input_gradient()
     gold_dense_ergodic()
     gold_graph_compile()
     gold_fbank()

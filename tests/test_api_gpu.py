@@ -470,3 +470,23 @@ def test_stick_breaking_phoneloop(beer, hyper):
         np.testing.assert_allclose(got[fin], want[fin], rtol=2e-4, atol=2e-4)
     np.testing.assert_allclose(elbos, g['elbos'], rtol=1e-5)
     np.testing.assert_allclose(sb.mean.cpu().numpy(), g['mean3'], rtol=2e-4)
+
+
+@pytest.mark.parametrize('name', ['hmm_small', 'hmm_scaled'])
+def test_gradient_wrt_frames(beer, name):
+    """`(exp_llh * w).sum().backward()` reaches the frames with the posteriors held fixed (hmm.py:79-87), the gradient
+    an encoder in front of the HMM receives (HMM-VAE): against the live reference's autograd."""
+    g, gg = load_golden(name), load_golden('hmm_input_grad')
+    graph = compiled(beer, g)
+    D = g['X'].shape[1]
+    hmm = beer.HMM.create(graph, normalset(beer, g, graph.n_states, D))
+    X = t32(g['X']).requires_grad_(True)
+    exp_llh = hmm.expected_log_likelihood(hmm.sufficient_statistics(X), inference_graph=graph, scale=float(g['scale']))
+    np.testing.assert_allclose(exp_llh.detach().double().cpu().numpy(), g['exp_llh'], rtol=1e-5, atol=1e-4)
+    (exp_llh * t32(gg[name + '_upstream'])).sum().backward()
+    want = gg[name + '_grad']
+    assert np.abs(X.grad.double().cpu().numpy() - want).max() <= 2e-5 * np.abs(want).max()
+    # the VB statistics of the same call are untouched by the autograd path
+    acc = hmm.accumulate(None)
+    par = hmm.modelset.original_modelset.means_precisions
+    assert np.abs(acc[par].cpu().numpy() - g['acc_normal']).max() <= 3e-5 * np.abs(g['acc_normal']).max()
