@@ -43,6 +43,7 @@ SIGNATURES = {
     'beer_accumulate_tc_supported': (C.c_int, [C.c_int, C.c_int]),
     'beer_accumulate_stats_tc': (C.c_int, [c_ptr, C.c_int64, C.c_int, c_ptr, C.c_int64, c_ptr, C.c_int64,
                                            c_ptr, c_ptr, C.c_int, C.c_int, c_ptr, c_ptr]),
+    'beer_accumulate_stats_path': (C.c_int, [c_ptr, C.c_int64, C.c_int, c_ptr, C.c_float, C.c_int, c_ptr, c_ptr]),
     'beer_mixture_weight_stats': (C.c_int, [c_ptr, C.c_int, C.c_int, c_ptr, C.c_int, c_ptr, c_ptr]),
     'beer_normalgamma_update': (C.c_int, [c_ptr] * 9 + [C.c_double, C.c_double, C.c_int, C.c_int, c_ptr]),
     'beer_normalgamma_kl': (C.c_int, [c_ptr] * 8 + [C.c_int, C.c_int, c_ptr, c_ptr]),

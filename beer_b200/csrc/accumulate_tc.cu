@@ -44,6 +44,8 @@ struct Args {
     int64_t ld_pdf;
     const float* comp_llh;
     const int32_t* comp_off;
+    const int32_t* pdf_ids;     // path mode: pdf of every frame ([N rounded up to 4] int32), weight = path_scale
+    float path_scale;
     int Kp, M, C;
     double* acc;
     int n_gtiles;
@@ -459,8 +461,12 @@ struct RawCfg {
     }
 };
 
-template <int D4, bool MIX>
-__global__ void __launch_bounds__(MIX ? MIX_THREADS : RAW_THREADS, 1) accumulate_tc_raw_kernel(Args a, int RS) {
+// MODE: 0 = dense posteriors of one Gaussian tile, 1 = mixtures, 2 = PATH: the posteriors are the one-hot rows of a
+// state path (Viterbi training, hmm.py:42-58), never materialised: a stage brings the 32 pdf ids of its frames
+// (128 bytes instead of 32 x M floats) and the producers form w = (pdf id == Gaussian) ? scale : 0.
+template <int D4, int MODE>
+__global__ void __launch_bounds__(MODE == 1 ? MIX_THREADS : RAW_THREADS, 1) accumulate_tc_raw_kernel(Args a, int RS) {
+    constexpr bool MIX = MODE == 1, PATH = MODE == 2;
     using C = RawCfg<D4>;
     constexpr int D = C::D, NB = C::NB, KG = C::KG, KF = C::KF, STAGES = RAW_OPS;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -472,7 +478,7 @@ __global__ void __launch_bounds__(MIX ? MIX_THREADS : RAW_THREADS, 1) accumulate
     const int g0 = gtile * GM;
     const int M = MIX ? min(GM, a.M - g0) : a.M;                // Gaussians of this tile
     const int nk = MIX ? GM / a.C : 0, k0 = MIX ? g0 / a.C : 0;
-    const int PW = MIX ? GM + 2 * nk : M;                      // floats per frame ahead of the features
+    const int PW = MIX ? GM + 2 * nk : (PATH ? 1 : M);         // floats per frame ahead of the features
     const int raw_floats = KF * (PW + D);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -562,9 +568,15 @@ __global__ void __launch_bounds__(MIX ? MIX_THREADS : RAW_THREADS, 1) accumulate
                 const uint32_t rows = (uint32_t)min((int64_t)KF, f_end - t0);
                 mbar_wait(&bars->raw_empty[rs], rph ^ 1);
                 float* dst = ring + (size_t)rs * raw_floats;
-                mbar_arrive_expect_tx(&bars->raw_full[rs], rows * (uint32_t)(M + D) * 4u);
-                bulk_g2s(dst, a.pdf_post + (size_t)t0 * M, rows * (uint32_t)M * 4u, &bars->raw_full[rs]);
-                bulk_g2s(dst + KF * M, a.X + (size_t)t0 * D, rows * (uint32_t)D * 4u, &bars->raw_full[rs]);
+                if constexpr (PATH) {
+                    const uint32_t idb = ((rows + 3u) & ~3u) * 4u;       // whole 16-byte pieces (the id array is padded)
+                    mbar_arrive_expect_tx(&bars->raw_full[rs], idb + rows * (uint32_t)D * 4u);
+                    bulk_g2s(dst, a.pdf_ids + t0, idb, &bars->raw_full[rs]);
+                } else {
+                    mbar_arrive_expect_tx(&bars->raw_full[rs], rows * (uint32_t)(M + D) * 4u);
+                    bulk_g2s(dst, a.pdf_post + (size_t)t0 * M, rows * (uint32_t)M * 4u, &bars->raw_full[rs]);
+                }
+                bulk_g2s(dst + KF * PW, a.X + (size_t)t0 * D, rows * (uint32_t)D * 4u, &bars->raw_full[rs]);
                 if (++rs == RS) {
                     rs = 0;
                     rph ^= 1;
@@ -670,6 +682,8 @@ __global__ void __launch_bounds__(MIX ? MIX_THREADS : RAW_THREADS, 1) accumulate
                 float* r0 = const_cast<float*>(rp);
                 if constexpr (MIX) {
                     for (int e = rows * nk + tid; e < KF * nk; e += RAW_PRODUCERS) r0[KF * GM + e] = 0.f;
+                } else if constexpr (PATH) {
+                    for (int e = rows + tid; e < KF; e += RAW_PRODUCERS) reinterpret_cast<int*>(r0)[e] = -1;
                 } else {
                     for (int e = rows * M + tid; e < KF * M; e += RAW_PRODUCERS) r0[e] = 0.f;
                 }
@@ -691,6 +705,8 @@ __global__ void __launch_bounds__(MIX ? MIX_THREADS : RAW_THREADS, 1) accumulate
                             const float post = rq[0];
                             const float e = ex2(1.4426950408889634f * (rp[(f0 + i) * GM + gl] - rq[KF * nk]));
                             w = (post != 0.f) ? post * e : 0.f;
+                        } else if constexpr (PATH) {
+                            w = (reinterpret_cast<const int*>(rp)[f0 + i] == gl) ? a.path_scale : 0.f;
                         } else {
                             w = rp[(f0 + i) * M + gl];
                         }
@@ -772,17 +788,18 @@ __global__ void __launch_bounds__(MIX ? MIX_THREADS : RAW_THREADS, 1) accumulate
     }
 }
 
-template <int D4, bool MIX>
+template <int D4, int MODE>
 static int launch_raw(const Args& a0, cudaStream_t st) {
+    constexpr bool MIX = MODE == 1;
     using C = RawCfg<D4>;
     Args a = a0;
-    const int pw = MIX ? GM + 2 * (GM / a.C) : a.M;
+    const int pw = MIX ? GM + 2 * (GM / a.C) : (MODE == 2 ? 1 : a.M);
     const int RS = C::raw_stages(pw);
     if (RS < 3) return BEER_ERR_UNSUPPORTED;
     const size_t smem = C::FIXED + (size_t)RS * C::raw_stage_bytes(pw);
     static bool attr_set = false;
     if (!attr_set) {
-        BEER_CUDA_TRY(cudaFuncSetAttribute(accumulate_tc_raw_kernel<D4, MIX>,
+        BEER_CUDA_TRY(cudaFuncSetAttribute(accumulate_tc_raw_kernel<D4, MODE>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
@@ -795,7 +812,7 @@ static int launch_raw(const Args& a0, cudaStream_t st) {
     fpc = (fpc + RAW_KF - 1) / RAW_KF * RAW_KF;
     chunks = (a.N + fpc - 1) / fpc;
     a.frames_per_cta = fpc;
-    accumulate_tc_raw_kernel<D4, MIX><<<(int)(chunks * a.n_gtiles), MIX ? MIX_THREADS : RAW_THREADS, smem, st>>>(a, RS);
+    accumulate_tc_raw_kernel<D4, MODE><<<(int)(chunks * a.n_gtiles), MIX ? MIX_THREADS : RAW_THREADS, smem, st>>>(a, RS);
     BEER_LAUNCH_CHECK();
     return BEER_OK;
 }
@@ -827,6 +844,7 @@ int beer_accumulate_stats_tc(const float* X, int64_t N, int D, const float* pdf_
     kctc::Args a;
     a.X = X; a.N = N; a.pdf_post = pdf_post; a.ld_post = ld_post; a.pdf_llh = pdf_llh; a.ld_pdf = ld_pdf;
     a.comp_llh = comp_llh; a.comp_off = comp_off; a.Kp = Kp; a.M = M; a.C = M / Kp; a.acc = acc_normal;
+    a.pdf_ids = nullptr; a.path_scale = 0.f;
     a.n_gtiles = 0; a.frames_per_cta = 0;
     cudaStream_t st = (cudaStream_t)stream;
     // dense posteriors of a single Gaussian tile: bulk-staged kernel (every stage is two contiguous copies)
@@ -834,8 +852,8 @@ int beer_accumulate_stats_tc(const float* X, int64_t N, int D, const float* pdf_
         ((uintptr_t)pdf_post & 15) == 0 && getenv("BEER_B200_KC_NO_BULK") == nullptr) {
         int rc = BEER_ERR_UNSUPPORTED;
         switch (D / 4) {
-            case 5: rc = kctc::launch_raw<5, false>(a, st); break;      // wider D: the drain's register sums
-            case 10: rc = kctc::launch_raw<10, false>(a, st); break;    // do not fit 18 warps per SM
+            case 5: rc = kctc::launch_raw<5, 0>(a, st); break;      // wider D: the drain's register sums
+            case 10: rc = kctc::launch_raw<10, 0>(a, st); break;    // do not fit 18 warps per SM
         }
         if (rc != BEER_ERR_UNSUPPORTED) return rc;
     }
@@ -846,8 +864,8 @@ int beer_accumulate_stats_tc(const float* X, int64_t N, int D, const float* pdf_
         getenv("BEER_B200_KC_NO_BULK") == nullptr) {
         int rc = BEER_ERR_UNSUPPORTED;
         switch (D / 4) {
-            case 5: rc = kctc::launch_raw<5, true>(a, st); break;
-            case 10: rc = kctc::launch_raw<10, true>(a, st); break;
+            case 5: rc = kctc::launch_raw<5, 1>(a, st); break;
+            case 10: rc = kctc::launch_raw<10, 1>(a, st); break;
         }
         if (rc != BEER_ERR_UNSUPPORTED) return rc;
     }
@@ -858,6 +876,20 @@ int beer_accumulate_stats_tc(const float* X, int64_t N, int D, const float* pdf_
         case 20: return kctc::launch<20, 32, 2>(a, st);
     }
     return BEER_ERR_UNSUPPORTED;
+}
+
+int beer_accumulate_stats_path(const float* X, int64_t N, int D, const int32_t* pdf_ids, float scale, int M,
+                               double* acc_normal, void* stream) {
+    if (!X || !pdf_ids || !acc_normal || N < 0 || D <= 0 || M <= 0) return BEER_ERR_ARG;
+    if (M > kctc::GM || !(D == 20 || D == 40)) return BEER_ERR_UNSUPPORTED;
+    if (((uintptr_t)X & 15) != 0 || ((uintptr_t)pdf_ids & 15) != 0) return BEER_ERR_ARG;
+    if (N == 0) return BEER_OK;
+    kctc::Args a;
+    a.X = X; a.N = N; a.pdf_post = nullptr; a.ld_post = 0; a.pdf_llh = nullptr; a.ld_pdf = 0; a.comp_llh = nullptr;
+    a.comp_off = nullptr; a.Kp = M; a.M = M; a.C = 1; a.acc = acc_normal; a.n_gtiles = 0; a.frames_per_cta = 0;
+    a.pdf_ids = pdf_ids; a.path_scale = scale;
+    cudaStream_t st = (cudaStream_t)stream;
+    return D == 20 ? kctc::launch_raw<5, 2>(a, st) : kctc::launch_raw<10, 2>(a, st);
 }
 
 }  // extern "C"

@@ -275,6 +275,9 @@ class VBEngine:
             ws_bytes = max(ws_bytes, nmax * plan.n_states * 2 + 4)      # uint16 back-pointers
             self._pdf_map = torch.as_tensor(np.asarray(plan.pdf_map), dtype=i32, device=self.dev)
             self._frame_llh = torch.empty(nmax, device=self.dev, dtype=f32)
+            # single-Gaussian pdfs in one statistics tile: the one-hot posteriors are never written, KC reads pdf ids
+            self._path_kc = (not emission.has_mixtures) and ops.accumulate_path_supported(M, D)
+            self._pdf_ids = torch.zeros(nmax + 4, device=self.dev, dtype=i32) if self._path_kc else None
         self.ws = torch.empty((ws_bytes + 3) // 4, device=self.dev, dtype=f32)
         self.frame_ref = torch.empty(nmax, device=self.dev, dtype=f32)
         self.utt_ell = torch.zeros(utts.n_utts, device=self.dev, dtype=f64)
@@ -340,8 +343,11 @@ class VBEngine:
                 if self.viterbi:
                     path = ops.hmm_viterbi(plan, pdf_llh, rel, scale=self.scale, workspace=self.ws)
                     _, frame = ops.path_posteriors(path, em.Kp, pdf_map=self._pdf_map, scale=self.scale,
-                                                   pdf_llh=pdf_llh, frame_ref=fref, out_post=pdf_post,
+                                                   pdf_llh=pdf_llh, frame_ref=fref, want_post=not self._path_kc,
+                                                   out_post=None if self._path_kc else pdf_post,
                                                    out_frame=self._frame_llh[:nf])
+                    if self._path_kc:
+                        torch.index_select(self._pdf_map, 0, path, out=self._pdf_ids[:nf])
                     # per-utterance sums of the per-frame expected llh (fp64 prefix sums, differences at the offsets)
                     cs = torch.cat([torch.zeros(1, dtype=f64, device=self.dev), frame.double().cumsum(0)])
                     self.utt_ell[u0:u1] = cs[rel[1:]] - cs[rel[:-1]]
@@ -354,10 +360,13 @@ class VBEngine:
                                              out_pdf_post=pdf_post, out_utt_exp_llh=self.utt_ell[u0:u1],
                                              unit_counts=self.unit_counts)
             with self._stage('KC_accumulate'):
-                ops.accumulate_stats(X, self.acc, pdf_post=pdf_post,
-                                     pdf_llh=pdf_llh if comp is not None else None, comp_llh=comp,
-                                     comp_off=em.comp_off if (comp is not None and not em.uniform_C) else None,
-                                     Kp=em.Kp)
+                if self.viterbi and self._path_kc:
+                    ops.accumulate_stats_path(X, self.acc, self._pdf_ids[:nf], scale=self.scale)
+                else:
+                    ops.accumulate_stats(X, self.acc, pdf_post=pdf_post,
+                                         pdf_llh=pdf_llh if comp is not None else None, comp_llh=comp,
+                                         comp_off=em.comp_off if (comp is not None and not em.uniform_C) else None,
+                                         Kp=em.Kp)
             self.gpu_launches += 3
             if self.host_mode:
                 self._free[ci & 1].record()

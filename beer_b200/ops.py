@@ -360,6 +360,23 @@ def accumulate_stats(X, acc_normal, pdf_post=None, pdf_llh=None, comp_llh=None, 
     return acc_normal
 
 
+def accumulate_path_supported(M, D):
+    return M <= 128 and D in (20, 40)
+
+
+def accumulate_stats_path(X, acc_normal, pdf_ids, scale=1.0):
+    """acc_normal [M, 2D+2] (fp64) += statistics of one-hot posteriors scale * onehot(pdf_ids[t]) (Viterbi training).
+    `pdf_ids`: int32 with at least N rounded up to 4 entries allocated (a view of a padded buffer)."""
+    lib = require_cuda()
+    N, D = X.shape
+    M = acc_normal.shape[0]
+    if pdf_ids.untyped_storage().nbytes() - pdf_ids.storage_offset() * 4 < ((N + 3) // 4) * 16:
+        raise ValueError('pdf_ids must be a view of a buffer padded to a multiple of 4 entries')
+    _lib.check(lib.beer_accumulate_stats_path(_p(X, f32), N, D, _p(pdf_ids, i32), float(scale), M, _p(acc_normal, f64),
+                                              _stream()), 'beer_accumulate_stats_path')
+    return acc_normal
+
+
 def mixture_weight_stats(acc_normal, D, comp_off=None, Kp=None):
     lib = require_cuda()
     M = acc_normal.shape[0]

@@ -277,6 +277,14 @@ BEER_API int beer_dirichlet_from_natural(const float* nat, int K, int C, float* 
 BEER_API int beer_segment_logsumexp(const float* comp_llh, int64_t N, int M, const int32_t* comp_off, int Kp,
                            float* pdf_llh, int64_t ld_pdf, void* stream);
 
+/* KC for a GIVEN path (Viterbi training / forced alignment, hmm.py:42-58 + hmm.py:94-100 + normalset.py:121-123): the
+ * posteriors are the one-hot rows scale * onehot(pdf_ids[t]); they are never materialised (a stage of the tensor-core
+ * kernel brings 32 pdf ids instead of 32 x M floats).  acc_normal [M, 2D+2] fp64 += as beer_accumulate_stats.
+ *   pdf_ids: int32, 16-byte aligned, readable up to N rounded up to a multiple of 4; M <= 128, D in {20, 40}
+ *   (BEER_ERR_UNSUPPORTED otherwise: use beer_path_posteriors + beer_accumulate_stats). */
+BEER_API int beer_accumulate_stats_path(const float* X, int64_t N, int D, const int32_t* pdf_ids, float scale, int M,
+                               double* acc_normal, void* stream);
+
 /* Posteriors of a GIVEN state path (viterbi=True / state_path=..., beer/models/hmm.py:42-58, 87):
  * pdf_post[t, :] = scale * onehot(map[path_t]) (overwritten), frame_exp_llh[t] = scale * llh of that pdf. */
 BEER_API int beer_path_posteriors(const int32_t* path, int64_t N, const int32_t* pdf_map, float scale,

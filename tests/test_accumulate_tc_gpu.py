@@ -92,3 +92,28 @@ def test_tc_ragged_components():
     torch.cuda.synchronize()
     scale = want.abs().max(dim=1, keepdim=True).values.clamp(min=1e-3)
     assert ((got - want).abs() / scale).max().item() <= 3e-6
+
+
+@pytest.mark.parametrize('M,D,N,scale', [(100, 40, 5013, 1.0), (100, 40, 148 * 32 * 9 + 1, 0.7), (7, 20, 77, 1.0),
+                                         (128, 40, 4096, 1.0)])
+def test_tc_statistics_of_a_path(M, D, N, scale):
+    """Viterbi training: statistics of one-hot posteriors read from pdf ids (never materialised) == the dense kernel
+    fed the one-hot matrix == the fp64 restatement."""
+    from beer_b200 import ops
+    ops.require_cuda()
+    g = torch.Generator().manual_seed(M + N)
+    X = (torch.randn(N, D, generator=g) * 2 + 0.5).to(DEV)
+    ids_h = torch.randint(0, M, (N,), generator=g, dtype=torch.int32)
+    buf = torch.zeros(N + 4, dtype=torch.int32, device=DEV)
+    buf[:N] = ids_h.to(DEV)
+    onehot = torch.zeros(N, M, device=DEV)
+    onehot[torch.arange(N, device=DEV), ids_h.to(DEV).long()] = scale
+    want = _exact(X, onehot)
+    got = torch.zeros(M, 2 * D + 2, device=DEV, dtype=torch.float64)
+    ops.accumulate_stats_path(X, got, buf[:N], scale=scale)
+    torch.cuda.synchronize()
+    sc = want.abs().max(dim=1, keepdim=True).values.clamp(min=1e-3)
+    assert ((got - want).abs() / sc).max().item() <= 3e-6
+    ops.accumulate_stats_path(X, got, buf[:N], scale=scale)        # += semantics
+    torch.cuda.synchronize()
+    assert ((got - 2 * want).abs() / sc).max().item() <= 6e-6
