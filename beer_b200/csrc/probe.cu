@@ -1,0 +1,149 @@
+// Roofline probes: the denominators bench.py reports fractions against are MEASURED on the GPU the bench runs on.
+//
+//   beer_probe_mma   : back-to-back tcgen05.mma (M = 128, N = 256, one k-step each) on resident shared-memory
+//                      operands, one CTA per SM -> the dispatch-limited peak of the tensor pipe for the MMA kind the
+//                      statistics / emission kernels use (kind::tf32 or kind::f16); their 3-pass split runs at a
+//                      third of it.
+//   beer_probe_fill  : write-only streams (float4 stores, or 1-D bulk copies shared -> global) -> the DRAM WRITE
+//                      ceiling an llh-producing kernel (KA) can reach.
+//   beer_probe_read  : read-only stream (float4 loads folded into one value per thread).
+//
+// Timing is done by the caller with CUDA events on the stream the probe is launched on.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "../../include/beer_b200.h"
+
+namespace beer {
+namespace probe {
+
+using namespace tcu;
+
+template <int KIND>   // 0 = tf32 (K = 8 per MMA), 1 = f16 (K = 16 per MMA)
+__global__ void __launch_bounds__(128, 1) mma_peak_kernel(int n_mma) {
+    constexpr int M = 128, N = 256;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    // one k-step = two 16-byte core-matrix columns: A 128 x 32 B, B 256 x 32 B (contents irrelevant: zeros)
+    for (int i = threadIdx.x; i < (M + N) * 32 / 16; i += blockDim.x)
+        reinterpret_cast<float4*>(smem_raw)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 32) tmem_alloc(&tmem_slot, 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (threadIdx.x == 0) {
+        const uint32_t fmt = KIND == 0 ? 2u : 0u;
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+        const uint64_t da = make_desc(smem_u32(smem_raw), 128, 256);
+        const uint64_t db = make_desc(smem_u32(smem_raw) + M * 32, 128, 256);
+        for (int i = 0; i < n_mma; ++i) {
+            const uint32_t d = tmem + (uint32_t)((i >> 2) & 1) * N;     // four accumulating k-steps per tile
+            if (KIND == 0) {
+                umma_tf32(d, da, db, idesc, (i & 3) != 0);
+            } else {
+                asm volatile(
+                    "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d),
+                    "l"(da), "l"(db), "r"(idesc), "r"((uint32_t)((i & 3) != 0))
+                    : "memory");
+            }
+        }
+        umma_commit(&bar);
+        mbar_wait(&bar, 0);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+__global__ void __launch_bounds__(256) fill_st_kernel(float4* __restrict__ dst, int64_t n4) {
+    const float4 v = make_float4(1.f, 2.f, 3.f, 4.f);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = v;
+}
+
+constexpr int BULK_BYTES = 32 * 1024;
+__global__ void __launch_bounds__(128) fill_bulk_kernel(float* __restrict__ dst, int64_t n_chunks) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    for (int i = threadIdx.x; i < BULK_BYTES / 16; i += blockDim.x)
+        reinterpret_cast<float4*>(smem_raw)[i] = make_float4(1.f, 2.f, 3.f, 4.f);
+    fence_proxy_async();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int pending = 0;
+        for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+            bulk_s2g(reinterpret_cast<uint8_t*>(dst) + c * BULK_BYTES, smem_raw, BULK_BYTES);
+            bulk_commit();
+            if (++pending == 8) {                 // at most 8 bulk stores (256 KB) in flight per SM
+                asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory");
+                pending = 4;
+            }
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+}
+
+__global__ void __launch_bounds__(256) read_kernel(const float4* __restrict__ src, int64_t n4, float* __restrict__ sink) {
+    float acc = 0.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(src + i);
+        acc += v.x + v.y + v.z + v.w;
+    }
+    if (acc == 123.456f) *sink = acc;      // never true: keeps the loads alive
+}
+
+}  // namespace probe
+}  // namespace beer
+
+using namespace beer;
+
+extern "C" {
+
+int beer_probe_mma(int kind, int n_mma, double* flops_out, void* stream) {
+    if ((kind != 0 && kind != 1) || n_mma <= 0) return BEER_ERR_ARG;
+    const size_t smem = (128 + 256) * 32 + 1024;
+    if (kind == 0)
+        probe::mma_peak_kernel<0><<<kNumSMs, 128, smem, (cudaStream_t)stream>>>(n_mma);
+    else
+        probe::mma_peak_kernel<1><<<kNumSMs, 128, smem, (cudaStream_t)stream>>>(n_mma);
+    BEER_LAUNCH_CHECK();
+    if (flops_out) *flops_out = (double)kNumSMs * (double)n_mma * 2.0 * 128.0 * 256.0 * (kind == 0 ? 8.0 : 16.0);
+    return BEER_OK;
+}
+
+int beer_probe_fill(float* dst, int64_t bytes, int mode, void* stream) {
+    if (!dst || bytes <= 0 || (((uintptr_t)dst) & 127) != 0) return BEER_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == 0) {
+        probe::fill_st_kernel<<<kNumSMs * 8, 256, 0, st>>>(reinterpret_cast<float4*>(dst), bytes / 16);
+    } else if (mode == 1) {
+        static bool attr = false;
+        if (!attr) {
+            BEER_CUDA_TRY(cudaFuncSetAttribute(probe::fill_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               probe::BULK_BYTES));
+            attr = true;
+        }
+        probe::fill_bulk_kernel<<<kNumSMs * 4, 128, probe::BULK_BYTES, st>>>(dst, bytes / probe::BULK_BYTES);
+    } else {
+        return BEER_ERR_ARG;
+    }
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
+int beer_probe_read(const float* src, int64_t bytes, float* sink, void* stream) {
+    if (!src || !sink || bytes <= 0 || (((uintptr_t)src) & 15) != 0) return BEER_ERR_ARG;
+    probe::read_kernel<<<kNumSMs * 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(src), bytes / 16, sink);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
+}  // extern "C"

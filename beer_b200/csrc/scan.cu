@@ -2086,9 +2086,13 @@ int64_t beer_hmm_workspace_bytes(const beer_graph_plan* plan, int64_t N) {
     return (N * fb_row_stride(plan) + 64) * (int64_t)sizeof(float);
 }
 
+// Units whose counts the forward-backward kernels can reduce themselves: only the one-warp left-to-right loop
+// kernel (<= 4 units per lane = <= 128 units) with an identity pdf map carries the fused counts.  Everything else
+// reports 0 and the caller reduces the ends x starts block of beer_hmm_transition_posteriors instead.
 int beer_hmm_unit_count_size(const beer_graph_plan* plan) {
     if (!plan) return BEER_ERR_ARG;
-    return plan->lr_su ? plan->K / plan->lr_su : 0;
+    if (!plan->lr_su || !plan->map_identity || plan->lr_u > 4) return 0;
+    return plan->K / plan->lr_su;
 }
 
 int beer_hmm_forward_backward(const beer_graph_plan* plan, const float* pdf_llh, int64_t ld_pdf,
@@ -2123,7 +2127,7 @@ int beer_hmm_forward_backward_units(const beer_graph_plan* plan, const float* pd
     a.lr_w = plan->lr_w;
     a.lr_row = 32 * plan->lr_su * plan->lr_u;
     a.unit_counts = unit_counts;
-    if (unit_counts != nullptr && !(plan->lr_su && plan->map_identity)) return BEER_ERR_UNSUPPORTED;
+    if (unit_counts != nullptr && beer_hmm_unit_count_size(plan) <= 0) return BEER_ERR_UNSUPPORTED;
     const bool post_ok = (pdf_post == nullptr || (ld_post % 4 == 0 && ((uintptr_t)pdf_post & 15) == 0)) &&
                          (state_post == nullptr || (plan->K % 4 == 0 && ((uintptr_t)state_post & 15) == 0));
     const char* force = getenv("BEER_B200_SCAN");   // debug: "generic" | "fast" | unset (best available)
@@ -2146,6 +2150,8 @@ int beer_hmm_forward_backward_units(const beer_graph_plan* plan, const float* pd
             if (u == 4) return launch_fb_lr<3, 4>(a, n_utts, st);
         }
     }
+    // only the left-to-right loop kernel accumulates unit counts: never drop them silently
+    if (unit_counts != nullptr) return BEER_ERR_UNSUPPORTED;
     if (force != nullptr && force[0] == 'g') goto generic;
     if (plan->fast_ok && a.vec && (state_post == nullptr || plan->K % 4 == 0) &&
         (pdf_post == nullptr || (ld_post % 4 == 0 && ((uintptr_t)pdf_post & 15) == 0)) &&

@@ -931,12 +931,19 @@ class PhoneLoop(HMM):
             phone_resps = block.sum(dim=(0, 1)) + first[:, torch.as_tensor(start_idxs, device=first.device)].sum(dim=0)
         elif 'unit_path' in self.cache:
             # one-hot transition posteriors of a Viterbi / given path (hmm.py:49-54)
+            # every utterance of a batch is its own sequence: no transition across a boundary, one first frame each
             path = self.cache['unit_path'].long()
+            utts = self.cache.get('utts')
+            off = utts.offsets.to(path.device) if utts is not None else \
+                torch.tensor([0, path.numel()], dtype=i64, device=path.device)
+            off = off[:-1][off[1:] > off[:-1]]                      # first frame of every non-empty utterance
             ends = torch.zeros(self.graph.n_states, dtype=torch.bool, device=path.device)
             ends[torch.as_tensor(list(self.end_pdf.values()), device=path.device)] = True
             starts = torch.as_tensor(start_idxs, device=path.device)
-            hit = ends[path[:-1]][:, None] & (path[1:, None] == starts[None, :])
-            phone_resps = hit.sum(dim=0).to(f64) + (path[0] == starts).to(f64)
+            inner = torch.ones(path.numel(), dtype=torch.bool, device=path.device)
+            inner[off] = False                                      # frame t is inner if t - 1 is in the same utterance
+            hit = (ends[path[:-1]] & inner[1:])[:, None] & (path[1:, None] == starts[None, :])
+            phone_resps = hit.sum(dim=0).to(f64) + (path[off][:, None] == starts[None, :]).sum(dim=0).to(f64)
         else:
             phone_resps = torch.zeros(n_units, dtype=f64, device=weights.posterior.params.concentrations.device)
         if isinstance(self.categorical, SBCategorical):

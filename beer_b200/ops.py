@@ -550,3 +550,54 @@ def add_deltas(fea, wlen):
     out = torch.empty_like(fea)
     _lib.check(lib.beer_add_deltas(_p(fea, f32), T, F, int(wlen), _p(out), _stream()), 'beer_add_deltas')
     return out
+
+
+# ---------------------------------------------------------------------------
+# roofline probes (measurement only)
+# ---------------------------------------------------------------------------
+
+def _timed(fn, reps):
+    """Best CUDA-event time in seconds of `fn()` launched on the current stream."""
+    fn()
+    torch.cuda.synchronize()
+    best = float('inf')
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        best = min(best, e0.elapsed_time(e1) * 1e-3)
+    return best
+
+
+def probe_mma_tflops(kind, n_mma=20000, reps=5):
+    """Measured dispatch-limited tcgen05 peak (TFLOP/s, dense) of MMA kind 'tf32' or 'f16' on this GPU."""
+    lib = require_cuda()
+    flops = C.c_double(0.0)
+    k = {'tf32': 0, 'f16': 1}[kind]
+
+    def run():
+        _lib.check(lib.beer_probe_mma(k, int(n_mma), C.byref(flops), _stream()), 'beer_probe_mma')
+    t = _timed(run, reps)
+    return flops.value / t / 1e12
+
+
+def probe_dram_gbs(mode, nbytes=4 << 30, reps=5):
+    """Measured DRAM stream rate in GB/s: mode 'fill_st' (float4 stores), 'fill_bulk' (bulk copies shared -> global)
+    or 'read'."""
+    lib = require_cuda()
+    buf = torch.empty(nbytes // 4, device='cuda', dtype=f32)
+    sink = torch.zeros(1, device='cuda', dtype=f32)
+    if mode == 'read':
+        buf.zero_()
+
+        def run():
+            _lib.check(lib.beer_probe_read(_p(buf), nbytes, _p(sink), _stream()), 'beer_probe_read')
+    else:
+        m = {'fill_st': 0, 'fill_bulk': 1}[mode]
+
+        def run():
+            _lib.check(lib.beer_probe_fill(_p(buf), nbytes, m, _stream()), 'beer_probe_fill')
+    t = _timed(run, reps)
+    return nbytes / t / 1e9

@@ -59,29 +59,36 @@ def phone_loop_graph(n_units, n_states=4, self_loop=0.75):
 
 def sample_utterances(graph, means, n_utts, n_frames, seed, device='cpu', noise=1.0, return_paths=False):
     """Sample a state path per utterance from `graph` and emit x_t = mu[pdf(s_t)] + noise * eps.
-    Returns an [n_utts * n_frames, D] fp32 tensor on `device` (utterances back to back); with
+    Everything is drawn on the HOST (numpy, inverse-CDF over the outgoing arcs of the current states, all utterances
+    of a frame at once) and moved to `device` in one copy, so that no sampling kernel shows up next to the kernels
+    under test.  Returns an [n_utts * n_frames, D] fp32 tensor on `device` (utterances back to back); with
     `return_paths` also the sampled state paths [n_utts, n_frames] (int64, on `device`)."""
-    gen = torch.Generator(device=device)
-    gen.manual_seed(seed)
-    init = graph.init_log_probs.double().exp().to(device)
-    trans = graph.trans_log_probs.double().exp().to(device)
-    init = (init / init.sum()).float()
-    trans = (trans / trans.sum(dim=1, keepdim=True)).float()
-    pdf = torch.as_tensor(graph.pdf_id_mapping, device=device)
-    means = torch.as_tensor(means, dtype=torch.float32, device=device)
+    rng = np.random.default_rng(seed)
+    init = np.exp(graph.init_log_probs.double().numpy())
+    trans = np.exp(graph.trans_log_probs.double().numpy())
+    init /= init.sum()
+    trans /= trans.sum(axis=1, keepdims=True)
+    K = len(init)
+    # outgoing arcs of every state, padded to the largest out-degree: [K, deg] next states and cumulative probabilities
+    deg = int((trans > 0).sum(axis=1).max())
+    order = np.argsort(-trans, axis=1, kind='stable')[:, :deg]
+    cum = np.cumsum(np.take_along_axis(trans, order, axis=1), axis=1)
+    cum[:, -1] = 1.0
+    pdf = np.asarray(graph.pdf_id_mapping, dtype=np.int64)
+    means = np.asarray(means.cpu() if torch.is_tensor(means) else means, dtype=np.float32)
     D = means.shape[1]
-    state = torch.multinomial(init.expand(n_utts, -1), 1, generator=gen).squeeze(1)
-    X = torch.empty(n_utts, n_frames, D, device=device, dtype=torch.float32)
-    paths = torch.empty(n_utts, n_frames, device=device, dtype=torch.int64) if return_paths else None
+    paths = np.empty((n_utts, n_frames), dtype=np.int64)
+    state = np.minimum(np.searchsorted(np.cumsum(init), rng.random(n_utts)), K - 1)
     for t in range(n_frames):
         if t > 0:
-            state = torch.multinomial(trans[state], 1, generator=gen).squeeze(1)
-        X[:, t] = means[pdf[state]]
-        if return_paths:
-            paths[:, t] = state
-    X += noise * torch.randn(X.shape, generator=gen, device=device, dtype=torch.float32)
-    X = X.reshape(n_utts * n_frames, D)
-    return (X, paths) if return_paths else X
+            u = rng.random(n_utts)
+            j = (cum[state] < u[:, None]).sum(axis=1)
+            state = order[state, np.minimum(j, deg - 1)]
+        paths[:, t] = state
+    X = means[pdf[paths.reshape(-1)]]
+    X += noise * rng.standard_normal(X.shape, dtype=np.float32)
+    X = torch.from_numpy(X).to(device)
+    return (X, torch.from_numpy(paths).to(device)) if return_paths else X
 
 
 def alignment_chains(paths, n_states, self_loop=0.75):

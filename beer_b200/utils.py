@@ -17,6 +17,7 @@ def onehot(labels, max_label, dtype, device):
 def logsumexp(tensor, dim=0):
     """log-sum-exp that returns +-inf when the maximum is +-inf (utils.py:105-123)."""
     tmax, _ = torch.max(tensor, dim=dim, keepdim=True)
-    retval = torch.where((tmax == float('-inf')) | (tmax == float('inf')), tmax.sum(dim=dim),
-                         tmax.sum(dim=dim) + (tensor - tmax).exp().sum(dim=dim).log())
-    return retval
+    inf = (tmax == float('-inf')) | (tmax == float('inf'))
+    safe = torch.where(inf, torch.zeros_like(tmax), tmax)
+    out = safe + (tensor - safe).exp().sum(dim=dim, keepdim=True).log()
+    return torch.where(inf, tmax, out).squeeze(dim)

@@ -1,16 +1,21 @@
 #!/usr/bin/env python
 """VB-EM frames/s on the HMM-GMM hot path (BASELINE.json metric), one process per GPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg2|cfg3] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg3|cfg2|cfg2ali] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one full VB-EM iteration over the rank's resident utterances: emission weights +
-KL, per-frame llh (KA), forward-backward (KB), statistics (KC), one all-reduce of the flat
-statistics buffer, M-step.  `value` = frames of all ranks / (max over ranks of the CUDA-event
-time per step), inputs resident in HBM.  `e2e` = the same through the public API with the
-features in pinned HOST memory (H2D copy of every frame and D2H read of the ELBO inside the
-timed region).  `--impl reference` times the CPU restatement of the reference algorithm
-(oracle/beer_oracle.py, numpy) on all host cores instead.
+Default workload = BASELINE configs[2], the north-star target: HMM-GMM 1000 states x 8 diag-Gauss, 1250 utterances x
+1000 frames per GPU (at N = 8 that IS the 10 000-utterance configuration).  BASELINE configs[1] (100 states x 1
+Gaussian, 4096 utterances per GPU) is measured in the same run and reported under `secondary`.
+
+A "step" is one full VB-EM iteration over the rank's resident utterances: emission weights + KL, per-frame llh (KA),
+forward-backward (KB), statistics (KC), one all-reduce of the flat statistics buffer, M-step.  `value` = frames of all
+ranks / (max over ranks of the CUDA-event time per step), inputs resident in HBM.  `e2e` = the same through the public
+engine API with the features in pinned HOST memory (H2D copy of every frame and D2H read of the ELBO inside the timed
+region).  `elbo_check` = ELBO of the engine against the reference itself run in float64 on the CPU (baseline/_ref;
+the numpy fp64 oracle when the reference is not installed) on a small subset, same initial model, in this run.
+`--impl reference` times the unmodified reference (beer.evidence_lower_bound + backward + optimizer step) on all host
+cores instead.
 """
 import argparse
 import json
@@ -39,51 +44,21 @@ def workload_name(cfg, c):
 
 
 def measured_peaks():
-    """HBM peak in GB/s: the driver-written MEASURED_PEAKS.json when present (key `hbm_gbs`; any numeric key
-    naming hbm is accepted), else the fallback of B200_PROFILING.md."""
-    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-    if os.path.exists(path):
-        try:
-            with open(path) as f:
-                p = json.load(f)
-
-            def find(d):
-                if isinstance(d, dict):
-                    if isinstance(d.get('hbm_gbs'), (int, float)):
-                        return float(d['hbm_gbs'])
-                    for k, v in d.items():
-                        if 'hbm' in str(k).lower() and isinstance(v, (int, float)):
-                            return float(v) * (1000.0 if float(v) < 50 else 1.0)     # TB/s -> GB/s
-                    for v in d.values():
-                        r = find(v)
-                        if r:
-                            return r
-                return None
-            v = find(p)
-            if v:
-                return v, 'measured'
-        except (OSError, ValueError):
-            pass
-    return 6650.0, 'fallback'
-
-
-def measured_bf16_tflops():
-    """Dense bf16 TFLOP/s (sustained figure: the contraction runs inside a long step) from MEASURED_PEAKS.json, else
-    the 1590 fallback of B200_PROFILING.md."""
+    """(HBM GB/s, source): the driver-written MEASURED_PEAKS.json when present, else the fallback of
+    B200_PROFILING.md."""
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     try:
         with open(path) as f:
             p = json.load(f)
-        for k in ('bf16_tflops_sustained', 'bf16_tflops'):
-            if isinstance(p.get(k), (int, float)):
-                return float(p[k]), 'measured'
+        if isinstance(p.get('hbm_gbs'), (int, float)):
+            return float(p['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
     except (OSError, ValueError):
         pass
-    return 1590.0, 'fallback'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
          'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
@@ -129,73 +104,132 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------
-# CPU baseline: the oracle port of the reference algorithm, one worker per host core
+# CPU side: the reference itself (baseline/_ref, else /root/reference), else the numpy port
 # ---------------------------------------------------------------------------------------
 
-def _cpu_worker(args):
-    cfg, seed, n_utts = args
+def host_utterances(c, n_utts, seed):
+    """`n_utts` synthetic utterances of configuration `c` sampled on the host (numpy, fp32)."""
     from oracle import beer_oracle as O
-    c = cfg
     rng = np.random.default_rng(seed)
     graph, _, _ = O.phone_loop_graph(c['n_units'], c['n_states'])
     K = c['n_units'] * c['n_states']
-    M = K * c['n_comp']
-    D = c['dim']
-    means = 2.0 * rng.standard_normal((K, D))
-    utts = O.sample_utterances(rng, graph, means, n_utts, c['n_frames'])
-    prior = (np.zeros((M, D)), np.ones((M, 1)), np.ones((M, 1)), np.ones((M, D)))
+    means = 2.0 * rng.standard_normal((K, c['dim']))
+    return O.sample_utterances(rng, graph, means, n_utts, c['n_frames']), graph
+
+
+def _port_worker(args):
+    """numpy port of the reference E-step + accumulate over a shard (fallback when the reference is absent)."""
+    c, utts, dtype = args
+    from oracle import beer_oracle as O
+    graph, _, _ = O.phone_loop_graph(c['n_units'], c['n_states'])
+    K = c['n_units'] * c['n_states']
+    M, D = K * c['n_comp'], c['dim']
+    rng = np.random.default_rng(2)
     post = (rng.standard_normal((M, D)), np.ones((M, 1)), np.ones((M, 1)), np.ones((M, D)))
-    dprior = dpost = None
-    if c['n_comp'] > 1:
-        dprior = np.ones((K, c['n_comp'])) / c['n_comp']
-        dpost = dprior.copy()
-    utts = [u.astype(np.float32) for u in utts]       # the reference default dtype is fp32
-    graph32 = tuple(np.asarray(a, dtype=np.float32) for a in graph[:3]) + (graph[3],)
-    post32 = tuple(a.astype(np.float32) for a in post)
+    dpost = np.ones((K, c['n_comp'])) / c['n_comp'] if c['n_comp'] > 1 else None
+    graph = tuple(np.asarray(a, dtype=dtype) for a in graph[:3]) + (graph[3],)
+    post = tuple(a.astype(dtype) for a in post)
     t0 = time.perf_counter()
     frames = 0
     with np.errstate(all='ignore'):
         for X in utts:
-            O.hmm_estep(X, post32, None if dpost is None else dpost.astype(np.float32), graph32)
+            O.hmm_estep(X.astype(dtype), post, None if dpost is None else dpost.astype(dtype), graph)
             frames += len(X)
-    return frames, time.perf_counter() - t0
+    return dict(frames=frames, seconds=time.perf_counter() - t0)
 
 
-def cpu_reference_throughput(c, utts_per_worker, n_workers=None):
-    """frames/s of the CPU port over `n_workers` processes (one per host core), the reference's
-    own parallel style (recipes/zrc2019/steps/aud_gnu_parallel.sh:73-86)."""
-    import multiprocessing as mp
-    n_workers = n_workers or os.cpu_count() or 1
-    os.environ.setdefault('OMP_NUM_THREADS', '1')
-    ctx = mp.get_context('spawn')
-    t0 = time.perf_counter()
-    with ctx.Pool(n_workers) as pool:
-        res = pool.map(_cpu_worker, [(c, 1000 + i, utts_per_worker) for i in range(n_workers)])
-    wall = max(r[1] for r in res)        # workers run concurrently; the slowest one ends the job
-    frames = sum(r[0] for r in res)
-    return frames / wall, n_workers, frames, time.perf_counter() - t0
+class CpuArm:
+    """A pool of single-threaded worker processes, one per host core: the reference's own parallel style
+    (recipes/zrc2019/steps/aud_gnu_parallel.sh:73-86, one `beer hmm accumulate` job per shard, then `update`)."""
+
+    def __init__(self, c, n_workers=None):
+        import multiprocessing as mp
+        from baseline import reference_arm as R
+        self.c, self.R = c, R
+        self.kind = 'reference' if R.find_reference() is not None else 'port'
+        self.n_workers = n_workers or os.cpu_count() or 1
+        os.environ.setdefault('OMP_NUM_THREADS', '1')
+        os.environ.setdefault('MKL_NUM_THREADS', '1')
+        self.pool = mp.get_context('spawn').Pool(self.n_workers)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+    def throughput(self, shards):
+        """One accumulate + update pass over `shards` (one per worker, all at once): frames / slowest worker."""
+        if self.kind == 'reference':
+            res = self.pool.map(self.R._worker, [(self.c, s, 1, False, False, None) for s in shards])
+        else:
+            res = self.pool.map(_port_worker, [(self.c, s, np.float32) for s in shards])
+        wall = max(r['seconds'] for r in res)
+        frames = sum(r['frames'] for r in res)
+        return frames / wall, frames, wall
+
+    def describe(self, upw, T):
+        what = ('unmodified reference (beer.evidence_lower_bound per utterance + backward + VBConjugateOptimizer.step, '
+                'torch CPU fp32)' if self.kind == 'reference' else
+                'numpy fp32 port of the reference E-step + accumulate (reference not installed)')
+        return f'{self.n_workers} single-threaded worker processes x {upw} utterance(s) x {T} frames: {what}'
+
+    def elbo_fp64(self, utts, datasize):
+        """(sum of the per-utterance ELBOs in float64, initial model arrays)."""
+        if self.kind == 'reference':
+            res = self.pool.map(self.R._worker, [(self.c, [u], 1, True, i == 0, datasize, False) for i, u in enumerate(utts)])
+            # every worker's `elbo` = empty accumulator + its utterance: plain sum (objectives.py:78-90)
+            return sum(r['per_utt'][0] for r in res), res[0]['model'], 'reference (float64)'
+        from oracle import beer_oracle as O
+        c = self.c
+        K = c['n_units'] * c['n_states']
+        M, D, C = K * c['n_comp'], c['dim'], c['n_comp']
+        rng = np.random.default_rng(2)
+        prior = (np.zeros((M, D)), np.ones((M, 1)), np.ones((M, 1)), np.ones((M, D)))
+        post = (rng.standard_normal((M, D)).astype(np.float32).astype(np.float64),) + prior[1:]
+        model = dict(ng_prior=prior, ng_post=post)
+        if C > 1:
+            model['dir_prior'] = model['dir_post'] = np.ones((K, C)) / C
+        graph, _, _ = O.phone_loop_graph(c['n_units'], c['n_states'])
+        elbo, _, _, _ = O.vb_iteration_hmm([u.astype(np.float64) for u in utts], prior, post, model.get('dir_prior'),
+                                           model.get('dir_post'), graph, datasize=datasize)
+        return elbo, model, 'numpy oracle (float64)'
 
 
-def run_reference(args, c):
+def cpu_sizes(c):
+    """(utterances per worker, frames kept of each utterance) for ~5-10 s of CPU work per pass: the cost of the
+    reference is linear in the frames, so the large configuration is sampled with the first 250 frames of one
+    utterance per worker."""
+    big = c['n_comp'] * c['n_units'] * c['n_states'] > 2000
+    return (1, min(250, c['n_frames'])) if big else (16, c['n_frames'])
+
+
+def cpu_shards(c, n_workers, seed=1000):
+    upw, keep = cpu_sizes(c)
+    utts, _ = host_utterances(c, n_workers * upw, seed=seed)
+    utts = [u[:keep] for u in utts]
+    return [utts[i * upw:(i + 1) * upw] for i in range(n_workers)], upw, keep
+
+
+def run_reference(args, name, c):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    upw = 48 if c['n_comp'] == 1 else 1          # ~5-10 s of CPU work per step on 16 cores
-    vals = []
+    arm = CpuArm(c)
+    shards, upw, keep = cpu_shards(c, arm.n_workers)
     for _ in range(args.warmup):
-        cpu_reference_throughput(c, 1)
+        arm.throughput([[s[0][:50]] for s in shards])
+    tot_frames, tot_time = 0, 0.0
     for _ in range(args.steps):
-        v, cores, frames, _ = cpu_reference_throughput(c, upw)
-        vals.append((v, frames))
-    tot_frames = sum(f for _, f in vals)
-    tot_time = sum(f / v for v, f in vals)
+        _, frames, wall = arm.throughput(shards)
+        tot_frames += frames
+        tot_time += wall
+    arm.close()
     value = tot_frames / tot_time
-    sample = f'{cores} worker processes x {upw} utterance(s) x {c["n_frames"]} frames per step, E-step + accumulate'
+    sample = arm.describe(upw, keep) + ' per step'
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * tot_time / max(args.steps, 1),
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': workload_name(args.config, c), 'sample': sample},
-            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+            'config': {'workload': workload_name(name, c), 'sample': sample},
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': arm.n_workers, 'kind': arm.kind, 'sample': sample},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line), flush=True)
@@ -205,35 +239,61 @@ def run_reference(args, c):
 # GPU arm
 # ---------------------------------------------------------------------------------------
 
-def run_gpu(args, c):
+class Ctx:
+    pass
+
+
+def make_engine_from_arrays(ctx, c, model, utts, plan, datasize):
+    import torch
+    from beer_b200.engine import EmissionParams, VBEngine, WeightGroup
+    dev = ctx.dev
+    K, C = c['n_units'] * c['n_states'], c['n_comp']
+
+    def ng(t):
+        m, k, a, b = t
+        f = lambda x: torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float32, device=dev).contiguous()
+        return f(m), f(np.reshape(k, -1)), f(np.reshape(a, -1)), f(b)
+
+    prior, post = ng(model['ng_prior']), ng(model['ng_post'])
+    groups, comp_off = (), None
+    if C > 1:
+        dp = torch.as_tensor(model['dir_prior'], dtype=torch.float32, device=dev).reshape(K, C).contiguous()
+        dq = torch.as_tensor(model['dir_post'], dtype=torch.float32, device=dev).reshape(K, C).contiguous()
+        groups = (WeightGroup(0, K, C, dp, dq),)
+        comp_off = np.arange(K + 1) * C
+    em = EmissionParams(prior, post, comp_off=comp_off, weight_groups=groups)
+    return VBEngine(em, plan, utts, datasize=datasize, distributed=False)
+
+
+def elbo_check(ctx, name, c, arm, n_check):
+    """Engine (fp32, GPU) against the reference in float64 (CPU) on `n_check` utterances, same initial model:
+    the summed ELBO of accumulate + update (objectives.py:180-184 added up as in accumulate.py:39-59)."""
+    import torch
+    from beer_b200 import ops, synthetic
+    from beer_b200.engine import Utterances
+    utts, _ = host_utterances(c, n_check, seed=4242)
+    utts = [u[:cpu_sizes(c)[1]] for u in utts]
+    N = float(sum(len(u) for u in utts))
+    t0 = time.perf_counter()
+    want, model, kind = arm.elbo_fp64(utts, N)
+    graph, _, _ = synthetic.phone_loop_graph(c['n_units'], c['n_states'])
+    K = c['n_units'] * c['n_states']
+    plan = ops.GraphPlan(graph.init_log_probs.numpy(), graph.final_log_probs.numpy(),
+                         graph.trans_log_probs.numpy(), graph.pdf_id_mapping, n_pdfs=K)
+    X = torch.as_tensor(np.concatenate(utts), dtype=torch.float32, device=ctx.dev)
+    eng = make_engine_from_arrays(ctx, c, model, Utterances(X, [len(u) for u in utts]), plan, N)
+    got = float(eng.step().item())
+    return {'rel_err': abs(got - want) / abs(want), 'n_utts': n_check, 'frames': int(N), 'engine_elbo': got,
+            'cpu_elbo': want, 'against': kind, 'seconds': time.perf_counter() - t0}
+
+
+def run_config(ctx, args, name, c, steps, warmup, primary):
+    """Time one configuration; returns the dict of its measurements (rank 0: everything, others: None)."""
     import torch
     import torch.distributed as dist
     from beer_b200 import ops, synthetic
     from beer_b200.engine import EmissionParams, Utterances, VBEngine, WeightGroup
-
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    if world != args.gpus:
-        raise SystemExit(f'--gpus {args.gpus} needs {args.gpus} ranks (torchrun), got WORLD_SIZE={world}')
-    torch.cuda.set_device(local_rank)
-    dev = torch.device('cuda', local_rank)
-    if world > 1:
-        from beer_b200.engine import bind_to_gpu_cpus
-        bind_to_gpu_cpus(local_rank)      # pinned feature buffers next to this rank's GPU (e2e leg)
-    if world > 1:
-        # NCCL announces its version on stdout at the first collective: keep stdout to the one JSON line
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group('nccl', device_id=dev)
-            dist.all_reduce(torch.zeros(1, device=dev))
-            torch.cuda.synchronize()
-        finally:
-            os.dup2(saved, 1)
-            os.close(saved)
-    ops.require_cuda()
+    dev, world, rank = ctx.dev, ctx.world, ctx.rank
 
     K = c['n_units'] * c['n_states']
     C = c['n_comp']
@@ -260,7 +320,7 @@ def run_gpu(args, c):
             comp_off = np.arange(K + 1) * C
         em = EmissionParams(prior, post, comp_off=comp_off, weight_groups=groups)
         return VBEngine(em, plan, utts, datasize=float(world * U * T), chunk_frames=chunk_frames,
-                        distributed=world > 1, use_graph=use_graph, viterbi=args.viterbi)
+                        distributed=world > 1, use_graph=use_graph, viterbi=bool(c.get('viterbi')))
 
     def barrier():
         if world > 1:
@@ -269,24 +329,24 @@ def run_gpu(args, c):
 
     eng = make_engine(use_graph=not args.no_graph)
     elbos = []
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         elbos.append(eng.step().clone())
     barrier()
     eng.gpu_launches = 0
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    sampler = ClockSampler(ctx.local_rank)
+    if rank == 0 and primary:
         sampler.start()
     t_wall = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.nvtx.range_push('bench_timed')     # ncu --nvtx --nvtx-include "bench_timed/" selects these launches
     ev0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         elbos.append(eng.step().clone())     # the graph's ELBO buffer is overwritten by the next step
     ev1.record()
     torch.cuda.nvtx.range_pop()
     barrier()
     wall = time.perf_counter() - t_wall
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if (rank == 0 and primary) else None
     ms = ev0.elapsed_time(ev1)
     launches = eng.gpu_launches
     # per-stage kernel durations: the same iteration launched eagerly with CUDA events around the stages
@@ -300,11 +360,11 @@ def run_gpu(args, c):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    if ms < 400.0:
+    if primary and ms < 400.0:
         # the timed region is shorter than a few nvidia-smi sampling periods: sample the same step loop,
         # untimed, for ~0.6 s right behind it (same number of extra steps on every rank)
-        n_probe = int(600.0 / max(ms / args.steps, 1e-3)) + 1
-        probe = ClockSampler(local_rank)
+        n_probe = int(600.0 / max(ms / steps, 1e-3)) + 1
+        probe = ClockSampler(ctx.local_rank)
         if rank == 0:
             probe.start()
         for _ in range(n_probe):
@@ -315,9 +375,9 @@ def run_gpu(args, c):
             clocks['window'] = (f'{n_probe} more steps of the same loop right after the timed region '
                                 '(timed region too short to sample)')
     frames_per_step = world * U * T
-    value = frames_per_step * args.steps / (ms * 1e-3)
+    value = frames_per_step * steps / (ms * 1e-3)
     elbo_pf = [float(eng.elbo_per_frame(e).item()) for e in elbos]
-    launches_step = launches // max(args.steps, 1)
+    tensor_kind = getattr(eng, 'tensor_kind', 'tf32')
 
     # ---- end to end: features in pinned host memory, H2D every step, ELBO read back --------
     host_X = torch.empty(X.shape, dtype=torch.float32, pin_memory=True)
@@ -326,7 +386,7 @@ def run_gpu(args, c):
     # features stay in pinned host memory: the engine streams them in chunks of whole utterances (the H2D
     # copy of chunk i+1 under the kernels of chunk i) and the ELBO is read back to the host every step
     eng2 = make_engine(Utterances(host_X, [T] * U), chunk_frames=args.e2e_chunk_frames or max(T, U * T // 8))
-    n_e2e = max(1, min(args.steps, 5))
+    n_e2e = max(1, min(steps, 5))
 
     def e2e_step():
         return float(eng2.step().item())
@@ -342,66 +402,152 @@ def run_gpu(args, c):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = frames_per_step * n_e2e / float(te.item())
-
-    if rank == 0:
-        peak, peak_src = measured_peaks()
-        # dominant kernel and its algorithmic bytes per frame (DESIGN.md "Kernels and rooflines")
-        # B_alg = 8D + 16K per frame = KA (read X, write llh) + KB (read llh once more, write and
-        # read alpha) + KC (read X); posteriors and responsibilities count as on-chip in the algorithmic figure
-        alg = {'KA_emission_llh': 4 * D + 4 * K, 'KB_forward_backward': 12 * K, 'KC_accumulate': 4 * D}
-        traffic_pf = {}
-        tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
-        if os.path.exists(tpath):        # dram bytes per frame per launch from the committed ncu capture
-            with open(tpath) as f:
-                traffic_pf = json.load(f).get(args.config, {})
-        dom = max((k for k in stage_ms if k in alg), key=lambda k: stage_ms[k], default=None)
-        roofline = None
-        if dom is not None:
-            achieved = alg[dom] * U * T / (stage_ms[dom] * 1e-3) / 1e9
-            roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                        'frac': achieved / peak,
-                        'traffic': (traffic_pf[dom] * U * T if dom in traffic_pf else None),
-                        'traffic_unit': 'bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)',
-                        'peak_source': peak_src,
-                        'alg_bytes_per_frame': alg[dom], 'launch_ms': stage_ms[dom],
-                        'step_alg_bytes_per_frame': 8 * D + 16 * K,
-                        'step_frac': (8 * D + 16 * K) * U * T / (ms / args.steps * 1e-3) / 1e9 / peak,
-                        'stage_ms': stage_ms}
-            # the whole step against its three rooflines, per GPU: HBM (B_alg = 8D + 16K bytes / frame),
-            # tensor pipe (F_alg = 4 Q M flop / frame at 3xTF32 = bf16 / 6) and the scan's special-function unit
-            # (S_alg = 2 nnz(A) log-add-exp terms / frame, phone loop nnz = 2K - P + P^2, against 148 SMs x 16 MUFU
-            # lanes x the measured SM clock)
-            fps = U * T / (ms / args.steps * 1e-3)
-            bf16, bf16_src = measured_bf16_tflops()
-            Pn = c['n_units']
-            nnz = 2 * K - Pn + Pn * Pn
-            mhz = (clocks or {}).get('sm_mhz') or 1965.0
-            roofline['step_fractions'] = {
-                'hbm': fps * (8 * D + 16 * K) / 1e9 / peak,
-                'tensor_3xtf32': fps * 4 * (2 * D + 2) * M / 1e12 / (bf16 / 6.0),
-                'scan_mufu': fps * 2 * nnz / (148 * 16 * mhz * 1e6),
-                'tensor_peak_tflops': bf16 / 6.0, 'tensor_peak_source': bf16_src + ' bf16 / 6'}
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            upw = 96 if C == 1 else 1        # ~10 s of CPU work
-            v, cores, frames, took = cpu_reference_throughput(c, upw)
-            cpu = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                   'sample': f'{cores} worker processes x {upw} utterance(s) x {T} frames, numpy port of the '
-                             f'reference E-step + accumulate ({took:.1f} s)'}
-        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-                'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-                'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-                'config': {'workload': workload_name(args.config, c), 'l2': 'inputs larger than L2 '
-                           f'({X.numel() * 4 / 2**20:.0f} MiB of features per GPU, no flush needed)',
-                           'chunk_frames': args.chunk_frames, 'parallelism': f'dp{world} (utterances sharded, '
-                           'one all-reduce of the statistics per step)'},
-                'clocks': clocks, 'wall_s_timed_region': wall,
-                'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(world * X.numel() * 4),
-                        'd2h_bytes_per_step': 8 * world, 'steps': n_e2e},
-                'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu,
-                'elbo_per_frame': {'first': elbo_pf[0], 'last': elbo_pf[-1]}}
-        print(json.dumps(line), flush=True)
+    h2d_rate = X.numel() * 4 * n_e2e / e2e_s / 1e9       # this rank's host -> device rate while streaming
+    rates = torch.tensor([h2d_rate], device=dev, dtype=torch.float64)
+    all_rates = [rates.clone() for _ in range(world)]
     if world > 1:
+        dist.all_gather(all_rates, rates)
+    del eng2, host_X
+    if rank != 0:
+        return None
+
+    peak, peak_src = measured_peaks()
+    Q = 2 * D + 2
+    nf = U * T
+    # algorithmic work per frame of every stage: bytes B_alg = 8D + 16K split over KA (read X, write
+    # llh), KB (read llh once more, write + read alpha) and KC (read X); flops F_alg = 4 Q M split over KA and KC
+    alg_bytes = {'KA_emission_llh': 4 * D + 4 * K, 'KB_forward_backward': 12 * K, 'KC_accumulate': 4 * D}
+    alg_flops = {'KA_emission_llh': 2 * Q * M, 'KC_accumulate': 2 * Q * M}
+    traffic_pf = {}
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tpath):        # dram bytes per frame per launch from the committed ncu capture
+        with open(tpath) as f:
+            traffic_pf = json.load(f).get(name, {})
+    tc_peak = ctx.tc_peak[tensor_kind] / 3.0      # 3-pass split (hi.hi + lo.hi + hi.lo) of the measured kind peak
+    fps = nf / (ms / steps * 1e-3)                # per GPU
+    Pn = c['n_units']
+    nnz = 2 * K - Pn + Pn * Pn
+    mhz = (clocks or {}).get('sm_mhz') or 1965.0
+    fractions = {
+        'hbm': fps * (8 * D + 16 * K) / 1e9 / peak,
+        'tensor_3pass': fps * 4 * Q * M / 1e12 / tc_peak,
+        'scan_mufu': fps * 2 * nnz / (148 * 16 * mhz * 1e6),
+        'tensor_peak_tflops': tc_peak,
+        'tensor_peak_source': f'beer_probe_mma kind::{tensor_kind} measured in this run '
+                              f'({ctx.tc_peak[tensor_kind]:.0f} TFLOP/s dense) / 3 passes',
+        'alg_bytes_per_frame': 8 * D + 16 * K, 'alg_flops_per_frame': 4 * Q * M}
+    # the binding roofline of the configuration: tensor pipe when the 3-pass contraction needs more time
+    # than the algorithmic bytes at HBM speed
+    tensor_bound = (4 * Q * M / 1e12 / tc_peak) > ((8 * D + 16 * K) / 1e9 / peak)
+    dom = max((k for k in stage_ms if k in alg_bytes), key=lambda k: stage_ms[k], default=None)
+    roofline = None
+    if dom is not None:
+        sec = stage_ms[dom] * 1e-3
+        if tensor_bound and dom in alg_flops:
+            achieved = alg_flops[dom] * nf / sec / 1e12
+            roofline = {'bound': 'tensor', 'kernel': dom, 'achieved': achieved, 'peak': tc_peak, 'unit': 'TFLOP/s',
+                        'frac': achieved / tc_peak, 'peak_source': fractions['tensor_peak_source'],
+                        'alg_flops_per_frame': alg_flops[dom]}
+        else:
+            achieved = alg_bytes[dom] * nf / sec / 1e9
+            roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                        'frac': achieved / peak, 'peak_source': peak_src, 'alg_bytes_per_frame': alg_bytes[dom]}
+        roofline.update({
+            'traffic': (traffic_pf[dom] * nf if dom in traffic_pf else None),
+            'traffic_unit': 'bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)',
+            'launch_ms': stage_ms[dom], 'stage_ms': stage_ms,
+            'step_frac': fractions['tensor_3pass'] if tensor_bound else fractions['hbm'],
+            'step_bound': 'tensor' if tensor_bound else 'hbm', 'step_fractions': fractions})
+    return {'workload': workload_name(name, c), 'value': value, 'ms_per_step': ms / steps, 'steps': steps,
+            'warmup': warmup, 'clocks': clocks, 'wall_s_timed_region': wall,
+            'l2': f'inputs larger than L2 ({X.numel() * 4 / 2**20:.0f} MiB of features per GPU, no flush needed)',
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(world * X.numel() * 4),
+                    'd2h_bytes_per_step': 8 * world, 'steps': n_e2e,
+                    'h2d_gbs_per_rank': [round(float(r.item()), 2) for r in all_rates]},
+            'gpu_launches': launches, 'roofline': roofline, 'tensor_kind': tensor_kind,
+            'elbo_per_frame': {'first': elbo_pf[0], 'last': elbo_pf[-1]}}
+
+
+def run_gpu(args, configs):
+    import torch
+    import torch.distributed as dist
+    from beer_b200 import ops
+    from beer_b200.synthetic import CONFIGS
+
+    ctx = Ctx()
+    ctx.world = int(os.environ.get('WORLD_SIZE', '1'))
+    ctx.rank = int(os.environ.get('RANK', '0'))
+    ctx.local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if ctx.world != args.gpus:
+        raise SystemExit(f'--gpus {args.gpus} needs {args.gpus} ranks (torchrun), got WORLD_SIZE={ctx.world}')
+    torch.cuda.set_device(ctx.local_rank)
+    ctx.dev = torch.device('cuda', ctx.local_rank)
+    if ctx.world > 1:
+        from beer_b200.engine import bind_to_gpu_cpus
+        ctx.cpus = bind_to_gpu_cpus(ctx.local_rank)      # pinned feature buffers next to this rank's GPU (e2e leg)
+        # NCCL announces its version on stdout at the first collective: keep stdout to the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=ctx.dev)
+            dist.all_reduce(torch.zeros(1, device=ctx.dev))
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+    ops.require_cuda()
+    # tensor-pipe peaks of the MMA kinds the kernels use, measured on this GPU before the timed work
+    ctx.tc_peak = {k: ops.probe_mma_tflops(k) for k in ('tf32', 'f16')}
+
+    results = []
+    for i, name in enumerate(configs):
+        c = dict(CONFIGS[name])
+        if args.n_utts:
+            c['n_utts'] = args.n_utts
+        if args.viterbi:
+            c['viterbi'] = True
+        steps, warmup = (args.steps, args.warmup) if i == 0 else (max(args.steps, 10), max(args.warmup, 3))
+        results.append((name, c, run_config(ctx, args, name, c, steps, warmup, primary=(i == 0))))
+        torch.cuda.empty_cache()
+    if ctx.world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    if ctx.rank == 0:
+        # CPU side, after the last collective: ELBO check of every configuration against the reference in float64
+        # and (one GPU only) the reference timed on the host cores
+        for name, c, r in results:
+            arm = None
+            if not args.no_elbo_check or (ctx.world == 1 and not args.no_cpu_baseline):
+                arm = CpuArm(c)
+            if not args.no_elbo_check:
+                n_check = 2 if c['n_comp'] * c['n_units'] * c['n_states'] > 2000 else 8
+                r['elbo_check'] = elbo_check(ctx, name, c, arm, min(n_check, arm.n_workers))
+            r['cpu_baseline'] = None
+            if ctx.world == 1 and not args.no_cpu_baseline:
+                shards, upw, keep = cpu_shards(c, arm.n_workers)
+                arm.throughput([[s[0][:50]] for s in shards])  # warm the workers (imports, first-call set-up)
+                v, frames, took = arm.throughput(shards)
+                r['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': arm.n_workers, 'kind': arm.kind,
+                                     'sample': arm.describe(upw, keep) + f' ({took:.1f} s)'}
+            if arm is not None:
+                arm.close()
+        name, c, r = results[0]
+        line = {'metric': METRIC, 'value': r['value'], 'unit': UNIT, 'n_gpus': ctx.world, 'steps': r['steps'],
+                'warmup': r['warmup'], 'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'config': {'workload': r['workload'], 'l2': r['l2'], 'chunk_frames': args.chunk_frames,
+                           'tensor_kind': r['tensor_kind'],
+                           'parallelism': f'dp{ctx.world} (utterances sharded, one all-reduce of the statistics per step)'},
+                'clocks': r['clocks'], 'wall_s_timed_region': r['wall_s_timed_region'], 'e2e': r['e2e'],
+                'gpu_launches': r['gpu_launches'], 'roofline': r['roofline'], 'cpu_baseline': r.get('cpu_baseline'),
+                'elbo_check': r.get('elbo_check'), 'elbo_per_frame': r['elbo_per_frame'],
+                'tensor_peaks_tflops': {k: round(v, 1) for k, v in ctx.tc_peak.items()}}
+        if len(results) > 1:
+            line['secondary'] = {n: {k: v for k, v in rr.items() if k not in ('clocks', 'wall_s_timed_region')}
+                                 for n, _, rr in results[1:]}
+        print(json.dumps(line), flush=True)
+    if ctx.world > 1:
         dist.destroy_process_group()
 
 
@@ -410,26 +556,30 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--config', default='cfg2')
+    ap.add_argument('--config', default=None, help='cfg3 (default, + cfg2 as `secondary`), cfg2, cfg2ali')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--chunk-frames', type=int, default=None)
     ap.add_argument('--e2e-chunk-frames', type=int, default=None)
     ap.add_argument('--n-utts', type=int, default=None, help='override utterances per GPU (debug)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-elbo-check', action='store_true')
+    ap.add_argument('--no-secondary', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel eagerly (no CUDA graph)')
     ap.add_argument('--viterbi', action='store_true', help='Viterbi training (one-hot posteriors of the best path) '
                     'instead of forward-backward; a secondary workload, not the BASELINE metric')
     args = ap.parse_args()
     from beer_b200.synthetic import CONFIGS
-    c = dict(CONFIGS[args.config])
-    if args.n_utts:
-        c['n_utts'] = args.n_utts
-    if args.viterbi:
-        c['viterbi'] = True
-    if args.impl == 'reference':
-        run_reference(args, c)
+    if args.config is None:
+        configs = ['cfg3'] + ([] if args.no_secondary else ['cfg2'])
     else:
-        run_gpu(args, c)
+        configs = [args.config]
+    if args.impl == 'reference':
+        c = dict(CONFIGS[configs[0]])
+        if args.n_utts:
+            c['n_utts'] = args.n_utts
+        run_reference(args, configs[0], c)
+    else:
+        run_gpu(args, configs)
 
 
 if __name__ == '__main__':

@@ -306,6 +306,19 @@ BEER_API int beer_fbank(const float* signal, int64_t n_samples, int frame_len, i
  * out[t] = sum_{k=1..wlen} k (fea[t+k] - fea[t-k]) / (2 sum k^2). */
 BEER_API int beer_add_deltas(const float* fea, int n_frames, int dim, int wlen, float* out, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Roofline probes (measurement only: bench.py / tools/microbench.py time them with CUDA events)
+ * ---------------------------------------------------------------------- */
+
+/* n_mma back-to-back tcgen05.mma (M = 128, N = 256, one k-step) per SM on resident operands: the dispatch-limited
+ * tensor-pipe peak of MMA kind 0 = tf32 (K = 8) or 1 = f16 (K = 16).  *flops_out_host = flops issued by the launch. */
+BEER_API int beer_probe_mma(int kind, int n_mma, double* flops_out_host, void* stream);
+/* Write-only stream over `bytes` of dst (128-byte aligned): mode 0 = float4 stores, 1 = 32 KB bulk copies
+ * shared -> global (cp.async.bulk).  The DRAM write ceiling of an llh-producing kernel. */
+BEER_API int beer_probe_fill(float* dst, int64_t bytes, int mode, void* stream);
+/* Read-only stream over `bytes` of src (float4 loads). */
+BEER_API int beer_probe_read(const float* src, int64_t bytes, float* sink, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

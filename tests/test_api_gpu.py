@@ -490,3 +490,41 @@ def test_gradient_wrt_frames(beer, name):
     acc = hmm.accumulate(None)
     par = hmm.modelset.original_modelset.means_precisions
     assert np.abs(acc[par].cpu().numpy() - g['acc_normal']).max() <= 3e-5 * np.abs(g['acc_normal']).max()
+
+
+@pytest.mark.parametrize('P,S', [(96, 4), (130, 3), (250, 4)])
+def test_phoneloop_unit_counts_many_units(beer, P, S):
+    """Unit counts of phone loops around the 128-unit limit of the fused reduction (phoneloop.py:83-101): 96 units
+    run the one-warp left-to-right kernel with the counts fused into its backward sweep; 130 and 250 units (the
+    1000-state graph of BASELINE configs[2]) have no counting kernel, `n_units` reports 0 and the model reduces the
+    ends x starts block of the transition posteriors instead.  Both against the oracle's dense xi."""
+    from beer_b200 import ops, synthetic
+    from oracle import beer_oracle as O
+    D, T = 8, 37
+    K = P * S
+    graph, starts, ends = synthetic.phone_loop_graph(P, S)
+    means = 2.0 * torch.randn(K, D, generator=torch.Generator().manual_seed(3))
+    X = synthetic.sample_utterances(graph, means, 1, T, seed=5, device=DEV)
+    ns = beer.NormalSet.create(torch.zeros(D, device=DEV), torch.ones(D, device=DEV), size=K, prior_strength=1.,
+                               noise_std=1., cov_type='diagonal')
+    start_pdf = {f'u{i}': int(s) for i, s in enumerate(starts)}
+    end_pdf = {f'u{i}': int(s) for i, s in enumerate(ends)}
+    pl = beer.PhoneLoop.create(graph, start_pdf, end_pdf, ns, prior_strength=1.)
+    plan = pl.graph.plan(n_pdfs=K)
+    assert plan.n_units == (P if P <= 128 else 0)
+    if plan.n_units == 0:
+        with pytest.raises(beer._lib.BeerB200Error):        # never dropped silently
+            pdf = torch.zeros(T, K, device=DEV)
+            ops.hmm_forward_backward(plan, pdf, None, torch.tensor([0, T], device=DEV),
+                                     unit_counts=torch.zeros(P, dtype=torch.float64, device=DEV))
+    stats = pl.sufficient_statistics(X)
+    pl.expected_log_likelihood(stats)
+    wu = pl.categorical.weights
+    got = pl.accumulate(stats)[wu].cpu().numpy()
+    post = tuple(a[:, None] if a.ndim == 1 else a for a in get_ng(ns.means_precisions.posterior))
+    post = (post[0], post[1].reshape(-1, 1), post[2].reshape(-1, 1), post[3])
+    og = (pl.graph.init_log_probs.double().numpy(), pl.graph.final_log_probs.double().numpy(),
+          pl.graph.trans_log_probs.double().numpy(), pl.graph.pdf_id_mapping)
+    r = O.hmm_estep(X.double().cpu().numpy(), post, None, og, trans_posteriors=True)
+    want = O.phoneloop_counts(r['gamma'], r['xi'], starts, ends)
+    np.testing.assert_allclose(got, want, rtol=3e-5, atol=3e-5)

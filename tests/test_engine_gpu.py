@@ -236,3 +236,46 @@ def test_vb_iterations_streamed_mixture_kernels(chunk):
     for g, w in zip(_host(em.post), ng_post):
         np.testing.assert_allclose(g, w, rtol=2e-4, atol=2e-4)
     np.testing.assert_allclose(groups[0].post.double().cpu().numpy(), dpost, rtol=2e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize('use_graph', [False, True])
+def test_vb_iterations_cfg3_shape(use_graph):
+    """The exact shape of BASELINE configs[2] (the north-star target): 250 units x 4 states = 1000 states, 8
+    Gaussians per state (M = 8000: 63 Gaussian tiles of the statistics kernel, 125 weight chunks of the emission
+    kernel), D = 40, the eight-warps-per-utterance left-to-right scan; three short ragged utterances, two VB
+    iterations against the fp64 oracle of accumulate + update (accumulate.py:37-63, update.py:39-62)."""
+    from beer_b200 import ops, synthetic
+    from beer_b200.engine import EmissionParams, Utterances, VBEngine, WeightGroup
+    dev = torch.device('cuda', 0)
+    P, S, D, C = 250, 4, 40, 8
+    K, M = P * S, P * S * C
+    lens = [70, 33, 129]
+    graph, _, _ = synthetic.phone_loop_graph(P, S)
+    plan = ops.GraphPlan(graph.init_log_probs.numpy(), graph.final_log_probs.numpy(),
+                         graph.trans_log_probs.numpy(), graph.pdf_id_mapping, n_pdfs=K)
+    means = 2.0 * torch.randn(K, D, generator=torch.Generator().manual_seed(0))
+    full = synthetic.sample_utterances(graph, means, len(lens), max(lens), seed=1, device=dev)
+    full = full.reshape(len(lens), max(lens), D)
+    utts_dev = [full[i, :n] for i, n in enumerate(lens)]
+    X = torch.cat(utts_dev)
+    prior, post = synthetic.initial_normal_gamma(M, D, seed=2, device=dev)
+    conc = torch.full((K, C), 1.0 / C, device=dev)
+    groups = (WeightGroup(0, K, C, conc.clone(), conc.clone()),)
+    em = EmissionParams(prior, post, comp_off=np.arange(K + 1) * C, weight_groups=groups)
+    assert em.use_tc and ops.accumulate_tc_supported(M, D)
+    dprior, dpost = conc.double().cpu().numpy(), conc.double().cpu().numpy()
+    N = sum(lens)
+    eng = VBEngine(em, plan, Utterances(X, lens), datasize=float(N), distributed=False, use_graph=use_graph)
+    ng_prior, ng_post = _host(prior), _host(post)
+    og = (graph.init_log_probs.double().numpy(), graph.final_log_probs.double().numpy(),
+          graph.trans_log_probs.double().numpy(), graph.pdf_id_mapping)
+    utts = [u.double().cpu().numpy() for u in utts_dev]
+    for it in range(3 if use_graph else 2):
+        want, ng_post, dpost, info = O.vb_iteration_hmm(utts, ng_prior, ng_post, dprior, dpost, og)
+        got = float(eng.step().item())
+        assert abs(got - want) <= 1e-5 * abs(want), (it, got, want)
+        acc = eng.acc.cpu().numpy()
+        assert np.abs(acc - info['acc_normal']).max() <= 3e-5 * np.abs(info['acc_normal']).max()
+    for g, w in zip(_host(em.post), ng_post):
+        np.testing.assert_allclose(g, w, rtol=2e-4, atol=2e-4)
+    np.testing.assert_allclose(groups[0].post.double().cpu().numpy(), dpost, rtol=2e-4, atol=1e-5)

@@ -289,3 +289,24 @@ def test_gamma_distribution_math():
     np.testing.assert_allclose(float(kl_div(q, p)), want, rtol=1e-10)
     q._natural_grad_update(p, torch.tensor([-2.0, 4.0], dtype=torch.float64), 1.0)
     np.testing.assert_allclose([float(q.params.shape), float(q.params.rate)], [a0 + 4.0, b0 + 2.0], rtol=1e-6)
+
+
+def test_utils_onehot_logsumexp():
+    """beer_b200.utils mirrors beer/utils.py:84-123: `onehot`, and a `logsumexp` that hands back +-inf when the
+    maximum is +-inf instead of NaN."""
+    import torch
+    from beer_b200 import utils
+    labels = [2, 0, 3, 3]
+    got = utils.onehot(labels, 4, torch.float64, 'cpu').numpy()
+    np.testing.assert_array_equal(got, O.onehot(np.asarray(labels), 4))
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((5, 7)) * 30
+    x[1, :] = -np.inf
+    x[3, 2] = -np.inf
+    for dim in (0, 1):
+        got = utils.logsumexp(torch.from_numpy(x), dim=dim).numpy()
+        with np.errstate(all='ignore'):
+            want = O.logsumexp(x, axis=dim)
+        np.testing.assert_allclose(got, want, rtol=1e-12)
+    assert utils.logsumexp(torch.tensor([float('inf'), 1.0]), dim=0).item() == float('inf')
+    assert utils.logsumexp(torch.full((3,), float('-inf')), dim=0).item() == float('-inf')

@@ -1,0 +1,35 @@
+#!/usr/bin/env python
+"""Roofline denominators measured on the GPU this runs on:
+
+    python tools/microbench.py > gpurun_out/microbench.json
+
+* tcgen05 dispatch-limited peak of kind::tf32 and kind::f16 (beer_probe_mma: M = 128, N = 256 MMAs back to back,
+  one CTA per SM) -> the 3-pass split of the statistics / emission kernels runs at a third of it;
+* DRAM write-only ceilings (float4 stores, 32 KB bulk copies shared -> global) and the read-only rate over 4 GiB,
+  next to the driver's copy figure in MEASURED_PEAKS.json.
+"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    import torch
+    from beer_b200 import ops
+    ops.require_cuda()
+    out = {'gpu': torch.cuda.get_device_name(0)}
+    for kind in ('tf32', 'f16'):
+        out[f'mma_{kind}_tflops'] = [round(ops.probe_mma_tflops(kind, n_mma=n), 1) for n in (2000, 20000, 200000)]
+    for mode in ('fill_st', 'fill_bulk', 'read'):
+        out[f'dram_{mode}_gbs'] = round(ops.probe_dram_gbs(mode), 1)
+    a = torch.empty(1 << 30, device='cuda', dtype=torch.float32)
+    b = torch.empty_like(a)
+    t = ops._timed(lambda: b.copy_(a), 5)
+    out['dram_copy_gbs'] = round(2 * a.numel() * 4 / t / 1e9, 1)
+    print(json.dumps(out))
+
+
+if __name__ == '__main__':
+    main()
