@@ -1,0 +1,931 @@
+// Mixture path (C Gaussians per pdf, M = Kp * C large: BASELINE configs[2]) on tcgen05 kind::f16 with a 3-pass
+// fp16 split (hi.hi + lo.hi + hi.lo: 22-bit operands, the accuracy of the 3xTF32 kernels at twice the MMA rate),
+// built so that the per-Gaussian llhs [N, M] NEVER reach HBM:
+//
+//   feature images (once per resident chunk)   X -> [x | -x^2/2] scaled per dimension by a power of two, split into
+//       fp16 hi / lo, stored as ready-made UMMA operand tiles of 64 frames: img1 = frame-major (K = statistics),
+//       img2 = statistic-major (K = frames).  TMA bulk copies land them in shared memory as they are: nobody
+//       transposes, splits or converts inside the hot kernels.
+//   KA16 (emission16_kernel)   S = img1 . W'^T per (128 frames x NB Gaussians), epilogue: z = S k1 + k2 (log2 domain),
+//       log-sum-exp over the C components -> llh2 [N, Kp] (log2 units, offset form).  Nothing per Gaussian is written.
+//   KCF (mixstats16_kernel)    the flash-attention structure: per (128 Gaussians x 64 frames)
+//         S^T = W' . img1^T           W' RESIDENT IN TENSOR MEMORY (A operand), accumulator lanes = Gaussians
+//         w   = 2^(S k1 + k2 + lg2(post) - llh2)   responsibilities x pdf posteriors, per thread = one Gaussian
+//         A2  = fp16 hi / lo of w written back IN PLACE over S^T with tcgen05.st
+//         acc += A2 . img2^T          second MMA with A from tensor memory, K = frames
+//       (mixtureset.py:100-112, normalset.py:121-123).  Costs 2 Q M more flop per frame than reading stored
+//       responsibilities, removes 2 x 4 M bytes per frame of HBM traffic (cfg3: 80 of the 121 GB per step).
+//
+// Both kernels compute S with the SAME operands (same images, same packed weights), the same k-step and pass order,
+// so the z of KCF is the z KA16 normalised: the responsibilities sum to one without a second normalisation.
+//
+// Reference semantics: beer/dists/normalgamma.py:55-59, beer/models/mixtureset.py:85-112, normalset.py:121-123.
+#include <cuda_fp16.h>
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "../../include/beer_b200.h"
+
+namespace beer {
+namespace mix16 {
+
+using namespace tcu;
+
+constexpr int TILE = 64;            // frames per image tile
+constexpr int HI_EXP = 12;          // scaled statistics: per-dimension maximum in [2^12, 2^13)
+constexpr int W_EXP = 13;           // scaled weights: per-Gaussian maximum in [2^13, 2^14)
+
+__host__ __device__ inline int kp_of(int D) { return (2 * D + 15) / 16 * 16; }
+
+// offsets in halfs inside one image half-tile
+__device__ __forceinline__ int off1(int f, int k, int KP) { return (f >> 3) * (KP * 8) + (k >> 3) * 64 + (f & 7) * 8 + (k & 7); }
+__device__ __forceinline__ int off2(int k, int f) { return (k >> 3) * (TILE * 8) + (f >> 3) * 64 + (k & 7) * 8 + (f & 7); }
+
+__device__ __forceinline__ uint32_t pack_h2(float lo_elem, float hi_elem) {
+    __half2 h = __floats2half2_rn(lo_elem, hi_elem);     // .x (low 16 bits) = first argument
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+// fp32 rounded to 11 significant bits (what fp16 keeps of a normal number): two integer instructions
+__device__ __forceinline__ float h_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+
+__device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// A operand in tensor memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
+    uint32_t r[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// feature images
+// ---------------------------------------------------------------------------------------------
+
+// absmax[d] = max_t |x_td| (bits of a non-negative float compare like integers)
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ X, int64_t N, int D, uint32_t* __restrict__ absmax) {
+    __shared__ uint32_t s_max[256];
+    for (int i = threadIdx.x; i < D; i += blockDim.x) s_max[i] = 0u;
+    __syncthreads();
+    const int D4 = D >> 2, rpb = 256 / D4;
+    const int c4 = threadIdx.x % D4, rl = threadIdx.x / D4;
+    float m[4] = {0.f, 0.f, 0.f, 0.f};
+    if (rl < rpb) {
+        for (int64_t r = (int64_t)blockIdx.x * rpb + rl; r < N; r += (int64_t)gridDim.x * rpb) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(X + (size_t)r * D) + c4);
+            m[0] = fmaxf(m[0], fabsf(v.x)); m[1] = fmaxf(m[1], fabsf(v.y));
+            m[2] = fmaxf(m[2], fabsf(v.z)); m[3] = fmaxf(m[3], fabsf(v.w));
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) atomicMax(&s_max[4 * c4 + e], __float_as_uint(m[e]));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < D; i += blockDim.x) atomicMax(&absmax[i], s_max[i]);
+}
+
+// alpha[k] = power of two that brings the largest |statistic k| into [2^HI_EXP, 2^(HI_EXP+1)); statistics = [x | -x^2/2]
+__global__ void scales_kernel(const uint32_t* __restrict__ absmax, int D, float* __restrict__ alpha) {
+    const int k = threadIdx.x;
+    if (k >= 2 * D) return;
+    const float mx = __uint_as_float(absmax[k < D ? k : k - D]);
+    const float v = (k < D) ? mx : 0.5f * mx * mx;
+    float a = 1.f;
+    if (v > 0.f && isfinite(v)) {
+        int e = HI_EXP - ilogbf(v);
+        e = max(-100, min(100, e));
+        a = ldexpf(1.f, e);
+    }
+    alpha[k] = a;
+}
+
+// One CTA per 64-frame tile: X -> img1 (frame-major) and img2 (statistic-major), fp16 hi | lo halves.
+__global__ void __launch_bounds__(256) feat_image_kernel(const float* __restrict__ X, int64_t N, int D,
+                                                         const float* __restrict__ alpha, __half* __restrict__ img1,
+                                                         __half* __restrict__ img2) {
+    extern __shared__ float xs[];      // [TILE][D + 1]
+    __shared__ float s_alpha[256];
+    const int KP = kp_of(D), D4 = D >> 2, ldx = D + 1;
+    const int64_t tile = blockIdx.x, t0 = tile * TILE;
+    for (int i = threadIdx.x; i < KP; i += blockDim.x) s_alpha[i] = (i < 2 * D) ? alpha[i] : 0.f;
+    for (int e = threadIdx.x; e < TILE * D4; e += blockDim.x) {
+        const int r = e / D4, c4 = e - r * D4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t0 + r < N) v = __ldg(reinterpret_cast<const float4*>(X + (size_t)(t0 + r) * D) + c4);
+        float* dst = xs + r * ldx + 4 * c4;
+        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    }
+    __syncthreads();
+    auto stat = [&](int f, int k) -> float {
+        if (k >= 2 * D) return 0.f;
+        const float x = xs[f * ldx + (k < D ? k : k - D)];
+        return ((k < D) ? x : -0.5f * x * x) * s_alpha[k];
+    };
+    __half* t1 = img1 + (size_t)tile * (2 * TILE * KP);
+    __half* t2 = img2 + (size_t)tile * (2 * TILE * KP);
+    const int KG = KP >> 3;
+    for (int item = threadIdx.x; item < TILE * KG; item += blockDim.x) {
+        const int f = item / KG, k8 = item - f * KG;
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float a = stat(f, 8 * k8 + 2 * e), b = stat(f, 8 * k8 + 2 * e + 1);
+            const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
+            hi[e] = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
+            lo[e] = pack_h2(a - __half2float(ha), b - __half2float(hb));
+        }
+        const int o = off1(f, 8 * k8, KP);
+        *reinterpret_cast<uint4*>(t1 + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(t1 + TILE * KP + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+    for (int item = threadIdx.x; item < KP * (TILE / 8); item += blockDim.x) {
+        const int k = item >> 3, f8 = item & 7;
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float a = stat(8 * f8 + 2 * e, k), b = stat(8 * f8 + 2 * e + 1, k);
+            const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
+            hi[e] = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
+            lo[e] = pack_h2(a - __half2float(ha), b - __half2float(hb));
+        }
+        const int o = off2(k, 8 * f8);
+        *reinterpret_cast<uint4*>(t2 + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(t2 + TILE * KP + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+// frame_ref[t] = sum_d (-x_td^2 / 2) ref[d] + ref[D]: the per-frame constant of the offset form (emission_prepare)
+__global__ void __launch_bounds__(256) frame_ref_kernel(const float* __restrict__ X, int64_t N, int D,
+                                                        const float* __restrict__ ref, float* __restrict__ out) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= N) return;
+    const float4* row = reinterpret_cast<const float4*>(X + (size_t)t * D);
+    float acc = 0.f;
+    for (int c = 0; c < (D >> 2); ++c) {
+        const float4 v = __ldg(row + c);
+        acc = fmaf(-0.5f * v.x * v.x, __ldg(ref + 4 * c), acc);
+        acc = fmaf(-0.5f * v.y * v.y, __ldg(ref + 4 * c + 1), acc);
+        acc = fmaf(-0.5f * v.z * v.z, __ldg(ref + 4 * c + 2), acc);
+        acc = fmaf(-0.5f * v.w * v.w, __ldg(ref + 4 * c + 3), acc);
+    }
+    out[t] = acc + __ldg(ref + D);
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight pack: one warp per Gaussian (rows M..Mp-1 are padding: zero weights, z = -inf)
+//   wimg   [n_chunks][hi | lo][NB x KP] halfs, core-matrix layout    (B operand of KA16)
+//   wtm    [Mp][KP/2 hi words | KP/2 lo words]                       (A operand of KCF, copied to tensor memory)
+//   k1     [Mp] = log2(e) / beta_j,  k2 [Mp] = bias_j log2(e)         (z = S k1 + k2, log2 domain)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) pack16_kernel(const float* __restrict__ W, const float* __restrict__ bias,
+                                                     const float* __restrict__ alpha, int M, int Mp, int D, int NB,
+                                                     __half* __restrict__ wimg, uint32_t* __restrict__ wtm,
+                                                     float* __restrict__ k1, float* __restrict__ k2) {
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (j >= Mp) return;
+    const int KP = kp_of(D), NPAIR = KP >> 1;
+    float v[3][2];
+    float mx = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int p = lane + 32 * i;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int k = 2 * p + e;
+            float w = 0.f;
+            if (j < M && p < NPAIR && k < 2 * D) w = W[(size_t)j * 2 * D + k] / alpha[k];     // exact: alpha = 2^e
+            v[i][e] = w;
+            mx = fmaxf(mx, fabsf(w));
+        }
+    }
+    mx = warp_max(mx);
+    int be = 0;
+    if (mx > 0.f && isfinite(mx)) be = max(-100, min(100, W_EXP - ilogbf(mx)));
+    const float beta = ldexpf(1.f, be);
+    const int chunk = j / NB, n = j - chunk * NB;
+    __half* img = wimg + (size_t)chunk * (2 * NB * KP);
+    uint32_t* tm = wtm + (size_t)j * KP;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int p = lane + 32 * i;
+        if (p >= NPAIR) continue;
+        const float a = v[i][0] * beta, b = v[i][1] * beta;
+        const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
+        const uint32_t hi = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
+        const uint32_t lo = pack_h2(a - __half2float(ha), b - __half2float(hb));
+        const int o = off1(n, 2 * p, KP);
+        *reinterpret_cast<uint32_t*>(img + o) = hi;
+        *reinterpret_cast<uint32_t*>(img + NB * KP + o) = lo;
+        tm[p] = hi;
+        tm[NPAIR + p] = lo;
+    }
+    if (lane == 0) {
+        k1[j] = (j < M) ? kLog2e * ldexpf(1.f, -be) : 0.f;
+        k2[j] = (j < M) ? bias[j] * kLog2e : kNegInf;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// KA16: llh2 [N, Kp] = log2 sum_c 2^(z_tkc)
+// ---------------------------------------------------------------------------------------------
+constexpr int KA_WORKERS = 256, KA_MMA_WARP = KA_WORKERS / 32, KA_LOAD_WARP = KA_MMA_WARP + 1, KA_THREADS = KA_WORKERS + 64;
+constexpr int K12_RING = 4;
+
+struct KaArgs {
+    const __half* img1;
+    int64_t N;
+    const __half* wimg;
+    const float* k1;
+    const float* k2;
+    int C, logC, Kp, NB, n_chunks;
+    float* llh2;
+    int64_t ld;
+};
+
+struct KaBarriers {
+    uint64_t a_full[2], a_empty[2];
+    uint64_t b_full[2], b_empty[2];
+    uint64_t t_full[2], t_empty[2];
+    uint32_t tmem_base;
+    uint32_t pad[3];
+};
+
+template <int KP>
+__global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a) {
+    constexpr int FR = 128, KSTEPS = KP / 16;
+    constexpr uint32_t LBO = 128, SBO = KP * 16;
+    constexpr int A_HALF = FR * KP;                     // halfs of one A image (hi or lo) of a 128-frame tile
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __half* As = reinterpret_cast<__half*>(smem_raw);                        // [2][hi | lo]
+    __half* Bs = As + 2 * 2 * A_HALF;                                        // [2][hi | lo] of NB x KP
+    const int b_stage = 2 * a.NB * KP;
+    float* s_k12 = reinterpret_cast<float*>(Bs + 2 * b_stage);               // [K12_RING][k1 NB | k2 NB]
+    KaBarriers* bars = reinterpret_cast<KaBarriers*>(s_k12 + K12_RING * 2 * a.NB);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t n_tiles = (a.N + FR - 1) / FR, n_tiles64 = (a.N + TILE - 1) / TILE;
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars->a_full[i], 1);
+            mbar_init(&bars->a_empty[i], 1);
+            mbar_init(&bars->b_full[i], 1);
+            mbar_init(&bars->b_empty[i], 1);
+            mbar_init(&bars->t_full[i], 1);
+            mbar_init(&bars->t_empty[i], KA_WORKERS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == KA_MMA_WARP) tmem_alloc(&bars->tmem_base, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == KA_LOAD_WARP) {
+        if (lane == 0) {
+            uint32_t it = 0, tile_it = 0;
+            const uint32_t half_bytes = TILE * KP * 2, b_bytes = (uint32_t)b_stage * 2u, k_bytes = (uint32_t)a.NB * 4u;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+                const int ab = tile_it & 1;
+                mbar_wait(&bars->a_empty[ab], ((tile_it >> 1) & 1) ^ 1);
+                const int64_t tA = 2 * tile, tB = tA + 1;
+                const bool two = tB < n_tiles64;
+                mbar_arrive_expect_tx(&bars->a_full[ab], (two ? 4u : 2u) * half_bytes);
+                __half* dst = As + (size_t)ab * 2 * A_HALF;
+                const __half* srcA = a.img1 + (size_t)tA * (2 * TILE * KP);
+                bulk_g2s(dst, srcA, half_bytes, &bars->a_full[ab]);                              // hi, rows 0..63
+                bulk_g2s(dst + A_HALF, srcA + TILE * KP, half_bytes, &bars->a_full[ab]);         // lo, rows 0..63
+                if (two) {
+                    const __half* srcB = a.img1 + (size_t)tB * (2 * TILE * KP);
+                    bulk_g2s(dst + TILE * KP, srcB, half_bytes, &bars->a_full[ab]);                       // hi, rows 64..127
+                    bulk_g2s(dst + A_HALF + TILE * KP, srcB + TILE * KP, half_bytes, &bars->a_full[ab]);  // lo
+                }
+                for (int c = 0; c < a.n_chunks; ++c, ++it) {
+                    const int st = it & 1;
+                    mbar_wait(&bars->b_empty[st], ((it >> 1) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&bars->b_full[st], b_bytes + 2u * k_bytes);
+                    bulk_g2s(Bs + (size_t)st * b_stage, a.wimg + (size_t)c * b_stage, b_bytes, &bars->b_full[st]);
+                    float* kd = s_k12 + (it & (K12_RING - 1)) * 2 * a.NB;
+                    bulk_g2s(kd, a.k1 + (size_t)c * a.NB, k_bytes, &bars->b_full[st]);
+                    bulk_g2s(kd + a.NB, a.k2 + (size_t)c * a.NB, k_bytes, &bars->b_full[st]);
+                }
+            }
+        }
+    } else if (warp == KA_MMA_WARP) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(a.NB >> 3) << 17) | ((uint32_t)(FR >> 4) << 24);   // f16 x f16 -> f32
+            uint32_t it = 0, tile_it = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+                const int ab = tile_it & 1;
+                mbar_wait(&bars->a_full[ab], (tile_it >> 1) & 1);
+                const uint32_t a_hi = smem_u32(As + (size_t)ab * 2 * A_HALF), a_lo = a_hi + A_HALF * 2u;
+                for (int c = 0; c < a.n_chunks; ++c, ++it) {
+                    const int st = it & 1, buf = it & 1;
+                    mbar_wait(&bars->b_full[st], (it >> 1) & 1);
+                    mbar_wait(&bars->t_empty[buf], ((it >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t b_hi = smem_u32(Bs + (size_t)st * b_stage), b_lo = b_hi + (uint32_t)a.NB * KP * 2u;
+                    const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256u;
+#pragma unroll 1
+                    for (int s = 0; s < KSTEPS; ++s) {
+                        const uint32_t ko = (uint32_t)s * 256u;
+                        const uint64_t dah = make_desc(a_hi + ko, LBO, SBO), dal = make_desc(a_lo + ko, LBO, SBO);
+                        const uint64_t dbh = make_desc(b_hi + ko, LBO, SBO), dbl = make_desc(b_lo + ko, LBO, SBO);
+                        umma_f16_ss(d_tmem, dah, dbh, idesc, s > 0);
+                        umma_f16_ss(d_tmem, dah, dbl, idesc, 1);      // statistics hi x weights lo
+                        umma_f16_ss(d_tmem, dal, dbh, idesc, 1);      // statistics lo x weights hi
+                    }
+                    umma_commit(&bars->t_full[buf]);
+                    umma_commit(&bars->b_empty[st]);
+                }
+                umma_commit(&bars->a_empty[ab]);
+            }
+        }
+    } else {
+        // epilogue: TMEM lane = frame row 32 (warp % 4) + lane; warps w and w + 4 split the columns
+        const int r = (warp & 3) * 32 + lane, he = warp >> 2;
+        const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+        const int C = a.C;
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int64_t t = tile * FR + r;
+            const bool valid = t < a.N;
+            for (int c = 0; c < a.n_chunks; ++c, ++it) {
+                const int buf = it & 1;
+                mbar_wait(&bars->t_full[buf], (it >> 1) & 1);
+                tc_fence_after();
+                const float* kk = s_k12 + (it & (K12_RING - 1)) * 2 * a.NB;
+                const uint32_t taddr = tmem_base + lane_addr + (uint32_t)buf * 256u;
+                const int nch = a.NB >> 4, ch0 = he ? (nch + 1) / 2 : 0, ch1 = he ? nch : (nch + 1) / 2;
+                for (int p = ch0 * 16; p < ch1 * 16; p += 16) {
+                    float v[16];
+                    tmem_ld16(taddr + (uint32_t)p, v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], kk[p + i], kk[a.NB + p + i]);
+                    if (!valid) continue;
+                    float o[8];
+                    int no = 0;
+#pragma unroll
+                    for (int lg = 1; lg <= 4; ++lg) {
+                        if (C == (1 << lg)) {
+                            const int CC = 1 << lg;
+                            no = 16 / CC;
+#pragma unroll
+                            for (int k = 0; k < 16 / CC; ++k) {
+                                float m = v[k * CC];
+#pragma unroll
+                                for (int j = 1; j < CC; ++j) m = fmaxf(m, v[k * CC + j]);
+                                const float ms = (m == kNegInf) ? 0.f : m;
+                                float sm = 0.f;
+#pragma unroll
+                                for (int j = 0; j < CC; ++j) sm += ex2(v[k * CC + j] - ms);
+                                o[k] = ms + lg2(sm);
+                            }
+                        }
+                    }
+                    const int k0 = (c * a.NB + p) >> a.logC;
+                    float* dst = a.llh2 + (size_t)t * a.ld + k0;
+                    if (no == 2 && (a.ld & 1) == 0) {
+                        *reinterpret_cast<float2*>(dst) = make_float2(o[0], o[1]);
+                    } else if (no == 4 && (a.ld & 3) == 0) {
+                        *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if (i < no && k0 + i < a.Kp) dst[i] = o[i];
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&bars->t_empty[buf]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == KA_MMA_WARP) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+static size_t ka_smem(int KP, int NB) {
+    return (size_t)2 * 2 * 128 * KP * 2 + (size_t)2 * 2 * NB * KP * 2 + (size_t)K12_RING * 2 * NB * 4 + sizeof(KaBarriers) + 1024;
+}
+
+// ---------------------------------------------------------------------------------------------
+// KCF: acc [M, 2D+2] += sum_t w_tj T(x_t),  w = pdf_post x responsibility, responsibilities recomputed on chip
+// ---------------------------------------------------------------------------------------------
+constexpr int GM = 128;                  // Gaussians per CTA (UMMA M, TMEM lanes)
+constexpr int EPI = 512;                 // 16 epilogue warps: 4 per TMEM lane quarter, each a quarter of the 64 frames
+constexpr int KC_MMA_WARP = EPI / 32, KC_LOAD_WARP = KC_MMA_WARP + 1, KC_U_WARP0 = KC_LOAD_WARP + 1;
+constexpr int KC_THREADS = EPI + 32 + 32 + 64;
+constexpr int NS_MAX = 4;                // shared-memory stages (one 64-frame tile of both images + its u block)
+constexpr int NSB = 3;                   // S^T / A2 buffers in tensor memory
+constexpr int DR = 4;                    // tiles per drain of the statistics accumulator (48 truncating accumulations)
+
+struct KcArgs {
+    const __half* img1;
+    const __half* img2;
+    int64_t N;
+    const uint32_t* wtm;
+    const float* k1;
+    const float* k2;
+    const float* alpha;
+    const float* post;       // [N, ld_post] pdf posteriors (x scale)
+    int64_t ld_post;
+    const float* llh2;       // [N, ld_llh]
+    int64_t ld_llh;
+    int M, C, Kp, n_gtiles;
+    int64_t frames_per_cta;  // multiple of TILE
+    float wexp;              // w is carried as w 2^wexp (top of the fp16 range)
+    int ns;                  // shared-memory stages (<= NS_MAX)
+    double* acc;
+    int D;
+};
+
+struct KcBarriers {
+    uint64_t st_full[NS_MAX], st_empty[NS_MAX];
+    uint64_t u_full[NS_MAX], u_empty[NS_MAX];
+    uint64_t s_full[NSB], a2_full[NSB];
+    uint64_t d2_full[2], d2_empty[2];
+    uint32_t tmem_base;
+    uint32_t pad[3];
+};
+
+template <int KP>
+__global__ void __launch_bounds__(KC_THREADS, 1) mixstats16_kernel(KcArgs a) {
+    constexpr int KS1 = KP / 16;                       // k-steps of S^T = W' . img1^T
+    constexpr int KS2 = TILE / 16;                     // k-steps of acc += A2 . img2^T
+    constexpr int IMG_HALF = TILE * KP;                // halfs of one image half-tile
+    constexpr int STAGE_HALFS = 4 * IMG_HALF;          // img1 hi | lo | img2 hi | lo
+    constexpr uint32_t COL_W = 0, COL_S = KP, COL_D2 = KP + NSB * TILE;     // tensor-memory columns
+    static_assert(COL_D2 + 2 * KP <= 512, "tensor memory");
+    constexpr int NCH = KP / 4;                        // 4-column chunks of the accumulator
+    constexpr int MYCH = (NCH + 3) / 4;                // per thread (four warps share a lane quarter)
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __half* stages = reinterpret_cast<__half*>(smem_raw);
+    const int nk = GM / a.C;                           // pdfs of a Gaussian tile
+    const int NS = a.ns;
+    // per (pdf, frame): (llh2, lg2(post) + wexp)
+    float2* s_u = reinterpret_cast<float2*>(stages + (size_t)NS * STAGE_HALFS);   // [NS][nk][TILE]
+    KcBarriers* bars = reinterpret_cast<KcBarriers*>(s_u + (size_t)NS * nk * TILE);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int gtile = blockIdx.x % a.n_gtiles;
+    const int g0 = gtile * GM;
+    const int64_t f_begin = (int64_t)(blockIdx.x / a.n_gtiles) * a.frames_per_cta;
+    const int64_t f_end = min(a.N, f_begin + a.frames_per_cta);
+    const int n_tiles = (f_end > f_begin) ? (int)((f_end - f_begin + TILE - 1) / TILE) : 0;
+    const int64_t tile0 = f_begin / TILE;
+
+    if (tid == 0) {
+        for (int i = 0; i < NS_MAX; ++i) {
+            mbar_init(&bars->st_full[i], 1);
+            mbar_init(&bars->st_empty[i], 1);
+            mbar_init(&bars->u_full[i], 64);
+            mbar_init(&bars->u_empty[i], EPI);
+        }
+        for (int i = 0; i < NSB; ++i) {
+            mbar_init(&bars->s_full[i], 1);
+            mbar_init(&bars->a2_full[i], EPI);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars->d2_full[i], 1);
+            mbar_init(&bars->d2_empty[i], EPI);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == KC_MMA_WARP) tmem_alloc(&bars->tmem_base, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    // the packed weights of this Gaussian tile -> tensor memory (A operand of the first MMA), once
+    if (warp < 4) {
+        const uint32_t* row = a.wtm + (size_t)(g0 + warp * 32 + lane) * KP;
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + COL_W;
+#pragma unroll 1
+        for (int c = 0; c < KP; c += 16) {
+            uint32_t r[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + c) + q);
+                r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
+            }
+            tmem_st16(taddr + (uint32_t)c, r);
+        }
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp == KC_LOAD_WARP) {
+        // ------------------------------ image loader (TMA) -------------------------
+        if (lane == 0) {
+            const uint32_t bytes = 2u * IMG_HALF * 2u;        // hi + lo of one image
+            for (int i = 0; i < n_tiles; ++i) {
+                const int s = i % NS;
+                mbar_wait(&bars->st_empty[s], ((i / NS) & 1) ^ 1);
+                mbar_arrive_expect_tx(&bars->st_full[s], 2u * bytes);
+                __half* dst = stages + (size_t)s * STAGE_HALFS;
+                bulk_g2s(dst, a.img1 + (size_t)(tile0 + i) * (2 * IMG_HALF), bytes, &bars->st_full[s]);
+                bulk_g2s(dst + 2 * IMG_HALF, a.img2 + (size_t)(tile0 + i) * (2 * IMG_HALF), bytes, &bars->st_full[s]);
+            }
+        }
+    } else if (warp == KC_MMA_WARP) {
+        // ------------------------------ MMA issuer ---------------------------------
+        if (lane == 0 && n_tiles > 0) {
+            const uint32_t idesc1 = (1u << 4) | ((uint32_t)(TILE >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
+            const uint32_t idesc2 = (1u << 4) | ((uint32_t)(KP >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
+            auto issue_g1 = [&](int i) {
+                const int s = i % NS, b = i % NSB;
+                mbar_wait(&bars->st_full[s], (i / NS) & 1);
+                tc_fence_after();
+                const uint32_t b_hi = smem_u32(stages + (size_t)s * STAGE_HALFS), b_lo = b_hi + IMG_HALF * 2u;
+                const uint32_t d = tmem_base + COL_S + (uint32_t)b * TILE;
+                const uint32_t w_hi = tmem_base + COL_W, w_lo = w_hi + KP / 2;
+#pragma unroll 1
+                for (int ks = 0; ks < KS1; ++ks) {
+                    const uint64_t dbh = make_desc(b_hi + ks * 256u, 128, KP * 16), dbl = make_desc(b_lo + ks * 256u, 128, KP * 16);
+                    umma_f16_ts(d, w_hi + 8u * ks, dbh, idesc1, ks > 0);
+                    umma_f16_ts(d, w_lo + 8u * ks, dbh, idesc1, 1);       // weights lo x statistics hi
+                    umma_f16_ts(d, w_hi + 8u * ks, dbl, idesc1, 1);       // weights hi x statistics lo
+                }
+                umma_commit(&bars->s_full[b]);
+            };
+            auto issue_g2 = [&](int i) {
+                const int s = i % NS, b = i % NSB;
+                const int grp = i / DR, dbuf = grp & 1;
+                const bool first = (i % DR) == 0, last = (i % DR) == DR - 1 || i == n_tiles - 1;
+                mbar_wait(&bars->a2_full[b], (i / NSB) & 1);
+                if (first) mbar_wait(&bars->d2_empty[dbuf], ((grp >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t b_hi = smem_u32(stages + (size_t)s * STAGE_HALFS + 2 * IMG_HALF), b_lo = b_hi + IMG_HALF * 2u;
+                const uint32_t d = tmem_base + COL_D2 + (uint32_t)dbuf * KP;
+                const uint32_t a2 = tmem_base + COL_S + (uint32_t)b * TILE;
+#pragma unroll 1
+                for (int ks = 0; ks < KS2; ++ks) {
+                    const uint64_t dbh = make_desc(b_hi + ks * 256u, 128, 1024), dbl = make_desc(b_lo + ks * 256u, 128, 1024);
+                    umma_f16_ts(d, a2 + 16u * ks, dbh, idesc2, !(first && ks == 0));
+                    umma_f16_ts(d, a2 + 16u * ks + 8u, dbh, idesc2, 1);   // w lo x statistics hi
+                    umma_f16_ts(d, a2 + 16u * ks, dbl, idesc2, 1);        // w hi x statistics lo
+                }
+                umma_commit(&bars->st_empty[s]);
+                if (last) umma_commit(&bars->d2_full[dbuf]);
+            };
+            issue_g1(0);
+            if (n_tiles > 1) issue_g1(1);
+            for (int i = 0; i < n_tiles; ++i) {
+                if (i + 2 < n_tiles) issue_g1(i + 2);
+                issue_g2(i);
+            }
+        }
+    } else if (warp >= KC_U_WARP0) {
+        // ------- (llh2, lg2(post) + wexp) per [pdf][frame] of the tile, transposed into shared memory -------
+        const int f = (warp - KC_U_WARP0) * 32 + lane;
+        const int k0 = g0 / a.C;
+        for (int i = 0; i < n_tiles; ++i) {
+            const int s = i % NS;
+            const int64_t t = f_begin + (int64_t)i * TILE + f;
+            const bool valid = t < f_end;
+            mbar_wait(&bars->u_empty[s], ((i / NS) & 1) ^ 1);
+            float2* us = s_u + (size_t)s * nk * TILE + f;
+            const float* pp = a.post + (size_t)(valid ? t : 0) * a.ld_post + k0;
+            const float* pl = a.llh2 + (size_t)(valid ? t : 0) * a.ld_llh + k0;
+            for (int j0 = 0; j0 < nk; j0 += 16) {
+                float4 p4[4], l4[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int k = j0 + 4 * q;
+                    const bool ok = valid && k < nk && k0 + k < a.Kp;
+                    p4[q] = ok ? __ldg(reinterpret_cast<const float4*>(pp + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    l4[q] = ok ? __ldg(reinterpret_cast<const float4*>(pl + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int k = j0 + 4 * q;
+                    if (k >= nk) continue;
+                    us[(k + 0) * TILE] = make_float2(l4[q].x, lg2(p4[q].x) + a.wexp);      // post = 0 -> -inf -> w = 0
+                    us[(k + 1) * TILE] = make_float2(l4[q].y, lg2(p4[q].y) + a.wexp);
+                    us[(k + 2) * TILE] = make_float2(l4[q].z, lg2(p4[q].z) + a.wexp);
+                    us[(k + 3) * TILE] = make_float2(l4[q].w, lg2(p4[q].w) + a.wexp);
+                }
+            }
+            mbar_arrive(&bars->u_full[s]);
+        }
+    } else {
+        // ------------------------------ epilogue warps -------------------------------
+        const int q = warp & 3, part = warp >> 2;            // TMEM lane quarter, quarter of the tile's frames
+        const int g = q * 32 + lane;                         // Gaussian (local) = TMEM lane
+        const int pl = g / a.C;                              // its pdf (local)
+        const float k1 = __ldg(a.k1 + g0 + g), k2 = __ldg(a.k2 + g0 + g);
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        float sums[MYCH][4], comp[MYCH][4];
+#pragma unroll
+        for (int m = 0; m < MYCH; ++m)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sums[m][i] = comp[m][i] = 0.f;
+        float wsum = 0.f, wcomp = 0.f;                       // sum_t w 2^wexp of this thread's frames (Kahan over tiles)
+        auto drain = [&](int grp) {
+            const int dbuf = grp & 1;
+            mbar_wait(&bars->d2_full[dbuf], (grp >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int m = 0; m < MYCH; ++m) {
+                const int ch = part + 4 * m;
+                if (ch < NCH) {
+                    float v[4];
+                    tmem_ld4(tmem_base + lane_addr + COL_D2 + (uint32_t)(dbuf * KP + ch * 4), v);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float y = v[i] - comp[m][i];
+                        const float t = sums[m][i] + y;
+                        comp[m][i] = (t - sums[m][i]) - y;
+                        sums[m][i] = t;
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&bars->d2_empty[dbuf]);
+        };
+
+        for (int i = 0; i < n_tiles; ++i) {
+            const int s = i % NS, b = i % NSB;
+            mbar_wait(&bars->s_full[b], (i / NSB) & 1);
+            mbar_wait(&bars->u_full[s], (i / NS) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + lane_addr + COL_S + (uint32_t)(b * TILE + part * 16);
+            float v[16];
+            tmem_ld16(taddr, v);
+            const float4* up = reinterpret_cast<const float4*>(s_u + (size_t)s * nk * TILE + pl * TILE + part * 16);
+            float tsum = 0.f;
+            uint32_t out[16];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const float4 ua = up[2 * h], ub = up[2 * h + 1];      // (llh2, lg2 post) of frames 4h .. 4h+3
+                const float l2[4] = {ua.x, ua.z, ub.x, ub.z}, lp[4] = {ua.y, ua.w, ub.y, ub.w};
+                float w[4], wh[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    // z = S k1 + k2 is bit for bit the value KA16 normalised: z - llh2 = log2 responsibility
+                    const float z = fmaf(v[4 * h + e], k1, k2);
+                    w[e] = ex2((z - l2[e]) + lp[e]);
+                    tsum += w[e];
+                    wh[e] = h_rn(w[e]);
+                }
+                out[2 * h] = pack_h2(wh[0], wh[1]);
+                out[2 * h + 1] = pack_h2(wh[2], wh[3]);
+                out[8 + 2 * h] = pack_h2(w[0] - wh[0], w[1] - wh[1]);
+                out[8 + 2 * h + 1] = pack_h2(w[2] - wh[2], w[3] - wh[3]);
+            }
+            tmem_st16(taddr, out);          // in place: [hi of 16 frames (8 columns) | lo (8 columns)]
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&bars->a2_full[b]);
+            mbar_arrive(&bars->u_empty[s]);
+            {
+                const float y = tsum - wcomp;
+                const float t = wsum + y;
+                wcomp = (t - wsum) - y;
+                wsum = t;
+            }
+            // drain the previous group one tile late: its last MMAs have certainly retired by then
+            if (i % DR == 1 && i > DR) drain(i / DR - 1);
+        }
+        if (n_tiles > 0) {
+            const int last_g = (n_tiles - 1) / DR;
+            if (last_g >= 1 && (n_tiles - 1) < last_g * DR + 1) drain(last_g - 1);
+            drain(last_g);
+            if (g0 + g < a.M) {
+                const int D = a.D, Q = 2 * D + 2;
+                double* row = a.acc + (size_t)(g0 + g) * Q;
+                const double unscale = exp2(-(double)a.wexp);
+#pragma unroll
+                for (int m = 0; m < MYCH; ++m) {
+                    const int ch = part + 4 * m;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int c = ch * 4 + i;
+                        if (ch < NCH && c < 2 * D) {
+                            const double val = ((double)sums[m][i] - (double)comp[m][i]) * unscale / (double)__ldg(a.alpha + c);
+                            if (val != 0.0) atomicAdd(row + c, val);
+                        }
+                    }
+                }
+                const double cnt = ((double)wsum - (double)wcomp) * unscale;
+                if (cnt != 0.0) {
+                    atomicAdd(row + 2 * D, -0.5 * cnt);
+                    atomicAdd(row + 2 * D + 1, 0.5 * cnt);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == KC_MMA_WARP) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+static size_t kc_smem(int KP, int C, int ns) {
+    return (size_t)ns * 4 * TILE * KP * 2 + (size_t)ns * (GM / C) * TILE * 8 + sizeof(KcBarriers) + 1024;
+}
+
+static int nb_of(int M, int C) {
+    // Gaussians per KA16 chunk: the largest divisor of M that is a multiple of 16 and of C, at most 256 (no padded
+    // columns in the last chunk); 128 with padding when M has none
+    int best = 0;
+    for (int nb = 16; nb <= 192; nb += 16)      // two weight stages + two statistics tiles fit in shared memory
+        if (M % nb == 0 && nb % C == 0) best = nb;
+    if (best >= 64) return best;
+    return 128;
+}
+
+}  // namespace mix16
+}  // namespace beer
+
+using namespace beer;
+
+extern "C" {
+
+int beer_mix16_supported(int M, int D, int C) {
+    if (M <= 0 || C <= 0 || M % C != 0) return 0;
+    if (!(D == 20 || D == 40)) return 0;
+    if (!(C == 4 || C == 8 || C == 16)) return 0;       // C | 128, u block of a tile <= 8 KB
+    if ((M / C) % 4 != 0) return 0;                      // float4 rows of posteriors / llhs
+    return 1;
+}
+
+int beer_mix16_geometry(int M, int D, int C, int64_t N, int64_t* sizes) {
+    if (!beer_mix16_supported(M, D, C) || N < 0 || !sizes) return BEER_ERR_UNSUPPORTED;
+    const int KP = mix16::kp_of(D), NB = mix16::nb_of(M, C);
+    const int n_chunks = (M + NB - 1) / NB;
+    int Mp = n_chunks * NB;
+    Mp = (Mp + mix16::GM - 1) / mix16::GM * mix16::GM;
+    const int64_t n_tiles = (N + mix16::TILE - 1) / mix16::TILE;
+    sizes[0] = n_tiles * 2 * mix16::TILE * KP;                 // halfs of img1 (and of img2)
+    sizes[1] = (int64_t)((Mp + NB - 1) / NB) * 2 * NB * KP;    // halfs of wimg
+    sizes[2] = (int64_t)Mp * KP;                               // words of wtm
+    sizes[3] = Mp;                                             // floats of k1 (and k2)
+    sizes[4] = NB;
+    sizes[5] = KP;
+    return BEER_OK;
+}
+
+int beer_mix16_feature_images(const float* X, int64_t N, int D, float* alpha, uint32_t* absmax_scratch, void* img1,
+                              void* img2, void* stream) {
+    if (!X || !alpha || !absmax_scratch || !img1 || !img2 || N < 0 || !(D == 20 || D == 40)) return BEER_ERR_ARG;
+    if (((uintptr_t)X & 15) != 0 || ((uintptr_t)img1 & 127) != 0 || ((uintptr_t)img2 & 127) != 0) return BEER_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    BEER_CUDA_TRY(cudaMemsetAsync(absmax_scratch, 0, (size_t)D * 4, st));
+    if (N == 0) return BEER_OK;
+    int blocks = (int)std::min<int64_t>((N + 24) / 25, kNumSMs * 8);
+    mix16::absmax_kernel<<<blocks, 256, 0, st>>>(X, N, D, absmax_scratch);
+    BEER_LAUNCH_CHECK();
+    mix16::scales_kernel<<<1, 128, 0, st>>>(absmax_scratch, D, alpha);
+    BEER_LAUNCH_CHECK();
+    const int64_t n_tiles = (N + mix16::TILE - 1) / mix16::TILE;
+    mix16::feat_image_kernel<<<(unsigned)n_tiles, 256, (size_t)mix16::TILE * (D + 1) * 4, st>>>(
+        X, N, D, alpha, (__half*)img1, (__half*)img2);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
+int beer_mix16_pack(const float* W, const float* bias, const float* alpha, int M, int D, int C, void* wimg,
+                    uint32_t* wtm, float* k1, float* k2, void* stream) {
+    if (!W || !bias || !alpha || !wimg || !wtm || !k1 || !k2) return BEER_ERR_ARG;
+    if (!beer_mix16_supported(M, D, C)) return BEER_ERR_UNSUPPORTED;
+    int64_t sz[6];
+    beer_mix16_geometry(M, D, C, 0, sz);
+    const int Mp = (int)sz[3], NB = (int)sz[4];
+    mix16::pack16_kernel<<<(Mp * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(W, bias, alpha, M, Mp, D, NB,
+                                                                                 (__half*)wimg, wtm, k1, k2);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
+int beer_mix16_frame_ref(const float* X, int64_t N, int D, const float* ref, float* frame_ref, void* stream) {
+    if (!X || !ref || !frame_ref || N < 0 || D % 4 != 0 || ((uintptr_t)X & 15) != 0) return BEER_ERR_ARG;
+    if (N == 0) return BEER_OK;
+    mix16::frame_ref_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(X, N, D, ref, frame_ref);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
+int beer_mix16_emission(const void* img1, int64_t N, int D, const void* wimg, const float* k1, const float* k2, int M,
+                        int C, float* llh2, int64_t ld, void* stream) {
+    if (!img1 || !wimg || !k1 || !k2 || !llh2 || N < 0) return BEER_ERR_ARG;
+    if (!beer_mix16_supported(M, D, C)) return BEER_ERR_UNSUPPORTED;
+    if (ld < M / C) return BEER_ERR_ARG;
+    if (N == 0) return BEER_OK;
+    int64_t sz[6];
+    beer_mix16_geometry(M, D, C, N, sz);
+    mix16::KaArgs a;
+    a.img1 = (const __half*)img1; a.N = N; a.wimg = (const __half*)wimg; a.k1 = k1; a.k2 = k2;
+    a.C = C; a.logC = 0;
+    while ((1 << a.logC) < C) ++a.logC;
+    a.Kp = M / C; a.NB = (int)sz[4];
+    a.n_chunks = (M + a.NB - 1) / a.NB;
+    a.llh2 = llh2; a.ld = ld;
+    const int KP = (int)sz[5];
+    const size_t smem = mix16::ka_smem(KP, a.NB);
+    if (smem > 227 * 1024) return BEER_ERR_UNSUPPORTED;
+    const int64_t n_tiles = (N + 127) / 128;
+    const int grid = (int)std::min<int64_t>(n_tiles, kNumSMs);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (KP == 80) {
+        static bool attr = false;
+        if (!attr) {
+            BEER_CUDA_TRY(cudaFuncSetAttribute(mix16::emission16_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr = true;
+        }
+        mix16::emission16_kernel<80><<<grid, mix16::KA_THREADS, smem, st>>>(a);
+    } else {
+        static bool attr = false;
+        if (!attr) {
+            BEER_CUDA_TRY(cudaFuncSetAttribute(mix16::emission16_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr = true;
+        }
+        mix16::emission16_kernel<48><<<grid, mix16::KA_THREADS, smem, st>>>(a);
+    }
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
+int beer_mix16_accumulate(const void* img1, const void* img2, int64_t N, int D, const uint32_t* wtm, const float* k1,
+                          const float* k2, const float* alpha, int M, int C, const float* pdf_post, int64_t ld_post,
+                          const float* llh2, int64_t ld_llh, float scale, double* acc_normal, void* stream) {
+    if (!img1 || !img2 || !wtm || !k1 || !k2 || !alpha || !pdf_post || !llh2 || !acc_normal || N < 0) return BEER_ERR_ARG;
+    if (!beer_mix16_supported(M, D, C)) return BEER_ERR_UNSUPPORTED;
+    if (ld_post < M / C || ld_llh < M / C || ld_post % 4 != 0 || ld_llh % 4 != 0) return BEER_ERR_ARG;
+    if (((uintptr_t)pdf_post & 15) != 0 || ((uintptr_t)llh2 & 15) != 0) return BEER_ERR_ARG;
+    if (N == 0) return BEER_OK;
+    mix16::KcArgs a;
+    a.img1 = (const __half*)img1; a.img2 = (const __half*)img2; a.N = N; a.wtm = wtm; a.k1 = k1; a.k2 = k2; a.alpha = alpha;
+    a.post = pdf_post; a.ld_post = ld_post; a.llh2 = llh2; a.ld_llh = ld_llh;
+    a.M = M; a.C = C; a.Kp = M / C; a.D = D; a.acc = acc_normal;
+    a.n_gtiles = (M + mix16::GM - 1) / mix16::GM;
+    // posteriors arrive multiplied by `scale`: keep w 2^wexp <= 2^14 (fp16 overflows at 2^16)
+    int e = 14;
+    if (scale > 1.f) e -= (int)ceilf(log2f(scale));
+    a.wexp = (float)e;
+    // CTAs = Gaussian tiles x frame ranges, consecutive CTAs = the Gaussian tiles of ONE range (they stream the same
+    // image tiles: L2 reuse); the largest grid of whole tile sets within 3 waves
+    int64_t ranges = std::max<int64_t>(1, (3 * kNumSMs) / a.n_gtiles);
+    const int64_t max_ranges = (N + mix16::TILE - 1) / mix16::TILE;
+    if (ranges > max_ranges) ranges = max_ranges;
+    int64_t fpc = (N + ranges - 1) / ranges;
+    fpc = (fpc + mix16::TILE - 1) / mix16::TILE * mix16::TILE;
+    ranges = (N + fpc - 1) / fpc;
+    a.frames_per_cta = fpc;
+    const int KP = mix16::kp_of(D);
+    a.ns = mix16::NS_MAX;
+    while (a.ns > 2 && mix16::kc_smem(KP, C, a.ns) > 227 * 1024) --a.ns;
+    const size_t smem = mix16::kc_smem(KP, C, a.ns);
+    if (smem > 227 * 1024) return BEER_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = (int)(ranges * a.n_gtiles);
+    if (KP == 80) {
+        static bool attr = false;
+        if (!attr) {
+            BEER_CUDA_TRY(cudaFuncSetAttribute(mix16::mixstats16_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr = true;
+        }
+        mix16::mixstats16_kernel<80><<<grid, mix16::KC_THREADS, smem, st>>>(a);
+    } else {
+        static bool attr = false;
+        if (!attr) {
+            BEER_CUDA_TRY(cudaFuncSetAttribute(mix16::mixstats16_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr = true;
+        }
+        mix16::mixstats16_kernel<48><<<grid, mix16::KC_THREADS, smem, st>>>(a);
+    }
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
+}  // extern "C"

@@ -223,6 +223,7 @@ struct FbArgs {
     const float* lr_w;  // aligned left-to-right loop weights (hmm_fb_lr_kernel)
     int lr_row;         // stride between the three weight arrays
     double* unit_counts;  // [K / SU] or NULL: sum_t xi_t(unit ends -> unit start) + gamma_0(start)
+    float llh_mul;        // log2(e) for llhs in nats, 1 for llhs already in log2 units (the kernels work in log2)
 };
 
 constexpr int FB_WARPS = 4;
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_kernel(FbArgs a) {
     float* ring_a = ring_p + PF * 32 * S;  // [PF][32*S]
     const int K = a.K, J = a.J;
     const bool vec = a.vec != 0, ident = a.map_identity != 0;
-    const float p_scale = a.scale * kLog2e;
+    const float p_scale = a.scale * a.llh_mul;
     const int gwarp = blockIdx.x * FB_WARPS + warp, nwarps = gridDim.x * FB_WARPS;
 
     for (int u = gwarp; u < a.n_utts; u += nwarps) {
@@ -634,7 +635,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_fast_kernel(FbArgs a) {
     float* ring_p = buf + ROW;                     // [PF][32 * S]
     float* ring_a = ring_p + PF * ROW;             // [PF][32 * S]
     const int K = a.K, J = a.J;
-    const float p_scale = a.scale * kLog2e;
+    const float p_scale = a.scale * a.llh_mul;
     const int gwarp = blockIdx.x * FB_WARPS + warp, nwarps = gridDim.x * FB_WARPS;
     const bool own = lane * S < K;                 // this lane holds real states (K % 4 == 0)
     // lanes past K never receive async copies: keep their ring slots finite
@@ -906,7 +907,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_lr_kernel(FbArgs a) {
     float* ring_p = smem + (size_t)warp * (2 * PF * ROW);   // [PF][32 * S]
     float* ring_a = ring_p + PF * ROW;                      // [PF][32 * S]
     const int K = a.K;
-    const float p_scale = a.scale * kLog2e;
+    const float p_scale = a.scale * a.llh_mul;
     const int gwarp = blockIdx.x * FB_WARPS + warp, nwarps = gridDim.x * FB_WARPS;
     const bool own = lane * S < K;
     for (int i = lane; i < 2 * PF * ROW; i += 32) ring_p[i] = 0.f;   // lanes past K stay finite
@@ -1244,7 +1245,7 @@ __global__ void __launch_bounds__(W * 32) hmm_fb_lrb_kernel(FbArgs a) {
     float* ring_a = ring_p + PF * ROW;
     float* xch = smem + (size_t)W * (2 * PF * ROW);     // [2][W][4] exchange slots
     const int K = a.K;
-    const float p_scale = a.scale * kLog2e;
+    const float p_scale = a.scale * a.llh_mul;
     const int gl = warp * 32 + lane;            // unit owned by this lane
     const int k0 = gl * S;                      // its first state
     const bool own = k0 < K;
@@ -2109,6 +2110,15 @@ int beer_hmm_forward_backward_units(const beer_graph_plan* plan, const float* pd
                                     float* state_post, float* pdf_post, int64_t ld_post, float* frame_exp_llh,
                                     double* utt_exp_llh, double* utt_logz, double* unit_counts, void* workspace,
                                     void* stream) {
+    return beer_hmm_forward_backward_ex(plan, pdf_llh, ld_pdf, frame_ref, utt_off, n_utts, scale, state_post, pdf_post,
+                                        ld_post, frame_exp_llh, utt_exp_llh, utt_logz, unit_counts, 0, workspace, stream);
+}
+
+int beer_hmm_forward_backward_ex(const beer_graph_plan* plan, const float* pdf_llh, int64_t ld_pdf,
+                                 const float* frame_ref, const int64_t* utt_off, int n_utts, float scale,
+                                 float* state_post, float* pdf_post, int64_t ld_post, float* frame_exp_llh,
+                                 double* utt_exp_llh, double* utt_logz, double* unit_counts, int llh_log2,
+                                 void* workspace, void* stream) {
     if (!plan || !pdf_llh || !utt_off || !utt_exp_llh || !workspace || n_utts < 0) return BEER_ERR_ARG;
     if (ld_pdf < plan->Kp || (pdf_post && ld_post < plan->Kp)) return BEER_ERR_ARG;
     if (n_utts == 0) return BEER_OK;
@@ -2127,14 +2137,16 @@ int beer_hmm_forward_backward_units(const beer_graph_plan* plan, const float* pd
     a.lr_w = plan->lr_w;
     a.lr_row = 32 * plan->lr_su * plan->lr_u;
     a.unit_counts = unit_counts;
+    a.llh_mul = llh_log2 ? 1.f : kLog2e;
     if (unit_counts != nullptr && beer_hmm_unit_count_size(plan) <= 0) return BEER_ERR_UNSUPPORTED;
     const bool post_ok = (pdf_post == nullptr || (ld_post % 4 == 0 && ((uintptr_t)pdf_post & 15) == 0)) &&
                          (state_post == nullptr || (plan->K % 4 == 0 && ((uintptr_t)state_post & 15) == 0));
     const char* force = getenv("BEER_B200_SCAN");   // debug: "generic" | "fast" | unset (best available)
     if (unit_counts != nullptr) force = nullptr;    // unit counts live in the left-to-right loop kernel
     const bool lr_vec = (plan->lr_su * plan->lr_u) % 4 == 0;   // the kernel moves whole float4 rows
-    if (plan->lr_su && plan->map_identity && (force == nullptr || force[0] == 'l') &&
-        (!lr_vec || (a.vec && post_ok))) {
+    // (its float4 rows need 16-byte aligned llh / posterior rows; a.vec is about the generic kernels' lane layout)
+    const bool lr_rows_ok = ld_pdf % 4 == 0 && ((uintptr_t)pdf_llh & 15) == 0 && post_ok;
+    if (plan->lr_su && plan->map_identity && (force == nullptr || force[0] == 'l') && (!lr_vec || lr_rows_ok)) {
         const int u = plan->lr_u;
         if (u == 8 && unit_counts == nullptr) {
             if (plan->lr_su == 4) return launch_fb_lrb<4, 8>(a, n_utts, st);

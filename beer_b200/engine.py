@@ -16,6 +16,8 @@ but as a handful of kernel launches over all utterances at once:
 
 Utterances shard over ranks (one process per GPU); the only exchange is the all-reduce.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -85,15 +87,18 @@ class EmissionParams:
         counts = np.diff(self.comp_off_host)
         self.uniform_C = int(counts[0]) if len(counts) and np.all(counts == counts[0]) else 0
         self.use_tc = bool(self.uniform_C) and ops.emission_tc_supported(self.M, self.D, self.uniform_C)
+        # mixtures of 4 / 8 / 16 Gaussians per pdf: the fp16-split kernels that keep the per-Gaussian llhs on chip
+        self.use16 = (self.has_mixtures and bool(self.uniform_C) and os.environ.get('BEER_B200_NO_MIX16') is None
+                      and ops.mix16_supported(self.M, self.D, self.uniform_C))
         self._image = None
 
-    def refresh(self):
+    def refresh(self, pack_tc=True):
         """(W, bias, ref) of the current posteriors."""
         for g in self.weight_groups:
             j0 = int(self.comp_off_host[g.pdf_start])
             self.logw[j0:j0 + g.n_pdfs * g.n_comp] = ops.dirichlet_expected_logw(g.post).reshape(-1)
         W, bias, ref = ops.emission_prepare(*self.post, logw=self.logw)
-        if self.use_tc:
+        if self.use_tc and pack_tc:
             self._image = ops.emission_tc_pack(W, bias, self.uniform_C, out=self._image)
         return W, bias, ref
 
@@ -269,7 +274,20 @@ class VBEngine:
         self.pdf_llh = torch.empty(nmax, Kp, device=self.dev, dtype=f32)
         self._nonident = self.chains or not (plan.info['map_identity'] and plan.n_states == Kp)
         self.pdf_post = (torch.zeros if self._nonident else torch.empty)(nmax, Kp, device=self.dev, dtype=f32)
-        self.comp_llh = torch.empty(nmax, M, device=self.dev, dtype=f32) if emission.has_mixtures else None
+        # mixtures through the fp16-split kernels (forward-backward over one graph plan): no per-Gaussian llhs at all,
+        # `pdf_llh` holds log2 values; the feature images of resident chunks are built once, here
+        self.mix16 = None
+        if emission.use16 and not self.viterbi and not self.chains:
+            self.mix16 = ops.Mix16(M, D, emission.uniform_C, self.dev)
+            self._images = [None] * len(self._chunks)
+            if not self.host_mode:
+                for ci, (u0, u1, f0, nf, rel) in enumerate(self._chunks):
+                    if nf > 0:
+                        self._images[ci] = self.mix16.build_images(utts.X[f0:f0 + nf])
+            self._stage_images = None
+        self.tensor_kind = 'f16' if self.mix16 is not None else 'tf32'
+        self.comp_llh = (torch.empty(nmax, M, device=self.dev, dtype=f32)
+                         if emission.has_mixtures and self.mix16 is None else None)
         ws_bytes = plan.workspace_bytes(nmax)
         if self.viterbi:
             ws_bytes = max(ws_bytes, nmax * plan.n_states * 2 + 4)      # uint16 back-pointers
@@ -314,13 +332,14 @@ class VBEngine:
         em, plan = self.em, self.plan
         self.flat.zero_()
         self.kl.zero_()
-        W, bias, ref = em.refresh()
+        W, bias, ref = em.refresh(pack_tc=self.mix16 is None)
         em.kl(out=self.kl)
         if self.units is not None:
             ops.dirichlet_kl(self.units.prior, self.units.post, out=self.kl)
         self.gpu_launches += 2 + 1 + 2 * len(em.weight_groups) + int(em.use_tc)
         nonident = self._nonident
         chunks = [c for c in self._chunks if c[3] > 0]
+        chunk_ids = [i for i, c in enumerate(self._chunks) if c[3] > 0]
         if self.host_mode and chunks:
             self._issue_copy(chunks[0], 0)
         for ci, (u0, u1, f0, nf, rel) in enumerate(chunks):
@@ -335,8 +354,22 @@ class VBEngine:
             pdf_llh = self.pdf_llh[:nf]
             pdf_post = self.pdf_post[:nf]
             comp = self.comp_llh[:nf] if self.comp_llh is not None else None
+            images = None
+            if self.mix16 is not None:
+                if self.host_mode:       # streamed features: the images of the chunk are rebuilt behind its copy
+                    with self._stage('KI_feature_images'):
+                        images = self._stage_images = self.mix16.build_images(X, out=self._stage_images)
+                    self.gpu_launches += 4
+                else:
+                    images = self._images[chunk_ids[ci]]
             with self._stage('KA_emission_llh'):
-                _, _, fref = em.llh(X, W, bias, ref, pdf_llh, comp, self.frame_ref[:nf])
+                if images is not None:
+                    self.mix16.pack(W, bias, images['alpha'])
+                    fref = self.mix16.frame_ref(X, ref, out=self.frame_ref[:nf])
+                    self.mix16.emission(images, out=pdf_llh)
+                    self.gpu_launches += 2
+                else:
+                    _, _, fref = em.llh(X, W, bias, ref, pdf_llh, comp, self.frame_ref[:nf])
             if nonident:
                 pdf_post.zero_()
             with self._stage('KB_forward_backward'):
@@ -358,9 +391,11 @@ class VBEngine:
                 else:
                     ops.hmm_forward_backward(plan, pdf_llh, fref, rel, scale=self.scale, workspace=self.ws,
                                              out_pdf_post=pdf_post, out_utt_exp_llh=self.utt_ell[u0:u1],
-                                             unit_counts=self.unit_counts)
+                                             unit_counts=self.unit_counts, llh_log2=images is not None)
             with self._stage('KC_accumulate'):
-                if self.viterbi and self._path_kc:
+                if images is not None:
+                    self.mix16.accumulate(images, pdf_post, pdf_llh, self.acc, scale=self.scale)
+                elif self.viterbi and self._path_kc:
                     ops.accumulate_stats_path(X, self.acc, self._pdf_ids[:nf], scale=self.scale)
                 else:
                     ops.accumulate_stats(X, self.acc, pdf_post=pdf_post,

@@ -177,7 +177,7 @@ class GraphPlan:
 
 def hmm_forward_backward(plan, pdf_llh, frame_ref, utt_off, scale=1.0, want_state_post=False,
                          want_pdf_post=True, want_frame_llh=False, want_logz=False, workspace=None,
-                         out_pdf_post=None, out_utt_exp_llh=None, unit_counts=None):
+                         out_pdf_post=None, out_utt_exp_llh=None, unit_counts=None, llh_log2=False):
     """Forward-backward for a ragged batch.  -> dict(state_post, pdf_post, frame_exp_llh,
     utt_exp_llh (fp64), utt_logz (fp64)).  `out_pdf_post` must be zero-filled by the caller
     when the graph's pdf map is not the identity (the kernel then scatter-adds)."""
@@ -199,12 +199,12 @@ def hmm_forward_backward(plan, pdf_llh, frame_ref, utt_off, scale=1.0, want_stat
     frame = torch.empty(N, device=dev, dtype=f32) if want_frame_llh else None
     utt_ell = out_utt_exp_llh if out_utt_exp_llh is not None else torch.empty(n_utts, device=dev, dtype=f64)
     utt_logz = torch.empty(n_utts, device=dev, dtype=f64) if want_logz else None
-    _lib.check(lib.beer_hmm_forward_backward_units(
+    _lib.check(lib.beer_hmm_forward_backward_ex(
         plan._h, _p(pdf_llh, f32), pdf_llh.stride(0), _p(frame_ref, f32, True), _p(utt_off, i64), n_utts,
         float(scale), _p(state_post, f32, True), _p(pdf_post, f32, True),
         pdf_post.stride(0) if pdf_post is not None else 0, _p(frame, f32, True),
-        _p(utt_ell, f64), _p(utt_logz, f64, True), _p(unit_counts, f64, True), _p(workspace), _stream()),
-        'beer_hmm_forward_backward')
+        _p(utt_ell, f64), _p(utt_logz, f64, True), _p(unit_counts, f64, True), int(bool(llh_log2)), _p(workspace),
+        _stream()), 'beer_hmm_forward_backward')
     return dict(state_post=state_post, pdf_post=pdf_post, frame_exp_llh=frame, utt_exp_llh=utt_ell,
                 utt_logz=utt_logz, workspace=workspace)
 
@@ -550,6 +550,83 @@ def add_deltas(fea, wlen):
     out = torch.empty_like(fea)
     _lib.check(lib.beer_add_deltas(_p(fea, f32), T, F, int(wlen), _p(out), _stream()), 'beer_add_deltas')
     return out
+
+
+# ---------------------------------------------------------------------------
+# mixture path without per-Gaussian llhs in HBM (csrc/mix16.cu)
+# ---------------------------------------------------------------------------
+
+def mix16_supported(M, D, C):
+    return bool(_lib.load().beer_mix16_supported(int(M), int(D), int(C)))
+
+
+class Mix16:
+    """Buffers and calls of the fp16-split mixture kernels for M Gaussians in pdfs of C, dimension D."""
+
+    def __init__(self, M, D, C, device):
+        lib = require_cuda()
+        if not lib.beer_mix16_supported(int(M), int(D), int(C)):
+            raise _lib.BeerB200Error('no mix16 kernels for this shape')
+        self.M, self.D, self.C, self.Kp, self.device = int(M), int(D), int(C), int(M) // int(C), device
+        sz = self._geometry(0)
+        self.NB, self.KP = int(sz[4]), int(sz[5])
+        self.wimg = torch.zeros(int(sz[1]), device=device, dtype=torch.float16)
+        self.wtm = torch.zeros(int(sz[2]), device=device, dtype=i32)
+        self.k1 = torch.zeros(int(sz[3]), device=device, dtype=f32)
+        self.k2 = torch.zeros(int(sz[3]), device=device, dtype=f32)
+        self._absmax = torch.zeros(D, device=device, dtype=i32)
+
+    def _geometry(self, N):
+        sz = np.zeros(6, dtype=np.int64)
+        _lib.check(_lib.load().beer_mix16_geometry(self.M, self.D, self.C, int(N), sz.ctypes.data), 'beer_mix16_geometry')
+        return sz
+
+    def image_halfs(self, N):
+        return int(self._geometry(N)[0])
+
+    def build_images(self, X, out=None):
+        """Feature images of a run of frames: dict(alpha [2D], img1, img2, N).  `out` = a dict from an earlier call
+        with at least as many frames (its buffers are reused)."""
+        lib = _lib.load()
+        N = X.shape[0]
+        n = self.image_halfs(N)
+        if out is None or out['img1'].numel() < n:
+            out = dict(alpha=torch.empty(2 * self.D, device=X.device, dtype=f32),
+                       img1=torch.empty(n, device=X.device, dtype=torch.float16),
+                       img2=torch.empty(n, device=X.device, dtype=torch.float16))
+        _lib.check(lib.beer_mix16_feature_images(_p(X, f32), N, self.D, _p(out['alpha']), _p(self._absmax),
+                                                 _p(out['img1']), _p(out['img2']), _stream()), 'beer_mix16_feature_images')
+        out['N'] = N
+        return out
+
+    def pack(self, W, bias, alpha):
+        _lib.check(_lib.load().beer_mix16_pack(_p(W, f32), _p(bias, f32), _p(alpha, f32), self.M, self.D, self.C,
+                                               _p(self.wimg), _p(self.wtm), _p(self.k1), _p(self.k2), _stream()),
+                   'beer_mix16_pack')
+
+    def frame_ref(self, X, ref, out=None):
+        N = X.shape[0]
+        out = out if out is not None else torch.empty(N, device=X.device, dtype=f32)
+        _lib.check(_lib.load().beer_mix16_frame_ref(_p(X, f32), N, self.D, _p(ref, f32), _p(out), _stream()),
+                   'beer_mix16_frame_ref')
+        return out
+
+    def emission(self, images, out=None):
+        """llh2 [N, Kp]: log2-domain pdf llhs in offset form (add frame_ref / ln 2 for absolute values)."""
+        N = images['N']
+        llh2 = out if out is not None else torch.empty(N, self.Kp, device=self.device, dtype=f32)
+        _lib.check(_lib.load().beer_mix16_emission(_p(images['img1']), N, self.D, _p(self.wimg), _p(self.k1), _p(self.k2),
+                                                   self.M, self.C, _p(llh2, f32), llh2.stride(0), _stream()),
+                   'beer_mix16_emission')
+        return llh2
+
+    def accumulate(self, images, pdf_post, llh2, acc_normal, scale=1.0):
+        N = images['N']
+        _lib.check(_lib.load().beer_mix16_accumulate(
+            _p(images['img1']), _p(images['img2']), N, self.D, _p(self.wtm), _p(self.k1), _p(self.k2),
+            _p(images['alpha']), self.M, self.C, _p(pdf_post, f32), pdf_post.stride(0), _p(llh2, f32), llh2.stride(0),
+            float(scale), _p(acc_normal, f64), _stream()), 'beer_mix16_accumulate')
+        return acc_normal
 
 
 # ---------------------------------------------------------------------------

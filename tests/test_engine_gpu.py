@@ -196,14 +196,17 @@ def test_viterbi_training_matches_oracle(C, chunk, scale):
         np.testing.assert_allclose(g, w, rtol=2e-4, atol=2e-4)
 
 
-@pytest.mark.parametrize('chunk', [None, 170])
-def test_vb_iterations_streamed_mixture_kernels(chunk):
-    """M = 160 Gaussians (20 pdfs x 8) at D = 20: the emission kernel streams its weight image in chunks and stores the
+@pytest.mark.parametrize('chunk,mix16', [(None, False), (170, False), (None, True), (170, True)])
+def test_vb_iterations_streamed_mixture_kernels(chunk, mix16, monkeypatch):
+    """(mix16 = False: the 3xTF32 kernels that materialise the per-Gaussian llhs; True: the fp16-split kernels that keep
+    them on chip, csrc/mix16.cu.)  M = 160 Gaussians (20 pdfs x 8) at D = 20: the emission kernel streams its weight image in chunks and stores the
     per-Gaussian llhs with TMA tensor stores, the statistics kernel runs its bulk-staged mixture variant; three VB
     iterations (ragged utterances, chunk boundaries inside frame tiles) against the oracle."""
     from beer_b200 import ops, synthetic
     from beer_b200.engine import EmissionParams, Utterances, VBEngine, WeightGroup
     dev = torch.device('cuda', 0)
+    if not mix16:
+        monkeypatch.setenv('BEER_B200_NO_MIX16', '1')
     P, S, D, C = 5, 4, 20, 8
     K, M = P * S, P * S * C
     lens = [150, 41, 97, 129, 64]
@@ -219,10 +222,11 @@ def test_vb_iterations_streamed_mixture_kernels(chunk):
     conc = torch.full((K, C), 1.0 / C, device=dev)
     groups = (WeightGroup(0, K, C, conc.clone(), conc.clone()),)
     em = EmissionParams(prior, post, comp_off=np.arange(K + 1) * C, weight_groups=groups)
-    assert em.use_tc and ops.accumulate_tc_supported(M, D)
+    assert em.use_tc and ops.accumulate_tc_supported(M, D) and em.use16 == mix16
     dprior, dpost = conc.double().cpu().numpy(), conc.double().cpu().numpy()
     N = sum(lens)
     eng = VBEngine(em, plan, Utterances(X, lens), datasize=float(N), chunk_frames=chunk, distributed=False)
+    assert (eng.mix16 is not None) == mix16
     ng_prior, ng_post = _host(prior), _host(post)
     og = (graph.init_log_probs.double().numpy(), graph.final_log_probs.double().numpy(),
           graph.trans_log_probs.double().numpy(), graph.pdf_id_mapping)
@@ -238,8 +242,8 @@ def test_vb_iterations_streamed_mixture_kernels(chunk):
     np.testing.assert_allclose(groups[0].post.double().cpu().numpy(), dpost, rtol=2e-4, atol=1e-5)
 
 
-@pytest.mark.parametrize('use_graph', [False, True])
-def test_vb_iterations_cfg3_shape(use_graph):
+@pytest.mark.parametrize('use_graph,mix16', [(False, True), (True, True), (False, False)])
+def test_vb_iterations_cfg3_shape(use_graph, mix16, monkeypatch):
     """The exact shape of BASELINE configs[2] (the north-star target): 250 units x 4 states = 1000 states, 8
     Gaussians per state (M = 8000: 63 Gaussian tiles of the statistics kernel, 125 weight chunks of the emission
     kernel), D = 40, the eight-warps-per-utterance left-to-right scan; three short ragged utterances, two VB
@@ -247,6 +251,8 @@ def test_vb_iterations_cfg3_shape(use_graph):
     from beer_b200 import ops, synthetic
     from beer_b200.engine import EmissionParams, Utterances, VBEngine, WeightGroup
     dev = torch.device('cuda', 0)
+    if not mix16:
+        monkeypatch.setenv('BEER_B200_NO_MIX16', '1')
     P, S, D, C = 250, 4, 40, 8
     K, M = P * S, P * S * C
     lens = [70, 33, 129]

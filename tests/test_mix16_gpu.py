@@ -1,0 +1,111 @@
+"""GPU parity tests of the mixture path that keeps the per-Gaussian llhs on chip (csrc/mix16.cu: fp16 hi / lo feature
+images, KA16 emission kernel, KCF statistics kernel with the responsibilities recomputed in tensor memory) against
+fp64 restatements of MixtureSet.expected_log_likelihood / accumulate (beer/models/mixtureset.py:85-112,
+normalset.py:117-123)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+LN2 = float(np.log(2.0))
+
+
+def _model(M, D, C, seed, spread=1.0):
+    g = torch.Generator().manual_seed(seed)
+    mean = spread * torch.randn(M, D, generator=g)
+    scale = torch.rand(M, generator=g) * 3 + 0.5
+    shape = torch.rand(M, generator=g) * 4 + 1.0
+    rates = torch.rand(M, D, generator=g) * 2 + 0.3
+    conc = torch.rand(M // C, C, generator=g) * 3 + 0.2
+    return [t.to(DEV).contiguous() for t in (mean, scale, shape, rates)], conc.to(DEV)
+
+
+def _reference(X, post, conc, C):
+    """fp64: comp llh [N, M] (with E[ln pi]), pdf llh [N, Kp]."""
+    from beer_b200 import ops
+    mean, scale, shape, rates = [t.double() for t in post]
+    D = mean.shape[1]
+    a, k = shape[:, None], scale[:, None]
+    lam = a / rates
+    ets = torch.cat([lam * mean, lam, D / k + (lam * mean ** 2).sum(1, keepdim=True),
+                     (torch.digamma(a) - rates.log()).sum(1, keepdim=True)], 1)
+    Xd = X.double()
+    stats = torch.cat([Xd, -0.5 * Xd ** 2, -0.5 * torch.ones(len(Xd), 1, device=DEV, dtype=torch.float64),
+                       0.5 * torch.ones(len(Xd), 1, device=DEV, dtype=torch.float64)], 1)
+    comp = stats @ ets.T - 0.5 * D * np.log(2 * np.pi)
+    logw = torch.digamma(conc.double()) - torch.digamma(conc.double().sum(1, keepdim=True))
+    comp = comp + logw.reshape(1, -1)
+    pdf = torch.logsumexp(comp.reshape(len(Xd), -1, C), dim=2)
+    return stats, comp, pdf
+
+
+@pytest.mark.parametrize('M,D,C,N', [(8000, 40, 8, 700), (256, 40, 8, 1000), (160, 20, 8, 333), (96, 40, 4, 130),
+                                     (320, 40, 16, 64)])
+def test_emission_and_statistics_match_fp64(M, D, C, N):
+    from beer_b200 import ops
+    Kp = M // C
+    post, conc = _model(M, D, C, seed=M + N)
+    g = torch.Generator().manual_seed(N)
+    X = (2.0 * torch.randn(N, D, generator=g)).to(DEV)
+    X[:, 0] *= 10.0                     # dimensions of different ranges: the per-dimension scales matter
+    X[:, 1] *= 0.01
+    logw = ops.dirichlet_expected_logw(conc).reshape(-1).contiguous()
+    W, bias, ref = ops.emission_prepare(*post, logw=logw)
+    mx = ops.Mix16(M, D, C, DEV)
+    images = mx.build_images(X)
+    # the images decode to the scaled statistics
+    KP = mx.KP
+    alpha = images['alpha'].double().cpu().numpy()
+    img1 = images['img1'].double().cpu().numpy().reshape(-1, 2, 8, KP // 8, 8, 8)     # tile, hi/lo, f8, k8, f, k
+    dec = (img1[:, 0] + img1[:, 1]).transpose(0, 1, 3, 2, 4).reshape(-1, KP)[:N, :2 * D] / alpha
+    Xd = X.double().cpu().numpy()
+    want = np.concatenate([Xd, -0.5 * Xd ** 2], 1)
+    assert np.abs(dec - want).max() <= 2.0 ** -20 * np.abs(want).max(axis=0).max()
+    img2 = images['img2'].double().cpu().numpy().reshape(-1, 2, KP // 8, 8, 8, 8)     # tile, hi/lo, k8, f8, k, f
+    dec2 = (img2[:, 0] + img2[:, 1]).transpose(0, 2, 4, 1, 3).reshape(-1, KP)[:N, :2 * D] / alpha
+    np.testing.assert_array_equal(dec2, dec)
+
+    mx.pack(W, bias, images['alpha'])
+    llh2 = mx.emission(images)
+    fref = mx.frame_ref(X, ref)
+    stats, comp, pdf = _reference(X, post, conc, C)
+    got = llh2.double() * LN2 + fref.double()[:, None]
+    err = (got - pdf).abs().max().item()
+    assert err <= 3e-6 * pdf.abs().max().item() + 1e-4, (err, pdf.abs().max().item())
+
+    # statistics with random pdf posteriors (some exactly zero), responsibilities recomputed on chip
+    pp = torch.rand(N, Kp, generator=g).to(DEV)
+    pp = torch.where(pp < 0.6, torch.zeros_like(pp), pp).contiguous()
+    acc = torch.zeros(M, 2 * D + 2, device=DEV, dtype=torch.float64)
+    mx.accumulate(images, pp, llh2, acc)
+    resp = (comp.reshape(N, Kp, C) - pdf[:, :, None]).exp()
+    w = (resp * pp.double()[:, :, None]).reshape(N, M)
+    want_acc = w.T @ stats
+    tol = 3e-5 * want_acc.abs().max().item()
+    assert (acc - want_acc).abs().max().item() <= tol, ((acc - want_acc).abs().max().item(), tol)
+    # the z of the statistics kernel is the z the emission kernel normalised: the responsibilities of a pdf sum to one
+    cnt = 2.0 * acc[:, 2 * D + 1].reshape(Kp, C).sum(1)
+    want_cnt = pp.double().sum(0)
+    assert (cnt - want_cnt).abs().max().item() <= 5e-6 * want_cnt.abs().max().item() + 1e-9
+    # accumulation semantics: a second call adds
+    mx.accumulate(images, pp, llh2, acc)
+    assert (acc - 2 * want_acc).abs().max().item() <= 2 * tol
+
+
+def test_forward_backward_accepts_log2_llhs():
+    """beer_hmm_forward_backward_ex(llh_log2=1) on llh / ln 2 == the call on llh (same posteriors, same ELBO terms)."""
+    from beer_b200 import ops, synthetic
+    P, S, T = 250, 4, 90
+    K = P * S
+    graph, _, _ = synthetic.phone_loop_graph(P, S)
+    plan = ops.GraphPlan(graph.init_log_probs.numpy(), graph.final_log_probs.numpy(),
+                         graph.trans_log_probs.numpy(), graph.pdf_id_mapping, n_pdfs=K)
+    g = torch.Generator().manual_seed(1)
+    llh = (5.0 * torch.randn(2 * T, K, generator=g)).to(DEV)
+    fref = torch.randn(2 * T, generator=g).to(DEV)
+    off = torch.tensor([0, T, 2 * T], device=DEV)
+    a = ops.hmm_forward_backward(plan, llh, fref, off, want_frame_llh=True)
+    b = ops.hmm_forward_backward(plan, (llh / LN2).contiguous(), fref, off, want_frame_llh=True, llh_log2=True)
+    assert (a['pdf_post'] - b['pdf_post']).abs().max().item() <= 2e-5
+    np.testing.assert_allclose(a['utt_exp_llh'].cpu().numpy(), b['utt_exp_llh'].cpu().numpy(), rtol=2e-6)
