@@ -20,6 +20,7 @@
 // so the z of KCF is the z KA16 normalised: the responsibilities sum to one without a second normalisation.
 //
 // Reference semantics: beer/dists/normalgamma.py:55-59, beer/models/mixtureset.py:85-112, normalset.py:121-123.
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -195,12 +196,12 @@ __global__ void __launch_bounds__(256) frame_ref_kernel(const float* __restrict_
 // weight pack: one warp per Gaussian (rows M..Mp-1 are padding: zero weights, z = -inf)
 //   wimg   [n_chunks][hi | lo][NB x KP] halfs, core-matrix layout    (B operand of KA16)
 //   wtm    [Mp][KP/2 hi words | KP/2 lo words]                       (A operand of KCF, copied to tensor memory)
-//   k1     [Mp] = log2(e) / beta_j,  k2 [Mp] = bias_j log2(e)         (z = S k1 + k2, log2 domain)
+//   k12    [Mp] = (log2(e) / beta_j, bias_j log2(e))                  (z = S k1 + k2, log2 domain)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) pack16_kernel(const float* __restrict__ W, const float* __restrict__ bias,
                                                      const float* __restrict__ alpha, int M, int Mp, int D, int NB,
                                                      __half* __restrict__ wimg, uint32_t* __restrict__ wtm,
-                                                     float* __restrict__ k1, float* __restrict__ k2) {
+                                                     float2* __restrict__ k12) {
     const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (j >= Mp) return;
     const int KP = kp_of(D), NPAIR = KP >> 1;
@@ -239,25 +240,21 @@ __global__ void __launch_bounds__(128) pack16_kernel(const float* __restrict__ W
         tm[p] = hi;
         tm[NPAIR + p] = lo;
     }
-    if (lane == 0) {
-        k1[j] = (j < M) ? kLog2e * ldexpf(1.f, -be) : 0.f;
-        k2[j] = (j < M) ? bias[j] * kLog2e : kNegInf;
-    }
+    if (lane == 0) k12[j] = (j < M) ? make_float2(kLog2e * ldexpf(1.f, -be), bias[j] * kLog2e) : make_float2(0.f, kNegInf);
 }
 
 // ---------------------------------------------------------------------------------------------
 // KA16: llh2 [N, Kp] = log2 sum_c 2^(z_tkc)
 // ---------------------------------------------------------------------------------------------
-constexpr int KA_WORKERS = 256, KA_MMA_WARP = KA_WORKERS / 32, KA_LOAD_WARP = KA_MMA_WARP + 1, KA_THREADS = KA_WORKERS + 64;
+constexpr int KA_WORKERS = 512, KA_MMA_WARP = KA_WORKERS / 32, KA_LOAD_WARP = KA_MMA_WARP + 1, KA_THREADS = KA_WORKERS + 64;
 constexpr int K12_RING = 4;
 
 struct KaArgs {
     const __half* img1;
     int64_t N;
     const __half* wimg;
-    const float* k1;
-    const float* k2;
-    int C, logC, Kp, NB, n_chunks;
+    const float2* k12;       // [Mp] (k1, k2)
+    int Kp, NB, n_chunks;
     float* llh2;
     int64_t ld;
 };
@@ -270,17 +267,19 @@ struct KaBarriers {
     uint32_t pad[3];
 };
 
-template <int KP>
+template <int KP, int C>
 __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a) {
     constexpr int FR = 128, KSTEPS = KP / 16;
     constexpr uint32_t LBO = 128, SBO = KP * 16;
     constexpr int A_HALF = FR * KP;                     // halfs of one A image (hi or lo) of a 128-frame tile
+    constexpr int UNIT = C < 8 ? 8 : C;                 // columns per epilogue unit (whole pdfs, one tcgen05.ld)
+    constexpr int PPU = UNIT / C;                       // pdfs per unit
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __half* As = reinterpret_cast<__half*>(smem_raw);                        // [2][hi | lo]
     __half* Bs = As + 2 * 2 * A_HALF;                                        // [2][hi | lo] of NB x KP
     const int b_stage = 2 * a.NB * KP;
-    float* s_k12 = reinterpret_cast<float*>(Bs + 2 * b_stage);               // [K12_RING][k1 NB | k2 NB]
-    KaBarriers* bars = reinterpret_cast<KaBarriers*>(s_k12 + K12_RING * 2 * a.NB);
+    float2* s_k12 = reinterpret_cast<float2*>(Bs + 2 * b_stage);             // [K12_RING][NB] (k1, k2)
+    KaBarriers* bars = reinterpret_cast<KaBarriers*>(s_k12 + K12_RING * a.NB);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t n_tiles = (a.N + FR - 1) / FR, n_tiles64 = (a.N + TILE - 1) / TILE;
@@ -305,7 +304,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a) {
     if (warp == KA_LOAD_WARP) {
         if (lane == 0) {
             uint32_t it = 0, tile_it = 0;
-            const uint32_t half_bytes = TILE * KP * 2, b_bytes = (uint32_t)b_stage * 2u, k_bytes = (uint32_t)a.NB * 4u;
+            const uint32_t half_bytes = TILE * KP * 2, b_bytes = (uint32_t)b_stage * 2u, k_bytes = (uint32_t)a.NB * 8u;
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
                 const int ab = tile_it & 1;
                 mbar_wait(&bars->a_empty[ab], ((tile_it >> 1) & 1) ^ 1);
@@ -324,11 +323,9 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a) {
                 for (int c = 0; c < a.n_chunks; ++c, ++it) {
                     const int st = it & 1;
                     mbar_wait(&bars->b_empty[st], ((it >> 1) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&bars->b_full[st], b_bytes + 2u * k_bytes);
+                    mbar_arrive_expect_tx(&bars->b_full[st], b_bytes + k_bytes);
                     bulk_g2s(Bs + (size_t)st * b_stage, a.wimg + (size_t)c * b_stage, b_bytes, &bars->b_full[st]);
-                    float* kd = s_k12 + (it & (K12_RING - 1)) * 2 * a.NB;
-                    bulk_g2s(kd, a.k1 + (size_t)c * a.NB, k_bytes, &bars->b_full[st]);
-                    bulk_g2s(kd + a.NB, a.k2 + (size_t)c * a.NB, k_bytes, &bars->b_full[st]);
+                    bulk_g2s(s_k12 + (it & (K12_RING - 1)) * a.NB, a.k12 + (size_t)c * a.NB, k_bytes, &bars->b_full[st]);
                 }
             }
         }
@@ -363,57 +360,62 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a) {
             }
         }
     } else {
-        // epilogue: TMEM lane = frame row 32 (warp % 4) + lane; warps w and w + 4 split the columns
-        const int r = (warp & 3) * 32 + lane, he = warp >> 2;
+        // epilogue: TMEM lane = frame row 32 (warp % 4) + lane; the four warps of a lane quarter take a contiguous
+        // quarter of the chunk's units (whole pdfs) each
+        const int r = (warp & 3) * 32 + lane, cq = warp >> 2;
         const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-        const int C = a.C;
+        const int n_units = a.NB / UNIT;
+        const int u0 = cq * n_units / 4, u1 = (cq + 1) * n_units / 4;
         uint32_t it = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int64_t t = tile * FR + r;
             const bool valid = t < a.N;
+            float* orow = a.llh2 + (size_t)(valid ? t : 0) * a.ld;
             for (int c = 0; c < a.n_chunks; ++c, ++it) {
                 const int buf = it & 1;
                 mbar_wait(&bars->t_full[buf], (it >> 1) & 1);
                 tc_fence_after();
-                const float* kk = s_k12 + (it & (K12_RING - 1)) * 2 * a.NB;
+                const float2* kk = s_k12 + (it & (K12_RING - 1)) * a.NB;
                 const uint32_t taddr = tmem_base + lane_addr + (uint32_t)buf * 256u;
-                const int nch = a.NB >> 4, ch0 = he ? (nch + 1) / 2 : 0, ch1 = he ? nch : (nch + 1) / 2;
-                for (int p = ch0 * 16; p < ch1 * 16; p += 16) {
-                    float v[16];
-                    tmem_ld16(taddr + (uint32_t)p, v);
+                for (int u = u0; u < u1; ++u) {
+                    const int p = u * UNIT;
+                    float v[UNIT];
+                    if constexpr (UNIT == 8) {
+                        uint32_t rr[8];
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                     : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]),
+                                       "=r"(rr[7])
+                                     : "r"(taddr + (uint32_t)p)
+                                     : "memory");
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], kk[p + i], kk[a.NB + p + i]);
-                    if (!valid) continue;
-                    float o[8];
-                    int no = 0;
-#pragma unroll
-                    for (int lg = 1; lg <= 4; ++lg) {
-                        if (C == (1 << lg)) {
-                            const int CC = 1 << lg;
-                            no = 16 / CC;
-#pragma unroll
-                            for (int k = 0; k < 16 / CC; ++k) {
-                                float m = v[k * CC];
-#pragma unroll
-                                for (int j = 1; j < CC; ++j) m = fmaxf(m, v[k * CC + j]);
-                                const float ms = (m == kNegInf) ? 0.f : m;
-                                float sm = 0.f;
-#pragma unroll
-                                for (int j = 0; j < CC; ++j) sm += ex2(v[k * CC + j] - ms);
-                                o[k] = ms + lg2(sm);
-                            }
-                        }
-                    }
-                    const int k0 = (c * a.NB + p) >> a.logC;
-                    float* dst = a.llh2 + (size_t)t * a.ld + k0;
-                    if (no == 2 && (a.ld & 1) == 0) {
-                        *reinterpret_cast<float2*>(dst) = make_float2(o[0], o[1]);
-                    } else if (no == 4 && (a.ld & 3) == 0) {
-                        *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+                        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(rr[i]);
                     } else {
+                        tmem_ld16(taddr + (uint32_t)p, v);
+                    }
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            if (i < no && k0 + i < a.Kp) dst[i] = o[i];
+                    for (int i = 0; i < UNIT; i += 2) {
+                        const float4 k = *reinterpret_cast<const float4*>(kk + p + i);      // (k1, k2) of two columns
+                        v[i] = fmaf(v[i], k.x, k.y);
+                        v[i + 1] = fmaf(v[i + 1], k.z, k.w);
+                    }
+                    float o[PPU];
+#pragma unroll
+                    for (int k = 0; k < PPU; ++k) {
+                        float m = v[k * C];
+#pragma unroll
+                        for (int j = 1; j < C; ++j) m = fmaxf(m, v[k * C + j]);
+                        const float ms = (m == kNegInf) ? 0.f : m;
+                        float sm = 0.f;
+#pragma unroll
+                        for (int j = 0; j < C; ++j) sm += ex2(v[k * C + j] - ms);
+                        o[k] = ms + lg2(sm);
+                    }
+                    if (valid) {
+                        const int k0 = (c * a.NB + p) / C;
+#pragma unroll
+                        for (int k = 0; k < PPU; ++k)
+                            if (k0 + k < a.Kp) orow[k0 + k] = o[k];
                     }
                 }
                 tc_fence_before();
@@ -430,17 +432,33 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a) {
 }
 
 static size_t ka_smem(int KP, int NB) {
-    return (size_t)2 * 2 * 128 * KP * 2 + (size_t)2 * 2 * NB * KP * 2 + (size_t)K12_RING * 2 * NB * 4 + sizeof(KaBarriers) + 1024;
+    return (size_t)2 * 2 * 128 * KP * 2 + (size_t)2 * 2 * NB * KP * 2 + (size_t)K12_RING * NB * 8 + sizeof(KaBarriers) + 1024;
+}
+
+template <int KP, int C>
+static int launch_ka(const KaArgs& a, cudaStream_t st) {
+    const size_t smem = ka_smem(KP, a.NB);
+    if (smem > 227 * 1024) return BEER_ERR_UNSUPPORTED;
+    static bool attr = false;
+    if (!attr) {
+        BEER_CUDA_TRY(cudaFuncSetAttribute(emission16_kernel<KP, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr = true;
+    }
+    const int64_t n_tiles = (a.N + 127) / 128;
+    const int grid = (int)std::min<int64_t>(n_tiles, kNumSMs);
+    emission16_kernel<KP, C><<<grid, KA_THREADS, smem, st>>>(a);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
-// KCF: acc [M, 2D+2] += sum_t w_tj T(x_t),  w = pdf_post x responsibility, responsibilities recomputed on chip
+// KCF: acc [M, 2D+2] += sum_t w_tj T(x_t),  w = pdf posterior x responsibility, responsibilities recomputed on chip
 // ---------------------------------------------------------------------------------------------
 constexpr int GM = 128;                  // Gaussians per CTA (UMMA M, TMEM lanes)
 constexpr int EPI = 512;                 // 16 epilogue warps: 4 per TMEM lane quarter, each a quarter of the 64 frames
-constexpr int KC_MMA_WARP = EPI / 32, KC_LOAD_WARP = KC_MMA_WARP + 1, KC_U_WARP0 = KC_LOAD_WARP + 1;
-constexpr int KC_THREADS = EPI + 32 + 32 + 64;
-constexpr int NS_MAX = 4;                // shared-memory stages (one 64-frame tile of both images + its u block)
+constexpr int KC_MMA_WARP = EPI / 32, KC_LOAD_WARP = KC_MMA_WARP + 1;
+constexpr int KC_THREADS = EPI + 64;
+constexpr int NS_MAX = 4;                // shared-memory stages (one 64-frame tile: both images + its llh / posterior block)
 constexpr int NSB = 3;                   // S^T / A2 buffers in tensor memory
 constexpr int DR = 4;                    // tiles per drain of the statistics accumulator (48 truncating accumulations)
 
@@ -449,14 +467,9 @@ struct KcArgs {
     const __half* img2;
     int64_t N;
     const uint32_t* wtm;
-    const float* k1;
-    const float* k2;
+    const float2* k12;
     const float* alpha;
-    const float* post;       // [N, ld_post] pdf posteriors (x scale)
-    int64_t ld_post;
-    const float* llh2;       // [N, ld_llh]
-    int64_t ld_llh;
-    int M, C, Kp, n_gtiles;
+    int M, Kp, n_gtiles;
     int64_t frames_per_cta;  // multiple of TILE
     float wexp;              // w is carried as w 2^wexp (top of the fp16 range)
     int ns;                  // shared-memory stages (<= NS_MAX)
@@ -466,30 +479,39 @@ struct KcArgs {
 
 struct KcBarriers {
     uint64_t st_full[NS_MAX], st_empty[NS_MAX];
-    uint64_t u_full[NS_MAX], u_empty[NS_MAX];
     uint64_t s_full[NSB], a2_full[NSB];
     uint64_t d2_full[2], d2_empty[2];
     uint32_t tmem_base;
     uint32_t pad[3];
 };
 
-template <int KP>
-__global__ void __launch_bounds__(KC_THREADS, 1) mixstats16_kernel(KcArgs a) {
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// map_l2 / map_lp: [N, Kp] fp32 arrays (log2 pdf llhs of KA16, log2 pdf posteriors of the forward-backward), boxes of
+// [TILE frames x GM / C pdfs]; rows past N and columns past Kp arrive as zeros.
+template <int KP, int C>
+__global__ void __launch_bounds__(KC_THREADS, 1)
+mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __grid_constant__ CUtensorMap map_lp) {
     constexpr int KS1 = KP / 16;                       // k-steps of S^T = W' . img1^T
     constexpr int KS2 = TILE / 16;                     // k-steps of acc += A2 . img2^T
     constexpr int IMG_HALF = TILE * KP;                // halfs of one image half-tile
-    constexpr int STAGE_HALFS = 4 * IMG_HALF;          // img1 hi | lo | img2 hi | lo
+    constexpr int NK = GM / C;                         // pdfs of a Gaussian tile
+    constexpr int RAW_FLOATS = TILE * NK;              // one [frame][pdf] block
+    constexpr int STAGE_BYTES = 4 * IMG_HALF * 2 + 2 * RAW_FLOATS * 4;    // img1 hi | lo | img2 hi | lo | llh2 | lpost
     constexpr uint32_t COL_W = 0, COL_S = KP, COL_D2 = KP + NSB * TILE;     // tensor-memory columns
     static_assert(COL_D2 + 2 * KP <= 512, "tensor memory");
+    static_assert(STAGE_BYTES % 128 == 0, "stage alignment");
     constexpr int NCH = KP / 4;                        // 4-column chunks of the accumulator
     constexpr int MYCH = (NCH + 3) / 4;                // per thread (four warps share a lane quarter)
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __half* stages = reinterpret_cast<__half*>(smem_raw);
-    const int nk = GM / a.C;                           // pdfs of a Gaussian tile
     const int NS = a.ns;
-    // per (pdf, frame): (llh2, lg2(post) + wexp)
-    float2* s_u = reinterpret_cast<float2*>(stages + (size_t)NS * STAGE_HALFS);   // [NS][nk][TILE]
-    KcBarriers* bars = reinterpret_cast<KcBarriers*>(s_u + (size_t)NS * nk * TILE);
+    KcBarriers* bars = reinterpret_cast<KcBarriers*>(smem_raw + (size_t)NS * STAGE_BYTES);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int gtile = blockIdx.x % a.n_gtiles;
@@ -503,8 +525,6 @@ __global__ void __launch_bounds__(KC_THREADS, 1) mixstats16_kernel(KcArgs a) {
         for (int i = 0; i < NS_MAX; ++i) {
             mbar_init(&bars->st_full[i], 1);
             mbar_init(&bars->st_empty[i], 1);
-            mbar_init(&bars->u_full[i], 64);
-            mbar_init(&bars->u_empty[i], EPI);
         }
         for (int i = 0; i < NSB; ++i) {
             mbar_init(&bars->s_full[i], 1);
@@ -543,16 +563,20 @@ __global__ void __launch_bounds__(KC_THREADS, 1) mixstats16_kernel(KcArgs a) {
     tc_fence_after();
 
     if (warp == KC_LOAD_WARP) {
-        // ------------------------------ image loader (TMA) -------------------------
+        // ------------------------------ loader (TMA) -------------------------------
         if (lane == 0) {
             const uint32_t bytes = 2u * IMG_HALF * 2u;        // hi + lo of one image
+            const int k0 = g0 / C;
             for (int i = 0; i < n_tiles; ++i) {
                 const int s = i % NS;
                 mbar_wait(&bars->st_empty[s], ((i / NS) & 1) ^ 1);
-                mbar_arrive_expect_tx(&bars->st_full[s], 2u * bytes);
-                __half* dst = stages + (size_t)s * STAGE_HALFS;
+                mbar_arrive_expect_tx(&bars->st_full[s], 2u * bytes + 2u * RAW_FLOATS * 4u);
+                uint8_t* dst = smem_raw + (size_t)s * STAGE_BYTES;
                 bulk_g2s(dst, a.img1 + (size_t)(tile0 + i) * (2 * IMG_HALF), bytes, &bars->st_full[s]);
-                bulk_g2s(dst + 2 * IMG_HALF, a.img2 + (size_t)(tile0 + i) * (2 * IMG_HALF), bytes, &bars->st_full[s]);
+                bulk_g2s(dst + bytes, a.img2 + (size_t)(tile0 + i) * (2 * IMG_HALF), bytes, &bars->st_full[s]);
+                const int t0 = (int)(f_begin + (int64_t)i * TILE);
+                tma_load_2d(dst + 2 * bytes, &map_l2, k0, t0, &bars->st_full[s]);
+                tma_load_2d(dst + 2 * bytes + RAW_FLOATS * 4, &map_lp, k0, t0, &bars->st_full[s]);
             }
         }
     } else if (warp == KC_MMA_WARP) {
@@ -564,7 +588,7 @@ __global__ void __launch_bounds__(KC_THREADS, 1) mixstats16_kernel(KcArgs a) {
                 const int s = i % NS, b = i % NSB;
                 mbar_wait(&bars->st_full[s], (i / NS) & 1);
                 tc_fence_after();
-                const uint32_t b_hi = smem_u32(stages + (size_t)s * STAGE_HALFS), b_lo = b_hi + IMG_HALF * 2u;
+                const uint32_t b_hi = smem_u32(smem_raw + (size_t)s * STAGE_BYTES), b_lo = b_hi + IMG_HALF * 2u;
                 const uint32_t d = tmem_base + COL_S + (uint32_t)b * TILE;
                 const uint32_t w_hi = tmem_base + COL_W, w_lo = w_hi + KP / 2;
 #pragma unroll 1
@@ -583,7 +607,7 @@ __global__ void __launch_bounds__(KC_THREADS, 1) mixstats16_kernel(KcArgs a) {
                 mbar_wait(&bars->a2_full[b], (i / NSB) & 1);
                 if (first) mbar_wait(&bars->d2_empty[dbuf], ((grp >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t b_hi = smem_u32(stages + (size_t)s * STAGE_HALFS + 2 * IMG_HALF), b_lo = b_hi + IMG_HALF * 2u;
+                const uint32_t b_hi = smem_u32(smem_raw + (size_t)s * STAGE_BYTES) + 2u * IMG_HALF * 2u, b_lo = b_hi + IMG_HALF * 2u;
                 const uint32_t d = tmem_base + COL_D2 + (uint32_t)dbuf * KP;
                 const uint32_t a2 = tmem_base + COL_S + (uint32_t)b * TILE;
 #pragma unroll 1
@@ -593,7 +617,7 @@ __global__ void __launch_bounds__(KC_THREADS, 1) mixstats16_kernel(KcArgs a) {
                     umma_f16_ts(d, a2 + 16u * ks + 8u, dbh, idesc2, 1);   // w lo x statistics hi
                     umma_f16_ts(d, a2 + 16u * ks, dbl, idesc2, 1);        // w hi x statistics lo
                 }
-                umma_commit(&bars->st_empty[s]);
+                umma_commit(&bars->st_empty[s]);        // the epilogue finished with the stage before a2_full completed
                 if (last) umma_commit(&bars->d2_full[dbuf]);
             };
             issue_g1(0);
@@ -603,45 +627,13 @@ __global__ void __launch_bounds__(KC_THREADS, 1) mixstats16_kernel(KcArgs a) {
                 issue_g2(i);
             }
         }
-    } else if (warp >= KC_U_WARP0) {
-        // ------- (llh2, lg2(post) + wexp) per [pdf][frame] of the tile, transposed into shared memory -------
-        const int f = (warp - KC_U_WARP0) * 32 + lane;
-        const int k0 = g0 / a.C;
-        for (int i = 0; i < n_tiles; ++i) {
-            const int s = i % NS;
-            const int64_t t = f_begin + (int64_t)i * TILE + f;
-            const bool valid = t < f_end;
-            mbar_wait(&bars->u_empty[s], ((i / NS) & 1) ^ 1);
-            float2* us = s_u + (size_t)s * nk * TILE + f;
-            const float* pp = a.post + (size_t)(valid ? t : 0) * a.ld_post + k0;
-            const float* pl = a.llh2 + (size_t)(valid ? t : 0) * a.ld_llh + k0;
-            for (int j0 = 0; j0 < nk; j0 += 16) {
-                float4 p4[4], l4[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int k = j0 + 4 * q;
-                    const bool ok = valid && k < nk && k0 + k < a.Kp;
-                    p4[q] = ok ? __ldg(reinterpret_cast<const float4*>(pp + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    l4[q] = ok ? __ldg(reinterpret_cast<const float4*>(pl + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int k = j0 + 4 * q;
-                    if (k >= nk) continue;
-                    us[(k + 0) * TILE] = make_float2(l4[q].x, lg2(p4[q].x) + a.wexp);      // post = 0 -> -inf -> w = 0
-                    us[(k + 1) * TILE] = make_float2(l4[q].y, lg2(p4[q].y) + a.wexp);
-                    us[(k + 2) * TILE] = make_float2(l4[q].z, lg2(p4[q].z) + a.wexp);
-                    us[(k + 3) * TILE] = make_float2(l4[q].w, lg2(p4[q].w) + a.wexp);
-                }
-            }
-            mbar_arrive(&bars->u_full[s]);
-        }
     } else {
         // ------------------------------ epilogue warps -------------------------------
         const int q = warp & 3, part = warp >> 2;            // TMEM lane quarter, quarter of the tile's frames
         const int g = q * 32 + lane;                         // Gaussian (local) = TMEM lane
-        const int pl = g / a.C;                              // its pdf (local)
-        const float k1 = __ldg(a.k1 + g0 + g), k2 = __ldg(a.k2 + g0 + g);
+        const int pl = g / C;                                // its pdf (local)
+        const float2 k12 = __ldg(a.k12 + g0 + g);
+        const float k1 = k12.x, k2 = k12.y;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         float sums[MYCH][4], comp[MYCH][4];
 #pragma unroll
@@ -674,38 +666,46 @@ __global__ void __launch_bounds__(KC_THREADS, 1) mixstats16_kernel(KcArgs a) {
 
         for (int i = 0; i < n_tiles; ++i) {
             const int s = i % NS, b = i % NSB;
+            mbar_wait(&bars->st_full[s], (i / NS) & 1);          // the llh / posterior block of the tile (TMA)
             mbar_wait(&bars->s_full[b], (i / NSB) & 1);
-            mbar_wait(&bars->u_full[s], (i / NS) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + lane_addr + COL_S + (uint32_t)(b * TILE + part * 16);
             float v[16];
             tmem_ld16(taddr, v);
-            const float4* up = reinterpret_cast<const float4*>(s_u + (size_t)s * nk * TILE + pl * TILE + part * 16);
+            const float* rl2 = reinterpret_cast<const float*>(smem_raw + (size_t)s * STAGE_BYTES + 4 * IMG_HALF * 2) +
+                               part * 16 * NK + pl;
+            const float* rlp = rl2 + RAW_FLOATS;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                // z = S k1 + k2 is bit for bit the value KA16 normalised: z - llh2 = log2 responsibility
+                const float z = fmaf(v[e], k1, k2);
+                v[e] = ex2((z - rl2[e * NK]) + (rlp[e * NK] + a.wexp));
+            }
+            const int nvalid = (int)min((int64_t)TILE, f_end - (f_begin + (int64_t)i * TILE)) - part * 16;
+            if (nvalid < 16) {       // the last tile of the batch: frames past the end carry no weight
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                    if (e >= nvalid) v[e] = 0.f;
+            }
             float tsum = 0.f;
             uint32_t out[16];
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
-                const float4 ua = up[2 * h], ub = up[2 * h + 1];      // (llh2, lg2 post) of frames 4h .. 4h+3
-                const float l2[4] = {ua.x, ua.z, ub.x, ub.z}, lp[4] = {ua.y, ua.w, ub.y, ub.w};
-                float w[4], wh[4];
+                float wh[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    // z = S k1 + k2 is bit for bit the value KA16 normalised: z - llh2 = log2 responsibility
-                    const float z = fmaf(v[4 * h + e], k1, k2);
-                    w[e] = ex2((z - l2[e]) + lp[e]);
-                    tsum += w[e];
-                    wh[e] = h_rn(w[e]);
+                    tsum += v[4 * h + e];
+                    wh[e] = h_rn(v[4 * h + e]);
                 }
                 out[2 * h] = pack_h2(wh[0], wh[1]);
                 out[2 * h + 1] = pack_h2(wh[2], wh[3]);
-                out[8 + 2 * h] = pack_h2(w[0] - wh[0], w[1] - wh[1]);
-                out[8 + 2 * h + 1] = pack_h2(w[2] - wh[2], w[3] - wh[3]);
+                out[8 + 2 * h] = pack_h2(v[4 * h] - wh[0], v[4 * h + 1] - wh[1]);
+                out[8 + 2 * h + 1] = pack_h2(v[4 * h + 2] - wh[2], v[4 * h + 3] - wh[3]);
             }
             tmem_st16(taddr, out);          // in place: [hi of 16 frames (8 columns) | lo (8 columns)]
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&bars->a2_full[b]);
-            mbar_arrive(&bars->u_empty[s]);
             {
                 const float y = tsum - wcomp;
                 const float t = wsum + y;
@@ -752,7 +752,65 @@ __global__ void __launch_bounds__(KC_THREADS, 1) mixstats16_kernel(KcArgs a) {
 }
 
 static size_t kc_smem(int KP, int C, int ns) {
-    return (size_t)ns * 4 * TILE * KP * 2 + (size_t)ns * (GM / C) * TILE * 8 + sizeof(KcBarriers) + 1024;
+    return (size_t)ns * (4 * TILE * KP * 2 + 2 * TILE * (GM / C) * 4) + sizeof(KcBarriers) + 1024;
+}
+
+// log2 of pdf posteriors (the forward-backward kernels that cannot write them themselves)
+__global__ void __launch_bounds__(256) log2_post_kernel(const float* __restrict__ post, int64_t N, int Kp, int64_t ld,
+                                                        float* __restrict__ out, int64_t ld_out) {
+    const int64_t total = N * Kp;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t t = i / Kp;
+        const int k = (int)(i - t * Kp);
+        out[t * ld_out + k] = lg2(post[t * ld + k]);
+    }
+}
+
+typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int encode_rows(CUtensorMap* map, const float* base, int64_t N, int Kp, int64_t ld, int box_cols) {
+    static EncodeTiled encode = nullptr;
+    if (encode == nullptr) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        BEER_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (fn == nullptr || q != cudaDriverEntryPointSuccess) return BEER_ERR_UNSUPPORTED;
+        encode = reinterpret_cast<EncodeTiled>(fn);
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)Kp, (cuuint64_t)N};
+    const cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)TILE};
+    const cuuint32_t estr[2] = {1, 1};
+    if (encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return BEER_ERR_UNSUPPORTED;
+    return BEER_OK;
+}
+
+template <int KP, int C>
+static int launch_kc(const KcArgs& a0, const float* llh2, int64_t ld_llh, const float* lpost, int64_t ld_lpost,
+                     int64_t ranges, cudaStream_t st) {
+    KcArgs a = a0;
+    a.ns = NS_MAX;
+    while (a.ns > 2 && kc_smem(KP, C, a.ns) > 227 * 1024) --a.ns;
+    const size_t smem = kc_smem(KP, C, a.ns);
+    if (smem > 227 * 1024) return BEER_ERR_UNSUPPORTED;
+    CUtensorMap m1, m2;
+    int rc = encode_rows(&m1, llh2, a.N, a.Kp, ld_llh, GM / C);
+    if (rc != BEER_OK) return rc;
+    rc = encode_rows(&m2, lpost, a.N, a.Kp, ld_lpost, GM / C);
+    if (rc != BEER_OK) return rc;
+    static bool attr = false;
+    if (!attr) {
+        BEER_CUDA_TRY(cudaFuncSetAttribute(mixstats16_kernel<KP, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr = true;
+    }
+    mixstats16_kernel<KP, C><<<(int)(ranges * a.n_gtiles), KC_THREADS, smem, st>>>(a, m1, m2);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
 }
 
 static int nb_of(int M, int C) {
@@ -790,7 +848,7 @@ int beer_mix16_geometry(int M, int D, int C, int64_t N, int64_t* sizes) {
     sizes[0] = n_tiles * 2 * mix16::TILE * KP;                 // halfs of img1 (and of img2)
     sizes[1] = (int64_t)((Mp + NB - 1) / NB) * 2 * NB * KP;    // halfs of wimg
     sizes[2] = (int64_t)Mp * KP;                               // words of wtm
-    sizes[3] = Mp;                                             // floats of k1 (and k2)
+    sizes[3] = 2 * (int64_t)Mp;                                // floats of k12 = (k1, k2) per Gaussian
     sizes[4] = NB;
     sizes[5] = KP;
     return BEER_OK;
@@ -816,14 +874,14 @@ int beer_mix16_feature_images(const float* X, int64_t N, int D, float* alpha, ui
 }
 
 int beer_mix16_pack(const float* W, const float* bias, const float* alpha, int M, int D, int C, void* wimg,
-                    uint32_t* wtm, float* k1, float* k2, void* stream) {
-    if (!W || !bias || !alpha || !wimg || !wtm || !k1 || !k2) return BEER_ERR_ARG;
+                    uint32_t* wtm, float* k12, void* stream) {
+    if (!W || !bias || !alpha || !wimg || !wtm || !k12) return BEER_ERR_ARG;
     if (!beer_mix16_supported(M, D, C)) return BEER_ERR_UNSUPPORTED;
     int64_t sz[6];
     beer_mix16_geometry(M, D, C, 0, sz);
-    const int Mp = (int)sz[3], NB = (int)sz[4];
+    const int Mp = (int)sz[3] / 2, NB = (int)sz[4];
     mix16::pack16_kernel<<<(Mp * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(W, bias, alpha, M, Mp, D, NB,
-                                                                                 (__half*)wimg, wtm, k1, k2);
+                                                                                 (__half*)wimg, wtm, (float2*)k12);
     BEER_LAUNCH_CHECK();
     return BEER_OK;
 }
@@ -836,60 +894,52 @@ int beer_mix16_frame_ref(const float* X, int64_t N, int D, const float* ref, flo
     return BEER_OK;
 }
 
-int beer_mix16_emission(const void* img1, int64_t N, int D, const void* wimg, const float* k1, const float* k2, int M,
-                        int C, float* llh2, int64_t ld, void* stream) {
-    if (!img1 || !wimg || !k1 || !k2 || !llh2 || N < 0) return BEER_ERR_ARG;
+int beer_mix16_emission(const void* img1, int64_t N, int D, const void* wimg, const float* k12, int M, int C,
+                        float* llh2, int64_t ld, void* stream) {
+    if (!img1 || !wimg || !k12 || !llh2 || N < 0) return BEER_ERR_ARG;
     if (!beer_mix16_supported(M, D, C)) return BEER_ERR_UNSUPPORTED;
     if (ld < M / C) return BEER_ERR_ARG;
     if (N == 0) return BEER_OK;
     int64_t sz[6];
     beer_mix16_geometry(M, D, C, N, sz);
     mix16::KaArgs a;
-    a.img1 = (const __half*)img1; a.N = N; a.wimg = (const __half*)wimg; a.k1 = k1; a.k2 = k2;
-    a.C = C; a.logC = 0;
-    while ((1 << a.logC) < C) ++a.logC;
+    a.img1 = (const __half*)img1; a.N = N; a.wimg = (const __half*)wimg; a.k12 = (const float2*)k12;
     a.Kp = M / C; a.NB = (int)sz[4];
     a.n_chunks = (M + a.NB - 1) / a.NB;
     a.llh2 = llh2; a.ld = ld;
     const int KP = (int)sz[5];
-    const size_t smem = mix16::ka_smem(KP, a.NB);
-    if (smem > 227 * 1024) return BEER_ERR_UNSUPPORTED;
-    const int64_t n_tiles = (N + 127) / 128;
-    const int grid = (int)std::min<int64_t>(n_tiles, kNumSMs);
     cudaStream_t st = (cudaStream_t)stream;
-    if (KP == 80) {
-        static bool attr = false;
-        if (!attr) {
-            BEER_CUDA_TRY(cudaFuncSetAttribute(mix16::emission16_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            attr = true;
-        }
-        mix16::emission16_kernel<80><<<grid, mix16::KA_THREADS, smem, st>>>(a);
-    } else {
-        static bool attr = false;
-        if (!attr) {
-            BEER_CUDA_TRY(cudaFuncSetAttribute(mix16::emission16_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            attr = true;
-        }
-        mix16::emission16_kernel<48><<<grid, mix16::KA_THREADS, smem, st>>>(a);
-    }
+#define BEER_KA_CASE(kp, c) \
+    if (KP == kp && C == c) return mix16::launch_ka<kp, c>(a, st);
+    BEER_KA_CASE(80, 4) BEER_KA_CASE(80, 8) BEER_KA_CASE(80, 16)
+    BEER_KA_CASE(48, 4) BEER_KA_CASE(48, 8) BEER_KA_CASE(48, 16)
+#undef BEER_KA_CASE
+    return BEER_ERR_UNSUPPORTED;
+}
+
+int beer_mix16_log2_posteriors(const float* pdf_post, int64_t N, int Kp, int64_t ld_post, float* pdf_lpost,
+                               int64_t ld_lpost, void* stream) {
+    if (!pdf_post || !pdf_lpost || N < 0 || Kp <= 0 || ld_post < Kp || ld_lpost < Kp) return BEER_ERR_ARG;
+    if (N == 0) return BEER_OK;
+    const int blocks = (int)std::min<int64_t>((N * Kp + 255) / 256, kNumSMs * 16);
+    mix16::log2_post_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pdf_post, N, Kp, ld_post, pdf_lpost, ld_lpost);
     BEER_LAUNCH_CHECK();
     return BEER_OK;
 }
 
-int beer_mix16_accumulate(const void* img1, const void* img2, int64_t N, int D, const uint32_t* wtm, const float* k1,
-                          const float* k2, const float* alpha, int M, int C, const float* pdf_post, int64_t ld_post,
+int beer_mix16_accumulate(const void* img1, const void* img2, int64_t N, int D, const uint32_t* wtm, const float* k12,
+                          const float* alpha, int M, int C, const float* pdf_lpost, int64_t ld_lpost,
                           const float* llh2, int64_t ld_llh, float scale, double* acc_normal, void* stream) {
-    if (!img1 || !img2 || !wtm || !k1 || !k2 || !alpha || !pdf_post || !llh2 || !acc_normal || N < 0) return BEER_ERR_ARG;
+    if (!img1 || !img2 || !wtm || !k12 || !alpha || !pdf_lpost || !llh2 || !acc_normal || N < 0) return BEER_ERR_ARG;
     if (!beer_mix16_supported(M, D, C)) return BEER_ERR_UNSUPPORTED;
-    if (ld_post < M / C || ld_llh < M / C || ld_post % 4 != 0 || ld_llh % 4 != 0) return BEER_ERR_ARG;
-    if (((uintptr_t)pdf_post & 15) != 0 || ((uintptr_t)llh2 & 15) != 0) return BEER_ERR_ARG;
+    if (ld_lpost < M / C || ld_llh < M / C || ld_lpost % 4 != 0 || ld_llh % 4 != 0) return BEER_ERR_ARG;
+    if (((uintptr_t)pdf_lpost & 15) != 0 || ((uintptr_t)llh2 & 15) != 0 || N >= (int64_t)1 << 31) return BEER_ERR_ARG;
     if (N == 0) return BEER_OK;
     mix16::KcArgs a;
-    a.img1 = (const __half*)img1; a.img2 = (const __half*)img2; a.N = N; a.wtm = wtm; a.k1 = k1; a.k2 = k2; a.alpha = alpha;
-    a.post = pdf_post; a.ld_post = ld_post; a.llh2 = llh2; a.ld_llh = ld_llh;
-    a.M = M; a.C = C; a.Kp = M / C; a.D = D; a.acc = acc_normal;
+    a.img1 = (const __half*)img1; a.img2 = (const __half*)img2; a.N = N; a.wtm = wtm; a.k12 = (const float2*)k12; a.alpha = alpha;
+    a.M = M; a.Kp = M / C; a.D = D; a.acc = acc_normal; a.ns = 0;
     a.n_gtiles = (M + mix16::GM - 1) / mix16::GM;
-    // posteriors arrive multiplied by `scale`: keep w 2^wexp <= 2^14 (fp16 overflows at 2^16)
+    // the posteriors carry `scale`: keep w 2^wexp <= 2^14 (fp16 overflows at 2^16)
     int e = 14;
     if (scale > 1.f) e -= (int)ceilf(log2f(scale));
     a.wexp = (float)e;
@@ -902,30 +952,14 @@ int beer_mix16_accumulate(const void* img1, const void* img2, int64_t N, int D, 
     fpc = (fpc + mix16::TILE - 1) / mix16::TILE * mix16::TILE;
     ranges = (N + fpc - 1) / fpc;
     a.frames_per_cta = fpc;
-    const int KP = mix16::kp_of(D);
-    a.ns = mix16::NS_MAX;
-    while (a.ns > 2 && mix16::kc_smem(KP, C, a.ns) > 227 * 1024) --a.ns;
-    const size_t smem = mix16::kc_smem(KP, C, a.ns);
-    if (smem > 227 * 1024) return BEER_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
-    const int grid = (int)(ranges * a.n_gtiles);
-    if (KP == 80) {
-        static bool attr = false;
-        if (!attr) {
-            BEER_CUDA_TRY(cudaFuncSetAttribute(mix16::mixstats16_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            attr = true;
-        }
-        mix16::mixstats16_kernel<80><<<grid, mix16::KC_THREADS, smem, st>>>(a);
-    } else {
-        static bool attr = false;
-        if (!attr) {
-            BEER_CUDA_TRY(cudaFuncSetAttribute(mix16::mixstats16_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            attr = true;
-        }
-        mix16::mixstats16_kernel<48><<<grid, mix16::KC_THREADS, smem, st>>>(a);
-    }
-    BEER_LAUNCH_CHECK();
-    return BEER_OK;
+    const int KP = mix16::kp_of(D);
+#define BEER_KC_CASE(kp, c) \
+    if (KP == kp && C == c) return mix16::launch_kc<kp, c>(a, llh2, ld_llh, pdf_lpost, ld_lpost, ranges, st);
+    BEER_KC_CASE(80, 4) BEER_KC_CASE(80, 8) BEER_KC_CASE(80, 16)
+    BEER_KC_CASE(48, 4) BEER_KC_CASE(48, 8) BEER_KC_CASE(48, 16)
+#undef BEER_KC_CASE
+    return BEER_ERR_UNSUPPORTED;
 }
 
 }  // extern "C"

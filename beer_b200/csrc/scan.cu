@@ -223,6 +223,8 @@ struct FbArgs {
     const float* lr_w;  // aligned left-to-right loop weights (hmm_fb_lr_kernel)
     int lr_row;         // stride between the three weight arrays
     double* unit_counts;  // [K / SU] or NULL: sum_t xi_t(unit ends -> unit start) + gamma_0(start)
+    float* pdf_lpost;     // [N, ld_lpost] or NULL: log2(scale * gamma) per pdf (identity pdf maps, loop kernels only)
+    int64_t ld_lpost;
     float llh_mul;        // log2(e) for llhs in nats, 1 for llhs already in log2 units (the kernels work in log2)
 };
 
@@ -908,6 +910,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_lr_kernel(FbArgs a) {
     float* ring_a = ring_p + PF * ROW;                      // [PF][32 * S]
     const int K = a.K;
     const float p_scale = a.scale * a.llh_mul;
+    const float lscale2 = lg2(a.scale);
     const int gwarp = blockIdx.x * FB_WARPS + warp, nwarps = gridDim.x * FB_WARPS;
     const bool own = lane * S < K;
     for (int i = lane; i < 2 * PF * ROW; i += 32) ring_p[i] = 0.f;   // lanes past K stay finite
@@ -1120,13 +1123,21 @@ __global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_lr_kernel(FbArgs a) {
             m = warp_max(m);
             const float ms = (m == kNegInf) ? 0.f : m;
             float sum = 0.f;
+            float vlog[S];
 #pragma unroll
             for (int j = 0; j < S; ++j) {
-                v[j] = ex2(v[j] - ms);
+                vlog[j] = v[j] - ms;
+                v[j] = ex2(vlog[j]);
                 sum += v[j];
             }
             sum = warp_sum(sum);
             const float inv = (sum > 0.f) ? __fdividef(1.f, sum) : 0.f;
+            if (a.pdf_lpost != nullptr) {
+                const float lnorm = lscale2 - lg2(sum);        // log2(scale gamma) = log value - log2 sum + log2 scale
+#pragma unroll
+                for (int j = 0; j < S; ++j) vlog[j] += lnorm;
+                write_row(a.pdf_lpost + (size_t)(t0 + t) * a.ld_lpost, vlog, 1.f);
+            }
             float fe = 0.f;      // sum_k llh_k gamma_k in raw-llh units (x p_scale at the end); llh is finite
 #pragma unroll
             for (int j = 0; j < S; ++j) {
@@ -1246,6 +1257,7 @@ __global__ void __launch_bounds__(W * 32) hmm_fb_lrb_kernel(FbArgs a) {
     float* xch = smem + (size_t)W * (2 * PF * ROW);     // [2][W][4] exchange slots
     const int K = a.K;
     const float p_scale = a.scale * a.llh_mul;
+    const float lscale2 = lg2(a.scale);
     const int gl = warp * 32 + lane;            // unit owned by this lane
     const int k0 = gl * S;                      // its first state
     const bool own = k0 < K;
@@ -1446,8 +1458,10 @@ __global__ void __launch_bounds__(W * 32) hmm_fb_lrb_kernel(FbArgs a) {
             m = warp_max(m);
             const float mls = (m == kNegInf) ? 0.f : m;
             float sl = 0.f, pe = 0.f;
+            float vlog[S];
 #pragma unroll
             for (int j = 0; j < S; ++j) {
+                vlog[j] = v[j];
                 v[j] = ex2(v[j] - mls);
                 sl += v[j];
                 pe = fmaf(p[j], v[j], pe);
@@ -1458,6 +1472,12 @@ __global__ void __launch_bounds__(W * 32) hmm_fb_lrb_kernel(FbArgs a) {
             exchange(m, sl, pe, ms, sum, pes);
             const float inv = (sum > 0.f) ? __fdividef(1.f, sum) : 0.f;
             const float resc = ex2(mls - ms) * inv;            // this warp's values -> block normalisation
+            if (a.pdf_lpost != nullptr) {
+                const float lnorm = lscale2 - ms - lg2(sum);
+#pragma unroll
+                for (int j = 0; j < S; ++j) vlog[j] += lnorm;
+                write_row(a.pdf_lpost + (size_t)(t0 + t) * a.ld_lpost, vlog, 1.f);
+            }
 #pragma unroll
             for (int j = 0; j < S; ++j) v[j] *= resc;
             if (threadIdx.x == 0) {
@@ -2096,6 +2116,12 @@ int beer_hmm_unit_count_size(const beer_graph_plan* plan) {
     return plan->K / plan->lr_su;
 }
 
+// 1 when beer_hmm_forward_backward_ex can write log2 posteriors for this graph (left-to-right loop kernels)
+int beer_hmm_lpost_supported(const beer_graph_plan* plan) {
+    if (!plan) return 0;
+    return (plan->lr_su && plan->map_identity && plan->lr_u > 0) ? 1 : 0;
+}
+
 int beer_hmm_forward_backward(const beer_graph_plan* plan, const float* pdf_llh, int64_t ld_pdf,
                               const float* frame_ref, const int64_t* utt_off, int n_utts, float scale,
                               float* state_post, float* pdf_post, int64_t ld_post, float* frame_exp_llh,
@@ -2111,14 +2137,14 @@ int beer_hmm_forward_backward_units(const beer_graph_plan* plan, const float* pd
                                     double* utt_exp_llh, double* utt_logz, double* unit_counts, void* workspace,
                                     void* stream) {
     return beer_hmm_forward_backward_ex(plan, pdf_llh, ld_pdf, frame_ref, utt_off, n_utts, scale, state_post, pdf_post,
-                                        ld_post, frame_exp_llh, utt_exp_llh, utt_logz, unit_counts, 0, workspace, stream);
+                                        ld_post, frame_exp_llh, utt_exp_llh, utt_logz, unit_counts, 0, nullptr, 0, workspace, stream);
 }
 
 int beer_hmm_forward_backward_ex(const beer_graph_plan* plan, const float* pdf_llh, int64_t ld_pdf,
                                  const float* frame_ref, const int64_t* utt_off, int n_utts, float scale,
                                  float* state_post, float* pdf_post, int64_t ld_post, float* frame_exp_llh,
                                  double* utt_exp_llh, double* utt_logz, double* unit_counts, int llh_log2,
-                                 void* workspace, void* stream) {
+                                 float* pdf_lpost, int64_t ld_lpost, void* workspace, void* stream) {
     if (!plan || !pdf_llh || !utt_off || !utt_exp_llh || !workspace || n_utts < 0) return BEER_ERR_ARG;
     if (ld_pdf < plan->Kp || (pdf_post && ld_post < plan->Kp)) return BEER_ERR_ARG;
     if (n_utts == 0) return BEER_OK;
@@ -2138,11 +2164,13 @@ int beer_hmm_forward_backward_ex(const beer_graph_plan* plan, const float* pdf_l
     a.lr_row = 32 * plan->lr_su * plan->lr_u;
     a.unit_counts = unit_counts;
     a.llh_mul = llh_log2 ? 1.f : kLog2e;
+    a.pdf_lpost = pdf_lpost; a.ld_lpost = ld_lpost;
+    if (pdf_lpost != nullptr && (ld_lpost < plan->Kp || ld_lpost % 4 != 0 || ((uintptr_t)pdf_lpost & 15) != 0)) return BEER_ERR_ARG;
     if (unit_counts != nullptr && beer_hmm_unit_count_size(plan) <= 0) return BEER_ERR_UNSUPPORTED;
     const bool post_ok = (pdf_post == nullptr || (ld_post % 4 == 0 && ((uintptr_t)pdf_post & 15) == 0)) &&
                          (state_post == nullptr || (plan->K % 4 == 0 && ((uintptr_t)state_post & 15) == 0));
     const char* force = getenv("BEER_B200_SCAN");   // debug: "generic" | "fast" | unset (best available)
-    if (unit_counts != nullptr) force = nullptr;    // unit counts live in the left-to-right loop kernel
+    if (unit_counts != nullptr || pdf_lpost != nullptr) force = nullptr;    // both live in the loop kernels only
     const bool lr_vec = (plan->lr_su * plan->lr_u) % 4 == 0;   // the kernel moves whole float4 rows
     // (its float4 rows need 16-byte aligned llh / posterior rows; a.vec is about the generic kernels' lane layout)
     const bool lr_rows_ok = ld_pdf % 4 == 0 && ((uintptr_t)pdf_llh & 15) == 0 && post_ok;
@@ -2162,8 +2190,8 @@ int beer_hmm_forward_backward_ex(const beer_graph_plan* plan, const float* pdf_l
             if (u == 4) return launch_fb_lr<3, 4>(a, n_utts, st);
         }
     }
-    // only the left-to-right loop kernel accumulates unit counts: never drop them silently
-    if (unit_counts != nullptr) return BEER_ERR_UNSUPPORTED;
+    // only the left-to-right loop kernels accumulate unit counts / write log2 posteriors: never drop them silently
+    if (unit_counts != nullptr || pdf_lpost != nullptr) return BEER_ERR_UNSUPPORTED;
     if (force != nullptr && force[0] == 'g') goto generic;
     if (plan->fast_ok && a.vec && (state_post == nullptr || plan->K % 4 == 0) &&
         (pdf_post == nullptr || (ld_post % 4 == 0 && ((uintptr_t)pdf_post & 15) == 0)) &&

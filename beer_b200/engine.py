@@ -389,9 +389,15 @@ class VBEngine:
                                                     workspace=self.ws, out_pdf_post=pdf_post,
                                                     out_utt_exp_llh=self.utt_ell[u0:u1])
                 else:
+                    direct = images is not None and not nonident and plan.writes_log2_posteriors
                     ops.hmm_forward_backward(plan, pdf_llh, fref, rel, scale=self.scale, workspace=self.ws,
-                                             out_pdf_post=pdf_post, out_utt_exp_llh=self.utt_ell[u0:u1],
+                                             want_pdf_post=not direct, out_pdf_post=None if direct else pdf_post,
+                                             out_pdf_lpost=pdf_post if direct else None,
+                                             out_utt_exp_llh=self.utt_ell[u0:u1],
                                              unit_counts=self.unit_counts, llh_log2=images is not None)
+                    if images is not None and not direct:      # graphs without a loop kernel: log2 of pdf_post
+                        self.mix16.log2_posteriors(pdf_post, out=pdf_post)
+                        self.gpu_launches += 1
             with self._stage('KC_accumulate'):
                 if images is not None:
                     self.mix16.accumulate(images, pdf_post, pdf_llh, self.acc, scale=self.scale)

@@ -169,6 +169,11 @@ class GraphPlan:
     def workspace_bytes(self, n_frames):
         return int(self._lib.beer_hmm_workspace_bytes(self._h, int(n_frames)))
 
+    @property
+    def writes_log2_posteriors(self):
+        """The forward-backward kernel of this graph can hand out log2 posteriors (`out_pdf_lpost`)."""
+        return bool(self._lib.beer_hmm_lpost_supported(self._h))
+
     def __del__(self):
         h, self._h = getattr(self, '_h', None), None
         if h:
@@ -177,7 +182,7 @@ class GraphPlan:
 
 def hmm_forward_backward(plan, pdf_llh, frame_ref, utt_off, scale=1.0, want_state_post=False,
                          want_pdf_post=True, want_frame_llh=False, want_logz=False, workspace=None,
-                         out_pdf_post=None, out_utt_exp_llh=None, unit_counts=None, llh_log2=False):
+                         out_pdf_post=None, out_utt_exp_llh=None, unit_counts=None, llh_log2=False, out_pdf_lpost=None):
     """Forward-backward for a ragged batch.  -> dict(state_post, pdf_post, frame_exp_llh,
     utt_exp_llh (fp64), utt_logz (fp64)).  `out_pdf_post` must be zero-filled by the caller
     when the graph's pdf map is not the identity (the kernel then scatter-adds)."""
@@ -203,7 +208,8 @@ def hmm_forward_backward(plan, pdf_llh, frame_ref, utt_off, scale=1.0, want_stat
         plan._h, _p(pdf_llh, f32), pdf_llh.stride(0), _p(frame_ref, f32, True), _p(utt_off, i64), n_utts,
         float(scale), _p(state_post, f32, True), _p(pdf_post, f32, True),
         pdf_post.stride(0) if pdf_post is not None else 0, _p(frame, f32, True),
-        _p(utt_ell, f64), _p(utt_logz, f64, True), _p(unit_counts, f64, True), int(bool(llh_log2)), _p(workspace),
+        _p(utt_ell, f64), _p(utt_logz, f64, True), _p(unit_counts, f64, True), int(bool(llh_log2)),
+        _p(out_pdf_lpost, f32, True), out_pdf_lpost.stride(0) if out_pdf_lpost is not None else 0, _p(workspace),
         _stream()), 'beer_hmm_forward_backward')
     return dict(state_post=state_post, pdf_post=pdf_post, frame_exp_llh=frame, utt_exp_llh=utt_ell,
                 utt_logz=utt_logz, workspace=workspace)
@@ -572,8 +578,7 @@ class Mix16:
         self.NB, self.KP = int(sz[4]), int(sz[5])
         self.wimg = torch.zeros(int(sz[1]), device=device, dtype=torch.float16)
         self.wtm = torch.zeros(int(sz[2]), device=device, dtype=i32)
-        self.k1 = torch.zeros(int(sz[3]), device=device, dtype=f32)
-        self.k2 = torch.zeros(int(sz[3]), device=device, dtype=f32)
+        self.k12 = torch.zeros(int(sz[3]), device=device, dtype=f32)
         self._absmax = torch.zeros(D, device=device, dtype=i32)
 
     def _geometry(self, N):
@@ -601,7 +606,7 @@ class Mix16:
 
     def pack(self, W, bias, alpha):
         _lib.check(_lib.load().beer_mix16_pack(_p(W, f32), _p(bias, f32), _p(alpha, f32), self.M, self.D, self.C,
-                                               _p(self.wimg), _p(self.wtm), _p(self.k1), _p(self.k2), _stream()),
+                                               _p(self.wimg), _p(self.wtm), _p(self.k12), _stream()),
                    'beer_mix16_pack')
 
     def frame_ref(self, X, ref, out=None):
@@ -615,18 +620,26 @@ class Mix16:
         """llh2 [N, Kp]: log2-domain pdf llhs in offset form (add frame_ref / ln 2 for absolute values)."""
         N = images['N']
         llh2 = out if out is not None else torch.empty(N, self.Kp, device=self.device, dtype=f32)
-        _lib.check(_lib.load().beer_mix16_emission(_p(images['img1']), N, self.D, _p(self.wimg), _p(self.k1), _p(self.k2),
-                                                   self.M, self.C, _p(llh2, f32), llh2.stride(0), _stream()),
+        _lib.check(_lib.load().beer_mix16_emission(_p(images['img1']), N, self.D, _p(self.wimg), _p(self.k12), self.M,
+                                                   self.C, _p(llh2, f32), llh2.stride(0), _stream()),
                    'beer_mix16_emission')
         return llh2
 
-    def accumulate(self, images, pdf_post, llh2, acc_normal, scale=1.0):
+    def accumulate(self, images, pdf_lpost, llh2, acc_normal, scale=1.0):
+        """`pdf_lpost` [N, Kp]: log2 of the (scaled) pdf posteriors, see `log2_posteriors`."""
         N = images['N']
         _lib.check(_lib.load().beer_mix16_accumulate(
-            _p(images['img1']), _p(images['img2']), N, self.D, _p(self.wtm), _p(self.k1), _p(self.k2),
-            _p(images['alpha']), self.M, self.C, _p(pdf_post, f32), pdf_post.stride(0), _p(llh2, f32), llh2.stride(0),
+            _p(images['img1']), _p(images['img2']), N, self.D, _p(self.wtm), _p(self.k12),
+            _p(images['alpha']), self.M, self.C, _p(pdf_lpost, f32), pdf_lpost.stride(0), _p(llh2, f32), llh2.stride(0),
             float(scale), _p(acc_normal, f64), _stream()), 'beer_mix16_accumulate')
         return acc_normal
+
+    def log2_posteriors(self, pdf_post, out=None):
+        N = pdf_post.shape[0]
+        out = out if out is not None else torch.empty(N, self.Kp, device=pdf_post.device, dtype=f32)
+        _lib.check(_lib.load().beer_mix16_log2_posteriors(_p(pdf_post, f32), N, self.Kp, pdf_post.stride(0), _p(out, f32),
+                                                          out.stride(0), _stream()), 'beer_mix16_log2_posteriors')
+        return out
 
 
 # ---------------------------------------------------------------------------

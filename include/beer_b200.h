@@ -306,13 +306,17 @@ BEER_API int beer_fbank(const float* signal, int64_t n_samples, int frame_len, i
  * out[t] = sum_{k=1..wlen} k (fea[t+k] - fea[t-k]) / (2 sum k^2). */
 BEER_API int beer_add_deltas(const float* fea, int n_frames, int dim, int wlen, float* out, void* stream);
 
+/* 1 when beer_hmm_forward_backward_ex can write pdf_lpost for this graph. */
+BEER_API int beer_hmm_lpost_supported(const beer_graph_plan* plan);
 /* Same as beer_hmm_forward_backward_units with the domain of the llhs stated: llh_log2 != 0 = pdf_llh holds log2
- * values (what beer_mix16_emission writes; frame_ref stays in nats), 0 = nats. */
+ * values (what beer_mix16_emission writes; frame_ref stays in nats), 0 = nats.  pdf_lpost (optional, [N, ld_lpost],
+ * 16-byte aligned rows) = log2(scale * posterior) per pdf, -inf for zero: only the left-to-right loop kernels write it
+ * (BEER_ERR_UNSUPPORTED otherwise: take pdf_post and beer_mix16_log2_posteriors). */
 BEER_API int beer_hmm_forward_backward_ex(const beer_graph_plan* plan, const float* pdf_llh, int64_t ld_pdf,
                                  const float* frame_ref, const int64_t* utt_off, int n_utts, float scale,
                                  float* state_post, float* pdf_post, int64_t ld_post, float* frame_exp_llh,
                                  double* utt_exp_llh, double* utt_logz, double* unit_counts, int llh_log2,
-                                 void* workspace, void* stream);
+                                 float* pdf_lpost, int64_t ld_lpost, void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------
  * Mixture path without per-Gaussian llhs in HBM (csrc/mix16.cu): MixtureSet.expected_log_likelihood +
@@ -321,7 +325,7 @@ BEER_API int beer_hmm_forward_backward_ex(const beer_graph_plan* plan, const flo
  * ---------------------------------------------------------------------- */
 
 BEER_API int beer_mix16_supported(int M, int D, int C);
-/* sizes_host[6] = {halfs of img1 (= of img2) for N frames, halfs of wimg, 32-bit words of wtm, floats of k1 (= of k2),
+/* sizes_host[6] = {halfs of img1 (= of img2) for N frames, halfs of wimg, 32-bit words of wtm, floats of k12,
  * Gaussians per emission chunk, padded statistics width KP}. */
 BEER_API int beer_mix16_geometry(int M, int D, int C, int64_t N, int64_t* sizes_host);
 /* Feature images of a resident run of frames, built once: alpha [2D] (out) = per-dimension power-of-two scales of the
@@ -331,20 +335,23 @@ BEER_API int beer_mix16_geometry(int M, int D, int C, int64_t N, int64_t* sizes_
 BEER_API int beer_mix16_feature_images(const float* X, int64_t N, int D, float* alpha, uint32_t* absmax_scratch, void* img1,
                               void* img2, void* stream);
 /* Per VB iteration: (W [M, 2D], bias [M]) of beer_emission_prepare -> packed fp16 weights for the two kernels
- * (wimg: emission, wtm: statistics) and the per-Gaussian affine z = S k1 + k2 (log2 domain). */
+ * (wimg: emission, wtm: statistics) and the per-Gaussian affine z = S k1 + k2 (log2 domain), k12 = (k1, k2) pairs. */
 BEER_API int beer_mix16_pack(const float* W, const float* bias, const float* alpha, int M, int D, int C, void* wimg,
-                    uint32_t* wtm, float* k1, float* k2, void* stream);
+                    uint32_t* wtm, float* k12, void* stream);
 /* frame_ref [N] = the per-frame constant of the offset form (see beer_emission_prepare). */
 BEER_API int beer_mix16_frame_ref(const float* X, int64_t N, int D, const float* ref, float* frame_ref, void* stream);
 /* llh2 [N, ld] = log2 sum_c 2^z (offset form, log2 units): MixtureSet.expected_log_likelihood without the
  * per-Gaussian llhs (mixtureset.py:85-98). */
-BEER_API int beer_mix16_emission(const void* img1, int64_t N, int D, const void* wimg, const float* k1, const float* k2, int M,
-                        int C, float* llh2, int64_t ld, void* stream);
-/* acc_normal [M, 2D+2] (fp64) += sum_t pdf_post[t, pdf(j)] r_tj T(x_t) with the responsibilities r = 2^(z - llh2)
- * recomputed on chip (mixtureset.py:100-112, normalset.py:121-123).  pdf_post already carries `scale`. */
-BEER_API int beer_mix16_accumulate(const void* img1, const void* img2, int64_t N, int D, const uint32_t* wtm, const float* k1,
-                          const float* k2, const float* alpha, int M, int C, const float* pdf_post, int64_t ld_post,
+BEER_API int beer_mix16_emission(const void* img1, int64_t N, int D, const void* wimg, const float* k12, int M, int C,
+                        float* llh2, int64_t ld, void* stream);
+/* acc_normal [M, 2D+2] (fp64) += sum_t 2^pdf_lpost[t, pdf(j)] r_tj T(x_t) with the responsibilities r = 2^(z - llh2)
+ * recomputed on chip (mixtureset.py:100-112, normalset.py:121-123).  pdf_lpost [N, ld] = log2 of the pdf posteriors
+ * (times `scale`, -inf = zero): written by beer_hmm_forward_backward_ex, or beer_mix16_log2_posteriors of pdf_post. */
+BEER_API int beer_mix16_accumulate(const void* img1, const void* img2, int64_t N, int D, const uint32_t* wtm, const float* k12,
+                          const float* alpha, int M, int C, const float* pdf_lpost, int64_t ld_lpost,
                           const float* llh2, int64_t ld_llh, float scale, double* acc_normal, void* stream);
+BEER_API int beer_mix16_log2_posteriors(const float* pdf_post, int64_t N, int Kp, int64_t ld_post, float* pdf_lpost,
+                               int64_t ld_lpost, void* stream);
 
 /* ------------------------------------------------------------------------
  * Roofline probes (measurement only: bench.py / tools/microbench.py time them with CUDA events)

@@ -78,7 +78,8 @@ def test_emission_and_statistics_match_fp64(M, D, C, N):
     pp = torch.rand(N, Kp, generator=g).to(DEV)
     pp = torch.where(pp < 0.6, torch.zeros_like(pp), pp).contiguous()
     acc = torch.zeros(M, 2 * D + 2, device=DEV, dtype=torch.float64)
-    mx.accumulate(images, pp, llh2, acc)
+    lpp = mx.log2_posteriors(pp)
+    mx.accumulate(images, lpp, llh2, acc)
     resp = (comp.reshape(N, Kp, C) - pdf[:, :, None]).exp()
     w = (resp * pp.double()[:, :, None]).reshape(N, M)
     want_acc = w.T @ stats
@@ -89,7 +90,7 @@ def test_emission_and_statistics_match_fp64(M, D, C, N):
     want_cnt = pp.double().sum(0)
     assert (cnt - want_cnt).abs().max().item() <= 5e-6 * want_cnt.abs().max().item() + 1e-9
     # accumulation semantics: a second call adds
-    mx.accumulate(images, pp, llh2, acc)
+    mx.accumulate(images, lpp, llh2, acc)
     assert (acc - 2 * want_acc).abs().max().item() <= 2 * tol
 
 
@@ -108,4 +109,20 @@ def test_forward_backward_accepts_log2_llhs():
     a = ops.hmm_forward_backward(plan, llh, fref, off, want_frame_llh=True)
     b = ops.hmm_forward_backward(plan, (llh / LN2).contiguous(), fref, off, want_frame_llh=True, llh_log2=True)
     assert (a['pdf_post'] - b['pdf_post']).abs().max().item() <= 2e-5
+    # log2 posteriors straight from the loop kernel
+    assert plan.writes_log2_posteriors
+    lp = torch.empty(2 * T, K, device=DEV)
+    ops.hmm_forward_backward(plan, llh, fref, off, want_pdf_post=False, out_pdf_lpost=lp, scale=0.5)
+    c = ops.hmm_forward_backward(plan, llh, fref, off, scale=0.5)
+    assert (torch.exp2(lp) - c['pdf_post']).abs().max().item() <= 2e-6
+    small = torch.zeros(40, 12, device=DEV)            # 3 units x 4 states: the one-warp loop kernel
+    g3, _, _ = synthetic.phone_loop_graph(3, 4)
+    p3 = ops.GraphPlan(g3.init_log_probs.numpy(), g3.final_log_probs.numpy(), g3.trans_log_probs.numpy(),
+                       g3.pdf_id_mapping, n_pdfs=12)
+    small.copy_(3.0 * torch.randn(40, 12, generator=g))
+    lp3 = torch.empty(40, 12, device=DEV)
+    o3 = torch.tensor([0, 40], device=DEV)
+    ops.hmm_forward_backward(p3, small, None, o3, want_pdf_post=False, out_pdf_lpost=lp3)
+    c3 = ops.hmm_forward_backward(p3, small, None, o3)
+    assert (torch.exp2(lp3) - c3['pdf_post']).abs().max().item() <= 2e-6
     np.testing.assert_allclose(a['utt_exp_llh'].cpu().numpy(), b['utt_exp_llh'].cpu().numpy(), rtol=2e-6)
