@@ -82,6 +82,7 @@ SIGNATURES = {
     'beer_mix16_accumulate': (C.c_int, [c_ptr, c_ptr, C.c_int64, C.c_int, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int,
                                         c_ptr, C.c_int64, c_ptr, C.c_int64, C.c_float, c_ptr, c_ptr]),
     'beer_probe_mma': (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), c_ptr]),
+    'beer_probe_tma': (C.c_int, [c_ptr, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr]),
     'beer_probe_fill': (C.c_int, [c_ptr, C.c_int64, C.c_int, c_ptr]),
     'beer_probe_read': (C.c_int, [c_ptr, C.c_int64, c_ptr, c_ptr]),
     'beer_path_posteriors': (C.c_int, [c_ptr, C.c_int64, c_ptr, C.c_float, c_ptr, C.c_int64, c_ptr, c_ptr,

@@ -246,7 +246,9 @@ __global__ void __launch_bounds__(128) pack16_kernel(const float* __restrict__ W
 // ---------------------------------------------------------------------------------------------
 // KA16: llh2 [N, Kp] = log2 sum_c 2^(z_tkc)
 // ---------------------------------------------------------------------------------------------
-constexpr int KA_WORKERS = 512, KA_MMA_WARP = KA_WORKERS / 32, KA_LOAD_WARP = KA_MMA_WARP + 1, KA_THREADS = KA_WORKERS + 64;
+constexpr int KA_WORKERS = 512, KA_MMA_WARP = KA_WORKERS / 32, KA_LOAD_WARP = KA_MMA_WARP + 1;
+constexpr int KA_LOADERS = 3;           // statistics tiles | weight chunks | (k1, k2) of the chunks
+constexpr int KA_THREADS = KA_WORKERS + 32 + 32 * KA_LOADERS;
 constexpr int K12_RING = 4;
 
 struct KaArgs {
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars->a_full[i], 1);
             mbar_init(&bars->a_empty[i], 1);
-            mbar_init(&bars->b_full[i], 1);
+            mbar_init(&bars->b_full[i], 2);
             mbar_init(&bars->b_empty[i], 1);
             mbar_init(&bars->t_full[i], 1);
             mbar_init(&bars->t_empty[i], KA_WORKERS);
@@ -301,31 +303,40 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a) {
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
-    if (warp == KA_LOAD_WARP) {
+    if (warp >= KA_LOAD_WARP) {
+        // one issuing thread per stream of copies (a thread sustains about one copy per 500 cycles)
         if (lane == 0) {
+            const int which = warp - KA_LOAD_WARP;
             uint32_t it = 0, tile_it = 0;
             const uint32_t half_bytes = TILE * KP * 2, b_bytes = (uint32_t)b_stage * 2u, k_bytes = (uint32_t)a.NB * 8u;
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
-                const int ab = tile_it & 1;
-                mbar_wait(&bars->a_empty[ab], ((tile_it >> 1) & 1) ^ 1);
-                const int64_t tA = 2 * tile, tB = tA + 1;
-                const bool two = tB < n_tiles64;
-                mbar_arrive_expect_tx(&bars->a_full[ab], (two ? 4u : 2u) * half_bytes);
-                __half* dst = As + (size_t)ab * 2 * A_HALF;
-                const __half* srcA = a.img1 + (size_t)tA * (2 * TILE * KP);
-                bulk_g2s(dst, srcA, half_bytes, &bars->a_full[ab]);                              // hi, rows 0..63
-                bulk_g2s(dst + A_HALF, srcA + TILE * KP, half_bytes, &bars->a_full[ab]);         // lo, rows 0..63
-                if (two) {
-                    const __half* srcB = a.img1 + (size_t)tB * (2 * TILE * KP);
-                    bulk_g2s(dst + TILE * KP, srcB, half_bytes, &bars->a_full[ab]);                       // hi, rows 64..127
-                    bulk_g2s(dst + A_HALF + TILE * KP, srcB + TILE * KP, half_bytes, &bars->a_full[ab]);  // lo
+                if (which == 0) {
+                    const int ab = tile_it & 1;
+                    mbar_wait(&bars->a_empty[ab], ((tile_it >> 1) & 1) ^ 1);
+                    const int64_t tA = 2 * tile, tB = tA + 1;
+                    const bool two = tB < n_tiles64;
+                    mbar_arrive_expect_tx(&bars->a_full[ab], (two ? 4u : 2u) * half_bytes);
+                    __half* dst = As + (size_t)ab * 2 * A_HALF;
+                    const __half* srcA = a.img1 + (size_t)tA * (2 * TILE * KP);
+                    bulk_g2s(dst, srcA, half_bytes, &bars->a_full[ab]);                              // hi, rows 0..63
+                    bulk_g2s(dst + A_HALF, srcA + TILE * KP, half_bytes, &bars->a_full[ab]);         // lo, rows 0..63
+                    if (two) {
+                        const __half* srcB = a.img1 + (size_t)tB * (2 * TILE * KP);
+                        bulk_g2s(dst + TILE * KP, srcB, half_bytes, &bars->a_full[ab]);                       // hi, rows 64..127
+                        bulk_g2s(dst + A_HALF + TILE * KP, srcB + TILE * KP, half_bytes, &bars->a_full[ab]);  // lo
+                    }
+                    continue;
                 }
                 for (int c = 0; c < a.n_chunks; ++c, ++it) {
                     const int st = it & 1;
                     mbar_wait(&bars->b_empty[st], ((it >> 1) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&bars->b_full[st], b_bytes + k_bytes);
-                    bulk_g2s(Bs + (size_t)st * b_stage, a.wimg + (size_t)c * b_stage, b_bytes, &bars->b_full[st]);
-                    bulk_g2s(s_k12 + (it & (K12_RING - 1)) * a.NB, a.k12 + (size_t)c * a.NB, k_bytes, &bars->b_full[st]);
+                    if (which == 1) {
+                        mbar_arrive_expect_tx(&bars->b_full[st], b_bytes);
+                        bulk_g2s(Bs + (size_t)st * b_stage, a.wimg + (size_t)c * b_stage, b_bytes, &bars->b_full[st]);
+                    } else {
+                        mbar_arrive_expect_tx(&bars->b_full[st], k_bytes);
+                        bulk_g2s(s_k12 + (it & (K12_RING - 1)) * a.NB, a.k12 + (size_t)c * a.NB, k_bytes, &bars->b_full[st]);
+                    }
                 }
             }
         }
@@ -457,7 +468,8 @@ static int launch_ka(const KaArgs& a, cudaStream_t st) {
 constexpr int GM = 128;                  // Gaussians per CTA (UMMA M, TMEM lanes)
 constexpr int EPI = 512;                 // 16 epilogue warps: 4 per TMEM lane quarter, each a quarter of the 64 frames
 constexpr int KC_MMA_WARP = EPI / 32, KC_LOAD_WARP = KC_MMA_WARP + 1;
-constexpr int KC_THREADS = EPI + 64;
+constexpr int KC_LOADERS = 4;            // one issuing thread per copy of a stage: a thread sustains ~1 copy / 500 cycles
+constexpr int KC_THREADS = EPI + 32 + 32 * KC_LOADERS;
 constexpr int NS_MAX = 4;                // shared-memory stages (one 64-frame tile: both images + its llh / posterior block)
 constexpr int NSB = 3;                   // S^T / A2 buffers in tensor memory
 constexpr int DR = 4;                    // tiles per drain of the statistics accumulator (48 truncating accumulations)
@@ -523,7 +535,7 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
 
     if (tid == 0) {
         for (int i = 0; i < NS_MAX; ++i) {
-            mbar_init(&bars->st_full[i], 1);
+            mbar_init(&bars->st_full[i], KC_LOADERS);
             mbar_init(&bars->st_empty[i], 1);
         }
         for (int i = 0; i < NSB; ++i) {
@@ -562,21 +574,31 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
     __syncthreads();
     tc_fence_after();
 
-    if (warp == KC_LOAD_WARP) {
-        // ------------------------------ loader (TMA) -------------------------------
+    if (warp >= KC_LOAD_WARP) {
+        // ------------------------------ loaders (TMA) ------------------------------
+        // four warps, one copy of the stage each (img1 tile, img2 tile, llh block, posterior block)
         if (lane == 0) {
+            const int which = warp - KC_LOAD_WARP;
             const uint32_t bytes = 2u * IMG_HALF * 2u;        // hi + lo of one image
             const int k0 = g0 / C;
             for (int i = 0; i < n_tiles; ++i) {
                 const int s = i % NS;
                 mbar_wait(&bars->st_empty[s], ((i / NS) & 1) ^ 1);
-                mbar_arrive_expect_tx(&bars->st_full[s], 2u * bytes + 2u * RAW_FLOATS * 4u);
                 uint8_t* dst = smem_raw + (size_t)s * STAGE_BYTES;
-                bulk_g2s(dst, a.img1 + (size_t)(tile0 + i) * (2 * IMG_HALF), bytes, &bars->st_full[s]);
-                bulk_g2s(dst + bytes, a.img2 + (size_t)(tile0 + i) * (2 * IMG_HALF), bytes, &bars->st_full[s]);
                 const int t0 = (int)(f_begin + (int64_t)i * TILE);
-                tma_load_2d(dst + 2 * bytes, &map_l2, k0, t0, &bars->st_full[s]);
-                tma_load_2d(dst + 2 * bytes + RAW_FLOATS * 4, &map_lp, k0, t0, &bars->st_full[s]);
+                if (which == 0) {
+                    mbar_arrive_expect_tx(&bars->st_full[s], bytes);
+                    bulk_g2s(dst, a.img1 + (size_t)(tile0 + i) * (2 * IMG_HALF), bytes, &bars->st_full[s]);
+                } else if (which == 1) {
+                    mbar_arrive_expect_tx(&bars->st_full[s], bytes);
+                    bulk_g2s(dst + bytes, a.img2 + (size_t)(tile0 + i) * (2 * IMG_HALF), bytes, &bars->st_full[s]);
+                } else if (which == 2) {
+                    mbar_arrive_expect_tx(&bars->st_full[s], RAW_FLOATS * 4u);
+                    tma_load_2d(dst + 2 * bytes, &map_l2, k0, t0, &bars->st_full[s]);
+                } else {
+                    mbar_arrive_expect_tx(&bars->st_full[s], RAW_FLOATS * 4u);
+                    tma_load_2d(dst + 2 * bytes + RAW_FLOATS * 4, &map_lp, k0, t0, &bars->st_full[s]);
+                }
             }
         }
     } else if (warp == KC_MMA_WARP) {

@@ -9,6 +9,7 @@
 //   beer_probe_read  : read-only stream (float4 loads folded into one value per thread).
 //
 // Timing is done by the caller with CUDA events on the stream the probe is launched on.
+#include <cuda.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "../../include/beer_b200.h"
@@ -100,6 +101,46 @@ __global__ void __launch_bounds__(256) read_kernel(const float4* __restrict__ sr
     if (acc == 123.456f) *sink = acc;      // never true: keeps the loads alive
 }
 
+// Global -> shared copy engine throughput per SM: every CTA (one per SM) streams `copies` chunks of `chunk` bytes from
+// a buffer that fits in L2 through a ring of `stages` shared-memory slots; a copy is re-issued as soon as it landed.
+//   MODE 0: cp.async.bulk (1-D bulk copy, UBLKCP)     MODE 1: cp.async.bulk.tensor.2d (tensor map, UTMALDG)
+template <int MODE>
+__global__ void __launch_bounds__(256, 1) tma_read_kernel(const uint8_t* __restrict__ src, int64_t src_bytes, int chunk,
+                                                          int stages, int copies, int issuers,
+                                                          const __grid_constant__ CUtensorMap map) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint64_t full[16];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 16; ++i) mbar_init(&full[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0 && w < issuers) {
+        // issuer w owns the slots s = w, w + issuers, ...
+        const int64_t n_chunks = src_bytes / chunk;
+        int64_t pos = ((int64_t)blockIdx.x * 37 + (int64_t)w * 1009) % n_chunks;
+        const int my_stages = (stages - w + issuers - 1) / issuers, my_copies = copies / issuers;
+        for (int i = 0; i < my_copies + my_stages; ++i) {
+            const int s = w + (i % my_stages) * issuers;
+            if (i >= my_stages) mbar_wait(&full[s], ((i / my_stages) - 1) & 1);
+            if (i < my_copies) {
+                mbar_arrive_expect_tx(&full[s], (uint32_t)chunk);
+                if (MODE == 0) {
+                    bulk_g2s(smem_raw + (size_t)s * chunk, src + pos * chunk, (uint32_t)chunk, &full[s]);
+                } else {
+                    asm volatile(
+                        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                            smem_u32(smem_raw + (size_t)s * chunk)),
+                        "l"(&map), "r"(0), "r"((int)(pos * (chunk / 256))), "r"(smem_u32(&full[s]))
+                        : "memory");
+                }
+                pos = (pos + 1) % n_chunks;
+            }
+        }
+    }
+}
+
 }  // namespace probe
 }  // namespace beer
 
@@ -142,6 +183,46 @@ int beer_probe_fill(float* dst, int64_t bytes, int mode, void* stream) {
 int beer_probe_read(const float* src, int64_t bytes, float* sink, void* stream) {
     if (!src || !sink || bytes <= 0 || (((uintptr_t)src) & 15) != 0) return BEER_ERR_ARG;
     probe::read_kernel<<<kNumSMs * 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(src), bytes / 16, sink);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
+typedef CUresult (*ProbeEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int beer_probe_tma(const float* src, int64_t src_bytes, int mode, int chunk_bytes, int stages, int copies_per_sm,
+                   int issuers, void* stream) {
+    if (issuers < 1 || issuers > 8 || issuers > stages) return BEER_ERR_ARG;
+    if (!src || (mode != 0 && mode != 1) || chunk_bytes < 256 || chunk_bytes % 256 != 0 || stages < 1 || stages > 16 ||
+        (size_t)chunk_bytes * stages > 200 * 1024 || src_bytes < chunk_bytes || chunk_bytes / 256 > 256)
+        return BEER_ERR_ARG;
+    CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    if (mode == 1) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        BEER_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (fn == nullptr || q != cudaDriverEntryPointSuccess) return BEER_ERR_UNSUPPORTED;
+        const cuuint64_t gdim[2] = {64, (cuuint64_t)(src_bytes / 256)};
+        const cuuint64_t gstride[1] = {256};
+        const cuuint32_t box[2] = {64, (cuuint32_t)(chunk_bytes / 256)};
+        const cuuint32_t estr[2] = {1, 1};
+        if (reinterpret_cast<ProbeEncodeTiled>(fn)(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(src), gdim,
+                                                   gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return BEER_ERR_UNSUPPORTED;
+    }
+    const size_t smem = (size_t)chunk_bytes * stages + 1024;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == 0) {
+        BEER_CUDA_TRY(cudaFuncSetAttribute(probe::tma_read_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        probe::tma_read_kernel<0><<<kNumSMs, 256, smem, st>>>((const uint8_t*)src, src_bytes, chunk_bytes, stages, copies_per_sm, issuers, map);
+    } else {
+        BEER_CUDA_TRY(cudaFuncSetAttribute(probe::tma_read_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        probe::tma_read_kernel<1><<<kNumSMs, 256, smem, st>>>((const uint8_t*)src, src_bytes, chunk_bytes, stages, copies_per_sm, issuers, map);
+    }
     BEER_LAUNCH_CHECK();
     return BEER_OK;
 }

@@ -691,3 +691,17 @@ def probe_dram_gbs(mode, nbytes=4 << 30, reps=5):
             _lib.check(lib.beer_probe_fill(_p(buf), nbytes, m, _stream()), 'beer_probe_fill')
     t = _timed(run, reps)
     return nbytes / t / 1e9
+
+
+def probe_tma_gbs(mode, chunk_bytes, stages, src_mib=64, copies=2000, reps=3, issuers=1):
+    """Aggregate global -> shared copy-engine rate (GB/s over 148 SMs) from an L2-sized buffer."""
+    lib = require_cuda()
+    buf = torch.zeros(src_mib << 18, device='cuda', dtype=f32)
+    m = {'bulk': 0, 'tensor': 1}[mode]
+
+    def run():
+        _lib.check(lib.beer_probe_tma(_p(buf), buf.numel() * 4, m, int(chunk_bytes), int(stages), int(copies), int(issuers),
+                                      _stream()),
+                   'beer_probe_tma')
+    t = _timed(run, reps)
+    return 148 * copies * chunk_bytes / t / 1e9

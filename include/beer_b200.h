@@ -363,6 +363,11 @@ BEER_API int beer_probe_mma(int kind, int n_mma, double* flops_out_host, void* s
 /* Write-only stream over `bytes` of dst (128-byte aligned): mode 0 = float4 stores, 1 = 32 KB bulk copies
  * shared -> global (cp.async.bulk).  The DRAM write ceiling of an llh-producing kernel. */
 BEER_API int beer_probe_fill(float* dst, int64_t bytes, int mode, void* stream);
+/* Global -> shared copy-engine rate: one CTA per SM streams copies_per_sm chunks of chunk_bytes (multiple of 256) from
+ * src (src_bytes, meant to fit in L2) through `stages` shared-memory slots, issued by `issuers` threads (one per warp);
+ * mode 0 = cp.async.bulk, 1 = 2-D tensor map. */
+BEER_API int beer_probe_tma(const float* src, int64_t src_bytes, int mode, int chunk_bytes, int stages, int copies_per_sm,
+                   int issuers, void* stream);
 /* Read-only stream over `bytes` of src (float4 loads). */
 BEER_API int beer_probe_read(const float* src, int64_t bytes, float* sink, void* stream);
 

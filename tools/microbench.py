@@ -24,6 +24,17 @@ def main():
         out[f'mma_{kind}_tflops'] = [round(ops.probe_mma_tflops(kind, n_mma=n), 1) for n in (2000, 20000, 200000)]
     for mode in ('fill_st', 'fill_bulk', 'read'):
         out[f'dram_{mode}_gbs'] = round(ops.probe_dram_gbs(mode), 1)
+    if '--tma' in sys.argv:
+        out['tma_gbs'] = {}
+        for mode in ('bulk', 'tensor'):
+            for chunk, stages, issuers in ((4096, 1, 1), (4096, 8, 1), (4096, 8, 2), (4096, 8, 4), (4096, 16, 8), (16384, 1, 1),
+                                           (16384, 8, 1), (16384, 8, 2), (16384, 8, 4), (32768, 4, 1), (32768, 4, 2),
+                                           (32768, 4, 4), (65536, 3, 1), (65536, 3, 3)):
+                copies = max(240, (64 << 20) // chunk)
+                out['tma_gbs'][f'{mode}_{chunk}x{stages}i{issuers}'] = round(
+                    ops.probe_tma_gbs(mode, chunk, stages, copies=copies, issuers=issuers), 0)
+        out['tma_gbs_dram'] = {f'{mode}_32768x4': round(ops.probe_tma_gbs(mode, 32768, 4, src_mib=2048, copies=400), 0)
+                               for mode in ('bulk', 'tensor')}
     a = torch.empty(1 << 30, device='cuda', dtype=torch.float32)
     b = torch.empty_like(a)
     t = ops._timed(lambda: b.copy_(a), 5)
