@@ -72,6 +72,7 @@ SIGNATURES = {
                                                c_ptr, c_ptr, C.c_int64, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr, C.c_int64, c_ptr, c_ptr]),
     'beer_hmm_lpost_supported': (C.c_int, [c_ptr]),
     'beer_mix16_log2_posteriors': (C.c_int, [c_ptr, C.c_int64, C.c_int, C.c_int64, c_ptr, C.c_int64, c_ptr]),
+    'beer_mix16_set_trace': (None, [c_ptr]),
     'beer_mix16_supported': (C.c_int, [C.c_int, C.c_int, C.c_int]),
     'beer_mix16_geometry': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, c_ptr]),
     'beer_mix16_feature_images': (C.c_int, [c_ptr, C.c_int64, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
@@ -82,7 +83,8 @@ SIGNATURES = {
     'beer_mix16_accumulate': (C.c_int, [c_ptr, c_ptr, C.c_int64, C.c_int, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int,
                                         c_ptr, C.c_int64, c_ptr, C.c_int64, C.c_float, c_ptr, c_ptr]),
     'beer_probe_mma': (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), c_ptr]),
-    'beer_probe_tma': (C.c_int, [c_ptr, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr]),
+    'beer_probe_mma_shape': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), c_ptr]),
+    'beer_probe_tma': (C.c_int, [c_ptr, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr]),
     'beer_probe_fill': (C.c_int, [c_ptr, C.c_int64, C.c_int, c_ptr]),
     'beer_probe_read': (C.c_int, [c_ptr, C.c_int64, c_ptr, c_ptr]),
     'beer_path_posteriors': (C.c_int, [c_ptr, C.c_int64, c_ptr, C.c_float, c_ptr, C.c_int64, c_ptr, c_ptr,

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(THREADS, 1) accumulate_tc_kernel(Args a) {
 
     if (warp == PRODUCERS / 32) {
         // ------------------------------ MMA issuer -------------------------------
-        if (lane == 0 && n_tiles > 0) {
+        if (n_tiles > 0 && elect_one()) {
             // D = f32, A = B = tf32, both K-major (K = frames), N = NB, M = 128
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NB >> 3) << 17) |
                                    ((uint32_t)(GM >> 4) << 24);
@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(MODE == 1 ? MIX_THREADS : RAW_THREADS, 1) accu
                     rph ^= 1;
                 }
             }
-        } else if (lane == 0) {
+        } else if (elect_one()) {
             int rs = 0;
             uint32_t rph = 0;                      // ring position / pass parity (no runtime division)
             for (int it = 0; it < n_tiles; ++it) {
@@ -585,7 +585,7 @@ __global__ void __launch_bounds__(MODE == 1 ? MIX_THREADS : RAW_THREADS, 1) accu
         }
     } else if (warp == RAW_PRODUCERS / 32) {
         // ------------------------------ MMA issuer -------------------------------
-        if (lane == 0 && n_tiles > 0) {
+        if (n_tiles > 0 && elect_one()) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NB >> 3) << 17) |
                                    ((uint32_t)(GM >> 4) << 24);
             constexpr uint32_t LBO = 128, SBO = (KF / 4) * 128;

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(THREADS, 1) emission_tc_kernel(Args a, const _
 
     if (warp == LOAD_WARP) {
         // ------------------------- weight-image producer -------------------------
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t bytes = (uint32_t)b_stage_floats * 4u;
             if (a.stages == 1) {
                 // a single chunk stays resident for the whole kernel
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(THREADS, 1) emission_tc_kernel(Args a, const _
         }
     } else if (warp == MMA_WARP) {
         // ------------------------------ MMA issuer -------------------------------
-        if (lane == 0) {
+        if (elect_one()) {
             // instruction descriptor: D=f32, A=B=tf32, both K-major, N = NB, M = 128
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.NB >> 3) << 17) |
                                    ((uint32_t)(FR >> 4) << 24);
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(THREADS, 1) emission_tc_kernel(Args a, const _
             const int buf = it & 1;
             if (a.staged) {
                 // the previous tile's bulk store must have read the staging tile before it is rewritten
-                if (tid == 0) bulk_wait_read0();
+                if (warp == 0 && elect_one()) bulk_wait_read0();
                 asm volatile("bar.sync 1, %0;" ::"n"(WORKERS) : "memory");
             }
             mbar_wait(&bars->t_full[buf], (it >> 1) & 1);
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(THREADS, 1) emission_tc_kernel(Args a, const _
                 // one bulk (TMA) store of the whole tile instead of 128 strided row stores
                 fence_proxy_async();
                 asm volatile("bar.sync 1, %0;" ::"n"(WORKERS) : "memory");
-                if (tid == 0) {
+                if (warp == 0 && elect_one()) {
                     const int64_t rows = min((int64_t)FR, a.N - tile * FR);
                     bulk_s2g(a.pdf_llh + (size_t)tile * FR * a.Kp, s_out, (uint32_t)(rows * a.Kp * 4));
                     bulk_commit();
@@ -318,7 +318,8 @@ __global__ void __launch_bounds__(THREADS, 1) emission_tc_kernel(Args a, const _
             // boxes: 1024-byte aligned (the swizzle is a function of the address)
             uint8_t* s_box = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bars + 1) + 1023) & ~uintptr_t(1023)) +
                              (size_t)he * (FR * CBOX * 4);
-            const bool issuer = (warp & 3) == 0 && lane == 0;
+            bool issuer = false;                      // one lane of the first warp of each column half
+            if ((warp & 3) == 0) issuer = elect_one();
             if (issuer) bulk_wait_read0();            // the previous chunk's store has read the box
             asm volatile("bar.sync %0, 128;" ::"r"(1 + he) : "memory");
             mbar_wait(&bars->t_full[buf], (it >> 1) & 1);
@@ -400,7 +401,7 @@ __global__ void __launch_bounds__(THREADS, 1) emission_tc_kernel(Args a, const _
                 prev = tile;
             }
             if (prev >= 0) epilogue(prev, it - 1, 0);
-            if (a.staged && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            if (a.staged && warp == 0 && elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         } else {
             uint32_t it = 0, tile_it = 0;
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
@@ -415,7 +416,7 @@ __global__ void __launch_bounds__(THREADS, 1) emission_tc_kernel(Args a, const _
                 else
                     for (int c = 0; c < a.n_chunks; ++c, ++it) epilogue(tile, it, c);
             }
-            if (a.cstaged && (warp & 3) == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            if (a.cstaged && (warp & 3) == 0 && elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
     }
     tc_fence_before();

@@ -32,6 +32,12 @@ namespace mix16 {
 using namespace tcu;
 
 constexpr int TILE = 64;            // frames per image tile
+constexpr int TRACE_SLOTS = 8, TRACE_ITEMS = 256;     // per traced item (chunk / tile): 8 time stamps of CTA 0
+static unsigned long long* g_trace = nullptr;        // device buffer [TRACE_ITEMS][TRACE_SLOTS] or null (beer_mix16_set_trace)
+
+__device__ __forceinline__ void trace(unsigned long long* buf, uint32_t item, int slot) {
+    if (buf != nullptr && blockIdx.x == 0 && item < TRACE_ITEMS) buf[item * TRACE_SLOTS + slot] = clock64();
+}
 constexpr int HI_EXP = 12;          // scaled statistics: per-dimension maximum in [2^12, 2^13)
 constexpr int W_EXP = 13;           // scaled weights: per-Gaussian maximum in [2^13, 2^14)
 
@@ -259,6 +265,7 @@ struct KaArgs {
     int Kp, NB, n_chunks;
     float* llh2;
     int64_t ld;
+    unsigned long long* trace;
 };
 
 struct KaBarriers {
@@ -305,7 +312,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a) {
 
     if (warp >= KA_LOAD_WARP) {
         // one issuing thread per stream of copies (a thread sustains about one copy per 500 cycles)
-        if (lane == 0) {
+        if (elect_one()) {
             const int which = warp - KA_LOAD_WARP;
             uint32_t it = 0, tile_it = 0;
             const uint32_t half_bytes = TILE * KP * 2, b_bytes = (uint32_t)b_stage * 2u, k_bytes = (uint32_t)a.NB * 8u;
@@ -331,6 +338,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a) {
                     const int st = it & 1;
                     mbar_wait(&bars->b_empty[st], ((it >> 1) & 1) ^ 1);
                     if (which == 1) {
+                        trace(a.trace, it, 0);
                         mbar_arrive_expect_tx(&bars->b_full[st], b_bytes);
                         bulk_g2s(Bs + (size_t)st * b_stage, a.wimg + (size_t)c * b_stage, b_bytes, &bars->b_full[st]);
                     } else {
@@ -341,7 +349,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a) {
             }
         }
     } else if (warp == KA_MMA_WARP) {
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = (1u << 4) | ((uint32_t)(a.NB >> 3) << 17) | ((uint32_t)(FR >> 4) << 24);   // f16 x f16 -> f32
             uint32_t it = 0, tile_it = 0;
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
@@ -351,7 +359,9 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a) {
                 for (int c = 0; c < a.n_chunks; ++c, ++it) {
                     const int st = it & 1, buf = it & 1;
                     mbar_wait(&bars->b_full[st], (it >> 1) & 1);
+                    trace(a.trace, it, 1);
                     mbar_wait(&bars->t_empty[buf], ((it >> 1) & 1) ^ 1);
+                    trace(a.trace, it, 2);
                     tc_fence_after();
                     const uint32_t b_hi = smem_u32(Bs + (size_t)st * b_stage), b_lo = b_hi + (uint32_t)a.NB * KP * 2u;
                     const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256u;
@@ -366,6 +376,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a) {
                     }
                     umma_commit(&bars->t_full[buf]);
                     umma_commit(&bars->b_empty[st]);
+                    trace(a.trace, it, 3);
                 }
                 umma_commit(&bars->a_empty[ab]);
             }
@@ -385,6 +396,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a) {
             for (int c = 0; c < a.n_chunks; ++c, ++it) {
                 const int buf = it & 1;
                 mbar_wait(&bars->t_full[buf], (it >> 1) & 1);
+                if (lane == 0 && (warp == 0 || warp == 15)) trace(a.trace, it, warp == 0 ? 4 : 6);
                 tc_fence_after();
                 const float2* kk = s_k12 + (it & (K12_RING - 1)) * a.NB;
                 const uint32_t taddr = tmem_base + lane_addr + (uint32_t)buf * 256u;
@@ -431,6 +443,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a) {
                 }
                 tc_fence_before();
                 mbar_arrive(&bars->t_empty[buf]);
+                if (lane == 0 && (warp == 0 || warp == 15)) trace(a.trace, it, warp == 0 ? 5 : 7);
             }
         }
     }
@@ -487,6 +500,7 @@ struct KcArgs {
     int ns;                  // shared-memory stages (<= NS_MAX)
     double* acc;
     int D;
+    unsigned long long* trace;
 };
 
 struct KcBarriers {
@@ -577,7 +591,7 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
     if (warp >= KC_LOAD_WARP) {
         // ------------------------------ loaders (TMA) ------------------------------
         // four warps, one copy of the stage each (img1 tile, img2 tile, llh block, posterior block)
-        if (lane == 0) {
+        if (elect_one()) {
             const int which = warp - KC_LOAD_WARP;
             const uint32_t bytes = 2u * IMG_HALF * 2u;        // hi + lo of one image
             const int k0 = g0 / C;
@@ -587,6 +601,7 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
                 uint8_t* dst = smem_raw + (size_t)s * STAGE_BYTES;
                 const int t0 = (int)(f_begin + (int64_t)i * TILE);
                 if (which == 0) {
+                    trace(a.trace, i, 0);
                     mbar_arrive_expect_tx(&bars->st_full[s], bytes);
                     bulk_g2s(dst, a.img1 + (size_t)(tile0 + i) * (2 * IMG_HALF), bytes, &bars->st_full[s]);
                 } else if (which == 1) {
@@ -603,12 +618,13 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
         }
     } else if (warp == KC_MMA_WARP) {
         // ------------------------------ MMA issuer ---------------------------------
-        if (lane == 0 && n_tiles > 0) {
+        if (n_tiles > 0 && elect_one()) {
             const uint32_t idesc1 = (1u << 4) | ((uint32_t)(TILE >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
             const uint32_t idesc2 = (1u << 4) | ((uint32_t)(KP >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
             auto issue_g1 = [&](int i) {
                 const int s = i % NS, b = i % NSB;
                 mbar_wait(&bars->st_full[s], (i / NS) & 1);
+                trace(a.trace, i, 1);
                 tc_fence_after();
                 const uint32_t b_hi = smem_u32(smem_raw + (size_t)s * STAGE_BYTES), b_lo = b_hi + IMG_HALF * 2u;
                 const uint32_t d = tmem_base + COL_S + (uint32_t)b * TILE;
@@ -621,12 +637,14 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
                     umma_f16_ts(d, w_hi + 8u * ks, dbl, idesc1, 1);       // weights hi x statistics lo
                 }
                 umma_commit(&bars->s_full[b]);
+                trace(a.trace, i, 2);
             };
             auto issue_g2 = [&](int i) {
                 const int s = i % NS, b = i % NSB;
                 const int grp = i / DR, dbuf = grp & 1;
                 const bool first = (i % DR) == 0, last = (i % DR) == DR - 1 || i == n_tiles - 1;
                 mbar_wait(&bars->a2_full[b], (i / NSB) & 1);
+                trace(a.trace, i, 3);
                 if (first) mbar_wait(&bars->d2_empty[dbuf], ((grp >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t b_hi = smem_u32(smem_raw + (size_t)s * STAGE_BYTES) + 2u * IMG_HALF * 2u, b_lo = b_hi + IMG_HALF * 2u;
@@ -641,6 +659,7 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
                 }
                 umma_commit(&bars->st_empty[s]);        // the epilogue finished with the stage before a2_full completed
                 if (last) umma_commit(&bars->d2_full[dbuf]);
+                trace(a.trace, i, 4);
             };
             issue_g1(0);
             if (n_tiles > 1) issue_g1(1);
@@ -689,7 +708,9 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
         for (int i = 0; i < n_tiles; ++i) {
             const int s = i % NS, b = i % NSB;
             mbar_wait(&bars->st_full[s], (i / NS) & 1);          // the llh / posterior block of the tile (TMA)
+            if (tid == 0) trace(a.trace, i, 5);
             mbar_wait(&bars->s_full[b], (i / NSB) & 1);
+            if (tid == 0) trace(a.trace, i, 6);
             tc_fence_after();
             const uint32_t taddr = tmem_base + lane_addr + COL_S + (uint32_t)(b * TILE + part * 16);
             float v[16];
@@ -728,6 +749,7 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&bars->a2_full[b]);
+            if (tid == 0) trace(a.trace, i, 7);
             {
                 const float y = tsum - wcomp;
                 const float t = wsum + y;
@@ -852,6 +874,12 @@ using namespace beer;
 
 extern "C" {
 
+// Debug: device buffer of 256 x 8 time stamps (clock64 of CTA 0) filled by the next emission / statistics launches:
+// emission, per chunk: 0 weight copy issued, 1 weights landed, 2 accumulator free, 3 MMAs issued, 4/5 first epilogue warp
+// starts / ends, 6/7 last epilogue warp; statistics, per tile: 0 image copy issued, 1 stage landed (MMA thread), 2 first
+// MMAs issued, 3 responsibilities ready, 4 second MMAs issued, 5 stage landed (epilogue), 6 S ready, 7 epilogue done.
+void beer_mix16_set_trace(void* dev_buf) { mix16::g_trace = (unsigned long long*)dev_buf; }
+
 int beer_mix16_supported(int M, int D, int C) {
     if (M <= 0 || C <= 0 || M % C != 0) return 0;
     if (!(D == 20 || D == 40)) return 0;
@@ -928,7 +956,7 @@ int beer_mix16_emission(const void* img1, int64_t N, int D, const void* wimg, co
     a.img1 = (const __half*)img1; a.N = N; a.wimg = (const __half*)wimg; a.k12 = (const float2*)k12;
     a.Kp = M / C; a.NB = (int)sz[4];
     a.n_chunks = (M + a.NB - 1) / a.NB;
-    a.llh2 = llh2; a.ld = ld;
+    a.llh2 = llh2; a.ld = ld; a.trace = mix16::g_trace;
     const int KP = (int)sz[5];
     cudaStream_t st = (cudaStream_t)stream;
 #define BEER_KA_CASE(kp, c) \
@@ -959,7 +987,7 @@ int beer_mix16_accumulate(const void* img1, const void* img2, int64_t N, int D, 
     if (N == 0) return BEER_OK;
     mix16::KcArgs a;
     a.img1 = (const __half*)img1; a.img2 = (const __half*)img2; a.N = N; a.wtm = wtm; a.k12 = (const float2*)k12; a.alpha = alpha;
-    a.M = M; a.Kp = M / C; a.D = D; a.acc = acc_normal; a.ns = 0;
+    a.M = M; a.Kp = M / C; a.D = D; a.acc = acc_normal; a.ns = 0; a.trace = mix16::g_trace;
     a.n_gtiles = (M + mix16::GM - 1) / mix16::GM;
     // the posteriors carry `scale`: keep w 2^wexp <= 2^14 (fp16 overflows at 2^16)
     int e = 14;

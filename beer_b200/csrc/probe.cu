@@ -65,6 +65,61 @@ __global__ void __launch_bounds__(128, 1) mma_peak_kernel(int n_mma) {
     }
 }
 
+// tcgen05.mma kind::f16 rate as a function of the tile width N, the number of independent accumulators the k-steps
+// rotate over (n_acc = 1: every MMA accumulates onto the previous one), the number of distinct shared-memory operand
+// buffers (n_buf = 1: the same 12 KB over and over) and the A operand's home (a_tmem != 0: tensor memory).
+template <bool ELECT>
+__global__ void __launch_bounds__(128, 1) mma_shape_kernel(int n_mma, int N, int n_acc, int n_buf, int a_tmem) {
+    constexpr int M = 128;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int buf_bytes = (M + N) * 32;
+    for (int i = threadIdx.x; i < n_buf * buf_bytes / 16; i += blockDim.x)
+        reinterpret_cast<float4*>(smem_raw)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 32) tmem_alloc(&tmem_slot, 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (threadIdx.x < 32 && (ELECT ? elect_one() : threadIdx.x == 0)) {
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+        const uint32_t a_col = 496;       // 8 columns of A in tensor memory (contents irrelevant)
+        int acc = 0, buf = 0;
+        for (int i = 0; i < n_mma; ++i) {
+            const uint32_t base = smem_u32(smem_raw) + (uint32_t)(buf * buf_bytes);
+            const uint64_t da = make_desc(base, 128, 256), db = make_desc(base + M * 32, 128, 256);
+            const uint32_t d = tmem + (uint32_t)(acc * N);
+            if (a_tmem) {
+                asm volatile(
+                    "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}" ::"r"(d),
+                    "r"(tmem + a_col), "l"(db), "r"(idesc), "r"(1u)
+                    : "memory");
+            } else {
+                asm volatile(
+                    "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d),
+                    "l"(da), "l"(db), "r"(idesc), "r"(1u)
+                    : "memory");
+            }
+            if (++acc == n_acc) acc = 0;
+            if (++buf == n_buf) buf = 0;
+        }
+        umma_commit(&bar);
+        mbar_wait(&bar, 0);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
 __global__ void __launch_bounds__(256) fill_st_kernel(float4* __restrict__ dst, int64_t n4) {
     const float4 v = make_float4(1.f, 2.f, 3.f, 4.f);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x)
@@ -106,7 +161,7 @@ __global__ void __launch_bounds__(256) read_kernel(const float4* __restrict__ sr
 //   MODE 0: cp.async.bulk (1-D bulk copy, UBLKCP)     MODE 1: cp.async.bulk.tensor.2d (tensor map, UTMALDG)
 template <int MODE>
 __global__ void __launch_bounds__(256, 1) tma_read_kernel(const uint8_t* __restrict__ src, int64_t src_bytes, int chunk,
-                                                          int stages, int copies, int issuers,
+                                                          int stages, int copies, int issuers, int shared_walk,
                                                           const __grid_constant__ CUtensorMap map) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint64_t full[16];
@@ -119,7 +174,8 @@ __global__ void __launch_bounds__(256, 1) tma_read_kernel(const uint8_t* __restr
     if ((threadIdx.x & 31) == 0 && w < issuers) {
         // issuer w owns the slots s = w, w + issuers, ...
         const int64_t n_chunks = src_bytes / chunk;
-        int64_t pos = ((int64_t)blockIdx.x * 37 + (int64_t)w * 1009) % n_chunks;
+        // issuers > 0: every SM walks its own part of the buffer; the caller passes stages < 0 ... (see `shared_walk`)
+        int64_t pos = shared_walk ? ((int64_t)w * 1009) % n_chunks : ((int64_t)blockIdx.x * 37 + (int64_t)w * 1009) % n_chunks;
         const int my_stages = (stages - w + issuers - 1) / issuers, my_copies = copies / issuers;
         for (int i = 0; i < my_copies + my_stages; ++i) {
             const int s = w + (i % my_stages) * issuers;
@@ -160,6 +216,23 @@ int beer_probe_mma(int kind, int n_mma, double* flops_out, void* stream) {
     return BEER_OK;
 }
 
+int beer_probe_mma_shape(int n_mma, int N, int n_acc, int n_buf, int a_tmem, int elect, double* flops_out, void* stream) {
+    if (n_mma <= 0 || N < 16 || N > 256 || N % 16 != 0 || n_acc < 1 || n_acc * N > 480 || n_buf < 1 ||
+        (size_t)n_buf * (128 + N) * 32 > 200 * 1024)
+        return BEER_ERR_ARG;
+    const size_t smem = (size_t)n_buf * (128 + N) * 32 + 1024;
+    if (elect) {
+        BEER_CUDA_TRY(cudaFuncSetAttribute(probe::mma_shape_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        probe::mma_shape_kernel<true><<<kNumSMs, 128, smem, (cudaStream_t)stream>>>(n_mma, N, n_acc, n_buf, a_tmem);
+    } else {
+        BEER_CUDA_TRY(cudaFuncSetAttribute(probe::mma_shape_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        probe::mma_shape_kernel<false><<<kNumSMs, 128, smem, (cudaStream_t)stream>>>(n_mma, N, n_acc, n_buf, a_tmem);
+    }
+    BEER_LAUNCH_CHECK();
+    if (flops_out) *flops_out = (double)kNumSMs * (double)n_mma * 2.0 * 128.0 * (double)N * 16.0;
+    return BEER_OK;
+}
+
 int beer_probe_fill(float* dst, int64_t bytes, int mode, void* stream) {
     if (!dst || bytes <= 0 || (((uintptr_t)dst) & 127) != 0) return BEER_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
@@ -192,7 +265,7 @@ typedef CUresult (*ProbeEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32
                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 int beer_probe_tma(const float* src, int64_t src_bytes, int mode, int chunk_bytes, int stages, int copies_per_sm,
-                   int issuers, void* stream) {
+                   int issuers, int shared_walk, void* stream) {
     if (issuers < 1 || issuers > 8 || issuers > stages) return BEER_ERR_ARG;
     if (!src || (mode != 0 && mode != 1) || chunk_bytes < 256 || chunk_bytes % 256 != 0 || stages < 1 || stages > 16 ||
         (size_t)chunk_bytes * stages > 200 * 1024 || src_bytes < chunk_bytes || chunk_bytes / 256 > 256)
@@ -218,10 +291,10 @@ int beer_probe_tma(const float* src, int64_t src_bytes, int mode, int chunk_byte
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == 0) {
         BEER_CUDA_TRY(cudaFuncSetAttribute(probe::tma_read_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        probe::tma_read_kernel<0><<<kNumSMs, 256, smem, st>>>((const uint8_t*)src, src_bytes, chunk_bytes, stages, copies_per_sm, issuers, map);
+        probe::tma_read_kernel<0><<<kNumSMs, 256, smem, st>>>((const uint8_t*)src, src_bytes, chunk_bytes, stages, copies_per_sm, issuers, shared_walk, map);
     } else {
         BEER_CUDA_TRY(cudaFuncSetAttribute(probe::tma_read_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        probe::tma_read_kernel<1><<<kNumSMs, 256, smem, st>>>((const uint8_t*)src, src_bytes, chunk_bytes, stages, copies_per_sm, issuers, map);
+        probe::tma_read_kernel<1><<<kNumSMs, 256, smem, st>>>((const uint8_t*)src, src_bytes, chunk_bytes, stages, copies_per_sm, issuers, shared_walk, map);
     }
     BEER_LAUNCH_CHECK();
     return BEER_OK;

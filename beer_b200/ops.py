@@ -693,7 +693,7 @@ def probe_dram_gbs(mode, nbytes=4 << 30, reps=5):
     return nbytes / t / 1e9
 
 
-def probe_tma_gbs(mode, chunk_bytes, stages, src_mib=64, copies=2000, reps=3, issuers=1):
+def probe_tma_gbs(mode, chunk_bytes, stages, src_mib=64, copies=2000, reps=3, issuers=1, shared_walk=False):
     """Aggregate global -> shared copy-engine rate (GB/s over 148 SMs) from an L2-sized buffer."""
     lib = require_cuda()
     buf = torch.zeros(src_mib << 18, device='cuda', dtype=f32)
@@ -701,7 +701,19 @@ def probe_tma_gbs(mode, chunk_bytes, stages, src_mib=64, copies=2000, reps=3, is
 
     def run():
         _lib.check(lib.beer_probe_tma(_p(buf), buf.numel() * 4, m, int(chunk_bytes), int(stages), int(copies), int(issuers),
-                                      _stream()),
+                                      int(bool(shared_walk)), _stream()),
                    'beer_probe_tma')
     t = _timed(run, reps)
     return 148 * copies * chunk_bytes / t / 1e9
+
+
+def probe_mma_shape_cycles(N, n_acc, n_buf, a_tmem, elect=True, n_mma=20000, reps=3, mhz=1965.0):
+    """Average cycles per tcgen05.mma (kind::f16, M = 128, width N, one k-step) at `mhz`."""
+    lib = require_cuda()
+    flops = C.c_double(0.0)
+
+    def run():
+        _lib.check(lib.beer_probe_mma_shape(int(n_mma), int(N), int(n_acc), int(n_buf), int(bool(a_tmem)), int(bool(elect)),
+                                            C.byref(flops), _stream()), 'beer_probe_mma_shape')
+    t = _timed(run, reps)
+    return t / n_mma * mhz * 1e6

@@ -325,6 +325,8 @@ BEER_API int beer_hmm_forward_backward_ex(const beer_graph_plan* plan, const flo
  * ---------------------------------------------------------------------- */
 
 BEER_API int beer_mix16_supported(int M, int D, int C);
+/* Debug: 256 x 8 uint64 time stamps (clock64 of CTA 0) per chunk / tile of the following mix16 launches; NULL = off. */
+BEER_API void beer_mix16_set_trace(void* dev_buf);
 /* sizes_host[6] = {halfs of img1 (= of img2) for N frames, halfs of wimg, 32-bit words of wtm, floats of k12,
  * Gaussians per emission chunk, padded statistics width KP}. */
 BEER_API int beer_mix16_geometry(int M, int D, int C, int64_t N, int64_t* sizes_host);
@@ -360,14 +362,19 @@ BEER_API int beer_mix16_log2_posteriors(const float* pdf_post, int64_t N, int Kp
 /* n_mma back-to-back tcgen05.mma (M = 128, N = 256, one k-step) per SM on resident operands: the dispatch-limited
  * tensor-pipe peak of MMA kind 0 = tf32 (K = 8) or 1 = f16 (K = 16).  *flops_out_host = flops issued by the launch. */
 BEER_API int beer_probe_mma(int kind, int n_mma, double* flops_out_host, void* stream);
+/* kind::f16 MMAs of width N (M = 128, one k-step each) rotating over n_acc accumulators and n_buf operand buffers, A in
+ * shared memory or (a_tmem != 0) tensor memory, issued under elect.sync (elect != 0) or under `lane == 0`: how tile width, accumulation chains and operand fetch pace the pipe. */
+BEER_API int beer_probe_mma_shape(int n_mma, int N, int n_acc, int n_buf, int a_tmem, int elect, double* flops_out_host,
+                         void* stream);
 /* Write-only stream over `bytes` of dst (128-byte aligned): mode 0 = float4 stores, 1 = 32 KB bulk copies
  * shared -> global (cp.async.bulk).  The DRAM write ceiling of an llh-producing kernel. */
 BEER_API int beer_probe_fill(float* dst, int64_t bytes, int mode, void* stream);
 /* Global -> shared copy-engine rate: one CTA per SM streams copies_per_sm chunks of chunk_bytes (multiple of 256) from
  * src (src_bytes, meant to fit in L2) through `stages` shared-memory slots, issued by `issuers` threads (one per warp);
- * mode 0 = cp.async.bulk, 1 = 2-D tensor map. */
+ * mode 0 = cp.async.bulk, 1 = 2-D tensor map; shared_walk != 0 = every SM reads the SAME chunks in the same order
+ * (what CTAs streaming a common operand do) instead of its own part of the buffer. */
 BEER_API int beer_probe_tma(const float* src, int64_t src_bytes, int mode, int chunk_bytes, int stages, int copies_per_sm,
-                   int issuers, void* stream);
+                   int issuers, int shared_walk, void* stream);
 /* Read-only stream over `bytes` of src (float4 loads). */
 BEER_API int beer_probe_read(const float* src, int64_t bytes, float* sink, void* stream);
 

@@ -24,6 +24,16 @@ def main():
         out[f'mma_{kind}_tflops'] = [round(ops.probe_mma_tflops(kind, n_mma=n), 1) for n in (2000, 20000, 200000)]
     for mode in ('fill_st', 'fill_bulk', 'read'):
         out[f'dram_{mode}_gbs'] = round(ops.probe_dram_gbs(mode), 1)
+    if '--mma' in sys.argv:
+        out['mma_cycles'] = {}
+        for N in (64, 80, 160, 256):
+            for n_acc in (1, 2):
+                if n_acc * N > 480:
+                    continue
+                for a_tmem in (0, 1):
+                    for elect in (0, 1):
+                        out['mma_cycles'][f'N{N}_acc{n_acc}_{"ts" if a_tmem else "ss"}_{"elect" if elect else "lane0"}'] = round(
+                            ops.probe_mma_shape_cycles(N, n_acc, 8, a_tmem, elect), 1)
     if '--tma' in sys.argv:
         out['tma_gbs'] = {}
         for mode in ('bulk', 'tensor'):
@@ -33,6 +43,11 @@ def main():
                 copies = max(240, (64 << 20) // chunk)
                 out['tma_gbs'][f'{mode}_{chunk}x{stages}i{issuers}'] = round(
                     ops.probe_tma_gbs(mode, chunk, stages, copies=copies, issuers=issuers), 0)
+        out['tma_gbs_shared_walk'] = {
+            f'bulk_{chunk}x{stages}i{issuers}': round(ops.probe_tma_gbs('bulk', chunk, stages, src_mib=mib, copies=copies,
+                                                                        issuers=issuers, shared_walk=True), 0)
+            for chunk, stages, issuers, mib, copies in ((16384, 8, 4, 64, 4096), (32768, 4, 2, 64, 2048), (49152, 4, 2, 3, 1400),
+                                                        (49152, 2, 1, 3, 1400), (20480, 8, 4, 64, 3000))}
         out['tma_gbs_dram'] = {f'{mode}_32768x4': round(ops.probe_tma_gbs(mode, 32768, 4, src_mib=2048, copies=400), 0)
                                for mode in ('bulk', 'tensor')}
     a = torch.empty(1 << 30, device='cuda', dtype=torch.float32)
