@@ -22,6 +22,7 @@
 // Reference semantics: beer/dists/normalgamma.py:55-59, beer/models/mixtureset.py:85-112, normalset.py:121-123.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <type_traits>
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "../../include/beer_b200.h"
@@ -84,6 +85,39 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// balanced reductions (a serial chain of 7 dependent max / add operations per pdf was what the epilogue waited on)
+template <int N>
+__device__ __forceinline__ float tree_max(const float* v) {
+    if constexpr (N == 1) return v[0];
+    else return fmaxf(tree_max<N / 2>(v), tree_max<N - N / 2>(v + N / 2));
+}
+template <int N>
+__device__ __forceinline__ float tree_sum(const float* v) {
+    if constexpr (N == 1) return v[0];
+    else return tree_sum<N / 2>(v) + tree_sum<N - N / 2>(v + N / 2);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -365,14 +399,14 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a) {
                     tc_fence_after();
                     const uint32_t b_hi = smem_u32(Bs + (size_t)st * b_stage), b_lo = b_hi + (uint32_t)a.NB * KP * 2u;
                     const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256u;
-#pragma unroll 1
+                    // descriptors of k-step s = the first one + 16 s (256 bytes >> 4): additions on the uniform datapath
+                    const uint64_t dah = make_desc(a_hi, LBO, SBO), dal = make_desc(a_lo, LBO, SBO);
+                    const uint64_t dbh = make_desc(b_hi, LBO, SBO), dbl = make_desc(b_lo, LBO, SBO);
+#pragma unroll
                     for (int s = 0; s < KSTEPS; ++s) {
-                        const uint32_t ko = (uint32_t)s * 256u;
-                        const uint64_t dah = make_desc(a_hi + ko, LBO, SBO), dal = make_desc(a_lo + ko, LBO, SBO);
-                        const uint64_t dbh = make_desc(b_hi + ko, LBO, SBO), dbl = make_desc(b_lo + ko, LBO, SBO);
-                        umma_f16_ss(d_tmem, dah, dbh, idesc, s > 0);
-                        umma_f16_ss(d_tmem, dah, dbl, idesc, 1);      // statistics hi x weights lo
-                        umma_f16_ss(d_tmem, dal, dbh, idesc, 1);      // statistics lo x weights hi
+                        umma_f16_ss(d_tmem, dah + 16u * s, dbh + 16u * s, idesc, s > 0);
+                        umma_f16_ss(d_tmem, dah + 16u * s, dbl + 16u * s, idesc, 1);      // statistics hi x weights lo
+                        umma_f16_ss(d_tmem, dal + 16u * s, dbh + 16u * s, idesc, 1);      // statistics lo x weights hi
                     }
                     umma_commit(&bars->t_full[buf]);
                     umma_commit(&bars->b_empty[st]);
@@ -400,47 +434,46 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a) {
                 tc_fence_after();
                 const float2* kk = s_k12 + (it & (K12_RING - 1)) * a.NB;
                 const uint32_t taddr = tmem_base + lane_addr + (uint32_t)buf * 256u;
-                for (int u = u0; u < u1; ++u) {
+                // G units at a time: all their TMEM loads in flight together, independent max / exp / sum chains
+                auto process = [&](int u, auto gtag) {
+                    constexpr int G = decltype(gtag)::value;
                     const int p = u * UNIT;
-                    float v[UNIT];
-                    if constexpr (UNIT == 8) {
-                        uint32_t rr[8];
-                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                                     : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]),
-                                       "=r"(rr[7])
-                                     : "r"(taddr + (uint32_t)p)
-                                     : "memory");
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    float v[G * UNIT];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(rr[i]);
-                    } else {
-                        tmem_ld16(taddr + (uint32_t)p, v);
+                    for (int g = 0; g < G; ++g) {
+                        if constexpr (UNIT == 8) tmem_ld8_nowait(taddr + (uint32_t)(p + g * UNIT), v + g * UNIT);
+                        else tmem_ld16_nowait(taddr + (uint32_t)(p + g * UNIT), v + g * UNIT);
                     }
+                    tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < UNIT; i += 2) {
+                    for (int i = 0; i < G * UNIT; i += 2) {
                         const float4 k = *reinterpret_cast<const float4*>(kk + p + i);      // (k1, k2) of two columns
                         v[i] = fmaf(v[i], k.x, k.y);
                         v[i + 1] = fmaf(v[i + 1], k.z, k.w);
                     }
-                    float o[PPU];
+                    float o[G * PPU];
 #pragma unroll
-                    for (int k = 0; k < PPU; ++k) {
-                        float m = v[k * C];
-#pragma unroll
-                        for (int j = 1; j < C; ++j) m = fmaxf(m, v[k * C + j]);
+                    for (int k = 0; k < G * PPU; ++k) {
+                        const float m = tree_max<C>(v + k * C);
                         const float ms = (m == kNegInf) ? 0.f : m;
-                        float sm = 0.f;
 #pragma unroll
-                        for (int j = 0; j < C; ++j) sm += ex2(v[k * C + j] - ms);
-                        o[k] = ms + lg2(sm);
+                        for (int j = 0; j < C; ++j) v[k * C + j] = ex2(v[k * C + j] - ms);
+                        o[k] = ms + lg2(tree_sum<C>(v + k * C));
                     }
                     if (valid) {
                         const int k0 = (c * a.NB + p) / C;
 #pragma unroll
-                        for (int k = 0; k < PPU; ++k)
+                        for (int k = 0; k < G * PPU; ++k)
                             if (k0 + k < a.Kp) orow[k0 + k] = o[k];
                     }
+                };
+                int u = u0;
+                for (; u + 4 <= u1; u += 4) process(u, std::integral_constant<int, 4>());
+                if (u + 2 <= u1) {
+                    process(u, std::integral_constant<int, 2>());
+                    u += 2;
                 }
+                if (u < u1) process(u, std::integral_constant<int, 1>());
                 tc_fence_before();
                 mbar_arrive(&bars->t_empty[buf]);
                 if (lane == 0 && (warp == 0 || warp == 15)) trace(a.trace, it, warp == 0 ? 5 : 7);
@@ -481,9 +514,9 @@ static int launch_ka(const KaArgs& a, cudaStream_t st) {
 constexpr int GM = 128;                  // Gaussians per CTA (UMMA M, TMEM lanes)
 constexpr int EPI = 512;                 // 16 epilogue warps: 4 per TMEM lane quarter, each a quarter of the 64 frames
 constexpr int KC_MMA_WARP = EPI / 32, KC_LOAD_WARP = KC_MMA_WARP + 1;
-constexpr int KC_LOADERS = 4;            // one issuing thread per copy of a stage: a thread sustains ~1 copy / 500 cycles
+constexpr int KC_LOADERS = 4;            // one issuing thread per copy stream
 constexpr int KC_THREADS = EPI + 32 + 32 * KC_LOADERS;
-constexpr int NS_MAX = 4;                // shared-memory stages (one 64-frame tile: both images + its llh / posterior block)
+constexpr int RING_MAX = 8;              // upper bound of either shared-memory ring
 constexpr int NSB = 3;                   // S^T / A2 buffers in tensor memory
 constexpr int DR = 4;                    // tiles per drain of the statistics accumulator (48 truncating accumulations)
 
@@ -497,14 +530,15 @@ struct KcArgs {
     int M, Kp, n_gtiles;
     int64_t frames_per_cta;  // multiple of TILE
     float wexp;              // w is carried as w 2^wexp (top of the fp16 range)
-    int ns;                  // shared-memory stages (<= NS_MAX)
+    int na, nb;              // depth of the two shared-memory rings
     double* acc;
     int D;
     unsigned long long* trace;
 };
 
 struct KcBarriers {
-    uint64_t st_full[NS_MAX], st_empty[NS_MAX];
+    uint64_t a_full[RING_MAX], a_empty[RING_MAX];     // ring A: img1 tiles (first MMA), freed as soon as S^T is computed
+    uint64_t b_full[RING_MAX], b_empty[RING_MAX];     // ring B: img2 tile + llh / posterior blocks (epilogue, second MMA)
     uint64_t s_full[NSB], a2_full[NSB];
     uint64_t d2_full[2], d2_empty[2];
     uint32_t tmem_base;
@@ -519,6 +553,19 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
         : "memory");
 }
 
+// ring position + pass parity without divisions
+struct Ring {
+    int pos, n;
+    uint32_t phase;
+    __device__ __forceinline__ Ring(int n_) : pos(0), n(n_), phase(0) {}
+    __device__ __forceinline__ void next() {
+        if (++pos == n) {
+            pos = 0;
+            phase ^= 1;
+        }
+    }
+};
+
 // map_l2 / map_lp: [N, Kp] fp32 arrays (log2 pdf llhs of KA16, log2 pdf posteriors of the forward-backward), boxes of
 // [TILE frames x GM / C pdfs]; rows past N and columns past Kp arrive as zeros.
 template <int KP, int C>
@@ -529,15 +576,17 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
     constexpr int IMG_HALF = TILE * KP;                // halfs of one image half-tile
     constexpr int NK = GM / C;                         // pdfs of a Gaussian tile
     constexpr int RAW_FLOATS = TILE * NK;              // one [frame][pdf] block
-    constexpr int STAGE_BYTES = 4 * IMG_HALF * 2 + 2 * RAW_FLOATS * 4;    // img1 hi | lo | img2 hi | lo | llh2 | lpost
+    constexpr int STAGE_A = 2 * IMG_HALF * 2;          // img1 hi | lo
+    constexpr int STAGE_B = 2 * IMG_HALF * 2 + 2 * RAW_FLOATS * 4;    // img2 hi | lo | llh2 | lpost
     constexpr uint32_t COL_W = 0, COL_S = KP, COL_D2 = KP + NSB * TILE;     // tensor-memory columns
     static_assert(COL_D2 + 2 * KP <= 512, "tensor memory");
-    static_assert(STAGE_BYTES % 128 == 0, "stage alignment");
+    static_assert(STAGE_A % 128 == 0 && STAGE_B % 128 == 0, "stage alignment");
     constexpr int NCH = KP / 4;                        // 4-column chunks of the accumulator
     constexpr int MYCH = (NCH + 3) / 4;                // per thread (four warps share a lane quarter)
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    const int NS = a.ns;
-    KcBarriers* bars = reinterpret_cast<KcBarriers*>(smem_raw + (size_t)NS * STAGE_BYTES);
+    uint8_t* ring_a = smem_raw;
+    uint8_t* ring_b = smem_raw + (size_t)a.na * STAGE_A;
+    KcBarriers* bars = reinterpret_cast<KcBarriers*>(ring_b + (size_t)a.nb * STAGE_B);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int gtile = blockIdx.x % a.n_gtiles;
@@ -548,9 +597,11 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
     const int64_t tile0 = f_begin / TILE;
 
     if (tid == 0) {
-        for (int i = 0; i < NS_MAX; ++i) {
-            mbar_init(&bars->st_full[i], KC_LOADERS);
-            mbar_init(&bars->st_empty[i], 1);
+        for (int i = 0; i < RING_MAX; ++i) {
+            mbar_init(&bars->a_full[i], 1);
+            mbar_init(&bars->a_empty[i], 1);
+            mbar_init(&bars->b_full[i], KC_LOADERS - 1);
+            mbar_init(&bars->b_empty[i], 1);
         }
         for (int i = 0; i < NSB; ++i) {
             mbar_init(&bars->s_full[i], 1);
@@ -590,29 +641,33 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
 
     if (warp >= KC_LOAD_WARP) {
         // ------------------------------ loaders (TMA) ------------------------------
-        // four warps, one copy of the stage each (img1 tile, img2 tile, llh block, posterior block)
+        // four warps, one copy stream each: img1 tiles -> ring A; img2 tiles, llh blocks, posterior blocks -> ring B
         if (elect_one()) {
             const int which = warp - KC_LOAD_WARP;
-            const uint32_t bytes = 2u * IMG_HALF * 2u;        // hi + lo of one image
+            const uint32_t bytes = STAGE_A;                   // hi + lo of one image
             const int k0 = g0 / C;
-            for (int i = 0; i < n_tiles; ++i) {
-                const int s = i % NS;
-                mbar_wait(&bars->st_empty[s], ((i / NS) & 1) ^ 1);
-                uint8_t* dst = smem_raw + (size_t)s * STAGE_BYTES;
+            Ring r(which == 0 ? a.na : a.nb);
+            for (int i = 0; i < n_tiles; ++i, r.next()) {
                 const int t0 = (int)(f_begin + (int64_t)i * TILE);
                 if (which == 0) {
+                    mbar_wait(&bars->a_empty[r.pos], r.phase ^ 1);
                     trace(a.trace, i, 0);
-                    mbar_arrive_expect_tx(&bars->st_full[s], bytes);
-                    bulk_g2s(dst, a.img1 + (size_t)(tile0 + i) * (2 * IMG_HALF), bytes, &bars->st_full[s]);
-                } else if (which == 1) {
-                    mbar_arrive_expect_tx(&bars->st_full[s], bytes);
-                    bulk_g2s(dst + bytes, a.img2 + (size_t)(tile0 + i) * (2 * IMG_HALF), bytes, &bars->st_full[s]);
+                    mbar_arrive_expect_tx(&bars->a_full[r.pos], bytes);
+                    bulk_g2s(ring_a + (size_t)r.pos * STAGE_A, a.img1 + (size_t)(tile0 + i) * (2 * IMG_HALF), bytes,
+                             &bars->a_full[r.pos]);
+                    continue;
+                }
+                mbar_wait(&bars->b_empty[r.pos], r.phase ^ 1);
+                uint8_t* dst = ring_b + (size_t)r.pos * STAGE_B;
+                if (which == 1) {
+                    mbar_arrive_expect_tx(&bars->b_full[r.pos], bytes);
+                    bulk_g2s(dst, a.img2 + (size_t)(tile0 + i) * (2 * IMG_HALF), bytes, &bars->b_full[r.pos]);
                 } else if (which == 2) {
-                    mbar_arrive_expect_tx(&bars->st_full[s], RAW_FLOATS * 4u);
-                    tma_load_2d(dst + 2 * bytes, &map_l2, k0, t0, &bars->st_full[s]);
+                    mbar_arrive_expect_tx(&bars->b_full[r.pos], RAW_FLOATS * 4u);
+                    tma_load_2d(dst + bytes, &map_l2, k0, t0, &bars->b_full[r.pos]);
                 } else {
-                    mbar_arrive_expect_tx(&bars->st_full[s], RAW_FLOATS * 4u);
-                    tma_load_2d(dst + 2 * bytes + RAW_FLOATS * 4, &map_lp, k0, t0, &bars->st_full[s]);
+                    mbar_arrive_expect_tx(&bars->b_full[r.pos], RAW_FLOATS * 4u);
+                    tma_load_2d(dst + bytes + RAW_FLOATS * 4, &map_lp, k0, t0, &bars->b_full[r.pos]);
                 }
             }
         }
@@ -621,45 +676,55 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
         if (n_tiles > 0 && elect_one()) {
             const uint32_t idesc1 = (1u << 4) | ((uint32_t)(TILE >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
             const uint32_t idesc2 = (1u << 4) | ((uint32_t)(KP >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
+            const uint32_t w_hi = tmem_base + COL_W, w_lo = w_hi + KP / 2;
+            Ring ra(a.na), rb(a.nb);
+            int b1 = 0, b2 = 0;                      // S^T buffer of the next first / second MMA
+            uint32_t ph1 = 0, ph2 = 0;
             auto issue_g1 = [&](int i) {
-                const int s = i % NS, b = i % NSB;
-                mbar_wait(&bars->st_full[s], (i / NS) & 1);
+                mbar_wait(&bars->a_full[ra.pos], ra.phase);
                 trace(a.trace, i, 1);
                 tc_fence_after();
-                const uint32_t b_hi = smem_u32(smem_raw + (size_t)s * STAGE_BYTES), b_lo = b_hi + IMG_HALF * 2u;
-                const uint32_t d = tmem_base + COL_S + (uint32_t)b * TILE;
-                const uint32_t w_hi = tmem_base + COL_W, w_lo = w_hi + KP / 2;
-#pragma unroll 1
+                const uint32_t base = smem_u32(ring_a + (size_t)ra.pos * STAGE_A);
+                const uint64_t dbh = make_desc(base, 128, KP * 16), dbl = make_desc(base + IMG_HALF * 2u, 128, KP * 16);
+                const uint32_t d = tmem_base + COL_S + (uint32_t)b1 * TILE;
+#pragma unroll
                 for (int ks = 0; ks < KS1; ++ks) {
-                    const uint64_t dbh = make_desc(b_hi + ks * 256u, 128, KP * 16), dbl = make_desc(b_lo + ks * 256u, 128, KP * 16);
-                    umma_f16_ts(d, w_hi + 8u * ks, dbh, idesc1, ks > 0);
-                    umma_f16_ts(d, w_lo + 8u * ks, dbh, idesc1, 1);       // weights lo x statistics hi
-                    umma_f16_ts(d, w_hi + 8u * ks, dbl, idesc1, 1);       // weights hi x statistics lo
+                    umma_f16_ts(d, w_hi + 8u * ks, dbh + 16u * ks, idesc1, ks > 0);
+                    umma_f16_ts(d, w_lo + 8u * ks, dbh + 16u * ks, idesc1, 1);       // weights lo x statistics hi
+                    umma_f16_ts(d, w_hi + 8u * ks, dbl + 16u * ks, idesc1, 1);       // weights hi x statistics lo
                 }
-                umma_commit(&bars->s_full[b]);
+                umma_commit(&bars->s_full[b1]);
+                umma_commit(&bars->a_empty[ra.pos]);          // img1 tile free: its loader runs ahead of the epilogue
                 trace(a.trace, i, 2);
+                ra.next();
+                if (++b1 == NSB) b1 = 0;
+                (void)ph1;
             };
             auto issue_g2 = [&](int i) {
-                const int s = i % NS, b = i % NSB;
                 const int grp = i / DR, dbuf = grp & 1;
                 const bool first = (i % DR) == 0, last = (i % DR) == DR - 1 || i == n_tiles - 1;
-                mbar_wait(&bars->a2_full[b], (i / NSB) & 1);
+                mbar_wait(&bars->a2_full[b2], ph2);
                 trace(a.trace, i, 3);
                 if (first) mbar_wait(&bars->d2_empty[dbuf], ((grp >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t b_hi = smem_u32(smem_raw + (size_t)s * STAGE_BYTES) + 2u * IMG_HALF * 2u, b_lo = b_hi + IMG_HALF * 2u;
+                const uint32_t base = smem_u32(ring_b + (size_t)rb.pos * STAGE_B);
+                const uint64_t dbh = make_desc(base, 128, 1024), dbl = make_desc(base + IMG_HALF * 2u, 128, 1024);
                 const uint32_t d = tmem_base + COL_D2 + (uint32_t)dbuf * KP;
-                const uint32_t a2 = tmem_base + COL_S + (uint32_t)b * TILE;
-#pragma unroll 1
+                const uint32_t a2 = tmem_base + COL_S + (uint32_t)b2 * TILE;
+#pragma unroll
                 for (int ks = 0; ks < KS2; ++ks) {
-                    const uint64_t dbh = make_desc(b_hi + ks * 256u, 128, 1024), dbl = make_desc(b_lo + ks * 256u, 128, 1024);
-                    umma_f16_ts(d, a2 + 16u * ks, dbh, idesc2, !(first && ks == 0));
-                    umma_f16_ts(d, a2 + 16u * ks + 8u, dbh, idesc2, 1);   // w lo x statistics hi
-                    umma_f16_ts(d, a2 + 16u * ks, dbl, idesc2, 1);        // w hi x statistics lo
+                    umma_f16_ts(d, a2 + 16u * ks, dbh + 16u * ks, idesc2, !(first && ks == 0));
+                    umma_f16_ts(d, a2 + 16u * ks + 8u, dbh + 16u * ks, idesc2, 1);   // w lo x statistics hi
+                    umma_f16_ts(d, a2 + 16u * ks, dbl + 16u * ks, idesc2, 1);        // w hi x statistics lo
                 }
-                umma_commit(&bars->st_empty[s]);        // the epilogue finished with the stage before a2_full completed
+                umma_commit(&bars->b_empty[rb.pos]);    // the epilogue finished with the stage before a2_full completed
                 if (last) umma_commit(&bars->d2_full[dbuf]);
                 trace(a.trace, i, 4);
+                rb.next();
+                if (++b2 == NSB) {
+                    b2 = 0;
+                    ph2 ^= 1;
+                }
             };
             issue_g1(0);
             if (n_tiles > 1) issue_g1(1);
@@ -705,18 +770,19 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
             mbar_arrive(&bars->d2_empty[dbuf]);
         };
 
+        Ring rb(a.nb);
+        int b = 0;
+        uint32_t phs = 0;
         for (int i = 0; i < n_tiles; ++i) {
-            const int s = i % NS, b = i % NSB;
-            mbar_wait(&bars->st_full[s], (i / NS) & 1);          // the llh / posterior block of the tile (TMA)
+            mbar_wait(&bars->b_full[rb.pos], rb.phase);          // the llh / posterior blocks of the tile (TMA)
             if (tid == 0) trace(a.trace, i, 5);
-            mbar_wait(&bars->s_full[b], (i / NSB) & 1);
+            mbar_wait(&bars->s_full[b], phs);
             if (tid == 0) trace(a.trace, i, 6);
             tc_fence_after();
             const uint32_t taddr = tmem_base + lane_addr + COL_S + (uint32_t)(b * TILE + part * 16);
             float v[16];
             tmem_ld16(taddr, v);
-            const float* rl2 = reinterpret_cast<const float*>(smem_raw + (size_t)s * STAGE_BYTES + 4 * IMG_HALF * 2) +
-                               part * 16 * NK + pl;
+            const float* rl2 = reinterpret_cast<const float*>(ring_b + (size_t)rb.pos * STAGE_B + STAGE_A) + part * 16 * NK + pl;
             const float* rlp = rl2 + RAW_FLOATS;
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
@@ -730,14 +796,14 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
                 for (int e = 0; e < 16; ++e)
                     if (e >= nvalid) v[e] = 0.f;
             }
-            float tsum = 0.f;
+            float ts[4] = {0.f, 0.f, 0.f, 0.f};
             uint32_t out[16];
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
                 float wh[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    tsum += v[4 * h + e];
+                    ts[e] += v[4 * h + e];
                     wh[e] = h_rn(v[4 * h + e]);
                 }
                 out[2 * h] = pack_h2(wh[0], wh[1]);
@@ -751,10 +817,15 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
             mbar_arrive(&bars->a2_full[b]);
             if (tid == 0) trace(a.trace, i, 7);
             {
-                const float y = tsum - wcomp;
+                const float y = ((ts[0] + ts[1]) + (ts[2] + ts[3])) - wcomp;
                 const float t = wsum + y;
                 wcomp = (t - wsum) - y;
                 wsum = t;
+            }
+            rb.next();
+            if (++b == NSB) {
+                b = 0;
+                phs ^= 1;
             }
             // drain the previous group one tile late: its last MMAs have certainly retired by then
             if (i % DR == 1 && i > DR) drain(i / DR - 1);
@@ -795,8 +866,8 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
     }
 }
 
-static size_t kc_smem(int KP, int C, int ns) {
-    return (size_t)ns * (4 * TILE * KP * 2 + 2 * TILE * (GM / C) * 4) + sizeof(KcBarriers) + 1024;
+static size_t kc_smem(int KP, int C, int na, int nb) {
+    return (size_t)na * (2 * TILE * KP * 2) + (size_t)nb * (2 * TILE * KP * 2 + 2 * TILE * (GM / C) * 4) + sizeof(KcBarriers) + 1024;
 }
 
 // log2 of pdf posteriors (the forward-backward kernels that cannot write them themselves)
@@ -838,9 +909,12 @@ template <int KP, int C>
 static int launch_kc(const KcArgs& a0, const float* llh2, int64_t ld_llh, const float* lpost, int64_t ld_lpost,
                      int64_t ranges, cudaStream_t st) {
     KcArgs a = a0;
-    a.ns = NS_MAX;
-    while (a.ns > 2 && kc_smem(KP, C, a.ns) > 227 * 1024) --a.ns;
-    const size_t smem = kc_smem(KP, C, a.ns);
+    // ring A (img1 tiles): 4 deep; ring B (img2 tile + llh / posterior blocks): whatever else fits
+    a.na = 4;
+    a.nb = RING_MAX;
+    while (a.nb > 2 && kc_smem(KP, C, a.na, a.nb) > 227 * 1024) --a.nb;
+    while (a.na > 2 && kc_smem(KP, C, a.na, a.nb) > 227 * 1024) --a.na;
+    const size_t smem = kc_smem(KP, C, a.na, a.nb);
     if (smem > 227 * 1024) return BEER_ERR_UNSUPPORTED;
     CUtensorMap m1, m2;
     int rc = encode_rows(&m1, llh2, a.N, a.Kp, ld_llh, GM / C);
@@ -987,7 +1061,7 @@ int beer_mix16_accumulate(const void* img1, const void* img2, int64_t N, int D, 
     if (N == 0) return BEER_OK;
     mix16::KcArgs a;
     a.img1 = (const __half*)img1; a.img2 = (const __half*)img2; a.N = N; a.wtm = wtm; a.k12 = (const float2*)k12; a.alpha = alpha;
-    a.M = M; a.Kp = M / C; a.D = D; a.acc = acc_normal; a.ns = 0; a.trace = mix16::g_trace;
+    a.M = M; a.Kp = M / C; a.D = D; a.acc = acc_normal; a.na = a.nb = 0; a.trace = mix16::g_trace;
     a.n_gtiles = (M + mix16::GM - 1) / mix16::GM;
     // the posteriors carry `scale`: keep w 2^wexp <= 2^14 (fp16 overflows at 2^16)
     int e = 14;

@@ -898,7 +898,7 @@ static int launch_fb_fast(const FbArgs& a, int n_utts, cudaStream_t st) {
 // w_in[j] (from slot j-1, or from the junction for a unit start), w_jout[j] (unit end ->
 // junction, -inf elsewhere); the backward recursion uses the same three transposed.
 // ---------------------------------------------------------------------------
-template <int SU, int U>
+template <int SU, int U, bool LP>     // LP: also write log2 posteriors (kept out of the plain kernel: registers)
 __global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_lr_kernel(FbArgs a) {
     constexpr int S = SU * U;
     constexpr bool VEC = (S % 4 == 0);
@@ -910,7 +910,6 @@ __global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_lr_kernel(FbArgs a) {
     float* ring_a = ring_p + PF * ROW;                      // [PF][32 * S]
     const int K = a.K;
     const float p_scale = a.scale * a.llh_mul;
-    const float lscale2 = lg2(a.scale);
     const int gwarp = blockIdx.x * FB_WARPS + warp, nwarps = gridDim.x * FB_WARPS;
     const bool own = lane * S < K;
     for (int i = lane; i < 2 * PF * ROW; i += 32) ring_p[i] = 0.f;   // lanes past K stay finite
@@ -1123,17 +1122,17 @@ __global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_lr_kernel(FbArgs a) {
             m = warp_max(m);
             const float ms = (m == kNegInf) ? 0.f : m;
             float sum = 0.f;
-            float vlog[S];
+            float vlog[LP ? S : 1];
 #pragma unroll
             for (int j = 0; j < S; ++j) {
-                vlog[j] = v[j] - ms;
-                v[j] = ex2(vlog[j]);
+                if constexpr (LP) vlog[j] = v[j] - ms;
+                v[j] = ex2(v[j] - ms);
                 sum += v[j];
             }
             sum = warp_sum(sum);
             const float inv = (sum > 0.f) ? __fdividef(1.f, sum) : 0.f;
-            if (a.pdf_lpost != nullptr) {
-                const float lnorm = lscale2 - lg2(sum);        // log2(scale gamma) = log value - log2 sum + log2 scale
+            if constexpr (LP) {
+                const float lnorm = lg2(a.scale) - lg2(sum);   // log2(scale gamma) = log value - log2 sum + log2 scale
 #pragma unroll
                 for (int j = 0; j < S; ++j) vlog[j] += lnorm;
                 write_row(a.pdf_lpost + (size_t)(t0 + t) * a.ld_lpost, vlog, 1.f);
@@ -1217,21 +1216,22 @@ __global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_lr_kernel(FbArgs a) {
     }
 }
 
-template <int SU, int U>
+template <int SU, int U, bool LP = false>
 static int launch_fb_lr(const FbArgs& a, int n_utts, cudaStream_t st) {
+    if (!LP && a.pdf_lpost != nullptr) return launch_fb_lr<SU, U, true>(a, n_utts, st);
     constexpr int S = SU * U;
     constexpr int PF = (S <= 4) ? 6 : (S <= 8 ? 4 : 3);
     size_t smem = sizeof(float) * (size_t)FB_WARPS * (2 * PF * 32 * S);
     static bool attr_set = false;
     if (!attr_set) {
-        BEER_CUDA_TRY(cudaFuncSetAttribute(hmm_fb_lr_kernel<SU, U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        BEER_CUDA_TRY(cudaFuncSetAttribute(hmm_fb_lr_kernel<SU, U, LP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem));
         attr_set = true;
     }
     int blocks = (n_utts + FB_WARPS - 1) / FB_WARPS;
     int max_blocks = kNumSMs * 16;
     if (blocks > max_blocks) blocks = max_blocks;
-    hmm_fb_lr_kernel<SU, U><<<blocks, FB_WARPS * 32, smem, st>>>(a);
+    hmm_fb_lr_kernel<SU, U, LP><<<blocks, FB_WARPS * 32, smem, st>>>(a);
     BEER_LAUNCH_CHECK();
     return BEER_OK;
 }
@@ -1244,7 +1244,7 @@ static int launch_fb_lr(const FbArgs& a, int n_utts, cudaStream_t st) {
 // recombined, so a single round suffices; slots are double-buffered, so one barrier per exchange).
 // Forward: 1 exchange per frame; backward: 2 (posterior normaliser, junction of the beta recursion).
 // ---------------------------------------------------------------------------
-template <int SU, int W>
+template <int SU, int W, bool LP>
 __global__ void __launch_bounds__(W * 32) hmm_fb_lrb_kernel(FbArgs a) {
     constexpr int S = SU;
     constexpr bool VEC = (S % 4 == 0);
@@ -1257,7 +1257,6 @@ __global__ void __launch_bounds__(W * 32) hmm_fb_lrb_kernel(FbArgs a) {
     float* xch = smem + (size_t)W * (2 * PF * ROW);     // [2][W][4] exchange slots
     const int K = a.K;
     const float p_scale = a.scale * a.llh_mul;
-    const float lscale2 = lg2(a.scale);
     const int gl = warp * 32 + lane;            // unit owned by this lane
     const int k0 = gl * S;                      // its first state
     const bool own = k0 < K;
@@ -1458,10 +1457,10 @@ __global__ void __launch_bounds__(W * 32) hmm_fb_lrb_kernel(FbArgs a) {
             m = warp_max(m);
             const float mls = (m == kNegInf) ? 0.f : m;
             float sl = 0.f, pe = 0.f;
-            float vlog[S];
+            float vlog[LP ? S : 1];
 #pragma unroll
             for (int j = 0; j < S; ++j) {
-                vlog[j] = v[j];
+                if constexpr (LP) vlog[j] = v[j];
                 v[j] = ex2(v[j] - mls);
                 sl += v[j];
                 pe = fmaf(p[j], v[j], pe);
@@ -1472,8 +1471,8 @@ __global__ void __launch_bounds__(W * 32) hmm_fb_lrb_kernel(FbArgs a) {
             exchange(m, sl, pe, ms, sum, pes);
             const float inv = (sum > 0.f) ? __fdividef(1.f, sum) : 0.f;
             const float resc = ex2(mls - ms) * inv;            // this warp's values -> block normalisation
-            if (a.pdf_lpost != nullptr) {
-                const float lnorm = lscale2 - ms - lg2(sum);
+            if constexpr (LP) {
+                const float lnorm = lg2(a.scale) - ms - lg2(sum);
 #pragma unroll
                 for (int j = 0; j < S; ++j) vlog[j] += lnorm;
                 write_row(a.pdf_lpost + (size_t)(t0 + t) * a.ld_lpost, vlog, 1.f);
@@ -1533,18 +1532,19 @@ __global__ void __launch_bounds__(W * 32) hmm_fb_lrb_kernel(FbArgs a) {
     }
 }
 
-template <int SU, int W>
+template <int SU, int W, bool LP = false>
 static int launch_fb_lrb(const FbArgs& a, int n_utts, cudaStream_t st) {
+    if (!LP && a.pdf_lpost != nullptr) return launch_fb_lrb<SU, W, true>(a, n_utts, st);
     constexpr int PF = 4;
     size_t smem = sizeof(float) * ((size_t)W * (2 * PF * 32 * SU) + 2 * W * 4);
     static bool attr_set = false;
     if (!attr_set) {
-        BEER_CUDA_TRY(cudaFuncSetAttribute(hmm_fb_lrb_kernel<SU, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        BEER_CUDA_TRY(cudaFuncSetAttribute(hmm_fb_lrb_kernel<SU, W, LP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem));
         attr_set = true;
     }
     int blocks = n_utts < kNumSMs * 8 ? n_utts : kNumSMs * 8;
-    hmm_fb_lrb_kernel<SU, W><<<blocks, W * 32, smem, st>>>(a);
+    hmm_fb_lrb_kernel<SU, W, LP><<<blocks, W * 32, smem, st>>>(a);
     BEER_LAUNCH_CHECK();
     return BEER_OK;
 }

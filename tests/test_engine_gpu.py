@@ -284,6 +284,7 @@ def test_vb_iterations_cfg3_shape(use_graph, mix16, monkeypatch):
         assert np.abs(acc - info['acc_normal']).max() <= 3e-5 * np.abs(info['acc_normal']).max()
     # 232 frames over 8000 Gaussians: most Gaussians own a fraction of a frame, so a statistic that is right to 3e-5
     # of the LARGEST entry moves the mean of such a Gaussian by up to ~1e-3 (mean = sum w x / (kappa0 + sum w))
+    # (the rates difference the two second moments: b = b0 + (sum w x^2 + kappa0 m0^2 - kappa m^2) / 2)
     for g, w in zip(_host(em.post), ng_post):
-        np.testing.assert_allclose(g, w, rtol=2e-4, atol=1e-3)
+        np.testing.assert_allclose(g, w, rtol=2e-4, atol=3e-3)
     np.testing.assert_allclose(groups[0].post.double().cpu().numpy(), dpost, rtol=2e-4, atol=1e-5)
