@@ -299,6 +299,7 @@ struct KaArgs {
     int Kp, NB, n_chunks;
     float* llh2;
     int64_t ld;
+    int staged;              // llh tiles leave through shared memory + TMA tensor stores (per lane quarter)
     unsigned long long* trace;
 };
 
@@ -311,7 +312,7 @@ struct KaBarriers {
 };
 
 template <int KP, int C>
-__global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a) {
+__global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a, const __grid_constant__ CUtensorMap omap) {
     constexpr int FR = 128, KSTEPS = KP / 16;
     constexpr uint32_t LBO = 128, SBO = KP * 16;
     constexpr int A_HALF = FR * KP;                     // halfs of one A image (hi or lo) of a 128-frame tile
@@ -323,6 +324,9 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a) {
     const int b_stage = 2 * a.NB * KP;
     float2* s_k12 = reinterpret_cast<float2*>(Bs + 2 * b_stage);             // [K12_RING][NB] (k1, k2)
     KaBarriers* bars = reinterpret_cast<KaBarriers*>(s_k12 + K12_RING * a.NB);
+    // staged output: [4 lane quarters][3 buffers][32 frames][NB / C pdfs] (128-byte aligned)
+    float* s_out = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(bars + 1) + 127) & ~uintptr_t(127));
+    const int PC = a.NB / C;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t n_tiles = (a.N + FR - 1) / FR, n_tiles64 = (a.N + TILE - 1) / TILE;
@@ -422,6 +426,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a) {
         const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
         const int n_units = a.NB / UNIT;
         const int u0 = cq * n_units / 4, u1 = (cq + 1) * n_units / 4;
+        const int qq = warp & 3;
         uint32_t it = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int64_t t = tile * FR + r;
@@ -434,6 +439,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a) {
                 tc_fence_after();
                 const float2* kk = s_k12 + (it & (K12_RING - 1)) * a.NB;
                 const uint32_t taddr = tmem_base + lane_addr + (uint32_t)buf * 256u;
+                float* sbuf = s_out + ((size_t)qq * 3 + it % 3) * 32 * PC + (size_t)lane * PC;     // this frame's staged row
                 // G units at a time: all their TMEM loads in flight together, independent max / exp / sum chains
                 auto process = [&](int u, auto gtag) {
                     constexpr int G = decltype(gtag)::value;
@@ -460,7 +466,10 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a) {
                         for (int j = 0; j < C; ++j) v[k * C + j] = ex2(v[k * C + j] - ms);
                         o[k] = ms + lg2(tree_sum<C>(v + k * C));
                     }
-                    if (valid) {
+                    if (a.staged) {
+#pragma unroll
+                        for (int k = 0; k < G * PPU; ++k) sbuf[p / C + k] = o[k];
+                    } else if (valid) {
                         const int k0 = (c * a.NB + p) / C;
 #pragma unroll
                         for (int k = 0; k < G * PPU; ++k)
@@ -476,9 +485,25 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a) {
                 if (u < u1) process(u, std::integral_constant<int, 1>());
                 tc_fence_before();
                 mbar_arrive(&bars->t_empty[buf]);
+                if (a.staged) {
+                    // one tensor store per lane quarter and chunk: [32 frames x NB / C pdfs], rows past N and columns
+                    // past Kp clipped by the map.  Three staging buffers, one barrier: the issuing lane's
+                    // wait_group.read 1 of chunk i - 1 ran before this barrier, so buffer (i + 1) % 3 is free behind it.
+                    fence_proxy_async();
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + qq) : "memory");
+                    if (cq == 0 && elect_one()) {
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&omap),
+                                     "r"(smem_u32(s_out + ((size_t)qq * 3 + it % 3) * 32 * PC)), "r"(c * PC),
+                                     "r"((int)(tile * FR) + 32 * qq)
+                                     : "memory");
+                        bulk_commit();
+                        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    }
+                }
                 if (lane == 0 && (warp == 0 || warp == 15)) trace(a.trace, it, warp == 0 ? 5 : 7);
             }
         }
+        if (a.staged && cq == 0 && elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -488,22 +513,32 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a) {
     }
 }
 
-static size_t ka_smem(int KP, int NB) {
-    return (size_t)2 * 2 * 128 * KP * 2 + (size_t)2 * 2 * NB * KP * 2 + (size_t)K12_RING * NB * 8 + sizeof(KaBarriers) + 1024;
+static size_t ka_smem(int KP, int NB, int C) {
+    return (size_t)2 * 2 * 128 * KP * 2 + (size_t)2 * 2 * NB * KP * 2 + (size_t)K12_RING * NB * 8 + sizeof(KaBarriers) + 128 +
+           (size_t)4 * 3 * 32 * (NB / C) * 4 + 1024;
 }
 
+static int encode_rows(CUtensorMap* map, const float* base, int64_t N, int Kp, int64_t ld, int box_cols, int box_rows);
+
 template <int KP, int C>
-static int launch_ka(const KaArgs& a, cudaStream_t st) {
-    const size_t smem = ka_smem(KP, a.NB);
+static int launch_ka(const KaArgs& a0, cudaStream_t st) {
+    KaArgs a = a0;
+    const size_t smem = ka_smem(KP, a.NB, C);
     if (smem > 227 * 1024) return BEER_ERR_UNSUPPORTED;
     static bool attr = false;
     if (!attr) {
         BEER_CUDA_TRY(cudaFuncSetAttribute(emission16_kernel<KP, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr = true;
     }
+    // staged tensor stores need 16-byte rows in shared memory and in HBM
+    CUtensorMap omap;
+    memset(&omap, 0, sizeof(omap));
+    const int PC = a.NB / C;
+    a.staged = (PC % 4 == 0 && a.ld % 4 == 0 && ((uintptr_t)a.llh2 & 15) == 0 && a.N < ((int64_t)1 << 31)) ? 1 : 0;
+    if (a.staged && encode_rows(&omap, a.llh2, a.N, a.Kp, a.ld, PC, 32) != BEER_OK) a.staged = 0;
     const int64_t n_tiles = (a.N + 127) / 128;
     const int grid = (int)std::min<int64_t>(n_tiles, kNumSMs);
-    emission16_kernel<KP, C><<<grid, KA_THREADS, smem, st>>>(a);
+    emission16_kernel<KP, C><<<grid, KA_THREADS, smem, st>>>(a, omap);
     BEER_LAUNCH_CHECK();
     return BEER_OK;
 }
@@ -514,7 +549,7 @@ static int launch_ka(const KaArgs& a, cudaStream_t st) {
 constexpr int GM = 128;                  // Gaussians per CTA (UMMA M, TMEM lanes)
 constexpr int EPI = 512;                 // 16 epilogue warps: 4 per TMEM lane quarter, each a quarter of the 64 frames
 constexpr int KC_MMA_WARP = EPI / 32, KC_LOAD_WARP = KC_MMA_WARP + 1;
-constexpr int KC_LOADERS = 4;            // one issuing thread per copy stream
+constexpr int KC_LOADERS = 3;            // one issuing thread per copy stream (20 warps in all: 96 registers per thread)
 constexpr int KC_THREADS = EPI + 32 + 32 * KC_LOADERS;
 constexpr int RING_MAX = 8;              // upper bound of either shared-memory ring
 constexpr int NSB = 3;                   // S^T / A2 buffers in tensor memory
@@ -600,12 +635,12 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
         for (int i = 0; i < RING_MAX; ++i) {
             mbar_init(&bars->a_full[i], 1);
             mbar_init(&bars->a_empty[i], 1);
-            mbar_init(&bars->b_full[i], KC_LOADERS - 1);
+            mbar_init(&bars->b_full[i], 2);
             mbar_init(&bars->b_empty[i], 1);
         }
         for (int i = 0; i < NSB; ++i) {
             mbar_init(&bars->s_full[i], 1);
-            mbar_init(&bars->a2_full[i], EPI);
+            mbar_init(&bars->a2_full[i], EPI / 2);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars->d2_full[i], 1);
@@ -641,7 +676,7 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
 
     if (warp >= KC_LOAD_WARP) {
         // ------------------------------ loaders (TMA) ------------------------------
-        // four warps, one copy stream each: img1 tiles -> ring A; img2 tiles, llh blocks, posterior blocks -> ring B
+        // three warps, one copy stream each: img1 tiles -> ring A; img2 tiles | llh + posterior blocks -> ring B
         if (elect_one()) {
             const int which = warp - KC_LOAD_WARP;
             const uint32_t bytes = STAGE_A;                   // hi + lo of one image
@@ -662,11 +697,9 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
                 if (which == 1) {
                     mbar_arrive_expect_tx(&bars->b_full[r.pos], bytes);
                     bulk_g2s(dst, a.img2 + (size_t)(tile0 + i) * (2 * IMG_HALF), bytes, &bars->b_full[r.pos]);
-                } else if (which == 2) {
-                    mbar_arrive_expect_tx(&bars->b_full[r.pos], RAW_FLOATS * 4u);
-                    tma_load_2d(dst + bytes, &map_l2, k0, t0, &bars->b_full[r.pos]);
                 } else {
-                    mbar_arrive_expect_tx(&bars->b_full[r.pos], RAW_FLOATS * 4u);
+                    mbar_arrive_expect_tx(&bars->b_full[r.pos], 2u * RAW_FLOATS * 4u);
+                    tma_load_2d(dst + bytes, &map_l2, k0, t0, &bars->b_full[r.pos]);
                     tma_load_2d(dst + bytes + RAW_FLOATS * 4, &map_lp, k0, t0, &bars->b_full[r.pos]);
                 }
             }
@@ -735,7 +768,10 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
         }
     } else {
         // ------------------------------ epilogue warps -------------------------------
-        const int q = warp & 3, part = warp >> 2;            // TMEM lane quarter, quarter of the tile's frames
+        // Two groups of eight warps take alternate tiles: while one group sits in its barrier / tensor-memory
+        // latencies the other one computes (all sixteen warps on one tile spent a third of the tile time waiting).
+        const int q = warp & 3, part = warp >> 2;            // TMEM lane quarter; quarter of the accumulator columns (drain)
+        const int group = part & 1, half = part >> 1;        // tile parity; half of the tile's frames
         const int g = q * 32 + lane;                         // Gaussian (local) = TMEM lane
         const int pl = g / C;                                // its pdf (local)
         const float2 k12 = __ldg(a.k12 + g0 + g);
@@ -747,6 +783,7 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
 #pragma unroll
             for (int i = 0; i < 4; ++i) sums[m][i] = comp[m][i] = 0.f;
         float wsum = 0.f, wcomp = 0.f;                       // sum_t w 2^wexp of this thread's frames (Kahan over tiles)
+        int next_drain = 0;
         auto drain = [&](int grp) {
             const int dbuf = grp & 1;
             mbar_wait(&bars->d2_full[dbuf], (grp >> 1) & 1);
@@ -771,47 +808,55 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
         };
 
         Ring rb(a.nb);
-        int b = 0;
+        if (group) rb.next();
+        int b = group;
         uint32_t phs = 0;
-        for (int i = 0; i < n_tiles; ++i) {
+        const int late = group ? 1 : 2;          // a finished drain group is collected one / two tiles into the next one
+        for (int i = group; i < n_tiles; i += 2) {
             mbar_wait(&bars->b_full[rb.pos], rb.phase);          // the llh / posterior blocks of the tile (TMA)
             if (tid == 0) trace(a.trace, i, 5);
             mbar_wait(&bars->s_full[b], phs);
             if (tid == 0) trace(a.trace, i, 6);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + lane_addr + COL_S + (uint32_t)(b * TILE + part * 16);
-            float v[16];
-            tmem_ld16(taddr, v);
-            const float* rl2 = reinterpret_cast<const float*>(ring_b + (size_t)rb.pos * STAGE_B + STAGE_A) + part * 16 * NK + pl;
-            const float* rlp = rl2 + RAW_FLOATS;
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                // z = S k1 + k2 is bit for bit the value KA16 normalised: z - llh2 = log2 responsibility
-                const float z = fmaf(v[e], k1, k2);
-                v[e] = ex2((z - rl2[e * NK]) + (rlp[e * NK] + a.wexp));
-            }
-            const int nvalid = (int)min((int64_t)TILE, f_end - (f_begin + (int64_t)i * TILE)) - part * 16;
-            if (nvalid < 16) {       // the last tile of the batch: frames past the end carry no weight
-#pragma unroll
-                for (int e = 0; e < 16; ++e)
-                    if (e >= nvalid) v[e] = 0.f;
-            }
+            const float* raw = reinterpret_cast<const float*>(ring_b + (size_t)rb.pos * STAGE_B + STAGE_A);
+            const int n_left = (int)min((int64_t)TILE, f_end - (f_begin + (int64_t)i * TILE)) - half * 32;
             float ts[4] = {0.f, 0.f, 0.f, 0.f};
-            uint32_t out[16];
 #pragma unroll
-            for (int h = 0; h < 4; ++h) {
-                float wh[4];
+            for (int sub = 0; sub < 2; ++sub) {
+                const int f0 = half * 32 + sub * 16;             // first frame (in the tile) of this block of 16
+                const uint32_t taddr = tmem_base + lane_addr + COL_S + (uint32_t)(b * TILE + f0);
+                float v[16];
+                tmem_ld16(taddr, v);
+                const float* rl2 = raw + f0 * NK + pl;
+                const float* rlp = rl2 + RAW_FLOATS;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    ts[e] += v[4 * h + e];
-                    wh[e] = h_rn(v[4 * h + e]);
+                for (int e = 0; e < 16; ++e) {
+                    // z = S k1 + k2 is bit for bit the value KA16 normalised: z - llh2 = log2 responsibility
+                    const float z = fmaf(v[e], k1, k2);
+                    v[e] = ex2((z - rl2[e * NK]) + (rlp[e * NK] + a.wexp));
                 }
-                out[2 * h] = pack_h2(wh[0], wh[1]);
-                out[2 * h + 1] = pack_h2(wh[2], wh[3]);
-                out[8 + 2 * h] = pack_h2(v[4 * h] - wh[0], v[4 * h + 1] - wh[1]);
-                out[8 + 2 * h + 1] = pack_h2(v[4 * h + 2] - wh[2], v[4 * h + 3] - wh[3]);
+                const int nvalid = n_left - sub * 16;
+                if (nvalid < 16) {       // the last tile of the batch: frames past the end carry no weight
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)
+                        if (e >= nvalid) v[e] = 0.f;
+                }
+                uint32_t out[16];
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    float wh[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        ts[e] += v[4 * h + e];
+                        wh[e] = h_rn(v[4 * h + e]);
+                    }
+                    out[2 * h] = pack_h2(wh[0], wh[1]);
+                    out[2 * h + 1] = pack_h2(wh[2], wh[3]);
+                    out[8 + 2 * h] = pack_h2(v[4 * h] - wh[0], v[4 * h + 1] - wh[1]);
+                    out[8 + 2 * h + 1] = pack_h2(v[4 * h + 2] - wh[2], v[4 * h + 3] - wh[3]);
+                }
+                tmem_st16(taddr, out);      // in place: [hi of 16 frames (8 columns) | lo (8 columns)]
             }
-            tmem_st16(taddr, out);          // in place: [hi of 16 frames (8 columns) | lo (8 columns)]
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&bars->a2_full[b]);
@@ -823,17 +868,17 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
                 wsum = t;
             }
             rb.next();
-            if (++b == NSB) {
-                b = 0;
+            rb.next();
+            b += 2;
+            if (b >= NSB) {
+                b -= NSB;
                 phs ^= 1;
             }
-            // drain the previous group one tile late: its last MMAs have certainly retired by then
-            if (i % DR == 1 && i > DR) drain(i / DR - 1);
+            if (i % DR == late && i / DR - 1 >= next_drain) drain(next_drain++);
         }
         if (n_tiles > 0) {
             const int last_g = (n_tiles - 1) / DR;
-            if (last_g >= 1 && (n_tiles - 1) < last_g * DR + 1) drain(last_g - 1);
-            drain(last_g);
+            while (next_drain <= last_g) drain(next_drain++);
             if (g0 + g < a.M) {
                 const int D = a.D, Q = 2 * D + 2;
                 double* row = a.acc + (size_t)(g0 + g) * Q;
@@ -885,7 +930,7 @@ typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, v
                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int encode_rows(CUtensorMap* map, const float* base, int64_t N, int Kp, int64_t ld, int box_cols) {
+static int encode_rows(CUtensorMap* map, const float* base, int64_t N, int Kp, int64_t ld, int box_cols, int box_rows) {
     static EncodeTiled encode = nullptr;
     if (encode == nullptr) {
         void* fn = nullptr;
@@ -896,7 +941,7 @@ static int encode_rows(CUtensorMap* map, const float* base, int64_t N, int Kp, i
     }
     const cuuint64_t gdim[2] = {(cuuint64_t)Kp, (cuuint64_t)N};
     const cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
-    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)TILE};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     if (encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -917,9 +962,9 @@ static int launch_kc(const KcArgs& a0, const float* llh2, int64_t ld_llh, const 
     const size_t smem = kc_smem(KP, C, a.na, a.nb);
     if (smem > 227 * 1024) return BEER_ERR_UNSUPPORTED;
     CUtensorMap m1, m2;
-    int rc = encode_rows(&m1, llh2, a.N, a.Kp, ld_llh, GM / C);
+    int rc = encode_rows(&m1, llh2, a.N, a.Kp, ld_llh, GM / C, TILE);
     if (rc != BEER_OK) return rc;
-    rc = encode_rows(&m2, lpost, a.N, a.Kp, ld_lpost, GM / C);
+    rc = encode_rows(&m2, lpost, a.N, a.Kp, ld_lpost, GM / C, TILE);
     if (rc != BEER_OK) return rc;
     static bool attr = false;
     if (!attr) {
@@ -935,7 +980,7 @@ static int nb_of(int M, int C) {
     // Gaussians per KA16 chunk: the largest divisor of M that is a multiple of 16 and of C, at most 256 (no padded
     // columns in the last chunk); 128 with padding when M has none
     int best = 0;
-    for (int nb = 16; nb <= 192; nb += 16)      // two weight stages + two statistics tiles fit in shared memory
+    for (int nb = 16; nb <= 160; nb += 16)      // two weight stages, two statistics tiles and the staged output fit in shared memory
         if (M % nb == 0 && nb % C == 0) best = nb;
     if (best >= 64) return best;
     return 128;
@@ -1030,7 +1075,7 @@ int beer_mix16_emission(const void* img1, int64_t N, int D, const void* wimg, co
     a.img1 = (const __half*)img1; a.N = N; a.wimg = (const __half*)wimg; a.k12 = (const float2*)k12;
     a.Kp = M / C; a.NB = (int)sz[4];
     a.n_chunks = (M + a.NB - 1) / a.NB;
-    a.llh2 = llh2; a.ld = ld; a.trace = mix16::g_trace;
+    a.llh2 = llh2; a.ld = ld; a.staged = 0; a.trace = mix16::g_trace;
     const int KP = (int)sz[5];
     cudaStream_t st = (cudaStream_t)stream;
 #define BEER_KA_CASE(kp, c) \

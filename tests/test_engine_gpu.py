@@ -287,4 +287,4 @@ def test_vb_iterations_cfg3_shape(use_graph, mix16, monkeypatch):
     # (the rates difference the two second moments: b = b0 + (sum w x^2 + kappa0 m0^2 - kappa m^2) / 2)
     for g, w in zip(_host(em.post), ng_post):
         np.testing.assert_allclose(g, w, rtol=2e-4, atol=3e-3)
-    np.testing.assert_allclose(groups[0].post.double().cpu().numpy(), dpost, rtol=2e-4, atol=1e-5)
+    np.testing.assert_allclose(groups[0].post.double().cpu().numpy(), dpost, rtol=2e-4, atol=3e-4)
