@@ -60,6 +60,8 @@ SIGNATURES = {
     'beer_dirichlet_from_natural': (C.c_int, [c_ptr, C.c_int, C.c_int, c_ptr, c_ptr]),
     'beer_segment_logsumexp': (C.c_int, [c_ptr, C.c_int64, C.c_int, c_ptr, C.c_int, c_ptr, C.c_int64, c_ptr]),
     'beer_fbank': (C.c_int, [c_ptr, C.c_int64, C.c_int, C.c_int, C.c_float, c_ptr, c_ptr, C.c_int, C.c_int, c_ptr, c_ptr]),
+    'beer_short_term_mspec': (C.c_int, [c_ptr, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_float, c_ptr, c_ptr, C.c_int,
+                                        C.c_int, C.c_float, c_ptr, c_ptr]),
     'beer_add_deltas': (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
     'beer_hmm_chain_row_stride': (C.c_int, [C.c_int]),
     'beer_hmm_chain_workspace_bytes': (C.c_int64, [C.c_int, C.c_int64]),

@@ -17,7 +17,8 @@ __global__ void __launch_bounds__(KF_WARPS * 32) fbank_kernel(const float* __res
                                                               int flen, int fshift, float preemph,
                                                               const float* __restrict__ window,
                                                               const float* __restrict__ filtT, int nfilt,
-                                                              float* __restrict__ out) {
+                                                              float* __restrict__ out, float dc, int frame_preemph,
+                                                              float log_offset) {
     constexpr int LOGN = (N == 256) ? 8 : (N == 512 ? 9 : 10);
     __shared__ float2 tw[N / 2];
     __shared__ float2 xs[KF_WARPS][N];
@@ -37,7 +38,10 @@ __global__ void __launch_bounds__(KF_WARPS * 32) fbank_kernel(const float* __res
             float v = 0.f;
             if (i < flen) {
                 const int64_t t = s0 + i;
-                const float cur = sig[t], prev = sig[t > 0 ? t - 1 : 0];
+                // fbank(): pre-emphasis over the whole signal; short_term_mspec(): DC removed, pre-emphasis inside
+                // the frame (its first sample against itself, features.py:131-132)
+                const float cur = sig[t] - dc;
+                const float prev = frame_preemph ? (i > 0 ? sig[t - 1] - dc : cur) : sig[t > 0 ? t - 1 : 0] - dc;
                 v = (cur - preemph * prev) * window[i];
             }
             x[i] = make_float2(v, 0.f);
@@ -62,10 +66,14 @@ __global__ void __launch_bounds__(KF_WARPS * 32) fbank_kernel(const float* __res
             mag[warp][k] = sqrtf(v.x * v.x + v.y * v.y);
         }
         __syncwarp();
-        for (int m = lane; m < nfilt; m += 32) {
-            float acc = 0.f;
-            for (int k = 0; k < N / 2; ++k) acc = fmaf(mag[warp][k], __ldg(filtT + (size_t)k * nfilt + m), acc);
-            out[(size_t)f * nfilt + m] = log1pf(acc);
+        if (filtT == nullptr) {          // magnitude spectrum itself (short_term_mspec)
+            for (int k = lane; k < N / 2; k += 32) out[(size_t)f * (N / 2) + k] = mag[warp][k];
+        } else {
+            for (int m = lane; m < nfilt; m += 32) {
+                float acc = 0.f;
+                for (int k = 0; k < N / 2; ++k) acc = fmaf(mag[warp][k], __ldg(filtT + (size_t)k * nfilt + m), acc);
+                out[(size_t)f * nfilt + m] = (log_offset == 1.f) ? log1pf(acc) : logf(log_offset + acc);
+            }
         }
         __syncwarp();
     }
@@ -94,28 +102,47 @@ using namespace beer;
 
 extern "C" {
 
-int beer_fbank(const float* signal, int64_t n_samples, int frame_len, int frame_shift, float preemph,
-               const float* window, const float* filters_t, int fft_len, int n_filters, float* out, void* stream) {
-    if (!signal || !window || !filters_t || !out || frame_len <= 0 || frame_shift <= 0 || n_filters <= 0)
-        return BEER_ERR_ARG;
+static int launch_fbank(const float* signal, int64_t n_samples, int frame_len, int frame_shift, float preemph,
+                        const float* window, const float* filters_t, int fft_len, int n_filters, float* out, float dc,
+                        int frame_preemph, float log_offset, void* stream) {
+    if (!signal || !window || !out || frame_len <= 0 || frame_shift <= 0) return BEER_ERR_ARG;
+    if (filters_t != nullptr && n_filters <= 0) return BEER_ERR_ARG;
     if (frame_len > fft_len) return BEER_ERR_ARG;
     if (n_samples < frame_len) return BEER_OK;
     const int nframes = (int)((n_samples - frame_len) / frame_shift + 1);
     int blocks = (nframes + KF_WARPS - 1) / KF_WARPS;
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     cudaStream_t st = (cudaStream_t)stream;
+#define BEER_FBANK_CASE(n)                                                                                             \
+    case n:                                                                                                            \
+        fbank_kernel<n><<<blocks, KF_WARPS * 32, 0, st>>>(signal, n_samples, nframes, frame_len, frame_shift, preemph, \
+                                                          window, filters_t, n_filters, out, dc, frame_preemph,       \
+                                                          log_offset);                                                 \
+        break;
     switch (fft_len) {
-        case 256: fbank_kernel<256><<<blocks, KF_WARPS * 32, 0, st>>>(signal, n_samples, nframes, frame_len, frame_shift,
-                                                                       preemph, window, filters_t, n_filters, out); break;
-        case 512: fbank_kernel<512><<<blocks, KF_WARPS * 32, 0, st>>>(signal, n_samples, nframes, frame_len, frame_shift,
-                                                                       preemph, window, filters_t, n_filters, out); break;
-        case 1024: fbank_kernel<1024><<<blocks, KF_WARPS * 32, 0, st>>>(signal, n_samples, nframes, frame_len,
-                                                                         frame_shift, preemph, window, filters_t,
-                                                                         n_filters, out); break;
+        BEER_FBANK_CASE(256)
+        BEER_FBANK_CASE(512)
+        BEER_FBANK_CASE(1024)
         default: return BEER_ERR_UNSUPPORTED;
     }
+#undef BEER_FBANK_CASE
     BEER_LAUNCH_CHECK();
     return BEER_OK;
+}
+
+int beer_fbank(const float* signal, int64_t n_samples, int frame_len, int frame_shift, float preemph,
+               const float* window, const float* filters_t, int fft_len, int n_filters, float* out, void* stream) {
+    if (!filters_t) return BEER_ERR_ARG;
+    return launch_fbank(signal, n_samples, frame_len, frame_shift, preemph, window, filters_t, fft_len, n_filters, out,
+                        0.f, 0, 1.f, stream);
+}
+
+int beer_short_term_mspec(const float* signal, int64_t n_samples, int frame_len, int frame_shift, float preemph,
+                          float dc_offset, const float* window, const float* filters_t, int fft_len, int n_filters,
+                          float log_offset, float* out, void* stream) {
+    if (filters_t != nullptr && !(log_offset > 0.f)) return BEER_ERR_ARG;
+    return launch_fbank(signal, n_samples, frame_len, frame_shift, preemph, window, filters_t, fft_len, n_filters, out,
+                        dc_offset, 1, log_offset, stream);
 }
 
 int beer_add_deltas(const float* fea, int n_frames, int dim, int wlen, float* out, void* stream) {

@@ -1245,7 +1245,7 @@ static int launch_fb_lr(const FbArgs& a, int n_utts, cudaStream_t st) {
 // Forward: 1 exchange per frame; backward: 2 (posterior normaliser, junction of the beta recursion).
 // ---------------------------------------------------------------------------
 template <int SU, int W, bool LP>
-__global__ void __launch_bounds__(W * 32) hmm_fb_lrb_kernel(FbArgs a) {
+__global__ void __launch_bounds__(W * 32, 4) hmm_fb_lrb_kernel(FbArgs a) {
     constexpr int S = SU;
     constexpr bool VEC = (S % 4 == 0);
     constexpr int PF = 4;

@@ -10,7 +10,7 @@ import torch
 
 from . import ops
 
-__all__ = ['hz2mel', 'mel2hz', 'create_fbank', 'fbank', 'add_deltas']
+__all__ = ['hz2mel', 'mel2hz', 'create_fbank', 'fbank', 'short_term_mspec', 'log_mel_spectrum', 'add_deltas']
 
 
 def hz2mel(freq_hz):
@@ -67,8 +67,42 @@ def fbank(signal, flen=0.025, frate=0.01, hifreq=8000, lowfreq=20, nfilters=26, 
         sig = signal.to(device=device, dtype=torch.float32).contiguous()
     else:
         sig = torch.as_tensor(np.asarray(signal, dtype=np.float32), device=device)
-    window, filt_t = _constants(flen_samp, fft_len, nfilters, srate, lowfreq, hifreq, str(sig.device))
+    # the reference builds the filterbank with create_fbank's default srate (16000) whatever `srate` is
+    # (features.py:198): kept, so that results are identical for every sampling rate
+    window, filt_t = _constants(flen_samp, fft_len, nfilters, 16000, lowfreq, hifreq, str(sig.device))
     return ops.fbank(sig, window, filt_t, frate_samp, preemph, fft_len)
+
+
+def _signal_and_dc(signal, device):
+    if isinstance(signal, torch.Tensor):
+        sig = signal.to(device=device, dtype=torch.float32).contiguous()
+        dc = float(signal.double().mean().item()) if signal.numel() else 0.0
+    else:
+        arr = np.asarray(signal)
+        dc = float(arr.mean()) if arr.size else 0.0          # as the reference: mean of the samples in float64
+        sig = torch.as_tensor(arr.astype(np.float32), device=device)
+    return sig, dc
+
+
+def short_term_mspec(signal, flen=0.025, frate=0.01, preemph=0.97, srate=16000, window=np.hamming, device='cuda'):
+    """Short-term magnitude spectrum (features.py:102-143): DC removed, pre-emphasis inside every frame, window,
+    |rFFT| without the Nyquist bin.  Returns (mspec [n_frames, fft_len / 2] on `device`, fft_len)."""
+    frate_samp, flen_samp = int(srate * frate), int(srate * flen)
+    fft_len = int(2 ** np.floor(np.log2(flen_samp) + 1))
+    sig, dc = _signal_and_dc(signal, device)
+    win = torch.as_tensor(window(flen_samp), dtype=torch.float32, device=sig.device)
+    return ops.short_term_mspec(sig, win, frate_samp, preemph, fft_len, dc), fft_len
+
+
+def log_mel_spectrum(signal, nfilters=40, flen=0.025, frate=0.01, preemph=0.97, srate=16000, lowfreq=20, hifreq=8000,
+                     device='cuda'):
+    """The features `beer features extract` writes for an fbank configuration (extract.py:107-127):
+    log(1e-6 + short_term_mspec(signal) @ create_fbank(nfilters, fft_len, lowfreq, highfreq).T), one fused kernel."""
+    frate_samp, flen_samp = int(srate * frate), int(srate * flen)
+    fft_len = int(2 ** np.floor(np.log2(flen_samp) + 1))
+    sig, dc = _signal_and_dc(signal, device)
+    window, filt_t = _constants(flen_samp, fft_len, nfilters, 16000, lowfreq, hifreq, str(sig.device))
+    return ops.short_term_mspec(sig, window, frate_samp, preemph, fft_len, dc, filters_t=filt_t, log_offset=1e-6)
 
 
 def add_deltas(fea, winlens=(2, 2)):

@@ -550,6 +550,21 @@ def fbank(signal, window, filters_t, frame_shift, preemph, fft_len):
     return out
 
 
+def short_term_mspec(signal, window, frame_shift, preemph, fft_len, dc_offset, filters_t=None, log_offset=1e-6):
+    """signal [L] fp32 -> magnitude spectrum [n_frames, fft_len / 2] (filters_t None) or log(log_offset + mel energies)."""
+    lib = require_cuda()
+    L, flen = signal.numel(), window.numel()
+    width = fft_len // 2 if filters_t is None else filters_t.shape[1]
+    nframes = max(0, (L - flen) // frame_shift + 1) if L >= flen else 0
+    out = torch.empty(nframes, width, device=signal.device, dtype=f32)
+    if nframes == 0:
+        return out
+    _lib.check(lib.beer_short_term_mspec(_p(signal, f32), L, flen, int(frame_shift), float(preemph), float(dc_offset),
+                                         _p(window, f32), _p(filters_t, f32, True), int(fft_len), int(width),
+                                         float(log_offset), _p(out), _stream()), 'beer_short_term_mspec')
+    return out
+
+
 def add_deltas(fea, wlen):
     lib = require_cuda()
     T, F = fea.shape

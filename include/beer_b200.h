@@ -302,6 +302,13 @@ BEER_API int beer_path_posteriors(const int32_t* path, int64_t N, const int32_t*
  *   out [(n_samples - frame_len) / frame_shift + 1, n_filters]. */
 BEER_API int beer_fbank(const float* signal, int64_t n_samples, int frame_len, int frame_shift, float preemph,
                const float* window, const float* filters_t, int fft_len, int n_filters, float* out, void* stream);
+/* The front-end `beer features extract` runs (beer/features.py:102-143 short_term_mspec +
+ * beer/cli/subcommands/features/extract.py:107-127): DC offset removed (dc_offset = mean of the signal), pre-emphasis
+ * INSIDE every frame (first sample against itself), window, |rFFT|.  filters_t == NULL: out [n_frames, fft_len/2] =
+ * the magnitude spectrum; else out [n_frames, n_filters] = log(log_offset + mspec @ filters) (extract.py: 1e-6). */
+BEER_API int beer_short_term_mspec(const float* signal, int64_t n_samples, int frame_len, int frame_shift, float preemph,
+                          float dc_offset, const float* window, const float* filters_t, int fft_len, int n_filters,
+                          float log_offset, float* out, void* stream);
 /* One order of the delta regression filter with replicated edges (beer/features.py:82-100):
  * out[t] = sum_{k=1..wlen} k (fea[t+k] - fea[t-k]) / (2 sum k^2). */
 BEER_API int beer_add_deltas(const float* fea, int n_frames, int dim, int wlen, float* out, void* stream);

@@ -711,6 +711,26 @@ def fbank(signal, flen=0.025, frate=0.01, hifreq=8000, lowfreq=20, nfilters=26, 
     return np.log(magspec @ filters.T + 1)
 
 
+def short_term_mspec(signal, flen=0.025, frate=0.01, preemph=0.97, srate=16000):
+    """Magnitude spectrum of `beer features extract` (features.py:102-143): mean removed, pre-emphasis inside each
+    frame (first sample against itself), Hamming window, |rFFT| without the Nyquist bin.  Returns (mspec, fft_len)."""
+    signal = np.asarray(signal) - np.asarray(signal).mean()
+    frate_samp, flen_samp = int(srate * frate), int(srate * flen)
+    nframes = (len(signal) - flen_samp) // frate_samp + 1
+    idx = np.arange(nframes)[:, None] * frate_samp + np.arange(flen_samp)[None, :]
+    frames = signal[idx].copy()
+    frames -= preemph * np.c_[frames[:, 0], frames[:, :-1]]
+    frames = frames * np.hamming(flen_samp)[None, :]
+    fft_len = int(2 ** np.floor(np.log2(flen_samp) + 1))
+    return np.abs(np.fft.rfft(frames, n=fft_len, axis=-1)[:, :-1]), fft_len
+
+
+def log_mel_spectrum(signal, nfilters=40, lowfreq=20, hifreq=8000, **kw):
+    """extract.py:107-127 for an fbank configuration: log(1e-6 + mspec @ filters.T)."""
+    mspec, fft_len = short_term_mspec(signal, **kw)
+    return np.log(1e-6 + mspec @ create_fbank(nfilters, fft_len, lowfreq=lowfreq, highfreq=hifreq).T)
+
+
 def add_deltas(fea, winlens=(2, 2)):
     """Append delta / delta-delta features: regression filter over +-wlen frames with the edges
     replicated (features.py:82-100)."""

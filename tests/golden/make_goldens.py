@@ -555,8 +555,12 @@ def gold_fbank():
     sig = np.round(sig).astype(np.int16)
     fb40 = F.fbank(sig, nfilters=40)
     fb26 = F.fbank(sig)
+    # the CLI front-end (cli/subcommands/features/extract.py:107-127): short_term_mspec + filterbank + log(1e-6 + .)
+    mspec, fft_len = F.short_term_mspec(sig, flen=0.025, frate=0.01, preemph=0.97, srate=16000)
+    cli40 = np.log(1e-6 + mspec @ F.create_fbank(40, fft_len, lowfreq=20, highfreq=8000).T)
     save('fbank', signal=sig, fbank40=fb40, fbank26=fb26, filters40=F.create_fbank(40, 512, lowfreq=20, highfreq=8000),
-         filters26=F.create_fbank(26, 512, lowfreq=20, highfreq=8000), deltas40=F.add_deltas(fb40))
+         filters26=F.create_fbank(26, 512, lowfreq=20, highfreq=8000), deltas40=F.add_deltas(fb40),
+         mspec=mspec, cli_logmel40=cli40)
 
 
 if __name__ == '__main__':

@@ -39,3 +39,17 @@ def test_add_deltas_matches_reference():
     np.testing.assert_allclose(got, g['deltas40'], rtol=0, atol=5e-6)
     got1 = F.add_deltas(fea[:1], winlens=(3,)).cpu().numpy()       # a single frame: zero deltas
     assert got1.shape == (1, 80) and np.all(got1[:, 40:] == 0)
+
+
+def test_cli_front_end_matches_reference():
+    """The features `beer features extract` writes (features.py:102-143 short_term_mspec, extract.py:107-127):
+    DC removal, per-frame pre-emphasis, |rFFT|, mel filterbank, log(1e-6 + .)."""
+    from beer_b200 import features as F
+    g = load_golden('fbank')
+    mspec, fft_len = F.short_term_mspec(g['signal'])
+    assert fft_len == 512 and mspec.shape == g['mspec'].shape
+    want = g['mspec']
+    assert np.abs(mspec.double().cpu().numpy() - want).max() <= 2e-6 * np.abs(want).max()
+    got = F.log_mel_spectrum(g['signal'], nfilters=40)
+    np.testing.assert_allclose(got.double().cpu().numpy(), g['cli_logmel40'], rtol=0, atol=2e-4)
+    assert F.short_term_mspec(g['signal'][:399])[0].shape == (0, 256)

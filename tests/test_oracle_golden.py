@@ -300,3 +300,8 @@ def test_fbank_front_end():
         np.testing.assert_allclose(O.create_fbank(nf, 512, lowfreq=20, highfreq=8000), g[f'filters{nf}'], atol=1e-15)
         np.testing.assert_allclose(O.fbank(g['signal'], nfilters=nf), g[f'fbank{nf}'], rtol=1e-12)
     np.testing.assert_allclose(O.add_deltas(g['fbank40']), g['deltas40'], atol=1e-12)
+    # the front-end of `beer features extract` (short_term_mspec + filterbank + log(1e-6 + .))
+    mspec, fft_len = O.short_term_mspec(g['signal'])
+    assert fft_len == 512
+    np.testing.assert_allclose(mspec, g['mspec'], rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(O.log_mel_spectrum(g['signal'], nfilters=40), g['cli_logmel40'], rtol=1e-12)
