@@ -287,8 +287,8 @@ __global__ void __launch_bounds__(128) pack16_kernel(const float* __restrict__ W
 // KA16: llh2 [N, Kp] = log2 sum_c 2^(z_tkc)
 // ---------------------------------------------------------------------------------------------
 constexpr int KA_WORKERS = 512, KA_MMA_WARP = KA_WORKERS / 32, KA_LOAD_WARP = KA_MMA_WARP + 1;
-constexpr int KA_LOADERS = 3;           // statistics tiles | weight chunks | (k1, k2) of the chunks
-constexpr int KA_THREADS = KA_WORKERS + 32 + 32 * KA_LOADERS;
+constexpr int KA_THREADS = KA_WORKERS + 64;
+constexpr int KA_STAGES = 3;            // weight-chunk ring
 constexpr int K12_RING = 4;
 
 struct KaArgs {
@@ -305,24 +305,27 @@ struct KaArgs {
 
 struct KaBarriers {
     uint64_t a_full[2], a_empty[2];
-    uint64_t b_full[2], b_empty[2];
+    uint64_t b_full[KA_STAGES], b_empty[KA_STAGES];
     uint64_t t_full[2], t_empty[2];
     uint32_t tmem_base;
     uint32_t pad[3];
 };
 
+// The statistics tile of 128 frames is the A operand and lives in TENSOR MEMORY (lane = frame, 40 columns of fp16 pairs
+// for hi and 40 for lo): with both operands in shared memory a 128 x 160 x 16 MMA took ~190 cycles against an 80-cycle
+// floor (9 KB of operand fetch per MMA); from tensor memory only the 5 KB weight slice is fetched.
 template <int KP, int C>
 __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a, const __grid_constant__ CUtensorMap omap) {
     constexpr int FR = 128, KSTEPS = KP / 16;
     constexpr uint32_t LBO = 128, SBO = KP * 16;
-    constexpr int A_HALF = FR * KP;                     // halfs of one A image (hi or lo) of a 128-frame tile
     constexpr int UNIT = C < 8 ? 8 : C;                 // columns per epilogue unit (whole pdfs, one tcgen05.ld)
     constexpr int PPU = UNIT / C;                       // pdfs per unit
+    constexpr uint32_t COL_A0 = 160, COL_A1 = 416;      // accumulators at columns 0 and 256 (<= 160 wide), A tiles behind them
+    static_assert(KP <= 96, "tensor memory");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __half* As = reinterpret_cast<__half*>(smem_raw);                        // [2][hi | lo]
-    __half* Bs = As + 2 * 2 * A_HALF;                                        // [2][hi | lo] of NB x KP
+    __half* Bs = reinterpret_cast<__half*>(smem_raw);                        // [KA_STAGES][hi | lo] of NB x KP
     const int b_stage = 2 * a.NB * KP;
-    float2* s_k12 = reinterpret_cast<float2*>(Bs + 2 * b_stage);             // [K12_RING][NB] (k1, k2)
+    float2* s_k12 = reinterpret_cast<float2*>(Bs + KA_STAGES * b_stage);     // [K12_RING][NB] (k1, k2)
     KaBarriers* bars = reinterpret_cast<KaBarriers*>(s_k12 + K12_RING * a.NB);
     // staged output: [4 lane quarters][3 buffers][32 frames][NB / C pdfs] (128-byte aligned)
     float* s_out = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(bars + 1) + 127) & ~uintptr_t(127));
@@ -333,12 +336,14 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a, con
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&bars->a_full[i], 1);
+            mbar_init(&bars->a_full[i], 128);
             mbar_init(&bars->a_empty[i], 1);
-            mbar_init(&bars->b_full[i], 2);
-            mbar_init(&bars->b_empty[i], 1);
             mbar_init(&bars->t_full[i], 1);
             mbar_init(&bars->t_empty[i], KA_WORKERS);
+        }
+        for (int i = 0; i < KA_STAGES; ++i) {
+            mbar_init(&bars->b_full[i], 1);
+            mbar_init(&bars->b_empty[i], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -348,40 +353,23 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a, con
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
-    if (warp >= KA_LOAD_WARP) {
-        // one issuing thread per stream of copies (a thread sustains about one copy per 500 cycles)
+    if (warp == KA_LOAD_WARP) {
+        // weight chunks + their (k1, k2) through a KA_STAGES-deep ring
         if (elect_one()) {
-            const int which = warp - KA_LOAD_WARP;
-            uint32_t it = 0, tile_it = 0;
-            const uint32_t half_bytes = TILE * KP * 2, b_bytes = (uint32_t)b_stage * 2u, k_bytes = (uint32_t)a.NB * 8u;
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
-                if (which == 0) {
-                    const int ab = tile_it & 1;
-                    mbar_wait(&bars->a_empty[ab], ((tile_it >> 1) & 1) ^ 1);
-                    const int64_t tA = 2 * tile, tB = tA + 1;
-                    const bool two = tB < n_tiles64;
-                    mbar_arrive_expect_tx(&bars->a_full[ab], (two ? 4u : 2u) * half_bytes);
-                    __half* dst = As + (size_t)ab * 2 * A_HALF;
-                    const __half* srcA = a.img1 + (size_t)tA * (2 * TILE * KP);
-                    bulk_g2s(dst, srcA, half_bytes, &bars->a_full[ab]);                              // hi, rows 0..63
-                    bulk_g2s(dst + A_HALF, srcA + TILE * KP, half_bytes, &bars->a_full[ab]);         // lo, rows 0..63
-                    if (two) {
-                        const __half* srcB = a.img1 + (size_t)tB * (2 * TILE * KP);
-                        bulk_g2s(dst + TILE * KP, srcB, half_bytes, &bars->a_full[ab]);                       // hi, rows 64..127
-                        bulk_g2s(dst + A_HALF + TILE * KP, srcB + TILE * KP, half_bytes, &bars->a_full[ab]);  // lo
-                    }
-                    continue;
-                }
+            uint32_t it = 0;
+            int st = 0;
+            uint32_t ph = 0;
+            const uint32_t b_bytes = (uint32_t)b_stage * 2u, k_bytes = (uint32_t)a.NB * 8u;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 for (int c = 0; c < a.n_chunks; ++c, ++it) {
-                    const int st = it & 1;
-                    mbar_wait(&bars->b_empty[st], ((it >> 1) & 1) ^ 1);
-                    if (which == 1) {
-                        trace(a.trace, it, 0);
-                        mbar_arrive_expect_tx(&bars->b_full[st], b_bytes);
-                        bulk_g2s(Bs + (size_t)st * b_stage, a.wimg + (size_t)c * b_stage, b_bytes, &bars->b_full[st]);
-                    } else {
-                        mbar_arrive_expect_tx(&bars->b_full[st], k_bytes);
-                        bulk_g2s(s_k12 + (it & (K12_RING - 1)) * a.NB, a.k12 + (size_t)c * a.NB, k_bytes, &bars->b_full[st]);
+                    mbar_wait(&bars->b_empty[st], ph ^ 1);
+                    trace(a.trace, it, 0);
+                    mbar_arrive_expect_tx(&bars->b_full[st], b_bytes + k_bytes);
+                    bulk_g2s(Bs + (size_t)st * b_stage, a.wimg + (size_t)c * b_stage, b_bytes, &bars->b_full[st]);
+                    bulk_g2s(s_k12 + (it & (K12_RING - 1)) * a.NB, a.k12 + (size_t)c * a.NB, k_bytes, &bars->b_full[st]);
+                    if (++st == KA_STAGES) {
+                        st = 0;
+                        ph ^= 1;
                     }
                 }
             }
@@ -390,13 +378,15 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a, con
         if (elect_one()) {
             const uint32_t idesc = (1u << 4) | ((uint32_t)(a.NB >> 3) << 17) | ((uint32_t)(FR >> 4) << 24);   // f16 x f16 -> f32
             uint32_t it = 0, tile_it = 0;
+            int st = 0;
+            uint32_t ph = 0;
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
                 const int ab = tile_it & 1;
                 mbar_wait(&bars->a_full[ab], (tile_it >> 1) & 1);
-                const uint32_t a_hi = smem_u32(As + (size_t)ab * 2 * A_HALF), a_lo = a_hi + A_HALF * 2u;
+                const uint32_t a_hi = tmem_base + (ab ? COL_A1 : COL_A0), a_lo = a_hi + KP / 2;
                 for (int c = 0; c < a.n_chunks; ++c, ++it) {
-                    const int st = it & 1, buf = it & 1;
-                    mbar_wait(&bars->b_full[st], (it >> 1) & 1);
+                    const int buf = it & 1;
+                    mbar_wait(&bars->b_full[st], ph);
                     trace(a.trace, it, 1);
                     mbar_wait(&bars->t_empty[buf], ((it >> 1) & 1) ^ 1);
                     trace(a.trace, it, 2);
@@ -404,17 +394,20 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a, con
                     const uint32_t b_hi = smem_u32(Bs + (size_t)st * b_stage), b_lo = b_hi + (uint32_t)a.NB * KP * 2u;
                     const uint32_t d_tmem = tmem_base + (uint32_t)buf * 256u;
                     // descriptors of k-step s = the first one + 16 s (256 bytes >> 4): additions on the uniform datapath
-                    const uint64_t dah = make_desc(a_hi, LBO, SBO), dal = make_desc(a_lo, LBO, SBO);
                     const uint64_t dbh = make_desc(b_hi, LBO, SBO), dbl = make_desc(b_lo, LBO, SBO);
 #pragma unroll
                     for (int s = 0; s < KSTEPS; ++s) {
-                        umma_f16_ss(d_tmem, dah + 16u * s, dbh + 16u * s, idesc, s > 0);
-                        umma_f16_ss(d_tmem, dah + 16u * s, dbl + 16u * s, idesc, 1);      // statistics hi x weights lo
-                        umma_f16_ss(d_tmem, dal + 16u * s, dbh + 16u * s, idesc, 1);      // statistics lo x weights hi
+                        umma_f16_ts(d_tmem, a_hi + 8u * s, dbh + 16u * s, idesc, s > 0);
+                        umma_f16_ts(d_tmem, a_hi + 8u * s, dbl + 16u * s, idesc, 1);      // statistics hi x weights lo
+                        umma_f16_ts(d_tmem, a_lo + 8u * s, dbh + 16u * s, idesc, 1);      // statistics lo x weights hi
                     }
                     umma_commit(&bars->t_full[buf]);
                     umma_commit(&bars->b_empty[st]);
                     trace(a.trace, it, 3);
+                    if (++st == KA_STAGES) {
+                        st = 0;
+                        ph ^= 1;
+                    }
                 }
                 umma_commit(&bars->a_empty[ab]);
             }
@@ -427,8 +420,42 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a, con
         const int n_units = a.NB / UNIT;
         const int u0 = cq * n_units / 4, u1 = (cq + 1) * n_units / 4;
         const int qq = warp & 3;
-        uint32_t it = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        // the statistics row of this thread's frame: image tile -> registers -> tensor memory (first warp of each quarter)
+        auto load_a = [&](int64_t tile, uint32_t tile_it) {
+            const int ab = tile_it & 1;
+            mbar_wait(&bars->a_empty[ab], ((tile_it >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const int64_t t64 = 2 * tile + (r >> 6);
+            const int f = r & 63;
+            const uint4* src = reinterpret_cast<const uint4*>(a.img1 + (size_t)t64 * (2 * TILE * KP) + (f >> 3) * (KP * 8) + (f & 7) * 8);
+            const bool have = t64 < n_tiles64;
+            const uint32_t taddr = tmem_base + lane_addr + (ab ? COL_A1 : COL_A0);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {                 // hi image, lo image
+                uint32_t w[KP / 2];
+#pragma unroll
+                for (int k8 = 0; k8 < KP / 8; ++k8) {     // 16-byte row pieces, 128 bytes apart
+                    const uint4 v = have ? __ldg(src + h * (TILE * KP / 8) + k8 * 8) : make_uint4(0u, 0u, 0u, 0u);
+                    w[4 * k8] = v.x; w[4 * k8 + 1] = v.y; w[4 * k8 + 2] = v.z; w[4 * k8 + 3] = v.w;
+                }
+#pragma unroll
+                for (int c = 0; c < KP / 2; c += 8) {
+                    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(
+                                     taddr + (uint32_t)(h * (KP / 2) + c)),
+                                 "r"(w[c]), "r"(w[c + 1]), "r"(w[c + 2]), "r"(w[c + 3]), "r"(w[c + 4]), "r"(w[c + 5]),
+                                 "r"(w[c + 6]), "r"(w[c + 7])
+                                 : "memory");
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&bars->a_full[ab]);
+        };
+        uint32_t it = 0, tile_it = 0;
+        if (cq == 0 && (int64_t)blockIdx.x < n_tiles) load_a(blockIdx.x, 0);
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+            // the next tile's statistics go to the other A buffer while this tile's chunks run
+            if (cq == 0 && tile + gridDim.x < n_tiles) load_a(tile + gridDim.x, tile_it + 1);
             const int64_t t = tile * FR + r;
             const bool valid = t < a.N;
             float* orow = a.llh2 + (size_t)(valid ? t : 0) * a.ld;
@@ -514,7 +541,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a, con
 }
 
 static size_t ka_smem(int KP, int NB, int C) {
-    return (size_t)2 * 2 * 128 * KP * 2 + (size_t)2 * 2 * NB * KP * 2 + (size_t)K12_RING * NB * 8 + sizeof(KaBarriers) + 128 +
+    return (size_t)KA_STAGES * 2 * NB * KP * 2 + (size_t)K12_RING * NB * 8 + sizeof(KaBarriers) + 128 +
            (size_t)4 * 3 * 32 * (NB / C) * 4 + 1024;
 }
 
