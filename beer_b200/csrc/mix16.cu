@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(128) pack16_kernel(const float* __restrict__ W
 constexpr int KA_WORKERS = 512, KA_MMA_WARP = KA_WORKERS / 32, KA_LOAD_WARP = KA_MMA_WARP + 1;
 constexpr int KA_THREADS = KA_WORKERS + 64;
 constexpr int KA_STAGES = 3;            // weight-chunk ring
-constexpr int K12_RING = 4;
+constexpr int K12_RING = 8;             // the loader runs up to KA_STAGES + 2 chunks ahead of the epilogue that reads (k1, k2)
 
 struct KaArgs {
     const __half* img1;
