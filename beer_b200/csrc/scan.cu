@@ -1549,6 +1549,328 @@ static int launch_fb_lrb(const FbArgs& a, int n_utts, cudaStream_t st) {
     return BEER_OK;
 }
 
+// ---------------------------------------------------------------------------
+// The multi-warp loop kernel with U units per lane (hmm_fb_lrc_kernel<SU, W, U>): W x 32 x U >= P units with HALF the
+// threads of the one-unit-per-lane kernel, so that more utterances are resident per SM.  The scan is latency bound
+// (three block exchanges per frame), its throughput is the number of utterances in flight: 1250 utterances of the
+// 1000-state graph (BASELINE configs[2]) over 148 SMs need 8.45 resident utterances per SM to finish in ONE wave;
+// the one-unit kernel fits 4 (64 registers x 256 threads) = three waves.  Per-state weights are re-read through the
+// read-only cache every step instead of living in registers (56 registers per thread at 9 blocks of 128 threads).
+// ---------------------------------------------------------------------------
+template <int SU, int W, int U, bool LP>
+__global__ void __launch_bounds__(W * 32, 9) hmm_fb_lrc_kernel(FbArgs a) {
+    constexpr int S = SU * U;
+    static_assert(S % 4 == 0, "float4 rows");
+    constexpr int PF = 3;
+    constexpr int ROW = 32 * S;                 // one warp's slice of a row
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* ring_p = smem + (size_t)warp * (2 * PF * ROW);
+    float* ring_a = ring_p + PF * ROW;
+    float* xch = smem + (size_t)W * (2 * PF * ROW);     // [2][W][4] exchange slots
+    const int K = a.K;
+    const float p_scale = a.scale * a.llh_mul;
+    const int k0 = (warp * 32 + lane) * S;      // first state of this lane
+    const bool own = k0 < K;
+    for (int i = lane; i < 2 * PF * ROW; i += 32) ring_p[i] = 0.f;
+    __syncwarp();
+    const float* w_self_p = a.lr_w + k0;
+    const float* w_in_p = a.lr_w + a.lr_row + k0;
+    float w_jout[U];
+#pragma unroll
+    for (int q = 0; q < U; ++q) w_jout[q] = own ? __ldg(a.lr_w + 2 * a.lr_row + k0 + q * SU + SU - 1) : kNegInf;
+
+    auto load_w = [&](const float* src, float* out) {       // rows are padded with -inf up to lr_row >= K
+#pragma unroll
+        for (int v = 0; v < S / 4; ++v) {
+            const float4 x = own ? __ldg(reinterpret_cast<const float4*>(src) + v)
+                                 : make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
+            out[4 * v] = x.x; out[4 * v + 1] = x.y; out[4 * v + 2] = x.z; out[4 * v + 3] = x.w;
+        }
+    };
+    auto prefetch = [&](float* slot, const float* row) {
+#pragma unroll
+        for (int v = 0; v < S / 4; ++v)
+            if (k0 + 4 * v < K) cp_async16(slot + lane * S + 4 * v, row + k0 + 4 * v);
+    };
+    auto read_row = [&](const float* slot, float* out) {
+#pragma unroll
+        for (int v = 0; v < S / 4; ++v) {
+            const float4 x = reinterpret_cast<const float4*>(slot + lane * S)[v];
+            out[4 * v] = x.x; out[4 * v + 1] = x.y; out[4 * v + 2] = x.z; out[4 * v + 3] = x.w;
+        }
+    };
+    auto write_row = [&](float* row, const float* v, float mul) {
+#pragma unroll
+        for (int q = 0; q < S / 4; ++q)
+            if (k0 + 4 * q < K)
+                reinterpret_cast<float4*>(row + k0)[q] =
+                    make_float4(mul * v[4 * q], mul * v[4 * q + 1], mul * v[4 * q + 2], mul * v[4 * q + 3]);
+    };
+    int xn = 0;
+    auto exchange = [&](float m, float s, float e, float& M, float& Ssum, float& E) {
+        float* slot = xch + (xn & 1) * (W * 4);
+        ++xn;
+        if (lane == 0) {
+            slot[warp * 4] = m;
+            slot[warp * 4 + 1] = s;
+            slot[warp * 4 + 2] = e;
+        }
+        __syncthreads();
+        float mm[W];
+        M = kNegInf;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            mm[w] = slot[w * 4];
+            M = fmaxf(M, mm[w]);
+        }
+        const float Ms = (M == kNegInf) ? 0.f : M;
+        Ssum = 0.f;
+        E = 0.f;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            const float f = ex2(mm[w] - Ms);
+            Ssum = fmaf(slot[w * 4 + 1], f, Ssum);
+            E = fmaf(slot[w * 4 + 2], f, E);
+        }
+        M = Ms;
+    };
+
+    for (int u = blockIdx.x; u < a.n_utts; u += gridDim.x) {
+        const int64_t t0 = a.utt_off[u];
+        const int T = (int)(a.utt_off[u + 1] - t0);
+        if (T <= 0) {
+            if (threadIdx.x == 0) {
+                a.utt_exp_llh[u] = 0.0;
+                if (a.utt_logz) a.utt_logz[u] = 0.0;
+            }
+            continue;
+        }
+        const float* pl_u = a.pl + (size_t)t0 * a.ld;
+        float* la_u = a.la_ws + (size_t)t0 * a.Kw;
+        double logz2 = 0.0;
+
+        // ------------------------------ forward ------------------------------
+        for (int r = 0; r < PF; ++r) {
+            if (r < T) prefetch(ring_p + r * ROW, pl_u + (size_t)r * a.ld);
+            cp_async_commit();
+        }
+        float cur[S], jv = kNegInf;
+        int slot = 0;
+        for (int t = 0; t < T; ++t) {
+            cp_async_wait<PF - 1>();
+            float p[S];
+            read_row(ring_p + slot * ROW, p);
+            if (t + PF < T) prefetch(ring_p + slot * ROW, pl_u + (size_t)(t + PF) * a.ld);
+            cp_async_commit();
+            slot = (slot + 1 == PF) ? 0 : slot + 1;
+            if (t == 0) {
+#pragma unroll
+                for (int j = 0; j < S; ++j)
+                    cur[j] = fmaf(p[j], p_scale, (k0 + j < K) ? __ldg(a.fwd.start + k0 + j) : kNegInf);
+            } else {
+                float ws[S], wi[S], v[S];
+                load_w(w_self_p, ws);
+                load_w(w_in_p, wi);
+#pragma unroll
+                for (int j = 0; j < S; ++j)
+                    v[j] = lse2(cur[j] + ws[j], ((j % SU == 0) ? jv : cur[j - (j % SU == 0 ? 0 : 1)]) + wi[j]);
+#pragma unroll
+                for (int j = 0; j < S; ++j) cur[j] = fmaf(p[j], p_scale, v[j]);
+            }
+            float ml = cur[0];
+#pragma unroll
+            for (int j = 1; j < S; ++j) ml = fmaxf(ml, cur[j]);
+            ml = warp_max(ml);
+            const float mls = (ml == kNegInf) ? 0.f : ml;
+            float se = 0.f;
+#pragma unroll
+            for (int q = 0; q < U; ++q) se += ex2(cur[q * SU + SU - 1] + w_jout[q] - mls);
+            const float sl = warp_sum(se);
+            float mx, js, unused;
+            exchange(ml, sl, 0.f, mx, js, unused);
+            jv = lg2(js);                         // junction of the NORMALISED values
+            logz2 += (double)mx;
+#pragma unroll
+            for (int j = 0; j < S; ++j) cur[j] -= mx;
+            write_row(la_u + (size_t)t * a.Kw, cur, 1.f);
+        }
+        cp_async_wait<0>();
+
+        if (a.utt_logz != nullptr) {
+            float m = kNegInf, v[S];
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                v[j] = cur[j] + ((k0 + j < K) ? __ldg(a.bwd.start + k0 + j) : kNegInf);
+                m = fmaxf(m, v[j]);
+            }
+            m = warp_max(m);
+            const float ms = (m == kNegInf) ? 0.f : m;
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < S; ++j) sum += ex2(v[j] - ms);
+            sum = warp_sum(sum);
+            float M, Ssum, unused;
+            exchange(m, sum, 0.f, M, Ssum, unused);
+            double rs = 0.0;
+            if (a.frame_ref != nullptr && warp == 0)
+                for (int t = lane; t < T; t += 32) rs += (double)a.frame_ref[t0 + t];
+            rs = warp_sum(rs);
+            if (threadIdx.x == 0)
+                a.utt_logz[u] = (logz2 + (double)M + (double)lg2(Ssum)) * (double)kLn2 + (double)a.scale * rs;
+        }
+
+        // ------------------------------ backward -----------------------------
+        __threadfence_block();
+        __syncthreads();         // every warp's la stores are visible to every warp's async copies
+        for (int r = 0; r < PF; ++r) {
+            const int t = T - 1 - r;
+            if (t >= 0) {
+                prefetch(ring_p + r * ROW, pl_u + (size_t)t * a.ld);
+                prefetch(ring_a + r * ROW, la_u + (size_t)t * a.Kw);
+            }
+            cp_async_commit();
+        }
+        float lb[S];
+        {
+            float m = kNegInf;
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                lb[j] = (k0 + j < K) ? __ldg(a.bwd.start + k0 + j) : kNegInf;
+                m = fmaxf(m, lb[j]);
+            }
+            m = warp_max(m);
+            float M, s0, s1;
+            exchange(m, 0.f, 0.f, M, s0, s1);
+#pragma unroll
+            for (int j = 0; j < S; ++j) lb[j] -= M;
+        }
+        float ell = 0.f;
+        double ell_d = 0.0;
+        slot = 0;
+        for (int i = 0; i < T; ++i) {
+            const int t = T - 1 - i;
+            cp_async_wait<PF - 1>();
+            float p[S], v[S];
+            read_row(ring_p + slot * ROW, p);
+            read_row(ring_a + slot * ROW, v);
+#pragma unroll
+            for (int j = 0; j < S; ++j) p[j] *= p_scale;
+            if (t - PF >= 0) {
+                prefetch(ring_p + slot * ROW, pl_u + (size_t)(t - PF) * a.ld);
+                prefetch(ring_a + slot * ROW, la_u + (size_t)(t - PF) * a.Kw);
+            }
+            cp_async_commit();
+            slot = (slot + 1 == PF) ? 0 : slot + 1;
+
+            // gamma_t: exchange (max, sum, sum of p * 2^(v - max))
+            float m = kNegInf;
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                v[j] = (k0 + j < K) ? v[j] + lb[j] : kNegInf;
+                m = fmaxf(m, v[j]);
+            }
+            m = warp_max(m);
+            const float mls = (m == kNegInf) ? 0.f : m;
+            float sl = 0.f, pe = 0.f;
+            float vlog[LP ? S : 1];
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                if constexpr (LP) vlog[j] = v[j];
+                v[j] = ex2(v[j] - mls);
+                sl += v[j];
+                pe = fmaf(p[j], v[j], pe);
+            }
+            sl = warp_sum(sl);
+            pe = warp_sum(pe);
+            float ms, sum, pes;
+            exchange(m, sl, pe, ms, sum, pes);
+            const float inv = (sum > 0.f) ? __fdividef(1.f, sum) : 0.f;
+            const float resc = ex2(mls - ms) * inv;            // this warp's values -> block normalisation
+            if constexpr (LP) {
+                const float lnorm = lg2(a.scale) - ms - lg2(sum);
+#pragma unroll
+                for (int j = 0; j < S; ++j) vlog[j] += lnorm;
+                write_row(a.pdf_lpost + (size_t)(t0 + t) * a.ld_lpost, vlog, 1.f);
+            }
+            if (a.state_post != nullptr || a.pdf_post != nullptr) {
+#pragma unroll
+                for (int j = 0; j < S; ++j) v[j] *= resc;
+                if (a.state_post != nullptr) write_row(a.state_post + (size_t)(t0 + t) * K, v, 1.f);
+                if (a.pdf_post != nullptr) write_row(a.pdf_post + (size_t)(t0 + t) * a.ld_post, v, a.scale);
+            }
+            if (threadIdx.x == 0) {
+                ell += pes * inv;
+                if ((i & 31) == 31) {
+                    ell_d += (double)ell;
+                    ell = 0.f;
+                }
+                if (a.frame_exp_llh != nullptr) {
+                    const float r = (a.frame_ref != nullptr) ? a.scale * a.frame_ref[t0 + t] : 0.f;
+                    a.frame_exp_llh[t0 + t] = pes * inv * kLn2 + r;
+                }
+            }
+            if (t == 0) break;
+            // beta_{t-1}: exchange (max of delta, junction partial over the unit starts); delta overwrites p
+            float ws[S], wi[S];
+            load_w(w_self_p, ws);
+            load_w(w_in_p, wi);
+            float md = kNegInf;
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                p[j] += lb[j];
+                md = fmaxf(md, p[j]);
+            }
+            md = warp_max(md);
+            const float mds = (md == kNegInf) ? 0.f : md;
+            float sj = 0.f;
+#pragma unroll
+            for (int q = 0; q < U; ++q) sj += ex2(p[q * SU] + wi[q * SU] - mds);
+            sj = warp_sum(sj);
+            float Md, Sj, unused;
+            exchange(md, sj, 0.f, Md, Sj, unused);
+            const float jb = Md + lg2(Sj);
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                const bool end = (j % SU == SU - 1);
+                const float nxt = end ? jb + w_jout[j / SU] : p[end ? j : j + 1] + wi[end ? j : j + 1];
+                lb[j] = lse2(p[j] + ws[j], nxt) - Md;      // normalised by max(delta): <= 1
+            }
+        }
+        cp_async_wait<0>();
+        if (threadIdx.x == 0) {
+            ell_d += (double)ell;
+            a.utt_exp_llh[u] = ell_d * (double)kLn2;
+        }
+        if (warp == 0) {
+            double rs = 0.0;
+            if (a.frame_ref != nullptr)
+                for (int t = lane; t < T; t += 32) rs += (double)a.frame_ref[t0 + t];
+            rs = warp_sum(rs);
+            __syncwarp();
+            if (lane == 0) a.utt_exp_llh[u] += (double)a.scale * rs;
+        }
+        __syncthreads();
+    }
+}
+
+template <int SU, int W, int U, bool LP = false>
+static int launch_fb_lrc(const FbArgs& a, int n_utts, cudaStream_t st) {
+    if (!LP && a.pdf_lpost != nullptr) return launch_fb_lrc<SU, W, U, true>(a, n_utts, st);
+    constexpr int PF = 3;
+    size_t smem = sizeof(float) * ((size_t)W * (2 * PF * 32 * SU * U) + 2 * W * 4);
+    static bool attr_set = false;
+    if (!attr_set) {
+        BEER_CUDA_TRY(cudaFuncSetAttribute(hmm_fb_lrc_kernel<SU, W, U, LP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem));
+        attr_set = true;
+    }
+    int blocks = n_utts < kNumSMs * 9 ? n_utts : kNumSMs * 9;
+    hmm_fb_lrc_kernel<SU, W, U, LP><<<blocks, W * 32, smem, st>>>(a);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
 // ------------------------------- Viterbi -----------------------------------
 struct VitArgs {
     ScanLists vit;
@@ -2177,6 +2499,12 @@ int beer_hmm_forward_backward_ex(const beer_graph_plan* plan, const float* pdf_l
     if (plan->lr_su && plan->map_identity && (force == nullptr || force[0] == 'l') && (!lr_vec || lr_rows_ok)) {
         const int u = plan->lr_u;
         if (u == 8 && unit_counts == nullptr) {
+            // many utterances: two units per lane on four warps, nine utterances resident per SM (one wave up to 1332
+            // utterances); few: the one-unit-per-lane kernel on eight warps has the shorter steps
+            const char* lrc = getenv("BEER_B200_SCAN_LRC");       // debug: "0" / "1" forces the choice
+            const bool many = lrc != nullptr ? lrc[0] == '1' : n_utts > kNumSMs * 4;
+            if (plan->lr_su == 4 && plan->K <= 4 * 32 * 2 * 4 && plan->K % 4 == 0 && many)
+                return launch_fb_lrc<4, 4, 2>(a, n_utts, st);
             if (plan->lr_su == 4) return launch_fb_lrb<4, 8>(a, n_utts, st);
             if (plan->lr_su == 3) return launch_fb_lrb<3, 8>(a, n_utts, st);
         }

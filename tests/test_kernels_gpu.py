@@ -298,11 +298,14 @@ def test_ragged_batch_equals_single(ops):
         np.testing.assert_allclose(r['utt_exp_llh'][i].item(), want['exp_llh'].sum(), rtol=1e-6)
 
 
-@pytest.mark.parametrize('P,S', [(130, 4), (250, 4), (140, 3)])
-def test_forward_backward_many_units_block_kernel(ops, P, S, monkeypatch):
+@pytest.mark.parametrize('P,S,lrc', [(130, 4, '0'), (250, 4, '0'), (140, 3, '0'), (250, 4, '1'), (130, 4, '1'),
+                                     (256, 4, '1')])
+def test_forward_backward_many_units_block_kernel(ops, P, S, lrc, monkeypatch):
     """Loops with more than 128 units (BASELINE configs[2]: 250 units x 4 states) run W warps per utterance
-    with one shared-memory exchange per reduction; same posteriors / evidence as the generic kernel and as
+    with one shared-memory exchange per reduction (lrc = '1': the two-units-per-lane variant on four warps that large
+    batches take; '0': one unit per lane on eight warps); same posteriors / evidence as the generic kernel and as
     the fp64 oracle on a ragged batch."""
+    monkeypatch.setenv('BEER_B200_SCAN_LRC', lrc)
     from beer_b200 import synthetic
     cg, _, _ = synthetic.phone_loop_graph(P, S)
     K = P * S
@@ -331,6 +334,12 @@ def test_forward_backward_many_units_block_kernel(ops, P, S, monkeypatch):
     with np.errstate(all='ignore'):
         gamma, _ = O.posteriors(0.8 * llh[off[u]:off[u + 1]].astype(np.float64), *g64)
     assert np.abs(outs['best']['state_post'][off[u]:off[u + 1]] - gamma).max() <= 1e-5
+    # log2 posteriors straight from the loop kernel
+    monkeypatch.delenv('BEER_B200_SCAN', raising=False)
+    lp = torch.empty(int(off[-1]), K, device='cuda')
+    ops.hmm_forward_backward(plan, dev(llh), None, dev(off, torch.int64), scale=0.8, want_pdf_post=False,
+                             out_pdf_lpost=lp)
+    assert np.abs(np.exp2(lp.double().cpu().numpy()) - outs['best']['pdf_post']).max() <= 2e-6
 
 
 @pytest.mark.parametrize('P,SU', [(8, 4), (25, 4), (11, 3), (32, 4)])
