@@ -1132,7 +1132,8 @@ __global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_lr_kernel(FbArgs a) {
             sum = warp_sum(sum);
             const float inv = (sum > 0.f) ? __fdividef(1.f, sum) : 0.f;
             if constexpr (LP) {
-                const float lnorm = lg2(a.scale) - lg2(sum);   // log2(scale gamma) = log value - log2 sum + log2 scale
+                // log2(scale gamma) = log value - log2 sum + log2 scale; an impossible frame (sum = 0) gives -inf, not NaN
+                const float lnorm = (sum > 0.f) ? lg2(a.scale) - lg2(sum) : kNegInf;
 #pragma unroll
                 for (int j = 0; j < S; ++j) vlog[j] += lnorm;
                 write_row(a.pdf_lpost + (size_t)(t0 + t) * a.ld_lpost, vlog, 1.f);
@@ -1472,7 +1473,7 @@ __global__ void __launch_bounds__(W * 32, 4) hmm_fb_lrb_kernel(FbArgs a) {
             const float inv = (sum > 0.f) ? __fdividef(1.f, sum) : 0.f;
             const float resc = ex2(mls - ms) * inv;            // this warp's values -> block normalisation
             if constexpr (LP) {
-                const float lnorm = lg2(a.scale) - ms - lg2(sum);
+                const float lnorm = (sum > 0.f) ? lg2(a.scale) - ms - lg2(sum) : kNegInf;
 #pragma unroll
                 for (int j = 0; j < S; ++j) vlog[j] += lnorm;
                 write_row(a.pdf_lpost + (size_t)(t0 + t) * a.ld_lpost, vlog, 1.f);
@@ -1788,7 +1789,7 @@ __global__ void __launch_bounds__(W * 32, 9) hmm_fb_lrc_kernel(FbArgs a) {
             const float inv = (sum > 0.f) ? __fdividef(1.f, sum) : 0.f;
             const float resc = ex2(mls - ms) * inv;            // this warp's values -> block normalisation
             if constexpr (LP) {
-                const float lnorm = lg2(a.scale) - ms - lg2(sum);
+                const float lnorm = (sum > 0.f) ? lg2(a.scale) - ms - lg2(sum) : kNegInf;
 #pragma unroll
                 for (int j = 0; j < S; ++j) vlog[j] += lnorm;
                 write_row(a.pdf_lpost + (size_t)(t0 + t) * a.ld_lpost, vlog, 1.f);
@@ -1867,6 +1868,352 @@ static int launch_fb_lrc(const FbArgs& a, int n_utts, cudaStream_t st) {
     }
     int blocks = n_utts < kNumSMs * 9 ? n_utts : kNumSMs * 9;
     hmm_fb_lrc_kernel<SU, W, U, LP><<<blocks, W * 32, smem, st>>>(a);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Aligned left-to-right loop with MANY units on ONE warp per utterance (hmm_fb_lrw_kernel<SU, U>): a lane owns U = 8
+// whole units (S = 32 states for the 250 x 4 = 1000-state graph of BASELINE configs[2]).  The multi-warp kernels above
+// spend most of their ~4300 warp-instructions per frame on what they replicate per warp (ring bookkeeping, block
+// exchanges recombined by every warp, reductions): with the whole utterance on one warp the junction and the
+// normaliser are warp reductions again, a frame costs ~1100 warp-instructions and 32 independent log-add chains per
+// lane hide each other's latency.  Registers hold only the recursion state (alpha / beta row slice, llh slice); the
+// per-state weights live in shared memory, shared by the 12 warps of the block, rows of the llh / alpha rings and the
+// weights are stored float4-interleaved ([vector][lane]) so that 16-byte accesses of a warp are conflict-free.
+// ---------------------------------------------------------------------------
+constexpr int LRW_WARPS = 12;
+
+template <int SU, int U, bool LP>
+__global__ void __launch_bounds__(LRW_WARPS * 32, 1) hmm_fb_lrw_kernel(FbArgs a) {
+    constexpr int S = SU * U, V = S / 4;
+    static_assert(S % 4 == 0, "float4 rows");
+    constexpr int PF = 2;
+    constexpr int ROW = 32 * S;
+    extern __shared__ __align__(16) float smem[];
+    float* s_wself = smem;                      // [V][32] float4, interleaved
+    float* s_win = smem + ROW;
+    float* s_wjout = smem + 2 * ROW;            // [32 * U] per unit (end state -> junction)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* ring_p = smem + 2 * ROW + 32 * U + (size_t)warp * (2 * PF * ROW);   // [PF][ROW]
+    float* ring_a = ring_p + PF * ROW;
+    const int K = a.K;
+    const float p_scale = a.scale * a.llh_mul;
+    const int gwarp = blockIdx.x * LRW_WARPS + warp, nwarps = gridDim.x * LRW_WARPS;
+    const int k0 = lane * S;
+
+    for (int i = threadIdx.x; i < ROW; i += blockDim.x) {
+        // state k = l * S + 4 v + e  ->  interleaved position (v * 32 + l) * 4 + e
+        const int l = i / S, r = i - l * S, pos = ((r >> 2) * 32 + l) * 4 + (r & 3);
+        s_wself[pos] = __ldg(a.lr_w + i);
+        s_win[pos] = __ldg(a.lr_w + a.lr_row + i);
+    }
+    for (int i = threadIdx.x; i < 32 * U; i += blockDim.x) s_wjout[i] = __ldg(a.lr_w + 2 * a.lr_row + i * SU + SU - 1);
+    for (int i = lane; i < 2 * PF * ROW; i += 32) ring_p[i] = 0.f;
+    __syncthreads();
+
+    auto prefetch = [&](float* slot, const float* row) {
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+            if (k0 + 4 * v < K) cp_async16(slot + (v * 32 + lane) * 4, row + k0 + 4 * v);
+    };
+    auto read_row = [&](const float* slot, float* out) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const float4 q = reinterpret_cast<const float4*>(slot)[v * 32 + lane];
+            out[4 * v] = q.x; out[4 * v + 1] = q.y; out[4 * v + 2] = q.z; out[4 * v + 3] = q.w;
+        }
+    };
+    auto write_row = [&](float* row, const float* v, float mul) {
+#pragma unroll
+        for (int q = 0; q < V; ++q)
+            if (k0 + 4 * q < K)
+                reinterpret_cast<float4*>(row + k0)[q] =
+                    make_float4(mul * v[4 * q], mul * v[4 * q + 1], mul * v[4 * q + 2], mul * v[4 * q + 3]);
+    };
+    // log2-sum-exp2 over the warp of U values per lane
+    auto warp_lse = [&](const float* v) {
+        float m = v[0];
+#pragma unroll
+        for (int u = 1; u < U; ++u) m = fmaxf(m, v[u]);
+        m = warp_max(m);
+        const float ms = (m == kNegInf) ? 0.f : m;
+        float sum = 0.f;
+#pragma unroll
+        for (int u = 0; u < U; ++u) sum += ex2(v[u] - ms);
+        sum = warp_sum(sum);
+        return ms + lg2(sum);
+    };
+    auto row_max = [&](const float* v) {
+        float m = v[0];
+#pragma unroll
+        for (int j = 1; j < S; ++j) m = fmaxf(m, v[j]);
+        return warp_max(m);
+    };
+
+    for (int u = gwarp; u < a.n_utts; u += nwarps) {
+        const int64_t t0 = a.utt_off[u];
+        const int T = (int)(a.utt_off[u + 1] - t0);
+        if (T <= 0) {
+            if (lane == 0) {
+                a.utt_exp_llh[u] = 0.0;
+                if (a.utt_logz) a.utt_logz[u] = 0.0;
+            }
+            continue;
+        }
+        const float* pl_u = a.pl + (size_t)t0 * a.ld;
+        float* la_u = a.la_ws + (size_t)t0 * a.Kw;
+        double logz2 = 0.0;
+
+        // ------------------------------ forward ------------------------------
+        for (int r = 0; r < PF; ++r) {
+            if (r < T) prefetch(ring_p + r * ROW, pl_u + (size_t)r * a.ld);
+            cp_async_commit();
+        }
+        float cur[S];
+        const bool want_logz = a.utt_logz != nullptr;
+        float lz = 0.f;
+        for (int t = 0; t < T; ++t) {
+            cp_async_wait<PF - 1>();
+            float p[S];
+            float* ring_slot = ring_p + (t & (PF - 1)) * ROW;
+            read_row(ring_slot, p);
+            if (t + PF < T) prefetch(ring_slot, pl_u + (size_t)(t + PF) * a.ld);
+            cp_async_commit();
+            if (t == 0) {
+#pragma unroll
+                for (int j = 0; j < S; ++j)
+                    cur[j] = fmaf(p[j], p_scale, (k0 + j < K) ? __ldg(a.fwd.start + k0 + j) : kNegInf);
+            } else {
+                float ends[U];
+#pragma unroll
+                for (int q = 0; q < U; ++q) ends[q] = cur[q * SU + SU - 1] + s_wjout[lane * U + q];
+                const float jv = warp_lse(ends);
+                // in place, last state first: state j needs the OLD value of state j - 1
+#pragma unroll
+                for (int v = V - 1; v >= 0; --v) {
+                    const float4 ws4 = reinterpret_cast<const float4*>(s_wself)[v * 32 + lane];
+                    const float4 wi4 = reinterpret_cast<const float4*>(s_win)[v * 32 + lane];
+                    const float ws[4] = {ws4.x, ws4.y, ws4.z, ws4.w}, wi[4] = {wi4.x, wi4.y, wi4.z, wi4.w};
+#pragma unroll
+                    for (int e = 3; e >= 0; --e) {
+                        const int j = 4 * v + e;
+                        const float prev = (j % SU == 0) ? jv : cur[j == 0 ? 0 : j - 1];
+                        cur[j] = fmaf(p[j], p_scale, lse2(cur[j] + ws[e], prev + wi[e]));
+                    }
+                }
+            }
+            const float mx = row_max(cur);
+            const float mxs = (mx == kNegInf) ? 0.f : mx;
+            if (want_logz) {
+                lz += mxs;
+                if ((t & 15) == 15) {
+                    logz2 += (double)lz;
+                    lz = 0.f;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < S; ++j) cur[j] -= mxs;
+            write_row(la_u + (size_t)t * a.Kw, cur, 1.f);
+        }
+        cp_async_wait<0>();
+        logz2 += (double)lz;
+
+        if (a.utt_logz != nullptr) {
+            float m = kNegInf, v[S];
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                v[j] = cur[j] + ((k0 + j < K) ? __ldg(a.bwd.start + k0 + j) : kNegInf);
+                m = fmaxf(m, v[j]);
+            }
+            m = warp_max(m);
+            const float ms = (m == kNegInf) ? 0.f : m;
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < S; ++j) sum += ex2(v[j] - ms);
+            sum = warp_sum(sum);
+            const double z = (logz2 + (double)ms + (double)lg2(sum)) * (double)kLn2;
+            double rs = 0.0;
+            if (a.frame_ref != nullptr)
+                for (int t = lane; t < T; t += 32) rs += (double)a.frame_ref[t0 + t];
+            rs = warp_sum(rs);
+            if (lane == 0) a.utt_logz[u] = z + (double)a.scale * rs;
+        }
+
+        // ------------------------------ backward -----------------------------
+        __threadfence_block();   // this warp's la stores -> visible to its own async copies
+        __syncwarp();
+        for (int r = 0; r < PF; ++r) {
+            const int t = T - 1 - r;
+            if (t >= 0) {
+                prefetch(ring_p + r * ROW, pl_u + (size_t)t * a.ld);
+                prefetch(ring_a + r * ROW, la_u + (size_t)t * a.Kw);
+            }
+            cp_async_commit();
+        }
+        float lb[S];
+        {
+#pragma unroll
+            for (int j = 0; j < S; ++j) lb[j] = (k0 + j < K) ? __ldg(a.bwd.start + k0 + j) : kNegInf;
+            const float m = row_max(lb);
+            const float ms = (m == kNegInf) ? 0.f : m;
+#pragma unroll
+            for (int j = 0; j < S; ++j) lb[j] -= ms;
+        }
+        float ell = 0.f;
+        double ell_d = 0.0;
+        const bool units = a.unit_counts != nullptr;
+        float cnt[U], dstart[U], mbs_prev = 0.f;   // unit counts, delta_{t+1} of the unit starts
+#pragma unroll
+        for (int q = 0; q < U; ++q) cnt[q] = dstart[q] = 0.f;
+        for (int i = 0; i < T; ++i) {
+            const int t = T - 1 - i;
+            cp_async_wait<PF - 1>();
+            float p[S], la[S];     // p: RAW llh (the scale is folded into the FMAs below)
+            read_row(ring_p + (i & (PF - 1)) * ROW, p);
+            read_row(ring_a + (i & (PF - 1)) * ROW, la);
+            if (t - PF >= 0) {
+                prefetch(ring_p + (i & (PF - 1)) * ROW, pl_u + (size_t)(t - PF) * a.ld);
+                prefetch(ring_a + (i & (PF - 1)) * ROW, la_u + (size_t)(t - PF) * a.Kw);
+            }
+            cp_async_commit();
+
+            float jvf = 0.f;       // forward junction value of frame t (unit counts only)
+            if (units && i > 0) {
+                float ends[U];
+#pragma unroll
+                for (int q = 0; q < U; ++q) ends[q] = la[q * SU + SU - 1] + s_wjout[lane * U + q];
+                jvf = warp_lse(ends);
+            }
+            // la := log2 of the unnormalised posteriors relative to their maximum
+#pragma unroll
+            for (int j = 0; j < S; ++j) la[j] += lb[j];
+            const float m = row_max(la);
+            const float ms = (m == kNegInf) ? 0.f : m;
+            float sum = 0.f, fe = 0.f;      // fe: sum_k llh_k gamma_k in raw-llh units (x p_scale at the end)
+            if constexpr (LP) {
+#pragma unroll
+                for (int j = 0; j < S; ++j) {
+                    la[j] -= ms;
+                    const float e = ex2(la[j]);
+                    sum += e;
+                    fe = fmaf(p[j], e, fe);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < S; ++j) {
+                    la[j] = ex2(la[j] - ms);
+                    sum += la[j];
+                    fe = fmaf(p[j], la[j], fe);
+                }
+            }
+            sum = warp_sum(sum);
+            const float inv = (sum > 0.f) ? __fdividef(1.f, sum) : 0.f;
+            fe *= inv;
+            ell += fe;
+            if ((i & 31) == 31) {
+                ell_d += (double)ell;
+                ell = 0.f;
+            }
+            if (a.frame_exp_llh != nullptr) {
+                const float f = warp_sum(fe);
+                if (lane == 0) {
+                    const float r = (a.frame_ref != nullptr) ? a.scale * a.frame_ref[t0 + t] : 0.f;
+                    a.frame_exp_llh[t0 + t] = f * p_scale * kLn2 + r;
+                }
+            }
+            if (units && sum > 0.f) {
+                // transition posteriors through the junction, reduced over the unit ends (graph.py:308-323,
+                // phoneloop.py:88-97): xi_t(ends -> start_q) = 2^(jv_t + w_in + delta_{t+1}(start_q) - mbs_t - Zg_t)
+                if (i > 0) {
+                    const float base = jvf - mbs_prev - (ms + lg2(sum));
+#pragma unroll
+                    for (int q = 0; q < U; ++q) {
+                        const int j = q * SU;
+                        cnt[q] += ex2(base + s_win[((j >> 2) * 32 + lane) * 4 + (j & 3)] + dstart[q]);
+                    }
+                }
+                if (t == 0) {
+#pragma unroll
+                    for (int q = 0; q < U; ++q) cnt[q] += (LP ? ex2(la[q * SU]) : la[q * SU]) * inv;
+                }
+            }
+            if constexpr (LP) {
+                // log2(scale gamma) = log value - log2 sum + log2 scale; an impossible frame (sum = 0) gives -inf
+                const float lnorm = (sum > 0.f) ? lg2(a.scale) - lg2(sum) : kNegInf;
+#pragma unroll
+                for (int j = 0; j < S; ++j) la[j] += lnorm;
+                write_row(a.pdf_lpost + (size_t)(t0 + t) * a.ld_lpost, la, 1.f);
+            } else {
+                if (a.state_post != nullptr) write_row(a.state_post + (size_t)(t0 + t) * K, la, inv);
+                if (a.pdf_post != nullptr) write_row(a.pdf_post + (size_t)(t0 + t) * a.ld_post, la, a.scale * inv);
+            }
+            if (t == 0) break;
+            // beta_{t-1}: lb := delta_j = p_tj + lb_tj, then the transposed recursion in place, first state first
+#pragma unroll
+            for (int j = 0; j < S; ++j) lb[j] = fmaf(p[j], p_scale, lb[j]);
+            float starts[U];
+#pragma unroll
+            for (int q = 0; q < U; ++q) {
+                const int j = q * SU;
+                dstart[q] = lb[j];
+                starts[q] = lb[j] + s_win[((j >> 2) * 32 + lane) * 4 + (j & 3)];
+            }
+            const float jb = warp_lse(starts);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const float4 ws4 = reinterpret_cast<const float4*>(s_wself)[v * 32 + lane];
+                // w_in of states 4v+1 .. 4v+4 (the successor of each state of the group)
+                const float4 wi4 = reinterpret_cast<const float4*>(s_win)[v * 32 + lane];
+                const float wi_next = (v + 1 < V) ? s_win[((v + 1) * 32 + lane) * 4] : kNegInf;
+                const float ws[4] = {ws4.x, ws4.y, ws4.z, ws4.w}, wn[4] = {wi4.y, wi4.z, wi4.w, wi_next};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int j = 4 * v + e;
+                    const bool end = (j % SU == SU - 1);
+                    const float nxt = end ? jb + s_wjout[lane * U + j / SU] : lb[j + 1 < S ? j + 1 : j] + wn[e];
+                    lb[j] = lse2(lb[j] + ws[e], nxt);
+                }
+            }
+            const float mb = row_max(lb);
+            const float mbs = (mb == kNegInf) ? 0.f : mb;
+#pragma unroll
+            for (int j = 0; j < S; ++j) lb[j] -= mbs;
+            mbs_prev = mbs;
+        }
+        cp_async_wait<0>();
+        if (units) {
+#pragma unroll
+            for (int q = 0; q < U; ++q) {
+                const int unit = lane * U + q;
+                if (unit * SU < K && cnt[q] != 0.f) atomicAdd(a.unit_counts + unit, (double)cnt[q]);
+            }
+        }
+        ell_d += (double)ell;
+        ell_d = warp_sum(ell_d);
+        double rs = 0.0;
+        if (a.frame_ref != nullptr)
+            for (int t = lane; t < T; t += 32) rs += (double)a.frame_ref[t0 + t];
+        rs = warp_sum(rs);
+        if (lane == 0) a.utt_exp_llh[u] = ell_d * (double)p_scale * (double)kLn2 + (double)a.scale * rs;
+        __syncwarp();
+    }
+}
+
+template <int SU, int U, bool LP = false>
+static int launch_fb_lrw(const FbArgs& a, int n_utts, cudaStream_t st) {
+    if (!LP && a.pdf_lpost != nullptr) return launch_fb_lrw<SU, U, true>(a, n_utts, st);
+    constexpr int S = SU * U, PF = 2;
+    size_t smem = sizeof(float) * ((size_t)2 * 32 * S + 32 * U + (size_t)LRW_WARPS * (2 * PF * 32 * S));
+    static bool attr_set = false;
+    if (!attr_set) {
+        BEER_CUDA_TRY(cudaFuncSetAttribute(hmm_fb_lrw_kernel<SU, U, LP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem));
+        attr_set = true;
+    }
+    int blocks = (n_utts + LRW_WARPS - 1) / LRW_WARPS;
+    if (blocks > kNumSMs) blocks = kNumSMs;
+    hmm_fb_lrw_kernel<SU, U, LP><<<blocks, LRW_WARPS * 32, smem, st>>>(a);
     BEER_LAUNCH_CHECK();
     return BEER_OK;
 }
@@ -2430,11 +2777,12 @@ int64_t beer_hmm_workspace_bytes(const beer_graph_plan* plan, int64_t N) {
 }
 
 // Units whose counts the forward-backward kernels can reduce themselves: only the one-warp left-to-right loop
-// kernel (<= 4 units per lane = <= 128 units) with an identity pdf map carries the fused counts.  Everything else
+// kernels (<= 128 units of 3 or 4 states, <= 256 units of 4 states) with an identity pdf map carry the fused counts.  Everything else
 // reports 0 and the caller reduces the ends x starts block of beer_hmm_transition_posteriors instead.
 int beer_hmm_unit_count_size(const beer_graph_plan* plan) {
     if (!plan) return BEER_ERR_ARG;
-    if (!plan->lr_su || !plan->map_identity || plan->lr_u > 4) return 0;
+    if (!plan->lr_su || !plan->map_identity) return 0;
+    if (plan->lr_u > 4 && !(plan->lr_u == 8 && plan->lr_su == 4 && plan->K % 4 == 0)) return 0;
     return plan->K / plan->lr_su;
 }
 
@@ -2498,12 +2846,11 @@ int beer_hmm_forward_backward_ex(const beer_graph_plan* plan, const float* pdf_l
     const bool lr_rows_ok = ld_pdf % 4 == 0 && ((uintptr_t)pdf_llh & 15) == 0 && post_ok;
     if (plan->lr_su && plan->map_identity && (force == nullptr || force[0] == 'l') && (!lr_vec || lr_rows_ok)) {
         const int u = plan->lr_u;
+        // 129 .. 256 units of four states: the whole utterance on ONE warp, eight units per lane (also reduces unit counts)
+        const char* lrc = getenv("BEER_B200_SCAN_LRC");       // debug: "0" = eight warps, "1" = four warps x two units
+        if (u == 8 && plan->lr_su == 4 && plan->K % 4 == 0 && lrc == nullptr) return launch_fb_lrw<4, 8>(a, n_utts, st);
         if (u == 8 && unit_counts == nullptr) {
-            // many utterances: two units per lane on four warps, nine utterances resident per SM (one wave up to 1332
-            // utterances); few: the one-unit-per-lane kernel on eight warps has the shorter steps
-            const char* lrc = getenv("BEER_B200_SCAN_LRC");       // debug: "0" / "1" forces the choice
-            const bool many = lrc != nullptr ? lrc[0] == '1' : n_utts > kNumSMs * 4;
-            if (plan->lr_su == 4 && plan->K <= 4 * 32 * 2 * 4 && plan->K % 4 == 0 && many)
+            if (plan->lr_su == 4 && plan->K <= 4 * 32 * 2 * 4 && plan->K % 4 == 0 && lrc != nullptr && lrc[0] == '1')
                 return launch_fb_lrc<4, 4, 2>(a, n_utts, st);
             if (plan->lr_su == 4) return launch_fb_lrb<4, 8>(a, n_utts, st);
             if (plan->lr_su == 3) return launch_fb_lrb<3, 8>(a, n_utts, st);
