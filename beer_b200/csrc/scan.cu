@@ -2846,9 +2846,13 @@ int beer_hmm_forward_backward_ex(const beer_graph_plan* plan, const float* pdf_l
     const bool lr_rows_ok = ld_pdf % 4 == 0 && ((uintptr_t)pdf_llh & 15) == 0 && post_ok;
     if (plan->lr_su && plan->map_identity && (force == nullptr || force[0] == 'l') && (!lr_vec || lr_rows_ok)) {
         const int u = plan->lr_u;
-        // 129 .. 256 units of four states: the whole utterance on ONE warp, eight units per lane (also reduces unit counts)
-        const char* lrc = getenv("BEER_B200_SCAN_LRC");       // debug: "0" = eight warps, "1" = four warps x two units
-        if (u == 8 && plan->lr_su == 4 && plan->K % 4 == 0 && lrc == nullptr) return launch_fb_lrw<4, 8>(a, n_utts, st);
+        // 129 .. 256 units.  Measured on BASELINE configs[2] (1250 utterances x 1000 frames, 250 units x 4 states): eight
+        // warps x one unit per lane 7.3 ms, four warps x two units 7.5 ms, ONE warp x eight units 12.0 ms (a frame is then
+        // one long dependent instruction stream per warp at 12 warps per SM).  The one-warp kernel is the only one of
+        // the three that reduces unit counts, so it runs when they are asked for.
+        const char* lrc = getenv("BEER_B200_SCAN_LRC");       // debug: "1" = four warps x two units, "w" = one warp
+        if (u == 8 && plan->lr_su == 4 && plan->K % 4 == 0 && (unit_counts != nullptr || (lrc != nullptr && lrc[0] == 'w')))
+            return launch_fb_lrw<4, 8>(a, n_utts, st);
         if (u == 8 && unit_counts == nullptr) {
             if (plan->lr_su == 4 && plan->K <= 4 * 32 * 2 * 4 && plan->K % 4 == 0 && lrc != nullptr && lrc[0] == '1')
                 return launch_fb_lrc<4, 4, 2>(a, n_utts, st);

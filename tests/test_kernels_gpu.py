@@ -299,12 +299,12 @@ def test_ragged_batch_equals_single(ops):
 
 
 @pytest.mark.parametrize('P,S,lrc', [(130, 4, '0'), (250, 4, '0'), (140, 3, '0'), (250, 4, '1'), (130, 4, '1'),
-                                     (256, 4, '1'), (250, 4, None), (130, 4, None), (256, 4, None), (140, 3, None)])
+                                     (256, 4, '1'), (250, 4, 'w'), (130, 4, 'w'), (256, 4, 'w'), (140, 3, None)])
 def test_forward_backward_many_units_block_kernel(ops, P, S, lrc, monkeypatch):
     """Loops with more than 128 units (BASELINE configs[2]: 250 units x 4 states) run W warps per utterance
     with one shared-memory exchange per reduction (lrc = '0': one unit per lane on eight warps, '1': two units per lane
-    on four warps) or, for units of four states, ONE warp per utterance with eight units per lane (lrc = None, what the
-    library picks); same posteriors / evidence as the generic kernel and as the fp64 oracle on a ragged batch."""
+    on four warps, 'w': ONE warp per utterance with eight units per lane, the kernel that also reduces unit counts;
+    None: what the library picks); same posteriors / evidence as the generic kernel and as the fp64 oracle on a ragged batch."""
     if lrc is not None:
         monkeypatch.setenv('BEER_B200_SCAN_LRC', lrc)
     else:
