@@ -1255,7 +1255,7 @@ __global__ void __launch_bounds__(W * 32, 4) hmm_fb_lrb_kernel(FbArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* ring_p = smem + (size_t)warp * (2 * PF * ROW);
     float* ring_a = ring_p + PF * ROW;
-    float* xch = smem + (size_t)W * (2 * PF * ROW);     // [2][W][4] exchange slots
+    float* xch = smem + (size_t)W * (2 * PF * ROW);     // [2][W][8] exchange slots
     const int K = a.K;
     const float p_scale = a.scale * a.llh_mul;
     const int gl = warp * 32 + lane;            // unit owned by this lane
@@ -1303,35 +1303,44 @@ __global__ void __launch_bounds__(W * 32, 4) hmm_fb_lrb_kernel(FbArgs a) {
                 if (k0 + j < K) row[k0 + j] = mul * v[j];
         }
     };
-    // One exchange: every warp publishes (its max m, sum s of 2^(x - m), optional extra e scaled the
-    // same way); afterwards every thread holds the block maximum M, S = sum_w s_w 2^(m_w - M) and E.
+    // One exchange: every warp publishes up to two (maximum m, sum s of 2^(x - m)) pairs, the first with an extra sum e
+    // scaled the same way; afterwards every thread holds the block maxima M, S = sum_w s_w 2^(m_w - M) and E.  The
+    // recombination runs ONCE per warp across lanes (lane l takes warp l % W's slot: one exp2 per pair and warp instead
+    // of W per thread -- the W-fold version was 46 % of the kernel's special-function work).
+    static_assert((W & (W - 1)) == 0 && W <= 32, "W must be a power of two");
     int xn = 0;
-    auto exchange = [&](float m, float s, float e, float& M, float& Ssum, float& E) {
-        float* slot = xch + (xn & 1) * (W * 4);
+    auto sum_w = [&](float v) {        // sum over the W distinct slots (every group of W lanes holds all of them)
+#pragma unroll
+        for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    };
+    auto exchange2 = [&](float m1, float s1, float e1, float m2, float s2, float& M1, float& S1, float& E1, float& M2,
+                         float& S2, bool second) {
+        float4* slot = reinterpret_cast<float4*>(xch + (xn & 1) * (W * 8));
         ++xn;
         if (lane == 0) {
-            slot[warp * 4] = m;
-            slot[warp * 4 + 1] = s;
-            slot[warp * 4 + 2] = e;
+            slot[warp * 2] = make_float4(m1, s1, e1, m2);
+            if (second) slot[warp * 2 + 1] = make_float4(s2, 0.f, 0.f, 0.f);
         }
         __syncthreads();
-        float mm[W];
-        M = kNegInf;
-#pragma unroll
-        for (int w = 0; w < W; ++w) {
-            mm[w] = slot[w * 4];
-            M = fmaxf(M, mm[w]);
+        const float4 x = slot[(lane & (W - 1)) * 2];
+        const float mx1 = warp_max(x.x);
+        M1 = (mx1 == kNegInf) ? 0.f : mx1;
+        const float f1 = ex2(x.x - M1);           // 2^(-inf) = 0 for warps without reachable states
+        S1 = sum_w(x.y * f1);
+        E1 = sum_w(x.z * f1);
+        M2 = 0.f;
+        S2 = 0.f;
+        if (second) {
+            const float y = slot[(lane & (W - 1)) * 2 + 1].x;
+            const float mx2 = warp_max(x.w);
+            M2 = (mx2 == kNegInf) ? 0.f : mx2;
+            S2 = sum_w(y * ex2(x.w - M2));
         }
-        const float Ms = (M == kNegInf) ? 0.f : M;
-        Ssum = 0.f;
-        E = 0.f;
-#pragma unroll
-        for (int w = 0; w < W; ++w) {
-            const float f = ex2(mm[w] - Ms);       // 2^(-inf) = 0 for warps without reachable states
-            Ssum = fmaf(slot[w * 4 + 1], f, Ssum);
-            E = fmaf(slot[w * 4 + 2], f, E);
-        }
-        M = Ms;
+    };
+    auto exchange = [&](float m, float s, float e, float& M, float& Ssum, float& E) {
+        float M2, S2;
+        exchange2(m, s, e, kNegInf, 0.f, M, Ssum, E, M2, S2, false);
     };
 
     for (int u = blockIdx.x; u < a.n_utts; u += gridDim.x) {
@@ -1448,7 +1457,8 @@ __global__ void __launch_bounds__(W * 32, 4) hmm_fb_lrb_kernel(FbArgs a) {
             }
             cp_async_commit();
 
-            // gamma_t: exchange (max, sum, sum of p * 2^(v - max))
+            // ONE exchange per frame: the posterior normaliser of frame t (max, sum, sum of p * 2^(v - max)) and the
+            // junction of the beta recursion (max of delta_t = p_t + lb_t, partial sum over the unit starts)
             float v[S], m = kNegInf;
 #pragma unroll
             for (int j = 0; j < S; ++j) {
@@ -1466,10 +1476,25 @@ __global__ void __launch_bounds__(W * 32, 4) hmm_fb_lrb_kernel(FbArgs a) {
                 sl += v[j];
                 pe = fmaf(p[j], v[j], pe);
             }
-            sl = warp_sum(sl);
-            pe = warp_sum(pe);
-            float ms, sum, pes;
-            exchange(m, sl, pe, ms, sum, pes);
+            float delta[S];
+            float md = kNegInf;
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                delta[j] = p[j] + lb[j];
+                md = fmaxf(md, delta[j]);
+            }
+            md = warp_max(md);
+            const float mds = (md == kNegInf) ? 0.f : md;
+            float sj = ex2(delta[0] + w_in[0] - mds);
+            // three sums in one butterfly
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                sl += __shfl_xor_sync(0xffffffffu, sl, o);
+                pe += __shfl_xor_sync(0xffffffffu, pe, o);
+                sj += __shfl_xor_sync(0xffffffffu, sj, o);
+            }
+            float ms, sum, pes, Md, Sj;
+            exchange2(m, sl, pe, md, sj, ms, sum, pes, Md, Sj, true);
             const float inv = (sum > 0.f) ? __fdividef(1.f, sum) : 0.f;
             const float resc = ex2(mls - ms) * inv;            // this warp's values -> block normalisation
             if constexpr (LP) {
@@ -1478,8 +1503,12 @@ __global__ void __launch_bounds__(W * 32, 4) hmm_fb_lrb_kernel(FbArgs a) {
                 for (int j = 0; j < S; ++j) vlog[j] += lnorm;
                 write_row(a.pdf_lpost + (size_t)(t0 + t) * a.ld_lpost, vlog, 1.f);
             }
+            if (a.state_post != nullptr || a.pdf_post != nullptr) {
 #pragma unroll
-            for (int j = 0; j < S; ++j) v[j] *= resc;
+                for (int j = 0; j < S; ++j) v[j] *= resc;
+                if (a.state_post != nullptr) write_row(a.state_post + (size_t)(t0 + t) * K, v, 1.f);
+                if (a.pdf_post != nullptr) write_row(a.pdf_post + (size_t)(t0 + t) * a.ld_post, v, a.scale);
+            }
             if (threadIdx.x == 0) {
                 ell += pes * inv;
                 if ((i & 31) == 31) {
@@ -1491,22 +1520,8 @@ __global__ void __launch_bounds__(W * 32, 4) hmm_fb_lrb_kernel(FbArgs a) {
                     a.frame_exp_llh[t0 + t] = pes * inv * kLn2 + r;
                 }
             }
-            if (a.state_post != nullptr) write_row(a.state_post + (size_t)(t0 + t) * K, v, 1.f);
-            if (a.pdf_post != nullptr) write_row(a.pdf_post + (size_t)(t0 + t) * a.ld_post, v, a.scale);
             if (t == 0) break;
-            // beta_{t-1}: exchange (max of delta, junction partial over the unit starts)
-            float delta[S];
-            float md = kNegInf;
-#pragma unroll
-            for (int j = 0; j < S; ++j) {
-                delta[j] = p[j] + lb[j];
-                md = fmaxf(md, delta[j]);
-            }
-            md = warp_max(md);
-            const float mds = (md == kNegInf) ? 0.f : md;
-            const float sj = warp_sum(ex2(delta[0] + w_in[0] - mds));
-            float Md, Sj, unused;
-            exchange(md, sj, 0.f, Md, Sj, unused);
+            // beta_{t-1} from delta_t and the junction value
             const float jb = Md + lg2(Sj);
 #pragma unroll
             for (int j = 0; j < S; ++j) {
@@ -1537,7 +1552,7 @@ template <int SU, int W, bool LP = false>
 static int launch_fb_lrb(const FbArgs& a, int n_utts, cudaStream_t st) {
     if (!LP && a.pdf_lpost != nullptr) return launch_fb_lrb<SU, W, true>(a, n_utts, st);
     constexpr int PF = 4;
-    size_t smem = sizeof(float) * ((size_t)W * (2 * PF * 32 * SU) + 2 * W * 4);
+    size_t smem = sizeof(float) * ((size_t)W * (2 * PF * 32 * SU) + 2 * W * 8);
     static bool attr_set = false;
     if (!attr_set) {
         BEER_CUDA_TRY(cudaFuncSetAttribute(hmm_fb_lrb_kernel<SU, W, LP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
