@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a, con
             const uint32_t b_bytes = (uint32_t)b_stage * 2u, k_bytes = (uint32_t)a.NB * 8u;
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 for (int c = 0; c < a.n_chunks; ++c, ++it) {
-                    mbar_wait(&bars->b_empty[st], ph ^ 1);
+                    mbar_wait_relaxed(&bars->b_empty[st], ph ^ 1, 200);
                     trace(a.trace, it, 0);
                     mbar_arrive_expect_tx(&bars->b_full[st], b_bytes + k_bytes);
                     bulk_g2s(Bs + (size_t)st * b_stage, a.wimg + (size_t)c * b_stage, b_bytes, &bars->b_full[st]);
@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a, con
                     const int buf = it & 1;
                     mbar_wait(&bars->b_full[st], ph);
                     trace(a.trace, it, 1);
-                    mbar_wait(&bars->t_empty[buf], ((it >> 1) & 1) ^ 1);
+                    mbar_wait_relaxed(&bars->t_empty[buf], ((it >> 1) & 1) ^ 1, 32);
                     trace(a.trace, it, 2);
                     tc_fence_after();
                     const uint32_t b_hi = smem_u32(Bs + (size_t)st * b_stage), b_lo = b_hi + (uint32_t)a.NB * KP * 2u;
@@ -712,14 +712,14 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
             for (int i = 0; i < n_tiles; ++i, r.next()) {
                 const int t0 = (int)(f_begin + (int64_t)i * TILE);
                 if (which == 0) {
-                    mbar_wait(&bars->a_empty[r.pos], r.phase ^ 1);
+                    mbar_wait_relaxed(&bars->a_empty[r.pos], r.phase ^ 1, 200);
                     trace(a.trace, i, 0);
                     mbar_arrive_expect_tx(&bars->a_full[r.pos], bytes);
                     bulk_g2s(ring_a + (size_t)r.pos * STAGE_A, a.img1 + (size_t)(tile0 + i) * (2 * IMG_HALF), bytes,
                              &bars->a_full[r.pos]);
                     continue;
                 }
-                mbar_wait(&bars->b_empty[r.pos], r.phase ^ 1);
+                mbar_wait_relaxed(&bars->b_empty[r.pos], r.phase ^ 1, 200);
                 uint8_t* dst = ring_b + (size_t)r.pos * STAGE_B;
                 if (which == 1) {
                     mbar_arrive_expect_tx(&bars->b_full[r.pos], bytes);
@@ -763,7 +763,7 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
             auto issue_g2 = [&](int i) {
                 const int grp = i / DR, dbuf = grp & 1;
                 const bool first = (i % DR) == 0, last = (i % DR) == DR - 1 || i == n_tiles - 1;
-                mbar_wait(&bars->a2_full[b2], ph2);
+                mbar_wait_relaxed(&bars->a2_full[b2], ph2, 32);
                 trace(a.trace, i, 3);
                 if (first) mbar_wait(&bars->d2_empty[dbuf], ((grp >> 1) & 1) ^ 1);
                 tc_fence_after();
