@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256, 1) tma_read_kernel(const uint8_t* __restr
     }
     __syncthreads();
     const int w = threadIdx.x >> 5;
-    if ((threadIdx.x & 31) == 0 && w < issuers) {
+    if (w < issuers && elect_one()) {       // (under `lane == 0` each copy cost its issuing thread ~500 cycles)
         // issuer w owns the slots s = w, w + issuers, ...
         const int64_t n_chunks = src_bytes / chunk;
         // issuers > 0: every SM walks its own part of the buffer; the caller passes stages < 0 ... (see `shared_walk`)
