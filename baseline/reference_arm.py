@@ -78,13 +78,21 @@ def phone_loop(beer, n_units, n_states):
 
 
 def build_model(cfg, seed=2, double=False):
-    """HMM over NormalSet (C = 1) or MixtureSet(NormalSet) (C > 1) of the bench configuration, created by the
-    reference's own constructors (mean 0, cov 1, prior_strength 1, noise_std 1: SURVEY 8d)."""
+    """HMM over NormalSet (C = 1) or MixtureSet(NormalSet) (C > 1) of the bench configuration -- or, for a `gmm`
+    configuration, a plain Mixture of n_comp Gaussians -- created by the reference's own constructors (mean 0, cov 1,
+    prior_strength 1, noise_std 1: SURVEY 8d).  Returns (beer, model, NormalSet, MixtureSet / Mixture or None, graph)."""
     import torch
     beer = _import_reference()
     torch.manual_seed(seed)
-    K = cfg['n_units'] * cfg['n_states']
     C, D = cfg['n_comp'], cfg['dim']
+    if cfg.get('gmm'):
+        ns = beer.NormalSet.create(torch.zeros(D), torch.ones(D), size=C, prior_strength=1., noise_std=1.,
+                                   cov_type='diagonal')
+        model = beer.Mixture.create(ns, prior_strength=1.)
+        if double:
+            model = model.double()
+        return beer, model, ns, model, None
+    K = cfg['n_units'] * cfg['n_states']
     cg = phone_loop(beer, cfg['n_units'], cfg['n_states'])
     ns = beer.NormalSet.create(torch.zeros(D), torch.ones(D), size=K * C, prior_strength=1., noise_std=1.,
                                cov_type='diagonal')
@@ -92,7 +100,7 @@ def build_model(cfg, seed=2, double=False):
     hmm = beer.HMM.create(cg, modelset)
     if double:
         hmm = hmm.double()
-    return beer, hmm, ns, (modelset if C > 1 else None)
+    return beer, hmm, ns, (modelset if C > 1 else None), hmm.graph
 
 
 def model_arrays(ns, ms):
@@ -102,8 +110,9 @@ def model_arrays(ns, ms):
         return tuple(t.detach().double().numpy().copy() for t in (p.mean, p.scale, p.shape, p.rates))
     out = dict(ng_prior=std(ns.means_precisions.prior), ng_post=std(ns.means_precisions.posterior))
     if ms is not None:
-        out['dir_prior'] = ms.categoricalset.weights.prior.params.concentrations.detach().double().numpy().copy()
-        out['dir_post'] = ms.categoricalset.weights.posterior.params.concentrations.detach().double().numpy().copy()
+        w = ms.categoricalset.weights if hasattr(ms, 'categoricalset') else ms.categorical.weights     # MixtureSet / Mixture
+        out['dir_prior'] = w.prior.params.concentrations.detach().double().numpy().copy()
+        out['dir_post'] = w.posterior.params.concentrations.detach().double().numpy().copy()
     return out
 
 
@@ -112,7 +121,8 @@ def vb_iteration(cfg, utts, threads=1, double=False, update=True, seed=2, want_m
     Returns dict(frames, seconds (E-step + backward + optimizer step, model construction excluded), elbo, model)."""
     import torch
     torch.set_num_threads(max(1, int(threads)))
-    beer, hmm, ns, ms = build_model(cfg, seed=seed, double=double)
+    beer, hmm, ns, ms, graph = build_model(cfg, seed=seed, double=double)
+    kw = {} if graph is None else {'inference_graph': graph}
     arrays = model_arrays(ns, ms) if want_model else None
     dtype = torch.float64 if double else torch.float32
     data = [torch.from_numpy(np.asarray(u)).to(dtype) for u in utts]
@@ -123,7 +133,7 @@ def vb_iteration(cfg, utts, threads=1, double=False, update=True, seed=2, want_m
     elbo = beer.evidence_lower_bound(datasize=N)
     per_utt = []
     for X in data:
-        e = beer.evidence_lower_bound(hmm, X, inference_graph=hmm.graph, datasize=N)
+        e = beer.evidence_lower_bound(hmm, X, datasize=N, **kw)
         per_utt.append(float(e))
         elbo += e
     if update:

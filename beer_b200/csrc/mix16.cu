@@ -953,6 +953,44 @@ __global__ void __launch_bounds__(256) log2_post_kernel(const float* __restrict_
     }
 }
 
+// GMM without an HMM on top (Mixture.expected_log_likelihood, mixture.py:70-93): the M components are treated as Kp
+// pseudo-pdfs of C each; KA16 has written their log2-sum-exp2, this kernel finishes the softmax over the frame:
+// L_t = log2 sum_k 2^llh2[t, k] (the expected llh of the frame, = LSE over all components), lpost[t, k] = llh2[t, k] - L_t
+// (so that KCF's w = 2^(z - llh2 + lpost) = 2^(z - L_t) is the component responsibility), and the per-utterance sums.
+// One warp per frame.
+__global__ void __launch_bounds__(256) gmm_post_kernel(const float* __restrict__ llh2, int64_t N, int Kp, int64_t ld,
+                                                       const float* __restrict__ frame_ref, const int64_t* __restrict__ utt_off,
+                                                       int n_utts, float scale, float* __restrict__ lpost, int64_t ld_post,
+                                                       float* __restrict__ frame_llh, double* __restrict__ utt_exp_llh) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float lscale = lg2(scale);
+    for (int64_t t = warp0; t < N; t += nwarps) {
+        const float* row = llh2 + (size_t)t * ld;
+        float m = kNegInf;
+        for (int k = lane; k < Kp; k += 32) m = fmaxf(m, row[k]);
+        m = warp_max(m);
+        const float ms = (m == kNegInf) ? 0.f : m;
+        float sm = 0.f;
+        for (int k = lane; k < Kp; k += 32) sm += ex2(row[k] - ms);
+        sm = warp_sum(sm);
+        const float L = ms + lg2(sm);
+        for (int k = lane; k < Kp; k += 32) lpost[(size_t)t * ld_post + k] = row[k] - L + lscale;
+        if (lane == 0) {
+            const float f = scale * (L * kLn2 + (frame_ref != nullptr ? frame_ref[t] : 0.f));
+            if (frame_llh != nullptr) frame_llh[t] = f;
+            if (utt_exp_llh != nullptr) {
+                int lo = 0, hi = n_utts;          // last utterance with utt_off[u] <= t
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (utt_off[mid] <= t) lo = mid; else hi = mid;
+                }
+                atomicAdd(utt_exp_llh + lo, (double)f);
+            }
+        }
+    }
+}
+
 typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1119,6 +1157,19 @@ int beer_mix16_log2_posteriors(const float* pdf_post, int64_t N, int Kp, int64_t
     if (N == 0) return BEER_OK;
     const int blocks = (int)std::min<int64_t>((N * Kp + 255) / 256, kNumSMs * 16);
     mix16::log2_post_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pdf_post, N, Kp, ld_post, pdf_lpost, ld_lpost);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
+int beer_mix16_gmm_posteriors(const float* llh2, int64_t N, int Kp, int64_t ld_llh, const float* frame_ref,
+                              const int64_t* utt_off, int n_utts, float scale, float* pdf_lpost, int64_t ld_lpost,
+                              float* frame_exp_llh, double* utt_exp_llh, void* stream) {
+    if (!llh2 || !pdf_lpost || N < 0 || Kp <= 0 || ld_llh < Kp || ld_lpost < Kp) return BEER_ERR_ARG;
+    if (utt_exp_llh != nullptr && (!utt_off || n_utts <= 0)) return BEER_ERR_ARG;
+    if (N == 0) return BEER_OK;
+    const int blocks = (int)std::min<int64_t>((N + 7) / 8, kNumSMs * 8);
+    mix16::gmm_post_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(llh2, N, Kp, ld_llh, frame_ref, utt_off, n_utts, scale,
+                                                                     pdf_lpost, ld_lpost, frame_exp_llh, utt_exp_llh);
     BEER_LAUNCH_CHECK();
     return BEER_OK;
 }

@@ -90,6 +90,10 @@ class EmissionParams:
         # mixtures of 4 / 8 / 16 Gaussians per pdf: the fp16-split kernels that keep the per-Gaussian llhs on chip
         self.use16 = (self.has_mixtures and bool(self.uniform_C) and os.environ.get('BEER_B200_NO_MIX16') is None
                       and ops.mix16_supported(self.M, self.D, self.uniform_C))
+        # a plain GMM (one pdf of M components): its components as pseudo-pdfs of 8 / 16 / 4 for the same kernels
+        self.gmm_C = 0
+        if self.Kp == 1 and self.M > 1 and os.environ.get('BEER_B200_NO_MIX16') is None:
+            self.gmm_C = next((c for c in (8, 16, 4) if self.M % c == 0 and ops.mix16_supported(self.M, self.D, c)), 0)
         self._image = None
 
     def refresh(self, pack_tc=True):
@@ -237,6 +241,11 @@ class VBEngine:
         # flat reduction buffer: [acc (M*Q) | unit counts (P) | sum_u (N/T_u) ell_u | sum_u T_u | n_utts | sum_u ell_u]
         self.units = unit_weights
         # per-utterance alignment chains (ops.ChainBatch: chain i belongs to utterance i of this shard) or one graph plan
+        # plan None: a GMM without an HMM on top (Mixture, beer/models/mixture.py:70-102): no forward-backward at all
+        self.gmm = plan is None
+        if self.gmm and (emission.gmm_C == 0 or unit_weights is not None or viterbi):
+            raise ValueError('the batched GMM mode needs one pdf whose number of components is a multiple of 32 '
+                             '(D = 20 or 40); other mixtures go through the model API (Mixture)')
         self.chains = isinstance(plan, ops.ChainBatch)
         if self.chains and (unit_weights is not None or plan.n_utts != utts.n_utts or self.viterbi):
             raise ValueError('a ChainBatch needs one chain per utterance of the shard, runs forward-backward and '
@@ -270,15 +279,15 @@ class VBEngine:
             self._ready = [torch.cuda.Event() for _ in range(2)]
             self._free = [torch.cuda.Event() for _ in range(2)]
             self._free_valid = [False, False]
-        Kp = emission.Kp
+        Kp = emission.Kp if not self.gmm else emission.M // emission.gmm_C
         self.pdf_llh = torch.empty(nmax, Kp, device=self.dev, dtype=f32)
-        self._nonident = self.chains or not (plan.info['map_identity'] and plan.n_states == Kp)
+        self._nonident = not self.gmm and (self.chains or not (plan.info['map_identity'] and plan.n_states == Kp))
         self.pdf_post = (torch.zeros if self._nonident else torch.empty)(nmax, Kp, device=self.dev, dtype=f32)
         # mixtures through the fp16-split kernels (forward-backward over one graph plan): no per-Gaussian llhs at all,
         # `pdf_llh` holds log2 values; the feature images of resident chunks are built once, here
         self.mix16 = None
-        if emission.use16 and not self.viterbi and not self.chains:
-            self.mix16 = ops.Mix16(M, D, emission.uniform_C, self.dev)
+        if self.gmm or (emission.use16 and not self.viterbi and not self.chains):
+            self.mix16 = ops.Mix16(M, D, emission.gmm_C if self.gmm else emission.uniform_C, self.dev)
             self._images = [None] * len(self._chunks)
             if not self.host_mode:
                 for ci, (u0, u1, f0, nf, rel) in enumerate(self._chunks):
@@ -288,7 +297,7 @@ class VBEngine:
         self.tensor_kind = 'f16' if self.mix16 is not None else 'tf32'
         self.comp_llh = (torch.empty(nmax, M, device=self.dev, dtype=f32)
                          if emission.has_mixtures and self.mix16 is None else None)
-        ws_bytes = plan.workspace_bytes(nmax)
+        ws_bytes = plan.workspace_bytes(nmax) if not self.gmm else 4
         if self.viterbi:
             ws_bytes = max(ws_bytes, nmax * plan.n_states * 2 + 4)      # uint16 back-pointers
             self._pdf_map = torch.as_tensor(np.asarray(plan.pdf_map), dtype=i32, device=self.dev)
@@ -301,7 +310,7 @@ class VBEngine:
         self.utt_ell = torch.zeros(utts.n_utts, device=self.dev, dtype=f64)
         self.gpu_launches = 0
         # the SIMT emission kernel reads the component offsets back to size its grid: not capturable
-        self.use_graph = (bool(use_graph) and (emission.use_tc or not emission.has_mixtures)
+        self.use_graph = (bool(use_graph) and (emission.use_tc or not emission.has_mixtures or self.mix16 is not None)
                           and unit_weights is None)      # the graph rewrite syncs with the host
         self._shard_counts = torch.tensor([float(self.local_frames), float(utts.n_utts)], device=self.dev, dtype=f64)
         self._graph, self._graph_elbo, self._graph_launches, self._eager_steps = None, None, 0, 0
@@ -373,7 +382,13 @@ class VBEngine:
             if nonident:
                 pdf_post.zero_()
             with self._stage('KB_forward_backward'):
-                if self.viterbi:
+                if self.gmm:
+                    # no graph: the softmax over the pseudo-pdfs of a frame is the whole "inference"
+                    self.utt_ell[u0:u1].zero_()
+                    self.mix16.gmm_posteriors(pdf_llh, fref, rel, scale=self.scale, out=pdf_post,
+                                              out_utt_exp_llh=self.utt_ell[u0:u1])
+                    self.gpu_launches += 1
+                elif self.viterbi:
                     path = ops.hmm_viterbi(plan, pdf_llh, rel, scale=self.scale, workspace=self.ws)
                     _, frame = ops.path_posteriors(path, em.Kp, pdf_map=self._pdf_map, scale=self.scale,
                                                    pdf_llh=pdf_llh, frame_ref=fref, want_post=not self._path_kc,

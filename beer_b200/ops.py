@@ -649,6 +649,19 @@ class Mix16:
             float(scale), _p(acc_normal, f64), _stream()), 'beer_mix16_accumulate')
         return acc_normal
 
+    def gmm_posteriors(self, llh2, frame_ref, utt_off, scale=1.0, out=None, out_utt_exp_llh=None, want_frame_llh=False):
+        """GMM without an HMM: softmax over the pseudo-pdfs of every frame -> (lpost [N, Kp], frame llh or None);
+        `out_utt_exp_llh` (fp64, zeroed by the caller) += the per-utterance sums of the frame llhs."""
+        N = llh2.shape[0]
+        lpost = out if out is not None else torch.empty(N, self.Kp, device=llh2.device, dtype=f32)
+        frame = torch.empty(N, device=llh2.device, dtype=f32) if want_frame_llh else None
+        n_utts = utt_off.numel() - 1 if utt_off is not None else 0
+        _lib.check(_lib.load().beer_mix16_gmm_posteriors(
+            _p(llh2, f32), N, self.Kp, llh2.stride(0), _p(frame_ref, f32, True), _p(utt_off, i64, True), n_utts,
+            float(scale), _p(lpost, f32), lpost.stride(0), _p(frame, f32, True), _p(out_utt_exp_llh, f64, True),
+            _stream()), 'beer_mix16_gmm_posteriors')
+        return lpost, frame
+
     def log2_posteriors(self, pdf_post, out=None):
         N = pdf_post.shape[0]
         out = out if out is not None else torch.empty(N, self.Kp, device=pdf_post.device, dtype=f32)

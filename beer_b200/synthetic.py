@@ -7,7 +7,8 @@ import torch
 
 from .graph import Graph
 
-__all__ = ['unit_graph', 'phone_loop_graph', 'sample_utterances', 'alignment_chains', 'initial_normal_gamma', 'CONFIGS']
+__all__ = ['unit_graph', 'phone_loop_graph', 'sample_utterances', 'sample_gmm_frames', 'alignment_chains',
+           'initial_normal_gamma', 'CONFIGS']
 
 # name -> (units, states per unit, Gaussians per state, dim, frames per utterance, utterances per GPU)
 CONFIGS = {
@@ -16,6 +17,9 @@ CONFIGS = {
     # cfg2 trained with one alignment graph per utterance (`beer hmm accumulate --alis`): the unit sequence each
     # utterance was sampled through, as a left-to-right chain
     'cfg2ali': dict(n_units=25, n_states=4, n_comp=1, dim=40, n_frames=1000, n_utts=4096, aligned=True),
+    # BASELINE configs[4]: the E-step + conjugate M-step of the 512-component diagonal GMM inside the GSM-GMM example
+    # (no HMM, no forward-backward; the subspace SGD step of the GSM stays in PyTorch)
+    'cfg5': dict(gmm=True, n_units=0, n_states=0, n_comp=512, dim=40, n_frames=1000, n_utts=1250),
 }
 
 
@@ -89,6 +93,16 @@ def sample_utterances(graph, means, n_utts, n_frames, seed, device='cpu', noise=
     X += noise * rng.standard_normal(X.shape, dtype=np.float32)
     X = torch.from_numpy(X).to(device)
     return (X, torch.from_numpy(paths).to(device)) if return_paths else X
+
+
+def sample_gmm_frames(n_frames, dim, seed, n_centres=32, spread=3.0, device='cpu'):
+    """Frames of a GMM workload: `n_centres` cluster centres ~ N(0, spread^2 I), unit-variance noise (host RNG, one copy
+    to `device`)."""
+    rng = np.random.default_rng(seed)
+    centres = spread * np.random.default_rng(12345).standard_normal((n_centres, dim)).astype(np.float32)
+    X = centres[rng.integers(0, n_centres, n_frames)]
+    X += rng.standard_normal(X.shape, dtype=np.float32)
+    return torch.from_numpy(X).to(device)
 
 
 def alignment_chains(paths, n_states, self_loop=0.75):

@@ -35,6 +35,9 @@ UNIT = 'frames/s'
 
 
 def workload_name(cfg, c):
+    if c.get('gmm'):
+        return (f"{cfg}: {c['n_comp']}-component diagonal GMM (the E-step + conjugate M-step inside GSM-GMM), {c['dim']}-d "
+                f"synthetic fbank, {c['n_utts']} utterances x {c['n_frames']} frames per GPU, no HMM")
     K = c['n_units'] * c['n_states']
     return (f"{cfg}: HMM-GMM {K} states x {c['n_comp']} diag-Gauss, {c['dim']}-d synthetic fbank, "
             f"{c['n_utts']} utterances x {c['n_frames']} frames per GPU, phone-loop graph "
@@ -110,6 +113,10 @@ class ClockSampler:
 def host_utterances(c, n_utts, seed):
     """`n_utts` synthetic utterances of configuration `c` sampled on the host (numpy, fp32)."""
     from oracle import beer_oracle as O
+    if c.get('gmm'):
+        from beer_b200.synthetic import sample_gmm_frames
+        X = sample_gmm_frames(n_utts * c['n_frames'], c['dim'], seed).numpy()
+        return [X[i * c['n_frames']:(i + 1) * c['n_frames']] for i in range(n_utts)], None
     rng = np.random.default_rng(seed)
     graph, _, _ = O.phone_loop_graph(c['n_units'], c['n_states'])
     K = c['n_units'] * c['n_states']
@@ -121,6 +128,18 @@ def _port_worker(args):
     """numpy port of the reference E-step + accumulate over a shard (fallback when the reference is absent)."""
     c, utts, dtype = args
     from oracle import beer_oracle as O
+    if c.get('gmm'):
+        M, D = c['n_comp'], c['dim']
+        rng = np.random.default_rng(2)
+        post = tuple(a.astype(dtype) for a in (rng.standard_normal((M, D)), np.ones((M, 1)), np.ones((M, 1)), np.ones((M, D))))
+        dpost = (np.ones(M) / M).astype(dtype)
+        t0 = time.perf_counter()
+        frames = 0
+        with np.errstate(all='ignore'):
+            for X in utts:
+                O.gmm_estep(X.astype(dtype), post, dpost)
+                frames += len(X)
+        return dict(frames=frames, seconds=time.perf_counter() - t0)
     graph, _, _ = O.phone_loop_graph(c['n_units'], c['n_states'])
     K = c['n_units'] * c['n_states']
     M, D = K * c['n_comp'], c['dim']
@@ -180,6 +199,15 @@ class CpuArm:
             return sum(r['per_utt'][0] for r in res), res[0]['model'], 'reference (float64)'
         from oracle import beer_oracle as O
         c = self.c
+        if c.get('gmm'):
+            M, D = c['n_comp'], c['dim']
+            rng = np.random.default_rng(2)
+            prior = (np.zeros((M, D)), np.ones((M, 1)), np.ones((M, 1)), np.ones((M, D)))
+            post = (rng.standard_normal((M, D)).astype(np.float32).astype(np.float64),) + prior[1:]
+            dp = np.ones(M) / M
+            kl = O.normalgamma_kl(post, prior).sum() + O.dirichlet_kl(dp, dp).sum()
+            elbo = sum(O.elbo_value(O.gmm_estep(u.astype(np.float64), post, dp)['exp_llh'], kl, datasize) for u in utts)
+            return elbo, dict(ng_prior=prior, ng_post=post, dir_prior=dp, dir_post=dp), 'numpy oracle (float64)'
         K = c['n_units'] * c['n_states']
         M, D, C = K * c['n_comp'], c['dim'], c['n_comp']
         rng = np.random.default_rng(2)
@@ -198,6 +226,8 @@ def cpu_sizes(c):
     """(utterances per worker, frames kept of each utterance) for ~5-10 s of CPU work per pass: the cost of the
     reference is linear in the frames, so the large configuration is sampled with the first 250 frames of one
     utterance per worker."""
+    if c.get('gmm'):
+        return 64, c['n_frames']
     big = c['n_comp'] * c['n_units'] * c['n_states'] > 2000
     return (1, min(250, c['n_frames'])) if big else (16, c['n_frames'])
 
@@ -247,7 +277,7 @@ def make_engine_from_arrays(ctx, c, model, utts, plan, datasize):
     import torch
     from beer_b200.engine import EmissionParams, VBEngine, WeightGroup
     dev = ctx.dev
-    K, C = c['n_units'] * c['n_states'], c['n_comp']
+    K, C = (1, c['n_comp']) if c.get('gmm') else (c['n_units'] * c['n_states'], c['n_comp'])
 
     def ng(t):
         m, k, a, b = t
@@ -276,10 +306,12 @@ def elbo_check(ctx, name, c, arm, n_check):
     N = float(sum(len(u) for u in utts))
     t0 = time.perf_counter()
     want, model, kind = arm.elbo_fp64(utts, N)
-    graph, _, _ = synthetic.phone_loop_graph(c['n_units'], c['n_states'])
-    K = c['n_units'] * c['n_states']
-    plan = ops.GraphPlan(graph.init_log_probs.numpy(), graph.final_log_probs.numpy(),
-                         graph.trans_log_probs.numpy(), graph.pdf_id_mapping, n_pdfs=K)
+    plan = None
+    if not c.get('gmm'):
+        graph, _, _ = synthetic.phone_loop_graph(c['n_units'], c['n_states'])
+        K = c['n_units'] * c['n_states']
+        plan = ops.GraphPlan(graph.init_log_probs.numpy(), graph.final_log_probs.numpy(),
+                             graph.trans_log_probs.numpy(), graph.pdf_id_mapping, n_pdfs=K)
     X = torch.as_tensor(np.concatenate(utts), dtype=torch.float32, device=ctx.dev)
     eng = make_engine_from_arrays(ctx, c, model, Utterances(X, [len(u) for u in utts]), plan, N)
     got = float(eng.step().item())
@@ -295,15 +327,22 @@ def run_config(ctx, args, name, c, steps, warmup, primary):
     from beer_b200.engine import EmissionParams, Utterances, VBEngine, WeightGroup
     dev, world, rank = ctx.dev, ctx.world, ctx.rank
 
-    K = c['n_units'] * c['n_states']
+    gmm = bool(c.get('gmm'))
+    K = 1 if gmm else c['n_units'] * c['n_states']
     C = c['n_comp']
     M, D, T, U = K * C, c['dim'], c['n_frames'], c['n_utts']
-    graph, _, _ = synthetic.phone_loop_graph(c['n_units'], c['n_states'])
-    plan = ops.GraphPlan(graph.init_log_probs.numpy(), graph.final_log_probs.numpy(),
-                         graph.trans_log_probs.numpy(), graph.pdf_id_mapping, n_pdfs=K)
-    gen = torch.Generator().manual_seed(7)
-    means = 2.0 * torch.randn(K, D, generator=gen)
-    if c.get('aligned'):
+    plan = None
+    if gmm:
+        X = synthetic.sample_gmm_frames(U * T, D, seed=100 + rank, device=dev)
+    else:
+        graph, _, _ = synthetic.phone_loop_graph(c['n_units'], c['n_states'])
+        plan = ops.GraphPlan(graph.init_log_probs.numpy(), graph.final_log_probs.numpy(),
+                             graph.trans_log_probs.numpy(), graph.pdf_id_mapping, n_pdfs=K)
+        gen = torch.Generator().manual_seed(7)
+        means = 2.0 * torch.randn(K, D, generator=gen)
+    if gmm:
+        pass
+    elif c.get('aligned'):
         X, paths = synthetic.sample_utterances(graph, means, U, T, seed=100 + rank, device=dev, return_paths=True)
         plan = ops.ChainBatch.from_arrays(*synthetic.alignment_chains(paths, c['n_states']), device=dev)
         del paths
@@ -417,6 +456,8 @@ def run_config(ctx, args, name, c, steps, warmup, primary):
     # algorithmic work per frame of every stage: bytes B_alg = 8D + 16K split over KA (read X, write
     # llh), KB (read llh once more, write + read alpha) and KC (read X); flops F_alg = 4 Q M split over KA and KC
     alg_bytes = {'KA_emission_llh': 4 * D + 4 * K, 'KB_forward_backward': 12 * K, 'KC_accumulate': 4 * D}
+    if gmm:      # B_alg = 8 D for the GMM-only configurations (the per-frame llh stays on chip in the count)
+        alg_bytes = {'KA_emission_llh': 4 * D, 'KB_forward_backward': 0, 'KC_accumulate': 4 * D}
     alg_flops = {'KA_emission_llh': 2 * Q * M, 'KC_accumulate': 2 * Q * M}
     traffic_pf = {}
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
@@ -426,19 +467,19 @@ def run_config(ctx, args, name, c, steps, warmup, primary):
     tc_peak = ctx.tc_peak[tensor_kind] / 3.0      # 3-pass split (hi.hi + lo.hi + hi.lo) of the measured kind peak
     fps = nf / (ms / steps * 1e-3)                # per GPU
     Pn = c['n_units']
-    nnz = 2 * K - Pn + Pn * Pn
+    nnz = 0 if gmm else 2 * K - Pn + Pn * Pn
     mhz = (clocks or {}).get('sm_mhz') or 1965.0
     fractions = {
-        'hbm': fps * (8 * D + 16 * K) / 1e9 / peak,
+        'hbm': fps * (8 * D + (0 if gmm else 16 * K)) / 1e9 / peak,
         'tensor_3pass': fps * 4 * Q * M / 1e12 / tc_peak,
         'scan_mufu': fps * 2 * nnz / (148 * 16 * mhz * 1e6),
         'tensor_peak_tflops': tc_peak,
         'tensor_peak_source': f'beer_probe_mma kind::{tensor_kind} measured in this run '
                               f'({ctx.tc_peak[tensor_kind]:.0f} TFLOP/s dense) / 3 passes',
-        'alg_bytes_per_frame': 8 * D + 16 * K, 'alg_flops_per_frame': 4 * Q * M}
+        'alg_bytes_per_frame': 8 * D + (0 if gmm else 16 * K), 'alg_flops_per_frame': 4 * Q * M}
     # the binding roofline of the configuration: tensor pipe when the 3-pass contraction needs more time
     # than the algorithmic bytes at HBM speed
-    tensor_bound = (4 * Q * M / 1e12 / tc_peak) > ((8 * D + 16 * K) / 1e9 / peak)
+    tensor_bound = (4 * Q * M / 1e12 / tc_peak) > ((8 * D + (0 if gmm else 16 * K)) / 1e9 / peak)
     dom = max((k for k in stage_ms if k in alg_bytes), key=lambda k: stage_ms[k], default=None)
     roofline = None
     if dom is not None:
@@ -521,7 +562,7 @@ def run_gpu(args, configs):
             if not args.no_elbo_check or (ctx.world == 1 and not args.no_cpu_baseline):
                 arm = CpuArm(c)
             if not args.no_elbo_check:
-                n_check = 2 if c['n_comp'] * c['n_units'] * c['n_states'] > 2000 else 8
+                n_check = 2 if c['n_comp'] * max(c['n_units'] * c['n_states'], 1) > 2000 and not c.get('gmm') else 8
                 r['elbo_check'] = elbo_check(ctx, name, c, arm, min(n_check, arm.n_workers))
             r['cpu_baseline'] = None
             if ctx.world == 1 and not args.no_cpu_baseline:
@@ -556,7 +597,7 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--config', default=None, help='cfg3 (default, + cfg2 as `secondary`), cfg2, cfg2ali')
+    ap.add_argument('--config', default=None, help='cfg3 (default, + cfg2 as `secondary`), cfg2, cfg2ali, cfg5 (GMM only)')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--chunk-frames', type=int, default=None)
     ap.add_argument('--e2e-chunk-frames', type=int, default=None)

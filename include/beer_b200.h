@@ -359,6 +359,13 @@ BEER_API int beer_mix16_emission(const void* img1, int64_t N, int D, const void*
 BEER_API int beer_mix16_accumulate(const void* img1, const void* img2, int64_t N, int D, const uint32_t* wtm, const float* k12,
                           const float* alpha, int M, int C, const float* pdf_lpost, int64_t ld_lpost,
                           const float* llh2, int64_t ld_llh, float scale, double* acc_normal, void* stream);
+/* GMM without an HMM (Mixture.expected_log_likelihood, beer/models/mixture.py:70-93) on the same kernels: the M
+ * components count as Kp pseudo-pdfs of C; after beer_mix16_emission this finishes the softmax over the frame:
+ * pdf_lpost[t, k] = llh2[t, k] - log2 sum_k 2^llh2[t, k] + log2(scale), frame_exp_llh[t] (optional) = scale * LSE over
+ * all components (nats, frame_ref added), utt_exp_llh[u] (optional, fp64, caller-zeroed) += their sums per utterance. */
+BEER_API int beer_mix16_gmm_posteriors(const float* llh2, int64_t N, int Kp, int64_t ld_llh, const float* frame_ref,
+                              const int64_t* utt_off, int n_utts, float scale, float* pdf_lpost, int64_t ld_lpost,
+                              float* frame_exp_llh, double* utt_exp_llh, void* stream);
 BEER_API int beer_mix16_log2_posteriors(const float* pdf_post, int64_t N, int Kp, int64_t ld_post, float* pdf_lpost,
                                int64_t ld_lpost, void* stream);
 

@@ -288,3 +288,46 @@ def test_vb_iterations_cfg3_shape(use_graph, mix16, monkeypatch):
     for g, w in zip(_host(em.post), ng_post):
         np.testing.assert_allclose(g, w, rtol=2e-4, atol=3e-3)
     np.testing.assert_allclose(groups[0].post.double().cpu().numpy(), dpost, rtol=2e-4, atol=3e-4)
+
+
+@pytest.mark.parametrize('chunk,use_graph', [(None, False), (500, False), (None, True)])
+def test_vb_iterations_gmm_only(chunk, use_graph):
+    """BASELINE configs[4]: the batched engine without an HMM (plan=None) on a 512-component diagonal GMM, D = 40 --
+    emission kernel over pseudo-pdfs of 8 components, softmax over the frame, statistics with the responsibilities
+    recomputed on chip -- three VB iterations over ragged utterances against the oracle of Mixture (mixture.py:70-102)
+    summed as `beer hmm accumulate` + `update` do."""
+    from beer_b200 import synthetic
+    from beer_b200.engine import EmissionParams, Utterances, VBEngine, WeightGroup
+    dev = torch.device('cuda', 0)
+    C, D = 512, 40
+    lens = [300, 41, 777, 129, 64]
+    N = sum(lens)
+    X = synthetic.sample_gmm_frames(N, D, seed=3, device=dev)
+    prior, post = synthetic.initial_normal_gamma(C, D, seed=2, device=dev)
+    conc = torch.full((1, C), 1.0 / C, device=dev)
+    groups = (WeightGroup(0, 1, C, conc.clone(), conc.clone()),)
+    em = EmissionParams(prior, post, comp_off=np.array([0, C]), weight_groups=groups)
+    assert em.gmm_C == 8
+    eng = VBEngine(em, None, Utterances(X, lens), datasize=float(N), chunk_frames=chunk, distributed=False,
+                   use_graph=use_graph)
+    ng_prior, ng_post = _host(prior), _host(post)
+    dprior = dpost = conc.double().cpu().numpy().reshape(-1)
+    off = np.concatenate([[0], np.cumsum(lens)])
+    Xh = X.double().cpu().numpy()
+    for it in range(3):
+        kl = O.normalgamma_kl(ng_post, ng_prior).sum() + O.dirichlet_kl(dpost, dprior).sum()
+        want, acc_n, acc_d = 0.0, 0.0, 0.0
+        for u in range(len(lens)):
+            r = O.gmm_estep(Xh[off[u]:off[u + 1]], ng_post, dpost)
+            want += O.elbo_value(r['exp_llh'], kl, N)
+            acc_n = acc_n + r['acc_normal']
+            acc_d = acc_d + r['acc_dirichlet']
+        got = float(eng.step().item())
+        assert abs(got - want) <= 1e-5 * abs(want), (it, got, want)
+        acc = eng.acc.cpu().numpy()
+        assert np.abs(acc - acc_n).max() <= 3e-5 * np.abs(acc_n).max()
+        ng_post = O.natural_grad_update_normalgamma(ng_prior, ng_post, acc_n, 1.)
+        dpost = O.natural_grad_update_dirichlet(dprior, dpost, acc_d, 1.)
+    for g, w in zip(_host(em.post), ng_post):
+        np.testing.assert_allclose(g, w, rtol=3e-4, atol=3e-4)
+    np.testing.assert_allclose(groups[0].post.double().cpu().numpy().reshape(-1), dpost, rtol=3e-4, atol=1e-5)
