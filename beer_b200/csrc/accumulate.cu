@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(KC_THREADS, 2) accumulate_simt_kernel(KcArgs a
 
 __global__ void mixture_weight_stats_kernel(const double* __restrict__ acc, int M, int D,
                                             const int32_t* __restrict__ comp_off, int Kp, double* __restrict__ out) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;     // one warp per pdf
     if (k >= Kp) return;
     int Q = 2 * D + 2;
     int c0, c1;
@@ -160,12 +160,13 @@ __global__ void mixture_weight_stats_kernel(const double* __restrict__ acc, int 
         c0 = comp_off[k]; c1 = comp_off[k + 1];
     }
     double tot = 0.0;
-    for (int j = c0; j < c1; ++j) {
+    for (int j = c0 + lane; j < c1; j += 32) {
         double n = 2.0 * acc[(size_t)j * Q + 2 * D + 1];
         tot += n;
         if (j < c1 - 1) out[j] = n;
     }
-    if (c1 > c0) out[c1 - 1] = tot;
+    tot = warp_sum(tot);
+    if (lane == 0 && c1 > c0) out[c1 - 1] = tot;
 }
 
 template <int FPT>
@@ -219,7 +220,7 @@ int beer_mixture_weight_stats(const double* acc_normal, int M, int D, const int3
                               double* acc_weights, void* stream) {
     if (!acc_normal || !acc_weights || M <= 0 || D <= 0 || Kp <= 0) return BEER_ERR_ARG;
     if (comp_off == nullptr && M % Kp != 0) return BEER_ERR_ARG;
-    mixture_weight_stats_kernel<<<(Kp + 127) / 128, 128, 0, (cudaStream_t)stream>>>(acc_normal, M, D, comp_off, Kp,
+    mixture_weight_stats_kernel<<<(Kp * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(acc_normal, M, D, comp_off, Kp,
                                                                                     acc_weights);
     BEER_LAUNCH_CHECK();
     return BEER_OK;

@@ -215,62 +215,64 @@ __global__ void ng_kl_kernel(const float* __restrict__ pm, const float* __restri
 // ---- Dirichlet -------------------------------------------------------------
 
 // One thread per row (K rows, C small).
+// One WARP per Dirichlet (row): a thread per row made a 512-component GMM (K = 1) a single-thread loop over 512
+// digamma / lgamma evaluations in fp64 (0.6 ms).
 __global__ void dir_logw_kernel(const float* __restrict__ conc, int K, int C, float* __restrict__ logw) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (k >= K) return;
     double tot = 0.0;
-    for (int c = 0; c < C; ++c) tot += conc[(size_t)k * C + c];
-    double psi_tot = digamma_d(tot);
-    for (int c = 0; c < C; ++c) logw[(size_t)k * C + c] = (float)(digamma_d((double)conc[(size_t)k * C + c]) - psi_tot);
+    for (int c = lane; c < C; c += 32) tot += conc[(size_t)k * C + c];
+    tot = warp_sum(tot);
+    const double psi_tot = digamma_d(tot);
+    for (int c = lane; c < C; c += 32)
+        logw[(size_t)k * C + c] = (float)(digamma_d((double)conc[(size_t)k * C + c]) - psi_tot);
 }
 
 __global__ void dir_update_kernel(const float* __restrict__ prior, float* conc, const double* __restrict__ acc,
                                   double s, double lr, int K, int C) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (k >= K) return;
     const float* p = prior + (size_t)k * C;
     float* q = conc + (size_t)k * C;
     const double* st = acc + (size_t)k * C;
     double sum_p = 0.0, sum_q = 0.0, sum_new = 0.0;
-    for (int c = 0; c < C; ++c) {
+    for (int c = lane; c < C; c += 32) {
         sum_p += (double)p[c] - 1.0;
         sum_q += (double)q[c] - 1.0;
     }
-    double e_last = sum_q + lr * (sum_p + s * st[C - 1] - sum_q);
-    for (int c = 0; c < C - 1; ++c) {
+    sum_p = warp_sum(sum_p);
+    sum_q = warp_sum(sum_q);        // every lane has read the old row before anyone writes it
+    const double e_last = sum_q + lr * (sum_p + s * st[C - 1] - sum_q);
+    for (int c = lane; c < C - 1; c += 32) {
         double e = (double)q[c] - 1.0;
         e += lr * ((double)p[c] - 1.0 + s * st[c] - e);
         sum_new += e;
         q[c] = (float)(e + 1.0);
     }
-    q[C - 1] = (float)(e_last - sum_new + 1.0);
+    sum_new = warp_sum(sum_new);
+    if (lane == 0) q[C - 1] = (float)(e_last - sum_new + 1.0);
 }
 
 __global__ void dir_kl_kernel(const float* __restrict__ prior, const float* __restrict__ conc, int K, int C,
                               double* kl) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    double val = 0.0;
-    if (k < K) {
-        const float* p = prior + (size_t)k * C;
-        const float* q = conc + (size_t)k * C;
-        double sp = 0.0, sq = 0.0, Ap = 0.0, Aq = 0.0;
-        for (int c = 0; c < C; ++c) {
-            sp += p[c];
-            sq += q[c];
-            Ap += lgamma((double)p[c]);
-            Aq += lgamma((double)q[c]);
-        }
-        Ap -= lgamma(sp);
-        Aq -= lgamma(sq);
-        double psi_last = digamma_d((double)q[C - 1]), psi_tot = digamma_d(sq);
-        double dot = 0.0;
-        for (int c = 0; c < C - 1; ++c)
-            dot += (digamma_d((double)q[c]) - psi_last) * ((double)p[c] - (double)q[c]);
-        dot += (psi_last - psi_tot) * ((sp - C) - (sq - C));
-        val = Ap - Aq - dot;
+    const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (k >= K) return;
+    const float* p = prior + (size_t)k * C;
+    const float* q = conc + (size_t)k * C;
+    double sp = 0.0, sq = 0.0, A = 0.0;
+    for (int c = lane; c < C; c += 32) {
+        sp += p[c];
+        sq += q[c];
+        A += lgamma((double)p[c]) - lgamma((double)q[c]);
     }
-    val = warp_sum(val);
-    if ((threadIdx.x & 31) == 0 && val != 0.0) atomicAdd(kl, val);
+    sp = warp_sum(sp);
+    sq = warp_sum(sq);
+    const double psi_last = digamma_d((double)q[C - 1]), psi_tot = digamma_d(sq);
+    double dot = 0.0;
+    for (int c = lane; c < C - 1; c += 32) dot += (digamma_d((double)q[c]) - psi_last) * ((double)p[c] - (double)q[c]);
+    double val = warp_sum(A - dot);
+    val += -lgamma(sp) + lgamma(sq) - (psi_last - psi_tot) * ((sp - C) - (sq - C));
+    if (lane == 0 && val != 0.0) atomicAdd(kl, val);
 }
 
 
@@ -448,7 +450,7 @@ int beer_normalgamma_expected_stats(const float* mean, const float* scale, const
 
 int beer_dirichlet_expected_logw(const float* conc, int K, int C, float* logw, void* stream) {
     if (K <= 0 || C <= 0) return BEER_ERR_ARG;
-    dir_logw_kernel<<<(K + 127) / 128, 128, 0, (cudaStream_t)stream>>>(conc, K, C, logw);
+    dir_logw_kernel<<<(K * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(conc, K, C, logw);
     BEER_LAUNCH_CHECK();
     return BEER_OK;
 }
@@ -459,7 +461,7 @@ int beer_emission_prepare(const float* mean, const float* scale, const float* sh
     cudaStream_t st = (cudaStream_t)stream;
     // many Gaussians: two-stage reduction with W (written only after ref is final) as fp64 scratch
     const int n_blocks = 64;
-    if (M >= 1024 && (size_t)M * 2 * D * sizeof(float) >= (size_t)n_blocks * (D + 1) * sizeof(double) &&
+    if (M >= 256 && (size_t)M * 2 * D * sizeof(float) >= (size_t)n_blocks * (D + 1) * sizeof(double) &&
         ((uintptr_t)W & 7) == 0) {
         double* part = reinterpret_cast<double*>(W);
         emission_ref_partial_kernel<<<n_blocks, 256, 0, st>>>(mean, scale, shape, rates, logw, M, D, part);
@@ -502,7 +504,7 @@ int beer_normalgamma_kl(const float* prior_mean, const float* prior_scale, const
 int beer_dirichlet_update(const float* prior_conc, float* conc, const double* acc, double stats_scale,
                           double lrate, int K, int C, void* stream) {
     if (K <= 0 || C <= 0) return BEER_ERR_ARG;
-    dir_update_kernel<<<(K + 127) / 128, 128, 0, (cudaStream_t)stream>>>(prior_conc, conc, acc, stats_scale, lrate,
+    dir_update_kernel<<<(K * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(prior_conc, conc, acc, stats_scale, lrate,
                                                                          K, C);
     BEER_LAUNCH_CHECK();
     return BEER_OK;
@@ -510,7 +512,7 @@ int beer_dirichlet_update(const float* prior_conc, float* conc, const double* ac
 
 int beer_dirichlet_kl(const float* prior_conc, const float* conc, int K, int C, double* kl, void* stream) {
     if (K <= 0 || C <= 0) return BEER_ERR_ARG;
-    dir_kl_kernel<<<(K + 127) / 128, 128, 0, (cudaStream_t)stream>>>(prior_conc, conc, K, C, kl);
+    dir_kl_kernel<<<(K * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(prior_conc, conc, K, C, kl);
     BEER_LAUNCH_CHECK();
     return BEER_OK;
 }

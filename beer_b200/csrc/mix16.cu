@@ -965,29 +965,40 @@ __global__ void __launch_bounds__(256) gmm_post_kernel(const float* __restrict__
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const float lscale = lg2(scale);
-    for (int64_t t = warp0; t < N; t += nwarps) {
-        const float* row = llh2 + (size_t)t * ld;
-        float m = kNegInf;
-        for (int k = lane; k < Kp; k += 32) m = fmaxf(m, row[k]);
-        m = warp_max(m);
-        const float ms = (m == kNegInf) ? 0.f : m;
-        float sm = 0.f;
-        for (int k = lane; k < Kp; k += 32) sm += ex2(row[k] - ms);
-        sm = warp_sum(sm);
-        const float L = ms + lg2(sm);
-        for (int k = lane; k < Kp; k += 32) lpost[(size_t)t * ld_post + k] = row[k] - L + lscale;
-        if (lane == 0) {
+    constexpr int RUN = 32;           // consecutive frames per warp: one atomic per run and utterance, not per frame
+    for (int64_t r0 = warp0 * RUN; r0 < N; r0 += nwarps * RUN) {
+        int cur_utt = -1;
+        int64_t cur_end = -1;
+        double acc = 0.0;
+        for (int64_t t = r0; t < min(N, r0 + RUN); ++t) {
+            const float* row = llh2 + (size_t)t * ld;
+            float m = kNegInf;
+            for (int k = lane; k < Kp; k += 32) m = fmaxf(m, row[k]);
+            m = warp_max(m);
+            const float ms = (m == kNegInf) ? 0.f : m;
+            float sm = 0.f;
+            for (int k = lane; k < Kp; k += 32) sm += ex2(row[k] - ms);
+            sm = warp_sum(sm);
+            const float L = ms + lg2(sm);
+            for (int k = lane; k < Kp; k += 32) lpost[(size_t)t * ld_post + k] = row[k] - L + lscale;
             const float f = scale * (L * kLn2 + (frame_ref != nullptr ? frame_ref[t] : 0.f));
-            if (frame_llh != nullptr) frame_llh[t] = f;
+            if (lane == 0 && frame_llh != nullptr) frame_llh[t] = f;
             if (utt_exp_llh != nullptr) {
-                int lo = 0, hi = n_utts;          // last utterance with utt_off[u] <= t
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (utt_off[mid] <= t) lo = mid; else hi = mid;
+                if (t >= cur_end) {       // (warp-uniform) the run enters another utterance
+                    if (lane == 0 && cur_utt >= 0) atomicAdd(utt_exp_llh + cur_utt, acc);
+                    int lo = 0, hi = n_utts;          // last utterance with utt_off[u] <= t
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (utt_off[mid] <= t) lo = mid; else hi = mid;
+                    }
+                    cur_utt = lo;
+                    cur_end = utt_off[lo + 1];
+                    acc = 0.0;
                 }
-                atomicAdd(utt_exp_llh + lo, (double)f);
+                acc += (double)f;
             }
         }
+        if (lane == 0 && cur_utt >= 0) atomicAdd(utt_exp_llh + cur_utt, acc);
     }
 }
 
@@ -1167,7 +1178,7 @@ int beer_mix16_gmm_posteriors(const float* llh2, int64_t N, int Kp, int64_t ld_l
     if (!llh2 || !pdf_lpost || N < 0 || Kp <= 0 || ld_llh < Kp || ld_lpost < Kp) return BEER_ERR_ARG;
     if (utt_exp_llh != nullptr && (!utt_off || n_utts <= 0)) return BEER_ERR_ARG;
     if (N == 0) return BEER_OK;
-    const int blocks = (int)std::min<int64_t>((N + 7) / 8, kNumSMs * 8);
+    const int blocks = (int)std::min<int64_t>((N + 8 * 32 - 1) / (8 * 32), kNumSMs * 8);
     mix16::gmm_post_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(llh2, N, Kp, ld_llh, frame_ref, utt_off, n_utts, scale,
                                                                      pdf_lpost, ld_lpost, frame_exp_llh, utt_exp_llh);
     BEER_LAUNCH_CHECK();
