@@ -487,6 +487,10 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a, con
                     float o[G * PPU];
 #pragma unroll
                     for (int k = 0; k < G * PPU; ++k) {
+                        if constexpr (C == 1) {       // single-Gaussian pdfs: z is the llh
+                            o[k] = v[k];
+                            continue;
+                        }
                         const float m = tree_max<C>(v + k * C);
                         const float ms = (m == kNegInf) ? 0.f : m;
 #pragma unroll
@@ -636,10 +640,11 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
     constexpr int KS1 = KP / 16;                       // k-steps of S^T = W' . img1^T
     constexpr int KS2 = TILE / 16;                     // k-steps of acc += A2 . img2^T
     constexpr int IMG_HALF = TILE * KP;                // halfs of one image half-tile
+    constexpr bool SINGLE = C == 1;                    // single-Gaussian pdfs: w = the pdf posterior itself, no first MMA
     constexpr int NK = GM / C;                         // pdfs of a Gaussian tile
     constexpr int RAW_FLOATS = TILE * NK;              // one [frame][pdf] block
     constexpr int STAGE_A = 2 * IMG_HALF * 2;          // img1 hi | lo
-    constexpr int STAGE_B = 2 * IMG_HALF * 2 + 2 * RAW_FLOATS * 4;    // img2 hi | lo | llh2 | lpost
+    constexpr int STAGE_B = 2 * IMG_HALF * 2 + (SINGLE ? 1 : 2) * RAW_FLOATS * 4;    // img2 hi | lo | llh2 | lpost (SINGLE: posteriors)
     constexpr uint32_t COL_W = 0, COL_S = KP, COL_D2 = KP + NSB * TILE;     // tensor-memory columns
     static_assert(COL_D2 + 2 * KP <= 512, "tensor memory");
     static_assert(STAGE_A % 128 == 0 && STAGE_B % 128 == 0, "stage alignment");
@@ -682,7 +687,7 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
     const uint32_t tmem_base = bars->tmem_base;
 
     // the packed weights of this Gaussian tile -> tensor memory (A operand of the first MMA), once
-    if (warp < 4) {
+    if (!SINGLE && warp < 4) {
         const uint32_t* row = a.wtm + (size_t)(g0 + warp * 32 + lane) * KP;
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + COL_W;
 #pragma unroll 1
@@ -709,7 +714,7 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
             const uint32_t bytes = STAGE_A;                   // hi + lo of one image
             const int k0 = g0 / C;
             Ring r(which == 0 ? a.na : a.nb);
-            for (int i = 0; i < n_tiles; ++i, r.next()) {
+            for (int i = 0; i < (SINGLE && which == 0 ? 0 : n_tiles); ++i, r.next()) {
                 const int t0 = (int)(f_begin + (int64_t)i * TILE);
                 if (which == 0) {
                     mbar_wait_relaxed(&bars->a_empty[r.pos], r.phase ^ 1, 200);
@@ -724,6 +729,9 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
                 if (which == 1) {
                     mbar_arrive_expect_tx(&bars->b_full[r.pos], bytes);
                     bulk_g2s(dst, a.img2 + (size_t)(tile0 + i) * (2 * IMG_HALF), bytes, &bars->b_full[r.pos]);
+                } else if (SINGLE) {
+                    mbar_arrive_expect_tx(&bars->b_full[r.pos], RAW_FLOATS * 4u);
+                    tma_load_2d(dst + bytes, &map_lp, k0, t0, &bars->b_full[r.pos]);       // [64 frames x 128 posteriors]
                 } else {
                     mbar_arrive_expect_tx(&bars->b_full[r.pos], 2u * RAW_FLOATS * 4u);
                     tma_load_2d(dst + bytes, &map_l2, k0, t0, &bars->b_full[r.pos]);
@@ -786,11 +794,15 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
                     ph2 ^= 1;
                 }
             };
-            issue_g1(0);
-            if (n_tiles > 1) issue_g1(1);
-            for (int i = 0; i < n_tiles; ++i) {
-                if (i + 2 < n_tiles) issue_g1(i + 2);
-                issue_g2(i);
+            if constexpr (SINGLE) {
+                for (int i = 0; i < n_tiles; ++i) issue_g2(i);
+            } else {
+                issue_g1(0);
+                if (n_tiles > 1) issue_g1(1);
+                for (int i = 0; i < n_tiles; ++i) {
+                    if (i + 2 < n_tiles) issue_g1(i + 2);
+                    issue_g2(i);
+                }
             }
         }
     } else {
@@ -801,8 +813,13 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
         const int group = part & 1, half = part >> 1;        // tile parity; half of the tile's frames
         const int g = q * 32 + lane;                         // Gaussian (local) = TMEM lane
         const int pl = g / C;                                // its pdf (local)
-        const float2 k12 = __ldg(a.k12 + g0 + g);
-        const float k1 = k12.x, k2 = k12.y;
+        float k1 = 0.f, k2 = 0.f;
+        if constexpr (!SINGLE) {
+            const float2 k12 = __ldg(a.k12 + g0 + g);
+            k1 = k12.x;
+            k2 = k12.y;
+        }
+        const float wscale = exp2f(a.wexp);
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         float sums[MYCH][4], comp[MYCH][4];
 #pragma unroll
@@ -842,7 +859,7 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
         for (int i = group; i < n_tiles; i += 2) {
             mbar_wait(&bars->b_full[rb.pos], rb.phase);          // the llh / posterior blocks of the tile (TMA)
             if (tid == 0) trace(a.trace, i, 5);
-            mbar_wait(&bars->s_full[b], phs);
+            if constexpr (!SINGLE) mbar_wait(&bars->s_full[b], phs);
             if (tid == 0) trace(a.trace, i, 6);
             tc_fence_after();
             const float* raw = reinterpret_cast<const float*>(ring_b + (size_t)rb.pos * STAGE_B + STAGE_A);
@@ -853,14 +870,21 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
                 const int f0 = half * 32 + sub * 16;             // first frame (in the tile) of this block of 16
                 const uint32_t taddr = tmem_base + lane_addr + COL_S + (uint32_t)(b * TILE + f0);
                 float v[16];
-                tmem_ld16(taddr, v);
-                const float* rl2 = raw + f0 * NK + pl;
-                const float* rlp = rl2 + RAW_FLOATS;
+                if constexpr (SINGLE) {
+                    // w = the pdf posterior (rows past N and columns past Kp arrive as zeros)
+                    const float* rp = raw + f0 * NK + pl;
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    // z = S k1 + k2 is bit for bit the value KA16 normalised: z - llh2 = log2 responsibility
-                    const float z = fmaf(v[e], k1, k2);
-                    v[e] = ex2((z - rl2[e * NK]) + (rlp[e * NK] + a.wexp));
+                    for (int e = 0; e < 16; ++e) v[e] = rp[e * NK] * wscale;
+                } else {
+                    tmem_ld16(taddr, v);
+                    const float* rl2 = raw + f0 * NK + pl;
+                    const float* rlp = rl2 + RAW_FLOATS;
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        // z = S k1 + k2 is bit for bit the value KA16 normalised: z - llh2 = log2 responsibility
+                        const float z = fmaf(v[e], k1, k2);
+                        v[e] = ex2((z - rl2[e * NK]) + (rlp[e * NK] + a.wexp));
+                    }
                 }
                 const int nvalid = n_left - sub * 16;
                 if (nvalid < 16) {       // the last tile of the batch: frames past the end carry no weight
@@ -939,7 +963,8 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
 }
 
 static size_t kc_smem(int KP, int C, int na, int nb) {
-    return (size_t)na * (2 * TILE * KP * 2) + (size_t)nb * (2 * TILE * KP * 2 + 2 * TILE * (GM / C) * 4) + sizeof(KcBarriers) + 1024;
+    return (size_t)na * (2 * TILE * KP * 2) + (size_t)nb * (2 * TILE * KP * 2 + (C == 1 ? 1 : 2) * TILE * (GM / C) * 4) +
+           sizeof(KcBarriers) + 1024;
 }
 
 // log2 of pdf posteriors (the forward-backward kernels that cannot write them themselves)
@@ -1031,10 +1056,10 @@ static int launch_kc(const KcArgs& a0, const float* llh2, int64_t ld_llh, const 
                      int64_t ranges, cudaStream_t st) {
     KcArgs a = a0;
     // ring A (img1 tiles): 4 deep; ring B (img2 tile + llh / posterior blocks): whatever else fits
-    a.na = 4;
+    a.na = C == 1 ? 0 : 4;
     a.nb = RING_MAX;
     while (a.nb > 2 && kc_smem(KP, C, a.na, a.nb) > 227 * 1024) --a.nb;
-    while (a.na > 2 && kc_smem(KP, C, a.na, a.nb) > 227 * 1024) --a.na;
+    while (C != 1 && a.na > 2 && kc_smem(KP, C, a.na, a.nb) > 227 * 1024) --a.na;
     const size_t smem = kc_smem(KP, C, a.na, a.nb);
     if (smem > 227 * 1024) return BEER_ERR_UNSUPPORTED;
     CUtensorMap m1, m2;
@@ -1055,6 +1080,7 @@ static int launch_kc(const KcArgs& a0, const float* llh2, int64_t ld_llh, const 
 static int nb_of(int M, int C) {
     // Gaussians per KA16 chunk: the largest divisor of M that is a multiple of 16 and of C, at most 256 (no padded
     // columns in the last chunk); 128 with padding when M has none
+    if (M <= 160 && C <= 16) return (M + 15) / 16 * 16;   // one chunk, no wider than needed
     int best = 0;
     for (int nb = 16; nb <= 160; nb += 16)      // two weight stages, two statistics tiles and the staged output fit in shared memory
         if (M % nb == 0 && nb % C == 0) best = nb;
@@ -1078,8 +1104,8 @@ void beer_mix16_set_trace(void* dev_buf) { mix16::g_trace = (unsigned long long*
 int beer_mix16_supported(int M, int D, int C) {
     if (M <= 0 || C <= 0 || M % C != 0) return 0;
     if (!(D == 20 || D == 40)) return 0;
-    if (!(C == 4 || C == 8 || C == 16)) return 0;       // C | 128, u block of a tile <= 8 KB
-    if ((M / C) % 4 != 0) return 0;                      // float4 rows of posteriors / llhs
+    if (!(C == 1 || C == 4 || C == 8 || C == 16)) return 0;      // C | 128, llh / posterior block of a tile <= 8 KB
+    if ((M / C) % 4 != 0) return 0;                      // 16-byte rows of posteriors / llhs
     return 1;
 }
 
@@ -1156,8 +1182,8 @@ int beer_mix16_emission(const void* img1, int64_t N, int D, const void* wimg, co
     cudaStream_t st = (cudaStream_t)stream;
 #define BEER_KA_CASE(kp, c) \
     if (KP == kp && C == c) return mix16::launch_ka<kp, c>(a, st);
-    BEER_KA_CASE(80, 4) BEER_KA_CASE(80, 8) BEER_KA_CASE(80, 16)
-    BEER_KA_CASE(48, 4) BEER_KA_CASE(48, 8) BEER_KA_CASE(48, 16)
+    BEER_KA_CASE(80, 1) BEER_KA_CASE(80, 4) BEER_KA_CASE(80, 8) BEER_KA_CASE(80, 16)
+    BEER_KA_CASE(48, 1) BEER_KA_CASE(48, 4) BEER_KA_CASE(48, 8) BEER_KA_CASE(48, 16)
 #undef BEER_KA_CASE
     return BEER_ERR_UNSUPPORTED;
 }
@@ -1188,8 +1214,13 @@ int beer_mix16_gmm_posteriors(const float* llh2, int64_t N, int Kp, int64_t ld_l
 int beer_mix16_accumulate(const void* img1, const void* img2, int64_t N, int D, const uint32_t* wtm, const float* k12,
                           const float* alpha, int M, int C, const float* pdf_lpost, int64_t ld_lpost,
                           const float* llh2, int64_t ld_llh, float scale, double* acc_normal, void* stream) {
-    if (!img1 || !img2 || !wtm || !k12 || !alpha || !pdf_lpost || !llh2 || !acc_normal || N < 0) return BEER_ERR_ARG;
+    if (!img2 || !alpha || !pdf_lpost || !acc_normal || N < 0) return BEER_ERR_ARG;
+    if (C != 1 && (!img1 || !wtm || !k12 || !llh2)) return BEER_ERR_ARG;
     if (!beer_mix16_supported(M, D, C)) return BEER_ERR_UNSUPPORTED;
+    if (C == 1) {            // single-Gaussian pdfs: pdf_lpost holds the posteriors themselves, nothing else is read
+        llh2 = pdf_lpost;
+        ld_llh = ld_lpost;
+    }
     if (ld_lpost < M / C || ld_llh < M / C || ld_lpost % 4 != 0 || ld_llh % 4 != 0) return BEER_ERR_ARG;
     if (((uintptr_t)pdf_lpost & 15) != 0 || ((uintptr_t)llh2 & 15) != 0 || N >= (int64_t)1 << 31) return BEER_ERR_ARG;
     if (N == 0) return BEER_OK;
@@ -1214,8 +1245,8 @@ int beer_mix16_accumulate(const void* img1, const void* img2, int64_t N, int D, 
     const int KP = mix16::kp_of(D);
 #define BEER_KC_CASE(kp, c) \
     if (KP == kp && C == c) return mix16::launch_kc<kp, c>(a, llh2, ld_llh, pdf_lpost, ld_lpost, ranges, st);
-    BEER_KC_CASE(80, 4) BEER_KC_CASE(80, 8) BEER_KC_CASE(80, 16)
-    BEER_KC_CASE(48, 4) BEER_KC_CASE(48, 8) BEER_KC_CASE(48, 16)
+    BEER_KC_CASE(80, 1) BEER_KC_CASE(80, 4) BEER_KC_CASE(80, 8) BEER_KC_CASE(80, 16)
+    BEER_KC_CASE(48, 1) BEER_KC_CASE(48, 4) BEER_KC_CASE(48, 8) BEER_KC_CASE(48, 16)
 #undef BEER_KC_CASE
     return BEER_ERR_UNSUPPORTED;
 }

@@ -88,7 +88,8 @@ class EmissionParams:
         self.uniform_C = int(counts[0]) if len(counts) and np.all(counts == counts[0]) else 0
         self.use_tc = bool(self.uniform_C) and ops.emission_tc_supported(self.M, self.D, self.uniform_C)
         # mixtures of 4 / 8 / 16 Gaussians per pdf: the fp16-split kernels that keep the per-Gaussian llhs on chip
-        self.use16 = (self.has_mixtures and bool(self.uniform_C) and os.environ.get('BEER_B200_NO_MIX16') is None
+        # (single-Gaussian pdfs, C = 1, take the same kernels: statistics / posteriors as tensor-memory operands)
+        self.use16 = (bool(self.uniform_C) and os.environ.get('BEER_B200_NO_MIX16') is None
                       and ops.mix16_supported(self.M, self.D, self.uniform_C))
         # a plain GMM (one pdf of M components): its components as pseudo-pdfs of 8 / 16 / 4 for the same kernels
         self.gmm_C = 0
@@ -404,13 +405,14 @@ class VBEngine:
                                                     workspace=self.ws, out_pdf_post=pdf_post,
                                                     out_utt_exp_llh=self.utt_ell[u0:u1])
                 else:
-                    direct = images is not None and not nonident and plan.writes_log2_posteriors
+                    direct = (images is not None and not nonident and plan.writes_log2_posteriors
+                              and self.mix16.C > 1)         # single-Gaussian pdfs: the statistics kernel takes pdf_post
                     ops.hmm_forward_backward(plan, pdf_llh, fref, rel, scale=self.scale, workspace=self.ws,
                                              want_pdf_post=not direct, out_pdf_post=None if direct else pdf_post,
                                              out_pdf_lpost=pdf_post if direct else None,
                                              out_utt_exp_llh=self.utt_ell[u0:u1],
                                              unit_counts=self.unit_counts, llh_log2=images is not None)
-                    if images is not None and not direct:      # graphs without a loop kernel: log2 of pdf_post
+                    if images is not None and not direct and self.mix16.C > 1:      # graphs without a loop kernel: log2 of pdf_post
                         self.mix16.log2_posteriors(pdf_post, out=pdf_post)
                         self.gpu_launches += 1
             with self._stage('KC_accumulate'):

@@ -641,8 +641,11 @@ class Mix16:
         return llh2
 
     def accumulate(self, images, pdf_lpost, llh2, acc_normal, scale=1.0):
-        """`pdf_lpost` [N, Kp]: log2 of the (scaled) pdf posteriors, see `log2_posteriors`."""
+        """`pdf_lpost` [N, Kp]: log2 of the (scaled) pdf posteriors, see `log2_posteriors`; for single-Gaussian pdfs
+        (C = 1) the posteriors themselves, `llh2` is then not read."""
         N = images['N']
+        if llh2 is None:
+            llh2 = pdf_lpost
         _lib.check(_lib.load().beer_mix16_accumulate(
             _p(images['img1']), _p(images['img2']), N, self.D, _p(self.wtm), _p(self.k12),
             _p(images['alpha']), self.M, self.C, _p(pdf_lpost, f32), pdf_lpost.stride(0), _p(llh2, f32), llh2.stride(0),

@@ -355,7 +355,9 @@ BEER_API int beer_mix16_emission(const void* img1, int64_t N, int D, const void*
                         float* llh2, int64_t ld, void* stream);
 /* acc_normal [M, 2D+2] (fp64) += sum_t 2^pdf_lpost[t, pdf(j)] r_tj T(x_t) with the responsibilities r = 2^(z - llh2)
  * recomputed on chip (mixtureset.py:100-112, normalset.py:121-123).  pdf_lpost [N, ld] = log2 of the pdf posteriors
- * (times `scale`, -inf = zero): written by beer_hmm_forward_backward_ex, or beer_mix16_log2_posteriors of pdf_post. */
+ * (times `scale`, -inf = zero): written by beer_hmm_forward_backward_ex, or beer_mix16_log2_posteriors of pdf_post.
+ * C = 1 (single-Gaussian pdfs, NormalSet.accumulate alone): pdf_lpost holds the posteriors THEMSELVES (linear, as
+ * beer_hmm_forward_backward writes pdf_post) and img1 / wtm / k12 / llh2 are not read (may be NULL). */
 BEER_API int beer_mix16_accumulate(const void* img1, const void* img2, int64_t N, int D, const uint32_t* wtm, const float* k12,
                           const float* alpha, int M, int C, const float* pdf_lpost, int64_t ld_lpost,
                           const float* llh2, int64_t ld_llh, float scale, double* acc_normal, void* stream);

@@ -196,6 +196,48 @@ def test_viterbi_training_matches_oracle(C, chunk, scale):
         np.testing.assert_allclose(g, w, rtol=2e-4, atol=2e-4)
 
 
+@pytest.mark.parametrize('chunk,use_graph,mix16', [(None, False, True), (333, False, True), (None, True, True),
+                                                   (None, False, False)])
+def test_vb_iterations_cfg2_shape(chunk, use_graph, mix16, monkeypatch):
+    """The shape of BASELINE configs[1]: 25 units x 4 states = 100 single-Gaussian pdfs, D = 40 (mix16 = True: the
+    fp16-split kernels with the statistics / posteriors as tensor-memory operands, csrc/mix16.cu with C = 1; False: the
+    3xTF32 kernels of round 1); ragged utterances, three VB iterations against the fp64 oracle."""
+    from beer_b200 import ops, synthetic
+    from beer_b200.engine import EmissionParams, Utterances, VBEngine
+    if not mix16:
+        monkeypatch.setenv('BEER_B200_NO_MIX16', '1')
+    dev = torch.device('cuda', 0)
+    P, S, D = 25, 4, 40
+    K = P * S
+    lens = [150, 41, 297, 129, 64, 1]
+    graph, _, _ = synthetic.phone_loop_graph(P, S)
+    plan = ops.GraphPlan(graph.init_log_probs.numpy(), graph.final_log_probs.numpy(),
+                         graph.trans_log_probs.numpy(), graph.pdf_id_mapping, n_pdfs=K)
+    means = 2.0 * torch.randn(K, D, generator=torch.Generator().manual_seed(0))
+    full = synthetic.sample_utterances(graph, means, len(lens), max(lens), seed=1, device=dev)
+    full = full.reshape(len(lens), max(lens), D)
+    utts_dev = [full[i, :n] for i, n in enumerate(lens)]
+    X = torch.cat(utts_dev)
+    prior, post = synthetic.initial_normal_gamma(K, D, seed=2, device=dev)
+    em = EmissionParams(prior, post)
+    N = sum(lens)
+    eng = VBEngine(em, plan, Utterances(X, lens), datasize=float(N), chunk_frames=chunk, distributed=False,
+                   use_graph=use_graph)
+    assert (eng.mix16 is not None) == mix16
+    ng_prior, ng_post = _host(prior), _host(post)
+    og = (graph.init_log_probs.double().numpy(), graph.final_log_probs.double().numpy(),
+          graph.trans_log_probs.double().numpy(), graph.pdf_id_mapping)
+    utts = [u.double().cpu().numpy() for u in utts_dev]
+    for it in range(3):
+        want, ng_post, _, info = O.vb_iteration_hmm(utts, ng_prior, ng_post, None, None, og)
+        got = float(eng.step().item())
+        assert abs(got - want) <= 1e-5 * abs(want), (it, got, want)
+        acc = eng.acc.cpu().numpy()
+        assert np.abs(acc - info['acc_normal']).max() <= 3e-5 * np.abs(info['acc_normal']).max()
+    for g, w in zip(_host(em.post), ng_post):
+        np.testing.assert_allclose(g, w, rtol=2e-4, atol=2e-4)
+
+
 @pytest.mark.parametrize('chunk,mix16', [(None, False), (170, False), (None, True), (170, True)])
 def test_vb_iterations_streamed_mixture_kernels(chunk, mix16, monkeypatch):
     """(mix16 = False: the 3xTF32 kernels that materialise the per-Gaussian llhs; True: the fp16-split kernels that keep

@@ -41,7 +41,7 @@ def _reference(X, post, conc, C):
 
 
 @pytest.mark.parametrize('M,D,C,N', [(8000, 40, 8, 700), (256, 40, 8, 1000), (160, 20, 8, 333), (96, 40, 4, 130),
-                                     (320, 40, 16, 64)])
+                                     (320, 40, 16, 64), (100, 40, 1, 1000), (256, 40, 1, 333), (12, 20, 1, 130)])
 def test_emission_and_statistics_match_fp64(M, D, C, N):
     from beer_b200 import ops
     Kp = M // C
@@ -50,7 +50,7 @@ def test_emission_and_statistics_match_fp64(M, D, C, N):
     X = (2.0 * torch.randn(N, D, generator=g)).to(DEV)
     X[:, 0] *= 10.0                     # dimensions of different ranges: the per-dimension scales matter
     X[:, 1] *= 0.01
-    logw = ops.dirichlet_expected_logw(conc).reshape(-1).contiguous()
+    logw = ops.dirichlet_expected_logw(conc).reshape(-1).contiguous()      # (C = 1: psi(a) - psi(a) = 0)
     W, bias, ref = ops.emission_prepare(*post, logw=logw)
     mx = ops.Mix16(M, D, C, DEV)
     images = mx.build_images(X)
@@ -78,7 +78,7 @@ def test_emission_and_statistics_match_fp64(M, D, C, N):
     pp = torch.rand(N, Kp, generator=g).to(DEV)
     pp = torch.where(pp < 0.6, torch.zeros_like(pp), pp).contiguous()
     acc = torch.zeros(M, 2 * D + 2, device=DEV, dtype=torch.float64)
-    lpp = mx.log2_posteriors(pp)
+    lpp = mx.log2_posteriors(pp) if C > 1 else pp      # single-Gaussian pdfs: the posteriors themselves
     mx.accumulate(images, lpp, llh2, acc)
     resp = (comp.reshape(N, Kp, C) - pdf[:, :, None]).exp()
     w = (resp * pp.double()[:, :, None]).reshape(N, M)
