@@ -325,8 +325,9 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a, con
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __half* Bs = reinterpret_cast<__half*>(smem_raw);                        // [KA_STAGES][hi | lo] of NB x KP
     const int b_stage = 2 * a.NB * KP;
-    float2* s_k12 = reinterpret_cast<float2*>(Bs + KA_STAGES * b_stage);     // [K12_RING][NB] (k1, k2)
-    KaBarriers* bars = reinterpret_cast<KaBarriers*>(s_k12 + K12_RING * a.NB);
+    const int n_stages = a.n_chunks > 1 ? KA_STAGES : 1, n_k12 = a.n_chunks > 1 ? K12_RING : 1;
+    float2* s_k12 = reinterpret_cast<float2*>(Bs + n_stages * b_stage);      // [K12_RING][NB] (k1, k2)
+    KaBarriers* bars = reinterpret_cast<KaBarriers*>(s_k12 + n_k12 * a.NB);
     // staged output: [4 lane quarters][3 buffers][32 frames][NB / C pdfs] (128-byte aligned)
     float* s_out = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(bars + 1) + 127) & ~uintptr_t(127));
     const int PC = a.NB / C;
@@ -360,7 +361,12 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a, con
             int st = 0;
             uint32_t ph = 0;
             const uint32_t b_bytes = (uint32_t)b_stage * 2u, k_bytes = (uint32_t)a.NB * 8u;
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            if (a.n_chunks == 1) {          // the whole weight image stays resident: loaded once
+                mbar_arrive_expect_tx(&bars->b_full[0], b_bytes + k_bytes);
+                bulk_g2s(Bs, a.wimg, b_bytes, &bars->b_full[0]);
+                bulk_g2s(s_k12, a.k12, k_bytes, &bars->b_full[0]);
+            }
+            for (int64_t tile = blockIdx.x; a.n_chunks > 1 && tile < n_tiles; tile += gridDim.x) {
                 for (int c = 0; c < a.n_chunks; ++c, ++it) {
                     mbar_wait_relaxed(&bars->b_empty[st], ph ^ 1, 200);
                     trace(a.trace, it, 0);
@@ -386,7 +392,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a, con
                 const uint32_t a_hi = tmem_base + (ab ? COL_A1 : COL_A0), a_lo = a_hi + KP / 2;
                 for (int c = 0; c < a.n_chunks; ++c, ++it) {
                     const int buf = it & 1;
-                    mbar_wait(&bars->b_full[st], ph);
+                    if (a.n_chunks > 1 || it == 0) mbar_wait(&bars->b_full[st], ph);      // (a resident image lands once)
                     trace(a.trace, it, 1);
                     mbar_wait_relaxed(&bars->t_empty[buf], ((it >> 1) & 1) ^ 1, 32);
                     trace(a.trace, it, 2);
@@ -402,11 +408,13 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a, con
                         umma_f16_ts(d_tmem, a_lo + 8u * s, dbh + 16u * s, idesc, 1);      // statistics lo x weights hi
                     }
                     umma_commit(&bars->t_full[buf]);
-                    umma_commit(&bars->b_empty[st]);
                     trace(a.trace, it, 3);
-                    if (++st == KA_STAGES) {
-                        st = 0;
-                        ph ^= 1;
+                    if (a.n_chunks > 1) {
+                        umma_commit(&bars->b_empty[st]);
+                        if (++st == KA_STAGES) {
+                            st = 0;
+                            ph ^= 1;
+                        }
                     }
                 }
                 umma_commit(&bars->a_empty[ab]);
@@ -464,7 +472,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a, con
                 mbar_wait(&bars->t_full[buf], (it >> 1) & 1);
                 if (lane == 0 && (warp == 0 || warp == 15)) trace(a.trace, it, warp == 0 ? 4 : 6);
                 tc_fence_after();
-                const float2* kk = s_k12 + (it & (K12_RING - 1)) * a.NB;
+                const float2* kk = s_k12 + (a.n_chunks > 1 ? (it & (K12_RING - 1)) * a.NB : 0);
                 const uint32_t taddr = tmem_base + lane_addr + (uint32_t)buf * 256u;
                 float* sbuf = s_out + ((size_t)qq * 3 + it % 3) * 32 * PC + (size_t)lane * PC;     // this frame's staged row
                 // G units at a time: all their TMEM loads in flight together, independent max / exp / sum chains
@@ -544,8 +552,9 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a, con
     }
 }
 
-static size_t ka_smem(int KP, int NB, int C) {
-    return (size_t)KA_STAGES * 2 * NB * KP * 2 + (size_t)K12_RING * NB * 8 + sizeof(KaBarriers) + 128 +
+static size_t ka_smem(int KP, int NB, int C, int n_chunks) {
+    const int stages = n_chunks > 1 ? KA_STAGES : 1, k12 = n_chunks > 1 ? K12_RING : 1;
+    return (size_t)stages * 2 * NB * KP * 2 + (size_t)k12 * NB * 8 + sizeof(KaBarriers) + 128 +
            (size_t)4 * 3 * 32 * (NB / C) * 4 + 1024;
 }
 
@@ -554,7 +563,7 @@ static int encode_rows(CUtensorMap* map, const float* base, int64_t N, int Kp, i
 template <int KP, int C>
 static int launch_ka(const KaArgs& a0, cudaStream_t st) {
     KaArgs a = a0;
-    const size_t smem = ka_smem(KP, a.NB, C);
+    const size_t smem = ka_smem(KP, a.NB, C, a.n_chunks);
     if (smem > 227 * 1024) return BEER_ERR_UNSUPPORTED;
     static bool attr = false;
     if (!attr) {
