@@ -552,10 +552,10 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a, con
     }
 }
 
-static size_t ka_smem(int KP, int NB, int C, int n_chunks) {
+static size_t ka_smem(int KP, int NB, int C, int n_chunks, bool staged) {
     const int stages = n_chunks > 1 ? KA_STAGES : 1, k12 = n_chunks > 1 ? K12_RING : 1;
     return (size_t)stages * 2 * NB * KP * 2 + (size_t)k12 * NB * 8 + sizeof(KaBarriers) + 128 +
-           (size_t)4 * 3 * 32 * (NB / C) * 4 + 1024;
+           (staged ? (size_t)4 * 3 * 32 * (NB / C) * 4 : 0) + 1024;
 }
 
 static int encode_rows(CUtensorMap* map, const float* base, int64_t N, int Kp, int64_t ld, int box_cols, int box_rows);
@@ -563,7 +563,9 @@ static int encode_rows(CUtensorMap* map, const float* base, int64_t N, int Kp, i
 template <int KP, int C>
 static int launch_ka(const KaArgs& a0, cudaStream_t st) {
     KaArgs a = a0;
-    const size_t smem = ka_smem(KP, a.NB, C, a.n_chunks);
+    // staged tensor stores when the staging buffers fit next to the weight ring (wide single-Gaussian chunks do not)
+    const bool fits = ka_smem(KP, a.NB, C, a.n_chunks, true) <= 227 * 1024;
+    const size_t smem = ka_smem(KP, a.NB, C, a.n_chunks, fits);
     if (smem > 227 * 1024) return BEER_ERR_UNSUPPORTED;
     static bool attr = false;
     if (!attr) {
@@ -574,7 +576,7 @@ static int launch_ka(const KaArgs& a0, cudaStream_t st) {
     CUtensorMap omap;
     memset(&omap, 0, sizeof(omap));
     const int PC = a.NB / C;
-    a.staged = (PC % 4 == 0 && a.ld % 4 == 0 && ((uintptr_t)a.llh2 & 15) == 0 && a.N < ((int64_t)1 << 31)) ? 1 : 0;
+    a.staged = (fits && PC % 4 == 0 && a.ld % 4 == 0 && ((uintptr_t)a.llh2 & 15) == 0 && a.N < ((int64_t)1 << 31)) ? 1 : 0;
     if (a.staged && encode_rows(&omap, a.llh2, a.N, a.Kp, a.ld, PC, 32) != BEER_OK) a.staged = 0;
     const int64_t n_tiles = (a.N + 127) / 128;
     const int grid = (int)std::min<int64_t>(n_tiles, kNumSMs);
@@ -615,9 +617,10 @@ struct KcBarriers {
     uint64_t a_full[RING_MAX], a_empty[RING_MAX];     // ring A: img1 tiles (first MMA), freed as soon as S^T is computed
     uint64_t b_full[RING_MAX], b_empty[RING_MAX];     // ring B: img2 tile + llh / posterior blocks (epilogue, second MMA)
     uint64_t s_full[NSB], a2_full[NSB];
+    uint64_t a2_empty[NSB];                           // single-Gaussian mode: the second MMA has read the A2 buffer
     uint64_t d2_full[2], d2_empty[2];
     uint32_t tmem_base;
-    uint32_t pad[3];
+    uint32_t pad[1];
 };
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -682,6 +685,7 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
         for (int i = 0; i < NSB; ++i) {
             mbar_init(&bars->s_full[i], 1);
             mbar_init(&bars->a2_full[i], EPI / 2);
+            mbar_init(&bars->a2_empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars->d2_full[i], 1);
@@ -795,6 +799,7 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
                     umma_f16_ts(d, a2 + 16u * ks, dbl + 16u * ks, idesc2, 1);        // w hi x statistics lo
                 }
                 umma_commit(&bars->b_empty[rb.pos]);    // the epilogue finished with the stage before a2_full completed
+                if constexpr (SINGLE) umma_commit(&bars->a2_empty[b2]);     // (mixtures: implied by the next s_full of the buffer)
                 if (last) umma_commit(&bars->d2_full[dbuf]);
                 trace(a.trace, i, 4);
                 rb.next();
@@ -868,7 +873,8 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
         for (int i = group; i < n_tiles; i += 2) {
             mbar_wait(&bars->b_full[rb.pos], rb.phase);          // the llh / posterior blocks of the tile (TMA)
             if (tid == 0) trace(a.trace, i, 5);
-            if constexpr (!SINGLE) mbar_wait(&bars->s_full[b], phs);
+            if constexpr (SINGLE) mbar_wait(&bars->a2_empty[b], phs ^ 1);     // the MMA of the tile three back has read the buffer
+            else mbar_wait(&bars->s_full[b], phs);
             if (tid == 0) trace(a.trace, i, 6);
             tc_fence_after();
             const float* raw = reinterpret_cast<const float*>(ring_b + (size_t)rb.pos * STAGE_B + STAGE_A);
