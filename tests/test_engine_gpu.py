@@ -209,7 +209,7 @@ def test_vb_iterations_cfg2_shape(chunk, use_graph, mix16, monkeypatch):
     dev = torch.device('cuda', 0)
     P, S, D = 25, 4, 40
     K = P * S
-    lens = [150, 41, 297, 129, 64, 1]
+    lens = [150, 41, 297, 129, 64, 5]
     graph, _, _ = synthetic.phone_loop_graph(P, S)
     plan = ops.GraphPlan(graph.init_log_probs.numpy(), graph.final_log_probs.numpy(),
                          graph.trans_log_probs.numpy(), graph.pdf_id_mapping, n_pdfs=K)
