@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 LIBPATH = os.path.join(LIBDIR, 'libbeer_b200.so')
-SOURCES = ['dists.cu', 'emission.cu', 'emission_tc.cu', 'scan.cu', 'accumulate.cu', 'accumulate_tc.cu', 'features.cu', 'transitions.cu', 'chains.cu', 'probe.cu', 'mix16.cu']
+SOURCES = ['dists.cu', 'emission.cu', 'emission_tc.cu', 'scan.cu', 'accumulate.cu', 'accumulate_tc.cu', 'features.cu', 'transitions.cu', 'chains.cu', 'probe.cu', 'mix16.cu', 'emission_bwd.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden']
 

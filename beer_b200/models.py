@@ -544,13 +544,21 @@ class Mixture(DiscreteLatentModel):
         X = frames_of(stats, em.D).detach()
         pdf, comp, fref = em.llh(X, want_comp=True)
         self.cache.update(X=X, pdf_llh=pdf, comp_llh=comp, emission=em, labels=None)
+        Xg = frames_with_grad(stats)
         if labels is None:
-            return pdf[:, 0] + fref
+            frame = pdf[:, 0] + fref
+            if Xg is not None:      # sum_c r_tc grad llh_c(x_t): detached responsibilities (mixture.py:79-93)
+                ones = torch.ones(X.shape[0], 1, device=X.device, dtype=f32)
+                frame = _attach_frame_grad(Xg, frame, ones, em, comp, pdf)
+            return frame
         labels = torch.as_tensor(labels, device=X.device).to(i32).contiguous()
         logw = em.log_weights()
         resps, frame = ops.path_posteriors(labels, em.M, pdf_llh=comp, frame_ref=fref)
         self.cache.update(labels=labels, resps=resps)
-        return frame - logw[labels.long()]
+        frame = frame - logw[labels.long()]
+        if Xg is not None:          # one-hot responsibilities: the gradient of the labelled component's llh
+            frame = _attach_frame_grad(Xg, frame, resps, em, None, None)
+        return frame
 
     def accumulate(self, stats, parent_msg=None):
         c = self.cache
@@ -706,23 +714,37 @@ class DynamicallyOrderedModelSet(ModelSet):
 
 class _FrameLlhGrad(torch.autograd.Function):
     """Gradient of the per-frame expected log-likelihood w.r.t. the frames with the posteriors held fixed
-    (hmm.py:79-87: the inference runs on `pc_llhs.detach()`, the returned value is `(pc_llhs * resps).sum(-1)`):
-    d/dx_t sum_k w_tk llh_k(x_t) = sum_k w_tk (E[lambda_k mu_k] - x_t E[lambda_k]), w = scale * posteriors per pdf.
-    Forward hands back the values the kernels computed; backward is two [N, Kp] x [Kp, D] products (a library GEMM:
-    this is the encoder-facing side of the model, not the VB hot path).  Single-Gaussian pdfs only."""
+    (hmm.py:79-87: the inference runs on `pc_llhs.detach()`, the returned value is `(pc_llhs * resps).sum(-1)`;
+    mixture.py:76-93: detached responsibilities times attached per-component llhs):
+        d/dx_t sum_j w_tj llh_j(x_t) = sum_j w_tj (E[lambda_j mu_j] - x_t E[lambda_j]),
+    w = scale * pdf posteriors (x responsibilities inside the pdf for mixtures).  Forward hands back the values the
+    kernels computed; backward is ONE tcgen05 kernel (csrc/emission_bwd.cu: w formed on chip as the tensor-memory
+    operand of [N, M] x [M, 2D]; w is never stored)."""
 
     @staticmethod
-    def forward(ctx, X, frame, pdf_post, ets, dim):
-        ctx.save_for_backward(X, pdf_post, ets)
-        ctx.dim = dim
+    def forward(ctx, X, frame, pdf_post, ets, comp_llh, pdf_llh, pdf_of, scale):
+        ctx.save_for_backward(X, pdf_post, ets, comp_llh, pdf_llh, pdf_of)
+        ctx.scale = scale
         return frame.clone()
 
     @staticmethod
     def backward(ctx, grad_out):
-        X, post, ets = ctx.saved_tensors
-        D = ctx.dim
-        g = post @ ets[:, :D] - X.detach() * (post @ ets[:, D:2 * D])
-        return grad_out[:, None] * g, None, None, None, None
+        X, post, ets, comp, pdf, pdf_of = ctx.saved_tensors
+        g = ops.emission_llh_bwd(X.detach(), ets, post, grad_out=grad_out.to(f32).contiguous(), comp_llh=comp,
+                                 pdf_llh=pdf, pdf_of=pdf_of, scale=ctx.scale)
+        return g, None, None, None, None, None, None, None
+
+
+def _attach_frame_grad(Xg, frame, post, em, comp, pdf, scale=1.0):
+    """`frame` (values of the kernels) with the autograd edge to the frames `Xg` described in _FrameLlhGrad."""
+    if not ops.emission_bwd_supported(em.M, em.D):
+        raise NotImplementedError(f'no gradient kernel w.r.t. the frames for D = {em.D} (2 D <= 128)')
+    ets = ops.normalgamma_expected_stats(*em._cat('posterior'))
+    pdf_of = None
+    if comp is not None:
+        pdf_of = torch.as_tensor(np.repeat(np.arange(em.Kp, dtype=np.int32), np.diff(em.comp_off_host)), device=em.device)
+    return _FrameLlhGrad.apply(Xg, frame, post.contiguous(), ets, comp, pdf if comp is not None else None, pdf_of,
+                               float(max(scale, 1.0)))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -801,10 +823,9 @@ class HMM(DiscreteLatentModel):
                           utts=utts, utt_exp_llh=utt_ell)
         Xg = frames_with_grad(stats)
         if Xg is not None:
-            if em.has_mixtures:
-                raise NotImplementedError('gradients w.r.t. the frames are available for single-Gaussian pdfs')
-            ets = ops.normalgamma_expected_stats(*em._cat('posterior'))
-            frame = _FrameLlhGrad.apply(Xg, frame, post, ets, em.D)
+            # (mixtures: mixtureset.py:92-98 returns a DETACHED log-normaliser, so the reference has no gradient here;
+            # this is the gradient of sum_k gamma_tk sum_c r_tkc llh_kc(x_t), the same construction one level down)
+            frame = _attach_frame_grad(Xg, frame, post, em, comp if em.has_mixtures else None, pdf, scale)
         return frame
 
     def accumulate(self, stats, parent_msg=None):

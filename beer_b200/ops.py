@@ -130,6 +130,33 @@ def emission_llh_tc(X, image, ref, M, C, want_comp=False, out=None, out_comp=Non
     return pdf_llh, comp, fref
 
 
+def emission_bwd_supported(M, D):
+    return bool(require_cuda().beer_emission_bwd_supported(int(M), int(D)))
+
+
+def emission_llh_bwd(X, exp_stats, pdf_post, grad_out=None, comp_llh=None, pdf_llh=None, pdf_of=None, scale=1.0):
+    """KA backward (beer_emission_llh_bwd): d/dX of sum_t grad_out[t] sum_k pdf_post[t,k] llh_k(x_t) with the posteriors
+    held fixed (hmm.py:79-87, vae.py:63-89).  `exp_stats` [M, >= 2D] = E[T(theta)] (normalgamma_expected_stats);
+    mixtures pass the per-Gaussian and per-pdf llhs of the forward call and `pdf_of` [M] (int32)."""
+    lib = require_cuda()
+    N, D = X.shape
+    M = exp_stats.shape[0]
+    dev = X.device
+    image = torch.empty(lib.beer_emission_bwd_image_bytes(M, D), dtype=torch.uint8, device=dev)
+    inv_scale = torch.empty(2 * D, dtype=f32, device=dev)
+    scratch = torch.empty(2 * D, dtype=i32, device=dev)
+    _lib.check(lib.beer_emission_bwd_pack(_p(exp_stats, f32), M, D, exp_stats.stride(0), _p(image), _p(inv_scale),
+                                          _p(scratch), _stream()), 'beer_emission_bwd_pack')
+    grad = torch.empty(N, D, dtype=f32, device=dev)
+    mixt = comp_llh is not None
+    _lib.check(lib.beer_emission_llh_bwd(
+        _p(X, f32), N, D, _p(image), _p(inv_scale), M, _p(pdf_post, f32), pdf_post.stride(0),
+        _p(comp_llh, f32, True), comp_llh.stride(0) if mixt else 0, _p(pdf_llh, f32, True),
+        pdf_llh.stride(0) if mixt else 0, _p(pdf_of, i32, True), _p(grad_out, f32, True), float(scale), _p(grad),
+        _stream()), 'beer_emission_llh_bwd')
+    return grad
+
+
 # ---------------------------------------------------------------------------
 # graph plan
 # ---------------------------------------------------------------------------

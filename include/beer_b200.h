@@ -108,6 +108,24 @@ BEER_API int beer_emission_llh_tc(const float* X, int64_t N, int D, const float*
                                   int C, float* pdf_llh, int64_t ld_pdf, float* comp_llh, float* frame_ref,
                                   void* stream);
 
+/* KA backward: gradient of sum_t grad_out[t] * sum_k pdf_post[t,k] llh_k(x_t) w.r.t. the frames, posteriors held fixed
+ * (beer/models/hmm.py:79-87 and mixtureset.py:85-98 run the inference on detached llhs; beer/models/vae.py:63-89 is the
+ * caller that back-propagates through prior.expected_log_likelihood):
+ *   grad_X[t] = grad_out[t] * ( sum_j w_tj E[lambda_j mu_j] - x_t o sum_j w_tj E[lambda_j] ),
+ *   w_tj = pdf_post[t, pdf(j)] * exp(comp_llh[t,j] - pdf_llh[t, pdf(j)])        (mixtures; comp_llh = NULL: w = pdf_post)
+ * One tcgen05 kernel (fp16 3-pass split, w as the tensor-memory A operand): w [N, M] is never stored.
+ *   beer_emission_bwd_pack(exp_stats [M, ld] = E[T(theta)] of beer_normalgamma_expected_stats, ...) -> image, inv_scale[2D]
+ *     (image: beer_emission_bwd_image_bytes(M, D) bytes; colmax_scratch: 2D uint32)
+ *   pdf_of [M] = pdf id of every Gaussian (mixtures only); grad_out [N] or NULL (= ones); scale = the factor pdf_post carries. */
+BEER_API int beer_emission_bwd_supported(int M, int D);
+BEER_API int64_t beer_emission_bwd_image_bytes(int M, int D);
+BEER_API int beer_emission_bwd_pack(const float* exp_stats, int M, int D, int64_t ld, void* image, float* inv_scale,
+                                    uint32_t* colmax_scratch, void* stream);
+BEER_API int beer_emission_llh_bwd(const float* X, int64_t N, int D, const void* image, const float* inv_scale, int M,
+                                   const float* pdf_post, int64_t ld_post, const float* comp_llh, int64_t ld_comp,
+                                   const float* pdf_llh, int64_t ld_pdf, const int* pdf_of, const float* grad_out,
+                                   float scale, float* grad_X, void* stream);
+
 /* Graph plan: device-resident sparse form of a CompiledGraph
  * (beer/graph.py:243-268: init_log_probs[K], final_log_probs[K], dense
  * trans_log_probs[K,K], pdf_id_mapping[K]).  Host pointers in, opaque handle out.

@@ -500,6 +500,36 @@ def gold_input_gradient():
 
 
 # ---------------------------------------------------------------------------
+def gold_mixture_input_gradient():
+    """d sum_t w_t exp_llh_t / dX through Mixture.expected_log_likelihood (mixture.py:70-93: the responsibilities are
+    detached, the per-component llhs are not), i.e. sum_c r_tc grad llh_c(x_t) -- the gradient a VAE encoder receives
+    from a GMM prior (vae.py:63-89).  200 components (ragged last chunk of 64), D = 40, 300 frames (ragged last tile);
+    free and labelled responsibilities."""
+    rng = np.random.default_rng(21)
+    C, D, N = 200, 40, 300
+    centres = 3.0 * rng.standard_normal((16, D))
+    X = (centres[rng.integers(0, 16, N)] + rng.standard_normal((N, D))).astype(np.float32)
+    torch.manual_seed(7)
+    ns = beer.NormalSet.create(torch.zeros(D), torch.ones(D), size=C, prior_strength=1., noise_std=2.,
+                               cov_type='diagonal')
+    gmm = beer.Mixture.create(ns).double()
+    par, w = gmm.modelset.means_precisions, gmm.categorical.weights
+    # uneven weights and precisions so that no term of the gradient is trivially constant
+    w.posterior.params.concentrations.copy_(torch.from_numpy(rng.uniform(0.2, 3.0, C)))
+    par.posterior.params.rates.mul_(torch.from_numpy(rng.uniform(0.5, 2.0, (C, D))))
+    out = dict(X=X, **ng_params(par.posterior, 'post_'), dpost=npy(w.posterior.params.concentrations))
+    up = torch.linspace(0.5, 1.5, N, dtype=torch.float64)
+    labels = torch.from_numpy(rng.integers(0, C, N))
+    for tag, kw in (('free', {}), ('labels', {'labels': labels})):
+        Xt = torch.from_numpy(X).double().requires_grad_(True)
+        exp_llh = gmm.expected_log_likelihood(gmm.sufficient_statistics(Xt), **kw)
+        (exp_llh * up).sum().backward()
+        out[tag + '_exp_llh'] = npy(exp_llh)
+        out[tag + '_grad'] = npy(Xt.grad)
+        gmm.clear_cache()
+    save('mixture_input_grad', upstream=npy(up), labels=npy(labels), **out)
+
+
 def gold_dense_ergodic():
     """Dense ergodic transitions as in tests/test_hmm.py:149-151, with exact
     Viterbi ties and an unreachable state."""
@@ -567,6 +597,9 @@ if __name__ == '__main__':
     if len(sys.argv) > 2 and sys.argv[2] == 'fbank':
         gold_fbank()
         sys.exit(0)
+    if len(sys.argv) > 2 and sys.argv[2] == 'mixture_input_grad':
+        gold_mixture_input_gradient()
+        sys.exit(0)
     gold_dists()
     gold_gmm_cfg1()
     hmm_case('hmm_small', n_units=3, n_states=4, D=5, T=60, seed=3, scale=1.0)
@@ -578,6 +611,7 @@ if __name__ == '__main__':
     gold_sb_phoneloop()
     gold_sb_phoneloop(hyper=True)
     gold_input_gradient()
+    gold_mixture_input_gradient()
     gold_dense_ergodic()
     gold_graph_compile()
     gold_fbank()

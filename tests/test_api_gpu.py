@@ -492,6 +492,57 @@ def test_gradient_wrt_frames(beer, name):
     assert np.abs(acc[par].cpu().numpy() - g['acc_normal']).max() <= 3e-5 * np.abs(g['acc_normal']).max()
 
 
+@pytest.mark.parametrize('tag', ['free', 'labels'])
+def test_gradient_wrt_frames_mixture(beer, tag):
+    """Mixture.expected_log_likelihood back-propagated to the frames (mixture.py:76-93: detached responsibilities x
+    attached per-component llhs; the path a VAE encoder sees with a GMM prior, vae.py:63-89) against the live
+    reference's autograd: 200 components (ragged chunk), D = 40, 300 frames (ragged tile) through the tcgen05
+    backward kernel (csrc/emission_bwd.cu)."""
+    g = load_golden('mixture_input_grad')
+    C, D = g['post_mean'].shape
+    ns = beer.NormalSet.create(torch.zeros(D, device=DEV), torch.ones(D, device=DEV), size=C, prior_strength=1.,
+                               noise_std=1., cov_type='diagonal')
+    set_ng(ns.means_precisions.posterior, g, 'post_')
+    gmm = beer.Mixture.create(ns)
+    gmm.categorical.weights.posterior.params.concentrations.copy_(t32(g['dpost']))
+    X = t32(g['X']).requires_grad_(True)
+    kw = {'labels': torch.from_numpy(g['labels'])} if tag == 'labels' else {}
+    exp_llh = gmm.expected_log_likelihood(gmm.sufficient_statistics(X), **kw)
+    np.testing.assert_allclose(exp_llh.detach().double().cpu().numpy(), g[tag + '_exp_llh'], rtol=1e-5, atol=1e-4)
+    (exp_llh * t32(g['upstream'])).sum().backward()
+    want = g[tag + '_grad']
+    assert np.abs(X.grad.double().cpu().numpy() - want).max() <= 2e-5 * np.abs(want).max()
+
+
+def test_gradient_wrt_frames_hmm_mixtureset(beer):
+    """HMM over a MixtureSet: the gradient of sum_t go_t sum_k gamma_tk sum_c r_tkc llh_kc(x_t) w.r.t. the frames
+    (posteriors and responsibilities held fixed) -- the mixture form of hmm.py:79-87.  The reference itself has no
+    gradient here (mixtureset.py:92-98 returns a detached log-normaliser), so the check is the definition evaluated in
+    fp64 from the posteriors / llhs the forward call cached."""
+    from beer_b200 import ops, synthetic
+    P, S, Cn, D, T = 6, 3, 4, 20, 170
+    K, M = P * S, P * S * Cn
+    graph, _, _ = synthetic.phone_loop_graph(P, S)
+    means = 2.0 * torch.randn(K, D, generator=torch.Generator().manual_seed(0))
+    X = synthetic.sample_utterances(graph, means, 1, T, seed=1, device=DEV).reshape(T, D)
+    ns = beer.NormalSet.create(torch.zeros(D, device=DEV), torch.ones(D, device=DEV), size=M, prior_strength=1.,
+                               noise_std=2., cov_type='diagonal')
+    hmm = beer.HMM.create(graph, beer.MixtureSet.create(K, ns, prior_strength=1.))
+    Xg = X.clone().requires_grad_(True)
+    scale = 0.7
+    exp_llh = hmm.expected_log_likelihood(hmm.sufficient_statistics(Xg), scale=scale)
+    up = torch.linspace(0.5, 1.5, T, device=DEV)
+    (exp_llh * up).sum().backward()
+    c = hmm.cache
+    w = (c['pdf_post'].double().repeat_interleave(Cn, dim=1)
+         * torch.exp(c['comp_llh'].double() - c['pdf_llh'].double().repeat_interleave(Cn, dim=1)))
+    ets = ops.normalgamma_expected_stats(*[t.float().contiguous() for t in
+                                           ns.means_precisions.posterior.params.as_tuple()]).double()
+    want = up.double()[:, None] * (w @ ets[:, :D] - X.double() * (w @ ets[:, D:2 * D]))
+    assert float(w.sum()) == pytest.approx(scale * T, rel=1e-5)
+    assert float((Xg.grad.double() - want).abs().max()) <= 2e-5 * float(want.abs().max())
+
+
 @pytest.mark.parametrize('P,S', [(96, 4), (130, 3), (250, 4)])
 def test_phoneloop_unit_counts_many_units(beer, P, S):
     """Unit counts of phone loops around the limits of the fused reduction (phoneloop.py:83-101): 96 units and the

@@ -370,3 +370,39 @@ def test_viterbi_loop_kernel_equals_generic_kernel_with_ties(ops, P, SU, monkeyp
         a, b = off[u], off[u + 1]
         want = O.best_path(llh[a:b].astype(np.float32).astype(np.float64), *[np.asarray(g, dtype=np.float64) for g in gr[:3]])
         np.testing.assert_array_equal(fast[a:b], want)
+
+
+@pytest.mark.parametrize('N,M,D,C,scale', [(300, 200, 40, 1, 1.0), (129, 64, 20, 1, 0.5), (1000, 1000, 40, 8, 3.0),
+                                           (77, 130, 13, 5, 1.0), (5, 3, 64, 1, 1.0)])
+def test_emission_llh_bwd(N, M, D, C, scale):
+    """KA backward (beer_emission_llh_bwd: fp16-split tcgen05, w as the tensor-memory operand) against the definition in
+    fp64: grad_t = go_t (sum_j w_tj E[lambda mu]_j - x_t o sum_j w_tj E[lambda]_j), w = post x exp(comp - pdf);
+    ragged tiles / chunks, every padded width of 2D, posteriors carrying a scale above and below one."""
+    from beer_b200 import ops
+    gen = torch.Generator().manual_seed(N + M)
+    dev = torch.device('cuda', 0)
+    X = (2.0 * torch.randn(N, D, generator=gen)).to(dev)
+    ets = torch.randn(M, 2 * D + 2, generator=gen)
+    ets[:, D:2 * D] = ets[:, D:2 * D].abs() * 3 + 0.1
+    ets[:, :D] *= 50.0                                     # columns of very different magnitude
+    ets = ets.to(dev)
+    Kp = M // C
+    post = torch.softmax(3.0 * torch.randn(N, Kp, generator=gen), dim=1) * scale
+    post[post < 1e-4 * scale] = 0.0
+    post = post.to(dev)
+    go = torch.linspace(-1.0, 2.0, N, device=dev)
+    comp = pdf = pdf_of = None
+    w = post.double()
+    if C > 1:
+        comp = (4.0 * torch.randn(N, M, generator=gen)).to(dev)
+        pdf = torch.logsumexp(comp.reshape(N, Kp, C).double(), dim=2).float()
+        pdf_of = torch.arange(Kp, dtype=torch.int32, device=dev).repeat_interleave(C)
+        w = w.repeat_interleave(C, dim=1) * torch.exp(comp.double() - pdf.double().repeat_interleave(C, dim=1))
+    got = ops.emission_llh_bwd(X, ets, post, grad_out=go, comp_llh=comp, pdf_llh=pdf, pdf_of=pdf_of, scale=scale)
+    e = ets.double()
+    want = go.double()[:, None] * (w @ e[:, :D] - X.double() * (w @ e[:, D:2 * D]))
+    assert float((got.double() - want).abs().max()) <= 5e-6 * float(want.abs().max())
+    # no upstream gradient = ones
+    got1 = ops.emission_llh_bwd(X, ets, post, comp_llh=comp, pdf_llh=pdf, pdf_of=pdf_of, scale=scale)
+    want1 = w @ e[:, :D] - X.double() * (w @ e[:, D:2 * D])
+    assert float((got1.double() - want1).abs().max()) <= 5e-6 * float(want1.abs().max())

@@ -49,7 +49,26 @@ run(6, 3, 1, 40, [50, 33], 'S=3 units (LR scalar rows)')
 run(16, 4, 8, 40, [130, 77, 40], 'mixtures C=8 (tcgen05, streamed weight image)')
 run(130, 4, 1, 40, [60, 35], 'many units (block scan), 5 Gaussian tiles')
 run(5, 4, 2, 12, [40, 41], 'SIMT kernels (D=12)')
-run(40, 4, 8, 40, [300, 61, 129], 'mixtures C=8, M=1280 (TMA tensor-map stores in KA, cp.async raw ring in KC)')
+run(40, 4, 8, 40, [300, 61, 129], 'mixtures C=8, M=1280 (fp16-split kernels, 8 weight chunks)')
+run(250, 4, 8, 40, [300, 61, 129, 700], 'BASELINE configs[2] shape: 1000 pdfs x 8 (fp16-split kernels, 8-warp scan)')
+run(12, 4, 4, 20, [90, 64, 1], 'mixtures C=4, D=20 (fp16-split kernels, single resident weight chunk)')
+os.environ['BEER_B200_NO_MIX16'] = '1'
+run(40, 4, 8, 40, [300, 61, 129], 'mixtures C=8, M=1280 (3xTF32 kernels: TMA tensor-map stores in KA, cp.async raw ring in KC)')
+del os.environ['BEER_B200_NO_MIX16']
+
+
+def run_gmm():
+    """A plain mixture of 64 Gaussians (VBEngine without a graph: emission -> frame softmax -> statistics)."""
+    C, D, N = 64, 40, 700
+    X = synthetic.sample_gmm_frames(N, D, seed=3, device=dev)
+    prior, post = synthetic.initial_normal_gamma(C, D, seed=2, device=dev)
+    conc = torch.full((1, C), 1.0 / C, device=dev)
+    em = EmissionParams(prior, post, comp_off=np.array([0, C]), weight_groups=(WeightGroup(0, 1, C, conc.clone(), conc.clone()),))
+    eng = VBEngine(em, None, Utterances(X, [N]), datasize=float(N), distributed=False)
+    print('gmm: elbo', [float(eng.step().item()) for _ in range(2)])
+
+
+run_gmm()
 
 
 def run_chains():
@@ -94,5 +113,6 @@ run_chains()
 sig = (np.random.default_rng(0).standard_normal(16000) * 1000).astype(np.int16)
 fb = features.fbank(sig, nfilters=40)
 print('fbank', tuple(fb.shape), tuple(features.add_deltas(fb).shape))
+print('mspec', tuple(features.short_term_mspec(sig)[0].shape))
 torch.cuda.synchronize()
 print('sanitize pass done')
