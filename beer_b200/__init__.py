@@ -17,5 +17,6 @@ from .inference import (EvidenceLowerBoundInstance, VBConjugateOptimizer, VBOpti
 from .models import (HMM, Categorical, CategoricalSet, DiscreteLatentModel,        # noqa: F401
                      DynamicallyOrderedModelSet, JointModelSet, Mixture, MixtureSet, Model, ModelSet,
                      NormalSet, PhoneLoop, BigramPhoneLoop, SBCategorical, SBCategoricalHyperPrior)
+from .vae import VAE                                                               # noqa: F401
 from .parameters import BayesianParameter, ConjugateBayesianParameter             # noqa: F401
 from .utils import logsumexp, onehot                                               # noqa: F401

@@ -42,7 +42,7 @@ class EvidenceLowerBoundInstance:
         return f'EvidenceLowerBoundInstance(value={float(self):.6f})'
 
     def __float__(self):
-        return float(self.value)
+        return float(self.value.detach() if isinstance(self.value, torch.Tensor) else self.value)
 
     def __add__(self, other):
         if not isinstance(other, EvidenceLowerBoundInstance):

@@ -530,6 +530,61 @@ def gold_mixture_input_gradient():
     save('mixture_input_grad', upstream=npy(up), labels=npy(labels), **out)
 
 
+class _Net(torch.nn.Sequential):
+    def __init__(self, dim_in, dim_out):
+        super().__init__(torch.nn.Linear(dim_in, dim_out), torch.nn.Tanh())
+        self.dim_in, self.dim_out = dim_in, dim_out
+
+
+def gold_vae():
+    """VAE (vae.py:27-89) with an HMM and with a GMM prior over a 5-d latent space: one `evidence_lower_bound` +
+    `backward()` with the reparameterisation noise recorded, so that the same draw can be replayed: ELBO, the value
+    matrix, the gradients of every network parameter (they flow through prior.expected_log_likelihood: hmm.py:79-87,
+    mixture.py:76-93) and the statistics accumulated for the prior."""
+    D, L, H, N = 12, 5, 16, 90
+    rng = np.random.default_rng(31)
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    out = dict(X=X)
+    for tag in ('hmm', 'gmm'):
+        torch.manual_seed(5)
+        if tag == 'hmm':
+            g, _, _, _ = phone_loop(3, 3)
+            cg = g.compile()
+            ns = beer.NormalSet.create(torch.zeros(L), torch.ones(L), size=cg.n_states, prior_strength=1., noise_std=1.,
+                                       cov_type='diagonal')
+            prior = beer.HMM.create(cg, ns)
+            out.update(**graph_arrays(cg, 'hmm_g_'))
+        else:
+            ns = beer.NormalSet.create(torch.zeros(L), torch.ones(L), size=7, prior_strength=1., noise_std=1.,
+                                       cov_type='diagonal')
+            prior = beer.Mixture.create(ns)
+        vae = beer.VAE(prior, _Net(D, H), _Net(L, H)).double()
+        par = ns.means_precisions
+        out.update(**ng_params(par.prior, tag + '_prior_'), **ng_params(par.posterior, tag + '_post_'))
+        for k, v in vae.state_dict().items():
+            if k.split('.')[0] in ('encoder', 'decoder', 'enc_mean_layer', 'enc_var_layer', 'dec_mean_layer', 'dec_var_layer'):
+                out[f'{tag}_sd_{k}'] = npy(v)
+        noise = torch.randn(N, 1, L, dtype=torch.float64)
+        real_randn = torch.randn
+        torch.randn = lambda *a, **k: noise.clone()
+        try:
+            Xt = torch.from_numpy(X).double()
+            value = vae.expected_log_likelihood(vae.sufficient_statistics(Xt))
+            vae.clear_cache()
+            elbo = beer.evidence_lower_bound(vae, Xt, datasize=N)
+            elbo.backward()
+        finally:
+            torch.randn = real_randn
+        out[tag + '_noise'] = npy(noise)
+        out[tag + '_value'] = npy(value)
+        out[tag + '_elbo'] = float(elbo)
+        out[tag + '_acc_normal'] = npy(elbo._acc_stats[par])
+        for k, p in vae.named_parameters():
+            if p.grad is not None:
+                out[f'{tag}_grad_{k}'] = npy(p.grad)
+    save('vae', **out)
+
+
 def gold_dense_ergodic():
     """Dense ergodic transitions as in tests/test_hmm.py:149-151, with exact
     Viterbi ties and an unreachable state."""
@@ -597,6 +652,9 @@ if __name__ == '__main__':
     if len(sys.argv) > 2 and sys.argv[2] == 'fbank':
         gold_fbank()
         sys.exit(0)
+    if len(sys.argv) > 2 and sys.argv[2] == 'vae':
+        gold_vae()
+        sys.exit(0)
     if len(sys.argv) > 2 and sys.argv[2] == 'mixture_input_grad':
         gold_mixture_input_gradient()
         sys.exit(0)
@@ -612,6 +670,7 @@ if __name__ == '__main__':
     gold_sb_phoneloop(hyper=True)
     gold_input_gradient()
     gold_mixture_input_gradient()
+    gold_vae()
     gold_dense_ergodic()
     gold_graph_compile()
     gold_fbank()

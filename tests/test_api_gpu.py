@@ -543,6 +543,57 @@ def test_gradient_wrt_frames_hmm_mixtureset(beer):
     assert float((Xg.grad.double() - want).abs().max()) <= 2e-5 * float(want.abs().max())
 
 
+class _Net(torch.nn.Sequential):
+    def __init__(self, dim_in, dim_out):
+        super().__init__(torch.nn.Linear(dim_in, dim_out), torch.nn.Tanh())
+        self.dim_in, self.dim_out = dim_in, dim_out
+
+
+@pytest.mark.parametrize('tag', ['hmm', 'gmm'])
+def test_vae_against_reference(beer, tag, monkeypatch):
+    """VAE (vae.py:27-89) over an HMM / a GMM prior: one evidence_lower_bound + backward() with the reference's
+    reparameterisation noise replayed.  The value matrix, the ELBO, the statistics of the prior and the gradient of every
+    network parameter -- which reaches the encoder through prior.expected_log_likelihood, i.e. through the backward
+    kernel of the emission llhs -- against the live reference's fp64 run."""
+    g = load_golden('vae')
+    X = t32(g['X'])
+    N, D = X.shape
+    L = g[tag + '_post_mean'].shape[1]
+    if tag == 'hmm':
+        graph = compiled(beer, g, 'hmm_g_')
+        ns = normalset(beer, g, graph.n_states, L, prior='hmm_prior_', post='hmm_post_')
+        prior = beer.HMM.create(graph, ns)
+    else:
+        ns = normalset(beer, g, g['gmm_post_mean'].shape[0], L, prior='gmm_prior_', post='gmm_post_')
+        prior = beer.Mixture.create(ns)
+    H = g[tag + '_sd_encoder.0.bias'].shape[0]
+    vae = beer.VAE(prior, _Net(D, H), _Net(L, H)).to(DEV)
+    sd = {k[len(tag) + 4:]: t32(g[k]) for k in g if k.startswith(tag + '_sd_')}
+    missing = vae.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys
+    noise = t32(g[tag + '_noise'])
+    monkeypatch.setattr(torch, 'randn', lambda *a, **k: noise.clone())
+    value = vae.expected_log_likelihood(vae.sufficient_statistics(X))
+    want = g[tag + '_value']
+    assert value.shape == want.shape                     # [N, N]: the reference's broadcast (vae.py:86)
+    assert np.abs(value.detach().double().cpu().numpy() - want).max() <= 2e-5 * np.abs(want).max()
+    vae.clear_cache()
+    elbo = beer.evidence_lower_bound(vae, X, datasize=N)
+    np.testing.assert_allclose(float(elbo), float(g[tag + '_elbo']), rtol=2e-5)
+    elbo.backward()
+    acc = elbo._acc_stats[ns.means_precisions].cpu().numpy()
+    assert np.abs(acc - g[tag + '_acc_normal']).max() <= 3e-5 * np.abs(g[tag + '_acc_normal']).max()
+    n_checked = 0
+    for name, p in vae.named_parameters():
+        key = f'{tag}_grad_{name}'
+        if key in g:
+            want = g[key]
+            assert p.grad is not None, name
+            assert np.abs(p.grad.double().cpu().numpy() - want).max() <= 1e-4 * np.abs(want).max(), name
+            n_checked += 1
+    assert n_checked == 12
+
+
 @pytest.mark.parametrize('P,S', [(96, 4), (130, 3), (250, 4)])
 def test_phoneloop_unit_counts_many_units(beer, P, S):
     """Unit counts of phone loops around the limits of the fused reduction (phoneloop.py:83-101): 96 units and the
