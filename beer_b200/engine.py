@@ -223,11 +223,15 @@ def stats_scale_from_flat(total_frames, datasize):
 class VBEngine:
     """One process per GPU; `utts` is this rank's shard.  Its frames stay resident in HBM, or --
     when `utts.X` is a pinned HOST tensor -- are streamed through two device staging buffers, the
-    copy of chunk i+1 overlapping the kernels of chunk i."""
+    copy of chunk i+1 overlapping the kernels of chunk i; with `prefetch` (default) the first chunk of the NEXT VB
+    iteration is copied under the last chunk of this one, so that in steady state no copy is exposed (the host tensor
+    must then not be modified between `step()` calls)."""
 
     def __init__(self, emission, plan, utts, datasize=None, scale=1.0, lrate=1.0, chunk_frames=None,
-                 process_group=None, distributed=None, use_graph=False, unit_weights=None, viterbi=False):
+                 process_group=None, distributed=None, use_graph=False, unit_weights=None, viterbi=False,
+                 prefetch=True):
         self.em, self.plan, self.utts = emission, plan, utts
+        self.prefetch = bool(prefetch)
         # Viterbi training (hmm.py:42-58 with viterbi=True, what recipes/zrc2019 trains with): one-hot posteriors of
         # the best path instead of forward-backward
         self.viterbi = bool(viterbi)
@@ -269,7 +273,9 @@ class VBEngine:
         self.profile = None      # optional {stage: [(start_event, end_event), ...]} (bench.py)
         self.host_mode = not utts.X.is_cuda
         if self.host_mode and chunk_frames is None:
-            chunk_frames = max(1, len(utts) // 8)
+            # ~100 MB of 40-d frames per chunk: large enough that the forward-backward grid fills the GPU (cfg3 with
+            # 1/8 of its 1250 utterances per chunk ran 26 % slower end to end than with 1/2)
+            chunk_frames = max(1, len(utts) // 8, min(len(utts), 640_000))
         self._chunks = self._make_chunks(chunk_frames)
         nmax = max((c[3] for c in self._chunks), default=0)
         if self.host_mode:
@@ -280,6 +286,7 @@ class VBEngine:
             self._ready = [torch.cuda.Event() for _ in range(2)]
             self._free = [torch.cuda.Event() for _ in range(2)]
             self._free_valid = [False, False]
+            self._copy_seq, self._pending = 0, None      # copies issued so far; staging buffer of the chunk in flight
         Kp = emission.Kp if not self.gmm else emission.M // emission.gmm_C
         self.pdf_llh = torch.empty(nmax, Kp, device=self.dev, dtype=f32)
         self._nonident = not self.gmm and (self.chains or not (plan.info['map_identity'] and plan.n_states == Kp))
@@ -354,13 +361,13 @@ class VBEngine:
         nonident = self._nonident
         chunks = [c for c in self._chunks if c[3] > 0]
         chunk_ids = [i for i, c in enumerate(self._chunks) if c[3] > 0]
-        if self.host_mode and chunks:
-            self._issue_copy(chunks[0], 0)
+        if self.host_mode and chunks and self._pending is None:
+            self._pending = self._next_copy(chunks[0])
         for ci, (u0, u1, f0, nf, rel) in enumerate(chunks):
             if self.host_mode:
-                b = ci & 1
-                if ci + 1 < len(chunks):
-                    self._issue_copy(chunks[ci + 1], (ci + 1) & 1)
+                b = self._pending
+                nxt = chunks[ci + 1] if ci + 1 < len(chunks) else (chunks[0] if self.prefetch else None)
+                self._pending = self._next_copy(nxt) if nxt is not None else None
                 torch.cuda.current_stream().wait_event(self._ready[b])
                 X = self._stage_buf[b][:nf]
             else:
@@ -431,13 +438,20 @@ class VBEngine:
                                          Kp=em.Kp)
             self.gpu_launches += 3
             if self.host_mode:
-                self._free[ci & 1].record()
-                self._free_valid[ci & 1] = True
+                self._free[b].record()
+                self._free_valid[b] = True
         # ELBO bookkeeping of the shard (objectives.py:176-190 summed as in accumulate.py:39-59)
         self.extras[1:3].copy_(self._shard_counts)       # device -> device: capturable in a CUDA graph
         self.extras[3] = self.utt_ell.sum()
         # sum_u ell_u / T_u; multiplied by the global datasize after the reduction
         self.extras[0] = (self.utt_ell * self.inv_len).sum()
+
+    def _next_copy(self, chunk):
+        """Issue the copy of `chunk` into the staging buffer whose turn it is; returns the buffer."""
+        b = self._copy_seq & 1
+        self._copy_seq += 1
+        self._issue_copy(chunk, b)
+        return b
 
     def _issue_copy(self, chunk, b):
         """H2D copy of one chunk into staging buffer b on the copy stream."""
