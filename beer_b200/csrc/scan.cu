@@ -40,6 +40,11 @@ struct beer_graph_plan {
     int jrows = 0;     // ELL rows of that junction (max over directions)
     int lr_su = 0, lr_u = 0;          // aligned left-to-right loop: states per unit, units per lane (0 = not)
     const float* lr_w = nullptr;      // device [3][32 * lr_su * lr_u]: self, incoming, end->junction (log2)
+    // the same loop for Viterbi, dense natural-log weights: [self K | previous state K | unit end -> any unit start P];
+    // vlr_ok: every unit start sees the SAME weight from a given unit end (bitwise), so that the first maximum over the
+    // unit ends is shared by all starts (register-resident kernel for more than 32 units)
+    const float* vlr = nullptr;
+    int vlr_ok = 0;
     beer::ScanLists fwd{}, bwd{}, vit{};
     const int* map = nullptr;        // device [K]
     const float* vit_final = nullptr;  // device [K] natural log
@@ -2528,6 +2533,237 @@ __global__ void __launch_bounds__(FB_WARPS * 32) hmm_viterbi_lr_kernel(VitArgs a
     }
 }
 
+// ---------------------------------------------------------------------------
+// The same recursion for MORE than 32 units (BASELINE configs[2]: 250 units x 4 states): one warp per utterance, U units
+// of SU states per lane, everything in registers.  Needs a loop whose unit starts all see the same weight from a given
+// unit end (plan->vlr_ok: the uniform phone loops of mkphoneloopgraph.py; bitwise equal columns of ln A[ends, starts]):
+// the first maximum over the P unit ends -- ascending source order, strict > -- is then ONE (value, index) pair per
+// frame, found with a lexicographic butterfly, and every start only compares it with its own self loop (which precedes
+// the end of unit v in source order iff its unit index <= v).  Back-pointers: one uint16 per unit and frame
+// (2 bits per inner state, 10 bits for the unit start), the backtrack stages 32 frames of them in shared memory.
+// The generic kernel walks 250 candidates for each of the 250 starts from shared memory: 340 ms per cfg3 batch
+// against ~2 ms here (same arithmetic, same tie-breaking: tests/test_kernels_gpu.py compares the paths exactly).
+// ---------------------------------------------------------------------------
+constexpr int VLM_WARPS = 4;
+
+template <int SU, int U>
+__global__ void __launch_bounds__(VLM_WARPS * 32) hmm_viterbi_lrm_kernel(VitArgs a, const float* __restrict__ vlr) {
+    constexpr int S = SU * U, PF = 4, ROW = 32 * S, BTLD = 32 * U;
+    constexpr int WARP_FLOATS = (PF * ROW * 4 > 32 * BTLD * 2) ? PF * ROW : 32 * BTLD / 2;
+    constexpr bool VEC = (S % 4) == 0;
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* ring = smem + (size_t)warp * WARP_FLOATS;                  // [PF][32 * S] llh rows
+    uint16_t* bt_s = reinterpret_cast<uint16_t*>(ring);               // backtrack: [32 frames][32 * U] (after the sweep)
+    const int K = a.K, P = K / SU, NONE = P + 1;
+    const int gwarp = blockIdx.x * VLM_WARPS + warp, nwarps = gridDim.x * VLM_WARPS;
+    const int unit0 = lane * U, k0 = unit0 * SU;
+    const bool vec_ok = VEC && (a.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.pl) & 15) == 0) && (K % 4 == 0);
+
+    float w_self[U][SU], w_prev[U][SU], wend[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const bool own = unit0 + u < P;
+        wend[u] = own ? __ldg(vlr + 2 * K + unit0 + u) : kNegInf;
+#pragma unroll
+        for (int s = 0; s < SU; ++s) {
+            const int k = k0 + u * SU + s;
+            w_self[u][s] = own ? __ldg(vlr + k) : kNegInf;
+            w_prev[u][s] = (own && s > 0) ? __ldg(vlr + K + k) : kNegInf;
+        }
+    }
+
+    auto prefetch = [&](float* slot, const float* row) {
+        if (vec_ok) {
+#pragma unroll
+            for (int v = 0; v < S / 4; ++v)
+                if (k0 + 4 * v < K) cp_async16(slot + lane * S + 4 * v, row + k0 + 4 * v);
+        } else {
+#pragma unroll
+            for (int j = 0; j < S; ++j)
+                if (k0 + j < K) cp_async4(slot + lane * S + j, row + k0 + j);
+        }
+    };
+
+    for (int utt = gwarp; utt < a.n_utts; utt += nwarps) {
+        const int64_t t0 = a.utt_off[utt];
+        const int T = (int)(a.utt_off[utt + 1] - t0);
+        if (T <= 0) continue;
+        const float* pl_u = a.pl + (size_t)t0 * a.ld;
+        uint16_t* bt_u = a.bt + (size_t)t0 * BTLD;
+        __syncwarp();                                    // the previous utterance's backtrack is done with the ring
+        for (int r = 0; r < PF; ++r) {
+            if (r < T) prefetch(ring + r * ROW, pl_u + (size_t)r * a.ld);
+            cp_async_commit();
+        }
+        float om[U][SU];
+        int slot = 0;
+        for (int t = 0; t < T; ++t) {
+            cp_async_wait<PF - 1>();
+            float p[U][SU];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int s = 0; s < SU; ++s)
+                    p[u][s] = (unit0 + u < P) ? a.scale * ring[slot * ROW + lane * S + u * SU + s] : kNegInf;
+            if (t + PF < T) prefetch(ring + slot * ROW, pl_u + (size_t)(t + PF) * a.ld);
+            cp_async_commit();
+            slot = (slot + 1 == PF) ? 0 : slot + 1;
+            if (t == 0) {
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int s = 0; s < SU; ++s)
+                        om[u][s] = (unit0 + u < P) ? p[u][s] + __ldg(a.vit.start + k0 + u * SU + s) : kNegInf;
+            } else {
+                // first maximum over all unit ends: own units in ascending order, then across lanes (value, index)
+                float best = kNegInf;
+                int code = NONE;                         // NONE: every candidate is -inf (argmax -> state 0)
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const float c = om[u][SU - 1] + wend[u];
+                    if (c > best) {
+                        best = c;
+                        code = unit0 + u;
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oc = __shfl_xor_sync(0xffffffffu, code, o);
+                    if (ob > best || (ob == best && oc < code)) {
+                        best = ob;
+                        code = oc;
+                    }
+                }
+                uint16_t packed[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int unit = unit0 + u;
+                    const bool own = unit < P;
+                    // the self arc (source SU * unit) precedes the end of unit v in source order iff unit <= v
+                    const float self0 = om[u][0] + w_self[u][0];
+                    float b = best;
+                    int c = code;
+                    if (self0 > b || (self0 == b && self0 != kNegInf && unit <= c)) {
+                        b = self0;
+                        c = P;                           // P: the state itself
+                    }
+                    unsigned pk = (unsigned)c << 6;
+                    float nw[SU];
+                    nw[0] = p[u][0] + b;
+#pragma unroll
+                    for (int s = 1; s < SU; ++s) {
+                        const float prev = om[u][s - 1] + w_prev[u][s], self = om[u][s] + w_self[u][s];
+                        float bb = prev;
+                        unsigned cc = (prev == kNegInf) ? 2u : 1u;     // 1: previous state, 0: itself, 2: all -inf
+                        if (self > bb) {
+                            bb = self;
+                            cc = 0u;
+                        }
+                        pk |= cc << (2 * (s - 1));
+                        nw[s] = p[u][s] + bb;
+                    }
+#pragma unroll
+                    for (int s = 0; s < SU; ++s) om[u][s] = own ? nw[s] : kNegInf;
+                    packed[u] = (uint16_t)pk;
+                }
+                uint16_t* dst = bt_u + (size_t)t * BTLD + unit0;
+                if constexpr (U == 8) {
+                    uint4 v;
+                    v.x = packed[0] | ((unsigned)packed[1] << 16); v.y = packed[2] | ((unsigned)packed[3] << 16);
+                    v.z = packed[4] | ((unsigned)packed[5] << 16); v.w = packed[6] | ((unsigned)packed[7] << 16);
+                    *reinterpret_cast<uint4*>(dst) = v;
+                } else {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) dst[u] = packed[u];
+                }
+            }
+            float mx = kNegInf;
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int s = 0; s < SU; ++s) mx = fmaxf(mx, om[u][s]);
+            mx = warp_max(mx);
+            const float mxs = (mx == kNegInf) ? 0.f : mx;
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int s = 0; s < SU; ++s) om[u][s] -= mxs;
+        }
+        cp_async_wait<0>();
+        // last state: first maximal index of omega + final
+        float best = kNegInf;
+        int arg = 0x7fffffff;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int s = 0; s < SU; ++s) {
+                const int k = k0 + u * SU + s;
+                if (k < K) {
+                    const float v = om[u][s] + __ldg(a.vit_final + k);
+                    if (arg == 0x7fffffff || v > best) { best = v; arg = k; }
+                }
+            }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+        }
+        __threadfence_block();
+        __syncwarp();
+        // backtrack, 32 frames of back-pointers at a time through shared memory (the llh ring is free now)
+        int k = arg;
+        if (lane == 0) a.path[t0 + T - 1] = k;
+        for (int tb = T - 1; tb >= 1; tb -= 32) {
+            const int t = tb - lane;
+            if (t >= 1) {
+                const uint4* src = reinterpret_cast<const uint4*>(bt_u + (size_t)t * BTLD);
+                uint4* dst = reinterpret_cast<uint4*>(bt_s + lane * BTLD);
+#pragma unroll
+                for (int q = 0; q < BTLD / 8; ++q) dst[q] = src[q];
+            }
+            __syncwarp();
+            if (lane == 0) {
+                for (int i = 0; i < 32 && tb - i >= 1; ++i) {
+                    const unsigned w = bt_s[i * BTLD + k / SU];
+                    const int s = k % SU;
+                    int kp;
+                    if (s == 0) {
+                        const int c = (int)(w >> 6);
+                        kp = c < P ? c * SU + SU - 1 : (c == P ? k : 0);
+                    } else {
+                        const unsigned c = (w >> (2 * (s - 1))) & 3u;
+                        kp = c == 1u ? k - 1 : (c == 0u ? k : 0);
+                    }
+                    a.path[t0 + tb - i - 1] = kp;
+                    k = kp;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+template <int SU, int U>
+static int launch_vit_lrm(const VitArgs& a, const float* vlr, int n_utts, cudaStream_t st) {
+    constexpr int S = SU * U;
+    constexpr int WARP_FLOATS = (4 * 32 * S * 4 > 32 * 32 * U * 2) ? 4 * 32 * S : 32 * 32 * U / 2;
+    const size_t smem = sizeof(float) * (size_t)VLM_WARPS * WARP_FLOATS;
+    static bool attr_set = false;
+    if (!attr_set) {
+        BEER_CUDA_TRY(cudaFuncSetAttribute(hmm_viterbi_lrm_kernel<SU, U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem));
+        attr_set = true;
+    }
+    int blocks = (n_utts + VLM_WARPS - 1) / VLM_WARPS;
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    hmm_viterbi_lrm_kernel<SU, U><<<blocks, VLM_WARPS * 32, smem, st>>>(a, vlr);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
 template <int SU>
 static int launch_vit_lr(const VitArgs& a, int n_utts, cudaStream_t st) {
     const size_t smem = sizeof(float) * (size_t)FB_WARPS * (6 * 32 * SU + 512);
@@ -2734,9 +2970,35 @@ int beer_graph_plan_create(const float* init_log, const float* final_log, const 
         }
     }
 
+    std::vector<float> vlr;
+    int vlr_ok = 0;
+    if (lr_su) {
+        const int su = lr_su, P = K / su;
+        auto val = [&](int i, int j) {
+            const float w = trans_log[(size_t)i * K + j];
+            return (w > -INFINITY && w == w) ? w : -INFINITY;
+        };
+        vlr.assign((size_t)2 * K + P, -INFINITY);
+        for (int k = 0; k < K; ++k) {
+            vlr[k] = val(k, k);
+            if (k % su) vlr[K + k] = val(k - 1, k);
+        }
+        vlr_ok = 1;
+        for (int v = 0; v < P; ++v) {
+            const int e = v * su + su - 1;
+            const float w0 = val(e, 0);
+            for (int u = 1; u < P; ++u) {
+                const float wu = val(e, u * su);
+                if (memcmp(&wu, &w0, sizeof(float)) != 0) vlr_ok = 0;
+            }
+            vlr[(size_t)2 * K + v] = w0;
+        }
+    }
+
     BlobWriter w;
     ListOffsets of = write_lists(w, hf), ob = write_lists(w, hb), ov = write_lists(w, hv);
     size_t o_lrw = w.add(lr_w.data(), lr_w.size() * 4);
+    size_t o_vlr = w.add(vlr.data(), vlr.size() * 4);
     size_t o_map = w.add(pdf_map, (size_t)K * 4);
     size_t o_vfinal = w.add(vfinal.data(), (size_t)K * 4);
 
@@ -2755,6 +3017,8 @@ int beer_graph_plan_create(const float* init_log, const float* final_log, const 
     p->map = (const int*)(base + o_map);
     p->lr_su = lr_su; p->lr_u = lr_u;
     p->lr_w = lr_su ? (const float*)(base + o_lrw) : nullptr;
+    p->vlr = lr_su ? (const float*)(base + o_vlr) : nullptr;
+    p->vlr_ok = vlr_ok;
     p->vit_final = (const float*)(base + o_vfinal);
     p->map_identity = 1;
     for (int k = 0; k < K; ++k)
@@ -2927,6 +3191,21 @@ int beer_hmm_viterbi(const beer_graph_plan* plan, const float* pdf_llh, int64_t 
             if (plan->lr_su == 4 && ld_pdf % 4 == 0 && ((uintptr_t)pdf_llh & 15) == 0)
                 return launch_vit_lr<4>(a, n_utts, st);
             if (plan->lr_su == 3) return launch_vit_lr<3>(a, n_utts, st);
+        }
+    }
+    {
+        // more than 32 units of a uniform loop: U units per lane (back-pointers: 32 U uint16 per frame <= K of them)
+        const char* force = getenv("BEER_B200_SCAN");
+        const int su = plan->lr_su, P = su ? plan->K / su : 0;
+        if (su && plan->vlr_ok && plan->map_identity && P > 32 && plan->K == su * P && ((uintptr_t)workspace & 15) == 0 &&
+            (force == nullptr || force[0] == 'l')) {
+            const int u = (P + 31) / 32;
+            if (su == 4 && u <= 2) return launch_vit_lrm<4, 2>(a, plan->vlr, n_utts, st);
+            if (su == 4 && u <= 4) return launch_vit_lrm<4, 4>(a, plan->vlr, n_utts, st);
+            if (su == 4 && u <= 8) return launch_vit_lrm<4, 8>(a, plan->vlr, n_utts, st);
+            if (su == 3 && u <= 2) return launch_vit_lrm<3, 2>(a, plan->vlr, n_utts, st);
+            if (su == 3 && u <= 4) return launch_vit_lrm<3, 4>(a, plan->vlr, n_utts, st);
+            if (su == 3 && u <= 8) return launch_vit_lrm<3, 8>(a, plan->vlr, n_utts, st);
         }
     }
     switch (plan->S) {

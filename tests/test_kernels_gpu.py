@@ -345,10 +345,11 @@ def test_forward_backward_many_units_block_kernel(ops, P, S, lrc, monkeypatch):
     assert np.abs(np.exp2(lp.double().cpu().numpy()) - outs['best']['pdf_post']).max() <= 2e-6
 
 
-@pytest.mark.parametrize('P,SU', [(8, 4), (25, 4), (11, 3), (32, 4)])
+@pytest.mark.parametrize('P,SU', [(8, 4), (25, 4), (11, 3), (32, 4), (33, 4), (64, 4), (100, 3), (130, 3), (250, 4), (256, 4)])
 def test_viterbi_loop_kernel_equals_generic_kernel_with_ties(ops, P, SU, monkeypatch):
-    """The register-resident Viterbi kernel of aligned left-to-right loops against the generic one on llhs quantised
-    to quarter units (thousands of exact ties): identical paths, i.e. the same first-max tie-breaking
+    """The register-resident Viterbi kernels of aligned left-to-right loops (one unit per lane up to 32 units, several units
+    per lane with a shared first maximum over the unit ends beyond: 250 x 4 is BASELINE configs[2]) against the generic one
+    on llhs quantised to quarter units (thousands of exact ties): identical paths, i.e. the same first-max tie-breaking
     (graph.py:329-344), and identical to the oracle where fp32 and fp64 agree on the ties (uniform weights)."""
     gr, _, _ = O.phone_loop_graph(P, SU, self_loop=0.5)
     K = P * SU
