@@ -77,6 +77,8 @@ SIGNATURES = {
                                             C.c_int64, c_ptr, c_ptr, c_ptr]),
     'beer_mix16_log2_posteriors': (C.c_int, [c_ptr, C.c_int64, C.c_int, C.c_int64, c_ptr, C.c_int64, c_ptr]),
     'beer_mix16_set_trace': (None, [c_ptr]),
+    'beer_path_accumulate_mix': (C.c_int, [c_ptr, C.c_int64, C.c_int, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, c_ptr, C.c_float,
+                                           c_ptr, c_ptr, c_ptr]),
     'beer_emission_bwd_supported': (C.c_int, [C.c_int, C.c_int]),
     'beer_emission_bwd_image_bytes': (C.c_int64, [C.c_int, C.c_int]),
     'beer_emission_bwd_pack': (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_int64, c_ptr, c_ptr, c_ptr, c_ptr]),

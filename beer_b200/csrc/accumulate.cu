@@ -177,6 +177,117 @@ static int launch_kc(const KcArgs& a, int grid, cudaStream_t st) {
     return BEER_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Statistics of a mixture model along a STATE PATH (Viterbi training, hmm.py:42-58 with viterbi=True; one-hot pdf
+// posteriors x the responsibilities inside the chosen pdf, mixtureset.py:100-112): per frame only the C Gaussians of its
+// pdf carry weight, so nothing dense is formed.  One warp walks a block of consecutive frames, two dimensions per
+// lane; the C weight rows of the current pdf stay in registers while the path stays in it (a state lasts several
+// frames), the per-Gaussian sums of the run are flushed with fp64 atomics when the pdf changes.
+//   z_c = W_jc . [x, -x^2/2] + bias_jc,  r_c = exp(z_c - lse),  acc[jc] += scale r_c T(x),  frame = scale (lse + ref_t)
+// ---------------------------------------------------------------------------------------------
+constexpr int PATH_FRAMES = 64;      // frames per warp
+
+template <int C>
+__global__ void __launch_bounds__(256) path_mix_stats_kernel(const float* __restrict__ X, int64_t N, int D,
+                                                             const int32_t* __restrict__ pdf_ids,
+                                                             const float* __restrict__ W, const float* __restrict__ bias,
+                                                             const float* __restrict__ frame_ref, float scale,
+                                                             double* __restrict__ acc, float* __restrict__ frame_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t t_begin = gwarp * PATH_FRAMES, t_end = min(N, t_begin + PATH_FRAMES);
+    if (t_begin >= N) return;
+    const int d0 = lane, d1 = lane + 32, Q = 2 * D + 2;
+    const bool v0 = d0 < D, v1 = d1 < D;
+    float w1[C][2], w2[C][2], b[C];          // weight rows of the current pdf: linear / quadratic part, bias
+    float s1[C][2], s2[C][2], cnt[C];        // sums of the current run
+    int cur = -1;
+    auto flush = [&]() {
+        if (cur < 0) return;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            double* row = acc + (size_t)(cur * C + c) * Q;
+            if (cnt[c] != 0.f) {
+                if (v0) {
+                    atomicAdd(row + d0, (double)s1[c][0]);
+                    atomicAdd(row + D + d0, (double)s2[c][0]);
+                }
+                if (v1) {
+                    atomicAdd(row + d1, (double)s1[c][1]);
+                    atomicAdd(row + D + d1, (double)s2[c][1]);
+                }
+                if (lane == 0) {
+                    atomicAdd(row + 2 * D, -0.5 * (double)cnt[c]);
+                    atomicAdd(row + 2 * D + 1, 0.5 * (double)cnt[c]);
+                }
+            }
+        }
+    };
+    for (int64_t t = t_begin; t < t_end; ++t) {
+        const int k = __ldg(pdf_ids + t);
+        if (k != cur) {
+            flush();
+            cur = k;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float* wr = W + (size_t)(k * C + c) * 2 * D;
+                w1[c][0] = v0 ? __ldg(wr + d0) : 0.f;
+                w2[c][0] = v0 ? __ldg(wr + D + d0) : 0.f;
+                w1[c][1] = v1 ? __ldg(wr + d1) : 0.f;
+                w2[c][1] = v1 ? __ldg(wr + D + d1) : 0.f;
+                b[c] = __ldg(bias + k * C + c);
+                s1[c][0] = s1[c][1] = s2[c][0] = s2[c][1] = cnt[c] = 0.f;
+            }
+        }
+        const float x0 = v0 ? __ldg(X + (size_t)t * D + d0) : 0.f, x1 = v1 ? __ldg(X + (size_t)t * D + d1) : 0.f;
+        const float q0 = -0.5f * x0 * x0, q1 = -0.5f * x1 * x1;
+        float z[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) z[c] = fmaf(w1[c][0], x0, fmaf(w2[c][0], q0, fmaf(w1[c][1], x1, w2[c][1] * q1)));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int c = 0; c < C; ++c) z[c] += __shfl_xor_sync(0xffffffffu, z[c], o);
+        float m = kNegInf;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            z[c] += b[c];
+            m = fmaxf(m, z[c]);
+        }
+        float se = 0.f;
+        float e[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            e[c] = (m == kNegInf) ? 0.f : __expf(z[c] - m);
+            se += e[c];
+        }
+        const float inv = se > 0.f ? scale / se : 0.f;
+        if (lane == 0 && frame_out != nullptr)
+            frame_out[t] = scale * ((m == kNegInf ? kNegInf : m + __logf(se)) + (frame_ref ? __ldg(frame_ref + t) : 0.f));
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float w = e[c] * inv;
+            s1[c][0] = fmaf(w, x0, s1[c][0]);
+            s2[c][0] = fmaf(w, q0, s2[c][0]);
+            s1[c][1] = fmaf(w, x1, s1[c][1]);
+            s2[c][1] = fmaf(w, q1, s2[c][1]);
+            cnt[c] += w;
+        }
+    }
+    flush();
+}
+
+template <int C>
+static int launch_path_mix(const float* X, int64_t N, int D, const int32_t* pdf_ids, const float* W, const float* bias,
+                           const float* frame_ref, float scale, double* acc, float* frame_out, cudaStream_t st) {
+    const int64_t warps = (N + PATH_FRAMES - 1) / PATH_FRAMES;
+    const int blocks = (int)((warps + 7) / 8);
+    path_mix_stats_kernel<C><<<blocks, 256, 0, st>>>(X, N, D, pdf_ids, W, bias, frame_ref, scale, acc, frame_out);
+    BEER_LAUNCH_CHECK();
+    return BEER_OK;
+}
+
 }  // namespace beer
 
 using namespace beer;
@@ -224,6 +335,23 @@ int beer_mixture_weight_stats(const double* acc_normal, int M, int D, const int3
                                                                                     acc_weights);
     BEER_LAUNCH_CHECK();
     return BEER_OK;
+}
+
+int beer_path_accumulate_mix(const float* X, int64_t N, int D, const int32_t* pdf_ids, const float* W, const float* bias,
+                             int M, int C, const float* frame_ref, float scale, double* acc_normal, float* frame_exp_llh,
+                             void* stream) {
+    if (!X || !pdf_ids || !W || !bias || !acc_normal || N < 0 || M <= 0 || C <= 0 || M % C != 0) return BEER_ERR_ARG;
+    if (D <= 0 || D > 64) return BEER_ERR_UNSUPPORTED;
+    if (N == 0) return BEER_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (C) {
+        case 1: return launch_path_mix<1>(X, N, D, pdf_ids, W, bias, frame_ref, scale, acc_normal, frame_exp_llh, st);
+        case 2: return launch_path_mix<2>(X, N, D, pdf_ids, W, bias, frame_ref, scale, acc_normal, frame_exp_llh, st);
+        case 4: return launch_path_mix<4>(X, N, D, pdf_ids, W, bias, frame_ref, scale, acc_normal, frame_exp_llh, st);
+        case 8: return launch_path_mix<8>(X, N, D, pdf_ids, W, bias, frame_ref, scale, acc_normal, frame_exp_llh, st);
+        case 16: return launch_path_mix<16>(X, N, D, pdf_ids, W, bias, frame_ref, scale, acc_normal, frame_exp_llh, st);
+    }
+    return BEER_ERR_UNSUPPORTED;
 }
 
 }  // extern "C"

@@ -16,6 +16,7 @@ but as a handful of kernel launches over all utterances at once:
 
 Utterances shard over ranks (one process per GPU); the only exchange is the all-reduce.
 """
+import math
 import os
 
 import numpy as np
@@ -294,7 +295,8 @@ class VBEngine:
         # mixtures through the fp16-split kernels (forward-backward over one graph plan): no per-Gaussian llhs at all,
         # `pdf_llh` holds log2 values; the feature images of resident chunks are built once, here
         self.mix16 = None
-        if self.gmm or (emission.use16 and not self.viterbi and not self.chains):
+        # (Viterbi training of mixtures takes the fp16 emission kernel only; its statistics are sparse along the path)
+        if self.gmm or (emission.use16 and not self.chains and not (self.viterbi and emission.uniform_C == 1)):
             self.mix16 = ops.Mix16(M, D, emission.gmm_C if self.gmm else emission.uniform_C, self.dev)
             self._images = [None] * len(self._chunks)
             if not self.host_mode:
@@ -312,7 +314,10 @@ class VBEngine:
             self._frame_llh = torch.empty(nmax, device=self.dev, dtype=f32)
             # single-Gaussian pdfs in one statistics tile: the one-hot posteriors are never written, KC reads pdf ids
             self._path_kc = (not emission.has_mixtures) and ops.accumulate_path_supported(M, D)
-            self._pdf_ids = torch.zeros(nmax + 4, device=self.dev, dtype=i32) if self._path_kc else None
+            # mixtures: only the Gaussians of the frame's pdf carry weight -- sparse statistics along the path
+            self._path_mix = self.mix16 is not None and emission.uniform_C > 1 and D <= 64
+            self._pdf_ids = (torch.zeros(nmax + 4, device=self.dev, dtype=i32)
+                             if (self._path_kc or self._path_mix) else None)
         self.ws = torch.empty((ws_bytes + 3) // 4, device=self.dev, dtype=f32)
         self.frame_ref = torch.empty(nmax, device=self.dev, dtype=f32)
         self.utt_ell = torch.zeros(utts.n_utts, device=self.dev, dtype=f64)
@@ -400,6 +405,13 @@ class VBEngine:
                     self.mix16.gmm_posteriors(pdf_llh, fref, rel, scale=self.scale, out=pdf_post,
                                               out_utt_exp_llh=self.utt_ell[u0:u1])
                     self.gpu_launches += 1
+                elif self.viterbi and self._path_mix:
+                    # the emission kernel wrote log2 llhs: the scale of the Viterbi recursion carries ln 2
+                    path = ops.hmm_viterbi(plan, pdf_llh, rel, scale=self.scale * math.log(2.0), workspace=self.ws)
+                    if plan.info['map_identity']:
+                        self._pdf_ids[:nf].copy_(path)
+                    else:
+                        torch.index_select(self._pdf_map, 0, path, out=self._pdf_ids[:nf])
                 elif self.viterbi:
                     path = ops.hmm_viterbi(plan, pdf_llh, rel, scale=self.scale, workspace=self.ws)
                     _, frame = ops.path_posteriors(path, em.Kp, pdf_map=self._pdf_map, scale=self.scale,
@@ -427,7 +439,12 @@ class VBEngine:
                         self.mix16.log2_posteriors(pdf_post, out=pdf_post)
                         self.gpu_launches += 1
             with self._stage('KC_accumulate'):
-                if images is not None:
+                if self.viterbi and self._path_mix:
+                    frame = ops.path_accumulate_mix(X, self._pdf_ids[:nf], W, bias, self.mix16.C, self.acc, frame_ref=fref,
+                                                    scale=self.scale, out_frame=self._frame_llh[:nf])
+                    cs = torch.cat([torch.zeros(1, dtype=f64, device=self.dev), frame.double().cumsum(0)])
+                    self.utt_ell[u0:u1] = cs[rel[1:]] - cs[rel[:-1]]
+                elif images is not None:
                     self.mix16.accumulate(images, pdf_post, pdf_llh, self.acc, scale=self.scale)
                 elif self.viterbi and self._path_kc:
                     ops.accumulate_stats_path(X, self.acc, self._pdf_ids[:nf], scale=self.scale)

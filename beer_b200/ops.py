@@ -130,6 +130,19 @@ def emission_llh_tc(X, image, ref, M, C, want_comp=False, out=None, out_comp=Non
     return pdf_llh, comp, fref
 
 
+def path_accumulate_mix(X, pdf_ids, W, bias, C, acc, frame_ref=None, scale=1.0, out_frame=None, want_frame=True):
+    """Sparse statistics of a mixture model along a state path (beer_path_accumulate_mix): acc [M, 2D+2] fp64 +=,
+    returns the per-frame expected llh [N] (scale * (log-sum-exp over the components of the frame's pdf + frame_ref))."""
+    lib = require_cuda()
+    N, D = X.shape
+    M = W.shape[0]
+    frame = out_frame if out_frame is not None else (torch.empty(N, device=X.device, dtype=f32) if want_frame else None)
+    _lib.check(lib.beer_path_accumulate_mix(_p(X, f32), N, D, _p(pdf_ids, i32), _p(W, f32), _p(bias, f32), M, int(C),
+                                            _p(frame_ref, f32, True), float(scale), _p(acc, f64), _p(frame, f32, True),
+                                            _stream()), 'beer_path_accumulate_mix')
+    return frame
+
+
 def emission_bwd_supported(M, D):
     return bool(require_cuda().beer_emission_bwd_supported(int(M), int(D)))
 

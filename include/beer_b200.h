@@ -108,6 +108,15 @@ BEER_API int beer_emission_llh_tc(const float* X, int64_t N, int D, const float*
                                   int C, float* pdf_llh, int64_t ld_pdf, float* comp_llh, float* frame_ref,
                                   void* stream);
 
+/* Statistics of a mixture model along a state path (Viterbi training: hmm.py:42-58 with viterbi=True gives one-hot pdf
+ * posteriors; the responsibilities inside the chosen pdf are those of mixtureset.py:100-112), sparse: per frame only the
+ * C Gaussians of pdf_ids[t] are evaluated (from W / bias of beer_emission_prepare, fp32 SIMT) and accumulated:
+ *   acc_normal [M, 2D+2] (fp64) += scale r_tc T(x_t);  frame_exp_llh [N] (optional) = scale (log sum_c exp z_tc + frame_ref[t]).
+ * C in {1, 2, 4, 8, 16}, D <= 64. */
+BEER_API int beer_path_accumulate_mix(const float* X, int64_t N, int D, const int32_t* pdf_ids, const float* W,
+                                      const float* bias, int M, int C, const float* frame_ref, float scale,
+                                      double* acc_normal, float* frame_exp_llh, void* stream);
+
 /* KA backward: gradient of sum_t grad_out[t] * sum_k pdf_post[t,k] llh_k(x_t) w.r.t. the frames, posteriors held fixed
  * (beer/models/hmm.py:79-87 and mixtureset.py:85-98 run the inference on detached llhs; beer/models/vae.py:63-89 is the
  * caller that back-propagates through prior.expected_log_likelihood):

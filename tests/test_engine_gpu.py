@@ -152,14 +152,16 @@ def test_engine_learns_unit_weights_like_phoneloop_model():
     np.testing.assert_allclose(tb[fin], ta[fin], rtol=1e-5, atol=1e-6)
 
 
-@pytest.mark.parametrize('C,chunk,scale', [(1, None, 1.0), (2, 150, 0.8)])
-def test_viterbi_training_matches_oracle(C, chunk, scale):
+@pytest.mark.parametrize('C,chunk,scale,P,S,D', [(1, None, 1.0, 5, 3, 8), (2, 150, 0.8, 5, 3, 8), (4, 150, 0.8, 12, 4, 20),
+                                                 (8, None, 1.0, 40, 4, 40), (8, 200, 1.0, 250, 4, 40)])
+def test_viterbi_training_matches_oracle(C, chunk, scale, P, S, D):
     """Viterbi training in the batched engine (hmm.py:42-58 with viterbi=True): one-hot posteriors of the best path,
-    three VB iterations against the oracle."""
+    three VB iterations against the oracle.  Mixtures of 4 / 8 Gaussians at D = 20 / 40 take the fp16 emission kernel
+    (log2 llhs into the Viterbi recursion) and the sparse statistics along the path; 40 and 250 units (BASELINE
+    configs[2]) run the several-units-per-lane Viterbi kernel."""
     from beer_b200 import ops, synthetic
     from beer_b200.engine import EmissionParams, Utterances, VBEngine, WeightGroup
     dev = torch.device('cuda', 0)
-    P, S, D = 5, 3, 8
     K, M = P * S, P * S * C
     lens = [90, 33, 140, 61]
     graph, _, _ = synthetic.phone_loop_graph(P, S)
@@ -181,6 +183,7 @@ def test_viterbi_training_matches_oracle(C, chunk, scale):
     N = sum(lens)
     eng = VBEngine(em, plan, Utterances(X, lens), datasize=float(N), chunk_frames=chunk, distributed=False,
                    scale=scale, viterbi=True)
+    assert bool(eng._path_mix) == (C >= 4)
     ng_prior, ng_post = _host(prior), _host(post)
     og = (graph.init_log_probs.double().numpy(), graph.final_log_probs.double().numpy(),
           graph.trans_log_probs.double().numpy(), graph.pdf_id_mapping)
