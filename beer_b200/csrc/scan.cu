@@ -2535,53 +2535,62 @@ __global__ void __launch_bounds__(FB_WARPS * 32) hmm_viterbi_lr_kernel(VitArgs a
 
 // ---------------------------------------------------------------------------
 // The same recursion for MORE than 32 units (BASELINE configs[2]: 250 units x 4 states): one warp per utterance, U units
-// of SU states per lane, everything in registers.  Needs a loop whose unit starts all see the same weight from a given
+// of SU states per lane, everything in registers.  UNI: a loop whose unit starts all see the same weight from a given
 // unit end (plan->vlr_ok: the uniform phone loops of mkphoneloopgraph.py; bitwise equal columns of ln A[ends, starts]):
 // the first maximum over the P unit ends -- ascending source order, strict > -- is then ONE (value, index) pair per
 // frame, found with a lexicographic butterfly, and every start only compares it with its own self loop (which precedes
-// the end of unit v in source order iff its unit index <= v).  Back-pointers: one uint16 per unit and frame
+// the end of unit v in source order iff its unit index <= v).  Learned unit weights (!UNI): see the comment at `vend`.  Back-pointers: one uint16 per unit and frame
 // (2 bits per inner state, 10 bits for the unit start), the backtrack stages 32 frames of them in shared memory.
 // The generic kernel walks 250 candidates for each of the 250 starts from shared memory: 340 ms per cfg3 batch
 // against ~2 ms here (same arithmetic, same tie-breaking: tests/test_kernels_gpu.py compares the paths exactly).
 // ---------------------------------------------------------------------------
 constexpr int VLM_WARPS = 4;
 
-template <int SU, int U>
-__global__ void __launch_bounds__(VLM_WARPS * 32) hmm_viterbi_lrm_kernel(VitArgs a, const float* __restrict__ vlr) {
+template <int SU, int U, bool UNI>
+__global__ void __launch_bounds__(VLM_WARPS * 32, 3) hmm_viterbi_lrm_kernel(VitArgs a, const float* __restrict__ vlr) {
     constexpr int S = SU * U, PF = 4, ROW = 32 * S, BTLD = 32 * U;
     constexpr int WARP_FLOATS = (PF * ROW * 4 > 32 * BTLD * 2) ? PF * ROW : 32 * BTLD / 2;
-    constexpr bool VEC = (S % 4) == 0;
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* ring = smem + (size_t)warp * WARP_FLOATS;                  // [PF][32 * S] llh rows
+    float* ring = smem + (size_t)warp * WARP_FLOATS;                  // [PF][32 * S] llh rows, in state order
     uint16_t* bt_s = reinterpret_cast<uint16_t*>(ring);               // backtrack: [32 frames][32 * U] (after the sweep)
     const int K = a.K, P = K / SU, NONE = P + 1;
     const int gwarp = blockIdx.x * VLM_WARPS + warp, nwarps = gridDim.x * VLM_WARPS;
-    const int unit0 = lane * U, k0 = unit0 * SU;
-    const bool vec_ok = VEC && (a.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.pl) & 15) == 0) && (K % 4 == 0);
+    // lane l owns the units l, l + 32, ..., l + 32 (U - 1): consecutive lanes read consecutive unit blocks of a row
+    // (a blocked assignment -- 32 consecutive floats per lane -- made every shared-memory read a 32-way bank conflict:
+    // 718 conflict cycles per frame, profiles/r02_viterbi.md)
+    const bool vec_ok = (SU == 4) && (a.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.pl) & 15) == 0);
 
+    // UNI: ln A[end v, any start] of this lane's unit ends.  Otherwise (learned unit weights, phoneloop.py:53-65): the
+    // factored weight lv[v] of this lane's unit ends, used only to RANK the ends; the candidates that can still be a
+    // first maximum for some start (within the factorisation error of the best one) are then compared exactly, per
+    // start, with the dense weights vend[v][u], in ascending order of v.
+    const float* vend = vlr + 2 * K + 2 * P;
     float w_self[U][SU], w_prev[U][SU], wend[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        const bool own = unit0 + u < P;
-        wend[u] = own ? __ldg(vlr + 2 * K + unit0 + u) : kNegInf;
+        const int unit = lane + 32 * u;
+        const bool own = unit < P;
+        wend[u] = own ? __ldg(vlr + 2 * K + (UNI ? 0 : P) + unit) : kNegInf;
 #pragma unroll
         for (int s = 0; s < SU; ++s) {
-            const int k = k0 + u * SU + s;
+            const int k = unit * SU + s;
             w_self[u][s] = own ? __ldg(vlr + k) : kNegInf;
             w_prev[u][s] = (own && s > 0) ? __ldg(vlr + K + k) : kNegInf;
         }
     }
 
     auto prefetch = [&](float* slot, const float* row) {
-        if (vec_ok) {
 #pragma unroll
-            for (int v = 0; v < S / 4; ++v)
-                if (k0 + 4 * v < K) cp_async16(slot + lane * S + 4 * v, row + k0 + 4 * v);
-        } else {
+        for (int u = 0; u < U; ++u) {
+            const int unit = lane + 32 * u;
+            if (unit >= P) continue;
+            if (vec_ok) {
+                cp_async16(slot + unit * SU, row + unit * SU);
+            } else {
 #pragma unroll
-            for (int j = 0; j < S; ++j)
-                if (k0 + j < K) cp_async4(slot + lane * S + j, row + k0 + j);
+                for (int j = 0; j < SU; ++j) cp_async4(slot + unit * SU + j, row + unit * SU + j);
+            }
         }
     };
 
@@ -2602,10 +2611,19 @@ __global__ void __launch_bounds__(VLM_WARPS * 32) hmm_viterbi_lrm_kernel(VitArgs
             cp_async_wait<PF - 1>();
             float p[U][SU];
 #pragma unroll
-            for (int u = 0; u < U; ++u)
+            for (int u = 0; u < U; ++u) {
+                const int unit = lane + 32 * u;
+                if constexpr (SU == 4) {
+                    const float4 v = (unit < P) ? *reinterpret_cast<const float4*>(ring + slot * ROW + unit * 4)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                    p[u][0] = v.x; p[u][1] = v.y; p[u][2] = v.z; p[u][3] = v.w;
+                } else {
 #pragma unroll
-                for (int s = 0; s < SU; ++s)
-                    p[u][s] = (unit0 + u < P) ? a.scale * ring[slot * ROW + lane * S + u * SU + s] : kNegInf;
+                    for (int s = 0; s < SU; ++s) p[u][s] = (unit < P) ? ring[slot * ROW + unit * SU + s] : 0.f;
+                }
+#pragma unroll
+                for (int s = 0; s < SU; ++s) p[u][s] = (unit < P) ? a.scale * p[u][s] : kNegInf;
+            }
             if (t + PF < T) prefetch(ring + slot * ROW, pl_u + (size_t)(t + PF) * a.ld);
             cp_async_commit();
             slot = (slot + 1 == PF) ? 0 : slot + 1;
@@ -2613,38 +2631,75 @@ __global__ void __launch_bounds__(VLM_WARPS * 32) hmm_viterbi_lrm_kernel(VitArgs
 #pragma unroll
                 for (int u = 0; u < U; ++u)
 #pragma unroll
-                    for (int s = 0; s < SU; ++s)
-                        om[u][s] = (unit0 + u < P) ? p[u][s] + __ldg(a.vit.start + k0 + u * SU + s) : kNegInf;
+                    for (int s = 0; s < SU; ++s) {
+                        const int unit = lane + 32 * u;
+                        om[u][s] = (unit < P) ? p[u][s] + __ldg(a.vit.start + unit * SU + s) : kNegInf;
+                    }
             } else {
                 // first maximum over all unit ends: own units in ascending order, then across lanes (value, index)
                 float best = kNegInf;
                 int code = NONE;                         // NONE: every candidate is -inf (argmax -> state 0)
+                float bests[U];
+                int codes[U];
+                if constexpr (UNI) {
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const float c = om[u][SU - 1] + wend[u];
-                    if (c > best) {
-                        best = c;
-                        code = unit0 + u;
+                    for (int u = 0; u < U; ++u) {
+                        const float c = om[u][SU - 1] + wend[u];
+                        if (c > best) {
+                            best = c;
+                            code = lane + 32 * u;
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                        const int oc = __shfl_xor_sync(0xffffffffu, code, o);
+                        if (ob > best || (ob == best && oc < code)) {
+                            best = ob;
+                            code = oc;
+                        }
+                    }
+                } else {
+                    float sc[U], m = kNegInf;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        sc[u] = om[u][SU - 1] + wend[u];
+                        m = fmaxf(m, sc[u]);
+                        bests[u] = kNegInf;
+                        codes[u] = NONE;
+                    }
+                    m = warp_max(m);
+                    // |ln A - (lv + lw)| <= 4e-6 (plan), three roundings of values of magnitude <= |m| + |weights|
+                    const float thr = m - (1.2e-5f + 1e-6f * fabsf(m));
+#pragma unroll
+                    for (int uu = 0; uu < U; ++uu) {     // ascending v = src + 32 uu
+                        unsigned lanes = __ballot_sync(0xffffffffu, sc[uu] >= thr && sc[uu] > kNegInf);
+                        while (lanes != 0u) {
+                            const int src = __ffs(lanes) - 1;
+                            lanes &= lanes - 1;
+                            const float e = __shfl_sync(0xffffffffu, om[uu][SU - 1], src);
+                            const int v = src + 32 * uu;
+                            const float* row = vend + (size_t)v * P;
+#pragma unroll
+                            for (int u = 0; u < U; ++u) {
+                                const int unit = lane + 32 * u;
+                                const float c = e + ((unit < P) ? __ldg(row + unit) : kNegInf);
+                                if (c > bests[u]) {
+                                    bests[u] = c;
+                                    codes[u] = v;
+                                }
+                            }
+                        }
                     }
                 }
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                    const int oc = __shfl_xor_sync(0xffffffffu, code, o);
-                    if (ob > best || (ob == best && oc < code)) {
-                        best = ob;
-                        code = oc;
-                    }
-                }
-                uint16_t packed[U];
-#pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const int unit = unit0 + u;
+                    const int unit = lane + 32 * u;
                     const bool own = unit < P;
                     // the self arc (source SU * unit) precedes the end of unit v in source order iff unit <= v
                     const float self0 = om[u][0] + w_self[u][0];
-                    float b = best;
-                    int c = code;
+                    float b = UNI ? best : bests[u];
+                    int c = UNI ? code : codes[u];
                     if (self0 > b || (self0 == b && self0 != kNegInf && unit <= c)) {
                         b = self0;
                         c = P;                           // P: the state itself
@@ -2666,25 +2721,21 @@ __global__ void __launch_bounds__(VLM_WARPS * 32) hmm_viterbi_lrm_kernel(VitArgs
                     }
 #pragma unroll
                     for (int s = 0; s < SU; ++s) om[u][s] = own ? nw[s] : kNegInf;
-                    packed[u] = (uint16_t)pk;
-                }
-                uint16_t* dst = bt_u + (size_t)t * BTLD + unit0;
-                if constexpr (U == 8) {
-                    uint4 v;
-                    v.x = packed[0] | ((unsigned)packed[1] << 16); v.y = packed[2] | ((unsigned)packed[3] << 16);
-                    v.z = packed[4] | ((unsigned)packed[5] << 16); v.w = packed[6] | ((unsigned)packed[7] << 16);
-                    *reinterpret_cast<uint4*>(dst) = v;
-                } else {
-#pragma unroll
-                    for (int u = 0; u < U; ++u) dst[u] = packed[u];
+                    bt_u[(size_t)t * BTLD + unit] = (uint16_t)pk;
                 }
             }
-            float mx = kNegInf;
+            float mxu[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u)
+            for (int u = 0; u < U; ++u) {
+                mxu[u] = om[u][0];
 #pragma unroll
-                for (int s = 0; s < SU; ++s) mx = fmaxf(mx, om[u][s]);
-            mx = warp_max(mx);
+                for (int s = 1; s < SU; ++s) mxu[u] = fmaxf(mxu[u], om[u][s]);
+            }
+#pragma unroll
+            for (int w = 1; w < U; w *= 2)
+#pragma unroll
+                for (int u = 0; u + w < U; u += 2 * w) mxu[u] = fmaxf(mxu[u], mxu[u + w]);
+            const float mx = warp_max(mxu[0]);
             const float mxs = (mx == kNegInf) ? 0.f : mx;
 #pragma unroll
             for (int u = 0; u < U; ++u)
@@ -2699,7 +2750,7 @@ __global__ void __launch_bounds__(VLM_WARPS * 32) hmm_viterbi_lrm_kernel(VitArgs
         for (int u = 0; u < U; ++u)
 #pragma unroll
             for (int s = 0; s < SU; ++s) {
-                const int k = k0 + u * SU + s;
+                const int k = (lane + 32 * u) * SU + s;
                 if (k < K) {
                     const float v = om[u][s] + __ldg(a.vit_final + k);
                     if (arg == 0x7fffffff || v > best) { best = v; arg = k; }
@@ -2717,12 +2768,12 @@ __global__ void __launch_bounds__(VLM_WARPS * 32) hmm_viterbi_lrm_kernel(VitArgs
         int k = arg;
         if (lane == 0) a.path[t0 + T - 1] = k;
         for (int tb = T - 1; tb >= 1; tb -= 32) {
-            const int t = tb - lane;
-            if (t >= 1) {
-                const uint4* src = reinterpret_cast<const uint4*>(bt_u + (size_t)t * BTLD);
-                uint4* dst = reinterpret_cast<uint4*>(bt_s + lane * BTLD);
-#pragma unroll
-                for (int q = 0; q < BTLD / 8; ++q) dst[q] = src[q];
+            // row i of the stage = frame tb - i, copied by the whole warp 16 bytes per lane at a time
+            for (int e = lane; e < 32 * (BTLD / 8); e += 32) {
+                const int i = e / (BTLD / 8), q = e % (BTLD / 8);
+                if (tb - i >= 1)
+                    reinterpret_cast<uint4*>(bt_s + i * BTLD)[q] =
+                        reinterpret_cast<const uint4*>(bt_u + (size_t)(tb - i) * BTLD)[q];
             }
             __syncwarp();
             if (lane == 0) {
@@ -2746,20 +2797,20 @@ __global__ void __launch_bounds__(VLM_WARPS * 32) hmm_viterbi_lrm_kernel(VitArgs
     }
 }
 
-template <int SU, int U>
+template <int SU, int U, bool UNI>
 static int launch_vit_lrm(const VitArgs& a, const float* vlr, int n_utts, cudaStream_t st) {
     constexpr int S = SU * U;
     constexpr int WARP_FLOATS = (4 * 32 * S * 4 > 32 * 32 * U * 2) ? 4 * 32 * S : 32 * 32 * U / 2;
     const size_t smem = sizeof(float) * (size_t)VLM_WARPS * WARP_FLOATS;
     static bool attr_set = false;
     if (!attr_set) {
-        BEER_CUDA_TRY(cudaFuncSetAttribute(hmm_viterbi_lrm_kernel<SU, U>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        BEER_CUDA_TRY(cudaFuncSetAttribute(hmm_viterbi_lrm_kernel<SU, U, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem));
         attr_set = true;
     }
     int blocks = (n_utts + VLM_WARPS - 1) / VLM_WARPS;
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-    hmm_viterbi_lrm_kernel<SU, U><<<blocks, VLM_WARPS * 32, smem, st>>>(a, vlr);
+    hmm_viterbi_lrm_kernel<SU, U, UNI><<<blocks, VLM_WARPS * 32, smem, st>>>(a, vlr);
     BEER_LAUNCH_CHECK();
     return BEER_OK;
 }
@@ -2978,7 +3029,7 @@ int beer_graph_plan_create(const float* init_log, const float* final_log, const 
             const float w = trans_log[(size_t)i * K + j];
             return (w > -INFINITY && w == w) ? w : -INFINITY;
         };
-        vlr.assign((size_t)2 * K + P, -INFINITY);
+        vlr.assign((size_t)2 * K + 2 * P + (size_t)P * P, -INFINITY);
         for (int k = 0; k < K; ++k) {
             vlr[k] = val(k, k);
             if (k % su) vlr[K + k] = val(k - 1, k);
@@ -2987,12 +3038,16 @@ int beer_graph_plan_create(const float* init_log, const float* final_log, const 
         for (int v = 0; v < P; ++v) {
             const int e = v * su + su - 1;
             const float w0 = val(e, 0);
-            for (int u = 1; u < P; ++u) {
+            for (int u = 0; u < P; ++u) {
                 const float wu = val(e, u * su);
                 if (memcmp(&wu, &w0, sizeof(float)) != 0) vlr_ok = 0;
+                vlr[(size_t)2 * K + 2 * P + (size_t)v * P + u] = wu;       // dense ln A[end v, start u]
             }
             vlr[(size_t)2 * K + v] = w0;
         }
+        // the factored weight of every unit end (ln A[end v, start u] = lv[v] + lw[u] to 4e-6): ranks the ends
+        const Junction& jn = junctions[0];
+        for (size_t r = 0; r < jn.rows.size(); ++r) vlr[(size_t)2 * K + P + jn.rows[r] / su] = (float)jn.lv[r];
     }
 
     BlobWriter w;
@@ -3197,15 +3252,17 @@ int beer_hmm_viterbi(const beer_graph_plan* plan, const float* pdf_llh, int64_t 
         // more than 32 units of a uniform loop: U units per lane (back-pointers: 32 U uint16 per frame <= K of them)
         const char* force = getenv("BEER_B200_SCAN");
         const int su = plan->lr_su, P = su ? plan->K / su : 0;
-        if (su && plan->vlr_ok && plan->map_identity && P > 32 && plan->K == su * P && ((uintptr_t)workspace & 15) == 0 &&
+        if (su && plan->map_identity && P > 32 && plan->K == su * P && ((uintptr_t)workspace & 15) == 0 &&
             (force == nullptr || force[0] == 'l')) {
             const int u = (P + 31) / 32;
-            if (su == 4 && u <= 2) return launch_vit_lrm<4, 2>(a, plan->vlr, n_utts, st);
-            if (su == 4 && u <= 4) return launch_vit_lrm<4, 4>(a, plan->vlr, n_utts, st);
-            if (su == 4 && u <= 8) return launch_vit_lrm<4, 8>(a, plan->vlr, n_utts, st);
-            if (su == 3 && u <= 2) return launch_vit_lrm<3, 2>(a, plan->vlr, n_utts, st);
-            if (su == 3 && u <= 4) return launch_vit_lrm<3, 4>(a, plan->vlr, n_utts, st);
-            if (su == 3 && u <= 8) return launch_vit_lrm<3, 8>(a, plan->vlr, n_utts, st);
+            const bool uni = plan->vlr_ok != 0 && getenv("BEER_B200_VIT_DENSE") == nullptr;
+#define BEER_VLM_CASE(su_, u_)                                                                   \
+    if (su == su_ && u <= u_)                                                                    \
+        return uni ? launch_vit_lrm<su_, u_, true>(a, plan->vlr, n_utts, st)                     \
+                   : launch_vit_lrm<su_, u_, false>(a, plan->vlr, n_utts, st);
+            BEER_VLM_CASE(4, 2) BEER_VLM_CASE(4, 4) BEER_VLM_CASE(4, 8)
+            BEER_VLM_CASE(3, 2) BEER_VLM_CASE(3, 4) BEER_VLM_CASE(3, 8)
+#undef BEER_VLM_CASE
         }
     }
     switch (plan->S) {

@@ -371,6 +371,27 @@ def test_viterbi_loop_kernel_equals_generic_kernel_with_ties(ops, P, SU, monkeyp
         a, b = off[u], off[u + 1]
         want = O.best_path(llh[a:b].astype(np.float32).astype(np.float64), *[np.asarray(g, dtype=np.float64) for g in gr[:3]])
         np.testing.assert_array_equal(fast[a:b], want)
+    if P > 32:
+        # the same loop through the variant for learned unit weights (candidate ends ranked by the factored weights,
+        # compared exactly with the dense ones) ...
+        monkeypatch.setenv('BEER_B200_VIT_DENSE', '1')
+        np.testing.assert_array_equal(ops.hmm_viterbi(plan, x, utt).cpu().numpy(), slow)
+        monkeypatch.delenv('BEER_B200_VIT_DENSE', raising=False)
+        # ... and with unit weights as PhoneLoop writes them: ln A[end, start u] = ln(1 - loop) + E[ln w_u] in fp32
+        # (phoneloop.py:53-65); weights close to each other so that the rounding of the sums decides near-ties
+        init, final, trans = [np.array(g, dtype=np.float32) for g in gr[:3]]
+        logw = np.log(rng.dirichlet(np.full(P, 50.0))).astype(np.float32)
+        for v in range(P):
+            e = v * SU + SU - 1
+            stay = np.float32(np.log1p(-np.exp(np.float32(trans[e, e]))))
+            trans[e, np.arange(P) * SU] = stay + logw
+        plan_w = ops.GraphPlan(init, final, trans, gr[3])
+        fast_w = ops.hmm_viterbi(plan_w, x, utt).cpu().numpy()
+        monkeypatch.setenv('BEER_B200_SCAN', 'generic')
+        slow_w = ops.hmm_viterbi(plan_w, x, utt).cpu().numpy()
+        monkeypatch.delenv('BEER_B200_SCAN', raising=False)
+        np.testing.assert_array_equal(fast_w, slow_w)
+        assert (fast_w != fast).any()
 
 
 @pytest.mark.parametrize('N,M,D,C,scale', [(300, 200, 40, 1, 1.0), (129, 64, 20, 1, 0.5), (1000, 1000, 40, 8, 3.0),
