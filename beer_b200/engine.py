@@ -256,8 +256,6 @@ class VBEngine:
         if self.chains and (unit_weights is not None or plan.n_utts != utts.n_utts or self.viterbi):
             raise ValueError('a ChainBatch needs one chain per utterance of the shard, runs forward-backward and '
                              'trains no unit weights (phoneloop.py:98-100)')
-        if self.viterbi and unit_weights is not None:
-            raise ValueError('Viterbi training of the unit weights is only available through the model API')
         P = plan.n_units if unit_weights is not None else 0
         if unit_weights is not None and P == 0:
             raise ValueError('unit weights need an aligned left-to-right phone loop (see beer_hmm_forward_backward_units)')
@@ -408,12 +406,14 @@ class VBEngine:
                 elif self.viterbi and self._path_mix:
                     # the emission kernel wrote log2 llhs: the scale of the Viterbi recursion carries ln 2
                     path = ops.hmm_viterbi(plan, pdf_llh, rel, scale=self.scale * math.log(2.0), workspace=self.ws)
+                    self._path_unit_counts(path, rel)
                     if plan.info['map_identity']:
                         self._pdf_ids[:nf].copy_(path)
                     else:
                         torch.index_select(self._pdf_map, 0, path, out=self._pdf_ids[:nf])
                 elif self.viterbi:
                     path = ops.hmm_viterbi(plan, pdf_llh, rel, scale=self.scale, workspace=self.ws)
+                    self._path_unit_counts(path, rel)
                     _, frame = ops.path_posteriors(path, em.Kp, pdf_map=self._pdf_map, scale=self.scale,
                                                    pdf_llh=pdf_llh, frame_ref=fref, want_post=not self._path_kc,
                                                    out_post=None if self._path_kc else pdf_post,
@@ -462,6 +462,22 @@ class VBEngine:
         self.extras[3] = self.utt_ell.sum()
         # sum_u ell_u / T_u; multiplied by the global datasize after the reduction
         self.extras[0] = (self.utt_ell * self.inv_len).sum()
+
+    def _path_unit_counts(self, path, rel):
+        """Unit counts of a state path: its one-hot transition posteriors summed over the ends x starts block, plus the
+        first frame of every utterance (hmm.py:49-54, phoneloop.py:83-101).  Index arithmetic on [N] integers."""
+        if self.unit_counts is None:
+            return
+        su = self.plan.n_states // self.unit_counts.numel()
+        p = path.long()
+        n = p.numel()
+        first = torch.zeros(n + 1, dtype=torch.bool, device=self.dev)
+        first[rel[:-1]] = True            # an empty utterance marks the next one's first frame (or the slot past the end)
+        is_start = (p % su) == 0
+        after_end = torch.zeros(n, dtype=torch.bool, device=self.dev)
+        after_end[1:] = (p[:-1] % su) == su - 1
+        hit = is_start & (after_end | first[:n])
+        self.unit_counts.index_add_(0, p // su, hit.to(f64))
 
     def _next_copy(self, chunk):
         """Issue the copy of `chunk` into the staging buffer whose turn it is; returns the buffer."""

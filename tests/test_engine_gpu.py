@@ -95,14 +95,17 @@ def test_smoke_entry():
     __graft_entry__.smoke()
 
 
-def test_engine_learns_unit_weights_like_phoneloop_model():
+@pytest.mark.parametrize('P,viterbi', [(7, False), (7, True), (40, True)])
+def test_engine_learns_unit_weights_like_phoneloop_model(P, viterbi):
     """Batched engine with learned unit weights == the PhoneLoop model driven utterance by utterance through
     evidence_lower_bound (itself checked against the reference golden in test_api_gpu.py): same ELBOs, same
-    unit-weight posteriors, same rewritten transitions after 3 iterations."""
+    unit-weight posteriors, same rewritten transitions after 3 iterations.  viterbi: the unit counts are the one-hot
+    transition posteriors of the best path (hmm.py:49-54, phoneloop.py:83-101); 40 units = the several-units-per-lane
+    Viterbi kernel with learned (non-uniform) unit weights from the second iteration on."""
     import beer_b200 as beer
     from beer_b200 import ops, synthetic
     dev = torch.device('cuda', 0)
-    P, S, D = 7, 4, 40
+    S, D = 4, 40
     K = P * S
     lens = [90, 41, 120, 64]
     N = sum(lens)
@@ -130,7 +133,7 @@ def test_engine_learns_unit_weights_like_phoneloop_model():
         optim.init_step()
         elbo = beer.evidence_lower_bound(datasize=N)
         for X in utts:
-            elbo += beer.evidence_lower_bound(pl, X, datasize=N)
+            elbo += beer.evidence_lower_bound(pl, X, datasize=N, viterbi=viterbi)
         elbo.backward()
         want.append(float(elbo))
         optim.step()
@@ -142,7 +145,7 @@ def test_engine_learns_unit_weights_like_phoneloop_model():
     units.rewrite_graph()
     em = beer.EmissionParams(tuple(t.clone() for t in prior), tuple(t.clone() for t in post))
     eng = beer.VBEngine(em, gb.plan(n_pdfs=K), beer.Utterances(torch.cat(utts), lens), datasize=float(N),
-                        distributed=False, unit_weights=units)
+                        distributed=False, unit_weights=units, viterbi=viterbi)
     got = [float(eng.step().item()) for _ in range(3)]
     np.testing.assert_allclose(got, want, rtol=2e-6)
     np.testing.assert_allclose(units.post.cpu().numpy(), pl.categorical.weights.posterior.params.concentrations.cpu().numpy(),
