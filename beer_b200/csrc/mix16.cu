@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a, con
     const int n_stages = a.n_chunks > 1 ? KA_STAGES : 1, n_k12 = a.n_chunks > 1 ? K12_RING : 1;
     float2* s_k12 = reinterpret_cast<float2*>(Bs + n_stages * b_stage);      // [K12_RING][NB] (k1, k2)
     KaBarriers* bars = reinterpret_cast<KaBarriers*>(s_k12 + n_k12 * a.NB);
-    // staged output: [4 lane quarters][3 buffers][32 frames][NB / C pdfs] (128-byte aligned)
+    // staged output: [4 lane quarters][2 epilogue groups][2 buffers][32 frames][NB / C pdfs] (128-byte aligned)
     float* s_out = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(bars + 1) + 127) & ~uintptr_t(127));
     const int PC = a.NB / C;
 
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a, con
             mbar_init(&bars->a_full[i], 128);
             mbar_init(&bars->a_empty[i], 1);
             mbar_init(&bars->t_full[i], 1);
-            mbar_init(&bars->t_empty[i], KA_WORKERS);
+            mbar_init(&bars->t_empty[i], KA_WORKERS / 2);       // one epilogue group per accumulator buffer
         }
         for (int i = 0; i < KA_STAGES; ++i) {
             mbar_init(&bars->b_full[i], 1);
@@ -339,12 +339,16 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a, con
             }
         }
     } else {
-        // epilogue: TMEM lane = frame row 32 (warp % 4) + lane; the four warps of a lane quarter take a contiguous
-        // quarter of the chunk's units (whole pdfs) each
-        const int r = (warp & 3) * 32 + lane, cq = warp >> 2;
+        // epilogue: TMEM lane = frame row 32 (warp % 4) + lane.  Two groups of eight warps take alternate chunks
+        // (= alternate accumulator buffers): while one group sits in its barrier / tensor-memory / store latencies the
+        // other one keeps the special-function unit busy (one exp2 per frame and Gaussian is the floor of this kernel;
+        // all sixteen warps on one chunk left it idle 40 % of the time).  The two warps a group has per lane quarter
+        // take half of the chunk's units (whole pdfs) each.
+        const int r = (warp & 3) * 32 + lane, part = warp >> 2;
+        const int group = part & 1, cq = part >> 1;
         const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
         const int n_units = a.NB / UNIT;
-        const int u0 = cq * n_units / 4, u1 = (cq + 1) * n_units / 4;
+        const int u0 = cq * n_units / 2, u1 = (cq + 1) * n_units / 2;
         const int qq = warp & 3;
         // the statistics row of this thread's frame: image tile -> registers -> tensor memory (first warp of each quarter)
         auto load_a = [&](int64_t tile, uint32_t tile_it) {
@@ -378,21 +382,24 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a, con
             mbar_arrive(&bars->a_full[ab]);
         };
         uint32_t it = 0, tile_it = 0;
-        if (cq == 0 && (int64_t)blockIdx.x < n_tiles) load_a(blockIdx.x, 0);
+        if (part == 0 && (int64_t)blockIdx.x < n_tiles) load_a(blockIdx.x, 0);
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
             // the next tile's statistics go to the other A buffer while this tile's chunks run
-            if (cq == 0 && tile + gridDim.x < n_tiles) load_a(tile + gridDim.x, tile_it + 1);
+            if (part == 0 && tile + gridDim.x < n_tiles) load_a(tile + gridDim.x, tile_it + 1);
             const int64_t t = tile * FR + r;
             const bool valid = t < a.N;
             float* orow = a.llh2 + (size_t)(valid ? t : 0) * a.ld;
             for (int c = 0; c < a.n_chunks; ++c, ++it) {
-                const int buf = it & 1;
+                if ((int)(it & 1) != group) continue;
+                const int buf = group;
                 mbar_wait(&bars->t_full[buf], (it >> 1) & 1);
                 if (lane == 0 && (warp == 0 || warp == 15)) trace(a.trace, it, warp == 0 ? 4 : 6);
                 tc_fence_after();
                 const float2* kk = s_k12 + (a.n_chunks > 1 ? (it & (K12_RING - 1)) * a.NB : 0);
                 const uint32_t taddr = tmem_base + lane_addr + (uint32_t)buf * 256u;
-                float* sbuf = s_out + ((size_t)qq * 3 + it % 3) * 32 * PC + (size_t)lane * PC;     // this frame's staged row
+                // staging buffers [lane quarter][group][2]: this frame's row of the chunk
+                float* stile = s_out + (size_t)((qq * 2 + group) * 2 + ((it >> 1) & 1)) * 32 * PC;
+                float* sbuf = stile + (size_t)lane * PC;
                 // G units at a time: all their TMEM loads in flight together, independent max / exp / sum chains
                 auto process = [&](int u, auto gtag) {
                     constexpr int G = decltype(gtag)::value;
@@ -404,6 +411,14 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a, con
                         else tmem_ld16_nowait(taddr + (uint32_t)(p + g * UNIT), v + g * UNIT);
                     }
                     tmem_ld_wait();
+                    if (u + G == u1) {
+                        // the warp's last columns are in registers: the accumulator goes back to the MMA thread now, the
+                        // math of this batch runs under the next chunk's MMAs (an accumulator belongs to one group: held
+                        // to the end of the epilogue, the MMAs of chunk i + 2 started only then and the group waited
+                        // ~1100 cycles per chunk for them)
+                        tc_fence_before();
+                        mbar_arrive(&bars->t_empty[buf]);
+                    }
 #pragma unroll
                     for (int i = 0; i < G * UNIT; i += 2) {
                         const float4 k = *reinterpret_cast<const float4*>(kk + p + i);      // (k1, k2) of two columns
@@ -433,28 +448,32 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a, con
                             if (k0 + k < a.Kp) orow[k0 + k] = o[k];
                     }
                 };
+                // batches of GMAX units, the remainder first: the LAST batch is a full one (half of the warp's columns at
+                // the cfg3 shape), so the accumulator is released halfway through the epilogue
+                constexpr int GMAX = UNIT == 8 ? 5 : 2;
                 int u = u0;
-                for (; u + 4 <= u1; u += 4) process(u, std::integral_constant<int, 4>());
-                if (u + 2 <= u1) {
-                    process(u, std::integral_constant<int, 2>());
-                    u += 2;
+                int rem = (u1 - u0) % GMAX;
+                if (rem >= 4) { process(u, std::integral_constant<int, 4>()); u += 4; rem -= 4; }
+                if (rem >= 2) { process(u, std::integral_constant<int, 2>()); u += 2; rem -= 2; }
+                if (rem >= 1) { process(u, std::integral_constant<int, 1>()); u += 1; }
+                for (; u + GMAX <= u1; u += GMAX) process(u, std::integral_constant<int, GMAX>());
+                if (u1 == u0) {          // (no units for this warp: it still owes its arrival)
+                    tc_fence_before();
+                    mbar_arrive(&bars->t_empty[buf]);
                 }
-                if (u < u1) process(u, std::integral_constant<int, 1>());
-                tc_fence_before();
-                mbar_arrive(&bars->t_empty[buf]);
                 if (a.staged) {
                     // one tensor store per lane quarter and chunk: [32 frames x NB / C pdfs], rows past N and columns
-                    // past Kp clipped by the map.  Three staging buffers, one barrier: the issuing lane's
-                    // wait_group.read 1 of chunk i - 1 ran before this barrier, so buffer (i + 1) % 3 is free behind it.
+                    // past Kp clipped by the map.  Two staging buffers per (quarter, group): the issuing lane waits for
+                    // its previous store (the other buffer, issued a whole chunk ago) BEFORE the barrier, so behind
+                    // the barrier both warps may write the other buffer.
                     fence_proxy_async();
-                    asm volatile("bar.sync %0, 128;" ::"r"(1 + qq) : "memory");
+                    if (cq == 0 && elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    asm volatile("bar.sync %0, 64;" ::"r"(1 + qq + 4 * group) : "memory");
                     if (cq == 0 && elect_one()) {
                         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&omap),
-                                     "r"(smem_u32(s_out + ((size_t)qq * 3 + it % 3) * 32 * PC)), "r"(c * PC),
-                                     "r"((int)(tile * FR) + 32 * qq)
+                                     "r"(smem_u32(stile)), "r"(c * PC), "r"((int)(tile * FR) + 32 * qq)
                                      : "memory");
                         bulk_commit();
-                        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                     }
                 }
                 if (lane == 0 && (warp == 0 || warp == 15)) trace(a.trace, it, warp == 0 ? 5 : 7);
@@ -473,7 +492,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a, con
 static size_t ka_smem(int KP, int NB, int C, int n_chunks, bool staged) {
     const int stages = n_chunks > 1 ? KA_STAGES : 1, k12 = n_chunks > 1 ? K12_RING : 1;
     return (size_t)stages * 2 * NB * KP * 2 + (size_t)k12 * NB * 8 + sizeof(KaBarriers) + 128 +
-           (staged ? (size_t)4 * 3 * 32 * (NB / C) * 4 : 0) + 1024;
+           (staged ? (size_t)4 * 4 * 32 * (NB / C) * 4 : 0) + 1024;
 }
 
 static int encode_rows(CUtensorMap* map, const float* base, int64_t N, int Kp, int64_t ld, int box_cols, int box_rows);
@@ -551,7 +570,9 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
 
 // map_l2 / map_lp: [N, Kp] fp32 arrays (log2 pdf llhs of KA16, log2 pdf posteriors of the forward-backward), boxes of
 // [TILE frames x GM / C pdfs]; rows past N and columns past Kp arrive as zeros.
-template <int KP, int C>
+// REL: map_lp holds d = log2(scale posterior) - llh2 in ONE array (beer_hmm_forward_backward_ex, lpost_relative): one
+// block per stage, one load and one addition per (frame, Gaussian) instead of two and three.
+template <int KP, int C, bool REL>
 __global__ void __launch_bounds__(KC_THREADS, 1)
 mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __grid_constant__ CUtensorMap map_lp) {
     constexpr int KS1 = KP / 16;                       // k-steps of S^T = W' . img1^T
@@ -561,7 +582,8 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
     constexpr int NK = GM / C;                         // pdfs of a Gaussian tile
     constexpr int RAW_FLOATS = TILE * NK;              // one [frame][pdf] block
     constexpr int STAGE_A = 2 * IMG_HALF * 2;          // img1 hi | lo
-    constexpr int STAGE_B = 2 * IMG_HALF * 2 + (SINGLE ? 1 : 2) * RAW_FLOATS * 4;    // img2 hi | lo | llh2 | lpost (SINGLE: posteriors)
+    constexpr int NRAW = (SINGLE || REL) ? 1 : 2;
+    constexpr int STAGE_B = 2 * IMG_HALF * 2 + NRAW * RAW_FLOATS * 4;    // img2 hi | lo | llh2 | lpost (SINGLE: posteriors, REL: d)
     constexpr uint32_t COL_W = 0, COL_S = KP, COL_D2 = KP + NSB * TILE;     // tensor-memory columns
     static_assert(COL_D2 + 2 * KP <= 512, "tensor memory");
     static_assert(STAGE_A % 128 == 0 && STAGE_B % 128 == 0, "stage alignment");
@@ -647,7 +669,7 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
                 if (which == 1) {
                     mbar_arrive_expect_tx(&bars->b_full[r.pos], bytes);
                     bulk_g2s(dst, a.img2 + (size_t)(tile0 + i) * (2 * IMG_HALF), bytes, &bars->b_full[r.pos]);
-                } else if (SINGLE) {
+                } else if (SINGLE || REL) {
                     mbar_arrive_expect_tx(&bars->b_full[r.pos], RAW_FLOATS * 4u);
                     tma_load_2d(dst + bytes, &map_lp, k0, t0, &bars->b_full[r.pos]);       // [64 frames x 128 posteriors]
                 } else {
@@ -739,6 +761,7 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
             k2 = k12.y;
         }
         const float wscale = exp2f(a.wexp);
+        const float k2w = k2 + a.wexp;                       // REL: w 2^wexp = 2^(S k1 + (k2 + wexp) + d)
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         float sums[MYCH][4], comp[MYCH][4];
 #pragma unroll
@@ -785,8 +808,11 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
             const float* raw = reinterpret_cast<const float*>(ring_b + (size_t)rb.pos * STAGE_B + STAGE_A);
             const int n_left = (int)min((int64_t)TILE, f_end - (f_begin + (int64_t)i * TILE)) - half * 32;
             float ts[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int sub = 0; sub < 2; ++sub) {
+            // one block of 16 frames: w 2^wexp -> fp16 hi (the top 11 significant bits, by truncation: exact in fp16)
+            // and lo = w - hi (exact in fp32, rounded to fp16), written back in place of S^T.  MASKED (the last tile of
+            // the batch only): frames past the end carry no weight.
+            auto block16 = [&](int sub, auto masked_tag) {
+                constexpr bool MASKED = decltype(masked_tag)::value;
                 const int f0 = half * 32 + sub * 16;             // first frame (in the tile) of this block of 16
                 const uint32_t taddr = tmem_base + lane_addr + COL_S + (uint32_t)(b * TILE + f0);
                 float v[16];
@@ -795,6 +821,11 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
                     const float* rp = raw + f0 * NK + pl;
 #pragma unroll
                     for (int e = 0; e < 16; ++e) v[e] = rp[e * NK] * wscale;
+                } else if constexpr (REL) {
+                    tmem_ld16(taddr, v);
+                    const float* rd = raw + f0 * NK + pl;
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] = ex2(fmaf(v[e], k1, k2w) + rd[e * NK]);
                 } else {
                     tmem_ld16(taddr, v);
                     const float* rl2 = raw + f0 * NK + pl;
@@ -806,8 +837,8 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
                         v[e] = ex2((z - rl2[e * NK]) + (rlp[e * NK] + a.wexp));
                     }
                 }
-                const int nvalid = n_left - sub * 16;
-                if (nvalid < 16) {       // the last tile of the batch: frames past the end carry no weight
+                if constexpr (MASKED) {
+                    const int nvalid = n_left - sub * 16;
 #pragma unroll
                     for (int e = 0; e < 16; ++e)
                         if (e >= nvalid) v[e] = 0.f;
@@ -819,7 +850,7 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         ts[e] += v[4 * h + e];
-                        wh[e] = h_rn(v[4 * h + e]);
+                        wh[e] = __uint_as_float(__float_as_uint(v[4 * h + e]) & 0xffffe000u);
                     }
                     out[2 * h] = pack_h2(wh[0], wh[1]);
                     out[2 * h + 1] = pack_h2(wh[2], wh[3]);
@@ -827,6 +858,13 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
                     out[8 + 2 * h + 1] = pack_h2(v[4 * h + 2] - wh[2], v[4 * h + 3] - wh[3]);
                 }
                 tmem_st16(taddr, out);      // in place: [hi of 16 frames (8 columns) | lo (8 columns)]
+            };
+            if (n_left >= 32) {
+                block16(0, std::false_type());
+                block16(1, std::false_type());
+            } else {
+                block16(0, std::true_type());
+                block16(1, std::true_type());
             }
             tmem_st_wait();
             tc_fence_before();
@@ -882,8 +920,8 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
     }
 }
 
-static size_t kc_smem(int KP, int C, int na, int nb) {
-    return (size_t)na * (2 * TILE * KP * 2) + (size_t)nb * (2 * TILE * KP * 2 + (C == 1 ? 1 : 2) * TILE * (GM / C) * 4) +
+static size_t kc_smem(int KP, int C, bool rel, int na, int nb) {
+    return (size_t)na * (2 * TILE * KP * 2) + (size_t)nb * (2 * TILE * KP * 2 + ((C == 1 || rel) ? 1 : 2) * TILE * (GM / C) * 4) +
            sizeof(KcBarriers) + 1024;
 }
 
@@ -971,16 +1009,19 @@ static int encode_rows(CUtensorMap* map, const float* base, int64_t N, int Kp, i
     return BEER_OK;
 }
 
-template <int KP, int C>
+template <int KP, int C, bool REL = false>
 static int launch_kc(const KcArgs& a0, const float* llh2, int64_t ld_llh, const float* lpost, int64_t ld_lpost,
                      int64_t ranges, cudaStream_t st) {
+    if constexpr (C != 1 && !REL) {
+        if (llh2 == nullptr) return launch_kc<KP, C, true>(a0, lpost, ld_lpost, lpost, ld_lpost, ranges, st);
+    }
     KcArgs a = a0;
     // ring A (img1 tiles): 4 deep; ring B (img2 tile + llh / posterior blocks): whatever else fits
     a.na = C == 1 ? 0 : 4;
     a.nb = RING_MAX;
-    while (a.nb > 2 && kc_smem(KP, C, a.na, a.nb) > 227 * 1024) --a.nb;
-    while (C != 1 && a.na > 2 && kc_smem(KP, C, a.na, a.nb) > 227 * 1024) --a.na;
-    const size_t smem = kc_smem(KP, C, a.na, a.nb);
+    while (a.nb > 2 && kc_smem(KP, C, REL, a.na, a.nb) > 227 * 1024) --a.nb;
+    while (C != 1 && a.na > 2 && kc_smem(KP, C, REL, a.na, a.nb) > 227 * 1024) --a.na;
+    const size_t smem = kc_smem(KP, C, REL, a.na, a.nb);
     if (smem > 227 * 1024) return BEER_ERR_UNSUPPORTED;
     CUtensorMap m1, m2;
     int rc = encode_rows(&m1, llh2, a.N, a.Kp, ld_llh, GM / C, TILE);
@@ -989,10 +1030,10 @@ static int launch_kc(const KcArgs& a0, const float* llh2, int64_t ld_llh, const 
     if (rc != BEER_OK) return rc;
     static bool attr = false;
     if (!attr) {
-        BEER_CUDA_TRY(cudaFuncSetAttribute(mixstats16_kernel<KP, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        BEER_CUDA_TRY(cudaFuncSetAttribute(mixstats16_kernel<KP, C, REL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr = true;
     }
-    mixstats16_kernel<KP, C><<<(int)(ranges * a.n_gtiles), KC_THREADS, smem, st>>>(a, m1, m2);
+    mixstats16_kernel<KP, C, REL><<<(int)(ranges * a.n_gtiles), KC_THREADS, smem, st>>>(a, m1, m2);
     BEER_LAUNCH_CHECK();
     return BEER_OK;
 }
@@ -1135,14 +1176,13 @@ int beer_mix16_accumulate(const void* img1, const void* img2, int64_t N, int D, 
                           const float* alpha, int M, int C, const float* pdf_lpost, int64_t ld_lpost,
                           const float* llh2, int64_t ld_llh, float scale, double* acc_normal, void* stream) {
     if (!img2 || !alpha || !pdf_lpost || !acc_normal || N < 0) return BEER_ERR_ARG;
-    if (C != 1 && (!img1 || !wtm || !k12 || !llh2)) return BEER_ERR_ARG;
+    if (C != 1 && (!img1 || !wtm || !k12)) return BEER_ERR_ARG;
     if (!beer_mix16_supported(M, D, C)) return BEER_ERR_UNSUPPORTED;
-    if (C == 1) {            // single-Gaussian pdfs: pdf_lpost holds the posteriors themselves, nothing else is read
-        llh2 = pdf_lpost;
-        ld_llh = ld_lpost;
-    }
+    const bool one_array = C == 1 || llh2 == nullptr;    // C = 1: the posteriors themselves; else the relative form
+    if (one_array) ld_llh = ld_lpost;
     if (ld_lpost < M / C || ld_llh < M / C || ld_lpost % 4 != 0 || ld_llh % 4 != 0) return BEER_ERR_ARG;
     if (((uintptr_t)pdf_lpost & 15) != 0 || ((uintptr_t)llh2 & 15) != 0 || N >= (int64_t)1 << 31) return BEER_ERR_ARG;
+    if (C == 1) llh2 = pdf_lpost;
     if (N == 0) return BEER_OK;
     mix16::KcArgs a;
     a.img1 = (const __half*)img1; a.img2 = (const __half*)img2; a.N = N; a.wtm = wtm; a.k12 = (const float2*)k12; a.alpha = alpha;

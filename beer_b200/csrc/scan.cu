@@ -231,6 +231,7 @@ struct FbArgs {
     float* pdf_lpost;     // [N, ld_lpost] or NULL: log2(scale * gamma) per pdf (identity pdf maps, loop kernels only)
     int64_t ld_lpost;
     float llh_mul;        // log2(e) for llhs in nats, 1 for llhs already in log2 units (the kernels work in log2)
+    int lpost_rel;        // pdf_lpost = log2(scale * gamma) - log2 llh (what beer_mix16_accumulate adds to z), not log2(scale * gamma)
 };
 
 constexpr int FB_WARPS = 4;
@@ -915,6 +916,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_lr_kernel(FbArgs a) {
     float* ring_a = ring_p + PF * ROW;                      // [PF][32 * S]
     const int K = a.K;
     const float p_scale = a.scale * a.llh_mul;
+    const float lp_rel = a.lpost_rel ? -a.llh_mul : 0.f;
     const int gwarp = blockIdx.x * FB_WARPS + warp, nwarps = gridDim.x * FB_WARPS;
     const bool own = lane * S < K;
     for (int i = lane; i < 2 * PF * ROW; i += 32) ring_p[i] = 0.f;   // lanes past K stay finite
@@ -1130,7 +1132,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_lr_kernel(FbArgs a) {
             float vlog[LP ? S : 1];
 #pragma unroll
             for (int j = 0; j < S; ++j) {
-                if constexpr (LP) vlog[j] = v[j] - ms;
+                if constexpr (LP) vlog[j] = fmaf(p[j], lp_rel, v[j]);       // (relative form: minus the log2 llh)
                 v[j] = ex2(v[j] - ms);
                 sum += v[j];
             }
@@ -1138,7 +1140,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_lr_kernel(FbArgs a) {
             const float inv = (sum > 0.f) ? __fdividef(1.f, sum) : 0.f;
             if constexpr (LP) {
                 // log2(scale gamma) = log value - log2 sum + log2 scale; an impossible frame (sum = 0) gives -inf, not NaN
-                const float lnorm = (sum > 0.f) ? lg2(a.scale) - lg2(sum) : kNegInf;
+                const float lnorm = (sum > 0.f) ? lg2(a.scale) - lg2(sum) - ms : kNegInf;
 #pragma unroll
                 for (int j = 0; j < S; ++j) vlog[j] += lnorm;
                 write_row(a.pdf_lpost + (size_t)(t0 + t) * a.ld_lpost, vlog, 1.f);
@@ -1263,6 +1265,7 @@ __global__ void __launch_bounds__(W * 32, 4) hmm_fb_lrb_kernel(FbArgs a) {
     float* xch = smem + (size_t)W * (2 * PF * ROW);     // [2][W][8] exchange slots
     const int K = a.K;
     const float p_scale = a.scale * a.llh_mul;
+    const float lp_rel_s = a.lpost_rel ? -1.f / a.scale : 0.f;      // p is scaled below: p / scale = the llh in log2 units
     const int gl = warp * 32 + lane;            // unit owned by this lane
     const int k0 = gl * S;                      // its first state
     const bool own = k0 < K;
@@ -1476,7 +1479,7 @@ __global__ void __launch_bounds__(W * 32, 4) hmm_fb_lrb_kernel(FbArgs a) {
             float vlog[LP ? S : 1];
 #pragma unroll
             for (int j = 0; j < S; ++j) {
-                if constexpr (LP) vlog[j] = v[j];
+                if constexpr (LP) vlog[j] = fmaf(p[j], lp_rel_s, v[j]);     // (relative form: minus the log2 llh, here where p is live)
                 v[j] = ex2(v[j] - mls);
                 sl += v[j];
                 pe = fmaf(p[j], v[j], pe);
@@ -1591,6 +1594,7 @@ __global__ void __launch_bounds__(W * 32, 9) hmm_fb_lrc_kernel(FbArgs a) {
     float* xch = smem + (size_t)W * (2 * PF * ROW);     // [2][W][4] exchange slots
     const int K = a.K;
     const float p_scale = a.scale * a.llh_mul;
+    const float lp_rel_s = a.lpost_rel ? -1.f / a.scale : 0.f;      // p is scaled below: p / scale = the llh in log2 units
     const int k0 = (warp * 32 + lane) * S;      // first state of this lane
     const bool own = k0 < K;
     for (int i = lane; i < 2 * PF * ROW; i += 32) ring_p[i] = 0.f;
@@ -1797,7 +1801,7 @@ __global__ void __launch_bounds__(W * 32, 9) hmm_fb_lrc_kernel(FbArgs a) {
             float vlog[LP ? S : 1];
 #pragma unroll
             for (int j = 0; j < S; ++j) {
-                if constexpr (LP) vlog[j] = v[j];
+                if constexpr (LP) vlog[j] = fmaf(p[j], lp_rel_s, v[j]);     // (relative form: minus the log2 llh, here where p is live)
                 v[j] = ex2(v[j] - mls);
                 sl += v[j];
                 pe = fmaf(p[j], v[j], pe);
@@ -1919,6 +1923,7 @@ __global__ void __launch_bounds__(LRW_WARPS * 32, 1) hmm_fb_lrw_kernel(FbArgs a)
     float* ring_a = ring_p + PF * ROW;
     const int K = a.K;
     const float p_scale = a.scale * a.llh_mul;
+    const float lp_rel = a.lpost_rel ? -a.llh_mul : 0.f;
     const int gwarp = blockIdx.x * LRW_WARPS + warp, nwarps = gridDim.x * LRW_WARPS;
     const int k0 = lane * S;
 
@@ -2162,7 +2167,7 @@ __global__ void __launch_bounds__(LRW_WARPS * 32, 1) hmm_fb_lrw_kernel(FbArgs a)
                 // log2(scale gamma) = log value - log2 sum + log2 scale; an impossible frame (sum = 0) gives -inf
                 const float lnorm = (sum > 0.f) ? lg2(a.scale) - lg2(sum) : kNegInf;
 #pragma unroll
-                for (int j = 0; j < S; ++j) la[j] += lnorm;
+                for (int j = 0; j < S; ++j) la[j] = fmaf(p[j], lp_rel, la[j] + lnorm);
                 write_row(a.pdf_lpost + (size_t)(t0 + t) * a.ld_lpost, la, 1.f);
             } else {
                 if (a.state_post != nullptr) write_row(a.state_post + (size_t)(t0 + t) * K, la, inv);
@@ -3147,9 +3152,10 @@ int beer_hmm_forward_backward_units(const beer_graph_plan* plan, const float* pd
 int beer_hmm_forward_backward_ex(const beer_graph_plan* plan, const float* pdf_llh, int64_t ld_pdf,
                                  const float* frame_ref, const int64_t* utt_off, int n_utts, float scale,
                                  float* state_post, float* pdf_post, int64_t ld_post, float* frame_exp_llh,
-                                 double* utt_exp_llh, double* utt_logz, double* unit_counts, int llh_log2,
+                                 double* utt_exp_llh, double* utt_logz, double* unit_counts, int flags,
                                  float* pdf_lpost, int64_t ld_lpost, void* workspace, void* stream) {
     if (!plan || !pdf_llh || !utt_off || !utt_exp_llh || !workspace || n_utts < 0) return BEER_ERR_ARG;
+    const bool llh_log2 = (flags & BEER_FB_LLH_LOG2) != 0;
     if (ld_pdf < plan->Kp || (pdf_post && ld_post < plan->Kp)) return BEER_ERR_ARG;
     if (n_utts == 0) return BEER_OK;
     cudaStream_t st = (cudaStream_t)stream;
@@ -3169,6 +3175,7 @@ int beer_hmm_forward_backward_ex(const beer_graph_plan* plan, const float* pdf_l
     a.unit_counts = unit_counts;
     a.llh_mul = llh_log2 ? 1.f : kLog2e;
     a.pdf_lpost = pdf_lpost; a.ld_lpost = ld_lpost;
+    a.lpost_rel = (flags & BEER_FB_LPOST_RELATIVE) ? 1 : 0;
     if (pdf_lpost != nullptr && (ld_lpost < plan->Kp || ld_lpost % 4 != 0 || ((uintptr_t)pdf_lpost & 15) != 0)) return BEER_ERR_ARG;
     if (unit_counts != nullptr && beer_hmm_unit_count_size(plan) <= 0) return BEER_ERR_UNSUPPORTED;
     const bool post_ok = (pdf_post == nullptr || (ld_post % 4 == 0 && ((uintptr_t)pdf_post & 15) == 0)) &&

@@ -379,6 +379,7 @@ class VBEngine:
             pdf_post = self.pdf_post[:nf]
             comp = self.comp_llh[:nf] if self.comp_llh is not None else None
             images = None
+            direct = False
             if self.mix16 is not None:
                 if self.host_mode:       # streamed features: the images of the chunk are rebuilt behind its copy
                     with self._stage('KI_feature_images'):
@@ -434,7 +435,7 @@ class VBEngine:
                                              want_pdf_post=not direct, out_pdf_post=None if direct else pdf_post,
                                              out_pdf_lpost=pdf_post if direct else None,
                                              out_utt_exp_llh=self.utt_ell[u0:u1],
-                                             unit_counts=self.unit_counts, llh_log2=ka16)
+                                             unit_counts=self.unit_counts, llh_log2=ka16, lpost_relative=direct)
                     if images is not None and not direct and self.mix16.C > 1:      # graphs without a loop kernel: log2 of pdf_post
                         self.mix16.log2_posteriors(pdf_post, out=pdf_post)
                         self.gpu_launches += 1
@@ -445,7 +446,9 @@ class VBEngine:
                     cs = torch.cat([torch.zeros(1, dtype=f64, device=self.dev), frame.double().cumsum(0)])
                     self.utt_ell[u0:u1] = cs[rel[1:]] - cs[rel[:-1]]
                 elif images is not None:
-                    self.mix16.accumulate(images, pdf_post, pdf_llh, self.acc, scale=self.scale)
+                    # `direct`: the scan wrote log2 posterior - log2 llh, the one array the statistics kernel adds to z
+                    self.mix16.accumulate(images, pdf_post, None if direct else pdf_llh, self.acc, scale=self.scale,
+                                          relative=direct)
                 elif self.viterbi and self._path_kc:
                     ops.accumulate_stats_path(X, self.acc, self._pdf_ids[:nf], scale=self.scale)
                 else:

@@ -342,14 +342,20 @@ BEER_API int beer_add_deltas(const float* fea, int n_frames, int dim, int wlen, 
 
 /* 1 when beer_hmm_forward_backward_ex can write pdf_lpost for this graph. */
 BEER_API int beer_hmm_lpost_supported(const beer_graph_plan* plan);
-/* Same as beer_hmm_forward_backward_units with the domain of the llhs stated: llh_log2 != 0 = pdf_llh holds log2
- * values (what beer_mix16_emission writes; frame_ref stays in nats), 0 = nats.  pdf_lpost (optional, [N, ld_lpost],
+/* Same as beer_hmm_forward_backward_units with the domain of the llhs stated: flags & BEER_FB_LLH_LOG2 = pdf_llh holds
+ * log2 values (what beer_mix16_emission writes; frame_ref stays in nats), else nats.  pdf_lpost (optional, [N, ld_lpost],
  * 16-byte aligned rows) = log2(scale * posterior) per pdf, -inf for zero: only the left-to-right loop kernels write it
- * (BEER_ERR_UNSUPPORTED otherwise: take pdf_post and beer_mix16_log2_posteriors). */
+ * (BEER_ERR_UNSUPPORTED otherwise: take pdf_post and beer_mix16_log2_posteriors).  flags & BEER_FB_LPOST_RELATIVE:
+ * pdf_lpost = log2(scale * posterior) - log2 llh of the pdf instead, the ONE array beer_mix16_accumulate (llh2 = NULL)
+ * adds to its z to weight a Gaussian (gamma_tk r_tkc = 2^(z_tkc + lpost_tk - llh2_tk), mixtureset.py:100-112); its
+ * rounding error is half an ulp of |llh2| in the exponent (offset-form llhs of a few hundred: <= 1e-5 of the weight,
+ * zero-mean over frames), where the two-array form subtracts z - llh2 exactly. */
+#define BEER_FB_LLH_LOG2 1
+#define BEER_FB_LPOST_RELATIVE 2
 BEER_API int beer_hmm_forward_backward_ex(const beer_graph_plan* plan, const float* pdf_llh, int64_t ld_pdf,
                                  const float* frame_ref, const int64_t* utt_off, int n_utts, float scale,
                                  float* state_post, float* pdf_post, int64_t ld_post, float* frame_exp_llh,
-                                 double* utt_exp_llh, double* utt_logz, double* unit_counts, int llh_log2,
+                                 double* utt_exp_llh, double* utt_logz, double* unit_counts, int flags,
                                  float* pdf_lpost, int64_t ld_lpost, void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------
@@ -383,6 +389,8 @@ BEER_API int beer_mix16_emission(const void* img1, int64_t N, int D, const void*
 /* acc_normal [M, 2D+2] (fp64) += sum_t 2^pdf_lpost[t, pdf(j)] r_tj T(x_t) with the responsibilities r = 2^(z - llh2)
  * recomputed on chip (mixtureset.py:100-112, normalset.py:121-123).  pdf_lpost [N, ld] = log2 of the pdf posteriors
  * (times `scale`, -inf = zero): written by beer_hmm_forward_backward_ex, or beer_mix16_log2_posteriors of pdf_post.
+ * llh2 = NULL (C > 1): pdf_lpost is in the relative form of BEER_FB_LPOST_RELATIVE (already minus llh2): one array
+ * streamed instead of two and a third fewer epilogue instructions per (frame, Gaussian).
  * C = 1 (single-Gaussian pdfs, NormalSet.accumulate alone): pdf_lpost holds the posteriors THEMSELVES (linear, as
  * beer_hmm_forward_backward writes pdf_post) and img1 / wtm / k12 / llh2 are not read (may be NULL). */
 BEER_API int beer_mix16_accumulate(const void* img1, const void* img2, int64_t N, int D, const uint32_t* wtm, const float* k12,

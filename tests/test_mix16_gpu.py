@@ -92,6 +92,16 @@ def test_emission_and_statistics_match_fp64(M, D, C, N):
     # accumulation semantics: a second call adds
     mx.accumulate(images, lpp, llh2, acc)
     assert (acc - 2 * want_acc).abs().max().item() <= 2 * tol
+    if C > 1:
+        # relative form: ONE array log2 posterior - llh2 (what the forward-backward writes with lpost_relative);
+        # its rounding is half an ulp of |llh2| in the exponent, zero-mean over the frames
+        acc_r = torch.zeros_like(acc)
+        mx.accumulate(images, (lpp - llh2).contiguous(), None, acc_r, relative=True)
+        assert (acc_r - want_acc).abs().max().item() <= tol, ((acc_r - want_acc).abs().max().item(), tol)
+        cnt = 2.0 * acc_r[:, 2 * D + 1].reshape(Kp, C).sum(1)
+        assert (cnt - want_cnt).abs().max().item() <= 2e-5 * want_cnt.abs().max().item() + 1e-9
+        with pytest.raises(ValueError):
+            mx.accumulate(images, lpp, llh2, acc_r, relative=True)
 
 
 def test_forward_backward_accepts_log2_llhs():
@@ -126,3 +136,16 @@ def test_forward_backward_accepts_log2_llhs():
     c3 = ops.hmm_forward_backward(p3, small, None, o3)
     assert (torch.exp2(lp3) - c3['pdf_post']).abs().max().item() <= 2e-6
     np.testing.assert_allclose(a['utt_exp_llh'].cpu().numpy(), b['utt_exp_llh'].cpu().numpy(), rtol=2e-6)
+    # relative form (BEER_FB_LPOST_RELATIVE): log2 posterior - log2 llh, from the eight-warp and the one-warp kernel
+    llh2 = (llh / LN2).contiguous()
+    lp_abs, lp_rel = torch.empty_like(lp), torch.empty_like(lp)
+    ops.hmm_forward_backward(plan, llh2, fref, off, want_pdf_post=False, out_pdf_lpost=lp_abs, llh_log2=True)
+    ops.hmm_forward_backward(plan, llh2, fref, off, want_pdf_post=False, out_pdf_lpost=lp_rel, llh_log2=True,
+                             lpost_relative=True)
+    fin = torch.isfinite(lp_abs)
+    assert ((lp_rel - (lp_abs - llh2))[fin]).abs().max().item() <= 2e-5
+    assert torch.equal(torch.isfinite(lp_rel), fin)
+    lp3r = torch.empty_like(lp3)
+    ops.hmm_forward_backward(p3, small, None, o3, want_pdf_post=False, out_pdf_lpost=lp3r, lpost_relative=True, scale=2.0)
+    c3s = ops.hmm_forward_backward(p3, small, None, o3, scale=2.0)
+    assert (torch.exp2(lp3r + small / LN2) - c3s['pdf_post']).abs().max().item() <= 1e-5

@@ -27,11 +27,12 @@ def main():
     llh2 = mx.emission(images)
     lp = torch.log2(torch.softmax(torch.randn(N, Kp, device=dev) * 4, dim=1)).contiguous()
     acc = torch.zeros(M, 2 * D + 2, device=dev, dtype=torch.float64)
-    mx.accumulate(images, lp, llh2, acc)
+    lrel = (lp - llh2).contiguous()      # the one-array form the forward-backward writes (BEER_FB_LPOST_RELATIVE)
+    mx.accumulate(images, lrel, None, acc, relative=True)
     torch.cuda.synchronize()
     lib = _lib.load()
     for name, fn in (('emission (per chunk)', lambda: mx.emission(images, out=llh2)),
-                     ('statistics (per tile)', lambda: mx.accumulate(images, lp, llh2, acc))):
+                     ('statistics (per tile)', lambda: mx.accumulate(images, lrel, None, acc, relative=True))):
         buf = torch.zeros(256 * 8, device=dev, dtype=torch.int64)
         lib.beer_mix16_set_trace(buf.data_ptr())
         fn()
