@@ -204,7 +204,8 @@ __global__ void __launch_bounds__(128) pack16_kernel(const float* __restrict__ W
 // ---------------------------------------------------------------------------------------------
 // KA16: llh2 [N, Kp] = log2 sum_c 2^(z_tkc)
 // ---------------------------------------------------------------------------------------------
-constexpr int KA_WORKERS = 512, KA_MMA_WARP = KA_WORKERS / 32, KA_LOAD_WARP = KA_MMA_WARP + 1;
+constexpr int KA_NCQ = 3;               // epilogue warps per (lane quarter, group): each takes 1 / KA_NCQ of the chunk's units
+constexpr int KA_WORKERS = 4 * 2 * KA_NCQ * 32, KA_MMA_WARP = KA_WORKERS / 32, KA_LOAD_WARP = KA_MMA_WARP + 1;
 constexpr int KA_THREADS = KA_WORKERS + 64;
 constexpr int KA_STAGES = 3;            // weight-chunk ring
 constexpr int K12_RING = 8;             // the loader runs up to KA_STAGES + 2 chunks ahead of the epilogue that reads (k1, k2)
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a, con
         const int group = part & 1, cq = part >> 1;
         const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
         const int n_units = a.NB / UNIT;
-        const int u0 = cq * n_units / 2, u1 = (cq + 1) * n_units / 2;
+        const int u0 = cq * n_units / KA_NCQ, u1 = (cq + 1) * n_units / KA_NCQ;
         const int qq = warp & 3;
         // the statistics row of this thread's frame: image tile -> registers -> tensor memory (first warp of each quarter)
         auto load_a = [&](int64_t tile, uint32_t tile_it) {
@@ -450,7 +451,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a, con
                 };
                 // batches of GMAX units, the remainder first: the LAST batch is a full one (half of the warp's columns at
                 // the cfg3 shape), so the accumulator is released halfway through the epilogue
-                constexpr int GMAX = UNIT == 8 ? 5 : 2;
+                constexpr int GMAX = UNIT == 8 ? (KA_NCQ >= 3 ? 3 : 5) : 2;
                 int u = u0;
                 int rem = (u1 - u0) % GMAX;
                 if (rem >= 4) { process(u, std::integral_constant<int, 4>()); u += 4; rem -= 4; }
@@ -468,7 +469,7 @@ __global__ void __launch_bounds__(KA_THREADS, 1) emission16_kernel(KaArgs a, con
                     // the barrier both warps may write the other buffer.
                     fence_proxy_async();
                     if (cq == 0 && elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    asm volatile("bar.sync %0, 64;" ::"r"(1 + qq + 4 * group) : "memory");
+                    asm volatile("bar.sync %0, %1;" ::"r"(1 + qq + 4 * group), "n"(32 * KA_NCQ) : "memory");
                     if (cq == 0 && elect_one()) {
                         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&omap),
                                      "r"(smem_u32(stile)), "r"(c * PC), "r"((int)(tile * FR) + 32 * qq)

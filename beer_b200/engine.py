@@ -145,14 +145,56 @@ class UnitWeights:
         self.start_idxs = [int(i) for i in start_idxs]
         self.end_idxs = [int(i) for i in end_idxs]
 
+    def expected_log_weights(self):
+        return ops.dirichlet_expected_logw(self.post)
+
+    def kl(self, out):
+        """out (fp64 [1]) += KL(posterior || prior) of the weights."""
+        ops.dirichlet_kl(self.prior, self.post, out=out)
+
+    def update(self, counts, stats_scale, lrate):
+        """Natural-gradient step from the unit counts (in the order of the weights): Dirichlet statistics with the
+        last entry replaced by the total (dirichlet.py:18-21)."""
+        stats = counts.clone()
+        stats[-1] = stats.sum()
+        ops.dirichlet_update(self.prior, self.post, stats, stats_scale, lrate)
+
     def rewrite_graph(self):
         """ln A[end, starts] = ln(1 - A[end, end]) + E[ln w] (phoneloop.py:53-65), on the host copy of the
         graph; its device plan is rebuilt on the next use."""
-        logw = ops.dirichlet_expected_logw(self.post)
+        logw = self.expected_log_weights()
         trans = self.graph.trans_log_probs
         logw = logw.to(device=trans.device, dtype=trans.dtype)
         for e in self.end_idxs:
             trans[e, self.start_idxs] = (1 - trans[e, e].exp()).log() + logw
+
+
+class CategoricalUnitWeights(UnitWeights):
+    """Unit weights held by a model of `beer_b200.models`: `Categorical` (Dirichlet), `SBCategorical` or
+    `SBCategoricalHyperPrior` (the stick-breaking priors of categorical.py:82-209; `gamma_dirichlet_process` is the
+    default of `beer hmm mkphoneloop`).  The engine hands it the unit counts of the iteration; the model's own
+    parameter objects do the statistics transform, the update and the callbacks (a handful of numbers per iteration)."""
+
+    def __init__(self, categorical, graph, start_idxs, end_idxs):
+        self.categorical = categorical
+        self.graph = graph
+        self.start_idxs = [int(i) for i in start_idxs]
+        self.end_idxs = [int(i) for i in end_idxs]
+
+    def expected_log_weights(self):
+        return self.categorical.expected_log_weights()
+
+    def kl(self, out):
+        out += self.categorical.kl_div_posterior_prior().sum().to(out.dtype)
+
+    def update(self, counts, stats_scale, lrate):
+        from .models import SBCategorical
+        stats = counts.clone().to(f64)
+        if not isinstance(self.categorical, SBCategorical):
+            stats[-1] = stats.sum()            # (stick-breaking weights take the plain counts: categorical.py:107-116)
+        param = self.categorical.mean_field_factorization()[0][0]
+        param.store_stats(stats * stats_scale)
+        param.natural_grad_update(lrate)
 
 
 class _StageTimer:
@@ -253,11 +295,12 @@ class VBEngine:
             raise ValueError('the batched GMM mode needs one pdf whose number of components is a multiple of 32 '
                              '(D = 20 or 40); other mixtures go through the model API (Mixture)')
         self.chains = isinstance(plan, ops.ChainBatch)
-        if self.chains and (unit_weights is not None or plan.n_utts != utts.n_utts or self.viterbi):
-            raise ValueError('a ChainBatch needs one chain per utterance of the shard, runs forward-backward and '
-                             'trains no unit weights (phoneloop.py:98-100)')
-        P = plan.n_units if unit_weights is not None else 0
-        if unit_weights is not None and P == 0:
+        if self.chains and (plan.n_utts != utts.n_utts or self.viterbi):
+            raise ValueError('a ChainBatch needs one chain per utterance of the shard and runs forward-backward')
+        # aligned training gives the unit weights ZERO statistics (phoneloop.py:98-100): with `unit_weights` their KL
+        # still enters the ELBO and their posterior takes the natural-gradient step towards the prior, as in the reference
+        P = plan.n_units if (unit_weights is not None and not self.chains) else 0
+        if unit_weights is not None and P == 0 and not self.chains:
             raise ValueError('unit weights need an aligned left-to-right phone loop (see beer_hmm_forward_backward_units)')
         self.flat = torch.zeros(M * self.Q + P + 4, device=self.dev, dtype=f64)
         self.acc = self.flat[:M * self.Q].view(M, self.Q)
@@ -359,7 +402,7 @@ class VBEngine:
         W, bias, ref = em.refresh(pack_tc=not ka16)
         em.kl(out=self.kl)
         if self.units is not None:
-            ops.dirichlet_kl(self.units.prior, self.units.post, out=self.kl)
+            self.units.kl(self.kl)
         self.gpu_launches += 2 + 1 + 2 * len(em.weight_groups) + int(em.use_tc)
         nonident = self._nonident
         chunks = [c for c in self._chunks if c[3] > 0]
@@ -519,13 +562,16 @@ class VBEngine:
             # unit counts in the order of the weights -> Dirichlet statistics (last entry = total,
             # dirichlet.py:18-21) -> natural-gradient step -> rewrite the graph -> new device plan
             u = self.units
-            su = self.plan.n_states // self.unit_counts.numel()
-            order = torch.as_tensor([s // su for s in u.start_idxs], device=self.dev)
-            stats = self.unit_counts[order].clone()
-            stats[-1] = stats.sum()
-            ops.dirichlet_update(u.prior, u.post, stats, stats_scale, self.lrate)
+            if self.chains:
+                counts = torch.zeros(len(u.start_idxs), device=self.dev, dtype=f64)
+            else:
+                su = self.plan.n_states // self.unit_counts.numel()
+                order = torch.as_tensor([s // su for s in u.start_idxs], device=self.dev)
+                counts = self.unit_counts[order]
+            u.update(counts, stats_scale, self.lrate)
             u.rewrite_graph()
-            self.plan = u.graph.plan(n_pdfs=self.em.Kp)
+            if not self.chains:
+                self.plan = u.graph.plan(n_pdfs=self.em.Kp)
             self.gpu_launches += 2
         return elbo
 

@@ -383,7 +383,7 @@ class SBCategorical(Model):
 
     def _transform_stats(self):
         stats = self.stickbreaking.stats
-        self.ordering = stats.sort(descending=True)[1]
+        self.ordering = stats.sort(descending=True, stable=True)[1]      # (ties as the CPU sort of the reference leaves them)
         stats = stats[self.ordering]
         s2 = torch.zeros_like(stats)
         s2[:-1] = stats[1:]

@@ -648,9 +648,96 @@ def gold_fbank():
          mspec=mspec, cli_logmel40=cli40)
 
 
+def gold_cli_files():
+    """The files the recipes pass between `beer hmm mkphoneloop`, `beer hmm accumulate` and `beer hmm update`
+    (cli/subcommands/hmm/accumulate.py:22-63, update.py:22-72, dataset/create.py:44-60), written by the live reference
+    into tests/golden/cli/: a features archive, the pickled Dataset, phone-loop models pickled by the reference
+    (Dirichlet unit weights; the CLI default `gamma_dirichlet_process` = SBCategoricalHyperPrior) and the models the
+    reference's own accumulate + update produce from them (unsupervised over five utterances; aligned with the
+    alignment archive over three)."""
+    import argparse
+    import io
+    import logging
+    import pickle
+    import types
+    sys.modules.setdefault('natsort', types.SimpleNamespace(natsorted=sorted))
+    from beer.cli.dataset import Dataset
+    from beer.cli.subcommands.hmm import accumulate, update
+    out = os.path.join(OUT, 'cli')
+    os.makedirs(out, exist_ok=True)
+    seed, D = 11, 4
+    rng = np.random.default_rng(seed)
+    torch.manual_seed(seed)
+    g, units, start_pdf, end_pdf = phone_loop(4, 3)
+    cg = g.compile()
+    K = cg.n_states
+    means = 2.0 * rng.standard_normal((K, D))
+    seqs = {'utt_a': ['u2', 'u0'], 'utt_b': ['u1'], 'utt_c': ['u3', 'u3', 'u0', 'u2']}      # = gold_alignment_archive
+    feats = {u: sample_from_graph(rng, ali_graph(seq, units), means, 30 + 12 * len(seq)) for u, seq in seqs.items()}
+    feats['utt_d'] = sample_from_graph(rng, cg, means, 64)
+    feats['utt_e'] = sample_from_graph(rng, cg, means, 51)
+    feapath = os.path.join(out, 'feats.npz')
+    np.savez(feapath, **feats)
+    Xall = np.concatenate(list(feats.values()))
+    ds = Dataset(feapath, torch.from_numpy(Xall.mean(0)).float(), torch.from_numpy(Xall.var(0)).float(), len(Xall))
+    with open(os.path.join(out, 'dataset.pkl'), 'wb') as f:
+        pickle.dump(ds, f)
+
+    def make_model(categorical):
+        C1, C2, K1 = 4, 2, 6
+        ns1 = beer.NormalSet.create(torch.zeros(D), torch.ones(D), size=K1 * C1, prior_strength=1., noise_std=1.,
+                                    cov_type='diagonal')
+        ns2 = beer.NormalSet.create(torch.zeros(D), torch.ones(D), size=(K - K1) * C2, prior_strength=1., noise_std=1.,
+                                    cov_type='diagonal')
+        emissions = beer.JointModelSet([beer.MixtureSet.create(K1, ns1, prior_strength=1.),
+                                        beer.MixtureSet.create(K - K1, ns2, prior_strength=1.)])
+        return beer.PhoneLoop.create(g.compile(), start_pdf, end_pdf, emissions, categorical)
+
+    log = logging.getLogger('gold_cli')
+    log.addHandler(logging.NullHandler())
+
+    def run(model_in, model_out, uttids, alis=None, scale=1.0, lrate=1.0):
+        acc_path = os.path.join(out, '_acc.tmp')
+        stdin = sys.stdin
+        try:
+            sys.stdin = io.StringIO(''.join(u + '\n' for u in uttids))
+            accumulate.main(argparse.Namespace(alis=alis, acoustic_scale=scale, model=model_in,
+                                               dataset=os.path.join(out, 'dataset.pkl'), out=acc_path), log)
+            sys.stdin = io.StringIO(acc_path + '\n')
+            update.main(argparse.Namespace(learning_rate=lrate, optim_state=None, model=model_in, out_model=model_out), log)
+        finally:
+            sys.stdin = stdin
+        with open(acc_path, 'rb') as f:
+            elbo, count = pickle.load(f)
+        os.remove(acc_path)
+        return float(elbo) / (count * elbo._datasize)
+
+    expected = {}
+    m0 = os.path.join(out, 'ploop_0.mdl')
+    with open(m0, 'wb') as f:
+        pickle.dump(make_model(beer.Categorical.create(torch.ones(4) / 4, prior_strength=2.)), f)
+    ids = sorted(feats)
+    expected['unsup_elbo_1'] = run(m0, os.path.join(out, 'ploop_1.mdl'), ids)
+    expected['unsup_elbo_2'] = run(os.path.join(out, 'ploop_1.mdl'), os.path.join(out, 'ploop_2.mdl'), ids)
+    os.remove(os.path.join(out, 'ploop_1.mdl'))          # (the test runs two epochs in one command)
+    s0 = os.path.join(out, 'ploop_sbhp_0.mdl')
+    with open(s0, 'wb') as f:
+        pickle.dump(make_model(beer.SBCategoricalHyperPrior.create(truncation=4, prior_strength=2.,
+                                                                   hyper_prior_strength=1.)), f)
+    expected['ali_elbo_1'] = run(s0, os.path.join(out, 'ploop_sbhp_ali_1.mdl'), ['utt_a', 'utt_b', 'utt_c'],
+                                 alis=os.path.join(OUT, 'alis.npz'), scale=0.8, lrate=0.5)
+    np.savez(os.path.join(out, 'expected.npz'), **{k: np.float64(v) for k, v in expected.items()})
+    for fn in sorted(os.listdir(out)):
+        print(f'cli/{fn}: {os.path.getsize(os.path.join(out, fn)) / 1024:.1f} KiB')
+    print(expected)
+
+
 if __name__ == '__main__':
     if len(sys.argv) > 2 and sys.argv[2] == 'fbank':
         gold_fbank()
+        sys.exit(0)
+    if len(sys.argv) > 2 and sys.argv[2] == 'cli':
+        gold_cli_files()
         sys.exit(0)
     if len(sys.argv) > 2 and sys.argv[2] == 'vae':
         gold_vae()
@@ -674,3 +761,4 @@ if __name__ == '__main__':
     gold_dense_ergodic()
     gold_graph_compile()
     gold_fbank()
+    gold_cli_files()

@@ -1,0 +1,62 @@
+"""`python -m beer_b200.hmm_train` (= `beer hmm accumulate` + `beer hmm update`, accumulate.py:22-63, update.py:22-72) on
+files written by the LIVE reference, against the models the reference's own accumulate + update produced from them
+(tests/golden/make_goldens.py gold_cli_files; the reference ran in float32 as its CLI does)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+CLI = os.path.join(HERE, 'golden', 'cli')
+
+
+def _compare(got_path, want_path, rtol, skip=()):
+    from beer_b200 import refpickle
+    from test_refpickle import _tensors
+    got, want = _tensors(refpickle.load(got_path)), _tensors(refpickle.load(want_path))
+    assert got.keys() == want.keys()
+    worst = 0.0
+    for k in want:
+        if any(s in k for s in skip):
+            continue
+        g, w = got[k].double(), want[k].double()
+        assert g.shape == w.shape and got[k].dtype == want[k].dtype, k
+        if w.dtype.is_floating_point and w.numel():
+            fin = torch.isfinite(w)
+            assert torch.equal(fin, torch.isfinite(g)), k
+            err = ((g - w)[fin].abs().max() / w[fin].abs().max().clamp(min=1e-3)).item() if fin.any() else 0.0
+            worst = max(worst, err)
+            assert err <= rtol, (k, err)
+    return worst
+
+
+def test_unsupervised_two_epochs(tmp_path, capsys):
+    from beer_b200 import hmm_train
+    ids = tmp_path / 'utts'
+    ids.write_text(''.join(f'{u} extra columns are ignored\n' for u in ('utt_a', 'utt_b', 'utt_c', 'utt_d', 'utt_e')))
+    out = str(tmp_path / 'ploop_2.mdl')
+    assert hmm_train.main(['-e', '2', '-u', str(ids), os.path.join(CLI, 'ploop_0.mdl'),
+                           os.path.join(CLI, 'dataset.pkl'), out]) == 0
+    want = np.load(os.path.join(CLI, 'expected.npz'))
+    logged = [float(line.split('=')[1]) for line in capsys.readouterr().out.splitlines() if 'ELBO=' in line]
+    np.testing.assert_allclose(logged, [want['unsup_elbo_1'], want['unsup_elbo_2']], atol=2e-3)
+    # every tensor of the pickle: emission posteriors + their statistics, mixture weights, unit weights, the decoding
+    # graph rewritten from the new unit weights (fp32 reference: 1e-4)
+    _compare(out, os.path.join(CLI, 'ploop_2.mdl'), rtol=5e-4)
+
+
+def test_aligned_training_with_the_cli_default_unit_prior(tmp_path, capsys):
+    from beer_b200 import hmm_train
+    ids = tmp_path / 'utts'
+    ids.write_text('utt_a\nutt_b\nutt_c\nutt_missing\n')
+    out = str(tmp_path / 'ploop_ali.mdl')
+    assert hmm_train.main(['-a', os.path.join(HERE, 'golden', 'alis.npz'), '-s', '0.8', '-l', '0.5', '-u', str(ids),
+                           os.path.join(CLI, 'ploop_sbhp_0.mdl'), os.path.join(CLI, 'dataset.pkl'), out]) == 0
+    want = np.load(os.path.join(CLI, 'expected.npz'))
+    cap = capsys.readouterr()
+    logged = [float(line.split('=')[1]) for line in cap.out.splitlines() if 'ELBO=' in line]
+    np.testing.assert_allclose(logged, [want['ali_elbo_1']], atol=2e-3)
+    assert 'utt_missing' in cap.err
+    _compare(out, os.path.join(CLI, 'ploop_sbhp_ali_1.mdl'), rtol=5e-4)
