@@ -532,7 +532,7 @@ constexpr int KC_MMA_WARP = EPI / 32, KC_LOAD_WARP = KC_MMA_WARP + 1;
 constexpr int KC_LOADERS = 3;            // one issuing thread per copy stream (20 warps in all: 96 registers per thread)
 constexpr int KC_THREADS = EPI + 32 + 32 * KC_LOADERS;
 constexpr int RING_MAX = 8;              // upper bound of either shared-memory ring
-constexpr int NSB = 3;                   // S^T / A2 buffers in tensor memory
+constexpr int NSB = 4;                   // S^T / A2 buffers in tensor memory (64 columns each; the first MMA fills a PAIR: N = 128)
 constexpr int DR = 4;                    // tiles per drain of the statistics accumulator (48 truncating accumulations)
 
 struct KcArgs {
@@ -654,17 +654,27 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
             const int which = warp - KC_LOAD_WARP;
             const uint32_t bytes = STAGE_A;                   // hi + lo of one image
             const int k0 = g0 / C;
-            Ring r(which == 0 ? a.na : a.nb);
-            for (int i = 0; i < (SINGLE && which == 0 ? 0 : n_tiles); ++i, r.next()) {
-                const int t0 = (int)(f_begin + (int64_t)i * TILE);
-                if (which == 0) {
-                    mbar_wait_relaxed(&bars->a_empty[r.pos], r.phase ^ 1, 200);
+            if (which == 0) {
+                // img1 tiles in PAIRS: [hi(t) | hi(t + 1) | lo(t) | lo(t + 1)], so that one descriptor spans the 128
+                // frames of the pair (a tile's hi / lo halves are adjacent in HBM: four copies per pair)
+                Ring rp(a.na / 2);
+                const uint32_t half_bytes = IMG_HALF * 2u;
+                for (int i = 0; !SINGLE && i < n_tiles; i += 2, rp.next()) {
+                    const int nt = min(2, n_tiles - i);
+                    mbar_wait_relaxed(&bars->a_empty[rp.pos], rp.phase ^ 1, 200);
                     trace(a.trace, i, 0);
-                    mbar_arrive_expect_tx(&bars->a_full[r.pos], bytes);
-                    bulk_g2s(ring_a + (size_t)r.pos * STAGE_A, a.img1 + (size_t)(tile0 + i) * (2 * IMG_HALF), bytes,
-                             &bars->a_full[r.pos]);
-                    continue;
+                    mbar_arrive_expect_tx(&bars->a_full[rp.pos], (uint32_t)nt * bytes);
+                    uint8_t* dst = ring_a + (size_t)rp.pos * (2 * STAGE_A);
+                    for (int t = 0; t < nt; ++t) {
+                        const __half* src = a.img1 + (size_t)(tile0 + i + t) * (2 * IMG_HALF);
+                        bulk_g2s(dst + (size_t)t * half_bytes, src, half_bytes, &bars->a_full[rp.pos]);
+                        bulk_g2s(dst + (size_t)(2 + t) * half_bytes, src + IMG_HALF, half_bytes, &bars->a_full[rp.pos]);
+                    }
                 }
+            }
+            Ring r(a.nb);
+            for (int i = 0; i < (which == 0 ? 0 : n_tiles); ++i, r.next()) {
+                const int t0 = (int)(f_begin + (int64_t)i * TILE);
                 mbar_wait_relaxed(&bars->b_empty[r.pos], r.phase ^ 1, 200);
                 uint8_t* dst = ring_b + (size_t)r.pos * STAGE_B;
                 if (which == 1) {
@@ -686,28 +696,31 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
             const uint32_t idesc1 = (1u << 4) | ((uint32_t)(TILE >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
             const uint32_t idesc2 = (1u << 4) | ((uint32_t)(KP >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
             const uint32_t w_hi = tmem_base + COL_W, w_lo = w_hi + KP / 2;
-            Ring ra(a.na), rb(a.nb);
-            int b1 = 0, b2 = 0;                      // S^T buffer of the next first / second MMA
-            uint32_t ph1 = 0, ph2 = 0;
-            auto issue_g1 = [&](int i) {
+            // S^T of TWO tiles per MMA (N = 128 frames): a 128 x 64 x 16 MMA with A in tensor memory takes ~51 cycles
+            // against 33 of tensor work, the 27 MMAs of a tile were the floor of this kernel (1400 cycles per tile)
+            const uint32_t idesc1p = (1u << 4) | ((uint32_t)((2 * TILE) >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
+            Ring ra(a.na / 2), rb(a.nb);
+            int b2 = 0;                              // S^T buffer of the next second MMA
+            uint32_t ph2 = 0;
+            auto issue_g1 = [&](int i) {             // tiles i, i + 1 (i even) -> buffers (i % 4), (i % 4) + 1
                 mbar_wait(&bars->a_full[ra.pos], ra.phase);
                 trace(a.trace, i, 1);
                 tc_fence_after();
-                const uint32_t base = smem_u32(ring_a + (size_t)ra.pos * STAGE_A);
-                const uint64_t dbh = make_desc(base, 128, KP * 16), dbl = make_desc(base + IMG_HALF * 2u, 128, KP * 16);
+                const uint32_t base = smem_u32(ring_a + (size_t)ra.pos * (2 * STAGE_A));
+                const uint64_t dbh = make_desc(base, 128, KP * 16), dbl = make_desc(base + 2u * IMG_HALF * 2u, 128, KP * 16);
+                const int b1 = i & 2;
                 const uint32_t d = tmem_base + COL_S + (uint32_t)b1 * TILE;
+                const uint32_t idesc = (i + 1 < n_tiles) ? idesc1p : idesc1;
 #pragma unroll
                 for (int ks = 0; ks < KS1; ++ks) {
-                    umma_f16_ts(d, w_hi + 8u * ks, dbh + 16u * ks, idesc1, ks > 0);
-                    umma_f16_ts(d, w_lo + 8u * ks, dbh + 16u * ks, idesc1, 1);       // weights lo x statistics hi
-                    umma_f16_ts(d, w_hi + 8u * ks, dbl + 16u * ks, idesc1, 1);       // weights hi x statistics lo
+                    umma_f16_ts(d, w_hi + 8u * ks, dbh + 16u * ks, idesc, ks > 0);
+                    umma_f16_ts(d, w_lo + 8u * ks, dbh + 16u * ks, idesc, 1);        // weights lo x statistics hi
+                    umma_f16_ts(d, w_hi + 8u * ks, dbl + 16u * ks, idesc, 1);        // weights hi x statistics lo
                 }
                 umma_commit(&bars->s_full[b1]);
-                umma_commit(&bars->a_empty[ra.pos]);          // img1 tile free: its loader runs ahead of the epilogue
+                umma_commit(&bars->a_empty[ra.pos]);          // img1 tiles free: their loader runs ahead of the epilogue
                 trace(a.trace, i, 2);
                 ra.next();
-                if (++b1 == NSB) b1 = 0;
-                (void)ph1;
             };
             auto issue_g2 = [&](int i) {
                 const int grp = i / DR, dbuf = grp & 1;
@@ -740,10 +753,10 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
                 for (int i = 0; i < n_tiles; ++i) issue_g2(i);
             } else {
                 issue_g1(0);
-                if (n_tiles > 1) issue_g1(1);
-                for (int i = 0; i < n_tiles; ++i) {
-                    if (i + 2 < n_tiles) issue_g1(i + 2);
-                    issue_g2(i);
+                for (int i = 0; i < n_tiles; i += 2) {
+                    if (i + 2 < n_tiles) issue_g1(i + 2);     // (overwrites the buffers of the pair before this one:
+                    issue_g2(i);                              //  their second MMAs were issued an iteration ago)
+                    if (i + 1 < n_tiles) issue_g2(i + 1);
                 }
             }
         }
@@ -803,7 +816,7 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
             mbar_wait(&bars->b_full[rb.pos], rb.phase);          // the llh / posterior blocks of the tile (TMA)
             if (tid == 0) trace(a.trace, i, 5);
             if constexpr (SINGLE) mbar_wait(&bars->a2_empty[b], phs ^ 1);     // the MMA of the tile three back has read the buffer
-            else mbar_wait(&bars->s_full[b], phs);
+            else mbar_wait(&bars->s_full[b & ~1], phs);          // (one completion per pair of tiles)
             if (tid == 0) trace(a.trace, i, 6);
             tc_fence_after();
             const float* raw = reinterpret_cast<const float*>(ring_b + (size_t)rb.pos * STAGE_B + STAGE_A);
@@ -1021,7 +1034,7 @@ static int launch_kc(const KcArgs& a0, const float* llh2, int64_t ld_llh, const 
     a.na = C == 1 ? 0 : 4;
     a.nb = RING_MAX;
     while (a.nb > 2 && kc_smem(KP, C, REL, a.na, a.nb) > 227 * 1024) --a.nb;
-    while (C != 1 && a.na > 2 && kc_smem(KP, C, REL, a.na, a.nb) > 227 * 1024) --a.na;
+    while (C != 1 && a.na > 2 && kc_smem(KP, C, REL, a.na, a.nb) > 227 * 1024) a.na -= 2;     // (pairs of tiles)
     const size_t smem = kc_smem(KP, C, REL, a.na, a.nb);
     if (smem > 227 * 1024) return BEER_ERR_UNSUPPORTED;
     CUtensorMap m1, m2;
