@@ -8,8 +8,13 @@
 //   chain_off [n_utts + 1], and per state: pdf id, ln a(j,j), ln a(j,j+1) (last state: the final weight)
 //
 // One warp per utterance, lane l owns states l*S .. l*S+S-1 in registers; the only exchange between
-// lanes is the neighbour's edge state (one shuffle per frame and direction) and the per-frame
-// normaliser (one redux).  log2 domain, renormalised every frame, like the other scan kernels.
+// lanes is the neighbour's edge state (one shuffle per frame and direction).  log2 domain; every LANE keeps its values
+// relative to its own integer offset (value = v + off, off an int32, re-based every frame so that the
+// lane's maximum is in [0, 1)): a chain moves its probability mass along the states like a wave, and a state on the
+// best path can sit hundreds of bits below the frame's maximum in alpha AND in beta -- relative to a per-FRAME
+// maximum its fp32 log value then carries 2^-24 x that distance (3e-5 on posteriors with i.i.d.-noise llhs on a
+// 300-state chain); relative to its lane's maximum it is within S states of a value near zero.  Offsets are integers,
+// so differences of offsets are exact.
 // S (4, 8, 16 or 32 states per lane) is picked PER UTTERANCE from its chain length: the batch is launched once per
 // class and a warp skips the utterances of the other classes (a batch-wide S = 16 for one long chain cost every
 // utterance 168 registers).  Rows in shared memory and in the alpha workspace are stored chunk-major (16-byte
@@ -37,7 +42,7 @@ struct ChainArgs {
     const float* lself;
     const float* lnext;
     const float* linit;      // [n_utts] ln weight of entering state 0
-    float* la_ws;            // [N, Kw]
+    float* la_ws;            // [N, Kw + 32]: lane-relative log2 alphas | the 32 lane offsets of the row
     int Kw;
     float* state_post;       // [N, Kw] or null (row stride Kw: chains differ in length)
     float* pdf_post;         // [N, ld_post], zeroed by the caller
@@ -64,8 +69,10 @@ __global__ void __launch_bounds__(CH_WARPS * 32) hmm_fb_chain_kernel(ChainArgs a
     constexpr int ROW = 32 * S;
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* ring_p = smem + (size_t)warp * (2 * PF * ROW);
+    float* ring_p = smem + (size_t)warp * (2 * PF * ROW + PF * 32);
     float* ring_a = ring_p + PF * ROW;
+    float* ring_o = ring_a + PF * ROW;             // [PF][32] lane offsets of the alpha rows
+    constexpr int kOffEmpty = -(1 << 29);          // offset of a lane without probability mass (differences of two never overflow)
     const float p_scale = a.scale * kLog2e;
     const int gwarp = blockIdx.x * CH_WARPS + warp, nwarps = gridDim.x * CH_WARPS;
 
@@ -93,10 +100,12 @@ __global__ void __launch_bounds__(CH_WARPS * 32) hmm_fb_chain_kernel(ChainArgs a
             w_in[j] = (k < L && k > 0) ? __ldg(a.lnext + c0 + k - 1) * kLog2e : kNegInf;
         }
         const bool own = lane * S < L;
-        for (int i = lane; i < 2 * PF * ROW; i += 32) ring_p[i] = 0.f;   // states past L stay finite
+        for (int i = lane; i < 2 * PF * ROW + PF * 32; i += 32) ring_p[i] = 0.f;   // states past L stay finite
         __syncwarp();
         const float* pl_u = a.pl + (size_t)t0 * a.ld;
-        float* la_u = a.la_ws + (size_t)t0 * a.Kw;
+        const int Kws = a.Kw + 32;                 // workspace row: alphas | lane offsets
+        float* la_u = a.la_ws + (size_t)t0 * Kws;
+        float* lo_u = la_u + a.Kw;
 
         auto gather = [&](float* slot, const float* row) {
             if (!own) return;
@@ -133,8 +142,7 @@ __global__ void __launch_bounds__(CH_WARPS * 32) hmm_fb_chain_kernel(ChainArgs a
             cp_async_commit();
         }
         float cur[S];
-        double logz2 = 0.0;
-        float lz = 0.f;
+        int off = kOffEmpty;
         int slot = 0;
         for (int t = 0; t < T; ++t) {
             cp_async_wait<PF - 1>();
@@ -144,13 +152,24 @@ __global__ void __launch_bounds__(CH_WARPS * 32) hmm_fb_chain_kernel(ChainArgs a
             if (t + PF < T) gather(ring_slot, pl_u + (size_t)(t + PF) * a.ld);
             cp_async_commit();
             slot = (slot + 1 == PF) ? 0 : slot + 1;
+            int base = kOffEmpty;                   // common offset of this lane's and its left neighbour's values
             if (t == 0) {
 #pragma unroll
                 for (int j = 0; j < S; ++j)
                     cur[j] = (lane == 0 && j == 0) ? fmaf(p[0], p_scale, __ldg(a.linit + u) * kLog2e) : kNegInf;
+                base = 0;
             } else {
                 float up = __shfl_up_sync(0xffffffffu, cur[S - 1], 1);
-                if (lane == 0) up = kNegInf;
+                int up_off = __shfl_up_sync(0xffffffffu, off, 1);
+                if (lane == 0) {
+                    up = kNegInf;
+                    up_off = kOffEmpty;
+                }
+                base = max(off, up_off);
+                const float sh = (float)(off - base);      // <= 0 (about -5e8 for an empty lane: -inf stays -inf)
+                up += (float)(up_off - base);
+#pragma unroll
+                for (int j = 0; j < S; ++j) cur[j] += sh;
 #pragma unroll
                 for (int j = S - 1; j >= 0; --j) {
                     const float prev = (j == 0) ? up : cur[j == 0 ? 0 : j - 1];
@@ -160,34 +179,36 @@ __global__ void __launch_bounds__(CH_WARPS * 32) hmm_fb_chain_kernel(ChainArgs a
             float mx = cur[0];
 #pragma unroll
             for (int j = 1; j < S; ++j) mx = fmaxf(mx, cur[j]);
-            mx = warp_max(mx);
-            const float mxs = (mx == kNegInf) ? 0.f : mx;
-            lz += mxs;
-            if ((t & 15) == 15) {
-                logz2 += (double)lz;
-                lz = 0.f;
-            }
+            if (mx == kNegInf) {
+                off = kOffEmpty;
+            } else {
+                const int r = __float2int_rd(mx);
+                const float rf = (float)r;
 #pragma unroll
-            for (int j = 0; j < S; ++j) cur[j] -= mxs;
-            write_row(la_u + (size_t)t * a.Kw, cur, false);
+                for (int j = 0; j < S; ++j) cur[j] -= rf;
+                off = base + r;
+            }
+            write_row(la_u + (size_t)t * Kws, cur, false);
+            lo_u[(size_t)t * Kws + lane] = __int_as_float(off);
         }
         cp_async_wait<0>();
-        logz2 += (double)lz;
         // final weight: the "next" arc of the last state
         float b_start[S];
 #pragma unroll
         for (int j = 0; j < S; ++j)
             b_start[j] = (lane * S + j == L - 1) ? __ldg(a.lnext + c0 + L - 1) * kLog2e : kNegInf;
         if (a.utt_logz != nullptr) {
-            float m = kNegInf;
+            // the chain ends in its last state: log Z = its alpha + the final weight
+            double z = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < S; ++j) m = fmaxf(m, cur[j] + b_start[j]);
-            m = warp_max(m);      // a single state carries it
+            for (int j = 0; j < S; ++j)
+                if (lane * S + j == L - 1) z = (double)cur[j] + (double)off + (double)b_start[j];
+            for (int o = 16; o > 0; o >>= 1) z = fmax(z, __shfl_xor_sync(0xffffffffu, z, o));
             double rs = 0.0;
             if (a.frame_ref != nullptr)
                 for (int t = lane; t < T; t += 32) rs += (double)a.frame_ref[t0 + t];
             rs = warp_sum(rs);
-            if (lane == 0) a.utt_logz[u] = (logz2 + (double)m) * (double)kLn2 + (double)a.scale * rs;
+            if (lane == 0) a.utt_logz[u] = z * (double)kLn2 + (double)a.scale * rs;
         }
 
         // ------------------------------ backward -----------------------------
@@ -197,19 +218,17 @@ __global__ void __launch_bounds__(CH_WARPS * 32) hmm_fb_chain_kernel(ChainArgs a
             const int t = T - 1 - r;
             if (t >= 0) {
                 gather(ring_p + r * ROW, pl_u + (size_t)t * a.ld);
-                copy_row(ring_a + r * ROW, la_u + (size_t)t * a.Kw);
+                copy_row(ring_a + r * ROW, la_u + (size_t)t * Kws);
+                cp_async4(ring_o + r * 32 + lane, lo_u + (size_t)t * Kws + lane);
             }
             cp_async_commit();
         }
         float lb[S];
-        {
-            float m = kNegInf;
+        int boff = kOffEmpty;                         // lane offset of the betas
 #pragma unroll
-            for (int j = 0; j < S; ++j) m = fmaxf(m, b_start[j]);
-            m = warp_max(m);
-            const float ms = (m == kNegInf) ? 0.f : m;
-#pragma unroll
-            for (int j = 0; j < S; ++j) lb[j] = b_start[j] - ms;
+        for (int j = 0; j < S; ++j) {
+            lb[j] = b_start[j];
+            if (lane * S + j == L - 1) boff = 0;
         }
         float ell = 0.f;
         double ell_d = 0.0;
@@ -220,17 +239,23 @@ __global__ void __launch_bounds__(CH_WARPS * 32) hmm_fb_chain_kernel(ChainArgs a
             float p[S], la[S];
             read_row(ring_p + slot * ROW, p);
             read_row(ring_a + slot * ROW, la);
+            const int aoff = __float_as_int(ring_o[slot * 32 + lane]);
             if (t - PF >= 0) {
                 gather(ring_p + slot * ROW, pl_u + (size_t)(t - PF) * a.ld);
-                copy_row(ring_a + slot * ROW, la_u + (size_t)(t - PF) * a.Kw);
+                copy_row(ring_a + slot * ROW, la_u + (size_t)(t - PF) * Kws);
+                cp_async4(ring_o + slot * 32 + lane, lo_u + (size_t)(t - PF) * Kws + lane);
             }
             cp_async_commit();
             slot = (slot + 1 == PF) ? 0 : slot + 1;
 
+            // posteriors: alpha + beta of a state = (la + lb) + (aoff + boff); the lanes' integer totals relative to
+            // the largest one (exact), so that the states that matter stay near zero
+            const int tot = aoff + boff;
+            const float dl = (float)(tot - __reduce_max_sync(0xffffffffu, tot));
             float v[S], m = kNegInf;
 #pragma unroll
             for (int j = 0; j < S; ++j) {
-                v[j] = (lane * S + j < L) ? la[j] + lb[j] : kNegInf;
+                v[j] = (lane * S + j < L) ? (la[j] + lb[j]) + dl : kNegInf;
                 m = fmaxf(m, v[j]);
             }
             m = warp_max(m);
@@ -273,7 +298,16 @@ __global__ void __launch_bounds__(CH_WARPS * 32) hmm_fb_chain_kernel(ChainArgs a
 #pragma unroll
             for (int j = 0; j < S; ++j) delta[j] = fmaf(p[j], p_scale, lb[j]);
             float dn = __shfl_down_sync(0xffffffffu, delta[0] + w_in[0], 1);   // into the next lane's first state
-            if (lane == 31) dn = kNegInf;
+            int dn_off = __shfl_down_sync(0xffffffffu, boff, 1);
+            if (lane == 31) {
+                dn = kNegInf;
+                dn_off = kOffEmpty;
+            }
+            const int base = max(boff, dn_off);
+            const float sh = (float)(boff - base);
+            dn += (float)(dn_off - base);
+#pragma unroll
+            for (int j = 0; j < S; ++j) delta[j] += sh;
             float mb = kNegInf;
 #pragma unroll
             for (int j = 0; j < S; ++j) {
@@ -281,10 +315,15 @@ __global__ void __launch_bounds__(CH_WARPS * 32) hmm_fb_chain_kernel(ChainArgs a
                 lb[j] = lse2c(delta[j] + w_self[j], nxt);
                 mb = fmaxf(mb, lb[j]);
             }
-            mb = warp_max(mb);
-            const float mbs = (mb == kNegInf) ? 0.f : mb;
+            if (mb == kNegInf) {
+                boff = kOffEmpty;
+            } else {
+                const int r = __float2int_rd(mb);
+                const float rf = (float)r;
 #pragma unroll
-            for (int j = 0; j < S; ++j) lb[j] -= mbs;
+                for (int j = 0; j < S; ++j) lb[j] -= rf;
+                boff = base + r;
+            }
         }
         cp_async_wait<0>();
         ell_d += (double)ell;
@@ -301,7 +340,7 @@ __global__ void __launch_bounds__(CH_WARPS * 32) hmm_fb_chain_kernel(ChainArgs a
 template <int S>
 int launch_chain(const ChainArgs& a, cudaStream_t st) {
     constexpr int PF = (S <= 4) ? 6 : (S <= 8 ? 4 : 3);
-    const size_t smem = sizeof(float) * (size_t)CH_WARPS * (2 * PF * 32 * S);
+    const size_t smem = sizeof(float) * (size_t)CH_WARPS * (2 * PF * 32 * S + PF * 32);
     static bool attr_set = false;
     if (!attr_set) {
         BEER_CUDA_TRY(cudaFuncSetAttribute(hmm_fb_chain_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -331,7 +370,7 @@ int beer_hmm_chain_row_stride(int max_chain_len) {
 
 int64_t beer_hmm_chain_workspace_bytes(int max_chain_len, int64_t N) {
     const int s = chain_S(max_chain_len);
-    return s ? (int64_t)N * 32 * s * (int64_t)sizeof(float) : BEER_ERR_UNSUPPORTED;
+    return s ? (int64_t)N * (32 * s + 32) * (int64_t)sizeof(float) : BEER_ERR_UNSUPPORTED;     // alpha rows + lane offsets
 }
 
 int beer_hmm_forward_backward_chains(const float* pdf_llh, int64_t ld_pdf, const float* frame_ref, const int64_t* utt_off,

@@ -55,9 +55,10 @@ def random_chain(rng, L, Kp):
 
 @pytest.mark.parametrize('scale,aligned', [(1.0, True), (0.6, True), (1.0, False)])
 def test_chain_forward_backward_matches_oracle(scale, aligned):
-    """`aligned`: the llhs favour one monotone path through every chain (what aligned training sees): 1e-5.
-    Otherwise they are i.i.d. noise of 6 nats per (frame, pdf): the prefix-best and the globally best paths then
-    differ by hundreds of nats, fp32 log values carry 2^-23 of that regret, and the bound is 1e-4."""
+    """`aligned`: the llhs favour one monotone path through every chain (what aligned training sees).  Otherwise they
+    are i.i.d. noise of 6 nats per (frame, pdf): the prefix-best and the globally best paths then differ by hundreds of
+    nats; log values relative to a per-FRAME maximum carried 2^-23 of that regret (3e-5 on posteriors), the per-lane
+    integer offsets of the kernel keep both cases inside 1e-5."""
     from beer_b200 import ops
     ops.require_cuda()
     rng = np.random.default_rng(3)
@@ -74,7 +75,7 @@ def test_chain_forward_backward_matches_oracle(scale, aligned):
         for u, ((L, T), gr) in enumerate(zip(shapes, graphs)):
             states = np.minimum(np.arange(T) * L // T, L - 1)
             llh[off[u] + np.arange(T), gr[3][states]] += 25.0
-    tol = 1e-5 if aligned else 1e-4
+    tol = 1e-5
     chains = ops.ChainBatch(graphs, DEV)
     assert chains.max_len == 300 and chains.row_stride == 512
     r = ops.hmm_forward_backward_chains(chains, torch.as_tensor(llh, dtype=torch.float32, device=DEV),
