@@ -209,12 +209,14 @@ extern "C" int beer_emission_llh(const float* X, int64_t N, int D, const float* 
         if (n_gtiles < 0) return BEER_ERR_ARG;
     }
     size_t smem = sizeof(float) * ((size_t)2 * D * KA_G + (size_t)2 * D * KA_AS_LD + KA_FR * KA_CS_LD + KA_G + D + 1);
-    if (smem > 110 * 1024) return BEER_ERR_UNSUPPORTED;  // D too large for this tiling
-    static bool attr_set = false;
-    if (!attr_set) {
+    // two blocks per SM up to D = 50; wider frames (a 64-d latent space: BASELINE configs[3]) run one block per SM
+    if (smem > 227 * 1024) return BEER_ERR_UNSUPPORTED;  // D too large for this tiling
+    static size_t attr_set = 0;
+    if (smem > attr_set) {       // (the kernel has static shared memory too: ask for what is needed, not for the maximum)
+        const size_t want = smem > 110 * 1024 ? smem : 110 * 1024;
         BEER_CUDA_TRY(cudaFuncSetAttribute(emission_llh_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           110 * 1024));
-        attr_set = true;
+                                           (int)want));
+        attr_set = want;
     }
     int64_t n_ftiles = (N + KA_FR - 1) / KA_FR;
     int64_t per_g = (2 * kNumSMs + n_gtiles - 1) / n_gtiles;

@@ -104,19 +104,28 @@ class VAE(Model):
             # the reference averages the prior's STATISTICS over the samples (vae.py:73-75); the kernels of the prior
             # take frames, not free-form statistics
             raise NotImplementedError('the latent prior runs on one sample per frame (nsamples = 1, the default)')
+        # a ragged batch of utterances (`Utterances`): the networks see all frames at once, the prior runs every
+        # utterance as its own sequence (one launch per kernel); the value is then the per-frame vector [N]
+        from .engine import Utterances
+        utts = data if isinstance(data, Utterances) else None
+        if utts is not None:
+            data = utts.X
         posts = self.posteriors(data)
         samples = posts.sample(nsamples)
         s_samples = posts.sufficient_statistics(samples).mean(dim=1)
         ent = -posts(s_samples, pdfwise=True)
         z = samples.view(-1, samples.shape[-1])
-        prior_stats = self.prior.sufficient_statistics(z)      # carries z: the prior's kernels read the frames
+        # (carries z: the prior's kernels read the frames)
+        prior_stats = self.prior.sufficient_statistics(z if utts is None else Utterances(z, utts.lengths))
         self.cache['prior_stats'] = prior_stats
-        xent = -self.prior.expected_log_likelihood(prior_stats).to(ent.dtype)
+        xent = -self.prior.expected_log_likelihood(prior_stats, **kwargs).to(ent.dtype)
         local_kl_div = xent - ent
         pdfs = self.pdfs(z)
         r_data = data[:, None, :].repeat(1, nsamples, 1).view(-1, data.shape[-1])
         llh = pdfs(pdfs.sufficient_statistics(r_data), pdfwise=True)
         llh = llh.reshape(len(data), nsamples, -1).mean(dim=1)
+        if utts is not None:
+            return llh_weight * llh.reshape(-1) - kl_weight * local_kl_div
         return llh_weight * llh - kl_weight * local_kl_div
 
     def accumulate(self, stats, parent_msg=None):

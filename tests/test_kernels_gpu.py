@@ -105,6 +105,20 @@ def test_emission_llh_normalset(ops, name):
     assert np.abs(d_got - d_ref)[near].max() < 3e-5
 
 
+def test_emission_llh_wide_frames(ops):
+    """A 64-d latent space (BASELINE configs[3], the HMM prior of an HMM-VAE): no tcgen05 emission tile for it, the
+    SIMT kernel runs it with one block per SM.  Against the fp64 restatement of normalgamma.py:118-146 + :55-59."""
+    rng = np.random.default_rng(5)
+    M, D, N = 100, 64, 333
+    post = (rng.standard_normal((M, D)), rng.uniform(0.5, 3, (M, 1)), rng.uniform(1, 5, (M, 1)), rng.uniform(0.3, 2, (M, D)))
+    X = 2.0 * rng.standard_normal((N, D))
+    pdf_llh, _, fref = _emission(ops, X, post)
+    f32 = lambda a: a.astype(np.float32).astype(np.float64)          # the values the kernel is handed
+    want = O.emission_llh(f32(X), tuple(f32(t) for t in post))[0]
+    got = pdf_llh.double().cpu().numpy() + fref.double().cpu().numpy()[:, None]
+    np.testing.assert_allclose(got, want, rtol=0, atol=2e-6 * np.abs(want).max())
+
+
 def _fb_case(ops, llh, gr, scale=1.0, factorize=True, **kw):
     plan = ops.GraphPlan(*gr, factorize=factorize)
     T = llh.shape[0]
