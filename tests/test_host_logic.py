@@ -225,7 +225,7 @@ def test_chain_batch_host_logic():
     np.testing.assert_array_equal(cb.pdf.numpy(), [4, 5, 4, 2])
     np.testing.assert_allclose(cb.log_self.numpy(), np.log([.75, .75, .75, .5]), rtol=1e-6)
     np.testing.assert_allclose(cb.log_next.numpy(), np.log([.25, .25, .25, .5]), rtol=1e-6)
-    assert cb.workspace_bytes(10) == 10 * 128 * 4
+    assert cb.workspace_bytes(10) == 10 * (128 + 32) * 4         # alpha rows + the 32 lane offsets of every row
     # chains of sampled paths: unit instances in visiting order, re-entry of the same unit is a new instance
     paths = np.array([[0, 0, 1, 1, 0, 1, 2, 3, 3, 2]])           # 2-state units: u0, u0 again, u1, u1 again
     off, pdf, ls, ln, li = synthetic.alignment_chains(paths, 2)
