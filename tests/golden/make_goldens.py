@@ -726,6 +726,24 @@ def gold_cli_files():
                                                                    hyper_prior_strength=1.)), f)
     expected['ali_elbo_1'] = run(s0, os.path.join(out, 'ploop_sbhp_ali_1.mdl'), ['utt_a', 'utt_b', 'utt_c'],
                                  alis=os.path.join(OUT, 'alis.npz'), scale=0.8, lrate=0.5)
+    # `beer hmm decode` (decode.py:41-87) of the trained model: decoding graph, per-frame, and on the alignment graphs
+    from beer.cli.subcommands.hmm import decode
+    import contextlib
+
+    def run_decode(model, **kw):
+        buf = io.StringIO()
+        ns = argparse.Namespace(alis=None, per_frame=False, acoustic_scale=1., utts=None, model=model,
+                                dataset=os.path.join(out, 'dataset.pkl'))
+        ns.__dict__.update(kw)
+        with contextlib.redirect_stdout(buf):
+            decode.main(ns, log)
+        return buf.getvalue()
+
+    m2 = os.path.join(out, 'ploop_2.mdl')
+    with open(os.path.join(out, 'decode_ploop_2.txt'), 'w') as f:
+        f.write(run_decode(m2))
+    with open(os.path.join(out, 'decode_ploop_2_per_frame_scale.txt'), 'w') as f:
+        f.write(run_decode(m2, per_frame=True, acoustic_scale=0.5))
     np.savez(os.path.join(out, 'expected.npz'), **{k: np.float64(v) for k, v in expected.items()})
     for fn in sorted(os.listdir(out)):
         print(f'cli/{fn}: {os.path.getsize(os.path.join(out, fn)) / 1024:.1f} KiB')

@@ -60,3 +60,25 @@ def test_aligned_training_with_the_cli_default_unit_prior(tmp_path, capsys):
     np.testing.assert_allclose(logged, [want['ali_elbo_1']], atol=2e-3)
     assert 'utt_missing' in cap.err
     _compare(out, os.path.join(CLI, 'ploop_sbhp_ali_1.mdl'), rtol=5e-4)
+
+
+def test_decode_matches_the_reference_cli(tmp_path):
+    """`python -m beer_b200.hmm_decode` == `beer hmm decode` (decode.py:41-87) of the same pickled model: the unit
+    sequences, and with --per-frame every frame's unit (alignments bit-exact), also under an acoustic scale."""
+    import io
+    from beer_b200 import hmm_decode
+    model, data = os.path.join(CLI, 'ploop_2.mdl'), os.path.join(CLI, 'dataset.pkl')
+    buf = io.StringIO()
+    assert hmm_decode.main([model, data], out=buf) == 0
+    with open(os.path.join(CLI, 'decode_ploop_2.txt')) as f:
+        assert buf.getvalue() == f.read()
+    buf = io.StringIO()
+    assert hmm_decode.main(['--per-frame', '-s', '0.5', model, data], out=buf) == 0
+    with open(os.path.join(CLI, 'decode_ploop_2_per_frame_scale.txt')) as f:
+        assert buf.getvalue() == f.read()
+    # on the alignment graphs the units are the aligned sequences themselves (make_goldens.py gold_alignment_archive)
+    ids = tmp_path / 'utts'
+    ids.write_text('utt_c\nutt_a\nutt_b\n')
+    buf = io.StringIO()
+    assert hmm_decode.main(['-a', os.path.join(HERE, 'golden', 'alis.npz'), '-u', str(ids), model, data], out=buf) == 0
+    assert buf.getvalue() == 'utt_c u3 u3 u0 u2\nutt_a u2 u0\nutt_b u1\n'
