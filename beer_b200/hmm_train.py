@@ -185,7 +185,10 @@ def _read_uttids(args, dataset):
         with open(args.uttids) as f:
             lines = f.readlines()
     elif not sys.stdin.isatty() and int(os.environ.get('WORLD_SIZE', '1')) == 1:
-        lines = sys.stdin.readlines()          # as `beer hmm accumulate`: one utterance id per line
+        try:
+            lines = sys.stdin.readlines()      # as `beer hmm accumulate`: one utterance id per line
+        except OSError:                        # (no usable stdin, e.g. under a test runner: the whole data set)
+            lines = []
     else:
         lines = []
     ids = [line.strip().split()[0] for line in lines if line.strip()]

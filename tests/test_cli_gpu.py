@@ -82,3 +82,30 @@ def test_decode_matches_the_reference_cli(tmp_path):
     buf = io.StringIO()
     assert hmm_decode.main(['-a', os.path.join(HERE, 'golden', 'alis.npz'), '-u', str(ids), model, data], out=buf) == 0
     assert buf.getvalue() == 'utt_c u3 u3 u0 u2\nutt_a u2 u0\nutt_b u1\n'
+
+
+def test_training_command_on_the_tensor_core_kernels(tmp_path, capsys):
+    """The same file-level check at a shape the tcgen05 kernels take (40-d features, 48 states x 8 Gaussians: fp16-split
+    emission, forward-backward with fused unit counts and relative log-posteriors, statistics with the responsibilities
+    recomputed on chip): two epochs against accumulate + update of the live reference replayed in float64 on the same
+    pickled files (make_goldens.py gold_cli_files_tc)."""
+    from beer_b200 import hmm_train, refpickle
+    tc = os.path.join(HERE, 'golden', 'cli_tc')
+    out = str(tmp_path / 'ploop_2.mdl')
+    assert hmm_train.main(['-e', '2', os.path.join(tc, 'ploop_0.mdl'), os.path.join(tc, 'dataset.pkl'), out]) == 0
+    want = np.load(os.path.join(tc, 'expected.npz'))
+    logged = [float(line.split('=')[1]) for line in capsys.readouterr().out.splitlines() if 'ELBO=' in line]
+    np.testing.assert_allclose(logged, [want['elbo_1'], want['elbo_2']], rtol=1e-5, atol=6e-4)      # (logged with 3 decimals)
+    v = refpickle.ModelView(refpickle.load(out))
+    assert [(g['n_pdfs'], g['n_comp']) for g in v.groups] == [(48, 8)]
+    mean, scale, shape, rates = (t.double().numpy() for t in v.normal_gamma(v.groups[0]['normal'], 'posterior'))
+    for got, key in ((mean, 'post_mean'), (scale, 'post_scale'), (shape, 'post_shape'), (rates, 'post_rates')):
+        w = want[key].reshape(got.shape)
+        assert np.abs(got - w).max() <= 2e-4 * np.abs(w).max(), (key, np.abs(got - w).max(), np.abs(w).max())
+    mix = v.concentrations(v.groups[0]['weights'], 'posterior').double().numpy()
+    assert np.abs(mix - want['mix_conc']).max() <= 2e-4 * np.abs(want['mix_conc']).max()
+    unit = v.concentrations(v.categorical._modules['weights'], 'posterior').double().numpy()
+    assert np.abs(unit - want['unit_conc']).max() <= 2e-4 * np.abs(want['unit_conc']).max()
+    trans = v.graph_arrays()[2].double().numpy()
+    fin = np.isfinite(want['trans'])
+    assert (np.isfinite(trans) == fin).all() and np.abs(trans[fin] - want['trans'][fin]).max() <= 2e-4
