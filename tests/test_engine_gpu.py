@@ -244,8 +244,9 @@ def test_vb_iterations_cfg2_shape(chunk, use_graph, mix16, monkeypatch):
         np.testing.assert_allclose(g, w, rtol=2e-4, atol=2e-4)
 
 
-@pytest.mark.parametrize('chunk,mix16', [(None, False), (170, False), (None, True), (170, True)])
-def test_vb_iterations_streamed_mixture_kernels(chunk, mix16, monkeypatch):
+@pytest.mark.parametrize('chunk,mix16,scale', [(None, False, 1.0), (170, False, 1.0), (None, True, 1.0), (170, True, 1.0),
+                                               (None, True, 0.7), (170, False, 0.7)])
+def test_vb_iterations_streamed_mixture_kernels(chunk, mix16, scale, monkeypatch):
     """(mix16 = False: the 3xTF32 kernels that materialise the per-Gaussian llhs; True: the fp16-split kernels that keep
     them on chip, csrc/mix16.cu.)  M = 160 Gaussians (20 pdfs x 8) at D = 20: the emission kernel streams its weight image in chunks and stores the
     per-Gaussian llhs with TMA tensor stores, the statistics kernel runs its bulk-staged mixture variant; three VB
@@ -273,14 +274,14 @@ def test_vb_iterations_streamed_mixture_kernels(chunk, mix16, monkeypatch):
     assert em.use_tc and ops.accumulate_tc_supported(M, D) and em.use16 == mix16
     dprior, dpost = conc.double().cpu().numpy(), conc.double().cpu().numpy()
     N = sum(lens)
-    eng = VBEngine(em, plan, Utterances(X, lens), datasize=float(N), chunk_frames=chunk, distributed=False)
+    eng = VBEngine(em, plan, Utterances(X, lens), datasize=float(N), chunk_frames=chunk, distributed=False, scale=scale)
     assert (eng.mix16 is not None) == mix16
     ng_prior, ng_post = _host(prior), _host(post)
     og = (graph.init_log_probs.double().numpy(), graph.final_log_probs.double().numpy(),
           graph.trans_log_probs.double().numpy(), graph.pdf_id_mapping)
     utts = [u.double().cpu().numpy() for u in utts_dev]
     for it in range(3):
-        want, ng_post, dpost, info = O.vb_iteration_hmm(utts, ng_prior, ng_post, dprior, dpost, og)
+        want, ng_post, dpost, info = O.vb_iteration_hmm(utts, ng_prior, ng_post, dprior, dpost, og, scale=scale)
         got = float(eng.step().item())
         assert abs(got - want) <= 1e-5 * abs(want), (it, got, want)
         acc = eng.acc.cpu().numpy()

@@ -145,6 +145,12 @@ def test_forward_backward_accepts_log2_llhs():
     fin = torch.isfinite(lp_abs)
     assert ((lp_rel - (lp_abs - llh2))[fin]).abs().max().item() <= 2e-5
     assert torch.equal(torch.isfinite(lp_rel), fin)
+    # ... and under an acoustic scale (the eight-warp kernel keeps the llhs scaled: it divides the scale out again)
+    ops.hmm_forward_backward(plan, llh2, fref, off, want_pdf_post=False, out_pdf_lpost=lp_abs, llh_log2=True, scale=0.5)
+    ops.hmm_forward_backward(plan, llh2, fref, off, want_pdf_post=False, out_pdf_lpost=lp_rel, llh_log2=True, scale=0.5,
+                             lpost_relative=True)
+    fin = torch.isfinite(lp_abs)
+    assert ((lp_rel - (lp_abs - llh2))[fin]).abs().max().item() <= 2e-5
     lp3r = torch.empty_like(lp3)
     ops.hmm_forward_backward(p3, small, None, o3, want_pdf_post=False, out_pdf_lpost=lp3r, lpost_relative=True, scale=2.0)
     c3s = ops.hmm_forward_backward(p3, small, None, o3, scale=2.0)
