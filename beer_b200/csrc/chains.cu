@@ -44,6 +44,7 @@ struct ChainArgs {
     const float* linit;      // [n_utts] ln weight of entering state 0
     float* la_ws;            // [N, Kw + 32]: lane-relative log2 alphas | the 32 lane offsets of the row
     int Kw;
+    int kpad;                // ROWS variant: floats of one staged llh row (Kp rounded up to 4)
     float* state_post;       // [N, Kw] or null (row stride Kw: chains differ in length)
     float* pdf_post;         // [N, ld_post], zeroed by the caller
     int64_t ld_post;
@@ -62,15 +63,20 @@ __device__ __forceinline__ float lse2c(float a, float b) {
     return mx + lg2(1.f + ex2(d));
 }
 
-template <int S>
+// ROWS: the llh row of a frame is staged WHOLE in shared memory (coalesced 16-byte copies) and the states pick their pdf's
+// value from there; otherwise every state gathers its value from global memory by a 4-byte cp.async (rows too wide to
+// stage).  The gathers lean on the L1 cache -- with more resident blocks (less L1 next to their shared memory) the
+// kernel got slower, not faster.
+template <int S, bool ROWS>
 __global__ void __launch_bounds__(CH_WARPS * 32) hmm_fb_chain_kernel(ChainArgs a) {
     static_assert(S % 4 == 0, "vector rows");
     constexpr int PF = (S <= 4) ? 6 : (S <= 8 ? 4 : 3);
     constexpr int ROW = 32 * S;
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* ring_p = smem + (size_t)warp * (2 * PF * ROW + PF * 32);
-    float* ring_a = ring_p + PF * ROW;
+    const int PROW = ROWS ? a.kpad : ROW;          // floats of one llh slot
+    float* ring_p = smem + (size_t)warp * (PF * PROW + PF * ROW + PF * 32);
+    float* ring_a = ring_p + PF * PROW;
     float* ring_o = ring_a + PF * ROW;             // [PF][32] lane offsets of the alpha rows
     constexpr int kOffEmpty = -(1 << 29);          // offset of a lane without probability mass (differences of two never overflow)
     const float p_scale = a.scale * kLog2e;
@@ -100,7 +106,7 @@ __global__ void __launch_bounds__(CH_WARPS * 32) hmm_fb_chain_kernel(ChainArgs a
             w_in[j] = (k < L && k > 0) ? __ldg(a.lnext + c0 + k - 1) * kLog2e : kNegInf;
         }
         const bool own = lane * S < L;
-        for (int i = lane; i < 2 * PF * ROW + PF * 32; i += 32) ring_p[i] = 0.f;   // states past L stay finite
+        for (int i = lane; i < PF * PROW + PF * ROW + PF * 32; i += 32) ring_p[i] = 0.f;   // states past L stay finite
         __syncwarp();
         const float* pl_u = a.pl + (size_t)t0 * a.ld;
         const int Kws = a.Kw + 32;                 // workspace row: alphas | lane offsets
@@ -108,10 +114,27 @@ __global__ void __launch_bounds__(CH_WARPS * 32) hmm_fb_chain_kernel(ChainArgs a
         float* lo_u = la_u + a.Kw;
 
         auto gather = [&](float* slot, const float* row) {
+            if constexpr (ROWS) {
+                for (int c = lane; c < a.kpad / 4; c += 32) cp_async16(slot + 4 * c, row + 4 * c);
+                return;
+            }
             if (!own) return;
 #pragma unroll
             for (int j = 0; j < S; ++j)
                 if (lane * S + j < L) cp_async4(slot + ((j >> 2) * 32 + lane) * 4 + (j & 3), row + pdf[j]);
+        };
+        // the llhs of this lane's states from a landed slot
+        auto read_llh = [&](const float* slot, float* out) {
+            if constexpr (ROWS) {
+#pragma unroll
+                for (int j = 0; j < S; ++j) out[j] = (lane * S + j < L) ? slot[pdf[j]] : 0.f;
+            } else {
+#pragma unroll
+                for (int v = 0; v < S / 4; ++v) {
+                    const float4 q = reinterpret_cast<const float4*>(slot)[v * 32 + lane];
+                    out[4 * v] = q.x; out[4 * v + 1] = q.y; out[4 * v + 2] = q.z; out[4 * v + 3] = q.w;
+                }
+            }
         };
         auto copy_row = [&](float* slot, const float* row) {
             if (!own) return;
@@ -138,7 +161,7 @@ __global__ void __launch_bounds__(CH_WARPS * 32) hmm_fb_chain_kernel(ChainArgs a
 
         // ------------------------------ forward ------------------------------
         for (int r = 0; r < PF; ++r) {
-            if (r < T) gather(ring_p + r * ROW, pl_u + (size_t)r * a.ld);
+            if (r < T) gather(ring_p + r * PROW, pl_u + (size_t)r * a.ld);
             cp_async_commit();
         }
         float cur[S];
@@ -147,8 +170,9 @@ __global__ void __launch_bounds__(CH_WARPS * 32) hmm_fb_chain_kernel(ChainArgs a
         for (int t = 0; t < T; ++t) {
             cp_async_wait<PF - 1>();
             float p[S];
-            float* ring_slot = ring_p + slot * ROW;
-            read_row(ring_slot, p);
+            float* ring_slot = ring_p + slot * PROW;
+            read_llh(ring_slot, p);
+            if constexpr (ROWS) __syncwarp();      // every lane has read the slot before it is refilled
             if (t + PF < T) gather(ring_slot, pl_u + (size_t)(t + PF) * a.ld);
             cp_async_commit();
             slot = (slot + 1 == PF) ? 0 : slot + 1;
@@ -217,7 +241,7 @@ __global__ void __launch_bounds__(CH_WARPS * 32) hmm_fb_chain_kernel(ChainArgs a
         for (int r = 0; r < PF; ++r) {
             const int t = T - 1 - r;
             if (t >= 0) {
-                gather(ring_p + r * ROW, pl_u + (size_t)t * a.ld);
+                gather(ring_p + r * PROW, pl_u + (size_t)t * a.ld);
                 copy_row(ring_a + r * ROW, la_u + (size_t)t * Kws);
                 cp_async4(ring_o + r * 32 + lane, lo_u + (size_t)t * Kws + lane);
             }
@@ -237,11 +261,12 @@ __global__ void __launch_bounds__(CH_WARPS * 32) hmm_fb_chain_kernel(ChainArgs a
             const int t = T - 1 - i;
             cp_async_wait<PF - 1>();
             float p[S], la[S];
-            read_row(ring_p + slot * ROW, p);
+            read_llh(ring_p + slot * PROW, p);
             read_row(ring_a + slot * ROW, la);
             const int aoff = __float_as_int(ring_o[slot * 32 + lane]);
+            if constexpr (ROWS) __syncwarp();
             if (t - PF >= 0) {
-                gather(ring_p + slot * ROW, pl_u + (size_t)(t - PF) * a.ld);
+                gather(ring_p + slot * PROW, pl_u + (size_t)(t - PF) * a.ld);
                 copy_row(ring_a + slot * ROW, la_u + (size_t)(t - PF) * Kws);
                 cp_async4(ring_o + slot * 32 + lane, lo_u + (size_t)(t - PF) * Kws + lane);
             }
@@ -337,21 +362,29 @@ __global__ void __launch_bounds__(CH_WARPS * 32) hmm_fb_chain_kernel(ChainArgs a
     }
 }
 
-template <int S>
-int launch_chain(const ChainArgs& a, cudaStream_t st) {
+template <int S, bool ROWS>
+int launch_chain_v(const ChainArgs& a, cudaStream_t st) {
     constexpr int PF = (S <= 4) ? 6 : (S <= 8 ? 4 : 3);
-    const size_t smem = sizeof(float) * (size_t)CH_WARPS * (2 * PF * 32 * S + PF * 32);
-    static bool attr_set = false;
-    if (!attr_set) {
-        BEER_CUDA_TRY(cudaFuncSetAttribute(hmm_fb_chain_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    const size_t smem = sizeof(float) * (size_t)CH_WARPS * (PF * (ROWS ? a.kpad : 32 * S) + PF * 32 * S + PF * 32);
+    static size_t attr_set = 0;
+    if (smem > attr_set) {
+        BEER_CUDA_TRY(cudaFuncSetAttribute(hmm_fb_chain_kernel<S, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem));
-        attr_set = true;
+        attr_set = smem;
     }
     int blocks = (a.n_utts + CH_WARPS - 1) / CH_WARPS;
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-    hmm_fb_chain_kernel<S><<<blocks, CH_WARPS * 32, smem, st>>>(a);
+    hmm_fb_chain_kernel<S, ROWS><<<blocks, CH_WARPS * 32, smem, st>>>(a);
     BEER_LAUNCH_CHECK();
     return BEER_OK;
+}
+
+template <int S>
+int launch_chain(const ChainArgs& a, cudaStream_t st) {
+    // whole rows are staged when they are 16-byte aligned and no wider than the gathered slots would be x 2
+    // (Kp <= 64 S: a row of 100 pdfs for chains of 250 states is 400 B against 8 scattered 4-byte copies per lane)
+    const bool rows = a.kpad > 0 && a.kpad <= 64 * S && a.ld % 4 == 0 && ((uintptr_t)a.pl & 15) == 0;
+    return rows ? launch_chain_v<S, true>(a, st) : launch_chain_v<S, false>(a, st);
 }
 
 int chain_S(int max_len) { return chain_class(max_len); }
@@ -389,6 +422,7 @@ int beer_hmm_forward_backward_chains(const float* pdf_llh, int64_t ld_pdf, const
     a.pl = pdf_llh; a.ld = ld_pdf; a.frame_ref = frame_ref; a.utt_off = utt_off; a.n_utts = n_utts; a.scale = scale;
     a.chain_off = chain_off; a.pdf = chain_pdf; a.lself = chain_log_self; a.lnext = chain_log_next;
     a.linit = chain_log_init; a.la_ws = (float*)workspace; a.Kw = 32 * S; a.state_post = state_post;
+    a.kpad = (ld_pdf % 4 == 0 && ld_pdf <= 8192) ? (int)ld_pdf : 0;      // whole rows of ld_pdf floats are staged
     a.pdf_post = pdf_post; a.ld_post = ld_post; a.frame_exp_llh = frame_exp_llh; a.utt_exp_llh = utt_exp_llh;
     a.utt_logz = utt_logz;
     cudaStream_t st = (cudaStream_t)stream;

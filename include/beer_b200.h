@@ -200,7 +200,9 @@ BEER_API int beer_hmm_viterbi(const beer_graph_plan* plan, const float* pdf_llh,
  * chain_log_next = ln a(j,j+1) (last state: the final weight); chain_log_init [n_utts] = ln weight of entering state 0.
  * Outputs as beer_hmm_forward_backward, except: pdf_post must be ZEROED by the caller (scatter-add, a pdf may occur
  * several times in a chain) and state_post, if given, has row stride beer_hmm_chain_row_stride(max_chain_len).
- * max_chain_len <= 1024.  workspace: beer_hmm_chain_workspace_bytes(max_chain_len, N) bytes. */
+ * max_chain_len <= 1024.  workspace: beer_hmm_chain_workspace_bytes(max_chain_len, N) bytes.  pdf_llh is an [N, ld_pdf]
+ * allocation: when ld_pdf is a multiple of 4 (and the base 16-byte aligned) whole rows of ld_pdf floats are staged in
+ * shared memory, so the padding columns of a row, the last one included, must be readable. */
 BEER_API int beer_hmm_chain_row_stride(int max_chain_len);
 BEER_API int64_t beer_hmm_chain_workspace_bytes(int max_chain_len, int64_t N);
 BEER_API int beer_hmm_forward_backward_chains(const float* pdf_llh, int64_t ld_pdf, const float* frame_ref,
