@@ -58,9 +58,10 @@ __host__ __device__ __forceinline__ int chain_class(int len) {
 }
 
 __device__ __forceinline__ float lse2c(float a, float b) {
-    const float mx = fmaxf(a, b), mn = fminf(a, b);
-    const float d = fmaxf(mn - mx, -1000.f);
-    return mx + lg2(1.f + ex2(d));
+    // min - max = -|a - b|: one subtraction, |.| and the sign are operand modifiers of the clamp (NaN of -inf - -inf and
+    // -inf itself are absorbed by fmaxf)
+    const float d = fmaxf(-fabsf(a - b), -1000.f);
+    return fmaxf(a, b) + lg2(1.f + ex2(d));
 }
 
 // ROWS: the llh row of a frame is staged WHOLE in shared memory (coalesced 16-byte copies) and the states pick their pdf's

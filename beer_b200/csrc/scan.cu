@@ -597,9 +597,10 @@ __device__ __forceinline__ void load_lane_lists(LaneLists<S, JR>& L, const ScanL
 
 // log2-domain log(2^a + 2^b); -inf safe (NaN of -inf - -inf is absorbed by fmaxf)
 __device__ __forceinline__ float lse2(float a, float b) {
-    const float mx = fmaxf(a, b), mn = fminf(a, b);
-    const float d = fmaxf(mn - mx, -1000.f);
-    return mx + lg2(1.f + ex2(d));
+    // min - max = -|a - b|: one subtraction, |.| and the sign are operand modifiers of the clamp (NaN of -inf - -inf and
+    // -inf itself are absorbed by fmaxf)
+    const float d = fmaxf(-fabsf(a - b), -1000.f);
+    return fmaxf(a, b) + lg2(1.f + ex2(d));
 }
 
 // value of the junction from the published per-state values in buf
