@@ -295,12 +295,18 @@ class VBEngine:
             raise ValueError('the batched GMM mode needs one pdf whose number of components is a multiple of 32 '
                              '(D = 20 or 40); other mixtures go through the model API (Mixture)')
         self.chains = isinstance(plan, ops.ChainBatch)
+        # one GraphPlan per utterance (alignment graphs that are not plain chains, e.g. units with skip arcs: the
+        # forward-backward runs utterance by utterance, emission and statistics kernels stay batched)
+        self.per_utt = isinstance(plan, (list, tuple))
+        if self.per_utt and (len(plan) != utts.n_utts or self.viterbi):
+            raise ValueError('a list of graph plans needs one plan per utterance of the shard and runs forward-backward')
+        aligned = self.chains or self.per_utt
         if self.chains and (plan.n_utts != utts.n_utts or self.viterbi):
             raise ValueError('a ChainBatch needs one chain per utterance of the shard and runs forward-backward')
         # aligned training gives the unit weights ZERO statistics (phoneloop.py:98-100): with `unit_weights` their KL
         # still enters the ELBO and their posterior takes the natural-gradient step towards the prior, as in the reference
-        P = plan.n_units if (unit_weights is not None and not self.chains) else 0
-        if unit_weights is not None and P == 0 and not self.chains:
+        P = plan.n_units if (unit_weights is not None and not aligned) else 0
+        if unit_weights is not None and P == 0 and not aligned:
             raise ValueError('unit weights need an aligned left-to-right phone loop (see beer_hmm_forward_backward_units)')
         self.flat = torch.zeros(M * self.Q + P + 4, device=self.dev, dtype=f64)
         self.acc = self.flat[:M * self.Q].view(M, self.Q)
@@ -331,13 +337,13 @@ class VBEngine:
             self._copy_seq, self._pending = 0, None      # copies issued so far; staging buffer of the chunk in flight
         Kp = emission.Kp if not self.gmm else emission.M // emission.gmm_C
         self.pdf_llh = torch.empty(nmax, Kp, device=self.dev, dtype=f32)
-        self._nonident = not self.gmm and (self.chains or not (plan.info['map_identity'] and plan.n_states == Kp))
+        self._nonident = not self.gmm and (aligned or not (plan.info['map_identity'] and plan.n_states == Kp))
         self.pdf_post = (torch.zeros if self._nonident else torch.empty)(nmax, Kp, device=self.dev, dtype=f32)
         # mixtures through the fp16-split kernels (forward-backward over one graph plan): no per-Gaussian llhs at all,
         # `pdf_llh` holds log2 values; the feature images of resident chunks are built once, here
         self.mix16 = None
         # (Viterbi training of mixtures takes the fp16 emission kernel only; its statistics are sparse along the path)
-        if self.gmm or (emission.use16 and not self.chains and not (self.viterbi and emission.uniform_C == 1)):
+        if self.gmm or (emission.use16 and not aligned and not (self.viterbi and emission.uniform_C == 1)):
             self.mix16 = ops.Mix16(M, D, emission.gmm_C if self.gmm else emission.uniform_C, self.dev)
             self._images = [None] * len(self._chunks)
             if not self.host_mode:
@@ -348,7 +354,11 @@ class VBEngine:
         self.tensor_kind = 'f16' if self.mix16 is not None else 'tf32'
         self.comp_llh = (torch.empty(nmax, M, device=self.dev, dtype=f32)
                          if emission.has_mixtures and self.mix16 is None else None)
-        ws_bytes = plan.workspace_bytes(nmax) if not self.gmm else 4
+        if self.per_utt:
+            ws_bytes = max([p.workspace_bytes(int(t)) for p, t in zip(plan, utts.lengths)] + [4])
+            self._one_off = [torch.tensor([0, int(t)], dtype=i64, device=self.dev) for t in utts.lengths]
+        else:
+            ws_bytes = plan.workspace_bytes(nmax) if not self.gmm else 4
         if self.viterbi:
             ws_bytes = max(ws_bytes, nmax * plan.n_states * 2 + 4)      # uint16 back-pointers
             self._pdf_map = torch.as_tensor(np.asarray(plan.pdf_map), dtype=i32, device=self.dev)
@@ -467,6 +477,15 @@ class VBEngine:
                     # per-utterance sums of the per-frame expected llh (fp64 prefix sums, differences at the offsets)
                     cs = torch.cat([torch.zeros(1, dtype=f64, device=self.dev), frame.double().cumsum(0)])
                     self.utt_ell[u0:u1] = cs[rel[1:]] - cs[rel[:-1]]
+                elif self.per_utt:
+                    off_h = self.utts.offsets_host
+                    for i in range(u0, u1):
+                        a, b = int(off_h[i] - off_h[u0]), int(off_h[i + 1] - off_h[u0])
+                        if b > a:
+                            ops.hmm_forward_backward(plan[i], pdf_llh[a:b], fref[a:b], self._one_off[i], scale=self.scale,
+                                                     workspace=self.ws, out_pdf_post=pdf_post[a:b],
+                                                     out_utt_exp_llh=self.utt_ell[i:i + 1])
+                    self.gpu_launches += u1 - u0
                 elif self.chains:
                     ops.hmm_forward_backward_chains(plan, pdf_llh, fref, rel, scale=self.scale, first_utt=u0,
                                                     workspace=self.ws, out_pdf_post=pdf_post,
@@ -562,7 +581,7 @@ class VBEngine:
             # unit counts in the order of the weights -> Dirichlet statistics (last entry = total,
             # dirichlet.py:18-21) -> natural-gradient step -> rewrite the graph -> new device plan
             u = self.units
-            if self.chains:
+            if self.chains or self.per_utt:
                 counts = torch.zeros(len(u.start_idxs), device=self.dev, dtype=f64)
             else:
                 su = self.plan.n_states // self.unit_counts.numel()
@@ -570,7 +589,7 @@ class VBEngine:
                 counts = self.unit_counts[order]
             u.update(counts, stats_scale, self.lrate)
             u.rewrite_graph()
-            if not self.chains:
+            if not (self.chains or self.per_utt):
                 self.plan = u.graph.plan(n_pdfs=self.em.Kp)
             self.gpu_launches += 2
         return elbo

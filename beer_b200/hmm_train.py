@@ -13,7 +13,8 @@ Neither side needs the other installed (beer_b200/refpickle.py).
 
 Covered: HMM / PhoneLoop over NormalSet (diagonal) / MixtureSet / JointModelSet emissions; unit weights with a
 Dirichlet, stick-breaking or Gamma-stick-breaking prior (the CLI default); forward-backward over the decoding graph or
-over per-utterance alignment graphs.  Not covered (use the model API): BigramPhoneLoop, full covariances.
+over per-utterance alignment graphs (chains in one launch; any other alignment graph utterance by utterance).  Not
+covered (use the model API): BigramPhoneLoop, full covariances.
 """
 import argparse
 import os
@@ -238,7 +239,12 @@ def main(argv=None):
     X = torch.from_numpy(np.concatenate(feats) if feats else np.zeros((0, model.emission.D), np.float32))
     utts = Utterances(X, [lens[i] for i in mine], device=dev)
     if alis is not None:
-        plan = alis.chain_batch([ids[i] for i in mine], dev)
+        try:
+            plan = alis.chain_batch([ids[i] for i in mine], dev)       # all chains in one launch
+        except ValueError:
+            # alignment graphs that are not plain left-to-right chains (units with skip arcs, e.g. the silence model of
+            # recipes/timit_v2/conf_61phns/hmm_gmm/hmm.yml): one graph plan and one forward-backward launch per utterance
+            plan = [alis[ids[i]].plan(n_pdfs=model.n_pdfs) for i in mine]
     else:
         plan = model.graph.plan(n_pdfs=model.n_pdfs)
     engine = VBEngine(model.emission, plan, utts, datasize=float(dataset.size), scale=args.acoustic_scale,

@@ -726,6 +726,23 @@ def gold_cli_files():
                                                                    hyper_prior_strength=1.)), f)
     expected['ali_elbo_1'] = run(s0, os.path.join(out, 'ploop_sbhp_ali_1.mdl'), ['utt_a', 'utt_b', 'utt_c'],
                                  alis=os.path.join(OUT, 'alis.npz'), scale=0.8, lrate=0.5)
+    # alignment graphs that are NOT chains: units with a skip arc (first -> third state), as the silence model of
+    # recipes/timit_v2/conf_61phns/hmm_gmm/hmm.yml; accumulate --alis + update of the Dirichlet model on them
+    def skip_unit(first_pdf):
+        u = beer.graph.Graph()
+        st = [u.add_state(pdf_id=None)] + [u.add_state(pdf_id=first_pdf + i) for i in range(3)] + [u.add_state(pdf_id=None)]
+        u.start_state, u.end_state = st[0], st[-1]
+        u.add_arc(st[0], st[1], 1.0)
+        u.add_arc(st[1], st[1], 0.5); u.add_arc(st[1], st[2], 0.3); u.add_arc(st[1], st[3], 0.2)
+        u.add_arc(st[2], st[2], 0.6); u.add_arc(st[2], st[3], 0.4)
+        u.add_arc(st[3], st[3], 0.7); u.add_arc(st[3], st[4], 0.3)
+        return u
+
+    skip_units = {f'u{i}': skip_unit(3 * i) for i in range(4)}
+    skip_alis = {u: np.array([ali_graph(seq, skip_units)]) for u, seq in seqs.items()}
+    np.savez(os.path.join(out, 'alis_skip.npz'), **skip_alis)
+    expected['skipali_elbo_1'] = run(m0, os.path.join(out, 'ploop_skipali_1.mdl'), ['utt_a', 'utt_b', 'utt_c'],
+                                     alis=os.path.join(out, 'alis_skip.npz'), scale=1.0, lrate=1.0)
     # `beer hmm decode` (decode.py:41-87) of the trained model: decoding graph, per-frame, and on the alignment graphs
     from beer.cli.subcommands.hmm import decode
     import contextlib

@@ -191,3 +191,48 @@ def test_model_api_list_of_inference_graphs():
     for param in (ns1.means_precisions, ns2.means_precisions, ms1.categoricalset.weights, ms2.categoricalset.weights):
         w = want[param].cpu().numpy()
         assert np.abs(acc[param].cpu().numpy() - w).max() <= 2e-5 * max(np.abs(w).max(), 1.0)
+
+
+def skip_graph(rng, L, Kp):
+    """An alignment graph that is NOT a chain: left-to-right with skip arcs (the topology of the silence unit in
+    recipes/timit_v2/conf_61phns/hmm_gmm/hmm.yml:14-37)."""
+    trans = np.full((L, L), -np.inf)
+    for i in range(L):
+        nxt = [j for j in (i, i + 1, i + 2) if j < L]
+        w = rng.dirichlet(np.ones(len(nxt) + (1 if i == L - 1 else 0)))
+        trans[i, nxt] = np.log(w[:len(nxt)])
+    init = np.full(L, -np.inf)
+    init[0] = 0.0
+    final = np.full(L, -np.inf)
+    final[-1] = np.log(0.3)
+    return init, final, trans, rng.integers(0, Kp, L)
+
+
+def test_engine_runs_any_alignment_graph_utterance_by_utterance():
+    """Alignment graphs with skip arcs are no ChainBatch: the engine takes one graph plan per utterance (forward-backward
+    launched per utterance, emission / statistics kernels batched); two VB iterations against the oracle of
+    accumulate.py:47-57 with one inference graph per utterance."""
+    from beer_b200 import ops, synthetic
+    from beer_b200.engine import EmissionParams, Utterances, VBEngine
+    rng = np.random.default_rng(11)
+    Kp, D = 12, 8
+    lens = [40, 75, 23, 5]
+    graphs = [skip_graph(rng, L, Kp) for L in (7, 12, 5, 3)]
+    with pytest.raises(ValueError):
+        ops.ChainBatch(graphs, DEV)
+    X = torch.as_tensor(2.0 * rng.standard_normal((sum(lens), D)), dtype=torch.float32, device=DEV)
+    prior, post = synthetic.initial_normal_gamma(Kp, D, seed=2, device=DEV)
+    em = EmissionParams(prior, post)
+    plans = [ops.GraphPlan(*g, n_pdfs=Kp) for g in graphs]
+    eng = VBEngine(em, plans, Utterances(X, lens), datasize=1000.0, scale=0.9, distributed=False, chunk_frames=120)
+    host = lambda t: (t[0].double().cpu().numpy(), t[1].double().cpu().numpy()[:, None],
+                      t[2].double().cpu().numpy()[:, None], t[3].double().cpu().numpy())
+    ng_prior, ng_post = host(prior), host(post)
+    off = np.concatenate([[0], np.cumsum(lens)])
+    utts = [X[a:b].double().cpu().numpy() for a, b in zip(off[:-1], off[1:])]
+    for it in range(2):
+        want, ng_post, _, info = O.vb_iteration_hmm(utts, ng_prior, ng_post, None, None, None, datasize=1000.0, scale=0.9,
+                                                    graphs=graphs)
+        got = float(eng.step().item())
+        assert abs(got - want) <= 1e-5 * abs(want), (it, got, want)
+        assert np.abs(eng.acc.cpu().numpy() - info['acc_normal']).max() <= 3e-5 * np.abs(info['acc_normal']).max()

@@ -109,3 +109,18 @@ def test_training_command_on_the_tensor_core_kernels(tmp_path, capsys):
     trans = v.graph_arrays()[2].double().numpy()
     fin = np.isfinite(want['trans'])
     assert (np.isfinite(trans) == fin).all() and np.abs(trans[fin] - want['trans'][fin]).max() <= 2e-4
+
+
+def test_aligned_training_on_graphs_that_are_not_chains(tmp_path, capsys):
+    """Alignment graphs whose units have a skip arc (pickled by the live reference, gold_cli_files): no ChainBatch, the
+    command falls back to one graph plan per utterance; against the reference's own accumulate --alis + update."""
+    from beer_b200 import hmm_train
+    ids = tmp_path / 'utts'
+    ids.write_text('utt_a\nutt_b\nutt_c\n')
+    out = str(tmp_path / 'ploop_skipali.mdl')
+    assert hmm_train.main(['-a', os.path.join(CLI, 'alis_skip.npz'), '-u', str(ids), os.path.join(CLI, 'ploop_0.mdl'),
+                           os.path.join(CLI, 'dataset.pkl'), out]) == 0
+    want = np.load(os.path.join(CLI, 'expected.npz'))
+    logged = [float(line.split('=')[1]) for line in capsys.readouterr().out.splitlines() if 'ELBO=' in line]
+    np.testing.assert_allclose(logged, [want['skipali_elbo_1']], atol=2e-3)
+    _compare(out, os.path.join(CLI, 'ploop_skipali_1.mdl'), rtol=5e-4)
