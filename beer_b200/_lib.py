@@ -73,6 +73,14 @@ SIGNATURES = {
     'beer_hmm_forward_backward_ex': (C.c_int, [c_ptr, c_ptr, C.c_int64, c_ptr, c_ptr, C.c_int, C.c_float,
                                                c_ptr, c_ptr, C.c_int64, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr, C.c_int64, c_ptr, c_ptr]),
     'beer_hmm_lpost_supported': (C.c_int, [c_ptr]),
+    'beer_hmm_block_activity_supported': (C.c_int, [c_ptr, C.c_int]),
+    'beer_hmm_forward_backward_blocks': (C.c_int, [c_ptr, c_ptr, C.c_int64, c_ptr, c_ptr, C.c_int, C.c_float,
+                                                   c_ptr, c_ptr, C.c_int64, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr,
+                                                   C.c_int64, c_ptr, C.c_int64, C.c_int, c_ptr, c_ptr]),
+    'beer_mix16_weight_exponent': (C.c_int, [C.c_float]),
+    'beer_mix16_accumulate_blocks': (C.c_int, [c_ptr, c_ptr, C.c_int64, C.c_int, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int,
+                                               c_ptr, C.c_int64, c_ptr, C.c_int64, C.c_float, c_ptr, C.c_int64, c_ptr,
+                                               c_ptr]),
     'beer_mix16_gmm_posteriors': (C.c_int, [c_ptr, C.c_int64, C.c_int, C.c_int64, c_ptr, c_ptr, C.c_int, C.c_float, c_ptr,
                                             C.c_int64, c_ptr, c_ptr, c_ptr]),
     'beer_mix16_log2_posteriors': (C.c_int, [c_ptr, C.c_int64, C.c_int, C.c_int64, c_ptr, C.c_int64, c_ptr]),

@@ -549,6 +549,9 @@ struct KcArgs {
     double* acc;
     int D;
     unsigned long long* trace;
+    const uint8_t* block_active;   // [ceil(N / TILE), ld_active] or NULL: tiles of 64 frames in which this Gaussian tile's pdfs
+    int64_t ld_active;             // carry weight at all (beer_hmm_forward_backward_blocks); the others are skipped
+    int act_cap;                   // tiles per CTA (capacity of the list of active tiles in shared memory)
 };
 
 struct KcBarriers {
@@ -558,7 +561,7 @@ struct KcBarriers {
     uint64_t a2_empty[NSB];                           // single-Gaussian mode: the second MMA has read the A2 buffer
     uint64_t d2_full[2], d2_empty[2];
     uint32_t tmem_base;
-    uint32_t pad[1];
+    int n_act;                                        // active tiles of this CTA
 };
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -600,8 +603,13 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
     const int g0 = gtile * GM;
     const int64_t f_begin = (int64_t)(blockIdx.x / a.n_gtiles) * a.frames_per_cta;
     const int64_t f_end = min(a.N, f_begin + a.frames_per_cta);
-    const int n_tiles = (f_end > f_begin) ? (int)((f_end - f_begin + TILE - 1) / TILE) : 0;
+    const int n_all = (f_end > f_begin) ? (int)((f_end - f_begin + TILE - 1) / TILE) : 0;
     const int64_t tile0 = f_begin / TILE;
+    // the tiles this CTA works on: all of its range, or (activity map) those in which the pdfs of its Gaussian tile have
+    // posterior mass -- elsewhere the weights are zero in both fp16 halves and the tile adds exactly nothing
+    const bool sparse = !SINGLE && a.block_active != nullptr;
+    uint16_t* act = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(bars + 1));
+    auto tix = [&](int k) { return sparse ? (int)act[k] : k; };
 
     if (tid == 0) {
         for (int i = 0; i < RING_MAX; ++i) {
@@ -622,10 +630,25 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == KC_MMA_WARP) tmem_alloc(&bars->tmem_base, 512);
+    if (warp == 4) {
+        int count = n_all;
+        if (sparse) {
+            count = 0;
+            for (int base = 0; base < n_all; base += 32) {
+                const int t = base + lane;
+                const bool f = t < n_all && a.block_active[(size_t)(tile0 + t) * a.ld_active + gtile] != 0;
+                const uint32_t mask = __ballot_sync(0xffffffffu, f);
+                if (f) act[count + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)t;
+                count += __popc(mask);
+            }
+        }
+        if (lane == 0) bars->n_act = count;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    const int n_tiles = bars->n_act;
 
     // the packed weights of this Gaussian tile -> tensor memory (A operand of the first MMA), once
     if (!SINGLE && warp < 4) {
@@ -666,7 +689,7 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
                     mbar_arrive_expect_tx(&bars->a_full[rp.pos], (uint32_t)nt * bytes);
                     uint8_t* dst = ring_a + (size_t)rp.pos * (2 * STAGE_A);
                     for (int t = 0; t < nt; ++t) {
-                        const __half* src = a.img1 + (size_t)(tile0 + i + t) * (2 * IMG_HALF);
+                        const __half* src = a.img1 + (size_t)(tile0 + tix(i + t)) * (2 * IMG_HALF);
                         bulk_g2s(dst + (size_t)t * half_bytes, src, half_bytes, &bars->a_full[rp.pos]);
                         bulk_g2s(dst + (size_t)(2 + t) * half_bytes, src + IMG_HALF, half_bytes, &bars->a_full[rp.pos]);
                     }
@@ -674,12 +697,12 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
             }
             Ring r(a.nb);
             for (int i = 0; i < (which == 0 ? 0 : n_tiles); ++i, r.next()) {
-                const int t0 = (int)(f_begin + (int64_t)i * TILE);
+                const int t0 = (int)(f_begin + (int64_t)tix(i) * TILE);
                 mbar_wait_relaxed(&bars->b_empty[r.pos], r.phase ^ 1, 200);
                 uint8_t* dst = ring_b + (size_t)r.pos * STAGE_B;
                 if (which == 1) {
                     mbar_arrive_expect_tx(&bars->b_full[r.pos], bytes);
-                    bulk_g2s(dst, a.img2 + (size_t)(tile0 + i) * (2 * IMG_HALF), bytes, &bars->b_full[r.pos]);
+                    bulk_g2s(dst, a.img2 + (size_t)(tile0 + tix(i)) * (2 * IMG_HALF), bytes, &bars->b_full[r.pos]);
                 } else if (SINGLE || REL) {
                     mbar_arrive_expect_tx(&bars->b_full[r.pos], RAW_FLOATS * 4u);
                     tma_load_2d(dst + bytes, &map_lp, k0, t0, &bars->b_full[r.pos]);       // [64 frames x 128 posteriors]
@@ -820,7 +843,7 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
             if (tid == 0) trace(a.trace, i, 6);
             tc_fence_after();
             const float* raw = reinterpret_cast<const float*>(ring_b + (size_t)rb.pos * STAGE_B + STAGE_A);
-            const int n_left = (int)min((int64_t)TILE, f_end - (f_begin + (int64_t)i * TILE)) - half * 32;
+            const int n_left = (int)min((int64_t)TILE, f_end - (f_begin + (int64_t)tix(i) * TILE)) - half * 32;
             float ts[4] = {0.f, 0.f, 0.f, 0.f};
             // one block of 16 frames: w 2^wexp -> fp16 hi (the top 11 significant bits, by truncation: exact in fp16)
             // and lo = w - hi (exact in fp32, rounded to fp16), written back in place of S^T.  MASKED (the last tile of
@@ -934,9 +957,9 @@ mixstats16_kernel(KcArgs a, const __grid_constant__ CUtensorMap map_l2, const __
     }
 }
 
-static size_t kc_smem(int KP, int C, bool rel, int na, int nb) {
+static size_t kc_smem(int KP, int C, bool rel, int na, int nb, int act_cap = 0) {
     return (size_t)na * (2 * TILE * KP * 2) + (size_t)nb * (2 * TILE * KP * 2 + ((C == 1 || rel) ? 1 : 2) * TILE * (GM / C) * 4) +
-           sizeof(KcBarriers) + 1024;
+           sizeof(KcBarriers) + (size_t)act_cap * 2 + 16 + 1024;
 }
 
 // log2 of pdf posteriors (the forward-backward kernels that cannot write them themselves)
@@ -1033,9 +1056,10 @@ static int launch_kc(const KcArgs& a0, const float* llh2, int64_t ld_llh, const 
     // ring A (img1 tiles): 4 deep; ring B (img2 tile + llh / posterior blocks): whatever else fits
     a.na = C == 1 ? 0 : 4;
     a.nb = RING_MAX;
-    while (a.nb > 2 && kc_smem(KP, C, REL, a.na, a.nb) > 227 * 1024) --a.nb;
-    while (C != 1 && a.na > 2 && kc_smem(KP, C, REL, a.na, a.nb) > 227 * 1024) a.na -= 2;     // (pairs of tiles)
-    const size_t smem = kc_smem(KP, C, REL, a.na, a.nb);
+    const int cap = a.block_active != nullptr ? a.act_cap : 0;
+    while (a.nb > 2 && kc_smem(KP, C, REL, a.na, a.nb, cap) > 227 * 1024) --a.nb;
+    while (C != 1 && a.na > 2 && kc_smem(KP, C, REL, a.na, a.nb, cap) > 227 * 1024) a.na -= 2;     // (pairs of tiles)
+    const size_t smem = kc_smem(KP, C, REL, a.na, a.nb, cap);
     if (smem > 227 * 1024) return BEER_ERR_UNSUPPORTED;
     CUtensorMap m1, m2;
     int rc = encode_rows(&m1, llh2, a.N, a.Kp, ld_llh, GM / C, TILE);
@@ -1186,9 +1210,24 @@ int beer_mix16_gmm_posteriors(const float* llh2, int64_t N, int Kp, int64_t ld_l
     return BEER_OK;
 }
 
+int beer_mix16_weight_exponent(float scale) {
+    // the posteriors carry `scale`: keep w 2^wexp <= 2^14 (fp16 overflows at 2^16)
+    int e = 14;
+    if (scale > 1.f) e -= (int)ceilf(log2f(scale));
+    return e;
+}
+
 int beer_mix16_accumulate(const void* img1, const void* img2, int64_t N, int D, const uint32_t* wtm, const float* k12,
                           const float* alpha, int M, int C, const float* pdf_lpost, int64_t ld_lpost,
                           const float* llh2, int64_t ld_llh, float scale, double* acc_normal, void* stream) {
+    return beer_mix16_accumulate_blocks(img1, img2, N, D, wtm, k12, alpha, M, C, pdf_lpost, ld_lpost, llh2, ld_llh, scale,
+                                        nullptr, 0, acc_normal, stream);
+}
+
+int beer_mix16_accumulate_blocks(const void* img1, const void* img2, int64_t N, int D, const uint32_t* wtm,
+                                 const float* k12, const float* alpha, int M, int C, const float* pdf_lpost,
+                                 int64_t ld_lpost, const float* llh2, int64_t ld_llh, float scale,
+                                 const uint8_t* block_active, int64_t ld_active, double* acc_normal, void* stream) {
     if (!img2 || !alpha || !pdf_lpost || !acc_normal || N < 0) return BEER_ERR_ARG;
     if (C != 1 && (!img1 || !wtm || !k12)) return BEER_ERR_ARG;
     if (!beer_mix16_supported(M, D, C)) return BEER_ERR_UNSUPPORTED;
@@ -1202,10 +1241,10 @@ int beer_mix16_accumulate(const void* img1, const void* img2, int64_t N, int D, 
     a.img1 = (const __half*)img1; a.img2 = (const __half*)img2; a.N = N; a.wtm = wtm; a.k12 = (const float2*)k12; a.alpha = alpha;
     a.M = M; a.Kp = M / C; a.D = D; a.acc = acc_normal; a.na = a.nb = 0; a.trace = mix16::g_trace;
     a.n_gtiles = (M + mix16::GM - 1) / mix16::GM;
-    // the posteriors carry `scale`: keep w 2^wexp <= 2^14 (fp16 overflows at 2^16)
-    int e = 14;
-    if (scale > 1.f) e -= (int)ceilf(log2f(scale));
-    a.wexp = (float)e;
+    a.wexp = (float)beer_mix16_weight_exponent(scale);
+    a.block_active = (C != 1) ? block_active : nullptr;
+    a.ld_active = ld_active;
+    if (a.block_active != nullptr && ld_active < a.n_gtiles) return BEER_ERR_ARG;
     // CTAs = Gaussian tiles x frame ranges, consecutive CTAs = the Gaussian tiles of ONE range (they stream the same
     // image tiles: L2 reuse); the largest grid of whole tile sets within 3 waves
     int64_t ranges = std::max<int64_t>(1, (3 * kNumSMs) / a.n_gtiles);
@@ -1215,6 +1254,8 @@ int beer_mix16_accumulate(const void* img1, const void* img2, int64_t N, int D, 
     fpc = (fpc + mix16::TILE - 1) / mix16::TILE * mix16::TILE;
     ranges = (N + fpc - 1) / fpc;
     a.frames_per_cta = fpc;
+    a.act_cap = (int)(fpc / mix16::TILE);
+    if (a.act_cap > 60000) a.block_active = nullptr;         // (16-bit tile indices: such ranges run dense)
     cudaStream_t st = (cudaStream_t)stream;
     const int KP = mix16::kp_of(D);
 #define BEER_KC_CASE(kp, c) \

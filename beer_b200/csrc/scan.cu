@@ -232,6 +232,34 @@ struct FbArgs {
     int64_t ld_lpost;
     float llh_mul;        // log2(e) for llhs in nats, 1 for llhs already in log2 units (the kernels work in log2)
     int lpost_rel;        // pdf_lpost = log2(scale * gamma) - log2 llh (what beer_mix16_accumulate adds to z), not log2(scale * gamma)
+    // activity map for the statistics kernel: blk_active[(frame / 64) * blk_ld + pdf / blk_ppb] = 1 wherever a pdf posterior
+    // of the block reaches 2^blk_thr (caller-zeroed; below that the weights round to zero in the kernel's fp16 operands)
+    uint8_t* blk_active;
+    int64_t blk_ld;
+    int blk_ppb;
+    float blk_thr;
+};
+
+// A lane's part of the activity map: the blocks g0 .. g1 of its pdfs (identity pdf map: state = pdf), and the tile it
+// marked last (a lane with mass marks once per tile of 64 frames, not once per frame).
+struct BlockMarker {
+    int g0, g1;
+    int64_t last;
+    __device__ __forceinline__ void init(const FbArgs& a, int first, int n) {
+        g0 = g1 = 0;
+        last = -1;
+        if (a.blk_active != nullptr && n > 0) {
+            g0 = first / a.blk_ppb;
+            g1 = (first + n - 1) / a.blk_ppb;
+        }
+    }
+    __device__ __forceinline__ void mark(const FbArgs& a, int64_t frame) {
+        const int64_t tile = frame >> 6;
+        if (tile == last) return;
+        last = tile;
+        uint8_t* row = a.blk_active + tile * a.blk_ld;
+        for (int g = g0; g <= g1; ++g) row[g] = 1;
+    }
 };
 
 constexpr int FB_WARPS = 4;
@@ -922,6 +950,8 @@ __global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_lr_kernel(FbArgs a) {
     const bool own = lane * S < K;
     for (int i = lane; i < 2 * PF * ROW; i += 32) ring_p[i] = 0.f;   // lanes past K stay finite
     __syncwarp();
+    BlockMarker marker;
+    marker.init(a, lane * S, own ? min(S, K - lane * S) : 0);
 
     float w_self[S], w_in[S], w_jout[S], f_start[S], b_start[S];
 #pragma unroll
@@ -1127,6 +1157,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_lr_kernel(FbArgs a) {
                 v[j] = la[j] + lb[j];
                 m = fmaxf(m, v[j]);
             }
+            const float ml = m;              // this lane's largest log posterior (unnormalised)
             m = warp_max(m);
             const float ms = (m == kNegInf) ? 0.f : m;
             float sum = 0.f;
@@ -1145,6 +1176,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_lr_kernel(FbArgs a) {
 #pragma unroll
                 for (int j = 0; j < S; ++j) vlog[j] += lnorm;
                 write_row(a.pdf_lpost + (size_t)(t0 + t) * a.ld_lpost, vlog, 1.f);
+                if (a.blk_active != nullptr && own && ml + lnorm >= a.blk_thr) marker.mark(a, t0 + t);
             }
             float fe = 0.f;      // sum_k llh_k gamma_k in raw-llh units (x p_scale at the end); llh is finite
 #pragma unroll
@@ -1272,6 +1304,8 @@ __global__ void __launch_bounds__(W * 32, 4) hmm_fb_lrb_kernel(FbArgs a) {
     const bool own = k0 < K;
     for (int i = lane; i < 2 * PF * ROW; i += 32) ring_p[i] = 0.f;
     __syncwarp();
+    BlockMarker marker;
+    marker.init(a, k0, own ? min(S, K - k0) : 0);
 
     float w_self[S], w_in[S], w_jout, f_start[S], b_start[S];
 #pragma unroll
@@ -1474,6 +1508,7 @@ __global__ void __launch_bounds__(W * 32, 4) hmm_fb_lrb_kernel(FbArgs a) {
                 v[j] = own ? la[j] + lb[j] : kNegInf;
                 m = fmaxf(m, v[j]);
             }
+            const float ml = m;              // this lane's largest log posterior (unnormalised)
             m = warp_max(m);
             const float mls = (m == kNegInf) ? 0.f : m;
             float sl = 0.f, pe = 0.f;
@@ -1511,6 +1546,7 @@ __global__ void __launch_bounds__(W * 32, 4) hmm_fb_lrb_kernel(FbArgs a) {
 #pragma unroll
                 for (int j = 0; j < S; ++j) vlog[j] += lnorm;
                 write_row(a.pdf_lpost + (size_t)(t0 + t) * a.ld_lpost, vlog, 1.f);
+                if (a.blk_active != nullptr && own && ml + lnorm >= a.blk_thr) marker.mark(a, t0 + t);
             }
             if (a.state_post != nullptr || a.pdf_post != nullptr) {
 #pragma unroll
@@ -3152,12 +3188,35 @@ int beer_hmm_forward_backward_units(const beer_graph_plan* plan, const float* pd
                                         ld_post, frame_exp_llh, utt_exp_llh, utt_logz, unit_counts, 0, nullptr, 0, workspace, stream);
 }
 
+int beer_hmm_block_activity_supported(const beer_graph_plan* plan, int with_unit_counts) {
+    if (!plan || !beer_hmm_lpost_supported(plan)) return 0;
+    // the one-warp kernel for more than 128 units (the only one that reduces unit counts there) does not mark blocks
+    if (plan->lr_u == 8) return with_unit_counts ? 0 : 1;
+    return (plan->lr_u == 1 || plan->lr_u == 2 || plan->lr_u == 4) ? 1 : 0;
+}
+
 int beer_hmm_forward_backward_ex(const beer_graph_plan* plan, const float* pdf_llh, int64_t ld_pdf,
                                  const float* frame_ref, const int64_t* utt_off, int n_utts, float scale,
                                  float* state_post, float* pdf_post, int64_t ld_post, float* frame_exp_llh,
                                  double* utt_exp_llh, double* utt_logz, double* unit_counts, int flags,
                                  float* pdf_lpost, int64_t ld_lpost, void* workspace, void* stream) {
+    return beer_hmm_forward_backward_blocks(plan, pdf_llh, ld_pdf, frame_ref, utt_off, n_utts, scale, state_post, pdf_post,
+                                            ld_post, frame_exp_llh, utt_exp_llh, utt_logz, unit_counts, flags, pdf_lpost,
+                                            ld_lpost, nullptr, 0, 0, workspace, stream);
+}
+
+int beer_hmm_forward_backward_blocks(const beer_graph_plan* plan, const float* pdf_llh, int64_t ld_pdf,
+                                     const float* frame_ref, const int64_t* utt_off, int n_utts, float scale,
+                                     float* state_post, float* pdf_post, int64_t ld_post, float* frame_exp_llh,
+                                     double* utt_exp_llh, double* utt_logz, double* unit_counts, int flags,
+                                     float* pdf_lpost, int64_t ld_lpost, uint8_t* block_active, int64_t ld_active,
+                                     int pdfs_per_block, void* workspace, void* stream) {
     if (!plan || !pdf_llh || !utt_off || !utt_exp_llh || !workspace || n_utts < 0) return BEER_ERR_ARG;
+    if (block_active != nullptr) {
+        if (pdf_lpost == nullptr || pdfs_per_block <= 0 || ld_active < (plan->Kp + pdfs_per_block - 1) / pdfs_per_block)
+            return BEER_ERR_ARG;
+        if (!beer_hmm_block_activity_supported(plan, unit_counts != nullptr)) return BEER_ERR_UNSUPPORTED;
+    }
     const bool llh_log2 = (flags & BEER_FB_LLH_LOG2) != 0;
     if (ld_pdf < plan->Kp || (pdf_post && ld_post < plan->Kp)) return BEER_ERR_ARG;
     if (n_utts == 0) return BEER_OK;
@@ -3179,6 +3238,10 @@ int beer_hmm_forward_backward_ex(const beer_graph_plan* plan, const float* pdf_l
     a.llh_mul = llh_log2 ? 1.f : kLog2e;
     a.pdf_lpost = pdf_lpost; a.ld_lpost = ld_lpost;
     a.lpost_rel = (flags & BEER_FB_LPOST_RELATIVE) ? 1 : 0;
+    a.blk_active = block_active; a.blk_ld = ld_active; a.blk_ppb = pdfs_per_block;
+    // a weight below 2^-25 of the statistics kernel's fp16 range (it carries w 2^wexp, wexp as in beer_mix16_accumulate) is
+    // zero in both halves of its operand; two more bits of margin for the roundings on the way
+    a.blk_thr = -(25.f + (float)beer_mix16_weight_exponent(scale) + 2.f);
     if (pdf_lpost != nullptr && (ld_lpost < plan->Kp || ld_lpost % 4 != 0 || ((uintptr_t)pdf_lpost & 15) != 0)) return BEER_ERR_ARG;
     if (unit_counts != nullptr && beer_hmm_unit_count_size(plan) <= 0) return BEER_ERR_UNSUPPORTED;
     const bool post_ok = (pdf_post == nullptr || (ld_post % 4 == 0 && ((uintptr_t)pdf_post & 15) == 0)) &&

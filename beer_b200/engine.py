@@ -272,7 +272,7 @@ class VBEngine:
 
     def __init__(self, emission, plan, utts, datasize=None, scale=1.0, lrate=1.0, chunk_frames=None,
                  process_group=None, distributed=None, use_graph=False, unit_weights=None, viterbi=False,
-                 prefetch=True):
+                 prefetch=True, sparse_stats=None):
         self.em, self.plan, self.utts = emission, plan, utts
         self.prefetch = bool(prefetch)
         # Viterbi training (hmm.py:42-58 with viterbi=True, what recipes/zrc2019 trains with): one-hot posteriors of
@@ -351,6 +351,11 @@ class VBEngine:
                     if nf > 0:
                         self._images[ci] = self.mix16.build_images(utts.X[f0:f0 + nf])
             self._stage_images = None
+        # skip (frame tile, Gaussian tile) pairs without posterior mass in the mixture statistics kernel (exact in the
+        # moments: see beer_mix16_accumulate_blocks); BEER_B200_DENSE_STATS=1 runs every pair
+        self.sparse_stats = (os.environ.get('BEER_B200_DENSE_STATS') is None) if sparse_stats is None else bool(sparse_stats)
+        self._blocks = None
+        self.active_fraction = None
         self.tensor_kind = 'f16' if self.mix16 is not None else 'tf32'
         self.comp_llh = (torch.empty(nmax, M, device=self.dev, dtype=f32)
                          if emission.has_mixtures and self.mix16 is None else None)
@@ -433,6 +438,8 @@ class VBEngine:
             comp = self.comp_llh[:nf] if self.comp_llh is not None else None
             images = None
             direct = False
+            blocks = None
+            nmax_tiles = (max(c[3] for c in self._chunks) + 63) // 64
             if self.mix16 is not None:
                 if self.host_mode:       # streamed features: the images of the chunk are rebuilt behind its copy
                     with self._stage('KI_feature_images'):
@@ -493,11 +500,23 @@ class VBEngine:
                 else:
                     direct = (images is not None and not nonident and plan.writes_log2_posteriors
                               and self.mix16.C > 1)         # single-Gaussian pdfs: the statistics kernel takes pdf_post
+                    # activity map: (tile of 64 frames, pdfs of one Gaussian tile) pairs with posterior mass; the statistics
+                    # kernel skips the others (their weights are exactly zero in its fp16 operands)
+                    blocks = None
+                    if direct and self.sparse_stats and plan.marks_active_blocks(self.unit_counts is not None):
+                        nb = (em.Kp + self.mix16.pdfs_per_block - 1) // self.mix16.pdfs_per_block
+                        if self._blocks is None or self._blocks.shape[1] != nb:
+                            self._blocks = torch.empty((nmax_tiles, nb), device=self.dev, dtype=torch.uint8)
+                        blocks = self._blocks[:(nf + 63) // 64]
+                        blocks.zero_()
+                        self.gpu_launches += 1
                     ops.hmm_forward_backward(plan, pdf_llh, fref, rel, scale=self.scale, workspace=self.ws,
                                              want_pdf_post=not direct, out_pdf_post=None if direct else pdf_post,
                                              out_pdf_lpost=pdf_post if direct else None,
                                              out_utt_exp_llh=self.utt_ell[u0:u1],
-                                             unit_counts=self.unit_counts, llh_log2=ka16, lpost_relative=direct)
+                                             unit_counts=self.unit_counts, llh_log2=ka16, lpost_relative=direct,
+                                             block_active=blocks,
+                                             pdfs_per_block=self.mix16.pdfs_per_block if blocks is not None else 0)
                     if images is not None and not direct and self.mix16.C > 1:      # graphs without a loop kernel: log2 of pdf_post
                         self.mix16.log2_posteriors(pdf_post, out=pdf_post)
                         self.gpu_launches += 1
@@ -510,7 +529,7 @@ class VBEngine:
                 elif images is not None:
                     # `direct`: the scan wrote log2 posterior - log2 llh, the one array the statistics kernel adds to z
                     self.mix16.accumulate(images, pdf_post, None if direct else pdf_llh, self.acc, scale=self.scale,
-                                          relative=direct)
+                                          relative=direct, block_active=blocks)
                 elif self.viterbi and self._path_kc:
                     ops.accumulate_stats_path(X, self.acc, self._pdf_ids[:nf], scale=self.scale)
                 else:
@@ -519,6 +538,8 @@ class VBEngine:
                                          comp_off=em.comp_off if (comp is not None and not em.uniform_C) else None,
                                          Kp=em.Kp)
             self.gpu_launches += 3
+            if blocks is not None and self.profile is not None:      # (outside the stage timers)
+                self.active_fraction = blocks.float().mean()
             if self.host_mode:
                 self._free[b].record()
                 self._free_valid[b] = True

@@ -214,6 +214,11 @@ class GraphPlan:
         """The forward-backward kernel of this graph can hand out log2 posteriors (`out_pdf_lpost`)."""
         return bool(self._lib.beer_hmm_lpost_supported(self._h))
 
+    def marks_active_blocks(self, with_unit_counts=False):
+        """The forward-backward kernel of this graph can fill the activity map (`block_active`) the statistics kernel of
+        mixtures skips by."""
+        return bool(self._lib.beer_hmm_block_activity_supported(self._h, int(bool(with_unit_counts))))
+
     def __del__(self):
         h, self._h = getattr(self, '_h', None), None
         if h:
@@ -223,11 +228,13 @@ class GraphPlan:
 def hmm_forward_backward(plan, pdf_llh, frame_ref, utt_off, scale=1.0, want_state_post=False,
                          want_pdf_post=True, want_frame_llh=False, want_logz=False, workspace=None,
                          out_pdf_post=None, out_utt_exp_llh=None, unit_counts=None, llh_log2=False, out_pdf_lpost=None,
-                         lpost_relative=False):
+                         lpost_relative=False, block_active=None, pdfs_per_block=0):
     """Forward-backward for a ragged batch.  -> dict(state_post, pdf_post, frame_exp_llh,
     utt_exp_llh (fp64), utt_logz (fp64)).  `out_pdf_post` must be zero-filled by the caller
     when the graph's pdf map is not the identity (the kernel then scatter-adds).  `lpost_relative`: `out_pdf_lpost` =
-    log2(scale posterior) - log2 llh, the form `Mix16.accumulate(..., relative=True)` reads (BEER_FB_LPOST_RELATIVE)."""
+    log2(scale posterior) - log2 llh, the form `Mix16.accumulate(..., relative=True)` reads (BEER_FB_LPOST_RELATIVE).
+    `block_active` (uint8 [ceil(N / 64), >= ceil(Kp / pdfs_per_block)], zeroed by the caller): the activity map of
+    beer_hmm_forward_backward_blocks, for `Mix16.accumulate(..., block_active=...)`."""
     lib = require_cuda()
     N = pdf_llh.shape[0]
     n_utts = utt_off.numel() - 1
@@ -246,14 +253,17 @@ def hmm_forward_backward(plan, pdf_llh, frame_ref, utt_off, scale=1.0, want_stat
     frame = torch.empty(N, device=dev, dtype=f32) if want_frame_llh else None
     utt_ell = out_utt_exp_llh if out_utt_exp_llh is not None else torch.empty(n_utts, device=dev, dtype=f64)
     utt_logz = torch.empty(n_utts, device=dev, dtype=f64) if want_logz else None
-    _lib.check(lib.beer_hmm_forward_backward_ex(
+    if block_active is not None and (block_active.dtype != torch.uint8 or block_active.shape[0] < (N + 63) // 64):
+        raise ValueError('block_active: uint8 [ceil(N / 64), blocks]')
+    _lib.check(lib.beer_hmm_forward_backward_blocks(
         plan._h, _p(pdf_llh, f32), pdf_llh.stride(0), _p(frame_ref, f32, True), _p(utt_off, i64), n_utts,
         float(scale), _p(state_post, f32, True), _p(pdf_post, f32, True),
         pdf_post.stride(0) if pdf_post is not None else 0, _p(frame, f32, True),
         _p(utt_ell, f64), _p(utt_logz, f64, True), _p(unit_counts, f64, True),
         (1 if llh_log2 else 0) | (2 if lpost_relative else 0),
-        _p(out_pdf_lpost, f32, True), out_pdf_lpost.stride(0) if out_pdf_lpost is not None else 0, _p(workspace),
-        _stream()), 'beer_hmm_forward_backward')
+        _p(out_pdf_lpost, f32, True), out_pdf_lpost.stride(0) if out_pdf_lpost is not None else 0,
+        _p(block_active, None, True), block_active.stride(0) if block_active is not None else 0, int(pdfs_per_block),
+        _p(workspace), _stream()), 'beer_hmm_forward_backward')
     return dict(state_post=state_post, pdf_post=pdf_post, frame_exp_llh=frame, utt_exp_llh=utt_ell,
                 utt_logz=utt_logz, workspace=workspace)
 
@@ -683,7 +693,12 @@ class Mix16:
                    'beer_mix16_emission')
         return llh2
 
-    def accumulate(self, images, pdf_lpost, llh2, acc_normal, scale=1.0, relative=False):
+    @property
+    def pdfs_per_block(self):
+        """pdfs of one tile of 128 Gaussians of the statistics kernel: the block width of the activity map."""
+        return 128 // self.C
+
+    def accumulate(self, images, pdf_lpost, llh2, acc_normal, scale=1.0, relative=False, block_active=None):
         """`pdf_lpost` [N, Kp]: log2 of the (scaled) pdf posteriors, see `log2_posteriors`; for single-Gaussian pdfs
         (C = 1) the posteriors themselves, `llh2` is then not read.  `relative`: `pdf_lpost` already holds
         log2 posterior - llh2 (`hmm_forward_backward(..., lpost_relative=True)`), `llh2` must be None."""
@@ -691,10 +706,11 @@ class Mix16:
         if self.C > 1 and relative != (llh2 is None):
             raise ValueError('relative=True takes llh2=None (and only then)')
         ld_llh = llh2.stride(0) if llh2 is not None else pdf_lpost.stride(0)
-        _lib.check(_lib.load().beer_mix16_accumulate(
+        _lib.check(_lib.load().beer_mix16_accumulate_blocks(
             _p(images['img1']), _p(images['img2']), N, self.D, _p(self.wtm), _p(self.k12),
             _p(images['alpha']), self.M, self.C, _p(pdf_lpost, f32), pdf_lpost.stride(0), _p(llh2, f32, True), ld_llh,
-            float(scale), _p(acc_normal, f64), _stream()), 'beer_mix16_accumulate')
+            float(scale), _p(block_active, None, True), block_active.stride(0) if block_active is not None else 0,
+            _p(acc_normal, f64), _stream()), 'beer_mix16_accumulate')
         return acc_normal
 
     def gmm_posteriors(self, llh2, frame_ref, utt_off, scale=1.0, out=None, out_utt_exp_llh=None, want_frame_llh=False):

@@ -350,7 +350,7 @@ def run_config(ctx, args, name, c, steps, warmup, primary):
         X = synthetic.sample_utterances(graph, means, U, T, seed=100 + rank, device=dev)
     utts = Utterances(X, [T] * U)
 
-    def make_engine(utts=utts, chunk_frames=args.chunk_frames, use_graph=False):
+    def make_engine(utts=utts, chunk_frames=args.chunk_frames, use_graph=False, sparse_stats=None):
         prior, post = synthetic.initial_normal_gamma(M, D, seed=2, device=dev)
         groups, comp_off = (), None
         if C > 1:
@@ -359,7 +359,8 @@ def run_config(ctx, args, name, c, steps, warmup, primary):
             comp_off = np.arange(K + 1) * C
         em = EmissionParams(prior, post, comp_off=comp_off, weight_groups=groups)
         return VBEngine(em, plan, utts, datasize=float(world * U * T), chunk_frames=chunk_frames,
-                        distributed=world > 1, use_graph=use_graph, viterbi=bool(c.get('viterbi')))
+                        distributed=world > 1, use_graph=use_graph, viterbi=bool(c.get('viterbi')),
+                        sparse_stats=sparse_stats)
 
     def barrier():
         if world > 1:
@@ -395,6 +396,8 @@ def run_config(ctx, args, name, c, steps, warmup, primary):
     torch.cuda.synchronize()
     stage_ms = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in eng.profile.items()}
     eng.profile = None
+    active = getattr(eng, 'active_fraction', None)
+    active = float(active.item()) if active is not None else None
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -417,6 +420,28 @@ def run_config(ctx, args, name, c, steps, warmup, primary):
     value = frames_per_step * steps / (ms * 1e-3)
     elbo_pf = [float(eng.elbo_per_frame(e).item()) for e in elbos]
     tensor_kind = getattr(eng, 'tensor_kind', 'tf32')
+
+    # ---- the same steps with the statistics kernel working on EVERY (frame tile, Gaussian tile) pair ----
+    # (mixtures skip the pairs whose weights are exactly zero in the kernel's fp16 operands -- bit-identical moments,
+    # beer_mix16_accumulate_blocks --, which makes the step time depend on how peaked the posteriors are: the dense
+    # figure is the data-independent one)
+    dense_ms = None
+    if active is not None:
+        eng_d = make_engine(use_graph=not args.no_graph, sparse_stats=False)
+        for _ in range(warmup):
+            eng_d.step()
+        barrier()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
+        for _ in range(steps):
+            eng_d.step()
+        d1.record()
+        barrier()
+        td = torch.tensor([d0.elapsed_time(d1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        dense_ms = float(td.item()) / steps
+        del eng_d
 
     # ---- end to end: features in pinned host memory, H2D every step, ELBO read back --------
     host_X = torch.empty(X.shape, dtype=torch.float32, pin_memory=True)
@@ -506,6 +531,13 @@ def run_config(ctx, args, name, c, steps, warmup, primary):
                     'd2h_bytes_per_step': 8 * world, 'steps': n_e2e,
                     'h2d_gbs_per_rank': [round(float(r.item()), 2) for r in all_rates]},
             'gpu_launches': launches, 'roofline': roofline, 'tensor_kind': tensor_kind,
+            'sparse_statistics': (None if active is None else {
+                'active_pair_fraction': active,
+                'what': 'fraction of (64-frame tile, 128-Gaussian tile) pairs the statistics kernel works on in the last '
+                        'timed iterations; the others carry weights that are exactly zero in its fp16 operands '
+                        '(first / second moments bit-identical to the dense kernel)',
+                'dense_ms_per_step': dense_ms,
+                'dense_value': (frames_per_step / (dense_ms * 1e-3)) if dense_ms else None}),
             'elbo_per_frame': {'first': elbo_pf[0], 'last': elbo_pf[-1]}}
 
 
@@ -583,6 +615,7 @@ def run_gpu(args, configs):
                 'clocks': r['clocks'], 'wall_s_timed_region': r['wall_s_timed_region'], 'e2e': r['e2e'],
                 'gpu_launches': r['gpu_launches'], 'roofline': r['roofline'], 'cpu_baseline': r.get('cpu_baseline'),
                 'elbo_check': r.get('elbo_check'), 'elbo_per_frame': r['elbo_per_frame'],
+                'sparse_statistics': r.get('sparse_statistics'),
                 'tensor_peaks_tflops': {k: round(v, 1) for k, v in ctx.tc_peak.items()}}
         if len(results) > 1:
             line['secondary'] = {n: {k: v for k, v in rr.items() if k not in ('clocks', 'wall_s_timed_region')}

@@ -359,6 +359,21 @@ BEER_API int beer_hmm_forward_backward_ex(const beer_graph_plan* plan, const flo
                                  float* state_post, float* pdf_post, int64_t ld_post, float* frame_exp_llh,
                                  double* utt_exp_llh, double* utt_logz, double* unit_counts, int flags,
                                  float* pdf_lpost, int64_t ld_lpost, void* workspace, void* stream);
+/* The same with an ACTIVITY MAP for beer_mix16_accumulate_blocks: block_active [ceil(N / 64), ld_active] bytes (zeroed
+ * by the caller) gets a 1 for every (tile of 64 frames, block of pdfs_per_block consecutive pdfs) in which some pdf
+ * posterior is large enough to be non-zero in the statistics kernel's fp16 weight operands (2^-(25 + wexp + 2), wexp =
+ * beer_mix16_weight_exponent(scale)).  Everywhere else gamma_tk r_tkc x_t contributes EXACTLY zero to the first and second
+ * moments there, so the statistics kernel may skip those (tile, block) pairs (mixtureset.py:100-112 has no such notion:
+ * the reference multiplies the zeros).  Needs pdf_lpost; beer_hmm_block_activity_supported(plan, unit_counts != NULL). */
+BEER_API int beer_hmm_block_activity_supported(const beer_graph_plan* plan, int with_unit_counts);
+BEER_API int beer_hmm_forward_backward_blocks(const beer_graph_plan* plan, const float* pdf_llh, int64_t ld_pdf,
+                                     const float* frame_ref, const int64_t* utt_off, int n_utts, float scale,
+                                     float* state_post, float* pdf_post, int64_t ld_post, float* frame_exp_llh,
+                                     double* utt_exp_llh, double* utt_logz, double* unit_counts, int flags,
+                                     float* pdf_lpost, int64_t ld_lpost, uint8_t* block_active, int64_t ld_active,
+                                     int pdfs_per_block, void* workspace, void* stream);
+/* The power of two the statistics kernel scales its weights by (w 2^wexp fills the fp16 range; posteriors carry `scale`). */
+BEER_API int beer_mix16_weight_exponent(float scale);
 
 /* ------------------------------------------------------------------------
  * Mixture path without per-Gaussian llhs in HBM (csrc/mix16.cu): MixtureSet.expected_log_likelihood +
@@ -398,6 +413,14 @@ BEER_API int beer_mix16_emission(const void* img1, int64_t N, int D, const void*
 BEER_API int beer_mix16_accumulate(const void* img1, const void* img2, int64_t N, int D, const uint32_t* wtm, const float* k12,
                           const float* alpha, int M, int C, const float* pdf_lpost, int64_t ld_lpost,
                           const float* llh2, int64_t ld_llh, float scale, double* acc_normal, void* stream);
+/* The same with the activity map of beer_hmm_forward_backward_blocks (pdfs_per_block = 128 / C, the pdfs of one tile of
+ * 128 Gaussians): a CTA works only on the tiles of 64 frames in which the pdfs of its Gaussian tile are marked.  The
+ * first and second moments are bit-identical to the dense call (the skipped weights are zero in both fp16 halves of the
+ * operand); the counts differ by the fp32 sum of those weights (< 2^-41 each).  block_active == NULL: the dense call. */
+BEER_API int beer_mix16_accumulate_blocks(const void* img1, const void* img2, int64_t N, int D, const uint32_t* wtm,
+                                 const float* k12, const float* alpha, int M, int C, const float* pdf_lpost,
+                                 int64_t ld_lpost, const float* llh2, int64_t ld_llh, float scale,
+                                 const uint8_t* block_active, int64_t ld_active, double* acc_normal, void* stream);
 /* GMM without an HMM (Mixture.expected_log_likelihood, beer/models/mixture.py:70-93) on the same kernels: the M
  * components count as Kp pseudo-pdfs of C; after beer_mix16_emission this finishes the softmax over the frame:
  * pdf_lpost[t, k] = llh2[t, k] - log2 sum_k 2^llh2[t, k] + log2(scale), frame_exp_llh[t] (optional) = scale * LSE over

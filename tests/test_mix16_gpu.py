@@ -155,3 +155,55 @@ def test_forward_backward_accepts_log2_llhs():
     ops.hmm_forward_backward(p3, small, None, o3, want_pdf_post=False, out_pdf_lpost=lp3r, lpost_relative=True, scale=2.0)
     c3s = ops.hmm_forward_backward(p3, small, None, o3, scale=2.0)
     assert (torch.exp2(lp3r + small / LN2) - c3s['pdf_post']).abs().max().item() <= 1e-5
+
+
+def test_statistics_skip_inactive_blocks_exactly():
+    """Activity map (beer_hmm_forward_backward_blocks -> beer_mix16_accumulate_blocks): the forward-backward marks the
+    (tile of 64 frames, pdfs of one Gaussian tile) pairs in which a posterior is large enough to be non-zero in the
+    statistics kernel's fp16 operands; the kernel skips the others.  The moments are bit-identical to the dense call."""
+    from beer_b200 import ops, synthetic
+    P, S, C, D, T, U = 40, 4, 8, 40, 150, 5
+    K, M = P * S, P * S * C
+    graph, _, _ = synthetic.phone_loop_graph(P, S)
+    plan = ops.GraphPlan(graph.init_log_probs.numpy(), graph.final_log_probs.numpy(), graph.trans_log_probs.numpy(),
+                         graph.pdf_id_mapping, n_pdfs=K)
+    assert plan.marks_active_blocks()
+    means = 2.0 * torch.randn(K, D, generator=torch.Generator().manual_seed(0))
+    X = synthetic.sample_utterances(graph, means, U, T, seed=1, device=DEV)
+    # a model that fits: component means at the state means (+ noise), so that the posteriors are peaked
+    g = torch.Generator().manual_seed(3)
+    mean = (means.repeat_interleave(C, 0) + 0.3 * torch.randn(M, D, generator=g)).to(DEV)
+    post = [mean, torch.full((M,), 2.0, device=DEV), torch.full((M,), 3.0, device=DEV), torch.full((M, D), 3.0, device=DEV)]
+    conc = torch.ones(K, C, device=DEV)
+    logw = ops.dirichlet_expected_logw(conc).reshape(-1).contiguous()
+    W, bias, ref = ops.emission_prepare(*post, logw=logw)
+    mx = ops.Mix16(M, D, C, DEV)
+    images = mx.build_images(X)
+    mx.pack(W, bias, images['alpha'])
+    llh2 = mx.emission(images)
+    fref = mx.frame_ref(X, ref)
+    off = torch.arange(U + 1, device=DEV) * T
+    N = U * T
+    nb = (K + mx.pdfs_per_block - 1) // mx.pdfs_per_block
+    blocks = torch.zeros((N + 63) // 64, nb, dtype=torch.uint8, device=DEV)
+    lrel, labs = torch.empty(N, K, device=DEV), torch.empty(N, K, device=DEV)
+    ops.hmm_forward_backward(plan, llh2, fref, off, want_pdf_post=False, out_pdf_lpost=labs, llh_log2=True)
+    ops.hmm_forward_backward(plan, llh2, fref, off, want_pdf_post=False, out_pdf_lpost=lrel, llh_log2=True,
+                             lpost_relative=True, block_active=blocks, pdfs_per_block=mx.pdfs_per_block)
+    # the marks are the blocks whose largest log2 posterior reaches -(25 + 14 + 2)
+    pad = (-N) % 64
+    lp = torch.nn.functional.pad(labs, (0, nb * mx.pdfs_per_block - K, 0, pad), value=float('-inf'))
+    top = lp.reshape(-1, 64, nb, mx.pdfs_per_block).amax(dim=(1, 3))
+    assert ((top >= -40.9) <= (blocks > 0)).all() and ((blocks > 0) <= (top >= -41.1)).all()
+    frac = blocks.float().mean().item()
+    assert 0.0 < frac < 0.5, frac          # peaked posteriors: most pairs carry no weight
+    dense = torch.zeros(M, 2 * D + 2, device=DEV, dtype=torch.float64)
+    sparse = torch.zeros_like(dense)
+    mx.accumulate(images, lrel, None, dense, relative=True)
+    mx.accumulate(images, lrel, None, sparse, relative=True, block_active=blocks)
+    assert torch.equal(dense[:, :2 * D], sparse[:, :2 * D])              # first and second moments: bit-identical
+    assert (dense[:, 2 * D:] - sparse[:, 2 * D:]).abs().max().item() <= 1e-9      # counts: the fp32 sum of weights < 2^-41
+    # ... and every block marked: the dense result again, bit for bit
+    full = torch.zeros_like(dense)
+    mx.accumulate(images, lrel, None, full, relative=True, block_active=torch.ones_like(blocks))
+    assert torch.equal(full, dense)
