@@ -351,8 +351,8 @@ class VBEngine:
                     if nf > 0:
                         self._images[ci] = self.mix16.build_images(utts.X[f0:f0 + nf])
             self._stage_images = None
-        # skip (frame tile, Gaussian tile) pairs without posterior mass in the mixture statistics kernel (exact in the
-        # moments: see beer_mix16_accumulate_blocks); BEER_B200_DENSE_STATS=1 runs every pair
+        # skip (frame tile, Gaussian tile) pairs without posterior mass in the mixture statistics kernel (they are exact
+        # zeros: see beer_mix16_accumulate_blocks); BEER_B200_DENSE_STATS=1 runs every pair
         self.sparse_stats = (os.environ.get('BEER_B200_DENSE_STATS') is None) if sparse_stats is None else bool(sparse_stats)
         self._blocks = None
         self.active_fraction = None

@@ -422,7 +422,7 @@ def run_config(ctx, args, name, c, steps, warmup, primary):
     tensor_kind = getattr(eng, 'tensor_kind', 'tf32')
 
     # ---- the same steps with the statistics kernel working on EVERY (frame tile, Gaussian tile) pair ----
-    # (mixtures skip the pairs whose weights are exactly zero in the kernel's fp16 operands -- bit-identical moments,
+    # (mixtures skip the pairs whose weights are exactly zero in the kernel's fp16 operands -- the same non-zero products, summed in another grouping,
     # beer_mix16_accumulate_blocks --, which makes the step time depend on how peaked the posteriors are: the dense
     # figure is the data-independent one)
     dense_ms = None
@@ -535,7 +535,7 @@ def run_config(ctx, args, name, c, steps, warmup, primary):
                 'active_pair_fraction': active,
                 'what': 'fraction of (64-frame tile, 128-Gaussian tile) pairs the statistics kernel works on in the last '
                         'timed iterations; the others carry weights that are exactly zero in its fp16 operands '
-                        '(first / second moments bit-identical to the dense kernel)',
+                        '(the same non-zero products as the dense kernel, grouped differently into its fp32 partial sums)',
                 'dense_ms_per_step': dense_ms,
                 'dense_value': (frames_per_step / (dense_ms * 1e-3)) if dense_ms else None}),
             'elbo_per_frame': {'first': elbo_pf[0], 'last': elbo_pf[-1]}}

@@ -415,8 +415,9 @@ BEER_API int beer_mix16_accumulate(const void* img1, const void* img2, int64_t N
                           const float* llh2, int64_t ld_llh, float scale, double* acc_normal, void* stream);
 /* The same with the activity map of beer_hmm_forward_backward_blocks (pdfs_per_block = 128 / C, the pdfs of one tile of
  * 128 Gaussians): a CTA works only on the tiles of 64 frames in which the pdfs of its Gaussian tile are marked.  The
- * first and second moments are bit-identical to the dense call (the skipped weights are zero in both fp16 halves of the
- * operand); the counts differ by the fp32 sum of those weights (< 2^-41 each).  block_active == NULL: the dense call. */
+ * skipped pairs contribute exactly zero to the first and second moments (their weights are zero in both fp16 halves of
+ * the operand); the remaining products are the same, grouped differently into the kernel's fp32 partial sums (equal to
+ * summation order, ~1e-7 relative); the counts differ by the fp32 sum of the skipped weights (< 2^-41 each).  block_active == NULL: the dense call. */
 BEER_API int beer_mix16_accumulate_blocks(const void* img1, const void* img2, int64_t N, int D, const uint32_t* wtm,
                                  const float* k12, const float* alpha, int M, int C, const float* pdf_lpost,
                                  int64_t ld_lpost, const float* llh2, int64_t ld_llh, float scale,

@@ -380,3 +380,40 @@ def test_vb_iterations_gmm_only(chunk, use_graph):
     for g, w in zip(_host(em.post), ng_post):
         np.testing.assert_allclose(g, w, rtol=3e-4, atol=3e-4)
     np.testing.assert_allclose(groups[0].post.double().cpu().numpy().reshape(-1), dpost, rtol=3e-4, atol=1e-5)
+
+
+def test_sparse_and_dense_statistics_give_the_same_iterations():
+    """VBEngine(sparse_stats=...) at the cfg3 shape: the statistics kernel over the marked (frame tile, Gaussian tile)
+    pairs only against the same kernel over every pair -- the skipped pairs are exact zeros, the rest is summed in another
+    grouping: statistics and models agree to fp32 summation order; the fraction of marked pairs falls as the model fits."""
+    from beer_b200 import ops, synthetic
+    from beer_b200.engine import EmissionParams, Utterances, VBEngine, WeightGroup
+    dev = torch.device('cuda', 0)
+    P, S, D, C = 250, 4, 40, 8
+    K, M = P * S, P * S * C
+    lens = [300, 129, 210, 64]
+    graph, _, _ = synthetic.phone_loop_graph(P, S)
+    plan = ops.GraphPlan(graph.init_log_probs.numpy(), graph.final_log_probs.numpy(),
+                         graph.trans_log_probs.numpy(), graph.pdf_id_mapping, n_pdfs=K)
+    means = 2.0 * torch.randn(K, D, generator=torch.Generator().manual_seed(0))
+    full = synthetic.sample_utterances(graph, means, len(lens), max(lens), seed=1, device=dev).reshape(len(lens), max(lens), D)
+    X = torch.cat([full[i, :n] for i, n in enumerate(lens)])
+    engines = []
+    for sparse in (True, False):
+        prior, post = synthetic.initial_normal_gamma(M, D, seed=2, device=dev)
+        conc = torch.full((K, C), 1.0 / C, device=dev)
+        em = EmissionParams(prior, post, comp_off=np.arange(K + 1) * C,
+                            weight_groups=(WeightGroup(0, K, C, conc.clone(), conc.clone()),))
+        engines.append(VBEngine(em, plan, Utterances(X, lens), datasize=float(sum(lens)), distributed=False,
+                                sparse_stats=sparse, chunk_frames=450))
+    fractions = []
+    for it in range(4):
+        engines[0].profile = {}
+        a, b = (float(e.step().item()) for e in engines)
+        fractions.append(float(engines[0].active_fraction))
+        assert abs(a - b) <= 1e-9 * abs(b), (it, a, b)
+        sa, da = engines[0].acc, engines[1].acc
+        assert (sa - da).abs().max().item() <= 2e-6 * da.abs().max().item(), it
+    for p, q in zip(engines[0].em.post, engines[1].em.post):
+        assert (p - q).abs().max().item() <= 1e-5 * q.abs().max().item()
+    assert fractions[-1] < 0.5 * fractions[0], fractions

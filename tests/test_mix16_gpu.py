@@ -160,7 +160,8 @@ def test_forward_backward_accepts_log2_llhs():
 def test_statistics_skip_inactive_blocks_exactly():
     """Activity map (beer_hmm_forward_backward_blocks -> beer_mix16_accumulate_blocks): the forward-backward marks the
     (tile of 64 frames, pdfs of one Gaussian tile) pairs in which a posterior is large enough to be non-zero in the
-    statistics kernel's fp16 operands; the kernel skips the others.  The moments are bit-identical to the dense call."""
+    statistics kernel's fp16 operands; the kernel skips the others: exact zeros.  What remains are the same products,
+    grouped differently into the fp32 partial sums (drain every four worked tiles): equal to summation order."""
     from beer_b200 import ops, synthetic
     P, S, C, D, T, U = 40, 4, 8, 40, 150, 5
     K, M = P * S, P * S * C
@@ -201,7 +202,9 @@ def test_statistics_skip_inactive_blocks_exactly():
     sparse = torch.zeros_like(dense)
     mx.accumulate(images, lrel, None, dense, relative=True)
     mx.accumulate(images, lrel, None, sparse, relative=True, block_active=blocks)
-    assert torch.equal(dense[:, :2 * D], sparse[:, :2 * D])              # first and second moments: bit-identical
+    mom_d, mom_s = dense[:, :2 * D], sparse[:, :2 * D]                   # first and second moments
+    assert (mom_d - mom_s).abs().max().item() <= 1e-6 * mom_d.abs().max().item()
+    assert torch.equal(mom_d == 0, mom_s == 0)
     assert (dense[:, 2 * D:] - sparse[:, 2 * D:]).abs().max().item() <= 1e-9      # counts: the fp32 sum of weights < 2^-41
     # ... and every block marked: the dense result again, bit for bit
     full = torch.zeros_like(dense)
