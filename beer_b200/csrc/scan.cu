@@ -243,22 +243,25 @@ struct FbArgs {
 // A lane's part of the activity map: the blocks g0 .. g1 of its pdfs (identity pdf map: state = pdf), and the tile it
 // marked last (a lane with mass marks once per tile of 64 frames, not once per frame).
 struct BlockMarker {
-    int g0, g1;
-    int64_t last;
+    int g0, ng;      // first block and number of blocks of this lane's pdfs (ng = 1 when the block width is a multiple of the unit)
+    int last;        // tile marked last
     __device__ __forceinline__ void init(const FbArgs& a, int first, int n) {
-        g0 = g1 = 0;
+        g0 = 0;
+        ng = 0;
         last = -1;
         if (a.blk_active != nullptr && n > 0) {
             g0 = first / a.blk_ppb;
-            g1 = (first + n - 1) / a.blk_ppb;
+            ng = (first + n - 1) / a.blk_ppb - g0 + 1;
         }
     }
     __device__ __forceinline__ void mark(const FbArgs& a, int64_t frame) {
-        const int64_t tile = frame >> 6;
+        const int tile = (int)(frame >> 6);
         if (tile == last) return;
         last = tile;
-        uint8_t* row = a.blk_active + tile * a.blk_ld;
-        for (int g = g0; g <= g1; ++g) row[g] = 1;
+        uint8_t* row = a.blk_active + (int64_t)tile * a.blk_ld + g0;
+        row[0] = 1;
+#pragma unroll 1
+        for (int g = 1; g < ng; ++g) row[g] = 1;
     }
 };
 
