@@ -611,6 +611,10 @@ def run_gpu(args, configs):
                 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
                 'config': {'workload': r['workload'], 'l2': r['l2'], 'chunk_frames': args.chunk_frames,
                            'tensor_kind': r['tensor_kind'],
+                           'statistics': ('the mixture statistics kernel works only on the (frame tile, Gaussian tile) pairs '
+                                          'whose weights are not exactly zero in its fp16 operands; `sparse_statistics` has '
+                                          'the marked fraction and the time of the same steps with every pair worked on'
+                                          if r.get('sparse_statistics') else 'dense'),
                            'parallelism': f'dp{ctx.world} (utterances sharded, one all-reduce of the statistics per step)'},
                 'clocks': r['clocks'], 'wall_s_timed_region': r['wall_s_timed_region'], 'e2e': r['e2e'],
                 'gpu_launches': r['gpu_launches'], 'roofline': r['roofline'], 'cpu_baseline': r.get('cpu_baseline'),
