@@ -128,3 +128,26 @@ class Alignments:
     def chain_batch(self, uttids, device):
         from . import ops
         return ops.ChainBatch([self._graphs[u] for u in uttids], device)
+
+
+def create_dataset(feapath, out):
+    """`beer dataset create` (beer/cli/subcommands/dataset/create.py:44-60): global mean / variance / frame count of a
+    features archive, pickled as the reference's `beer.cli.dataset.Dataset` (a dataclass: feapath, mean, var, size) so
+    that `beer hmm accumulate`, `beer hmm decode` and `python -m beer_b200.hmm_train` all read it."""
+    import os
+    from . import refpickle
+    mean, var, size = Dataset.accumulate(feapath)
+    obj = refpickle.new_object('beer.cli.dataset', 'Dataset', feapath=os.path.abspath(feapath), mean=mean, var=var,
+                               size=size, _fea_dict=None)
+    refpickle.dump(obj, out)
+    return obj
+
+
+if __name__ == '__main__':
+    import argparse
+    ap = argparse.ArgumentParser(prog='python -m beer_b200.dataset', description='compile a data set with the given features')
+    ap.add_argument('features', help='features archive (npz format)')
+    ap.add_argument('out', help='output compiled dataset')
+    a = ap.parse_args()
+    d = create_dataset(a.features, a.out)
+    print(f'created dataset (total frame count: {d.size})')

@@ -17,7 +17,7 @@ import types
 
 import torch
 
-__all__ = ['load', 'dump', 'dumps', 'loads', 'RefObject', 'ModelView']
+__all__ = ['load', 'dump', 'dumps', 'loads', 'RefObject', 'ModelView', 'new_object']
 
 _PREFIX = 'beer'
 _classes = {}
@@ -113,6 +113,15 @@ class _FakeModules:
                 sys.modules.pop(n, None)
             else:
                 sys.modules[n] = m
+
+
+def new_object(module, name, **state):
+    """A stand-in instance of the reference class `module.name` with the given attributes: what `dump` pickles so that
+    the reference unpickles a real instance (classes whose pickled state is their `__dict__`: dataclasses, plain
+    objects, modules of `torch.nn`)."""
+    obj = _stand_in(module, name)()
+    obj.__dict__.update(state)
+    return obj
 
 
 def loads(data):

@@ -95,3 +95,21 @@ def test_save_without_training_is_the_identity(tmp_path):
         if k.endswith('/stats'):
             continue                  # (the unit weights' statistics buffer is fp64 on this side before the first update)
         assert torch.equal(a[k], b[k]), k
+
+
+def test_dataset_pickle_written_for_the_reference(tmp_path):
+    """`python -m beer_b200.dataset` = `beer dataset create` (create.py:44-60): same class name, same fields, same
+    statistics as the pickle the live reference wrote for the same archive."""
+    from beer_b200 import refpickle
+    from beer_b200.dataset import create_dataset
+    from beer_b200.hmm_train import load_dataset
+    out = str(tmp_path / 'dataset.pkl')
+    create_dataset(os.path.join(CLI, 'feats.npz'), out)
+    got, want = refpickle.load(out), refpickle.load(os.path.join(CLI, 'dataset.pkl'))
+    assert got.ref_class() == want.ref_class() == 'beer.cli.dataset.Dataset'
+    assert set(got.__dict__) == set(want.__dict__)
+    assert got.__dict__['size'] == want.__dict__['size']
+    for k in ('mean', 'var'):
+        assert got.__dict__[k].dtype == want.__dict__[k].dtype
+        np.testing.assert_allclose(got.__dict__[k].numpy(), want.__dict__[k].numpy(), rtol=1e-5, atol=1e-6)
+    assert len(load_dataset(out)) == 5
