@@ -244,24 +244,29 @@ struct FbArgs {
 // marked last (a lane with mass marks once per tile of 64 frames, not once per frame).
 struct BlockMarker {
     int g0, ng;      // first block and number of blocks of this lane's pdfs (ng = 1 when the block width is a multiple of the unit)
-    int last;        // tile marked last
+    float tmax;      // largest log2 posterior of this lane's pdfs over the frames of the current tile
     __device__ __forceinline__ void init(const FbArgs& a, int first, int n) {
         g0 = 0;
         ng = 0;
-        last = -1;
+        tmax = kNegInf;
         if (a.blk_active != nullptr && n > 0) {
             g0 = first / a.blk_ppb;
             ng = (first + n - 1) / a.blk_ppb - g0 + 1;
         }
     }
-    __device__ __forceinline__ void mark(const FbArgs& a, int64_t frame) {
-        const int tile = (int)(frame >> 6);
-        if (tile == last) return;
-        last = tile;
-        uint8_t* row = a.blk_active + (int64_t)tile * a.blk_ld + g0;
-        row[0] = 1;
+    // per frame: one max; at the first frame of a tile (the sweep runs backwards) or of the utterance -- a warp-uniform
+    // test -- the lanes with mass in the tile store their byte(s)
+    __device__ __forceinline__ void frame(const FbArgs& a, float lpost_max, int64_t f, bool first_of_utt) {
+        tmax = fmaxf(tmax, lpost_max);
+        if ((f & 63) == 0 || first_of_utt) {
+            if (ng > 0 && tmax >= a.blk_thr) {
+                uint8_t* row = a.blk_active + (f >> 6) * a.blk_ld + g0;
+                row[0] = 1;
 #pragma unroll 1
-        for (int g = 1; g < ng; ++g) row[g] = 1;
+                for (int g = 1; g < ng; ++g) row[g] = 1;
+            }
+            tmax = kNegInf;
+        }
     }
 };
 
@@ -1179,7 +1184,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) hmm_fb_lr_kernel(FbArgs a) {
 #pragma unroll
                 for (int j = 0; j < S; ++j) vlog[j] += lnorm;
                 write_row(a.pdf_lpost + (size_t)(t0 + t) * a.ld_lpost, vlog, 1.f);
-                if (a.blk_active != nullptr && own && ml + lnorm >= a.blk_thr) marker.mark(a, t0 + t);
+                if (a.blk_active != nullptr) marker.frame(a, ml + lnorm, t0 + t, t == 0);
             }
             float fe = 0.f;      // sum_k llh_k gamma_k in raw-llh units (x p_scale at the end); llh is finite
 #pragma unroll
@@ -1549,7 +1554,7 @@ __global__ void __launch_bounds__(W * 32, 4) hmm_fb_lrb_kernel(FbArgs a) {
 #pragma unroll
                 for (int j = 0; j < S; ++j) vlog[j] += lnorm;
                 write_row(a.pdf_lpost + (size_t)(t0 + t) * a.ld_lpost, vlog, 1.f);
-                if (a.blk_active != nullptr && own && ml + lnorm >= a.blk_thr) marker.mark(a, t0 + t);
+                if (a.blk_active != nullptr) marker.frame(a, ml + lnorm, t0 + t, t == 0);
             }
             if (a.state_post != nullptr || a.pdf_post != nullptr) {
 #pragma unroll
