@@ -1304,6 +1304,7 @@ __global__ void __launch_bounds__(W * 32, 4) hmm_fb_lrb_kernel(FbArgs a) {
     float* ring_p = smem + (size_t)warp * (2 * PF * ROW);
     float* ring_a = ring_p + PF * ROW;
     float* xch = smem + (size_t)W * (2 * PF * ROW);     // [2][W][8] exchange slots
+    float* ml_park = xch + 2 * W * 8 + threadIdx.x;     // this thread's lane maximum, parked across the block exchange
     const int K = a.K;
     const float p_scale = a.scale * a.llh_mul;
     const float lp_rel_s = a.lpost_rel ? -1.f / a.scale : 0.f;      // p is scaled below: p / scale = the llh in log2 units
@@ -1516,7 +1517,7 @@ __global__ void __launch_bounds__(W * 32, 4) hmm_fb_lrb_kernel(FbArgs a) {
                 v[j] = own ? la[j] + lb[j] : kNegInf;
                 m = fmaxf(m, v[j]);
             }
-            const float ml = m;              // this lane's largest log posterior (unnormalised)
+            if (a.blk_active != nullptr) *ml_park = m;       // this lane's largest log posterior (unnormalised): no register across the exchange
             m = warp_max(m);
             const float mls = (m == kNegInf) ? 0.f : m;
             float sl = 0.f, pe = 0.f;
@@ -1554,7 +1555,7 @@ __global__ void __launch_bounds__(W * 32, 4) hmm_fb_lrb_kernel(FbArgs a) {
 #pragma unroll
                 for (int j = 0; j < S; ++j) vlog[j] += lnorm;
                 write_row(a.pdf_lpost + (size_t)(t0 + t) * a.ld_lpost, vlog, 1.f);
-                if (a.blk_active != nullptr) marker.frame(a, ml + lnorm, t0 + t, t == 0);
+                if (a.blk_active != nullptr) marker.frame(a, *ml_park + lnorm, t0 + t, t == 0);
             }
             if (a.state_post != nullptr || a.pdf_post != nullptr) {
 #pragma unroll
@@ -1605,7 +1606,7 @@ template <int SU, int W, bool LP = false>
 static int launch_fb_lrb(const FbArgs& a, int n_utts, cudaStream_t st) {
     if (!LP && a.pdf_lpost != nullptr) return launch_fb_lrb<SU, W, true>(a, n_utts, st);
     constexpr int PF = 4;
-    size_t smem = sizeof(float) * ((size_t)W * (2 * PF * 32 * SU) + 2 * W * 8);
+    size_t smem = sizeof(float) * ((size_t)W * (2 * PF * 32 * SU) + 2 * W * 8 + W * 32);
     static bool attr_set = false;
     if (!attr_set) {
         BEER_CUDA_TRY(cudaFuncSetAttribute(hmm_fb_lrb_kernel<SU, W, LP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
