@@ -268,7 +268,9 @@ class VBEngine:
     when `utts.X` is a pinned HOST tensor -- are streamed through two device staging buffers, the
     copy of chunk i+1 overlapping the kernels of chunk i; with `prefetch` (default) the first chunk of the NEXT VB
     iteration is copied under the last chunk of this one, so that in steady state no copy is exposed (the host tensor
-    must then not be modified between `step()` calls)."""
+    must then not be modified between `step()` calls).  `sparse_stats` (default: on unless BEER_B200_DENSE_STATS is set):
+    mixtures on the fp16-split kernels let the forward-backward mark the (frame tile, Gaussian tile) pairs with posterior
+    mass and run the statistics kernel over those only (the others are exact zeros in its operands)."""
 
     def __init__(self, emission, plan, utts, datasize=None, scale=1.0, lrate=1.0, chunk_frames=None,
                  process_group=None, distributed=None, use_graph=False, unit_weights=None, viterbi=False,

@@ -701,7 +701,9 @@ class Mix16:
     def accumulate(self, images, pdf_lpost, llh2, acc_normal, scale=1.0, relative=False, block_active=None):
         """`pdf_lpost` [N, Kp]: log2 of the (scaled) pdf posteriors, see `log2_posteriors`; for single-Gaussian pdfs
         (C = 1) the posteriors themselves, `llh2` is then not read.  `relative`: `pdf_lpost` already holds
-        log2 posterior - llh2 (`hmm_forward_backward(..., lpost_relative=True)`), `llh2` must be None."""
+        log2 posterior - llh2 (`hmm_forward_backward(..., lpost_relative=True)`), `llh2` must be None.  `block_active`
+        (uint8 [ceil(N / 64), >= M / 128], from `hmm_forward_backward(..., block_active=..., pdfs_per_block=
+        self.pdfs_per_block)`): work only on the marked (frame tile, Gaussian tile) pairs; the others are exact zeros."""
         N = images['N']
         if self.C > 1 and relative != (llh2 is None):
             raise ValueError('relative=True takes llh2=None (and only then)')
