@@ -3267,6 +3267,7 @@ int beer_hmm_forward_backward_blocks(const beer_graph_plan* plan, const float* p
         // one long dependent instruction stream per warp at 12 warps per SM).  The one-warp kernel is the only one of
         // the three that reduces unit counts, so it runs when they are asked for.
         const char* lrc = getenv("BEER_B200_SCAN_LRC");       // debug: "1" = four warps x two units, "w" = one warp
+        if (a.blk_active != nullptr) lrc = nullptr;            // (those two variants do not write the activity map)
         if (u == 8 && plan->lr_su == 4 && plan->K % 4 == 0 && (unit_counts != nullptr || (lrc != nullptr && lrc[0] == 'w')))
             return launch_fb_lrw<4, 8>(a, n_utts, st);
         if (u == 8 && unit_counts == nullptr) {
