@@ -323,9 +323,11 @@ class VBEngine:
         self.profile = None      # optional {stage: [(start_event, end_event), ...]} (bench.py)
         self.host_mode = not utts.X.is_cuda
         if self.host_mode and chunk_frames is None:
-            # ~100 MB of 40-d frames per chunk: large enough that the forward-backward grid fills the GPU (cfg3 with
-            # 1/8 of its 1250 utterances per chunk ran 26 % slower end to end than with 1/2)
-            chunk_frames = max(1, len(utts) // 8, min(len(utts), 640_000))
+            # the whole shard as ONE chunk while two staging buffers of it are affordable (4.2 M frames of 40 dimensions:
+            # 2 x 670 MB): the copy of the next VB iteration then runs under all the kernels of this one, and the
+            # forward-backward keeps its full rounds of resident utterances (cfg3 with two chunks of 625 utterances:
+            # 9.1e7 frames/s end to end, one chunk: 1.0e8); larger shards in ~4 M-frame chunks
+            chunk_frames = max(1, min(len(utts), 4_200_000))
         self._chunks = self._make_chunks(chunk_frames)
         nmax = max((c[3] for c in self._chunks), default=0)
         if self.host_mode:

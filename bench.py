@@ -449,7 +449,7 @@ def run_config(ctx, args, name, c, steps, warmup, primary):
     del eng
     # features stay in pinned host memory: the engine streams them in chunks of whole utterances (the H2D
     # copy of chunk i+1 under the kernels of chunk i) and the ELBO is read back to the host every step
-    eng2 = make_engine(Utterances(host_X, [T] * U), chunk_frames=args.e2e_chunk_frames or max(T, min(U * T, 640_000)))
+    eng2 = make_engine(Utterances(host_X, [T] * U), chunk_frames=args.e2e_chunk_frames or max(T, min(U * T, 4_200_000)))
     n_e2e = max(1, min(steps, 5))
 
     def e2e_step():
