@@ -9,7 +9,7 @@ does (there is no CPU fallback, see beer_b200/_lib.py)."""
 __version__ = '0.2.0'
 
 from . import dists, features, graph, vbi                                                    # noqa: F401
-from .engine import EmissionParams, UnitWeights, Utterances, VBEngine, WeightGroup              # noqa: F401
+from .engine import BigramUnitWeights, CategoricalUnitWeights, EmissionParams, UnitWeights, Utterances, VBEngine, WeightGroup              # noqa: F401
 from .dataset import Alignments, Dataset                                                      # noqa: F401
 from .graph import CompiledGraph, Graph                                            # noqa: F401
 from .inference import (EvidenceLowerBoundInstance, VBConjugateOptimizer, VBOptimizer,  # noqa: F401

@@ -197,6 +197,44 @@ class CategoricalUnitWeights(UnitWeights):
         param.natural_grad_update(lrate)
 
 
+class BigramUnitWeights(UnitWeights):
+    """Bigram unit weights of a `BigramPhoneLoop` (beer/models/phoneloop.py:105-191): a `CategoricalSet` of one Dirichlet
+    per unit over the unit starts.  The engine hands it the ends x starts block of the transition posteriors summed over
+    the frames of the iteration (phoneloop.py:175-186)."""
+
+    needs_block = True
+
+    def __init__(self, categoricalset, graph, start_idxs, end_idxs):
+        self.categoricalset = categoricalset
+        self.graph = graph
+        self.start_idxs = [int(i) for i in start_idxs]
+        self.end_idxs = [int(i) for i in end_idxs]
+
+    def expected_log_weights(self):
+        return self.categoricalset.weights.posterior.expected_log_weights()       # [model, class]
+
+    def kl(self, out):
+        out += self.categoricalset.kl_div_posterior_prior().sum().to(out.dtype)
+
+    def update(self, counts, stats_scale, lrate):
+        """counts: [ends, starts] block; every row is the statistics of one Dirichlet, last entry = the row total
+        (dirichlet.py:18-21)."""
+        stats = counts.clone().to(f64)
+        stats[:, -1] = counts.sum(dim=-1)
+        param = self.categoricalset.weights
+        param.store_stats(stats * stats_scale)
+        param.natural_grad_update(lrate)
+
+    def rewrite_graph(self):
+        """Arc (end_i -> start_m) = ln(1 - A[end_i, end_i]) + E[ln pi]_{m i}: the reference evaluates the set on eye(P),
+        indexed [class, model], and writes row i onto the arcs out of unit i (phoneloop.py:145-157); kept as it is."""
+        logw = self.expected_log_weights()
+        trans = self.graph.trans_log_probs
+        logw = logw.to(device=trans.device, dtype=trans.dtype)
+        for i, e in enumerate(self.end_idxs):
+            trans[e, self.start_idxs] = (1 - trans[e, e].exp()).log() + logw[:, i]
+
+
 class _StageTimer:
     """CUDA events around one kernel stage on the current stream (only when profiling)."""
 
@@ -308,8 +346,16 @@ class VBEngine:
         # aligned training gives the unit weights ZERO statistics (phoneloop.py:98-100): with `unit_weights` their KL
         # still enters the ELBO and their posterior takes the natural-gradient step towards the prior, as in the reference
         P = plan.n_units if (unit_weights is not None and not aligned) else 0
-        if unit_weights is not None and P == 0 and not aligned:
-            raise ValueError('unit weights need an aligned left-to-right phone loop (see beer_hmm_forward_backward_units)')
+        # phone loops the fused unit counting does not take (units of uneven length, shared pdfs, a bigram over the
+        # units): the ends x starts block of the transition posteriors (csrc/transitions.cu) summed over the frames,
+        # plus the start-state posteriors of every utterance's first frame -- what PhoneLoop / BigramPhoneLoop.accumulate
+        # reduce (phoneloop.py:83-101, 175-186)
+        self._xi_block = unit_weights is not None and not aligned and (P == 0 or getattr(unit_weights, 'needs_block', False))
+        if self._xi_block:
+            if self.viterbi:
+                raise ValueError('Viterbi training with learned unit weights needs an aligned left-to-right phone loop')
+            self._nE, self._nS = len(unit_weights.end_idxs), len(unit_weights.start_idxs)
+            P = self._nE * self._nS + self._nS
         self.flat = torch.zeros(M * self.Q + P + 4, device=self.dev, dtype=f64)
         self.acc = self.flat[:M * self.Q].view(M, self.Q)
         self.unit_counts = self.flat[M * self.Q:M * self.Q + P] if P else None
@@ -514,13 +560,16 @@ class VBEngine:
                         blocks = self._blocks[:(nf + 63) // 64]
                         blocks.zero_()
                         self.gpu_launches += 1
-                    ops.hmm_forward_backward(plan, pdf_llh, fref, rel, scale=self.scale, workspace=self.ws,
-                                             want_pdf_post=not direct, out_pdf_post=None if direct else pdf_post,
+                    r = ops.hmm_forward_backward(plan, pdf_llh, fref, rel, scale=self.scale, workspace=self.ws,
+                                                 want_pdf_post=not direct, out_pdf_post=None if direct else pdf_post,
                                              out_pdf_lpost=pdf_post if direct else None,
                                              out_utt_exp_llh=self.utt_ell[u0:u1],
-                                             unit_counts=self.unit_counts, llh_log2=ka16, lpost_relative=direct,
-                                             block_active=blocks,
-                                             pdfs_per_block=self.mix16.pdfs_per_block if blocks is not None else 0)
+                                             unit_counts=None if self._xi_block else self.unit_counts,
+                                             llh_log2=ka16, lpost_relative=direct, block_active=blocks,
+                                             pdfs_per_block=self.mix16.pdfs_per_block if blocks is not None else 0,
+                                             want_state_post=self._xi_block)
+                    if self._xi_block:
+                        self._block_counts(r['state_post'], pdf_llh, rel, u0, u1, self.scale * (math.log(2.0) if ka16 else 1.0))
                     if images is not None and not direct and self.mix16.C > 1:      # graphs without a loop kernel: log2 of pdf_post
                         self.mix16.log2_posteriors(pdf_post, out=pdf_post)
                         self.gpu_launches += 1
@@ -552,6 +601,41 @@ class VBEngine:
         self.extras[3] = self.utt_ell.sum()
         # sum_u ell_u / T_u; multiplied by the global datasize after the reduction
         self.extras[0] = (self.utt_ell * self.inv_len).sum()
+
+    def _block_counts(self, state_post, pdf_llh, rel, u0, u1, scale, max_floats=1 << 26):
+        """unit_counts[:E * S] += sum_t xi_t[ends, starts], unit_counts[E * S:] += sum_u gamma_0[starts] over the
+        utterances of a chunk.  The per-step block [frames, E, S] is formed for groups of utterances of at most
+        `max_floats` elements and summed in float64."""
+        u = self.units
+        nE, nS = self._nE, self._nS
+        if not hasattr(self, '_xi_rows'):
+            g = u.graph
+            self._xi_rows = torch.as_tensor(u.end_idxs, dtype=i32, device=self.dev)
+            self._xi_cols = torch.as_tensor(u.start_idxs, dtype=i32, device=self.dev)
+            self._xi_map = torch.as_tensor(np.asarray(g.pdf_id_mapping), dtype=i32, device=self.dev)
+        g = u.graph
+        init = g.init_log_probs.detach().to(device=self.dev, dtype=f32).contiguous()
+        trans = g.trans_log_probs.detach().to(device=self.dev, dtype=f32).contiguous()     # rewritten every iteration
+        block = self.unit_counts[:nE * nS].view(nE, nS)
+        first = self.unit_counts[nE * nS:]
+        oh = self.utts.offsets_host
+        off_h = [int(oh[k] - oh[u0]) for k in range(u0, u1 + 1)]
+        n_utts = len(off_h) - 1
+        per_frame = max(nE * nS, 1)
+        i = 0
+        while i < n_utts:
+            j = i + 1
+            while j < n_utts and (off_h[j + 1] - off_h[i]) * per_frame <= max_floats:
+                j += 1
+            a, b = off_h[i], off_h[j]
+            if b > a:
+                xi = ops.hmm_transition_posteriors(pdf_llh[a:b], state_post[a:b], (rel[i:j + 1] - a).contiguous(), init, trans,
+                                                   pdf_map=self._xi_map, scale=scale, rows=self._xi_rows, cols=self._xi_cols)
+                block += xi.sum(dim=0, dtype=f64)
+                self.gpu_launches += 2
+            i = j
+        starts = rel[:-1][rel[1:] > rel[:-1]]               # first frame of every non-empty utterance
+        first += state_post[starts][:, self._xi_cols.long()].sum(dim=0, dtype=f64)
 
     def _path_unit_counts(self, path, rel):
         """Unit counts of a state path: its one-hot transition posteriors summed over the ends x starts block, plus the
@@ -607,7 +691,12 @@ class VBEngine:
             # dirichlet.py:18-21) -> natural-gradient step -> rewrite the graph -> new device plan
             u = self.units
             if self.chains or self.per_utt:
-                counts = torch.zeros(len(u.start_idxs), device=self.dev, dtype=f64)
+                # aligned training: zero statistics (phoneloop.py:98-100, 187-190)
+                shape = (len(u.end_idxs), len(u.start_idxs)) if getattr(u, 'needs_block', False) else (len(u.start_idxs),)
+                counts = torch.zeros(shape, device=self.dev, dtype=f64)
+            elif self._xi_block:
+                block = self.unit_counts[:self._nE * self._nS].view(self._nE, self._nS)
+                counts = block if getattr(u, 'needs_block', False) else block.sum(dim=0) + self.unit_counts[self._nE * self._nS:]
             else:
                 su = self.plan.n_states // self.unit_counts.numel()
                 order = torch.as_tensor([s // su for s in u.start_idxs], device=self.dev)

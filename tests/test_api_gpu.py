@@ -389,6 +389,54 @@ def test_bigram_and_uneven_phoneloop(beer, tag):
         np.testing.assert_allclose(gotp.reshape(wantp.shape), wantp, rtol=3e-4, atol=3e-4)
 
 
+@pytest.mark.parametrize('tag', ['bg', 'un'])
+def test_engine_bigram_and_uneven_phoneloop(beer, tag):
+    """The batched engine on the phone loops that read the transition posteriors themselves (BigramPhoneLoop,
+    phoneloop.py:105-191; PhoneLoop with units of different lengths): both utterances in one launch per kernel, the
+    ends x starts block summed over the frames (VBEngine block counting) -- ELBOs, unit-weight posteriors, rewritten
+    transitions and Normal-Gamma posteriors after two iterations against the live-reference golden 'bigram_phoneloop'."""
+    g = load_golden('bigram_phoneloop')
+    cg = compiled(beer, g, tag + '_g0_')
+    D = g[tag + '_X1'].shape[1]
+    ns = normalset(beer, g, cg.n_states, D, prior=tag + '_prior_', post=tag + '_post0_')
+    start_pdf = {f'u{i}': int(s) for i, s in enumerate(g[tag + '_start_idxs'])}
+    end_pdf = {f'u{i}': int(s) for i, s in enumerate(g[tag + '_end_idxs'])}
+    # the unit weights stand alone (as in hmm_train): no model callback rewrites the graph behind the engine -- with a
+    # one-state unit (start == end) the rewrite of phoneloop.py:53-65 is not idempotent, it must run once per update
+    n = len(start_pdf)
+    starts, ends = list(start_pdf.values()), list(end_pdf.values())
+    if tag == 'bg':
+        cs = beer.CategoricalSet.create(torch.ones(n, n, device=DEV) / n, 1.)
+        units, wu = beer.BigramUnitWeights(cs, cg, starts, ends), cs.weights
+    else:
+        cat = beer.Categorical.create(torch.ones(n, device=DEV) / n, 1.)
+        units, wu = beer.CategoricalUnitWeights(cat, cg, starts, ends), cat.weights
+    units.rewrite_graph()                        # what the model's constructor does (phoneloop.py:49-50, 142-143)
+    np.testing.assert_allclose(wu.posterior.params.concentrations.cpu().numpy(), g[tag + '_u_dpost0'], rtol=1e-6)
+    np.testing.assert_allclose(cg.trans_log_probs.numpy(), g[tag + '_g_trans'], rtol=1e-5, atol=1e-6)
+
+    def flat(dist):          # (mean [K, D], scale [K], shape [K], rates [K, D]) as the engine holds them
+        K = cg.n_states
+        return tuple(getattr(dist.params, n).detach().to(DEV, torch.float32).reshape((K, D) if n in ('mean', 'rates') else (K,))
+                     .contiguous().clone() for n in ('mean', 'scale', 'shape', 'rates'))
+
+    em = beer.EmissionParams(flat(ns.means_precisions.prior), flat(ns.means_precisions.posterior))
+    X1, X2 = t32(g[tag + '_X1']), t32(g[tag + '_X2'])
+    N = len(X1) + len(X2)
+    eng = beer.VBEngine(em, cg.plan(n_pdfs=em.Kp), beer.Utterances(torch.cat([X1, X2]), [len(X1), len(X2)]),
+                        datasize=float(N), distributed=False, unit_weights=units)
+    elbos = [float(eng.step().item()) for _ in range(2)]
+    np.testing.assert_allclose(elbos, g[tag + '_elbos'], rtol=1e-5)
+    np.testing.assert_allclose(wu.posterior.params.concentrations.cpu().numpy(), g[tag + '_u_dpost2'], rtol=2e-4)
+    got, want = cg.trans_log_probs.numpy(), g[tag + '_trans2']
+    fin = np.isfinite(want)
+    assert np.array_equal(np.isfinite(got), fin)
+    np.testing.assert_allclose(got[fin], want[fin], rtol=2e-4, atol=2e-4)
+    for gotp, pname in zip(em.post, ('mean', 'scale', 'shape', 'rates')):
+        wantp = g[tag + '_post2_' + pname]
+        np.testing.assert_allclose(gotp.double().cpu().numpy().reshape(wantp.shape), wantp, rtol=3e-4, atol=3e-4)
+
+
 def test_mixture_cfg5_shape(beer):
     """BASELINE configs[4] shape: the E-step + M-step of a 512-component diagonal GMM on 40-d frames (the inner
     model of the GSM-GMM example), two VB iterations against the oracle (mixture.py:70-102)."""
