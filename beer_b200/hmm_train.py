@@ -63,6 +63,8 @@ def _categorical_from_reference(cat, device):
 
     if kind == 'Categorical':
         return models.Categorical(dirichlet_param(cat._modules['weights']))
+    if kind == 'CategoricalSet':          # the bigram weights of `beer hmm mkphoneloopbigram --weights-prior dirichlet2`
+        return models.CategoricalSet(dirichlet_param(cat._modules['weights']))
     if kind in ('SBCategorical', 'SBCategoricalHyperPrior'):
         sb = dirichlet_param(cat._modules['stickbreaking'])
         if kind == 'SBCategorical':
@@ -93,7 +95,7 @@ def _categorical_to_reference(model_cat, cat):
         old = param_ref._buffers['stats']
         param_ref._buffers['stats'] = param.stats.detach().to(device=old.device, dtype=old.dtype).clone()
 
-    if kind == 'Categorical':
+    if kind in ('Categorical', 'CategoricalSet'):
         V.set_concentrations(cat._modules['weights'], model_cat.weights.posterior.params.concentrations)
         put_stats(cat._modules['weights'], model_cat.weights)
         return
@@ -114,13 +116,11 @@ class ReferenceModel:
     (`emission`, `unit_weights`, `graph`) and `save()` that writes them back under the reference's class names."""
 
     def __init__(self, path, device):
-        from .engine import CategoricalUnitWeights, EmissionParams, WeightGroup
+        from .engine import BigramUnitWeights, CategoricalUnitWeights, EmissionParams, WeightGroup
         from .graph import CompiledGraph
         self.device = device
         self.tree = refpickle.load(path)
         self.view = v = refpickle.ModelView(self.tree)
-        if v.kind == 'BigramPhoneLoop':
-            raise NotImplementedError('BigramPhoneLoop trains through the model API (beer_b200.models.BigramPhoneLoop)')
         init, final, trans, pdf_map = v.graph_arrays()
         self.graph = CompiledGraph(init.detach().float().cpu().clone(), final.detach().float().cpu().clone(),
                                    trans.detach().float().cpu().clone(), pdf_map)
@@ -148,6 +148,12 @@ class ReferenceModel:
             self.categorical = _categorical_from_reference(v.categorical, device)
             self.unit_weights = CategoricalUnitWeights(self.categorical, self.graph, list(v.start_pdf.values()),
                                                        list(v.end_pdf.values()))
+        elif v.kind == 'BigramPhoneLoop':
+            # one Dirichlet per unit over the unit starts (phoneloop.py:105-191); the engine sums the ends x starts
+            # block of the transition posteriors for it
+            self.categorical = _categorical_from_reference(v.categorical, device)
+            self.unit_weights = BigramUnitWeights(self.categorical, self.graph, list(v.start_pdf.values()),
+                                                  list(v.end_pdf.values()))
 
     def save(self, path, acc=None, stats_scale=1.0):
         """Posteriors (and, as `update` leaves them, the stored statistics) back into the tree, then the pickle."""

@@ -180,7 +180,7 @@ class ModelView:
             raise TypeError(f'not an HMM-based model of the reference: {model!r}')
         self.graph = model._modules['graph']
         ms = model._modules['modelset']
-        if _cls(ms) == 'DynamicallyOrderedModelSet':
+        while _cls(ms) == 'DynamicallyOrderedModelSet':      # (mkphoneloopbigram wraps the unigram loop's wrapped set again)
             ms = ms._modules['original_modelset']
         sets = list(ms._modules['modelsets']._modules.values()) if _cls(ms) == 'JointModelSet' else [ms]
         self.groups = [self._group(s) for s in sets]

@@ -768,6 +768,43 @@ def gold_cli_files():
 
 
 
+def gold_cli_bigram():
+    """`beer hmm mkphoneloopbigram --weights-prior dirichlet2` (mkphoneloopbigram.py:35-55) of cli/ploop_0.mdl, then the
+    reference's own accumulate + update over the five utterances: cli/ploop_bigram_0.mdl, cli/ploop_bigram_1.mdl and
+    cli/expected_bigram.npz (the other files of cli/ are read, not rewritten)."""
+    import argparse
+    import io
+    import logging
+    import pickle
+    import types
+    sys.modules.setdefault('natsort', types.SimpleNamespace(natsorted=sorted))
+    from beer.cli.subcommands.hmm import accumulate, mkphoneloopbigram, update
+    out = os.path.join(OUT, 'cli')
+    log = logging.getLogger('gold_cli')
+    log.addHandler(logging.NullHandler())
+    torch.manual_seed(13)
+    b0, b1 = os.path.join(out, 'ploop_bigram_0.mdl'), os.path.join(out, 'ploop_bigram_1.mdl')
+    mkphoneloopbigram.main(argparse.Namespace(weights_prior='dirichlet2', phoneloop=os.path.join(out, 'ploop_0.mdl'),
+                                              out=b0), log)
+    acc_path = os.path.join(out, '_acc.tmp')
+    ids = sorted(np.load(os.path.join(out, 'feats.npz')).files)
+    stdin = sys.stdin
+    try:
+        sys.stdin = io.StringIO(''.join(u + '\n' for u in ids))
+        accumulate.main(argparse.Namespace(alis=None, acoustic_scale=1.0, model=b0,
+                                           dataset=os.path.join(out, 'dataset.pkl'), out=acc_path), log)
+        sys.stdin = io.StringIO(acc_path + '\n')
+        update.main(argparse.Namespace(learning_rate=1.0, optim_state=None, model=b0, out_model=b1), log)
+    finally:
+        sys.stdin = stdin
+    with open(acc_path, 'rb') as f:
+        elbo, count = pickle.load(f)
+    os.remove(acc_path)
+    expected = {'bigram_elbo_1': np.float64(float(elbo) / (count * elbo._datasize))}
+    np.savez(os.path.join(out, 'expected_bigram.npz'), **expected)
+    print(expected, os.path.getsize(b0), os.path.getsize(b1))
+
+
 def gold_cli_files_tc():
     """The same file-level fixture at a shape the tensor-core kernels take (40-d features, 12 units x 4 states, 8
     Gaussians per state = 384 Gaussians): the model and the data set are pickled by the live reference as its CLI does,
@@ -839,6 +876,9 @@ if __name__ == '__main__':
     if len(sys.argv) > 2 and sys.argv[2] == 'cli':
         gold_cli_files()
         sys.exit(0)
+    if len(sys.argv) > 2 and sys.argv[2] == 'cli_bigram':
+        gold_cli_bigram()
+        sys.exit(0)
     if len(sys.argv) > 2 and sys.argv[2] == 'cli_tc':
         gold_cli_files_tc()
         sys.exit(0)
@@ -865,4 +905,5 @@ if __name__ == '__main__':
     gold_graph_compile()
     gold_fbank()
     gold_cli_files()
+    gold_cli_bigram()
     gold_cli_files_tc()

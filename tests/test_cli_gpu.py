@@ -124,3 +124,16 @@ def test_aligned_training_on_graphs_that_are_not_chains(tmp_path, capsys):
     logged = [float(line.split('=')[1]) for line in capsys.readouterr().out.splitlines() if 'ELBO=' in line]
     np.testing.assert_allclose(logged, [want['skipali_elbo_1']], atol=2e-3)
     _compare(out, os.path.join(CLI, 'ploop_skipali_1.mdl'), rtol=5e-4)
+
+
+def test_bigram_phone_loop(tmp_path, capsys):
+    """A BigramPhoneLoop pickled by `beer hmm mkphoneloopbigram --weights-prior dirichlet2` (mkphoneloopbigram.py:35-55):
+    one epoch of the batched engine (ends x starts block of the transition posteriors, phoneloop.py:175-186) against the
+    reference's own accumulate + update of the same file -- logged ELBO and every tensor of the pickle."""
+    from beer_b200 import hmm_train
+    out = str(tmp_path / 'ploop_bigram_1.mdl')
+    assert hmm_train.main([os.path.join(CLI, 'ploop_bigram_0.mdl'), os.path.join(CLI, 'dataset.pkl'), out]) == 0
+    want = np.load(os.path.join(CLI, 'expected_bigram.npz'))
+    logged = [float(line.split('=')[1]) for line in capsys.readouterr().out.splitlines() if 'ELBO=' in line]
+    np.testing.assert_allclose(logged, [want['bigram_elbo_1']], atol=2e-3)
+    _compare(out, os.path.join(CLI, 'ploop_bigram_1.mdl'), rtol=5e-4)
