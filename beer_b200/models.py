@@ -818,7 +818,7 @@ class HMM(DiscreteLatentModel):
                     pdf, r['state_post'], off, graph.init_log_probs.detach().to(device=dev, dtype=f32).contiguous(),
                     graph.trans_log_probs.detach().to(device=dev, dtype=f32).contiguous(),
                     pdf_map=graph.pdf_map_device(dev), scale=scale, rows=rows, cols=cols)
-                self.cache['first_state_post'] = r['state_post'][off[:-1]]      # gamma_0 of every utterance
+                self.cache['first_state_post'] = r['state_post'][off[:-1][off[1:] > off[:-1]]]   # gamma_0 of every (non-empty) utterance
         self.cache.update(X=X, pdf_post=post, pdf_llh=pdf, comp_llh=comp, emission=em, scale=scale,
                           utts=utts, utt_exp_llh=utt_ell)
         Xg = frames_with_grad(stats)

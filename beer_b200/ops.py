@@ -370,6 +370,10 @@ def hmm_transition_posteriors(pdf_llh, state_post, utt_off, log_init, log_trans,
     `rows` / `cols` (int32 state ids) keep a sub-block, e.g. unit ends x unit starts."""
     lib = require_cuda()
     N, K = state_post.shape
+    # the kernel places utterance u's rows at t0 - u: every utterance must hold a frame, empty ones are dropped here
+    nonempty = utt_off[1:] > utt_off[:-1]
+    if not bool(nonempty.all()):
+        utt_off = torch.cat([utt_off[:1], utt_off[1:][nonempty]]).contiguous()
     n_utts = utt_off.numel() - 1
     R = K if rows is None else rows.numel()
     Cn = K if cols is None else cols.numel()

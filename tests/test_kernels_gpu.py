@@ -442,3 +442,27 @@ def test_emission_llh_bwd(N, M, D, C, scale):
     got1 = ops.emission_llh_bwd(X, ets, post, comp_llh=comp, pdf_llh=pdf, pdf_of=pdf_of, scale=scale)
     want1 = w @ e[:, :D] - X.double() * (w @ e[:, D:2 * D])
     assert float((got1.double() - want1).abs().max()) <= 5e-6 * float(want1.abs().max())
+
+
+def test_transition_posteriors_skip_empty_utterances():
+    """A zero-length utterance inside the batch holds no transition: the block of the transition posteriors
+    (graph.py:308-323 per utterance) is the one of the batch without it."""
+    from beer_b200 import ops, synthetic
+    dev = torch.device('cuda', 0)
+    P, S, T1, T2 = 3, 3, 17, 9
+    K = P * S
+    graph, starts, ends = synthetic.phone_loop_graph(P, S)
+    plan = graph.plan(n_pdfs=K)
+    llh = torch.randn(T1 + T2, K, generator=torch.Generator().manual_seed(5)).to(dev)
+    fref = torch.zeros(T1 + T2, device=dev)
+    init = graph.init_log_probs.float().to(dev).contiguous()
+    trans = graph.trans_log_probs.float().to(dev).contiguous()
+    rows = torch.as_tensor(ends, dtype=torch.int32, device=dev)
+    cols = torch.as_tensor(starts, dtype=torch.int32, device=dev)
+    out = []
+    for offs in ([0, T1, T1 + T2], [0, 0, T1, T1, T1 + T2, T1 + T2]):
+        off = torch.tensor(offs, dtype=torch.int64, device=dev)
+        r = ops.hmm_forward_backward(plan, llh, fref, off, want_state_post=True)
+        out.append(ops.hmm_transition_posteriors(llh, r['state_post'], off, init, trans, rows=rows, cols=cols))
+    assert out[0].shape == (T1 + T2 - 2, P, P)
+    assert torch.equal(out[0], out[1])
