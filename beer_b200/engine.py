@@ -352,8 +352,6 @@ class VBEngine:
         # reduce (phoneloop.py:83-101, 175-186)
         self._xi_block = unit_weights is not None and not aligned and (P == 0 or getattr(unit_weights, 'needs_block', False))
         if self._xi_block:
-            if self.viterbi:
-                raise ValueError('Viterbi training with learned unit weights needs an aligned left-to-right phone loop')
             self._nE, self._nS = len(unit_weights.end_idxs), len(unit_weights.start_idxs)
             P = self._nE * self._nS + self._nS
         self.flat = torch.zeros(M * self.Q + P + 4, device=self.dev, dtype=f64)
@@ -642,11 +640,27 @@ class VBEngine:
         first frame of every utterance (hmm.py:49-54, phoneloop.py:83-101).  Index arithmetic on [N] integers."""
         if self.unit_counts is None:
             return
-        su = self.plan.n_states // self.unit_counts.numel()
         p = path.long()
         n = p.numel()
         first = torch.zeros(n + 1, dtype=torch.bool, device=self.dev)
         first[rel[:-1]] = True            # an empty utterance marks the next one's first frame (or the slot past the end)
+        if self._xi_block:
+            # block counting: (unit whose end state frame t - 1 is in, unit whose start state frame t is in) pairs
+            nE, nS = self._nE, self._nS
+            if not hasattr(self, '_end_of'):
+                K = self.plan.n_states
+                self._end_of = torch.full((K,), -1, dtype=i64, device=self.dev)
+                self._end_of[torch.as_tensor(self.units.end_idxs, device=self.dev)] = torch.arange(nE, device=self.dev)
+                self._start_of = torch.full((K,), -1, dtype=i64, device=self.dev)
+                self._start_of[torch.as_tensor(self.units.start_idxs, device=self.dev)] = torch.arange(nS, device=self.dev)
+            s_unit = self._start_of[p]
+            e_unit = torch.full_like(s_unit, -1)
+            e_unit[1:] = self._end_of[p[:-1]]
+            hit = (s_unit >= 0) & (e_unit >= 0) & ~first[:n]
+            self.unit_counts[:nE * nS].index_add_(0, (e_unit * nS + s_unit).clamp(min=0), hit.to(f64))
+            self.unit_counts[nE * nS:].index_add_(0, s_unit.clamp(min=0), ((s_unit >= 0) & first[:n]).to(f64))
+            return
+        su = self.plan.n_states // self.unit_counts.numel()
         is_start = (p % su) == 0
         after_end = torch.zeros(n, dtype=torch.bool, device=self.dev)
         after_end[1:] = (p[:-1] % su) == su - 1

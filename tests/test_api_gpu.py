@@ -389,12 +389,14 @@ def test_bigram_and_uneven_phoneloop(beer, tag):
         np.testing.assert_allclose(gotp.reshape(wantp.shape), wantp, rtol=3e-4, atol=3e-4)
 
 
-@pytest.mark.parametrize('tag', ['bg', 'un'])
-def test_engine_bigram_and_uneven_phoneloop(beer, tag):
+@pytest.mark.parametrize('tag,viterbi', [('bg', False), ('un', False), ('bg', True), ('un', True)])
+def test_engine_bigram_and_uneven_phoneloop(beer, tag, viterbi):
     """The batched engine on the phone loops that read the transition posteriors themselves (BigramPhoneLoop,
     phoneloop.py:105-191; PhoneLoop with units of different lengths): both utterances in one launch per kernel, the
     ends x starts block summed over the frames (VBEngine block counting) -- ELBOs, unit-weight posteriors, rewritten
-    transitions and Normal-Gamma posteriors after two iterations against the live-reference golden 'bigram_phoneloop'."""
+    transitions and Normal-Gamma posteriors after two iterations against the live-reference golden 'bigram_phoneloop'.
+    viterbi: the block of the one-hot transition posteriors of the best paths (hmm.py:49-54), against the model API
+    driven utterance by utterance (BigramPhoneLoop / PhoneLoop of beer_b200.models, themselves pinned by the golden)."""
     g = load_golden('bigram_phoneloop')
     cg = compiled(beer, g, tag + '_g0_')
     D = g[tag + '_X1'].shape[1]
@@ -424,16 +426,35 @@ def test_engine_bigram_and_uneven_phoneloop(beer, tag):
     X1, X2 = t32(g[tag + '_X1']), t32(g[tag + '_X2'])
     N = len(X1) + len(X2)
     eng = beer.VBEngine(em, cg.plan(n_pdfs=em.Kp), beer.Utterances(torch.cat([X1, X2]), [len(X1), len(X2)]),
-                        datasize=float(N), distributed=False, unit_weights=units)
+                        datasize=float(N), distributed=False, unit_weights=units, viterbi=viterbi)
     elbos = [float(eng.step().item()) for _ in range(2)]
-    np.testing.assert_allclose(elbos, g[tag + '_elbos'], rtol=1e-5)
-    np.testing.assert_allclose(wu.posterior.params.concentrations.cpu().numpy(), g[tag + '_u_dpost2'], rtol=2e-4)
-    got, want = cg.trans_log_probs.numpy(), g[tag + '_trans2']
+    if viterbi:
+        cg_m = compiled(beer, g, tag + '_g0_')
+        ns_m = normalset(beer, g, cg_m.n_states, D, prior=tag + '_prior_', post=tag + '_post0_')
+        pl = (beer.BigramPhoneLoop if tag == 'bg' else beer.PhoneLoop).create(cg_m, start_pdf, end_pdf, ns_m, prior_strength=1.)
+        optim = beer.VBConjugateOptimizer(pl.conjugate_bayesian_parameters(keepgroups=True), lrate=1.)
+        want_elbos = []
+        for _ in range(2):
+            optim.init_step()
+            elbo = beer.evidence_lower_bound(datasize=N)
+            for X in (X1, X2):
+                elbo += beer.evidence_lower_bound(pl, X, datasize=N, viterbi=True)
+            elbo.backward()
+            want_elbos.append(float(elbo))
+            optim.step()
+        want_conc = (pl.categoricalset if tag == 'bg' else pl.categorical).weights.posterior.params.concentrations.cpu().numpy()
+        want = cg_m.trans_log_probs.numpy()
+        want_post = get_ng(ns_m.means_precisions.posterior)
+    else:
+        want_elbos, want_conc, want = g[tag + '_elbos'], g[tag + '_u_dpost2'], g[tag + '_trans2']
+        want_post = [g[tag + '_post2_' + pname] for pname in ('mean', 'scale', 'shape', 'rates')]
+    np.testing.assert_allclose(elbos, want_elbos, rtol=1e-5)
+    np.testing.assert_allclose(wu.posterior.params.concentrations.cpu().numpy(), want_conc, rtol=2e-4)
+    got = cg.trans_log_probs.numpy()
     fin = np.isfinite(want)
     assert np.array_equal(np.isfinite(got), fin)
     np.testing.assert_allclose(got[fin], want[fin], rtol=2e-4, atol=2e-4)
-    for gotp, pname in zip(em.post, ('mean', 'scale', 'shape', 'rates')):
-        wantp = g[tag + '_post2_' + pname]
+    for gotp, wantp in zip(em.post, want_post):
         np.testing.assert_allclose(gotp.double().cpu().numpy().reshape(wantp.shape), wantp, rtol=3e-4, atol=3e-4)
 
 
