@@ -417,3 +417,47 @@ def test_sparse_and_dense_statistics_give_the_same_iterations():
     for p, q in zip(engines[0].em.post, engines[1].em.post):
         assert (p - q).abs().max().item() <= 1e-5 * q.abs().max().item()
     assert fractions[-1] < 0.5 * fractions[0], fractions
+
+
+@pytest.mark.parametrize('viterbi', [False, True])
+def test_bigram_loop_on_the_fp16_mixture_kernels(viterbi, monkeypatch):
+    """A bigram phone loop over mixtures at a shape the fp16-split kernels take (40-d, 8 Gaussians per pdf): the emission
+    kernel then hands log2 llhs to the generic scan and to the transition-posterior kernel (scale x ln 2).  Against the
+    same engine on the fp32 SIMT kernels (BEER_B200_NO_MIX16): ELBOs, bigram posteriors and rewritten arcs."""
+    import beer_b200 as beer
+    from beer_b200 import synthetic
+    dev = torch.device('cuda', 0)
+    P, S, D, C = 8, 4, 40, 8
+    K, M = P * S, P * S * C
+    lens = [150, 64, 97]
+    g0, starts, ends = synthetic.phone_loop_graph(P, S)
+    means = 2.0 * torch.randn(K, D, generator=torch.Generator().manual_seed(0))
+    full = synthetic.sample_utterances(g0, means, len(lens), max(lens), seed=1, device=dev).reshape(len(lens), max(lens), D)
+    X = torch.cat([full[i, :n] for i, n in enumerate(lens)])
+    out = []
+    for mix16 in (True, False):
+        if mix16:
+            monkeypatch.delenv('BEER_B200_NO_MIX16', raising=False)
+        else:
+            monkeypatch.setenv('BEER_B200_NO_MIX16', '1')
+        graph, _, _ = synthetic.phone_loop_graph(P, S)
+        cs = beer.CategoricalSet.create(torch.ones(P, P, device=dev) / P, 1.)
+        units = beer.BigramUnitWeights(cs, graph, starts, ends)
+        units.rewrite_graph()
+        prior, post = synthetic.initial_normal_gamma(M, D, seed=2, device=dev)
+        conc = torch.full((K, C), 1.0 / C, device=dev)
+        em = beer.EmissionParams(prior, post, comp_off=np.arange(K + 1) * C,
+                                 weight_groups=(beer.WeightGroup(0, K, C, conc.clone(), conc.clone()),))
+        eng = beer.VBEngine(em, graph.plan(n_pdfs=K), beer.Utterances(X, lens), datasize=float(sum(lens)),
+                            distributed=False, unit_weights=units, viterbi=viterbi)
+        assert (eng.mix16 is not None) == mix16
+        elbos = [float(eng.step().item()) for _ in range(3)]
+        out.append((elbos, cs.weights.posterior.params.concentrations.double().cpu().numpy(),
+                    graph.trans_log_probs.numpy().copy()))
+    (ea, ca, ta), (eb, cb, tb) = out
+    np.testing.assert_allclose(ea, eb, rtol=2e-6)
+    np.testing.assert_allclose(ca, cb, rtol=1e-4, atol=1e-4)
+    fin = np.isfinite(tb)
+    assert np.array_equal(np.isfinite(ta), fin)
+    np.testing.assert_allclose(ta[fin], tb[fin], rtol=1e-4, atol=1e-4)
+    assert np.abs(cb - 1.0 / P).max() > 0.5          # the bigram counts did arrive
