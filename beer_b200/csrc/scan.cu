@@ -10,7 +10,6 @@
 // Reference semantics: beer/graph.py:270-344, beer/models/hmm.py:79-100,
 // beer/models/modelset.py:140-154.
 #include <algorithm>
-#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -239,7 +238,6 @@ struct FbArgs {
     int64_t blk_ld;
     int blk_ppb;
     float blk_thr;
-    unsigned int* work;   // hmm_fb_lrb_kernel: the counter its blocks draw sweeps from (zeroed before the launch)
 };
 
 // A lane's part of the activity map: the blocks g0 .. g1 of its pdfs (identity pdf map: state = pdf), and the tile it
@@ -1397,27 +1395,11 @@ __global__ void __launch_bounds__(W * 32, 4) hmm_fb_lrb_kernel(FbArgs a) {
         exchange2(m, s, e, kNegInf, 0.f, M, Ssum, E, M2, S2, false);
     };
 
-    // The unit of work is one SWEEP of one utterance, drawn from a counter: the forward sweeps of all utterances first,
-    // then the backward sweeps.  The backward sweep takes nothing from the forward one but the alpha rows in the
-    // workspace, so it can run in any block; with whole utterances per block the busiest SM did ceil(utterances / SMs)
-    // of them (BASELINE configs[2]: 1250 utterances on 148 SMs = 8.45 -> 9, the kernel is issue-bound), with sweeps it
-    // does ceil(2 x 8.45) = 17 halves.  A forward sweep never waits; a backward sweep waits for "forward done" of its
-    // utterance, published through utt_exp_llh[u] (a NaN payload no result can equal) -- that sweep was drawn earlier,
-    // by a block that is running, so the wait ends.
-    constexpr unsigned long long kForwardDone = 0x7ff8bee5b200f0adull;
-    __shared__ int s_work;
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_work = (int)atomicAdd(a.work, 1u);
-        __syncthreads();
-        const int work = s_work;
-        if (work >= 2 * a.n_utts) break;
-        const bool backward = work >= a.n_utts;
-        const int u = backward ? work - a.n_utts : work;
+    for (int u = blockIdx.x; u < a.n_utts; u += gridDim.x) {
         const int64_t t0 = a.utt_off[u];
         const int T = (int)(a.utt_off[u + 1] - t0);
         if (T <= 0) {
-            if (threadIdx.x == 0 && !backward) {
+            if (threadIdx.x == 0) {
                 a.utt_exp_llh[u] = 0.0;
                 if (a.utt_logz) a.utt_logz[u] = 0.0;
             }
@@ -1425,7 +1407,6 @@ __global__ void __launch_bounds__(W * 32, 4) hmm_fb_lrb_kernel(FbArgs a) {
         }
         const float* pl_u = a.pl + (size_t)t0 * a.ld;
         float* la_u = a.la_ws + (size_t)t0 * a.Kw;
-        if (!backward) {
         double logz2 = 0.0;
 
         // ------------------------------ forward ------------------------------
@@ -1489,20 +1470,10 @@ __global__ void __launch_bounds__(W * 32, 4) hmm_fb_lrb_kernel(FbArgs a) {
             if (threadIdx.x == 0)
                 a.utt_logz[u] = (logz2 + (double)M + (double)lg2(Ssum)) * (double)kLn2 + (double)a.scale * rs;
         }
-        // every thread's alpha rows are out before the utterance is marked (release)
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) atomicExch(reinterpret_cast<unsigned long long*>(a.utt_exp_llh + u), kForwardDone);
-        continue;
-        }
 
         // ------------------------------ backward -----------------------------
-        if (threadIdx.x == 0) {
-            const volatile unsigned long long* flag = reinterpret_cast<const volatile unsigned long long*>(a.utt_exp_llh + u);
-            while (*flag != kForwardDone) __nanosleep(200);
-            __threadfence();     // (acquire: the alpha rows are read after the mark)
-        }
-        __syncthreads();
+        __threadfence_block();
+        __syncthreads();         // every warp's la stores are visible to every warp's async copies
         for (int r = 0; r < PF; ++r) {
             const int t = T - 1 - r;
             if (t >= 0) {
@@ -1627,16 +1598,13 @@ __global__ void __launch_bounds__(W * 32, 4) hmm_fb_lrb_kernel(FbArgs a) {
             rs = warp_sum(rs);
             if (lane == 0) a.utt_exp_llh[u] += (double)a.scale * rs;
         }
+        __syncthreads();
     }
 }
 
-// counters the blocks of hmm_fb_lrb_kernel draw their sweeps from: one per launch in flight (taken in turn)
-__device__ unsigned int g_lrb_work[64];
-
 template <int SU, int W, bool LP = false>
-static int launch_fb_lrb(const FbArgs& a_in, int n_utts, cudaStream_t st) {
-    if (!LP && a_in.pdf_lpost != nullptr) return launch_fb_lrb<SU, W, true>(a_in, n_utts, st);
-    FbArgs a = a_in;
+static int launch_fb_lrb(const FbArgs& a, int n_utts, cudaStream_t st) {
+    if (!LP && a.pdf_lpost != nullptr) return launch_fb_lrb<SU, W, true>(a, n_utts, st);
     constexpr int PF = 4;
     size_t smem = sizeof(float) * ((size_t)W * (2 * PF * 32 * SU) + 2 * W * 8 + W * 32);
     static bool attr_set = false;
@@ -1645,13 +1613,9 @@ static int launch_fb_lrb(const FbArgs& a_in, int n_utts, cudaStream_t st) {
                                            (int)smem));
         attr_set = true;
     }
-    // as many blocks as are resident (four per SM): every block draws sweeps until none is left
-    int blocks = 2 * n_utts < kNumSMs * 4 ? 2 * n_utts : kNumSMs * 4;
-    static std::atomic<unsigned> turn{0};
-    unsigned int* pool = nullptr;
-    BEER_CUDA_TRY(cudaGetSymbolAddress((void**)&pool, g_lrb_work));
-    a.work = pool + (turn.fetch_add(1) & 63);
-    BEER_CUDA_TRY(cudaMemsetAsync(a.work, 0, sizeof(unsigned int), st));
+    int blocks = n_utts < kNumSMs * 8 ? n_utts : kNumSMs * 8;
+    // (fewer blocks than 8 per SM -- 3 or 2 resident utterances per SM in equal rounds instead of 4 + 4 + a sparse third
+    // round at 1250 utterances -- measured slower: 5.51 / 6.15 ms against 5.10 - 5.25)
     hmm_fb_lrb_kernel<SU, W, LP><<<blocks, W * 32, smem, st>>>(a);
     BEER_LAUNCH_CHECK();
     return BEER_OK;
@@ -3287,7 +3251,6 @@ int beer_hmm_forward_backward_blocks(const beer_graph_plan* plan, const float* p
     // a weight below 2^-25 of the statistics kernel's fp16 range (it carries w 2^wexp, wexp as in beer_mix16_accumulate) is
     // zero in both halves of its operand; two more bits of margin for the roundings on the way
     a.blk_thr = -(25.f + (float)beer_mix16_weight_exponent(scale) + 2.f);
-    a.work = nullptr;
     if (pdf_lpost != nullptr && (ld_lpost < plan->Kp || ld_lpost % 4 != 0 || ((uintptr_t)pdf_lpost & 15) != 0)) return BEER_ERR_ARG;
     if (unit_counts != nullptr && beer_hmm_unit_count_size(plan) <= 0) return BEER_ERR_UNSUPPORTED;
     const bool post_ok = (pdf_post == nullptr || (ld_post % 4 == 0 && ((uintptr_t)pdf_post & 15) == 0)) &&
