@@ -4,6 +4,7 @@ Run in the build container only (the reference checkout does not exist on the
 GPU box):
 
     python tests/golden/make_goldens.py [/root/reference]
+    python tests/golden/make_goldens.py /root/reference cli | cli_bigram | cli_tc | vae | mixture_input_grad   (one group only)
 
 Everything is computed by the unmodified reference (beer-asr/beer @ d53d2a1)
 in float64; inputs, parameters and outputs are dumped to ``*.npz`` so that the
