@@ -113,3 +113,34 @@ def test_dataset_pickle_written_for_the_reference(tmp_path):
         assert got.__dict__[k].dtype == want.__dict__[k].dtype
         np.testing.assert_allclose(got.__dict__[k].numpy(), want.__dict__[k].numpy(), rtol=1e-5, atol=1e-6)
     assert len(load_dataset(out)) == 5
+
+
+def test_bigram_phone_loop_pickle(tmp_path):
+    """A BigramPhoneLoop written by `beer hmm mkphoneloopbigram --weights-prior dirichlet2` (mkphoneloopbigram.py:35-55):
+    the unigram loop's already wrapped emission set is wrapped once more, the unit weights are a CategoricalSet of one
+    Dirichlet per unit; opened for the engine and saved untrained, every tensor comes back as it was."""
+    from beer_b200 import refpickle
+    from beer_b200.engine import BigramUnitWeights
+    from beer_b200.hmm_train import ReferenceModel
+    src = os.path.join(CLI, 'ploop_bigram_0.mdl')
+    tree = refpickle.load(src)
+    assert tree.ref_class() == 'beer.models.phoneloop.BigramPhoneLoop'
+    v = refpickle.ModelView(tree)
+    assert v.kind == 'BigramPhoneLoop' and [(g['n_pdfs'], g['n_comp']) for g in v.groups] == [(6, 4), (6, 2)]
+    assert refpickle.ModelView.concentrations(v.categorical._modules['weights'], 'posterior').shape == (4, 4)
+    m = ReferenceModel(src, 'cpu')
+    assert isinstance(m.unit_weights, BigramUnitWeights)
+    assert m.unit_weights.start_idxs == [0, 3, 6, 9] and m.unit_weights.end_idxs == [2, 5, 8, 11]
+    assert tuple(m.categorical.weights.posterior.params.concentrations.shape) == (4, 4)
+    out = str(tmp_path / 'same.mdl')
+    m.save(out)
+    a, b = _tensors(refpickle.load(src)), _tensors(refpickle.load(out))
+    # (an untrained model's posterior shares tensors with its prior; the walker lists a shared tensor once, the saved
+    # posterior holds its own copies: more paths on that side, the same values)
+    assert set(a) <= set(b)
+    for k in a:
+        assert a[k].dtype == b[k].dtype and a[k].shape == b[k].shape, k
+        if not k.endswith('/stats'):
+            assert torch.equal(a[k], b[k]), k
+    for k in set(b) - set(a):
+        assert '/posterior/' in k and torch.equal(b[k], b[k.replace('/posterior/', '/prior/')]), k
