@@ -606,12 +606,11 @@ class VBEngine:
         `max_floats` elements and summed in float64."""
         u = self.units
         nE, nS = self._nE, self._nS
+        g = u.graph
         if not hasattr(self, '_xi_rows'):
-            g = u.graph
             self._xi_rows = torch.as_tensor(u.end_idxs, dtype=i32, device=self.dev)
             self._xi_cols = torch.as_tensor(u.start_idxs, dtype=i32, device=self.dev)
             self._xi_map = torch.as_tensor(np.asarray(g.pdf_id_mapping), dtype=i32, device=self.dev)
-        g = u.graph
         init = g.init_log_probs.detach().to(device=self.dev, dtype=f32).contiguous()
         trans = g.trans_log_probs.detach().to(device=self.dev, dtype=f32).contiguous()     # rewritten every iteration
         block = self.unit_counts[:nE * nS].view(nE, nS)
